@@ -1,0 +1,495 @@
+"""ORACLE — test infrastructure, not product code.
+
+CPU restatement (plain PyTorch, fp32 by default, fp64 on request) of the guided
+`p_sample_loop` hot path of jacarvalho/mpd-public. Only `tests/`, `__graft_entry__.smoke()` and
+`bench.py`'s CPU-baseline / `--impl reference` legs may import this file; the product
+(`mpd_public_b200/`) never does and fails loudly when its CUDA library is missing.
+
+Pinning status
+--------------
+* **Reference-pinned** (checked against outputs of the reference's own code, generated in the build
+  container by `tests/golden/make_golden.py` under the name-only shim of `oracle/ref_shim.py`):
+  `unet_forward` (reference temporal_unet.py:118-171, layers.py:229-355), `make_schedule`
+  (diffusion_model_base.py:66-104, helpers.py:40-46), `p_mean_variance` (:143-155),
+  `ddpm_step` (sample_functions.py:18-62), `guide_gradient_steps` (:65-83), `p_sample_loop`
+  (diffusion_model_base.py:158-182), `guide_manager_grad` (guides.py:173-236: per-cost autograd,
+  clip-by-norm with +1e-6, endpoint zeroing, weighting, negation), `limits_unnormalize`
+  (normalization.py:156-167, including the batch-global clip branch).
+* **Parity unpinned** (sources absent from /root/reference: `mp_baselines@8a50c3c`,
+  `torch_robotics@d704c78`, `storm@54543cf`, see .SUBMODULES.json): `interpolate_points`,
+  `panda_sphere_centers`, `GridSDF`, `collision_cost_*`, `gp_cost`. These follow the frozen spec of
+  SURVEY.md Appendix C/E; each choice is a named switch below. The reference holds no tests or
+  golden vectors for any of this path.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+# ------------------------------------------------------------------------------------------------
+# Switches for the unpinned arithmetic
+# ------------------------------------------------------------------------------------------------
+SWITCH_C3_COLLISION_ON_INTERPOLATED = True   # C3: collision costs see the interpolated trajectory
+SWITCH_C5_NEAREST_CELL = True                # C5: nearest-cell lookup, gradient from the stored texel
+
+
+# ------------------------------------------------------------------------------------------------
+# TemporalUnet  (reference temporal_unet.py:118-171)
+# ------------------------------------------------------------------------------------------------
+def group_norm_n_groups(n_channels, target_n_groups=8):
+    """reference layers.py:389-395"""
+    if n_channels < target_n_groups:
+        return 1
+    for n_groups in range(target_n_groups, target_n_groups + 10):
+        if n_channels % n_groups == 0:
+            return n_groups
+    return 1
+
+
+def sinusoidal_pos_emb(t, dim=32):
+    """reference layers.py:243-255 (always evaluated in fp32 there; here in t's float dtype)."""
+    half = dim // 2
+    e = math.log(10000) / (half - 1)
+    freq = torch.exp(torch.arange(half, device=t.device) * -e)
+    emb = t[:, None] * freq[None, :]
+    return torch.cat((emb.sin(), emb.cos()), dim=-1)
+
+
+def time_mlp(sd, t, dtype):
+    """reference layers.py:229-240: Sinusoidal(32) -> Linear(32,128) -> Mish -> Linear(128,32)."""
+    emb = sinusoidal_pos_emb(t).to(dtype)
+    h = F.mish(F.linear(emb, sd["time_mlp.encoder.1.weight"], sd["time_mlp.encoder.1.bias"]))
+    return F.linear(h, sd["time_mlp.encoder.3.weight"], sd["time_mlp.encoder.3.bias"])
+
+
+def conv1d_block(sd, p, x):
+    """reference layers.py:276-293: Conv1d(k, pad k//2) -> GroupNorm -> Mish."""
+    w = sd[p + ".block.0.weight"]
+    y = F.conv1d(x, w, sd[p + ".block.0.bias"], padding=w.shape[-1] // 2)
+    y = F.group_norm(y, group_norm_n_groups(w.shape[0]), sd[p + ".block.2.weight"], sd[p + ".block.2.bias"], eps=1e-5)
+    return F.mish(y)
+
+
+def residual_temporal_block(sd, p, x, c_emb):
+    """reference layers.py:343-355."""
+    cond = F.linear(F.mish(c_emb), sd[p + ".cond_mlp.1.weight"], sd[p + ".cond_mlp.1.bias"])
+    h = conv1d_block(sd, p + ".blocks.0", x) + cond[:, :, None]
+    h = conv1d_block(sd, p + ".blocks.1", h)
+    if (p + ".residual_conv.weight") in sd:
+        res = F.conv1d(x, sd[p + ".residual_conv.weight"], sd[p + ".residual_conv.bias"])
+    else:
+        res = x
+    return h + res
+
+
+def unet_forward(sd, x, t, n_levels=None):
+    """ε = TemporalUnet(x [B,H,D], t [B]) with conditioning_type=None, self_attention=False.
+
+    `sd`: TemporalUnet state-dict (no 'model.' prefix) of torch tensors.
+    """
+    dtype = x.dtype
+    if n_levels is None:
+        n_levels = 1 + max(int(k.split(".")[1]) for k in sd if k.startswith("downs."))
+    c_emb = time_mlp(sd, t, dtype)
+    x = x.transpose(1, 2)  # b h c -> b c h  (temporal_unet.py:138)
+    skips = []
+    for i in range(n_levels):
+        x = residual_temporal_block(sd, f"downs.{i}.0", x, c_emb)
+        x = residual_temporal_block(sd, f"downs.{i}.1", x, c_emb)
+        skips.append(x)
+        if i < n_levels - 1:
+            x = F.conv1d(x, sd[f"downs.{i}.4.conv.weight"], sd[f"downs.{i}.4.conv.bias"], stride=2, padding=1)
+    x = residual_temporal_block(sd, "mid_block1", x, c_emb)
+    x = residual_temporal_block(sd, "mid_block2", x, c_emb)
+    for i in range(n_levels - 1):
+        x = torch.cat((x, skips.pop()), dim=1)
+        x = residual_temporal_block(sd, f"ups.{i}.0", x, c_emb)
+        x = residual_temporal_block(sd, f"ups.{i}.1", x, c_emb)
+        x = F.conv_transpose1d(x, sd[f"ups.{i}.4.conv.weight"], sd[f"ups.{i}.4.conv.bias"], stride=2, padding=1)
+    x = conv1d_block(sd, "final_conv.0", x)
+    x = F.conv1d(x, sd["final_conv.1.weight"], sd["final_conv.1.bias"])
+    return x.transpose(1, 2)
+
+
+# ------------------------------------------------------------------------------------------------
+# Schedule (reference diffusion_model_base.py:66-104, helpers.py:26-46)
+# ------------------------------------------------------------------------------------------------
+def make_schedule(n_diffusion_steps, variance_schedule="exponential"):
+    T = n_diffusion_steps
+    if variance_schedule == "exponential":
+        x = torch.linspace(0, T, T)
+        beta_start, beta_end = torch.tensor(1e-4), torch.tensor(1.0)
+        a = 1 / T * torch.log(beta_end / beta_start)
+        betas = beta_start * torch.exp(a * x)
+    elif variance_schedule == "cosine":
+        steps = T + 1
+        xs = np.linspace(0, steps, steps)
+        ac = np.cos(((xs / steps) + 0.008) / (1 + 0.008) * np.pi * 0.5) ** 2
+        ac = ac / ac[0]
+        betas = torch.tensor(np.clip(1 - (ac[1:] / ac[:-1]), a_min=0, a_max=0.999), dtype=torch.float32)
+    else:
+        raise NotImplementedError
+    alphas = 1.0 - betas
+    ac = torch.cumprod(alphas, dim=0)
+    ac_prev = torch.cat([torch.ones(1), ac[:-1]])
+    pv = betas * (1.0 - ac_prev) / (1.0 - ac)
+    return {
+        "betas": betas,
+        "alphas_cumprod": ac,
+        "alphas_cumprod_prev": ac_prev,
+        "sqrt_alphas_cumprod": torch.sqrt(ac),
+        "sqrt_one_minus_alphas_cumprod": torch.sqrt(1.0 - ac),
+        "log_one_minus_alphas_cumprod": torch.log(1.0 - ac),
+        "sqrt_recip_alphas_cumprod": torch.sqrt(1.0 / ac),
+        "sqrt_recipm1_alphas_cumprod": torch.sqrt(1.0 / ac - 1),
+        "posterior_variance": pv,
+        "posterior_log_variance_clipped": torch.log(torch.clamp(pv, min=1e-20)),
+        "posterior_mean_coef1": betas * np.sqrt(ac_prev) / (1.0 - ac),
+        "posterior_mean_coef2": (1.0 - ac_prev) * np.sqrt(alphas) / (1.0 - ac),
+    }
+
+
+# ------------------------------------------------------------------------------------------------
+# Normaliser (reference normalization.py:149-167)
+# ------------------------------------------------------------------------------------------------
+def limits_normalize(x, mins, maxs):
+    x = (x - mins) / (maxs - mins)
+    return 2 * x - 1
+
+
+def limits_unnormalize(x, mins, maxs, eps=1e-4):
+    if x.max() > 1 + eps or x.min() < -1 - eps:   # batch-global branch
+        x = torch.clip(x, -1, 1)
+    x = (x + 1) / 2.0
+    return x * (maxs - mins) + mins
+
+
+# ------------------------------------------------------------------------------------------------
+# Restated (unpinned) planning arithmetic — SURVEY Appendix C / E
+# ------------------------------------------------------------------------------------------------
+def interpolate_points(x, n):
+    """C1: linear resampling along the horizon, align_corners=True, all D channels."""
+    return F.interpolate(x.transpose(-2, -1), size=n, mode="linear", align_corners=True).transpose(-2, -1)
+
+
+def _rx(roll, dtype):
+    c, s = math.cos(roll), math.sin(roll)
+    return torch.tensor([[1, 0, 0], [0, c, -s], [0, s, c]], dtype=dtype)
+
+
+def panda_frames(q, joint_xyz, joint_roll, flange_xyz):
+    """Origins [..., 8, 3] and rotations [..., 8, 3, 3] of link 1..7 + flange (App. E)."""
+    dtype = q.dtype
+    lead = q.shape[:-1]
+    R = torch.eye(3, dtype=dtype).expand(*lead, 3, 3)
+    o = torch.zeros(*lead, 3, dtype=dtype)
+    origins, rots = [], []
+    for i in range(7):
+        o = o + (R @ torch.as_tensor(joint_xyz[i], dtype=dtype))
+        c, s = torch.cos(q[..., i]), torch.sin(q[..., i])
+        z, one = torch.zeros_like(c), torch.ones_like(c)
+        Rz = torch.stack([torch.stack([c, -s, z], -1), torch.stack([s, c, z], -1), torch.stack([z, z, one], -1)], -2)
+        R = R @ _rx(float(joint_roll[i]), dtype) @ Rz
+        origins.append(o); rots.append(R)
+    o = o + (R @ torch.as_tensor(flange_xyz, dtype=dtype))
+    origins.append(o); rots.append(R)
+    return torch.stack(origins, -2), torch.stack(rots, -3)
+
+
+def sphere_centers(robot, q):
+    """C2/E1: world positions of the robot's collision spheres, [..., S, ws_dim]."""
+    if robot.kind == "pointmass":
+        return q[..., None, :]
+    from mpd_public_b200 import synthetic as S
+    o, R = panda_frames(q, S.PANDA_JOINT_XYZ, S.PANDA_JOINT_ROLL, S.PANDA_FLANGE_XYZ)
+    f = torch.as_tensor(robot.sphere_frame.astype(np.int64) - 1)
+    off = torch.as_tensor(robot.sphere_offset, dtype=q.dtype)
+    return o[..., f, :] + torch.einsum("...sij,sj->...si", R[..., f, :, :], off)
+
+
+def sdf_and_grad_analytic(p, spheres, boxes):
+    """C5: min over primitives of the signed distance and its closed-form gradient at p[N, dim]."""
+    dim = p.shape[-1]
+    best = torch.full(p.shape[:-1], float("inf"), dtype=p.dtype)
+    grad = torch.zeros_like(p)
+    for s in np.asarray(spheres, dtype=np.float64).reshape(-1, dim + 1):
+        c = torch.as_tensor(s[:dim], dtype=p.dtype)
+        d = p - c
+        n = torch.sqrt((d * d).sum(-1))
+        val = n - float(s[dim])
+        g = d / torch.clamp(n, min=1e-12)[..., None]
+        take = val < best
+        best = torch.where(take, val, best)
+        grad = torch.where(take[..., None], g, grad)
+    for b in np.asarray(boxes, dtype=np.float64).reshape(-1, 2 * dim):
+        c = torch.as_tensor(b[:dim], dtype=p.dtype)
+        h = torch.as_tensor(b[dim:], dtype=p.dtype)
+        d = p - c
+        qv = d.abs() - h
+        qpos = torch.clamp(qv, min=0)
+        outside = torch.sqrt((qpos * qpos).sum(-1))
+        qmax, amax = qv.max(dim=-1)
+        val = outside + torch.clamp(qmax, max=0)
+        sgn = torch.where(d >= 0, torch.ones_like(d), -torch.ones_like(d))
+        g_out = sgn * qpos / torch.clamp(outside, min=1e-12)[..., None]
+        g_in = sgn * F.one_hot(amax, dim).to(p.dtype)
+        g = torch.where((outside > 0)[..., None], g_out, g_in)
+        take = val < best
+        best = torch.where(take, val, best)
+        grad = torch.where(take[..., None], g, grad)
+    return best, grad
+
+
+class GridSDF:
+    """C5: voxel grid over the env limits; each node stores {sdf, d/dx, d/dy[, d/dz]}.
+
+    `texels`: float tensor [prod(shape), 1+dim] (x slowest ... last axis fastest).
+    """
+
+    def __init__(self, limits, cell, texels, shape):
+        self.lo = torch.as_tensor(np.asarray(limits)[0], dtype=torch.float32)
+        self.cell = float(cell)
+        self.shape = tuple(int(s) for s in shape)
+        self.texels = texels
+        self.dim = len(self.shape)
+
+    @classmethod
+    def build(cls, limits, cell, shape, spheres, boxes, dtype=torch.float32):
+        axes = [torch.as_tensor(limits[0][d], dtype=dtype) + torch.arange(shape[d], dtype=dtype) * torch.as_tensor(cell, dtype=dtype)
+                for d in range(len(shape))]
+        pts = torch.stack(torch.meshgrid(*axes, indexing="ij"), -1).reshape(-1, len(shape))
+        vals, grads = [], []
+        for chunk in torch.split(pts, 1 << 20):
+            v, g = sdf_and_grad_analytic(chunk, spheres, boxes)
+            vals.append(v); grads.append(g)
+        tex = torch.cat([torch.cat(vals)[:, None], torch.cat(grads)], dim=1).to(torch.float32)
+        return cls(limits, cell, tex, shape)
+
+    def __call__(self, p):
+        """sdf(p) with value from the nearest node and gradient = stored texel (surrogate)."""
+        tex = self.texels.to(p.dtype)
+        idx = torch.round((p.detach() - self.lo.to(p.dtype)) / torch.as_tensor(self.cell, dtype=p.dtype)).long()
+        flat = torch.zeros(p.shape[:-1], dtype=torch.long)
+        for d in range(self.dim):
+            flat = flat * self.shape[d] + idx[..., d].clamp(0, self.shape[d] - 1)
+        t = tex[flat]
+        return t[..., 0] + ((p - p.detach()) * t[..., 1:]).sum(-1)
+
+
+def border_sdf(p, limits):
+    """C4: distance to the nearest workspace wall, positive inside."""
+    lo = torch.as_tensor(np.asarray(limits)[0], dtype=p.dtype)
+    hi = torch.as_tensor(np.asarray(limits)[1], dtype=p.dtype)
+    return torch.minimum(p - lo, hi - p).min(dim=-1).values
+
+
+def collision_cost(sdf_fn, centers, radii, cutoff_margin):
+    """C4: sum over horizon rows and link spheres of relu(r + margin - sdf(p)); sigma_coll = 1."""
+    d = sdf_fn(centers)
+    r = torch.as_tensor(radii, dtype=centers.dtype)
+    return torch.relu(r + cutoff_margin - d).sum(dim=(-1, -2))
+
+
+def gp_cost(x, q_dim, dt, sigma_gp=1.0):
+    """C6: constant-velocity GP prior, sum_h e_h^T Q^-1 e_h, e_h = x_{h+1} - Phi x_h."""
+    p, v = x[..., :q_dim], x[..., q_dim:2 * q_dim]
+    ep = p[..., 1:, :] - p[..., :-1, :] - dt * v[..., :-1, :]
+    ev = v[..., 1:, :] - v[..., :-1, :]
+    s = 1.0 / (sigma_gp ** 2)
+    a, b, c = 12.0 / dt ** 3 * s, -6.0 / dt ** 2 * s, 4.0 / dt * s
+    return (a * ep * ep + 2 * b * ep * ev + c * ev * ev).sum(dim=(-1, -2))
+
+
+@dataclass
+class GuideSpec:
+    """Everything `GuideManagerTrajectoriesWithVelocity` + `CostComposite` hold (inference.py:195-236)."""
+    robot: object                 # synthetic.RobotSpec
+    mins: torch.Tensor            # [D]
+    maxs: torch.Tensor
+    grid_fields: list             # list[GridSDF]
+    border_limits: object         # [2, dim] or None
+    cutoff_margin: float
+    dt: float
+    weight_collision: float
+    weight_smoothness: float
+    sigma_gp: float = 1.0
+    clip_grad: bool = True
+    max_grad_norm: float = 1.0
+    n_interp: int = 128
+    interpolate: bool = True
+
+
+def composite_costs(spec: GuideSpec, x, x_interp):
+    """C3: CostComposite(trajs, x_interpolated=..., return_invidual_costs_and_weights=True)."""
+    q = spec.robot.q_dim
+    xs = x_interp if SWITCH_C3_COLLISION_ON_INTERPOLATED else x
+    centers = sphere_centers(spec.robot, xs[..., :q])
+    costs, weights = [], []
+    for g in spec.grid_fields:
+        costs.append(collision_cost(g, centers, spec.robot.sphere_radius, spec.cutoff_margin))
+        weights.append(spec.weight_collision)
+    if spec.border_limits is not None:
+        costs.append(collision_cost(lambda p: border_sdf(p, spec.border_limits), centers,
+                                    spec.robot.sphere_radius, spec.cutoff_margin))
+        weights.append(spec.weight_collision)
+    costs.append(gp_cost(x, q, spec.dt, spec.sigma_gp))
+    weights.append(spec.weight_smoothness)
+    return costs, weights
+
+
+def clip_grad_by_norm(grad, max_grad_norm):
+    """reference guides.py:224-230."""
+    n = torch.linalg.norm(grad + 1e-6, dim=-1, keepdims=True)
+    return torch.clip(n, 0.0, max_grad_norm) / n * grad
+
+
+def guide_manager_grad(spec: GuideSpec, x_normalized, return_parts=False):
+    """reference guides.py:173-211 — returns -sum_c w_c * zero_ends(clip(d cost_c / d x_unnormalized))."""
+    x = x_normalized.clone()
+    with torch.enable_grad():
+        x.requires_grad_(True)
+        x = limits_unnormalize(x, spec.mins.to(x.dtype), spec.maxs.to(x.dtype))
+        x_interp = interpolate_points(x, spec.n_interp) if spec.interpolate else x
+        cost_l, w_l = composite_costs(spec, x, x_interp)
+        grad = 0
+        parts = []
+        for cost, w in zip(cost_l, w_l):
+            g = torch.autograd.grad([cost.sum()], [x], retain_graph=True)[0]
+            if spec.clip_grad:
+                g = clip_grad_by_norm(g, spec.max_grad_norm)
+            g[..., 0, :] = 0.0
+            g[..., -1, :] = 0.0
+            parts.append(g)
+            grad = grad + w * g
+    grad = -1.0 * grad
+    return (grad, parts) if return_parts else grad
+
+
+# ------------------------------------------------------------------------------------------------
+# Sampler (reference diffusion_model_base.py:143-182, sample_functions.py:5-83)
+# ------------------------------------------------------------------------------------------------
+def apply_hard_conditioning(x, conditions):
+    for t, val in conditions.items():
+        x[:, t, :] = val.clone()
+    return x
+
+
+def _extract(a, t, ndim):
+    return a.gather(-1, t).reshape(t.shape[0], *((1,) * (ndim - 1)))
+
+
+class OracleDiffusion:
+    """GaussianDiffusionModel restated for sampling (predict_epsilon / clip_denoised as configured)."""
+
+    def __init__(self, unet_sd, n_diffusion_steps=25, variance_schedule="exponential", predict_epsilon=True,
+                 clip_denoised=True, dtype=torch.float32):
+        self.dtype = dtype
+        self.sd = {k: torch.as_tensor(v).to(dtype) for k, v in unet_sd.items()}
+        self.n_diffusion_steps = n_diffusion_steps
+        self.predict_epsilon = predict_epsilon
+        self.clip_denoised = clip_denoised
+        self.buf = {k: v.to(dtype) for k, v in make_schedule(n_diffusion_steps, variance_schedule).items()}
+        self.state_dim = self.sd["final_conv.1.weight"].shape[0]
+
+    def model(self, x, t):
+        return unet_forward(self.sd, x, t)
+
+    def p_mean_variance(self, x, t):
+        b = self.buf
+        noise = self.model(x, t)
+        if self.predict_epsilon:
+            x_recon = (_extract(b["sqrt_recip_alphas_cumprod"], t, x.ndim) * x
+                       - _extract(b["sqrt_recipm1_alphas_cumprod"], t, x.ndim) * noise)
+        else:
+            x_recon = noise
+        if self.clip_denoised:
+            x_recon = x_recon.clamp(-1.0, 1.0)
+        mean = (_extract(b["posterior_mean_coef1"], t, x.ndim) * x_recon
+                + _extract(b["posterior_mean_coef2"], t, x.ndim) * x)
+        return mean, _extract(b["posterior_variance"], t, x.ndim), _extract(b["posterior_log_variance_clipped"], t, x.ndim)
+
+    def guide_gradient_steps(self, x, hard_conds, guide, n_guide_steps=1, scale_grad_by_std=False, model_var=None):
+        for _ in range(n_guide_steps):
+            g = guide(x)
+            if scale_grad_by_std:
+                g = model_var * g
+            x = x + g
+            x = apply_hard_conditioning(x, hard_conds)
+        return x
+
+    def ddpm_step(self, x, hard_conds, t, noise, guide=None, n_guide_steps=1, scale_grad_by_std=False,
+                  t_start_guide=float("inf"), noise_std=1.0, return_mean=False):
+        """One `ddpm_sample_fn` call with the step noise injected (`noise` replaces randn_like)."""
+        t_single = int(t[0])
+        if t_single < 0:
+            t = torch.zeros_like(t)
+        mean, _, _ = self.p_mean_variance(x, t)
+        logvar = _extract(self.buf["posterior_log_variance_clipped"], t, x.ndim)
+        std, var = torch.exp(0.5 * logvar), torch.exp(logvar)
+        x = mean
+        if guide is not None and t_single < t_start_guide:
+            x = self.guide_gradient_steps(x, hard_conds, guide, n_guide_steps, scale_grad_by_std, var)
+        noise = noise.clone()
+        noise[t == 0] = 0
+        out = x + std * noise * noise_std
+        return (out, mean) if return_mean else out
+
+    def p_sample_loop(self, shape, hard_conds, noise=None, generator=None, return_chain=False,
+                      n_diffusion_steps_without_noise=0, guide=None, n_guide_steps=1, scale_grad_by_std=False,
+                      t_start_guide=float("inf"), noise_std_fn=None):
+        """`noise`: [n_steps+1, B, H, D] injected (row 0 = initial x); else drawn in reference order
+        from the global torch generator (randn(shape), then randn_like per step)."""
+        steps = list(reversed(range(-n_diffusion_steps_without_noise, self.n_diffusion_steps)))
+        draw = (lambda k: noise[k].to(self.dtype).clone()) if noise is not None else \
+               (lambda k: torch.randn(shape, generator=generator).to(self.dtype))
+        x = draw(0)
+        x = apply_hard_conditioning(x, hard_conds)
+        chain = [x] if return_chain else None
+        for k, i in enumerate(steps):
+            t = torch.full((shape[0],), i, dtype=torch.long)
+            ns = 1.0 if noise_std_fn is None else float(noise_std_fn(t[0]))
+            x = self.ddpm_step(x, hard_conds, t, draw(k + 1), guide, n_guide_steps, scale_grad_by_std, t_start_guide, ns)
+            x = apply_hard_conditioning(x, hard_conds)
+            if return_chain:
+                chain.append(x)
+        if return_chain:
+            return x, torch.stack(chain, dim=1)
+        return x
+
+
+# ------------------------------------------------------------------------------------------------
+# Convenience: build the oracle-side guide from a synthetic.ProblemSpec
+# ------------------------------------------------------------------------------------------------
+def hard_conditions(problem, normalize=True, dtype=torch.float32):
+    """reference trajectories.py:214-237: {0: [q_start, 0], H-1: [q_goal, 0]} (normalised)."""
+    s = torch.cat([torch.as_tensor(problem.start), torch.zeros(problem.robot.q_dim)]).to(dtype)
+    g = torch.cat([torch.as_tensor(problem.goal), torch.zeros(problem.robot.q_dim)]).to(dtype)
+    if normalize:
+        mins, maxs = torch.as_tensor(problem.mins).to(dtype), torch.as_tensor(problem.maxs).to(dtype)
+        s, g = limits_normalize(s, mins, maxs), limits_normalize(g, mins, maxs)
+    return {0: s, problem.n_support_points - 1: g}
+
+
+def build_grid_fields(problem, texels_list=None):
+    env = problem.env
+    fields = []
+    sets = [(env.spheres, env.boxes)]
+    if np.asarray(env.extra_spheres).size or np.asarray(env.extra_boxes).size:
+        sets.append((env.extra_spheres, env.extra_boxes))
+    for k, (sp, bx) in enumerate(sets):
+        if texels_list is not None:
+            fields.append(GridSDF(env.limits, env.cell, texels_list[k], env.grid_shape))
+        else:
+            fields.append(GridSDF.build(env.limits, env.cell, env.grid_shape, sp, bx))
+    return fields
+
+
+def make_guide_spec(problem, weight_collision, weight_smoothness, texels_list=None, n_interp=128, **kw) -> GuideSpec:
+    return GuideSpec(robot=problem.robot, mins=torch.as_tensor(problem.mins), maxs=torch.as_tensor(problem.maxs),
+                     grid_fields=build_grid_fields(problem, texels_list), border_limits=problem.env.limits,
+                     cutoff_margin=problem.cutoff_margin, dt=problem.dt, weight_collision=weight_collision,
+                     weight_smoothness=weight_smoothness, n_interp=n_interp, **kw)

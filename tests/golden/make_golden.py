@@ -1,0 +1,117 @@
+"""Generates tests/golden/*.npz by running the REFERENCE's own code (from /root/reference, under the
+name-only shim of oracle/ref_shim.py). Run in the build container: `python tests/golden/make_golden.py`.
+
+The reference holds no tests or golden vectors for this path, so these files are the
+pin: UNet / schedule / p_mean_variance / ddpm_sample_fn / guide manager / p_sample_loop outputs are
+produced by reference code. The cost arithmetic under the guide (collision/GP/FK/SDF — sources absent)
+is the oracle's restatement bound into the reference guide manager ("parity unpinned" part).
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+
+from oracle import mpd_oracle as O  # noqa: E402
+from oracle import ref_shim  # noqa: E402
+from tests.golden import cases as C  # noqa: E402
+from mpd_public_b200 import synthetic as S  # noqa: E402
+
+torch.set_num_threads(8)
+
+
+def save(name, **arrs):
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **{k: np.asarray(v) for k, v in arrs.items()})
+    print(f"wrote {path} ({os.path.getsize(path) / 1024:.1f} KiB)")
+
+
+def ref_model(case):
+    d, h, opt, seed = C.UNET_CASES[case]
+    return ref_shim.build_reference_model(C.unet_weights(case), d, h, 32, S.UNET_DIM_MULTS[opt], C.T_DIFF)
+
+
+def gen_unet():
+    out = {}
+    for case in C.UNET_CASES:
+        model = ref_model(case)
+        x = torch.as_tensor(C.unet_input(case))
+        t = torch.tensor(C.UNET_T, dtype=torch.long)
+        with torch.no_grad():
+            out[case] = model.model(x, t, None).numpy()
+    save("unet_eps", **out)
+
+
+def gen_schedule():
+    ref = ref_shim.load()
+    out = {}
+    for sched, T in (("exponential", 25), ("cosine", 20)):
+        class _M(torch.nn.Module):
+            state_dim = 4
+        m = ref.GaussianDiffusionModel(model=_M(), variance_schedule=sched, n_diffusion_steps=T, predict_epsilon=True)
+        for k, v in m.state_dict().items():
+            out[f"{sched}.{k}"] = v.numpy()
+    save("schedule", **out)
+
+
+def gen_normalizer():
+    ref = ref_shim.load()
+    prob = C.guide_problem("panda3d")
+    nz = ref.LimitsNormalizer(torch.stack([torch.as_tensor(prob.mins), torch.as_tensor(prob.maxs)]))
+    x_in = torch.as_tensor(C.guide_input("panda3d"))
+    x_out = torch.as_tensor(C.guide_input("panda3d", out_of_range=True))
+    save("normalizer", un_in=nz.unnormalize(x_in).numpy(), un_out=nz.unnormalize(x_out).numpy(),
+         renorm=nz.normalize(nz.unnormalize(x_in)).numpy())
+
+
+def gen_guide_and_steps():
+    ref = ref_shim.load()
+    for case, (model_id, ucase, cell, wc, ws, batch) in C.GUIDE_CASES.items():
+        prob = C.guide_problem(case)
+        spec = O.make_guide_spec(prob, wc, ws)
+        guide = ref_shim.build_reference_guide(spec)
+        model = ref_model(ucase)
+        hard = O.hard_conditions(prob)
+        out = {}
+        # guide manager alone
+        for tag, oor in (("in", False), ("oor", True)):
+            x = torch.as_tensor(C.guide_input(case, out_of_range=oor))
+            out[f"guide_grad_{tag}"] = guide(x).numpy()
+        # guide_gradient_steps (5 iterations)
+        x = torch.as_tensor(C.guide_input(case))
+        hc = {k: v[None].repeat(batch, 1) for k, v in hard.items()}
+        out["guide_steps5"] = ref.guide_gradient_steps(x.clone(), hard_conds=hc, guide=guide, n_guide_steps=5).numpy()
+        # teacher-forced single steps
+        for i in C.STEP_LIST:
+            x = torch.as_tensor(C.step_input(case, i))
+            t = torch.full((batch,), i, dtype=torch.long)
+            with torch.no_grad():
+                mean, _, _ = model.p_mean_variance(x=x.clone(), hard_conds=hc, context=None, t=torch.clamp(t, min=0))
+            out[f"mean_{i}"] = mean.numpy()
+            for gtag, g in (("noguide", None), ("guide", guide)):
+                torch.manual_seed(1000 + i)
+                xn, _ = ref.ddpm_sample_fn(model, x.clone(), hc, None, t, guide=g, n_guide_steps=C.N_GUIDE_STEPS,
+                                           t_start_guide=C.T_START_GUIDE, noise_std_extra_schedule_fn=lambda _t: C.NOISE_STD)
+                out[f"step_{gtag}_{i}"] = xn.numpy()
+        # full loops (reference run_inference, RNG = global torch generator)
+        for gtag, g in (("noguide", None), ("guide", guide)):
+            torch.manual_seed(77)
+            chain = model.run_inference(None, hard, n_samples=batch, horizon=prob.n_support_points, return_chain=True,
+                                        sample_fn=ref.ddpm_sample_fn, guide=g, n_guide_steps=C.N_GUIDE_STEPS,
+                                        t_start_guide=C.T_START_GUIDE, noise_std_extra_schedule_fn=lambda _t: C.NOISE_STD,
+                                        n_diffusion_steps_without_noise=C.N_EXTRA)
+            out[f"loop_chain_{gtag}"] = chain.numpy()
+        save(f"guided_{case}", **out)
+
+
+if __name__ == "__main__":
+    assert ref_shim.available(), "reference tree not present"
+    gen_schedule()
+    gen_unet()
+    gen_normalizer()
+    gen_guide_and_steps()
