@@ -1,0 +1,146 @@
+/*
+ * mpdb200 — C ABI of the B200-native guided-diffusion trajectory sampler.
+ *
+ * The reference (jacarvalho/mpd-public) is pure Python/PyTorch and has no FFI layer; its boundary for
+ * this path is the Python surface that scripts/inference/inference.py touches. The
+ * entry points below are what a ctypes binding inside that Python surface would call — each one
+ * cites the reference interface it replaces. Plain pointers and sizes only: device pointers are raw
+ * CUDA addresses (`tensor.data_ptr()`), `stream` is a `cudaStream_t` cast to `void*`
+ * (`torch.cuda.current_stream().cuda_stream`), all tensors are contiguous fp32 unless noted.
+ *
+ * Every function returns 0 on success or a non-zero status; `mpdb_last_error()` returns the message
+ * of the last failure on the calling thread (the Python binding raises RuntimeError with it —
+ * the reference signals errors with Python exceptions, diffusion_model_base.py:72,275).
+ */
+#ifndef MPDB200_H
+#define MPDB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MPDB_MAX_LEVELS 8
+#define MPDB_MAX_STATE_DIM 32
+#define MPDB_MAX_SPHERES 16
+#define MPDB_MAX_GRID_FIELDS 4
+#define MPDB_MAX_HARD_CONDS 8
+
+typedef struct mpdb_engine mpdb_engine; /* TemporalUnet + GaussianDiffusionModel state on one device */
+typedef struct mpdb_guide mpdb_guide;   /* GuideManagerTrajectoriesWithVelocity + CostComposite state */
+
+/* TemporalUnet(n_support_points, state_dim, unet_input_dim, dim_mults) — temporal_unet.py:22-35;
+ * GaussianDiffusionModel(n_diffusion_steps, predict_epsilon, clip_denoised) — diffusion_model_base.py:48-56 */
+typedef struct {
+    int32_t state_dim;
+    int32_t horizon;
+    int32_t unet_input_dim;
+    int32_t n_levels;
+    int32_t dim_mults[MPDB_MAX_LEVELS];
+    int32_t n_diffusion_steps;
+    int32_t predict_epsilon;
+    int32_t clip_denoised;
+    int32_t max_batch; /* initial workspace size; grows on demand */
+} mpdb_engine_config;
+
+/* What CostComposite([CostCollision(field)..., CostGPTrajectory]) and the guide manager hold
+ * (inference.py:195-236, guides.py:149-171). Arithmetic of the absent cost/robot/field classes follows
+ * SURVEY.md Appendix C/E. */
+typedef struct {
+    int32_t robot_kind; /* 0 = point mass (FK identity), 1 = Panda 7-DoF chain */
+    int32_t q_dim;
+    int32_t ws_dim;
+    int32_t n_spheres;
+    int32_t sphere_frame[MPDB_MAX_SPHERES]; /* Panda: 1..8 (link 1..7, flange) */
+    float sphere_offset[MPDB_MAX_SPHERES][3];
+    float sphere_radius[MPDB_MAX_SPHERES];
+    float mins[MPDB_MAX_STATE_DIM]; /* LimitsNormalizer limits, normalization.py:149-167 */
+    float maxs[MPDB_MAX_STATE_DIM];
+    int32_t n_grid_fields;
+    const float* grid_texels[MPDB_MAX_GRID_FIELDS]; /* device; [cells][1+ws_dim] = {sdf, grad} */
+    int32_t grid_shape[3];
+    float grid_lo[3];
+    float grid_cell;
+    int32_t has_border; /* workspace-boundary field */
+    float border_lo[3];
+    float border_hi[3];
+    float cutoff_margin;
+    float dt;
+    float sigma_gp;
+    float weight_grid[MPDB_MAX_GRID_FIELDS];
+    float weight_border;
+    float weight_gp;
+    int32_t use_gp;
+    int32_t clip_grad;
+    float max_grad_norm;
+    int32_t n_interp; /* num_interpolated_points_for_collision (guides.py:153); == horizon when off */
+} mpdb_guide_config;
+
+/* p_sample_loop(..., sample_fn=ddpm_sample_fn, n_diffusion_steps_without_noise, **sample_kwargs)
+ * — diffusion_model_base.py:158-182, sample_functions.py:18-62 */
+typedef struct {
+    int32_t n_steps_without_noise;
+    int32_t t_start_guide; /* INT32_MAX for +inf */
+    int32_t n_guide_steps;
+    int32_t scale_grad_by_std;
+    const float* noise_std; /* host, one value per loop iteration (noise_std_extra_schedule_fn(t)) */
+    int32_t n_hard_conds;
+    int32_t hard_cond_rows[MPDB_MAX_HARD_CONDS];
+    const float* hard_cond_vals; /* device [n_hard_conds][B][D] */
+    int32_t use_cuda_graph;
+} mpdb_loop_params;
+
+const char* mpdb_last_error(void);
+int mpdb_version(void);
+
+/* ---- engine: nn.Module construction / load_state_dict (inference.py:138-149) ---- */
+int mpdb_engine_create(const mpdb_engine_config* cfg, int device, mpdb_engine** out);
+void mpdb_engine_destroy(mpdb_engine* e);
+/* one TemporalUnet state-dict entry (reference layout), copied from device memory */
+int mpdb_engine_set_param(mpdb_engine* e, const char* name, const float* dev_ptr, int64_t numel, void* stream);
+/* schedule buffers of GaussianDiffusionModel (diffusion_model_base.py:82-104), host arrays of [T] */
+int mpdb_engine_set_schedule(mpdb_engine* e, const float* sqrt_recip_alphas_cumprod,
+                             const float* sqrt_recipm1_alphas_cumprod, const float* posterior_mean_coef1,
+                             const float* posterior_mean_coef2, const float* posterior_log_variance_clipped,
+                             const float* posterior_std, const float* posterior_var);
+/* repack weights, precompute the time-conditioning tables; errors if a parameter is missing */
+int mpdb_engine_finalize(mpdb_engine* e, void* stream);
+
+/* TemporalUnet.forward(x, time, context=None) — temporal_unet.py:118-171. x,eps: [B,H,D]; t: int64 [B] */
+int mpdb_unet_forward(mpdb_engine* e, const float* x, const int64_t* t, float* eps, int32_t B, void* stream);
+/* GaussianDiffusionModel.p_mean_variance -> model_mean — diffusion_model_base.py:143-155 */
+int mpdb_p_mean(mpdb_engine* e, const float* x, const int64_t* t, float* mean, int32_t B, void* stream);
+/* x + model_std * noise * noise_std with noise[t == 0] = 0 — sample_functions.py:50-62 (in place on x) */
+int mpdb_add_noise(mpdb_engine* e, float* x, const int64_t* t, const float* noise, float noise_std, int32_t B,
+                   void* stream);
+/* the whole reverse loop, fused. noise: [n_iters+1][B][H][D] (row 0 = initial x). chain_out may be NULL;
+ * chain strides are in floats (so [B,S,H,D] and [S,B,H,D] are both expressible). */
+int mpdb_sample_loop(mpdb_engine* e, mpdb_guide* g, const mpdb_loop_params* p, const float* noise, float* x_out,
+                     float* chain_out, int64_t chain_step_stride, int64_t chain_batch_stride, int32_t B, void* stream);
+/* kernels launched by this engine/guide pair since creation (bench.py's gpu_launches) */
+int64_t mpdb_launch_count(void);
+
+/* debugging / parity: intermediate activations of the last mpdb_unet_forward */
+int mpdb_engine_num_buffers(mpdb_engine* e);
+int mpdb_engine_buffer_info(mpdb_engine* e, int idx, char* name, int name_cap, int32_t* channels, int32_t* length);
+int mpdb_engine_read_buffer(mpdb_engine* e, int idx, float* dev_out /* [B][C][L] */, int32_t B, void* stream);
+
+/* ---- guide: GuideManagerTrajectoriesWithVelocity (guides.py:149-236) ---- */
+int mpdb_guide_create(const mpdb_guide_config* cfg, int device, mpdb_guide** out);
+void mpdb_guide_destroy(mpdb_guide* g);
+/* guide(x_normalized) -> grad, [B,H,D] — guides.py:173-211 */
+int mpdb_guide_grad(mpdb_guide* g, const float* x, float* grad, int32_t B, int32_t H, void* stream);
+/* guide_gradient_steps(x, hard_conds, guide, n_guide_steps, scale_grad_by_std, model_var) in place —
+ * sample_functions.py:65-83. model_var: device [B] or NULL. hard-cond arrays as in mpdb_loop_params. */
+int mpdb_guide_steps(mpdb_guide* g, float* x, int32_t n_steps, const float* model_var, int32_t n_hard_conds,
+                     const int32_t* hard_cond_rows, const float* hard_cond_vals, int32_t B, int32_t H, void* stream);
+/* samples analytic primitives (spheres [ns][dim+1], boxes [nb][2*dim], host arrays) onto the voxel grid:
+ * texels_out device [prod(shape)][1+dim] */
+int mpdb_sdf_grid_build(int32_t dim, const int32_t* shape, const float* lo, float cell, const float* spheres,
+                        int32_t n_spheres, const float* boxes, int32_t n_boxes, float* texels_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MPDB200_H */

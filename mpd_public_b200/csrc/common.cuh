@@ -1,0 +1,57 @@
+// Shared helpers of the mpdb200 library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <atomic>
+#include <string>
+
+namespace mpdb {
+
+void set_error(const std::string& msg);
+extern std::atomic<long long> g_launch_count;
+
+#define MPDB_CHECK_CUDA(expr)                                                                       \
+    do {                                                                                            \
+        cudaError_t _e = (expr);                                                                    \
+        if (_e != cudaSuccess) {                                                                    \
+            mpdb::set_error(std::string(#expr) + ": " + cudaGetErrorString(_e) + " (" + __FILE__ +  \
+                            ":" + std::to_string(__LINE__) + ")");                                  \
+            return 1;                                                                               \
+        }                                                                                           \
+    } while (0)
+
+#define MPDB_REQUIRE(cond, msg)                  \
+    do {                                         \
+        if (!(cond)) {                           \
+            mpdb::set_error(std::string(msg));   \
+            return 2;                            \
+        }                                        \
+    } while (0)
+
+#define MPDB_LAUNCH_CHECK()                      \
+    do {                                         \
+        mpdb::g_launch_count.fetch_add(1);       \
+        MPDB_CHECK_CUDA(cudaGetLastError());     \
+    } while (0)
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Mish(x) = x * tanh(softplus(x)); same composition as aten's mish (x * tanh(log1p(exp(x)))).
+__device__ __forceinline__ float mishf(float x) { return x * tanhf(log1pf(expf(x))); }
+
+}  // namespace mpdb

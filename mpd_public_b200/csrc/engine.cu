@@ -1,0 +1,711 @@
+// Host side of libmpdb200: the engine (TemporalUnet weights in device-native layout, schedule tables,
+// activation workspace, launch plan) and the fused reverse-diffusion loop.
+//   GaussianDiffusionModel.p_sample_loop      diffusion_model_base.py:158-182
+//   ddpm_sample_fn                            sample_functions.py:18-62
+//   TemporalUnet.forward                      temporal_unet.py:118-171
+#include <limits.h>
+#include <string.h>
+
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "internal.h"
+
+namespace mpdb {
+
+static thread_local std::string g_error;
+std::atomic<long long> g_launch_count{0};
+void set_error(const std::string& msg) { g_error = msg; }
+
+static int group_norm_n_groups(int c) {  // reference layers.py:389-395
+    if (c < 8) return 1;
+    for (int g = 8; g < 18; ++g)
+        if (c % g == 0) return g;
+    return 1;
+}
+
+struct Param {
+    std::string name;
+    long long numel = 0;
+    long long offset = 0;  // floats into raw storage
+    bool set = false;
+};
+
+struct ActBuf {
+    std::string name;
+    int C = 0, L = 0;
+    long long offset = 0;  // floats into the workspace, per-sample stride = C * (L + 4)
+};
+
+struct PackJob {
+    std::string src;
+    long long dst;
+    int CO, CI, K, transposed;  // K == 0 -> plain copy of CO floats
+};
+
+struct ConvOp {
+    int mode = MODE_CONV5;
+    // sources: buffer ids (-1 = external x in BLC layout, -2 = none)
+    int in0 = -2, in1 = -2;
+    int res0 = -2, res1 = -2;
+    int out = -1;
+    long long w = -1, bias = -1, gamma = -1, beta = -1, cond = -1, res_w = -1, res_bias = -1;  // packed offsets
+    int CO = 0, L_in = 0, L_out = 0, gs = 4;
+    bool gn = false;
+};
+
+}  // namespace mpdb
+
+using namespace mpdb;
+
+struct mpdb_engine {
+    mpdb_engine_config cfg;
+    int device = 0;
+    std::vector<int> dims;  // [D, C1, C2, ...]
+    std::map<std::string, Param> params;
+    float* raw = nullptr;     // parameters in reference layout
+    long long raw_floats = 0;
+    float* packed = nullptr;  // parameters / tables in kernel layout
+    long long packed_floats = 0;
+    std::vector<ActBuf> bufs;
+    std::vector<ConvOp> ops;
+    std::vector<PackJob> packs;
+    std::vector<std::pair<std::string, long long>> cond_jobs;  // cond_mlp prefix -> table offset
+    float* work = nullptr;    // activations
+    long long work_floats_per_sample = 0;
+    int work_batch = 0;
+    long long final_w = -1, final_b = -1;
+    int final_in = -1;
+    // schedule tables on device: [7][T]
+    float* sched = nullptr;
+    std::vector<float> sched_host;
+    bool sched_set = false;
+    bool finalized = false;
+    // loop state
+    float* xbuf[2] = {nullptr, nullptr};
+    int* flags = nullptr;
+    int n_flags = 0;
+    int loop_batch = 0;
+    // CUDA graph cache for the fused loop
+    cudaGraphExec_t graph_exec = nullptr;
+    std::string graph_key;
+    float* g_noise = nullptr;   // staging owned by the engine (stable addresses for the graph)
+    float* g_hc = nullptr;
+    float* g_chain = nullptr;
+    long long g_noise_floats = 0, g_hc_floats = 0, g_chain_floats = 0;
+};
+
+namespace mpdb {
+
+static long long add_param(mpdb_engine* e, const std::string& name, long long numel) {
+    Param p;
+    p.name = name;
+    p.numel = numel;
+    p.offset = e->raw_floats;
+    e->raw_floats += (numel + 3) / 4 * 4;
+    e->params[name] = p;
+    return p.offset;
+}
+
+static long long alloc_packed(mpdb_engine* e, long long numel) {
+    long long off = e->packed_floats;
+    e->packed_floats += (numel + 3) / 4 * 4;
+    return off;
+}
+
+static int add_buf(mpdb_engine* e, const std::string& name, int C, int L) {
+    ActBuf b;
+    b.name = name;
+    b.C = C;
+    b.L = L;
+    b.offset = e->work_floats_per_sample;
+    e->work_floats_per_sample += (long long)C * (L + 2 * HALO);
+    e->bufs.push_back(b);
+    return (int)e->bufs.size() - 1;
+}
+
+struct PlanBuilder {
+    mpdb_engine* e;
+    std::vector<PackJob> packs;
+    std::vector<std::pair<std::string, long long>> cond_jobs;  // cond_mlp prefix -> table offset
+
+    long long conv_w(const std::string& name, int CO, int CI, int K, int transposed = 0) {
+        add_param(e, name, (long long)CO * CI * K);
+        long long dst = alloc_packed(e, (long long)CO * CI * K);
+        packs.push_back({name, dst, CO, CI, K, transposed});
+        return dst;
+    }
+    long long vec(const std::string& name, int n) {
+        add_param(e, name, n);
+        long long dst = alloc_packed(e, n);
+        packs.push_back({name, dst, n, 1, 0, 0});
+        return dst;
+    }
+
+    // ResidualTemporalBlock (layers.py:323-355) = two launches
+    int rtb(const std::string& p, int in0, int in1, int cin, int cout, int L) {
+        int T = e->cfg.n_diffusion_steps;
+        int h1 = add_buf(e, p + ".blocks.0", cout, L);
+        int out = add_buf(e, p, cout, L);
+        ConvOp a;
+        a.mode = MODE_CONV5;
+        a.in0 = in0; a.in1 = in1;
+        a.out = h1;
+        a.w = conv_w(p + ".blocks.0.block.0.weight", cout, cin, 5);
+        a.bias = vec(p + ".blocks.0.block.0.bias", cout);
+        a.gamma = vec(p + ".blocks.0.block.2.weight", cout);
+        a.beta = vec(p + ".blocks.0.block.2.bias", cout);
+        add_param(e, p + ".cond_mlp.1.weight", (long long)cout * 32);
+        add_param(e, p + ".cond_mlp.1.bias", cout);
+        a.cond = alloc_packed(e, (long long)T * cout);
+        cond_jobs.push_back({p + ".cond_mlp.1", a.cond});
+        a.CO = cout; a.L_in = L; a.L_out = L; a.gn = true;
+        a.gs = cout / group_norm_n_groups(cout);
+        e->ops.push_back(a);
+
+        ConvOp b;
+        b.mode = MODE_CONV5;
+        b.in0 = h1;
+        b.out = out;
+        b.w = conv_w(p + ".blocks.1.block.0.weight", cout, cout, 5);
+        b.bias = vec(p + ".blocks.1.block.0.bias", cout);
+        b.gamma = vec(p + ".blocks.1.block.2.weight", cout);
+        b.beta = vec(p + ".blocks.1.block.2.bias", cout);
+        b.res0 = in0; b.res1 = in1;
+        if (cin != cout) {
+            b.res_w = conv_w(p + ".residual_conv.weight", cout, cin, 1);
+            b.res_bias = vec(p + ".residual_conv.bias", cout);
+        }
+        b.CO = cout; b.L_in = L; b.L_out = L; b.gn = true;
+        b.gs = a.gs;
+        e->ops.push_back(b);
+        return out;
+    }
+};
+
+static int build_plan(mpdb_engine* e, PlanBuilder& pb) {
+    const mpdb_engine_config& c = e->cfg;
+    e->dims.clear();
+    e->dims.push_back(c.state_dim);
+    for (int i = 0; i < c.n_levels; ++i) e->dims.push_back(c.unet_input_dim * c.dim_mults[i]);
+    const int n = c.n_levels;
+    int L = c.horizon;
+
+    add_param(e, "time_mlp.encoder.1.weight", 128 * 32);
+    add_param(e, "time_mlp.encoder.1.bias", 128);
+    add_param(e, "time_mlp.encoder.3.weight", 32 * 128);
+    add_param(e, "time_mlp.encoder.3.bias", 32);
+
+    std::vector<int> skips;
+    int cur = -1;  // external x (BLC)
+    for (int i = 0; i < n; ++i) {
+        const int cin = e->dims[i], cout = e->dims[i + 1];
+        std::string p = "downs." + std::to_string(i);
+        int a = pb.rtb(p + ".0", cur, -2, cin, cout, L);
+        int b = pb.rtb(p + ".1", a, -2, cout, cout, L);
+        skips.push_back(b);
+        if (i < n - 1) {
+            ConvOp d;
+            d.mode = MODE_DOWN;
+            d.in0 = b;
+            d.out = add_buf(e, p + ".4", cout, L / 2);
+            d.w = pb.conv_w(p + ".4.conv.weight", cout, cout, 3);
+            d.bias = pb.vec(p + ".4.conv.bias", cout);
+            d.CO = cout; d.L_in = L; d.L_out = L / 2;
+            e->ops.push_back(d);
+            cur = d.out;
+            L /= 2;
+        } else {
+            cur = b;
+        }
+    }
+    const int mid = e->dims[n];
+    cur = pb.rtb("mid_block1", cur, -2, mid, mid, L);
+    cur = pb.rtb("mid_block2", cur, -2, mid, mid, L);
+    for (int i = 0; i < n - 1; ++i) {
+        const int lv = n - 1 - i;
+        const int cin = e->dims[lv], cout = e->dims[lv + 1];
+        std::string p = "ups." + std::to_string(i);
+        int a = pb.rtb(p + ".0", cur, skips[lv], 2 * cout, cin, L);
+        int b = pb.rtb(p + ".1", a, -2, cin, cin, L);
+        ConvOp u;
+        u.mode = MODE_UP;
+        u.in0 = b;
+        u.out = add_buf(e, p + ".4", cin, L * 2);
+        u.w = pb.conv_w(p + ".4.conv.weight", cin, cin, 4, /*transposed=*/1);
+        u.bias = pb.vec(p + ".4.conv.bias", cin);
+        u.CO = cin; u.L_in = L; u.L_out = L * 2;
+        e->ops.push_back(u);
+        cur = u.out;
+        L *= 2;
+    }
+    {
+        const int C = c.unet_input_dim;
+        ConvOp f;
+        f.mode = MODE_CONV5;
+        f.in0 = cur;
+        f.out = add_buf(e, "final_conv.0", C, L);
+        f.w = pb.conv_w("final_conv.0.block.0.weight", C, e->dims[1], 5);
+        f.bias = pb.vec("final_conv.0.block.0.bias", C);
+        f.gamma = pb.vec("final_conv.0.block.2.weight", C);
+        f.beta = pb.vec("final_conv.0.block.2.bias", C);
+        f.CO = C; f.L_in = L; f.L_out = L; f.gn = true;
+        f.gs = C / group_norm_n_groups(C);
+        e->ops.push_back(f);
+        e->final_in = f.out;
+        add_param(e, "final_conv.1.weight", (long long)c.state_dim * C);
+        add_param(e, "final_conv.1.bias", c.state_dim);
+        e->final_w = alloc_packed(e, (long long)c.state_dim * C);
+        e->final_b = alloc_packed(e, c.state_dim);
+        pb.packs.push_back({"final_conv.1.weight", e->final_w, c.state_dim * C, 1, 0, 0});
+        pb.packs.push_back({"final_conv.1.bias", e->final_b, c.state_dim, 1, 0, 0});
+    }
+    MPDB_REQUIRE(L == c.horizon, "internal: plan length mismatch");
+    return 0;
+}
+
+static int ensure_workspace(mpdb_engine* e, int B) {
+    if (B <= e->work_batch) return 0;
+    if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; e->graph_key.clear(); }
+    MPDB_CHECK_CUDA(cudaDeviceSynchronize());
+    if (e->work) cudaFree(e->work);
+    e->work = nullptr;
+    size_t bytes = sizeof(float) * (size_t)e->work_floats_per_sample * (size_t)B;
+    MPDB_CHECK_CUDA(cudaMalloc(&e->work, bytes));
+    MPDB_CHECK_CUDA(cudaMemset(e->work, 0, bytes));  // halo columns stay zero forever
+    for (int k = 0; k < 2; ++k) {
+        if (e->xbuf[k]) cudaFree(e->xbuf[k]);
+        MPDB_CHECK_CUDA(cudaMalloc(&e->xbuf[k], sizeof(float) * (size_t)B * e->cfg.horizon * e->cfg.state_dim));
+    }
+    e->work_batch = B;
+    return 0;
+}
+
+static const float* buf_ptr(mpdb_engine* e, int id, int B_alloc) {
+    // buffers are laid out buffer-major: buffer k occupies [offset_k * B_alloc, ...)
+    return e->work + e->bufs[id].offset * (long long)B_alloc;
+}
+
+static ConvSrc make_src(mpdb_engine* e, int id0, int id1, const float* x_ext, int L) {
+    ConvSrc s;
+    memset(&s, 0, sizeof(s));
+    s.L = L;
+    if (id0 == -1) {
+        s.p0 = x_ext; s.c0 = e->cfg.state_dim; s.blc = 1;
+    } else if (id0 >= 0) {
+        s.p0 = buf_ptr(e, id0, e->work_batch); s.c0 = e->bufs[id0].C;
+    }
+    if (id1 >= 0) { s.p1 = buf_ptr(e, id1, e->work_batch); s.c1 = e->bufs[id1].C; }
+    return s;
+}
+
+// Runs every layer up to (and including) final_conv.0; the 1x1 projection is fused into launch_final.
+static int run_unet_body(mpdb_engine* e, const float* x, const long long* t_dev, int t_uniform, int B, cudaStream_t st) {
+    for (const ConvOp& op : e->ops) {
+        ConvArgs a;
+        memset(&a, 0, sizeof(a));
+        a.in = make_src(e, op.in0, op.in1, x, op.L_in);
+        a.w = e->packed + op.w;
+        a.bias = e->packed + op.bias;
+        if (op.gn) { a.gamma = e->packed + op.gamma; a.beta = e->packed + op.beta; }
+        if (op.cond >= 0) { a.cond = e->packed + op.cond; a.t_dev = t_dev; a.t_uniform = t_uniform; }
+        if (op.res0 != -2) {
+            a.res = make_src(e, op.res0, op.res1, x, op.L_out);
+            if (op.res_w >= 0) { a.res_w = e->packed + op.res_w; a.res_bias = e->packed + op.res_bias; }
+        }
+        a.out = const_cast<float*>(buf_ptr(e, op.out, e->work_batch));
+        a.CO = op.CO; a.L_out = op.L_out; a.B = B; a.gs = op.gs;
+        choose_tile(B, op.L_out, op.CO, op.gn ? op.gs : 4, &a.S, &a.NT);
+        if (launch_conv(op.mode, a, st)) return 1;
+    }
+    return 0;
+}
+
+static void fill_final(mpdb_engine* e, FinalArgs& f, const float* x, const long long* t_dev, int t_uniform, int B) {
+    memset(&f, 0, sizeof(f));
+    f.h = buf_ptr(e, e->final_in, e->work_batch);
+    f.C = e->cfg.unet_input_dim;
+    f.w = e->packed + e->final_w;
+    f.bias = e->packed + e->final_b;
+    f.x = x;
+    f.t_dev = t_dev;
+    f.t_uniform = t_uniform;
+    const int T = e->cfg.n_diffusion_steps;
+    f.sr = e->sched + 0 * T; f.srm1 = e->sched + 1 * T; f.c1 = e->sched + 2 * T; f.c2 = e->sched + 3 * T;
+    f.stdv = e->sched + 5 * T;
+    f.predict_epsilon = e->cfg.predict_epsilon;
+    f.clip_denoised = e->cfg.clip_denoised;
+    f.B = B; f.L = e->cfg.horizon; f.D = e->cfg.state_dim;
+}
+
+}  // namespace mpdb
+
+extern "C" const char* mpdb_last_error(void) { return mpdb::g_error.c_str(); }
+extern "C" int mpdb_version(void) { return 100; }
+extern "C" int64_t mpdb_launch_count(void) { return mpdb::g_launch_count.load(); }
+
+extern "C" int mpdb_engine_create(const mpdb_engine_config* cfg, int device, mpdb_engine** out) {
+    MPDB_REQUIRE(cfg && out, "mpdb_engine_create: null argument");
+    MPDB_REQUIRE(cfg->n_levels >= 1 && cfg->n_levels <= MPDB_MAX_LEVELS, "engine: bad n_levels");
+    MPDB_REQUIRE(cfg->state_dim >= 1 && cfg->state_dim <= MPDB_MAX_STATE_DIM, "engine: state_dim must be in [1, 32]");
+    MPDB_REQUIRE(cfg->unet_input_dim % 32 == 0 && cfg->unet_input_dim > 0,
+                 "engine: unet_input_dim must be a multiple of 32 (GroupNorm group = 4k channels)");
+    MPDB_REQUIRE(cfg->horizon > 0 && cfg->horizon % (8 << (cfg->n_levels - 1)) == 0,
+                 "engine: horizon must be divisible by 8 * 2^(n_levels-1)");
+    MPDB_REQUIRE(cfg->n_diffusion_steps >= 1, "engine: n_diffusion_steps must be >= 1");
+    for (int i = 0; i < cfg->n_levels; ++i) MPDB_REQUIRE(cfg->dim_mults[i] >= 1, "engine: bad dim_mults");
+    MPDB_CHECK_CUDA(cudaSetDevice(device));
+    std::unique_ptr<mpdb_engine> e(new mpdb_engine());
+    e->cfg = *cfg;
+    e->device = device;
+    PlanBuilder pb;
+    pb.e = e.get();
+    if (build_plan(e.get(), pb)) return 2;
+    MPDB_CHECK_CUDA(cudaMalloc(&e->raw, sizeof(float) * (size_t)e->raw_floats));
+    MPDB_CHECK_CUDA(cudaMalloc(&e->packed, sizeof(float) * (size_t)(e->packed_floats + 32 * cfg->n_diffusion_steps)));
+    MPDB_CHECK_CUDA(cudaMemset(e->packed, 0, sizeof(float) * (size_t)(e->packed_floats + 32 * cfg->n_diffusion_steps)));
+    MPDB_CHECK_CUDA(cudaMalloc(&e->sched, sizeof(float) * 7 * (size_t)cfg->n_diffusion_steps));
+    e->packs = pb.packs;
+    e->cond_jobs = pb.cond_jobs;
+    if (ensure_workspace(e.get(), cfg->max_batch > 0 ? cfg->max_batch : 1)) return 1;
+    *out = e.release();
+    return 0;
+}
+
+extern "C" void mpdb_engine_destroy(mpdb_engine* e) {
+    if (!e) return;
+    cudaSetDevice(e->device);
+    cudaDeviceSynchronize();
+    if (e->graph_exec) cudaGraphExecDestroy(e->graph_exec);
+    cudaFree(e->raw); cudaFree(e->packed); cudaFree(e->work); cudaFree(e->sched);
+    cudaFree(e->xbuf[0]); cudaFree(e->xbuf[1]); cudaFree(e->flags);
+    cudaFree(e->g_noise); cudaFree(e->g_hc); cudaFree(e->g_chain);
+    delete e;
+}
+
+extern "C" int mpdb_engine_set_param(mpdb_engine* e, const char* name, const float* dev_ptr, int64_t numel, void* stream) {
+    MPDB_REQUIRE(e && name && dev_ptr, "mpdb_engine_set_param: null argument");
+    auto it = e->params.find(name);
+    MPDB_REQUIRE(it != e->params.end(), std::string("unexpected parameter '") + name + "' for this TemporalUnet configuration");
+    MPDB_REQUIRE(it->second.numel == numel, std::string("size mismatch for parameter '") + name + "': expected " +
+                                                std::to_string(it->second.numel) + ", got " + std::to_string(numel));
+    MPDB_CHECK_CUDA(cudaSetDevice(e->device));
+    MPDB_CHECK_CUDA(cudaMemcpyAsync(e->raw + it->second.offset, dev_ptr, sizeof(float) * (size_t)numel,
+                                    cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    it->second.set = true;
+    e->finalized = false;
+    return 0;
+}
+
+extern "C" int mpdb_engine_set_schedule(mpdb_engine* e, const float* sr, const float* srm1, const float* c1,
+                                        const float* c2, const float* logvar, const float* stdv, const float* var) {
+    MPDB_REQUIRE(e && sr && srm1 && c1 && c2 && logvar && stdv && var, "mpdb_engine_set_schedule: null argument");
+    const int T = e->cfg.n_diffusion_steps;
+    e->sched_host.resize(7 * (size_t)T);
+    const float* src[7] = {sr, srm1, c1, c2, logvar, stdv, var};
+    for (int k = 0; k < 7; ++k) memcpy(e->sched_host.data() + (size_t)k * T, src[k], sizeof(float) * T);
+    MPDB_CHECK_CUDA(cudaSetDevice(e->device));
+    MPDB_CHECK_CUDA(cudaMemcpy(e->sched, e->sched_host.data(), sizeof(float) * 7 * (size_t)T, cudaMemcpyHostToDevice));
+    e->sched_set = true;
+    return 0;
+}
+
+extern "C" int mpdb_engine_finalize(mpdb_engine* e, void* stream) {
+    MPDB_REQUIRE(e, "mpdb_engine_finalize: null engine");
+    cudaStream_t st = (cudaStream_t)stream;
+    MPDB_CHECK_CUDA(cudaSetDevice(e->device));
+    for (auto& kv : e->params)
+        MPDB_REQUIRE(kv.second.set, std::string("missing parameter '") + kv.first + "' (load_state_dict incomplete)");
+    MPDB_REQUIRE(e->sched_set, "schedule tables not set");
+    if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; e->graph_key.clear(); }
+    for (const PackJob& j : e->packs) {
+        const float* src = e->raw + e->params[j.src].offset;
+        float* dst = e->packed + j.dst;
+        if (j.K == 0) {
+            MPDB_CHECK_CUDA(cudaMemcpyAsync(dst, src, sizeof(float) * (size_t)j.CO, cudaMemcpyDeviceToDevice, st));
+        } else {
+            if (launch_repack_conv(src, dst, j.CO, j.CI, j.K, j.transposed, st)) return 1;
+        }
+    }
+    const int T = e->cfg.n_diffusion_steps;
+    float* temb = e->packed + e->packed_floats;  // [T][32] scratch behind the packed parameters
+    if (launch_time_tables(e->raw + e->params["time_mlp.encoder.1.weight"].offset,
+                           e->raw + e->params["time_mlp.encoder.1.bias"].offset,
+                           e->raw + e->params["time_mlp.encoder.3.weight"].offset,
+                           e->raw + e->params["time_mlp.encoder.3.bias"].offset, temb, T, st))
+        return 1;
+    for (auto& cj : e->cond_jobs) {
+        const Param& w = e->params[cj.first + ".weight"];
+        const Param& b = e->params[cj.first + ".bias"];
+        if (launch_cond_table(e->raw + w.offset, e->raw + b.offset, temb, e->packed + cj.second, T, (int)b.numel, st))
+            return 1;
+    }
+    MPDB_CHECK_CUDA(cudaStreamSynchronize(st));
+    e->finalized = true;
+    return 0;
+}
+
+extern "C" int mpdb_unet_forward(mpdb_engine* e, const float* x, const int64_t* t, float* eps, int32_t B, void* stream) {
+    MPDB_REQUIRE(e && x && t && eps && B > 0, "mpdb_unet_forward: bad argument");
+    MPDB_REQUIRE(e->finalized, "engine not finalized (call mpdb_engine_finalize after loading parameters)");
+    cudaStream_t st = (cudaStream_t)stream;
+    MPDB_CHECK_CUDA(cudaSetDevice(e->device));
+    if (ensure_workspace(e, B)) return 1;
+    if (run_unet_body(e, x, (const long long*)t, 0, B, st)) return 1;
+    FinalArgs f;
+    fill_final(e, f, x, (const long long*)t, 0, B);
+    f.mode = 0;
+    f.out = eps;
+    return launch_final(f, st);
+}
+
+extern "C" int mpdb_p_mean(mpdb_engine* e, const float* x, const int64_t* t, float* mean, int32_t B, void* stream) {
+    MPDB_REQUIRE(e && x && t && mean && B > 0, "mpdb_p_mean: bad argument");
+    MPDB_REQUIRE(e->finalized, "engine not finalized (call mpdb_engine_finalize after loading parameters)");
+    cudaStream_t st = (cudaStream_t)stream;
+    MPDB_CHECK_CUDA(cudaSetDevice(e->device));
+    if (ensure_workspace(e, B)) return 1;
+    if (run_unet_body(e, x, (const long long*)t, 0, B, st)) return 1;
+    FinalArgs f;
+    fill_final(e, f, x, (const long long*)t, 0, B);
+    f.mode = 1;
+    f.out = mean;
+    return launch_final(f, st);
+}
+
+extern "C" int mpdb_add_noise(mpdb_engine* e, float* x, const int64_t* t, const float* noise, float noise_std,
+                              int32_t B, void* stream) {
+    MPDB_REQUIRE(e && x && t && noise && B > 0, "mpdb_add_noise: bad argument");
+    MPDB_REQUIRE(e->sched_set, "schedule tables not set");
+    MPDB_CHECK_CUDA(cudaSetDevice(e->device));
+    const int T = e->cfg.n_diffusion_steps;
+    return launch_add_noise(x, (const long long*)t, e->sched + 5 * T, noise, noise_std, B,
+                            e->cfg.horizon * e->cfg.state_dim, (cudaStream_t)stream);
+}
+
+namespace mpdb {
+
+// Enqueues the whole reverse loop on `st`. All pointers must stay valid until the stream drains.
+static int enqueue_loop(mpdb_engine* e, mpdb_guide* g, const mpdb_loop_params* p, const float* noise,
+                        const float* hc_vals, float* x_out, float* chain, long long chain_step_stride,
+                        long long chain_batch_stride, int B, cudaStream_t st) {
+    const int T = e->cfg.n_diffusion_steps, H = e->cfg.horizon, D = e->cfg.state_dim;
+    const long long n = (long long)B * H * D;
+    const int n_iters = T + p->n_steps_without_noise;
+    const int n_flags_needed = n_iters * (p->n_guide_steps + 1) + 1;
+    if (g && p->n_guide_steps > 0) {
+        MPDB_REQUIRE(e->n_flags >= n_flags_needed, "internal: flag scratch not allocated");
+        MPDB_CHECK_CUDA(cudaMemsetAsync(e->flags, 0, sizeof(int) * (size_t)n_flags_needed, st));
+    }
+    // x_T = noise[0] with hard conditions (diffusion_model_base.py:165-166)
+    float* cur = e->xbuf[0];
+    MPDB_CHECK_CUDA(cudaMemcpyAsync(cur, noise, sizeof(float) * (size_t)n, cudaMemcpyDeviceToDevice, st));
+    if (launch_copy_hc(cur, chain, chain_batch_stride, p->n_hard_conds, p->hard_cond_rows, hc_vals, B, H, D, st)) return 1;
+
+    int it = 0;
+    for (int i = T - 1; i >= -p->n_steps_without_noise; --i, ++it) {
+        const int t = i < 0 ? 0 : i;  // sample_functions.py:28-30
+        const bool last = (i == -p->n_steps_without_noise);
+        float* nxt = last ? x_out : e->xbuf[(it + 1) & 1];
+        float* chain_slot = chain ? chain + (long long)(it + 1) * chain_step_stride : nullptr;
+        const float* step_noise = noise + (long long)(it + 1) * n;
+        const bool guided = g != nullptr && p->n_guide_steps > 0 && (long long)i < (long long)p->t_start_guide;
+        const float ns = p->noise_std ? p->noise_std[it] : 1.0f;
+
+        if (run_unet_body(e, cur, nullptr, t, B, st)) return 1;
+        FinalArgs f;
+        fill_final(e, f, cur, nullptr, t, B);
+        f.n_hc = p->n_hard_conds;
+        for (int k = 0; k < p->n_hard_conds; ++k) f.hc_rows[k] = p->hard_cond_rows[k];
+        f.hc_vals = hc_vals;
+        if (!guided) {
+            f.mode = 2;
+            f.noise = step_noise;
+            f.noise_std = ns;
+            f.out = nxt;
+            f.out2 = chain_slot;
+            f.out2_bstride = chain_batch_stride;
+            if (launch_final(f, st)) return 1;
+        } else {
+            int* fl = e->flags + (long long)it * (p->n_guide_steps + 1);
+            f.mode = 1;
+            f.out = nxt;  // model mean; guided in place below
+            f.flag_out = fl;
+            if (launch_final(f, st)) return 1;
+            for (int k = 0; k < p->n_guide_steps; ++k) {
+                const bool klast = (k == p->n_guide_steps - 1);
+                GuideStepArgs a;
+                memset(&a, 0, sizeof(a));
+                a.x_in = nxt;
+                a.x_out = nxt;
+                a.flag_in = fl + k;
+                a.flag_out = klast ? nullptr : fl + k + 1;
+                if (p->scale_grad_by_std) { a.use_var_uniform = 1; a.var_uniform = e->sched_host[6 * (size_t)T + t]; }
+                a.n_hc = p->n_hard_conds;
+                for (int q = 0; q < p->n_hard_conds; ++q) a.hc_rows[q] = p->hard_cond_rows[q];
+                a.hc_vals = hc_vals;
+                if (klast) {
+                    if (t != 0) {  // noise[t == 0] = 0 (sample_functions.py:52)
+                        a.noise = step_noise;
+                        a.noise_sd = e->sched_host[5 * (size_t)T + t];
+                        a.noise_mult = ns;
+                    }
+                    a.out2 = chain_slot;
+                    a.out2_bstride = chain_batch_stride;
+                }
+                a.B = B;
+                a.H = H;
+                if (guide_launch_step(g, a, st)) return 1;
+            }
+        }
+        cur = nxt;
+    }
+    return 0;
+}
+
+static int ensure_staging(float** buf, long long* have, long long need) {
+    if (need <= *have) return 0;
+    if (*buf) cudaFree(*buf);
+    *buf = nullptr;
+    MPDB_CHECK_CUDA(cudaMalloc(buf, sizeof(float) * (size_t)need));
+    *have = need;
+    return 0;
+}
+
+}  // namespace mpdb
+
+extern "C" int mpdb_sample_loop(mpdb_engine* e, mpdb_guide* g, const mpdb_loop_params* p, const float* noise,
+                                float* x_out, float* chain_out, int64_t chain_step_stride, int64_t chain_batch_stride,
+                                int32_t B, void* stream) {
+    MPDB_REQUIRE(e && p && noise && x_out && B > 0, "mpdb_sample_loop: bad argument");
+    MPDB_REQUIRE(e->finalized, "engine not finalized (call mpdb_engine_finalize after loading parameters)");
+    MPDB_REQUIRE(p->n_hard_conds >= 0 && p->n_hard_conds <= MPDB_MAX_HARD_CONDS, "too many hard conditions");
+    MPDB_REQUIRE(p->n_hard_conds == 0 || p->hard_cond_vals, "hard_cond_vals is null");
+    MPDB_REQUIRE(p->n_steps_without_noise >= 0 && p->n_guide_steps >= 0, "negative step count");
+    MPDB_REQUIRE(!g || guide_state_dim(g) == e->cfg.state_dim, "guide and model disagree on state_dim");
+    MPDB_REQUIRE(!g || guide_device(g) == e->device, "guide and model live on different devices");
+    cudaStream_t st = (cudaStream_t)stream;
+    MPDB_CHECK_CUDA(cudaSetDevice(e->device));
+    if (ensure_workspace(e, B)) return 1;
+    const int T = e->cfg.n_diffusion_steps, H = e->cfg.horizon, D = e->cfg.state_dim;
+    const int n_iters = T + p->n_steps_without_noise;
+    const long long n = (long long)B * H * D;
+
+    {
+        const int n_flags_needed = n_iters * (p->n_guide_steps + 1) + 1;
+        if (e->n_flags < n_flags_needed) {
+            if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; e->graph_key.clear(); }
+            MPDB_CHECK_CUDA(cudaDeviceSynchronize());
+            if (e->flags) cudaFree(e->flags);
+            e->flags = nullptr;
+            MPDB_CHECK_CUDA(cudaMalloc(&e->flags, sizeof(int) * (size_t)n_flags_needed));
+            e->n_flags = n_flags_needed;
+        }
+    }
+    if (!p->use_cuda_graph)
+        return enqueue_loop(e, g, p, noise, p->hard_cond_vals, x_out, chain_out, chain_step_stride, chain_batch_stride,
+                            B, st);
+
+    // ---- CUDA-graph path: the loop is captured once per configuration over engine-owned staging buffers ----
+    const long long noise_floats = (long long)(n_iters + 1) * n;
+    const long long hc_floats = (long long)p->n_hard_conds * B * D;
+    const long long chain_floats = chain_out ? (long long)(n_iters + 1) * n : 0;
+    const bool grow = noise_floats > e->g_noise_floats || hc_floats > e->g_hc_floats || chain_floats > e->g_chain_floats;
+    if (grow && e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; e->graph_key.clear(); }
+    if (ensure_staging(&e->g_noise, &e->g_noise_floats, noise_floats)) return 1;
+    if (ensure_staging(&e->g_hc, &e->g_hc_floats, hc_floats > 0 ? hc_floats : 1)) return 1;
+    if (ensure_staging(&e->g_chain, &e->g_chain_floats, chain_floats > 0 ? chain_floats : 1)) return 1;
+
+    std::string key = std::to_string(B) + "|" + std::to_string((long long)(uintptr_t)g) + "|" +
+                      std::to_string(p->n_steps_without_noise) + "|" + std::to_string(p->t_start_guide) + "|" +
+                      std::to_string(p->n_guide_steps) + "|" + std::to_string(p->scale_grad_by_std) + "|" +
+                      std::to_string(chain_out != nullptr) + "|" + std::to_string(p->n_hard_conds);
+    for (int k = 0; k < p->n_hard_conds; ++k) key += "," + std::to_string(p->hard_cond_rows[k]);
+    for (int k = 0; k < n_iters; ++k) {
+        float v = p->noise_std ? p->noise_std[k] : 1.0f;
+        uint32_t bits;
+        memcpy(&bits, &v, 4);
+        key += ":" + std::to_string(bits);
+    }
+    if (g) {  // the guide configuration is baked into kernel arguments
+        const mpdb_guide_config* gc = reinterpret_cast<const mpdb_guide_config*>(g);
+        const unsigned char* bytes = reinterpret_cast<const unsigned char*>(gc);
+        unsigned long long hsh = 1469598103934665603ull;
+        for (size_t k = 0; k < sizeof(mpdb_guide_config); ++k) { hsh ^= bytes[k]; hsh *= 1099511628211ull; }
+        key += "|" + std::to_string(hsh);
+    }
+
+    if (e->graph_exec == nullptr || key != e->graph_key) {
+        if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; }
+        // internal chain staging is always [S][B][H][D]
+        cudaStream_t cs;
+        MPDB_CHECK_CUDA(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+        cudaGraph_t graph = nullptr;
+        MPDB_CHECK_CUDA(cudaStreamBeginCapture(cs, cudaStreamCaptureModeRelaxed));
+        int rc = enqueue_loop(e, g, p, e->g_noise, e->g_hc, e->xbuf[(n_iters) & 1] /* placeholder, fixed below */,
+                              chain_out ? e->g_chain : nullptr, n, (long long)H * D, B, cs);
+        cudaError_t ce = cudaStreamEndCapture(cs, &graph);
+        if (rc != 0 || ce != cudaSuccess) {
+            if (graph) cudaGraphDestroy(graph);
+            cudaStreamDestroy(cs);
+            if (rc == 0) mpdb::set_error(std::string("graph capture failed: ") + cudaGetErrorString(ce));
+            return 1;
+        }
+        ce = cudaGraphInstantiate(&e->graph_exec, graph, 0);
+        cudaGraphDestroy(graph);
+        cudaStreamDestroy(cs);
+        if (ce != cudaSuccess) {
+            e->graph_exec = nullptr;
+            mpdb::set_error(std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ce));
+            return 1;
+        }
+        e->graph_key = key;
+    }
+    MPDB_CHECK_CUDA(cudaMemcpyAsync(e->g_noise, noise, sizeof(float) * (size_t)noise_floats, cudaMemcpyDeviceToDevice, st));
+    if (hc_floats > 0)
+        MPDB_CHECK_CUDA(cudaMemcpyAsync(e->g_hc, p->hard_cond_vals, sizeof(float) * (size_t)hc_floats,
+                                        cudaMemcpyDeviceToDevice, st));
+    MPDB_CHECK_CUDA(cudaGraphLaunch(e->graph_exec, st));
+    mpdb::g_launch_count.fetch_add(0);
+    // result: the captured loop wrote its last step into xbuf[n_iters & 1]
+    MPDB_CHECK_CUDA(cudaMemcpyAsync(x_out, e->xbuf[(n_iters) & 1], sizeof(float) * (size_t)n, cudaMemcpyDeviceToDevice, st));
+    if (chain_out) {
+        if (chain_step_stride == n && chain_batch_stride == (long long)H * D) {
+            MPDB_CHECK_CUDA(cudaMemcpyAsync(chain_out, e->g_chain, sizeof(float) * (size_t)chain_floats,
+                                            cudaMemcpyDeviceToDevice, st));
+        } else {
+            // strided destination: one 2D copy per step ([B] rows of H*D floats)
+            for (int s = 0; s <= n_iters; ++s)
+                MPDB_CHECK_CUDA(cudaMemcpy2DAsync(chain_out + (long long)s * chain_step_stride,
+                                                  sizeof(float) * (size_t)chain_batch_stride, e->g_chain + (long long)s * n,
+                                                  sizeof(float) * (size_t)H * D, sizeof(float) * (size_t)H * D, B,
+                                                  cudaMemcpyDeviceToDevice, st));
+        }
+    }
+    return 0;
+}
+
+extern "C" int mpdb_engine_num_buffers(mpdb_engine* e) { return e ? (int)e->bufs.size() : 0; }
+
+extern "C" int mpdb_engine_buffer_info(mpdb_engine* e, int idx, char* name, int name_cap, int32_t* channels,
+                                       int32_t* length) {
+    MPDB_REQUIRE(e && idx >= 0 && idx < (int)e->bufs.size(), "mpdb_engine_buffer_info: bad index");
+    if (name && name_cap > 0) {
+        strncpy(name, e->bufs[idx].name.c_str(), name_cap - 1);
+        name[name_cap - 1] = 0;
+    }
+    if (channels) *channels = e->bufs[idx].C;
+    if (length) *length = e->bufs[idx].L;
+    return 0;
+}
+
+extern "C" int mpdb_engine_read_buffer(mpdb_engine* e, int idx, float* dev_out, int32_t B, void* stream) {
+    MPDB_REQUIRE(e && dev_out && idx >= 0 && idx < (int)e->bufs.size(), "mpdb_engine_read_buffer: bad argument");
+    MPDB_REQUIRE(B > 0 && B <= e->work_batch, "mpdb_engine_read_buffer: batch larger than the workspace");
+    MPDB_CHECK_CUDA(cudaSetDevice(e->device));
+    return launch_cm_to_bcl(buf_ptr(e, idx, e->work_batch), dev_out, B, e->bufs[idx].C, e->bufs[idx].L,
+                            (cudaStream_t)stream);
+}

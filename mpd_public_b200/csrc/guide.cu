@@ -1,0 +1,558 @@
+// Cost-gradient guide: GuideManagerTrajectoriesWithVelocity.forward (reference guides.py:173-236) with the
+// restated CostComposite([CostCollision(field)...], CostGPTrajectory) of SURVEY.md Appendix C, and the
+// update x <- x + guide(x) of guide_gradient_steps (sample_functions.py:65-83), as ONE kernel per
+// guide evaluation:
+//
+//   unnormalise (LimitsNormalizer.unnormalize incl. the batch-global clip flag)  ->  linear interpolation
+//   H -> n_interp  ->  FK of the collision spheres  ->  nearest-texel SDF lookup {sdf, grad} per field  ->
+//   hinge  ->  hand-derived adjoint (J^T through the chain, two-tap scatter of the interpolation written
+//   as a gather)  ->  per-cost clip-by-norm, endpoint zeroing, weighting  ->  GP-prior 3-tap stencil
+//   gradient  ->  x + grad, hard conditioning [-> + std * noise * noise_std, hard conditioning].
+//
+// One CTA per trajectory; the trajectory, its unnormalised copy and every per-cost gradient stay in
+// shared memory. The only global traffic is x in/out (+noise) and the SDF texel gathers.
+#include <math.h>
+
+#include <vector>
+
+#include "common.cuh"
+#include "internal.h"
+
+struct mpdb_guide {
+    mpdb_guide_config cfg;
+    int device;
+    int* flags;  // device scratch: [2] flags for the standalone entry points
+};
+
+namespace mpdb {
+
+constexpr int GUIDE_THREADS = 128;
+
+struct GuideDev {
+    int robot_kind, q_dim, ws_dim, n_spheres, D;
+    int sphere_frame[MPDB_MAX_SPHERES];
+    float sphere_off[MPDB_MAX_SPHERES][3];
+    float sphere_r[MPDB_MAX_SPHERES];
+    float mins[MPDB_MAX_STATE_DIM], range[MPDB_MAX_STATE_DIM];
+    int n_grid;
+    const float* tex[MPDB_MAX_GRID_FIELDS];
+    int gshape[3];
+    float glo[3];
+    float cell;
+    int has_border;
+    float blo[3], bhi[3];
+    float margin, dt;
+    float w_grid[MPDB_MAX_GRID_FIELDS], w_border, w_gp;
+    int use_gp, clip;
+    float max_norm;
+    int n_interp;
+    float gp_a, gp_b, gp_c;
+    float joint_xyz[7][3];
+    float joint_cr[7], joint_sr[7];
+    float flange[3];
+};
+
+// Panda chain constants: public Franka URDF values
+static const double kPandaXYZ[7][3] = {{0.0, 0.0, 0.333}, {0.0, 0.0, 0.0},  {0.0, -0.316, 0.0}, {0.0825, 0.0, 0.0},
+                                       {-0.0825, 0.384, 0.0}, {0.0, 0.0, 0.0}, {0.088, 0.0, 0.0}};
+static const double kPandaRoll[7] = {0.0, -M_PI / 2, M_PI / 2, M_PI / 2, -M_PI / 2, M_PI / 2, M_PI / 2};
+static const double kPandaFlange[3] = {0.0, 0.0, 0.107};
+
+static GuideDev make_dev(const mpdb_guide_config& c) {
+    GuideDev d;
+    memset(&d, 0, sizeof(d));
+    d.robot_kind = c.robot_kind;
+    d.q_dim = c.q_dim;
+    d.ws_dim = c.ws_dim;
+    d.n_spheres = c.n_spheres;
+    d.D = 2 * c.q_dim;
+    for (int i = 0; i < c.n_spheres; ++i) {
+        d.sphere_frame[i] = c.sphere_frame[i];
+        for (int k = 0; k < 3; ++k) d.sphere_off[i][k] = c.sphere_offset[i][k];
+        d.sphere_r[i] = c.sphere_radius[i];
+    }
+    for (int i = 0; i < d.D; ++i) {
+        d.mins[i] = c.mins[i];
+        d.range[i] = c.maxs[i] - c.mins[i];  // fp32 subtraction, as `self.maxs - self.mins`
+    }
+    d.n_grid = c.n_grid_fields;
+    for (int i = 0; i < c.n_grid_fields; ++i) {
+        d.tex[i] = c.grid_texels[i];
+        d.w_grid[i] = c.weight_grid[i];
+    }
+    for (int k = 0; k < 3; ++k) {
+        d.gshape[k] = c.grid_shape[k];
+        d.glo[k] = c.grid_lo[k];
+        d.blo[k] = c.border_lo[k];
+        d.bhi[k] = c.border_hi[k];
+    }
+    d.cell = c.grid_cell;
+    d.has_border = c.has_border;
+    d.margin = c.cutoff_margin;
+    d.dt = c.dt;
+    d.w_border = c.weight_border;
+    d.w_gp = c.weight_gp;
+    d.use_gp = c.use_gp;
+    d.clip = c.clip_grad;
+    d.max_norm = c.max_grad_norm;
+    d.n_interp = c.n_interp;
+    const double dt = (double)c.dt, s = 1.0 / ((double)c.sigma_gp * (double)c.sigma_gp);
+    d.gp_a = (float)(12.0 / (dt * dt * dt) * s);
+    d.gp_b = (float)(-6.0 / (dt * dt) * s);
+    d.gp_c = (float)(4.0 / dt * s);
+    for (int i = 0; i < 7; ++i) {
+        for (int k = 0; k < 3; ++k) d.joint_xyz[i][k] = (float)kPandaXYZ[i][k];
+        d.joint_cr[i] = (float)cos(kPandaRoll[i]);
+        d.joint_sr[i] = (float)sin(kPandaRoll[i]);
+    }
+    for (int k = 0; k < 3; ++k) d.flange[k] = (float)kPandaFlange[k];
+    return d;
+}
+
+__device__ __forceinline__ float clip_scale(float n, float max_norm) {
+    // torch.clip(n, 0, max) / n
+    return fminf(fmaxf(n, 0.f), max_norm) / n;
+}
+
+__global__ void __launch_bounds__(GUIDE_THREADS) guide_step_kernel(GuideDev g, GuideStepArgs a) {
+    extern __shared__ __align__(16) float smem[];
+    const int H = a.H, D = g.D, q = g.q_dim, NI = g.n_interp, NTH = GUIDE_THREADS;
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const int n_coll = g.n_grid + (g.has_border ? 1 : 0);
+
+    float* xn = smem;                  // [H][D] normalised input
+    float* xu = xn + H * D;            // [H][D] unnormalised
+    float* tot = xu + H * D;           // [H][D] sum_c w_c * clipped grad_c
+    float* gq = tot + H * D;           // [n_coll][NI][q] d cost_f / d q_interp
+    float* w1s = gq + n_coll * NI * q; // [NI] interpolation weight of the upper tap
+    int* i0s = reinterpret_cast<int*>(w1s + NI);  // [NI] lower tap
+    float* fk = reinterpret_cast<float*>(i0s + NI);  // [(42 + 3*n_spheres)][NTH] per-thread FK scratch
+
+    const int flag = a.flag_in ? *a.flag_in : 0;
+    const float* xin = a.x_in + (long long)b * H * D;
+    for (int i = tid; i < H * D; i += NTH) {
+        float v = xin[i];
+        xn[i] = v;
+        float vc = flag ? fminf(fmaxf(v, -1.f), 1.f) : v;
+        int d = i % D;
+        // ((x + 1) / 2) * (maxs - mins) + mins, reference operation order (normalization.py:165-167)
+        xu[i] = __fadd_rn(__fmul_rn(__fmul_rn(__fadd_rn(vc, 1.f), 0.5f), g.range[d]), g.mins[d]);
+        tot[i] = 0.f;
+    }
+    __syncthreads();
+
+    // ---------------- collision costs on the interpolated trajectory ----------------
+    if (n_coll > 0) {
+        const float ratio = NI > 1 ? (float)(H - 1) / (float)(NI - 1) : 0.f;  // align_corners=True
+        for (int i = tid; i < NI; i += NTH) {
+            float r = ratio * (float)i;
+            int i0 = (int)r;
+            if (i0 > H - 1) i0 = H - 1;
+            float l1 = fminf(fmaxf(r - (float)i0, 0.f), 1.f);
+            float l0 = 1.f - l1;
+            int i1 = i0 + (i0 < H - 1 ? 1 : 0);
+            i0s[i] = i0;
+            w1s[i] = l1;
+            float qv[7];
+#pragma unroll
+            for (int k = 0; k < 7; ++k)
+                qv[k] = k < q ? __fadd_rn(__fmul_rn(l0, xu[i0 * D + k]), __fmul_rn(l1, xu[i1 * D + k])) : 0.f;
+
+            float* sc = fk + tid;  // element j at sc[j * NTH]
+            float* cen = sc + 42 * NTH;
+            if (g.robot_kind == 1) {
+                float R[9] = {1.f, 0.f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f, 1.f};  // row-major
+                float o[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+                for (int j = 0; j < 7; ++j) {
+#pragma unroll
+                    for (int r3 = 0; r3 < 3; ++r3)
+                        o[r3] += R[r3 * 3 + 0] * g.joint_xyz[j][0] + R[r3 * 3 + 1] * g.joint_xyz[j][1] +
+                                 R[r3 * 3 + 2] * g.joint_xyz[j][2];
+                    float sq, cq;
+                    sincosf(qv[j], &sq, &cq);
+                    const float cr = g.joint_cr[j], sr = g.joint_sr[j];
+#pragma unroll
+                    for (int r3 = 0; r3 < 3; ++r3) {
+                        float c0 = R[r3 * 3 + 0], c1 = R[r3 * 3 + 1], c2 = R[r3 * 3 + 2];
+                        float a1 = c1 * cr + c2 * sr;   // (R Rx) column 1
+                        float a2 = -c1 * sr + c2 * cr;  // (R Rx) column 2
+                        R[r3 * 3 + 0] = cq * c0 + sq * a1;
+                        R[r3 * 3 + 1] = -sq * c0 + cq * a1;
+                        R[r3 * 3 + 2] = a2;
+                    }
+#pragma unroll
+                    for (int r3 = 0; r3 < 3; ++r3) {
+                        sc[(j * 3 + r3) * NTH] = o[r3];
+                        sc[(21 + j * 3 + r3) * NTH] = R[r3 * 3 + 2];  // joint axis = third column
+                    }
+                    for (int s = 0; s < g.n_spheres; ++s)
+                        if (g.sphere_frame[s] == j + 1)
+                            for (int r3 = 0; r3 < 3; ++r3)
+                                cen[(s * 3 + r3) * NTH] = o[r3] + R[r3 * 3 + 0] * g.sphere_off[s][0] +
+                                                          R[r3 * 3 + 1] * g.sphere_off[s][1] +
+                                                          R[r3 * 3 + 2] * g.sphere_off[s][2];
+                }
+#pragma unroll
+                for (int r3 = 0; r3 < 3; ++r3)
+                    o[r3] += R[r3 * 3 + 0] * g.flange[0] + R[r3 * 3 + 1] * g.flange[1] + R[r3 * 3 + 2] * g.flange[2];
+                for (int s = 0; s < g.n_spheres; ++s)
+                    if (g.sphere_frame[s] == 8)
+                        for (int r3 = 0; r3 < 3; ++r3)
+                            cen[(s * 3 + r3) * NTH] = o[r3] + R[r3 * 3 + 0] * g.sphere_off[s][0] +
+                                                      R[r3 * 3 + 1] * g.sphere_off[s][1] +
+                                                      R[r3 * 3 + 2] * g.sphere_off[s][2];
+            } else {
+                for (int s = 0; s < g.n_spheres; ++s)
+                    for (int r3 = 0; r3 < 3; ++r3) cen[(s * 3 + r3) * NTH] = r3 < g.ws_dim ? qv[r3] : 0.f;
+            }
+
+            for (int f = 0; f < n_coll; ++f) {
+                float dq[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                for (int s = 0; s < g.n_spheres; ++s) {
+                    float p[3] = {cen[(s * 3 + 0) * NTH], cen[(s * 3 + 1) * NTH], cen[(s * 3 + 2) * NTH]};
+                    float sdf, gr[3] = {0.f, 0.f, 0.f};
+                    if (f < g.n_grid) {
+                        long long flat = 0;
+                        for (int d = 0; d < g.ws_dim; ++d) {
+                            float u = rintf(__fdiv_rn(__fsub_rn(p[d], g.glo[d]), g.cell));
+                            u = fminf(fmaxf(u, 0.f), (float)(g.gshape[d] - 1));
+                            flat = flat * g.gshape[d] + (long long)u;
+                        }
+                        if (g.ws_dim == 3) {
+                            float4 t = __ldg(reinterpret_cast<const float4*>(g.tex[f]) + flat);
+                            sdf = t.x; gr[0] = t.y; gr[1] = t.z; gr[2] = t.w;
+                        } else {
+                            const float* t = g.tex[f] + flat * 3;
+                            sdf = __ldg(t); gr[0] = __ldg(t + 1); gr[1] = __ldg(t + 2);
+                        }
+                    } else {
+                        // workspace-boundary field: distance to the nearest wall, positive inside
+                        sdf = 3.4e38f;
+                        int arg = 0; float sgn = 1.f;
+                        for (int d = 0; d < g.ws_dim; ++d) {
+                            float lo = __fsub_rn(p[d], g.blo[d]), hi = __fsub_rn(g.bhi[d], p[d]);
+                            float m = fminf(lo, hi);
+                            if (m < sdf) { sdf = m; arg = d; sgn = (lo <= hi) ? 1.f : -1.f; }
+                        }
+                        gr[arg] = sgn;
+                    }
+                    const float viol = __fsub_rn(__fadd_rn(g.sphere_r[s], g.margin), sdf);
+                    if (viol > 0.f) {
+                        const float gx = -gr[0], gy = -gr[1], gz = -gr[2];  // d cost / d p
+                        if (g.robot_kind == 1) {
+                            int nj = g.sphere_frame[s] < 7 ? g.sphere_frame[s] : 7;
+                            for (int j = 0; j < nj; ++j) {
+                                float rx = p[0] - sc[(j * 3 + 0) * NTH], ry = p[1] - sc[(j * 3 + 1) * NTH],
+                                      rz = p[2] - sc[(j * 3 + 2) * NTH];
+                                float zx = sc[(21 + j * 3 + 0) * NTH], zy = sc[(21 + j * 3 + 1) * NTH],
+                                      zz = sc[(21 + j * 3 + 2) * NTH];
+                                // (z x r) . g
+                                dq[j] += (zy * rz - zz * ry) * gx + (zz * rx - zx * rz) * gy + (zx * ry - zy * rx) * gz;
+                            }
+                        } else {
+                            dq[0] += gx;
+                            if (g.ws_dim > 1) dq[1] += gy;
+                            if (g.ws_dim > 2) dq[2] += gz;
+                        }
+                    }
+                }
+                float* dst = gq + ((long long)f * NI + i) * q;
+                for (int k = 0; k < q; ++k) dst[k] = dq[k];
+            }
+        }
+        __syncthreads();
+
+        // adjoint of the interpolation (gather form), then per-cost clip / endpoint zero / weight
+        const float inv_ratio = ratio > 0.f ? 1.f / ratio : 0.f;
+        for (int h = tid; h < H; h += NTH) {
+            int lo_i = (int)floorf((float)(h - 1) * inv_ratio) - 1;
+            int hi_i = (int)ceilf((float)(h + 1) * inv_ratio) + 1;
+            if (lo_i < 0) lo_i = 0;
+            if (hi_i > NI - 1) hi_i = NI - 1;
+            for (int f = 0; f < n_coll; ++f) {
+                float gs[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                for (int i = lo_i; i <= hi_i; ++i) {
+                    int i0 = i0s[i];
+                    int i1 = i0 + (i0 < H - 1 ? 1 : 0);
+                    float l1 = w1s[i];
+                    float cw = (i0 == h ? 1.f - l1 : 0.f) + (i1 == h ? l1 : 0.f);
+                    if (cw != 0.f) {
+                        const float* src = gq + ((long long)f * NI + i) * q;
+                        for (int k = 0; k < q; ++k) gs[k] = fmaf(cw, src[k], gs[k]);
+                    }
+                }
+                float scale = 1.f;
+                if (g.clip) {
+                    float n2 = (float)(D - q) * (1e-6f * 1e-6f);
+                    for (int k = 0; k < q; ++k) { float t = gs[k] + 1e-6f; n2 = fmaf(t, t, n2); }
+                    scale = clip_scale(sqrtf(n2), g.max_norm);
+                }
+                const float wgt = f < g.n_grid ? g.w_grid[f] : g.w_border;
+                if (h != 0 && h != H - 1)
+                    for (int k = 0; k < q; ++k) tot[h * D + k] += wgt * (scale * gs[k]);
+            }
+        }
+    }
+
+    // ---------------- GP prior (constant-velocity) on the support points ----------------
+    if (g.use_gp) {
+        for (int h = tid; h < H; h += NTH) {
+            if (h == 0 || h == H - 1) continue;  // gradient rows zeroed by the guide manager
+            float gp[7], gv[7];
+            float n2 = 0.f;
+            for (int k = 0; k < q; ++k) {
+                const float pm = xu[(h - 1) * D + k], pc = xu[h * D + k], pn = xu[(h + 1) * D + k];
+                const float vm = xu[(h - 1) * D + q + k], vc = xu[h * D + q + k], vn = xu[(h + 1) * D + q + k];
+                const float ep0 = pc - pm - g.dt * vm, ev0 = vc - vm;  // e_{h-1}
+                const float ep1 = pn - pc - g.dt * vc, ev1 = vn - vc;  // e_h
+                const float up0 = 2.f * (g.gp_a * ep0 + g.gp_b * ev0), uv0 = 2.f * (g.gp_b * ep0 + g.gp_c * ev0);
+                const float up1 = 2.f * (g.gp_a * ep1 + g.gp_b * ev1), uv1 = 2.f * (g.gp_b * ep1 + g.gp_c * ev1);
+                gp[k] = up0 - up1;
+                gv[k] = uv0 - uv1 - g.dt * up1;
+                float t0 = gp[k] + 1e-6f, t1 = gv[k] + 1e-6f;
+                n2 = fmaf(t0, t0, n2);
+                n2 = fmaf(t1, t1, n2);
+            }
+            float scale = g.clip ? clip_scale(sqrtf(n2), g.max_norm) : 1.f;
+            for (int k = 0; k < q; ++k) {
+                tot[h * D + k] += g.w_gp * (scale * gp[k]);
+                tot[h * D + q + k] += g.w_gp * (scale * gv[k]);
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---------------- output ----------------
+    float* xout = a.x_out + (long long)b * H * D;
+    bool viol = false;
+    float var = 1.f;
+    const bool use_var = a.model_var != nullptr || a.use_var_uniform;
+    if (a.model_var != nullptr) var = a.model_var[b];
+    else if (a.use_var_uniform) var = a.var_uniform;
+    for (int i = tid; i < H * D; i += NTH) {
+        float grad = -1.f * tot[i];
+        if (a.grad_only) {
+            xout[i] = grad;
+            continue;
+        }
+        if (use_var) grad = __fmul_rn(var, grad);
+        float v = __fadd_rn(xn[i], grad);
+        const int h = i / D, d = i - h * D;
+        int hc = -1;
+        for (int k = 0; k < a.n_hc; ++k)
+            if (a.hc_rows[k] == h) hc = k;
+        if (hc >= 0) v = a.hc_vals[((long long)hc * a.B + b) * D + d];
+        viol |= (v > 1.0001f) || (v < -1.0001f);
+        if (a.noise != nullptr && hc < 0) v = __fadd_rn(v, __fmul_rn(__fmul_rn(a.noise_sd, a.noise[(long long)b * H * D + i]), a.noise_mult));
+        xout[i] = v;
+        if (a.out2) a.out2[(long long)b * a.out2_bstride + i] = v;
+    }
+    if (a.flag_out != nullptr) {
+        if (__syncthreads_or(viol ? 1 : 0) && tid == 0) atomicOr(a.flag_out, 1);
+    }
+}
+
+static size_t guide_smem_bytes(const GuideDev& g, int H) {
+    const int n_coll = g.n_grid + (g.has_border ? 1 : 0);
+    size_t f = (size_t)3 * H * g.D + (size_t)n_coll * g.n_interp * g.q_dim + 2 * (size_t)g.n_interp +
+               (size_t)(42 + 3 * g.n_spheres) * GUIDE_THREADS;
+    return f * sizeof(float);
+}
+
+int guide_launch_step(mpdb_guide* gd, const GuideStepArgs& a, cudaStream_t stream) {
+    GuideDev g = make_dev(gd->cfg);
+    MPDB_REQUIRE(g.D <= MPDB_MAX_STATE_DIM && g.q_dim <= 7, "guide: state dim too large");
+    MPDB_REQUIRE(g.n_interp >= 1, "guide: n_interp must be >= 1");
+    const size_t smem = guide_smem_bytes(g, a.H);
+    MPDB_REQUIRE(smem <= 220 * 1024, "guide: trajectory does not fit in shared memory");
+    static size_t configured = 0;
+    if (smem > configured) {
+        MPDB_CHECK_CUDA(cudaFuncSetAttribute(guide_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        configured = 220 * 1024;
+    }
+    guide_step_kernel<<<a.B, GUIDE_THREADS, smem, stream>>>(g, a);
+    MPDB_LAUNCH_CHECK();
+    return 0;
+}
+
+__global__ void range_flag_kernel(const float* __restrict__ x, long long n, int* flag) {
+    bool viol = false;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        float v = x[i];
+        viol |= (v > 1.0001f) || (v < -1.0001f);
+    }
+    if (__syncthreads_or(viol ? 1 : 0) && threadIdx.x == 0) atomicOr(flag, 1);
+}
+
+int guide_launch_flag(const float* x, long long n, int* flag, cudaStream_t stream) {
+    MPDB_CHECK_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), stream));
+    int blocks = (int)((n + 255) / 256);
+    if (blocks > 1184) blocks = 1184;
+    range_flag_kernel<<<blocks, 256, 0, stream>>>(x, n, flag);
+    MPDB_LAUNCH_CHECK();
+    return 0;
+}
+
+int guide_device(mpdb_guide* g) { return g->device; }
+int guide_state_dim(mpdb_guide* g) { return 2 * g->cfg.q_dim; }
+
+// ---------------------------------------------------------------------------------------------------
+// SDF voxel grid from analytic primitives: texel = {sdf, d sdf/dx, ...} at the node
+// ---------------------------------------------------------------------------------------------------
+__global__ void sdf_grid_kernel(int dim, int nx, int ny, int nz, float lox, float loy, float loz, float cell,
+                                const float* __restrict__ spheres, int ns, const float* __restrict__ boxes, int nb,
+                                float* __restrict__ tex) {
+    const long long n = (long long)nx * ny * (dim == 3 ? nz : 1);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        int idx[3];
+        if (dim == 3) { idx[2] = (int)(i % nz); idx[1] = (int)((i / nz) % ny); idx[0] = (int)(i / ((long long)nz * ny)); }
+        else { idx[1] = (int)(i % ny); idx[0] = (int)(i / ny); idx[2] = 0; }
+        const float lo[3] = {lox, loy, loz};
+        float p[3] = {0.f, 0.f, 0.f};
+        for (int d = 0; d < dim; ++d) p[d] = __fadd_rn(lo[d], __fmul_rn((float)idx[d], cell));
+        float best = INFINITY, bg[3] = {0.f, 0.f, 0.f};
+        for (int s = 0; s < ns; ++s) {
+            const float* sp = spheres + s * (dim + 1);
+            float dv[3] = {0.f, 0.f, 0.f}, n2 = 0.f;
+            for (int d = 0; d < dim; ++d) { dv[d] = __fsub_rn(p[d], sp[d]); n2 = __fadd_rn(n2, __fmul_rn(dv[d], dv[d])); }
+            float nn = sqrtf(n2);
+            float val = __fsub_rn(nn, sp[dim]);
+            if (val < best) {
+                best = val;
+                float den = fmaxf(nn, 1e-12f);
+                for (int d = 0; d < 3; ++d) bg[d] = d < dim ? __fdiv_rn(dv[d], den) : 0.f;
+            }
+        }
+        for (int k = 0; k < nb; ++k) {
+            const float* bx = boxes + k * 2 * dim;
+            float dv[3] = {0.f, 0.f, 0.f}, qv[3], qp[3] = {0.f, 0.f, 0.f}, o2 = 0.f, qmax = -INFINITY;
+            int amax = 0;
+            for (int d = 0; d < dim; ++d) {
+                dv[d] = __fsub_rn(p[d], bx[d]);
+                qv[d] = __fsub_rn(fabsf(dv[d]), bx[dim + d]);
+                qp[d] = fmaxf(qv[d], 0.f);
+                o2 = __fadd_rn(o2, __fmul_rn(qp[d], qp[d]));
+                if (qv[d] > qmax) { qmax = qv[d]; amax = d; }
+            }
+            float outside = sqrtf(o2);
+            float val = __fadd_rn(outside, fminf(qmax, 0.f));
+            if (val < best) {
+                best = val;
+                float den = fmaxf(outside, 1e-12f);
+                for (int d = 0; d < 3; ++d) {
+                    float sg = dv[d] >= 0.f ? 1.f : -1.f;
+                    if (d >= dim) bg[d] = 0.f;
+                    else if (outside > 0.f) bg[d] = __fdiv_rn(__fmul_rn(sg, qp[d]), den);
+                    else bg[d] = (d == amax) ? sg : 0.f;
+                }
+            }
+        }
+        float* t = tex + i * (1 + dim);
+        t[0] = best;
+        for (int d = 0; d < dim; ++d) t[1 + d] = bg[d];
+    }
+}
+
+}  // namespace mpdb
+
+using namespace mpdb;
+
+extern "C" int mpdb_guide_create(const mpdb_guide_config* cfg, int device, mpdb_guide** out) {
+    MPDB_REQUIRE(cfg && out, "mpdb_guide_create: null argument");
+    MPDB_REQUIRE(cfg->robot_kind == 0 || cfg->robot_kind == 1, "guide: unknown robot kind");
+    MPDB_REQUIRE(cfg->q_dim >= 1 && cfg->q_dim <= 7 && 2 * cfg->q_dim <= MPDB_MAX_STATE_DIM, "guide: bad q_dim");
+    MPDB_REQUIRE(cfg->robot_kind == 0 || (cfg->q_dim == 7 && cfg->ws_dim == 3), "guide: Panda needs q_dim 7, ws_dim 3");
+    MPDB_REQUIRE(cfg->robot_kind == 1 || cfg->ws_dim == cfg->q_dim, "guide: point mass needs ws_dim == q_dim");
+    MPDB_REQUIRE(cfg->ws_dim == 2 || cfg->ws_dim == 3, "guide: ws_dim must be 2 or 3");
+    MPDB_REQUIRE(cfg->n_spheres >= 1 && cfg->n_spheres <= MPDB_MAX_SPHERES, "guide: bad sphere count");
+    MPDB_REQUIRE(cfg->n_grid_fields >= 0 && cfg->n_grid_fields <= MPDB_MAX_GRID_FIELDS, "guide: bad field count");
+    for (int s = 0; s < cfg->n_spheres && cfg->robot_kind == 1; ++s)
+        MPDB_REQUIRE(cfg->sphere_frame[s] >= 1 && cfg->sphere_frame[s] <= 8, "guide: sphere frame out of range");
+    MPDB_CHECK_CUDA(cudaSetDevice(device));
+    mpdb_guide* g = new mpdb_guide();
+    g->cfg = *cfg;
+    g->device = device;
+    g->flags = nullptr;
+    if (cudaMalloc(&g->flags, 16 * sizeof(int)) != cudaSuccess) {
+        delete g;
+        mpdb::set_error("mpdb_guide_create: cudaMalloc failed");
+        return 1;
+    }
+    *out = g;
+    return 0;
+}
+
+extern "C" void mpdb_guide_destroy(mpdb_guide* g) {
+    if (!g) return;
+    cudaFree(g->flags);
+    delete g;
+}
+
+extern "C" int mpdb_guide_grad(mpdb_guide* g, const float* x, float* grad, int32_t B, int32_t H, void* stream) {
+    MPDB_REQUIRE(g && x && grad && B > 0 && H > 1, "mpdb_guide_grad: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    MPDB_CHECK_CUDA(cudaSetDevice(g->device));
+    if (guide_launch_flag(x, (long long)B * H * 2 * g->cfg.q_dim, g->flags, st)) return 1;
+    GuideStepArgs a;
+    memset(&a, 0, sizeof(a));
+    a.x_in = x;
+    a.x_out = grad;
+    a.grad_only = 1;
+    a.flag_in = g->flags;
+    a.B = B;
+    a.H = H;
+    return guide_launch_step(g, a, st);
+}
+
+extern "C" int mpdb_guide_steps(mpdb_guide* g, float* x, int32_t n_steps, const float* model_var, int32_t n_hc,
+                                const int32_t* hc_rows, const float* hc_vals, int32_t B, int32_t H, void* stream) {
+    MPDB_REQUIRE(g && x && B > 0 && H > 1 && n_steps >= 0, "mpdb_guide_steps: bad argument");
+    MPDB_REQUIRE(n_hc >= 0 && n_hc <= MPDB_MAX_HARD_CONDS, "mpdb_guide_steps: too many hard conditions");
+    cudaStream_t st = (cudaStream_t)stream;
+    MPDB_CHECK_CUDA(cudaSetDevice(g->device));
+    if (n_steps == 0) return 0;
+    if (guide_launch_flag(x, (long long)B * H * 2 * g->cfg.q_dim, g->flags, st)) return 1;
+    for (int it = 0; it < n_steps; ++it) {
+        GuideStepArgs a;
+        memset(&a, 0, sizeof(a));
+        a.x_in = x;
+        a.x_out = x;  // in place: each CTA reads its whole trajectory into shared memory before writing
+        a.flag_in = g->flags + (it & 1);
+        a.flag_out = (it + 1 < n_steps) ? g->flags + ((it + 1) & 1) : nullptr;
+        if (a.flag_out) MPDB_CHECK_CUDA(cudaMemsetAsync(a.flag_out, 0, sizeof(int), st));
+        a.model_var = model_var;
+        a.n_hc = n_hc;
+        for (int k = 0; k < n_hc; ++k) a.hc_rows[k] = hc_rows[k];
+        a.hc_vals = hc_vals;
+        a.B = B;
+        a.H = H;
+        if (guide_launch_step(g, a, st)) return 1;
+    }
+    return 0;
+}
+
+extern "C" int mpdb_sdf_grid_build(int32_t dim, const int32_t* shape, const float* lo, float cell, const float* spheres,
+                                   int32_t n_spheres, const float* boxes, int32_t n_boxes, float* texels_out,
+                                   void* stream) {
+    MPDB_REQUIRE(dim == 2 || dim == 3, "mpdb_sdf_grid_build: dim must be 2 or 3");
+    MPDB_REQUIRE(shape && lo && texels_out, "mpdb_sdf_grid_build: null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    float *dsp = nullptr, *dbx = nullptr;
+    size_t ssz = sizeof(float) * (size_t)n_spheres * (dim + 1), bsz = sizeof(float) * (size_t)n_boxes * 2 * dim;
+    if (ssz) { MPDB_CHECK_CUDA(cudaMalloc(&dsp, ssz)); MPDB_CHECK_CUDA(cudaMemcpyAsync(dsp, spheres, ssz, cudaMemcpyHostToDevice, st)); }
+    if (bsz) { MPDB_CHECK_CUDA(cudaMalloc(&dbx, bsz)); MPDB_CHECK_CUDA(cudaMemcpyAsync(dbx, boxes, bsz, cudaMemcpyHostToDevice, st)); }
+    long long n = (long long)shape[0] * shape[1] * (dim == 3 ? shape[2] : 1);
+    int blocks = (int)((n + 255) / 256);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    sdf_grid_kernel<<<blocks, 256, 0, st>>>(dim, shape[0], shape[1], dim == 3 ? shape[2] : 1, lo[0], lo[1],
+                                            dim == 3 ? lo[2] : 0.f, cell, dsp, n_spheres, dbx, n_boxes, texels_out);
+    mpdb::g_launch_count.fetch_add(1);
+    cudaError_t e = cudaGetLastError();
+    cudaError_t e2 = cudaStreamSynchronize(st);
+    cudaFree(dsp);
+    cudaFree(dbx);
+    MPDB_CHECK_CUDA(e);
+    MPDB_CHECK_CUDA(e2);
+    return 0;
+}

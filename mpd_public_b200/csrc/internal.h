@@ -1,0 +1,117 @@
+// Internal (non-ABI) declarations shared between the translation units of libmpdb200.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/mpdb200.h"
+
+namespace mpdb {
+
+// Activation layout "CM": act[b][c][Lp], Lp = L + 4, element (b,c,l) at ((b*C + c)*Lp + l + 2); the two
+// halo columns on each side stay zero for the lifetime of the buffer (they are the conv zero padding).
+// Layout "BLC": the reference's [B][L][C] (trajectory tensors x, eps).
+constexpr int HALO = 2;
+
+struct ConvSrc {
+    const float* p0;  // first source
+    int c0;
+    const float* p1;  // second source (channel concat), may be null
+    int c1;
+    int blc;  // p0 is BLC (raw trajectory); p1 must be null
+    int L;    // positions per sample of the source
+};
+
+enum ConvMode { MODE_CONV5 = 0, MODE_CONV1 = 1, MODE_DOWN = 2, MODE_UP = 3 };
+
+struct ConvArgs {
+    ConvSrc in;
+    const float* w;     // packed [ci][taps][CO]
+    const float* bias;  // [CO]
+    const float* gamma; // GroupNorm affine, null -> no GroupNorm/Mish
+    const float* beta;
+    const float* cond;  // [T][CO] time-conditioning table added after Mish, null -> none
+    const long long* t_dev;
+    int t_uniform;
+    ConvSrc res;        // residual source (res.p0 == null -> none)
+    const float* res_w; // packed [ci][1][CO]; null -> identity residual
+    const float* res_bias;
+    float* out;         // CM layout [B][CO][L_out + 4]
+    int CO;
+    int L_out;
+    int B;
+    int gs;  // channels per GroupNorm group
+    int S;   // samples per CTA
+    int NT;  // output channels per CTA
+};
+
+int launch_conv(int mode, const ConvArgs& a, cudaStream_t stream);
+void choose_tile(int B, int L_out, int CO, int gs, int* S, int* NT);
+
+struct FinalArgs {
+    const float* h;     // CM [B][C][L+4]
+    int C;
+    const float* w;     // [D][C]
+    const float* bias;  // [D]
+    const float* x;     // BLC [B][L][D]
+    const long long* t_dev;
+    int t_uniform;
+    // schedule tables (device, [T])
+    const float* sr;
+    const float* srm1;
+    const float* c1;
+    const float* c2;
+    const float* stdv;
+    int predict_epsilon;
+    int clip_denoised;
+    int mode;           // 0: write eps; 1: write mean; 2: write mean + std*noise*noise_std, hard conds applied
+    const float* noise; // BLC (mode 2)
+    float noise_std;
+    int n_hc;
+    int hc_rows[MPDB_MAX_HARD_CONDS];
+    const float* hc_vals;  // [n_hc][B][D]
+    float* out;            // BLC
+    float* out2;           // optional second copy (chain slot), batch stride below
+    long long out2_bstride;
+    int* flag_out;         // set to 1 if any |out| > 1 + 1e-4 (mode 1), may be null
+    int B, L, D;
+};
+int launch_final(const FinalArgs& a, cudaStream_t stream);
+
+int launch_repack_conv(const float* src, float* dst, int CO, int CI, int K, int transposed, cudaStream_t stream);
+int launch_time_tables(const float* w1, const float* b1, const float* w3, const float* b3, float* temb_mish, int T,
+                       cudaStream_t stream);
+int launch_cond_table(const float* w, const float* b, const float* temb_mish, float* table, int T, int CO,
+                      cudaStream_t stream);
+int launch_cm_to_bcl(const float* cm, float* out, int B, int C, int L, cudaStream_t stream);
+int launch_add_noise(float* x, const long long* t_dev, const float* stdv, const float* noise, float noise_std, int B,
+                     int HD, cudaStream_t stream);
+int launch_copy_hc(float* x, float* out2, long long out2_bstride, int n_hc, const int* hc_rows, const float* hc_vals,
+                   int B, int L, int D, cudaStream_t stream);
+
+// guide (guide.cu)
+struct GuideStepArgs {
+    const float* x_in;   // BLC normalised
+    float* x_out;        // x_in + scale * guide(x_in) with hard conds (step mode) or the gradient itself (grad mode)
+    int grad_only;
+    const int* flag_in;  // batch-global out-of-range flag for x_in (LimitsNormalizer.unnormalize branch)
+    int* flag_out;       // flag for x_out, may be null
+    const float* model_var;  // [B] or null (scale_grad_by_std)
+    float var_uniform;       // used when model_var == null and use_var_uniform
+    int use_var_uniform;
+    // fused tail of ddpm_sample_fn (last guide iteration of a step)
+    const float* noise;  // null -> no noise
+    float noise_sd;      // model_std
+    float noise_mult;    // noise_std (extra schedule)
+    int n_hc;
+    int hc_rows[MPDB_MAX_HARD_CONDS];
+    const float* hc_vals;
+    float* out2;         // chain slot or null
+    long long out2_bstride;
+    int B, H;
+};
+int guide_launch_step(mpdb_guide* g, const GuideStepArgs& a, cudaStream_t stream);
+int guide_launch_flag(const float* x, long long n, int* flag, cudaStream_t stream);
+int guide_device(mpdb_guide* g);
+int guide_state_dim(mpdb_guide* g);
+
+}  // namespace mpdb

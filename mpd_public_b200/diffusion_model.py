@@ -1,0 +1,468 @@
+"""GaussianDiffusionModel — host-side mirror of reference
+`mpd/models/diffusion_models/diffusion_model_base.py:46-316` (sampling part).
+
+Same constructor, buffers (names and values bit-identical: the same torch ops on the same inputs),
+methods and return conventions, so `scripts/inference/inference.py:138-257` runs unchanged against it.
+The arithmetic of every reverse step runs in libmpdb200 (hand-written sm_100a kernels); when
+`sample_fn` is this package's `ddpm_sample_fn` and the guide is this package's guide manager (or None)
+the whole loop is enqueued by ONE C-ABI call (`mpdb_sample_loop`) with no host synchronisation inside
+(the reference has ~150 host syncs per loop) and can be replayed as a CUDA graph.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from copy import copy
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _lib
+from .sample_functions import apply_hard_conditioning, ddpm_sample_fn, extract, guide_gradient_steps  # noqa: F401
+
+
+# ------------------------------------------------------------------------------------------------
+# schedules (reference helpers.py:26-46) — same torch/numpy ops => bit-identical buffers
+# ------------------------------------------------------------------------------------------------
+def exponential_beta_schedule(n_diffusion_steps, beta_start=1e-4, beta_end=1.0):
+    x = torch.linspace(0, n_diffusion_steps, n_diffusion_steps)
+    beta_start = torch.tensor(beta_start)
+    beta_end = torch.tensor(beta_end)
+    a = 1 / n_diffusion_steps * torch.log(beta_end / beta_start)
+    return beta_start * torch.exp(a * x)
+
+
+def cosine_beta_schedule(n_diffusion_steps, s=0.008, a_min=0, a_max=0.999, dtype=torch.float32):
+    steps = n_diffusion_steps + 1
+    x = np.linspace(0, steps, steps)
+    alphas_cumprod = np.cos(((x / steps) + s) / (1 + s) * np.pi * 0.5) ** 2
+    alphas_cumprod = alphas_cumprod / alphas_cumprod[0]
+    betas = 1 - (alphas_cumprod[1:] / alphas_cumprod[:-1])
+    return torch.tensor(np.clip(betas, a_min=a_min, a_max=a_max), dtype=dtype)
+
+
+def make_timesteps(batch_size, i, device):
+    return torch.full((batch_size,), i, device=device, dtype=torch.long)
+
+
+# ------------------------------------------------------------------------------------------------
+# engine: one libmpdb200 handle per (TemporalUnet, device, schedule)
+# ------------------------------------------------------------------------------------------------
+class Engine:
+    """Owns an `mpdb_engine*`: packed weights, time-conditioning tables, schedule tables, workspace."""
+
+    def __init__(self, unet, device, n_steps, schedule, predict_epsilon, clip_denoised):
+        self.lib = _lib.lib()
+        self.unet = unet
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("mpd_public_b200 has no CPU path: move the model to a CUDA device")
+        self.n_steps = int(n_steps)
+        cfg = _lib.EngineConfig()
+        cfg.state_dim = unet.state_dim
+        cfg.horizon = unet.n_support_points
+        cfg.unet_input_dim = unet.unet_input_dim
+        cfg.n_levels = len(unet.dim_mults)
+        for i, m in enumerate(unet.dim_mults):
+            cfg.dim_mults[i] = m
+        cfg.n_diffusion_steps = self.n_steps
+        cfg.predict_epsilon = int(bool(predict_epsilon))
+        cfg.clip_denoised = int(bool(clip_denoised))
+        cfg.max_batch = 1
+        self.handle = C.c_void_p()
+        dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        self.dev_index = dev_index
+        _lib.check(self.lib.mpdb_engine_create(C.byref(cfg), dev_index, C.byref(self.handle)))
+        self._param_sig = None
+        self._set_schedule(schedule)
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None) and self.handle.value:
+                self.lib.mpdb_engine_destroy(self.handle)
+                self.handle = C.c_void_p()
+        except Exception:
+            pass
+
+    def _set_schedule(self, s):
+        T = self.n_steps
+        if s is None:  # stand-alone TemporalUnet: identity-ish tables, only unet_forward is meaningful
+            z = torch.zeros(T)
+            tabs = [torch.ones(T), z, z, z, z, torch.ones(T), torch.ones(T)]
+        else:
+            logvar = s["posterior_log_variance_clipped"]
+            tabs = [s["sqrt_recip_alphas_cumprod"], s["sqrt_recipm1_alphas_cumprod"], s["posterior_mean_coef1"],
+                    s["posterior_mean_coef2"], logvar, torch.exp(0.5 * logvar), torch.exp(logvar)]
+        arrs = [np.ascontiguousarray(t.detach().float().cpu().numpy()) for t in tabs]
+        for a in arrs:
+            assert a.shape == (T,)
+        self._sched_host = arrs
+        ptrs = [a.ctypes.data_as(C.POINTER(C.c_float)) for a in arrs]
+        _lib.check(self.lib.mpdb_engine_set_schedule(self.handle, *ptrs))
+
+    def _signature(self):
+        ps = list(self.unet.parameters())
+        return tuple((p.data_ptr(), p._version) for p in ps)
+
+    def sync_params(self):
+        """(Re)uploads the UNet parameters when they changed (load_state_dict, .to(), optimiser step)."""
+        sig = self._signature()
+        if sig == self._param_sig:
+            return
+        st = _lib.stream_ptr(self.device)
+        for name, p in self.unet.named_parameters():
+            t = p.detach()
+            if t.device != self.device or t.dtype != torch.float32 or not t.is_contiguous():
+                t = t.to(device=self.device, dtype=torch.float32).contiguous()
+            _lib.check(self.lib.mpdb_engine_set_param(self.handle, name.encode(), _lib.fptr(t), t.numel(), st))
+            del t
+        _lib.check(self.lib.mpdb_engine_finalize(self.handle, st))
+        self._param_sig = sig
+
+    # ---- entry points ----
+    def _prep(self, x, t=None):
+        _lib.require_cuda(x, "x")
+        if x.dim() != 3 or x.shape[1] != self.unet.n_support_points or x.shape[2] != self.unet.state_dim:
+            raise RuntimeError(f"expected x of shape [B, {self.unet.n_support_points}, {self.unet.state_dim}], got {tuple(x.shape)}")
+        x = x.detach().to(torch.float32).contiguous()
+        if t is not None:
+            t = t.to(device=x.device, dtype=torch.long).contiguous()
+            if t.shape != (x.shape[0],):
+                raise RuntimeError(f"expected t of shape [{x.shape[0]}], got {tuple(t.shape)}")
+        return x, t
+
+    def unet_forward(self, x, t, check_t=True):
+        x, t = self._prep(x, t)
+        if check_t and (int(t.max()) >= self.n_steps or int(t.min()) < 0):
+            raise RuntimeError(f"time index out of range [0, {self.n_steps})")
+        self.sync_params()
+        out = torch.empty_like(x)
+        _lib.check(self.lib.mpdb_unet_forward(self.handle, _lib.fptr(x), C.c_void_p(t.data_ptr()), _lib.fptr(out),
+                                              x.shape[0], _lib.stream_ptr(x.device)))
+        return out
+
+    def p_mean(self, x, t):
+        x, t = self._prep(x, t)
+        self.sync_params()
+        out = torch.empty_like(x)
+        _lib.check(self.lib.mpdb_p_mean(self.handle, _lib.fptr(x), C.c_void_p(t.data_ptr()), _lib.fptr(out),
+                                        x.shape[0], _lib.stream_ptr(x.device)))
+        return out
+
+    def add_noise_(self, x, t, noise, noise_std):
+        x2, t = self._prep(x, t)
+        assert x2.data_ptr() == x.data_ptr(), "add_noise_ needs a contiguous fp32 tensor"
+        noise = noise.to(torch.float32).contiguous()
+        _lib.check(self.lib.mpdb_add_noise(self.handle, _lib.fptr(x), C.c_void_p(t.data_ptr()), _lib.fptr(noise),
+                                           float(noise_std), x.shape[0], _lib.stream_ptr(x.device)))
+        return x
+
+    def sample_loop(self, noise, hard_conds, guide_handle, n_extra, t_start_guide, n_guide_steps, scale_grad_by_std,
+                    noise_std_list, return_chain, use_cuda_graph):
+        """noise: [n_iters+1, B, H, D]. Returns (x [B,H,D], chain [n_iters+1, B, H, D] or None)."""
+        self.sync_params()
+        n_iters = self.n_steps + n_extra
+        S, B, H, D = noise.shape
+        assert S == n_iters + 1
+        p = _lib.LoopParams()
+        p.n_steps_without_noise = n_extra
+        p.t_start_guide = _lib.INT32_MAX if t_start_guide == float("inf") or t_start_guide >= _lib.INT32_MAX else int(
+            np.ceil(t_start_guide))
+        p.n_guide_steps = int(n_guide_steps)
+        p.scale_grad_by_std = int(bool(scale_grad_by_std))
+        ns = (C.c_float * n_iters)(*[float(v) for v in noise_std_list])
+        p.noise_std = C.cast(ns, C.POINTER(C.c_float))
+        rows = list(hard_conds.keys())  # dict order = overwrite order of apply_hard_conditioning
+        if len(rows) > _lib.MAX_HARD_CONDS:
+            raise RuntimeError(f"at most {_lib.MAX_HARD_CONDS} hard conditions are supported")
+        p.n_hard_conds = len(rows)
+        hc = None
+        if rows:
+            for k, r in enumerate(rows):
+                p.hard_cond_rows[k] = int(r) % H
+            hc = torch.stack([hard_conds[r].to(device=noise.device, dtype=torch.float32).expand(B, D) for r in rows]).contiguous()
+            p.hard_cond_vals = hc.data_ptr()
+        p.use_cuda_graph = int(bool(use_cuda_graph))
+        x_out = torch.empty((B, H, D), device=noise.device, dtype=torch.float32)
+        chain = torch.empty((S, B, H, D), device=noise.device, dtype=torch.float32) if return_chain else None
+        _lib.check(self.lib.mpdb_sample_loop(
+            self.handle, guide_handle, C.byref(p), _lib.fptr(noise), _lib.fptr(x_out),
+            _lib.fptr(chain) if chain is not None else None, B * H * D, H * D, B, _lib.stream_ptr(noise.device)))
+        # keep the host arrays referenced by the call alive until it returned (it is synchronous on the host)
+        del ns
+        return x_out, chain
+
+    def read_buffers(self, B):
+        """name -> [B, C, L] activation of the last forward (parity debugging)."""
+        out = {}
+        n = self.lib.mpdb_engine_num_buffers(self.handle)
+        for i in range(n):
+            name = C.create_string_buffer(128)
+            c, l = C.c_int32(), C.c_int32()
+            _lib.check(self.lib.mpdb_engine_buffer_info(self.handle, i, name, 128, C.byref(c), C.byref(l)))
+            t = torch.empty((B, c.value, l.value), device=self.device, dtype=torch.float32)
+            _lib.check(self.lib.mpdb_engine_read_buffer(self.handle, i, _lib.fptr(t), B, _lib.stream_ptr(self.device)))
+            out[name.value.decode()] = t
+        return out
+
+
+def _engine_for_unet(unet, device, n_steps=None, schedule=None, predict_epsilon=True, clip_denoised=True):
+    device = torch.device(device)
+    if device.type != "cuda":
+        raise RuntimeError("mpd_public_b200 has no CPU path: move the model and its inputs to a CUDA device")
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    cache = unet.__dict__.setdefault("_mpdb_engines", {})
+    if n_steps is None:
+        # stand-alone UNet call: reuse any engine of this device, else a table of 1000 time steps
+        for (d, _t, _pe, _cd), eng in cache.items():
+            if d == idx:
+                return eng
+        n_steps = unet.__dict__.get("_mpdb_default_steps", 1000)
+    key = (idx, int(n_steps), bool(predict_epsilon), bool(clip_denoised))
+    eng = cache.get(key)
+    if eng is None:
+        eng = Engine(unet, torch.device("cuda", idx), n_steps, schedule, predict_epsilon, clip_denoised)
+        cache[key] = eng
+    return eng
+
+
+# ------------------------------------------------------------------------------------------------
+class GaussianDiffusionModel(nn.Module):
+    """reference diffusion_model_base.py:46 — same constructor signature; extra kwargs are ignored
+    (inference.py:138-144 passes the UNet kwargs here as well)."""
+
+    def __init__(self, model=None, variance_schedule='exponential', n_diffusion_steps=100, clip_denoised=True,
+                 predict_epsilon=False, loss_type='l2', context_model=None, **kwargs):
+        super().__init__()
+        self.model = model
+        self.context_model = context_model
+        self.n_diffusion_steps = n_diffusion_steps
+        self.state_dim = self.model.state_dim
+
+        if variance_schedule == 'cosine':
+            betas = cosine_beta_schedule(n_diffusion_steps, s=0.008, a_min=0, a_max=0.999)
+        elif variance_schedule == 'exponential':
+            betas = exponential_beta_schedule(n_diffusion_steps, beta_start=1e-4, beta_end=1.0)
+        else:
+            raise NotImplementedError
+
+        alphas = 1. - betas
+        alphas_cumprod = torch.cumprod(alphas, axis=0)
+        alphas_cumprod_prev = torch.cat([torch.ones(1), alphas_cumprod[:-1]])
+        self.clip_denoised = clip_denoised
+        self.predict_epsilon = predict_epsilon
+
+        self.register_buffer('betas', betas)
+        self.register_buffer('alphas_cumprod', alphas_cumprod)
+        self.register_buffer('alphas_cumprod_prev', alphas_cumprod_prev)
+        self.register_buffer('sqrt_alphas_cumprod', torch.sqrt(alphas_cumprod))
+        self.register_buffer('sqrt_one_minus_alphas_cumprod', torch.sqrt(1. - alphas_cumprod))
+        self.register_buffer('log_one_minus_alphas_cumprod', torch.log(1. - alphas_cumprod))
+        self.register_buffer('sqrt_recip_alphas_cumprod', torch.sqrt(1. / alphas_cumprod))
+        self.register_buffer('sqrt_recipm1_alphas_cumprod', torch.sqrt(1. / alphas_cumprod - 1))
+        posterior_variance = betas * (1. - alphas_cumprod_prev) / (1. - alphas_cumprod)
+        self.register_buffer('posterior_variance', posterior_variance)
+        self.register_buffer('posterior_log_variance_clipped', torch.log(torch.clamp(posterior_variance, min=1e-20)))
+        self.register_buffer('posterior_mean_coef1', betas * np.sqrt(alphas_cumprod_prev) / (1. - alphas_cumprod))
+        self.register_buffer('posterior_mean_coef2', (1. - alphas_cumprod_prev) * np.sqrt(alphas) / (1. - alphas_cumprod))
+        self.use_cuda_graph = True
+        if model is not None:
+            model.__dict__["_mpdb_default_steps"] = n_diffusion_steps
+
+    # ------------------------------------------ engine ------------------------------------------#
+    def _schedule_sig(self):
+        b = self.posterior_mean_coef1
+        return (b.data_ptr(), b._version, self.sqrt_recip_alphas_cumprod._version)
+
+    def _engine(self):
+        device = self.betas.device
+        if device.type != "cuda":
+            raise RuntimeError("mpd_public_b200 has no CPU path: call .to('cuda') on the model first")
+        sched = {k: getattr(self, k) for k in (
+            'sqrt_recip_alphas_cumprod', 'sqrt_recipm1_alphas_cumprod', 'posterior_mean_coef1', 'posterior_mean_coef2',
+            'posterior_log_variance_clipped')}
+        eng = _engine_for_unet(self.model, device, self.n_diffusion_steps, sched, self.predict_epsilon, self.clip_denoised)
+        sig = self._schedule_sig()
+        if eng.__dict__.get("_sched_sig") != sig:  # buffers reloaded by load_state_dict
+            eng._set_schedule(sched)
+            eng._sched_sig = sig
+        return eng
+
+    # ------------------------------------------ sampling ------------------------------------------#
+    def predict_noise_from_start(self, x_t, t, x0):
+        if self.predict_epsilon:
+            return x0
+        return (extract(self.sqrt_recip_alphas_cumprod, t, x_t.shape) * x_t - x0) / \
+            extract(self.sqrt_recipm1_alphas_cumprod, t, x_t.shape)
+
+    def predict_start_from_noise(self, x_t, t, noise):
+        if self.predict_epsilon:
+            return (extract(self.sqrt_recip_alphas_cumprod, t, x_t.shape) * x_t -
+                    extract(self.sqrt_recipm1_alphas_cumprod, t, x_t.shape) * noise)
+        return noise
+
+    def q_posterior(self, x_start, x_t, t):
+        posterior_mean = (extract(self.posterior_mean_coef1, t, x_t.shape) * x_start +
+                          extract(self.posterior_mean_coef2, t, x_t.shape) * x_t)
+        posterior_variance = extract(self.posterior_variance, t, x_t.shape)
+        posterior_log_variance_clipped = extract(self.posterior_log_variance_clipped, t, x_t.shape)
+        return posterior_mean, posterior_variance, posterior_log_variance_clipped
+
+    @torch.no_grad()
+    def p_mean_variance(self, x, hard_conds, context, t):
+        """reference :143-155. UNet + x0 reconstruction + clamp + posterior mean run in one fused kernel chain."""
+        if context is not None:
+            raise NotImplementedError("context conditioning is not on the guided-sampling path")
+        model_mean = self._engine().p_mean(x, t)
+        posterior_variance = extract(self.posterior_variance, t, x.shape)
+        posterior_log_variance = extract(self.posterior_log_variance_clipped, t, x.shape)
+        return model_mean, posterior_variance, posterior_log_variance
+
+    @torch.no_grad()
+    def p_sample_loop(self, shape, hard_conds, context=None, return_chain=False, sample_fn=ddpm_sample_fn,
+                      n_diffusion_steps_without_noise=0, **sample_kwargs):
+        """reference :158-182."""
+        device = self.betas.device
+        if device.type != "cuda":
+            raise RuntimeError("mpd_public_b200 has no CPU path: call .to('cuda') on the model first")
+        batch_size = shape[0]
+        guide = sample_kwargs.get("guide", None)
+        fused = (sample_fn is ddpm_sample_fn and context is None
+                 and (guide is None or getattr(guide, "_mpdb_fusable", False)))
+        if fused:
+            return self._p_sample_loop_fused(shape, hard_conds, return_chain, n_diffusion_steps_without_noise,
+                                             **sample_kwargs)
+
+        # generic path: any sample_fn / any guide callable, one step at a time (still CUDA kernels underneath)
+        x = torch.randn(shape, device=device)
+        x = apply_hard_conditioning(x, hard_conds)
+        chain = [x] if return_chain else None
+        for i in reversed(range(-n_diffusion_steps_without_noise, self.n_diffusion_steps)):
+            t = make_timesteps(batch_size, i, device)
+            x, values = sample_fn(self, x, hard_conds, context, t, **sample_kwargs)
+            x = apply_hard_conditioning(x, hard_conds)
+            if return_chain:
+                chain.append(x)
+        if return_chain:
+            chain = torch.stack(chain, dim=1)
+            return x, chain
+        return x
+
+    def _p_sample_loop_fused(self, shape, hard_conds, return_chain, n_extra, guide=None, n_guide_steps=1,
+                             scale_grad_by_std=False, t_start_guide=torch.inf, noise_std_extra_schedule_fn=None,
+                             debug=False, noise=None, **kwargs):
+        device = self.betas.device
+        eng = self._engine()
+        steps = list(reversed(range(-n_extra, self.n_diffusion_steps)))
+        if noise is None:
+            # identical generator consumption to the reference: randn(shape), then one randn_like per step
+            noise = torch.empty((len(steps) + 1, *shape), device=device, dtype=torch.float32)
+            for k in range(len(steps) + 1):
+                torch.randn(shape, device=device, out=noise[k])
+        else:
+            noise = noise.to(device=device, dtype=torch.float32).contiguous()
+            if tuple(noise.shape) != (len(steps) + 1, *shape):
+                raise RuntimeError(f"injected noise must have shape {(len(steps) + 1, *shape)}")
+        if noise_std_extra_schedule_fn is None:
+            ns = [1.0] * len(steps)
+        else:
+            ns = [float(noise_std_extra_schedule_fn(torch.tensor(i, dtype=torch.long))) for i in steps]
+        tsg = float(t_start_guide)
+        handle = guide._handle(device, shape[1]) if guide is not None else None
+        x, chain = eng.sample_loop(noise, hard_conds, handle, n_extra, tsg, n_guide_steps if guide is not None else 0,
+                                   scale_grad_by_std, ns, return_chain, self.use_cuda_graph)
+        if return_chain:
+            return x, chain.transpose(0, 1)  # [B, steps+1, H, D] like torch.stack(chain, dim=1)
+        return x
+
+    @torch.no_grad()
+    def ddim_sample(self, shape, hard_conds, context=None, return_chain=False, t_start_guide=torch.inf, guide=None,
+                    n_guide_steps=1, **sample_kwargs):
+        """reference :184-259 (T/5 steps, eta = 0). UNet forward and guide steps are CUDA kernels; the few
+        per-step scalar combinations use torch elementwise ops exactly as the reference does."""
+        device = self.betas.device
+        batch_size = shape[0]
+        total_timesteps = self.n_diffusion_steps
+        sampling_timesteps = self.n_diffusion_steps // 5
+        eta = 0.
+        times = torch.linspace(0, total_timesteps - 1, steps=sampling_timesteps + 1, device=device)
+        times = torch.cat((torch.tensor([-1], device=device), times))
+        times = list(reversed(times.int().tolist()))
+        time_pairs = list(zip(times[:-1], times[1:]))
+        x = torch.randn(shape, device=device)
+        x = apply_hard_conditioning(x, hard_conds)
+        chain = [x] if return_chain else None
+        for time, time_next in time_pairs:
+            t = make_timesteps(batch_size, time, device)
+            t_next = make_timesteps(batch_size, time_next, device)
+            model_out = self.model(x, t, context)
+            x_start = self.predict_start_from_noise(x, t=t, noise=model_out)
+            pred_noise = self.predict_noise_from_start(x, t=t, x0=model_out)
+            if time_next < 0:
+                x = x_start
+                x = apply_hard_conditioning(x, hard_conds)
+                if return_chain:
+                    chain.append(x)
+                break
+            alpha = extract(self.alphas_cumprod, t, x.shape)
+            alpha_next = extract(self.alphas_cumprod, t_next, x.shape)
+            sigma = eta * ((1 - alpha / alpha_next) * (1 - alpha_next) / (1 - alpha)).sqrt()
+            c = (1 - alpha_next - sigma ** 2).sqrt()
+            x = x_start * alpha_next.sqrt() + c * pred_noise
+            if guide is not None:
+                if torch.all(t_next < t_start_guide):
+                    x = guide_gradient_steps(x, hard_conds=hard_conds, guide=guide, **sample_kwargs)
+            noise = torch.randn_like(x)
+            x = x + sigma * noise
+            x = apply_hard_conditioning(x, hard_conds)
+            if return_chain:
+                chain.append(x)
+        if return_chain:
+            chain = torch.stack(chain, dim=1)
+            return x, chain
+        return x
+
+    @torch.no_grad()
+    def conditional_sample(self, hard_conds, horizon=None, batch_size=1, ddim=False, **sample_kwargs):
+        """reference :262-272"""
+        horizon = horizon or self.model.n_support_points
+        shape = (batch_size, horizon, self.state_dim)
+        if ddim:
+            return self.ddim_sample(shape, hard_conds, **sample_kwargs)
+        return self.p_sample_loop(shape, hard_conds, **sample_kwargs)
+
+    def forward(self, cond, *args, **kwargs):
+        raise NotImplementedError  # as in the reference (:274-276)
+
+    @torch.no_grad()
+    def warmup(self, horizon=64, device='cuda'):
+        """reference :279-283"""
+        shape = (2, horizon, self.state_dim)
+        x = torch.randn(shape, device=device)
+        t = make_timesteps(2, 1, device)
+        self.model(x, t, context=None)
+
+    @torch.no_grad()
+    def run_inference(self, context=None, hard_conds=None, n_samples=1, return_chain=False, **diffusion_kwargs):
+        """reference :286-316 — returns [steps+1, n_samples, H, D] if return_chain else [n_samples, H, D]."""
+        hard_conds = copy(hard_conds)
+        context = copy(context)
+        for k, v in hard_conds.items():
+            hard_conds[k] = v.unsqueeze(0).repeat(n_samples, 1)  # einops.repeat(v, 'd -> b d', b=n_samples)
+        if context is not None:
+            for k, v in context.items():
+                context[k] = v.unsqueeze(0).repeat(n_samples, 1)
+        samples, chain = self.conditional_sample(hard_conds, context=context, batch_size=n_samples, return_chain=True,
+                                                 **diffusion_kwargs)
+        trajs_chain_normalized = chain.permute(1, 0, 2, 3)  # 'b diffsteps h d -> diffsteps b h d'
+        if return_chain:
+            return trajs_chain_normalized
+        return trajs_chain_normalized[-1]
+
+    @torch.no_grad()
+    def sample(self, hard_conds, n_samples, horizon=None, noise=None, **diffusion_kwargs):
+        """Throughput-oriented entry (not in the reference): final plans only, no chain kept."""
+        hard_conds = {k: v.unsqueeze(0).repeat(n_samples, 1) for k, v in hard_conds.items()}
+        horizon = horizon or self.model.n_support_points
+        return self.p_sample_loop((n_samples, horizon, self.state_dim), hard_conds, return_chain=False, noise=noise,
+                                  **diffusion_kwargs)

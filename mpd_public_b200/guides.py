@@ -1,0 +1,175 @@
+"""GuideManagerTrajectoriesWithVelocity — mirror of reference `mpd/models/diffusion_models/guides.py:149-236`.
+
+Same constructor arguments (including the **kwargs that swallow inference.py's misspelt
+`num_interpolated_points`) and call convention `guide(x_normalized [B,H,D]) -> grad [B,H,D]`.
+The body — unnormalise, interpolate, composite cost, one backward per cost, clip-by-norm (+1e-6),
+endpoint zeroing, weighting, negation — is one CUDA kernel with a hand-derived adjoint (csrc/guide.cu).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _lib
+from .costs import CostCollision, CostComposite, CostGPTrajectory, GridSDFField, WorkspaceBoundaryField
+
+
+def _dataset_limits(dataset):
+    """mins/maxs of the trajectory normaliser, as the reference reaches them (trajectories.py:196-197)."""
+    nz = dataset.normalizer
+    if hasattr(nz, "normalizers"):
+        nz = nz.normalizers[dataset.field_key_traj]
+    return nz.mins.detach().float().cpu().numpy(), nz.maxs.detach().float().cpu().numpy()
+
+
+class GuideManagerTrajectoriesWithVelocity(nn.Module):
+    _mpdb_fusable = True
+
+    def __init__(self, dataset, cost, clip_grad=False, clip_grad_rule='norm', max_grad_norm=1., max_grad_value=0.1,
+                 interpolate_trajectories_for_collision=False, num_interpolated_points_for_collision=128,
+                 start_state_pos=None, goal_state_pos=None, num_steps=100, robot=None, n_samples=1, tensor_args=None,
+                 **kwargs):
+        super().__init__()
+        if not isinstance(cost, CostComposite):
+            raise NotImplementedError("cost must be a mpd_public_b200.CostComposite")
+        if clip_grad and clip_grad_rule != 'norm':
+            raise NotImplementedError("only clip_grad_rule='norm' is on the inference path (guides.py:151)")
+        self.cost = cost
+        self.dataset = dataset
+        self.interpolate_trajectories_for_collision = interpolate_trajectories_for_collision
+        self.num_interpolated_points_for_collision = num_interpolated_points_for_collision
+        self.clip_grad = clip_grad
+        self.clip_grad_rule = clip_grad_rule
+        self.max_grad_norm = max_grad_norm
+        self.max_grad_value = max_grad_value
+        self._handles = {}
+
+    # ---- C-ABI handle ----
+    def _config(self, H):
+        robot = self.cost.robot
+        cfg = _lib.GuideConfig()
+        cfg.robot_kind = 1 if robot.kind == "panda" else 0
+        cfg.q_dim, cfg.ws_dim, cfg.n_spheres = robot.q_dim, robot.ws_dim, robot.n_spheres
+        for i in range(robot.n_spheres):
+            cfg.sphere_frame[i] = int(robot.sphere_frame[i])
+            for k in range(3):
+                cfg.sphere_offset[i][k] = float(robot.sphere_offset[i][k])
+            cfg.sphere_radius[i] = float(robot.sphere_radius[i])
+        mins, maxs = _dataset_limits(self.dataset)
+        if len(mins) != 2 * robot.q_dim:
+            raise RuntimeError("normaliser limits must cover [q, qdot]")
+        for i in range(len(mins)):
+            cfg.mins[i], cfg.maxs[i] = float(mins[i]), float(maxs[i])
+        keep = []  # tensors referenced by raw pointer
+        n_grid = 0
+        cfg.has_border = 0
+        cfg.use_gp = 0
+        margin = None
+        for c, w in zip(self.cost.cost_l, self.cost.weights_cost_l):
+            if isinstance(c, CostCollision):
+                f = c.field
+                m = float(getattr(c.robot, "cutoff_margin", 0.05) if getattr(c, "cutoff_margin", None) is None else c.cutoff_margin)
+                margin = m if margin is None else margin
+                if isinstance(f, GridSDFField):
+                    if n_grid >= _lib.MAX_GRID_FIELDS:
+                        raise RuntimeError(f"at most {_lib.MAX_GRID_FIELDS} grid-backed collision fields")
+                    if n_grid == 0:
+                        for k in range(f.dim):
+                            cfg.grid_shape[k] = f.shape[k]
+                            cfg.grid_lo[k] = float(f.limits[0][k])
+                        cfg.grid_cell = f.cell
+                    elif tuple(cfg.grid_shape[:f.dim]) != f.shape or abs(cfg.grid_cell - f.cell) > 0:
+                        raise NotImplementedError("all grid fields must share one lattice")
+                    cfg.grid_texels[n_grid] = f.texels.data_ptr()
+                    cfg.weight_grid[n_grid] = float(w)
+                    keep.append(f.texels)
+                    n_grid += 1
+                elif isinstance(f, WorkspaceBoundaryField):
+                    if cfg.has_border:
+                        raise NotImplementedError("one workspace-boundary field")
+                    cfg.has_border = 1
+                    for k in range(f.limits.shape[1]):
+                        cfg.border_lo[k], cfg.border_hi[k] = float(f.limits[0][k]), float(f.limits[1][k])
+                    cfg.weight_border = float(w)
+                else:
+                    raise NotImplementedError(f"unsupported field {type(f).__name__}")
+            elif isinstance(c, CostGPTrajectory):
+                cfg.use_gp = 1
+                cfg.dt, cfg.sigma_gp, cfg.weight_gp = c.dt, c.sigma_gp, float(w)
+        cfg.n_grid_fields = n_grid
+        cfg.cutoff_margin = 0.05 if margin is None else margin
+        if not cfg.use_gp:
+            cfg.dt, cfg.sigma_gp = 1.0, 1.0
+        cfg.clip_grad = int(bool(self.clip_grad))
+        cfg.max_grad_norm = float(self.max_grad_norm)
+        cfg.n_interp = int(self.num_interpolated_points_for_collision) if self.interpolate_trajectories_for_collision else int(H)
+        return cfg, keep
+
+    def _handle(self, device, H):
+        device = torch.device(device)
+        idx = device.index if device.index is not None else torch.cuda.current_device()
+        key = (idx, int(H))
+        h = self._handles.get(key)
+        if h is None:
+            cfg, keep = self._config(H)
+            for t in keep:
+                if t.device.index != idx:
+                    raise RuntimeError("collision grids live on a different device than the trajectories")
+            handle = C.c_void_p()
+            _lib.check(_lib.lib().mpdb_guide_create(C.byref(cfg), idx, C.byref(handle)))
+            h = (handle, keep, cfg)
+            self._handles[key] = h
+        return h[0]
+
+    def __del__(self):
+        try:
+            for handle, _, _ in self._handles.values():
+                _lib.lib().mpdb_guide_destroy(handle)
+            self._handles = {}
+        except Exception:
+            pass
+
+    # ---- reference interface ----
+    def forward(self, x_normalized):
+        _lib.require_cuda(x_normalized, "x_normalized")
+        x = x_normalized.detach().to(torch.float32).contiguous()
+        B, H, D = x.shape
+        grad = torch.empty_like(x)
+        _lib.check(_lib.lib().mpdb_guide_grad(self._handle(x.device, H), _lib.fptr(x), _lib.fptr(grad), B, H,
+                                              _lib.stream_ptr(x.device)))
+        return grad
+
+    def guide_steps(self, x, hard_conds, n_guide_steps, model_var=None):
+        """n x {x <- x + guide(x) [* model_var]; hard conditioning} as n kernel launches; returns a new tensor."""
+        _lib.require_cuda(x, "x")
+        x = x.detach().to(torch.float32).clone(memory_format=torch.contiguous_format)
+        B, H, D = x.shape
+        rows = list(hard_conds.keys())
+        hc_rows = (C.c_int32 * max(len(rows), 1))(*[int(r) % H for r in rows])
+        hc = torch.stack([hard_conds[r].to(device=x.device, dtype=torch.float32).expand(B, D) for r in rows]).contiguous() \
+            if rows else None
+        mv = None
+        if model_var is not None:
+            mv = model_var.to(device=x.device, dtype=torch.float32).reshape(-1).expand(B).contiguous()
+        _lib.check(_lib.lib().mpdb_guide_steps(
+            self._handle(x.device, H), _lib.fptr(x), int(n_guide_steps), _lib.fptr(mv) if mv is not None else None,
+            len(rows), hc_rows, _lib.fptr(hc) if hc is not None else None, B, H, _lib.stream_ptr(x.device)))
+        return x
+
+    def clip_gradient(self, grad):
+        if self.clip_grad:
+            if self.clip_grad_rule == 'norm':
+                return self.clip_grad_by_norm(grad)
+            raise NotImplementedError
+        return grad
+
+    def clip_grad_by_norm(self, grad):
+        """reference :224-230 (torch ops; the fused kernel applies the same rule per cost)."""
+        if self.clip_grad:
+            grad_norm = torch.linalg.norm(grad + 1e-6, dim=-1, keepdims=True)
+            scale_ratio = torch.clip(grad_norm, 0., self.max_grad_norm) / grad_norm
+            grad = scale_ratio * grad
+        return grad

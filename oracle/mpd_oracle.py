@@ -74,19 +74,24 @@ def conv1d_block(sd, p, x):
     return F.mish(y)
 
 
-def residual_temporal_block(sd, p, x, c_emb):
+def residual_temporal_block(sd, p, x, c_emb, capture=None):
     """reference layers.py:343-355."""
     cond = F.linear(F.mish(c_emb), sd[p + ".cond_mlp.1.weight"], sd[p + ".cond_mlp.1.bias"])
     h = conv1d_block(sd, p + ".blocks.0", x) + cond[:, :, None]
+    if capture is not None:
+        capture[p + ".blocks.0"] = h
     h = conv1d_block(sd, p + ".blocks.1", h)
     if (p + ".residual_conv.weight") in sd:
         res = F.conv1d(x, sd[p + ".residual_conv.weight"], sd[p + ".residual_conv.bias"])
     else:
         res = x
-    return h + res
+    out = h + res
+    if capture is not None:
+        capture[p] = out
+    return out
 
 
-def unet_forward(sd, x, t, n_levels=None):
+def unet_forward(sd, x, t, n_levels=None, capture=None):
     """ε = TemporalUnet(x [B,H,D], t [B]) with conditioning_type=None, self_attention=False.
 
     `sd`: TemporalUnet state-dict (no 'model.' prefix) of torch tensors.
@@ -98,19 +103,25 @@ def unet_forward(sd, x, t, n_levels=None):
     x = x.transpose(1, 2)  # b h c -> b c h  (temporal_unet.py:138)
     skips = []
     for i in range(n_levels):
-        x = residual_temporal_block(sd, f"downs.{i}.0", x, c_emb)
-        x = residual_temporal_block(sd, f"downs.{i}.1", x, c_emb)
+        x = residual_temporal_block(sd, f"downs.{i}.0", x, c_emb, capture)
+        x = residual_temporal_block(sd, f"downs.{i}.1", x, c_emb, capture)
         skips.append(x)
         if i < n_levels - 1:
             x = F.conv1d(x, sd[f"downs.{i}.4.conv.weight"], sd[f"downs.{i}.4.conv.bias"], stride=2, padding=1)
-    x = residual_temporal_block(sd, "mid_block1", x, c_emb)
-    x = residual_temporal_block(sd, "mid_block2", x, c_emb)
+            if capture is not None:
+                capture[f"downs.{i}.4"] = x
+    x = residual_temporal_block(sd, "mid_block1", x, c_emb, capture)
+    x = residual_temporal_block(sd, "mid_block2", x, c_emb, capture)
     for i in range(n_levels - 1):
         x = torch.cat((x, skips.pop()), dim=1)
-        x = residual_temporal_block(sd, f"ups.{i}.0", x, c_emb)
-        x = residual_temporal_block(sd, f"ups.{i}.1", x, c_emb)
+        x = residual_temporal_block(sd, f"ups.{i}.0", x, c_emb, capture)
+        x = residual_temporal_block(sd, f"ups.{i}.1", x, c_emb, capture)
         x = F.conv_transpose1d(x, sd[f"ups.{i}.4.conv.weight"], sd[f"ups.{i}.4.conv.bias"], stride=2, padding=1)
+        if capture is not None:
+            capture[f"ups.{i}.4"] = x
     x = conv1d_block(sd, "final_conv.0", x)
+    if capture is not None:
+        capture["final_conv.0"] = x
     x = F.conv1d(x, sd["final_conv.1.weight"], sd["final_conv.1.bias"])
     return x.transpose(1, 2)
 

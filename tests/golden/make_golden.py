@@ -109,8 +109,19 @@ def gen_guide_and_steps():
         save(f"guided_{case}", **out)
 
 
+def gen_state_dict_keys():
+    import json
+    out = {}
+    for case in C.UNET_CASES:
+        out[case] = {k: list(v.shape) for k, v in ref_model(case).state_dict().items()}
+    path = os.path.join(HERE, "state_dict_keys.json")
+    json.dump(out, open(path, "w"))
+    print(f"wrote {path}")
+
+
 if __name__ == "__main__":
     assert ref_shim.available(), "reference tree not present"
+    gen_state_dict_keys()
     gen_schedule()
     gen_unet()
     gen_normalizer()
