@@ -1,0 +1,402 @@
+#!/usr/bin/env python
+"""bench.py — trajectories/s of the full guided p_sample_loop (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg4|cfg2|cfg5]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+A "step" = one complete guided reverse loop (T=25 + 5 noiseless steps = 30 UNet forwards, 60 guide
+evaluations; inference.py:49-60 defaults) over one batch of synthetic start/goal problems. The default
+workload is BASELINE config 4, EnvSpheres3D-RobotPanda, H=64, B=100 per GPU (weak scaling: N GPUs sample
+N*100 trajectories and all-gather the plans). Prints ONE JSON line on rank 0.
+
+`--impl reference` times the CPU restatement of the reference path (oracle/, PyTorch CPU, all host
+threads) on the same workload; the reference itself is Python whose cost/robot dependencies are absent
+(SURVEY §0.2), so it cannot travel to the GPU box — the oracle port is pinned to it by the golden vectors.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np
+import torch
+
+METRIC = "trajectories/sec full guided p_sample_loop"
+UNIT = "trajectories/s"
+
+WORKLOADS = {
+    # name: (model id, H, B per GPU, dim_mults option, w_collision, w_smoothness)   (BASELINE.json configs)
+    "cfg4": ("EnvSpheres3D-RobotPanda", 64, 100, 1, 1e-2, 1e-7),
+    "cfg2": ("EnvDense2D-RobotPointMass", 64, 100, 1, 3e-2, 1e-2),
+    "cfg5": ("EnvSpheres3D-RobotPanda", 128, 512, 1, 1e-2, 1e-7),
+}
+T_DIFF, N_EXTRA, N_GUIDE, T_START_GUIDE, NOISE_STD, N_INTERP = 25, 5, 5, 7, 0.5, 128
+
+
+def workload_config(name, n_gpus):
+    mid, H, B, opt, wc, ws = WORKLOADS[name]
+    return {"workload": f"{mid} H={H} B={B}/GPU guided p_sample_loop (T=25+5, n_guide_steps=5, t_start_guide=7, "
+                        f"128 interp points, dim_mults option {opt})",
+            "model_id": mid, "horizon": H, "batch_per_gpu": B, "global_batch": B * n_gpus,
+            "parallelism": f"batch-sharded x{n_gpus}, one final all-gather" if n_gpus > 1 else "single GPU",
+            "weights": "seeded synthetic (reference state-dict layout)", "l2_flush": "256 MiB memset between timed steps",
+            "precision": "fp32 end to end"}
+
+
+# ---------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index, period=0.1):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons, self.max_mhz, self.power = [], set(), None, []
+        self._stop = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception as e:  # pragma: no cover
+            self.err = str(e)
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake_slowdown",
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+                self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+            except Exception:
+                pass
+            self._stop.wait(self.period)
+
+    def stop(self):
+        self._stop.set()
+        self.join(timeout=2)
+        if not self.ok or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "note": "NVML unavailable"}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples), "power_w_max": max(self.power) if self.power else None}
+
+
+# ---------------------------------------------------------------------------------------------------
+def algorithmic_work(H, D, opt, L_spheres, n_grid_fields, ws_dim):
+    """UNet FLOPs per trajectory per forward (2*MAC of every conv/linear) and SDF-gradient
+    bytes per trajectory per guide evaluation."""
+    from mpd_public_b200.synthetic import UNET_DIM_MULTS, unet_param_shapes
+    mults = UNET_DIM_MULTS[opt]
+    dims = [D] + [32 * m for m in mults]
+    n = len(mults)
+    flops = 0.0
+    L = H
+    def rtb(cin, cout, L):
+        f = 2 * L * cout * cin * 5 + 2 * L * cout * cout * 5 + 2 * 32 * cout
+        if cin != cout:
+            f += 2 * L * cout * cin
+        return f
+    for i in range(n):
+        flops += rtb(dims[i], dims[i + 1], L) + rtb(dims[i + 1], dims[i + 1], L)
+        if i < n - 1:
+            flops += 2 * (L // 2) * dims[i + 1] * dims[i + 1] * 3
+            L //= 2
+    flops += 2 * rtb(dims[n], dims[n], L)
+    for i in range(n - 1):
+        lv = n - 1 - i
+        cin, cout = dims[lv], dims[lv + 1]
+        flops += rtb(2 * cout, cin, L) + rtb(cin, cin, L)
+        flops += 2 * L * cin * cin * 4
+        L *= 2
+    flops += 2 * L * 32 * 32 * 5 + 2 * L * D * 32
+    flops += 2 * (32 * 128 + 128 * 32)  # time MLP
+    texel = 16 if ws_dim == 3 else 12
+    sdf_bytes = 2 * H * D * 4 + n_grid_fields * N_INTERP * L_spheres * texel
+    return flops, sdf_bytes
+
+
+def build_problem(name, device):
+    """Model + guide + hard conditions for a workload, the way inference.py:127-245 builds them."""
+    import mpd_public_b200 as M
+    from mpd_public_b200 import synthetic as S
+    mid, H, B, opt, wc, ws = WORKLOADS[name]
+    prob = S.make_problem_by_id(mid, H)
+    D = prob.robot.state_dim
+    sd = S.make_unet_state_dict(0, D, 32, S.UNET_DIM_MULTS[opt])
+    import contextlib, io
+    with contextlib.redirect_stdout(io.StringIO()):
+        unet = M.TemporalUnet(n_support_points=H, state_dim=D, unet_input_dim=32, dim_mults=S.UNET_DIM_MULTS[opt])
+    model = M.GaussianDiffusionModel(model=unet, variance_schedule="exponential", n_diffusion_steps=T_DIFF, predict_epsilon=True)
+    model.load_state_dict({"model." + k: torch.as_tensor(v) for k, v in sd.items()}, strict=False)
+    model = model.to(device).eval()
+    ds = M.TrajectoryDataset(prob, device)
+    robot = ds.robot
+    fields = ds.task.get_collision_fields()
+    costs = [M.CostCollision(robot, H, field=f, sigma_coll=1.0) for f in fields]
+    weights = [wc] * len(costs)
+    costs.append(M.CostGPTrajectory(robot, H, prob.dt, sigma_gp=1.0))
+    weights.append(ws)
+    guide = M.GuideManagerTrajectoriesWithVelocity(ds, M.CostComposite(robot, H, costs, weights_cost_l=weights),
+                                                   clip_grad=True, interpolate_trajectories_for_collision=True,
+                                                   num_interpolated_points=int(np.ceil(H * 1.5)))  # swallowed, as upstream
+    n_grid = sum(hasattr(f, "texels") for f in fields)
+    return model, guide, ds, prob, sd, n_grid
+
+
+def sample_kwargs(guide):
+    import mpd_public_b200 as M
+    return dict(sample_fn=M.ddpm_sample_fn, guide=guide, n_guide_steps=N_GUIDE, t_start_guide=T_START_GUIDE,
+                noise_std_extra_schedule_fn=lambda _t: NOISE_STD, n_diffusion_steps_without_noise=N_EXTRA)
+
+
+# ---------------------------------------------------------------------------------------------------
+def cpu_oracle_runner(name, threads):
+    """Returns (fn() -> seconds for one full guided loop at the workload's batch, description)."""
+    from mpd_public_b200 import synthetic as S
+    from oracle import mpd_oracle as O
+    mid, H, B, opt, wc, ws = WORKLOADS[name]
+    torch.set_num_threads(threads)
+    prob = S.make_problem_by_id(mid, H)
+    D = prob.robot.state_dim
+    sd = S.make_unet_state_dict(0, D, 32, S.UNET_DIM_MULTS[opt])
+    om = O.OracleDiffusion(sd, n_diffusion_steps=T_DIFF)
+    spec = O.make_guide_spec(prob, wc, ws)
+    hard = O.hard_conditions(prob)
+    hc = {k: v[None].repeat(B, 1) for k, v in hard.items()}
+    gen = torch.Generator().manual_seed(3)
+    noise = torch.randn((T_DIFF + N_EXTRA + 1, B, H, D), generator=gen)
+
+    def run():
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            om.p_sample_loop((B, H, D), hc, noise=noise, n_diffusion_steps_without_noise=N_EXTRA,
+                             guide=lambda z: O.guide_manager_grad(spec, z), n_guide_steps=N_GUIDE,
+                             t_start_guide=T_START_GUIDE, noise_std_fn=lambda _t: NOISE_STD)
+        return time.perf_counter() - t0
+    return run, B
+
+
+def run_reference_arm(args):
+    """CPU arm: the oracle port of the reference path on all host threads; rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    run, B = cpu_oracle_runner(args.workload, threads)
+    for _ in range(min(args.warmup, 1)):
+        run()
+    steps = max(1, min(args.steps, 10))  # bounded: each step is a full CPU loop (seconds)
+    times = [run() for _ in range(steps)]
+    total = sum(times)
+    value = B * steps / total
+    cfg = workload_config(args.workload, 1)
+    out = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+           "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * total / steps, "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
+           "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                            "sample": f"{steps} full guided loop(s) at B={B} (same workload), PyTorch CPU eager, "
+                                      f"{threads} threads; requested steps capped at 10"},
+           "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
+    print(json.dumps(out), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg4", choices=list(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true")
+    args = ap.parse_args()
+
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    import torch.distributed as dist
+    from mpd_public_b200 import _lib
+    from mpd_public_b200.parallel import allgather_plans
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py (impl=ours) needs a CUDA device: there is no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=device)
+    n_gpus = world
+    W = max(args.warmup, 3)
+    K = max(args.steps, 1)
+
+    mid, H, B, opt, wc, ws = WORKLOADS[args.workload]
+    model, guide, ds, prob, sd, n_grid = build_problem(args.workload, device)
+    model.use_cuda_graph = not args.no_graph
+    D = prob.robot.state_dim
+    kw = sample_kwargs(guide)
+    start_goal_host = torch.vstack((torch.as_tensor(prob.start), torch.as_tensor(prob.goal))).pin_memory()
+    hard = ds.get_hard_conditions(start_goal_host.to(device), normalize=True)
+    n_iters = T_DIFF + N_EXTRA
+    torch.manual_seed(1234 + rank)
+    noise = torch.randn((n_iters + 1, B, H, D), device=device)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
+    n_total = B * n_gpus
+
+    def step_resident():
+        """Inputs (noise, hard conditions) already in HBM."""
+        x = model.sample(hard, B, noise=noise, **kw)
+        return allgather_plans(x, n_total) if world > 1 else x
+
+    out_host = torch.empty((n_total, H, D), dtype=torch.float32).pin_memory()
+
+    def step_e2e():
+        """The public call a user makes (inference.py:248-257): start/goal from pinned host memory, noise drawn
+        by the API on the device exactly as the reference does, plans read back to the host."""
+        sg = start_goal_host.to(device, non_blocking=True)
+        hc = ds.get_hard_conditions(sg, normalize=True)
+        x = model.run_inference(None, hc, n_samples=B, horizon=H, return_chain=False, **kw)
+        if world > 1:
+            x = allgather_plans(x, n_total)
+        out_host.copy_(x, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return out_host
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, k_steps, sampler=None):
+        barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if sampler:
+            sampler.start()
+        ev0.record()
+        for _ in range(k_steps):
+            flush.zero_()
+            fn()
+        ev1.record()
+        barrier()
+        ms = ev0.elapsed_time(ev1)
+        if world > 1:
+            t = torch.tensor([ms], device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    for _ in range(W):
+        step_resident()
+    launches0 = _lib.launch_count()
+    sampler = ClockSampler(local_rank)
+    ms_total = timed(step_resident, K, sampler)
+    clocks = sampler.stop()
+    launches = _lib.launch_count() - launches0
+    value = n_total * K / (ms_total / 1e3)
+
+    for _ in range(2):
+        step_e2e()
+    ms_e2e = timed(step_e2e, K)
+    e2e_value = n_total * K / (ms_e2e / 1e3)
+
+    result = None
+    if rank == 0:
+        # ---- roofline of the dominant kernel: per-layer CUDA-event timing of one UNet forward ----
+        lib = _lib.lib()
+        eng = model._engine()
+        n_ops = lib.mpdb_engine_num_ops(eng.handle)
+        ms = (C.c_float * n_ops)()
+        fl = (C.c_double * n_ops)()
+        md = (C.c_int32 * n_ops)()
+        x0 = noise[0].contiguous()
+        _lib.check(lib.mpdb_profile_forward(eng.handle, _lib.fptr(x0), 5, B, 20, ms, fl, md, _lib.stream_ptr(device)))
+        ms, fl, md = np.array(ms[:]), np.array(fl[:]), np.array(md[:])
+        conv5 = md == 0
+        fwd_ms = float(ms.sum())
+        conv5_ms, conv5_flops = float(ms[conv5].sum()), float(fl[conv5].sum())
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
+        peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)"
+        ach_tf = conv5_flops / (conv5_ms * 1e-3) / 1e12
+        flops_traj, sdf_bytes = algorithmic_work(H, D, opt, prob.robot.n_spheres, n_grid, prob.robot.ws_dim)
+        roofline = {"kernel": "mpdb::conv_kernel<MODE_CONV5> (Conv1d k5 + GroupNorm + Mish [+cond][+residual]), "
+                              f"{int(conv5.sum())} launches per UNet forward",
+                    "bound": "tensor", "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach_tf / peak_tf,
+                    "traffic": None, "peak_source": peak_src,
+                    "note": "fp32 CUDA-core FMA kernel (exact fp32 parity path); achieved = algorithmic 2*MAC FLOPs of "
+                            "its launches / their summed CUDA-event time; share of one UNet forward "
+                            f"{conv5_ms / fwd_ms:.3f}",
+                    "unet_forward_ms": fwd_ms, "unet_flops_per_trajectory_per_forward": flops_traj}
+        # guide kernel (HBM-bound by construction; at B=100 it is latency-bound)
+        gms = C.c_float()
+        xg = noise[1].clamp(-1, 1).contiguous()
+        _lib.check(lib.mpdb_profile_guide(guide._handle(device, H), _lib.fptr(xg), B, H, 50, C.byref(gms),
+                                          _lib.stream_ptr(device)))
+        peak_hbm = float(peaks.get("hbm_gbs", 6650.0))
+        ach_gbs = sdf_bytes * B / (gms.value * 1e-3) / 1e9
+        roofline_sdf = {"kernel": "mpdb::guide_step_kernel (unnormalise+interp+FK+SDF lookup+adjoint+clip+GP stencil+update)",
+                        "bound": "hbm", "achieved": ach_gbs, "peak": peak_hbm, "unit": "GB/s", "frac": ach_gbs / peak_hbm,
+                        "traffic": None, "ms_per_launch": gms.value, "bytes_per_trajectory": sdf_bytes}
+
+        cfg = workload_config(args.workload, n_gpus)
+        result = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": K, "warmup": W,
+                  "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                  "dtype": "f32", "data": "synthetic", "config": cfg, "clocks": clocks,
+                  "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / K,
+                          "h2d_bytes_per_step": int(start_goal_host.numel() * 4),
+                          "d2h_bytes_per_step": int(n_total * H * D * 4),
+                          "note": "run_inference() with start/goal from pinned host memory, noise drawn on the device by "
+                                  "the API as in the reference (diffusion_model_base.py:165), plans copied to pinned host"},
+                  "gpu_launches": int(launches), "roofline": roofline, "roofline_sdf": roofline_sdf,
+                  "cuda_graph": bool(model.use_cuda_graph)}
+        if n_gpus == 1 and not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            run, Bc = cpu_oracle_runner(args.workload, threads)
+            t = run()
+            result["cpu_baseline"] = {"value": Bc / t, "unit": UNIT, "cores": threads, "kind": "port",
+                                      "sample": f"1 full guided loop at B={Bc} (the same workload), oracle port of the "
+                                                f"reference path, PyTorch CPU eager fp32, {threads} threads, {t:.2f} s"}
+        print(json.dumps(result), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

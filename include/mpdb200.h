@@ -121,6 +121,15 @@ int mpdb_sample_loop(mpdb_engine* e, mpdb_guide* g, const mpdb_loop_params* p, c
 /* kernels launched by this engine/guide pair since creation (bench.py's gpu_launches) */
 int64_t mpdb_launch_count(void);
 
+/* measurement (bench.py's roofline object): per-layer device time of one UNet forward at uniform t, CUDA
+ * events on `stream`; arrays hold mpdb_engine_num_ops(e) entries (mode 0..3 = conv5/conv1/down/up, 4 = fused
+ * final projection + posterior mean). */
+int mpdb_engine_num_ops(mpdb_engine* e);
+int mpdb_profile_forward(mpdb_engine* e, const float* x, int32_t t, int32_t B, int32_t reps, float* ms_out,
+                         double* flops_out, int32_t* mode_out, void* stream);
+/* average device time of one guide evaluation on x (in place), CUDA events on `stream` */
+int mpdb_profile_guide(mpdb_guide* g, float* x, int32_t B, int32_t H, int32_t reps, float* ms_out, void* stream);
+
 /* debugging / parity: intermediate activations of the last mpdb_unet_forward */
 int mpdb_engine_num_buffers(mpdb_engine* e);
 int mpdb_engine_buffer_info(mpdb_engine* e, int idx, char* name, int name_cap, int32_t* channels, int32_t* length);

@@ -91,6 +91,7 @@ struct mpdb_engine {
     int loop_batch = 0;
     // CUDA graph cache for the fused loop
     cudaGraphExec_t graph_exec = nullptr;
+    long long graph_kernels = 0;  // kernel nodes in the captured loop
     std::string graph_key;
     float* g_noise = nullptr;   // staging owned by the engine (stable addresses for the graph)
     float* g_hc = nullptr;
@@ -302,26 +303,45 @@ static ConvSrc make_src(mpdb_engine* e, int id0, int id1, const float* x_ext, in
     return s;
 }
 
+static int launch_op(mpdb_engine* e, const ConvOp& op, const float* x, const long long* t_dev, int t_uniform, int B,
+                     cudaStream_t st) {
+    ConvArgs a;
+    memset(&a, 0, sizeof(a));
+    a.in = make_src(e, op.in0, op.in1, x, op.L_in);
+    a.w = e->packed + op.w;
+    a.bias = e->packed + op.bias;
+    if (op.gn) { a.gamma = e->packed + op.gamma; a.beta = e->packed + op.beta; }
+    if (op.cond >= 0) { a.cond = e->packed + op.cond; a.t_dev = t_dev; a.t_uniform = t_uniform; }
+    if (op.res0 != -2) {
+        a.res = make_src(e, op.res0, op.res1, x, op.L_out);
+        if (op.res_w >= 0) { a.res_w = e->packed + op.res_w; a.res_bias = e->packed + op.res_bias; }
+    }
+    a.out = const_cast<float*>(buf_ptr(e, op.out, e->work_batch));
+    a.CO = op.CO; a.L_out = op.L_out; a.B = B; a.gs = op.gs;
+    choose_tile(B, op.L_out, op.CO, op.gn ? op.gs : 4, &a.S, &a.NT);
+    return launch_conv(op.mode, a, st);
+}
+
 // Runs every layer up to (and including) final_conv.0; the 1x1 projection is fused into launch_final.
 static int run_unet_body(mpdb_engine* e, const float* x, const long long* t_dev, int t_uniform, int B, cudaStream_t st) {
-    for (const ConvOp& op : e->ops) {
-        ConvArgs a;
-        memset(&a, 0, sizeof(a));
-        a.in = make_src(e, op.in0, op.in1, x, op.L_in);
-        a.w = e->packed + op.w;
-        a.bias = e->packed + op.bias;
-        if (op.gn) { a.gamma = e->packed + op.gamma; a.beta = e->packed + op.beta; }
-        if (op.cond >= 0) { a.cond = e->packed + op.cond; a.t_dev = t_dev; a.t_uniform = t_uniform; }
-        if (op.res0 != -2) {
-            a.res = make_src(e, op.res0, op.res1, x, op.L_out);
-            if (op.res_w >= 0) { a.res_w = e->packed + op.res_w; a.res_bias = e->packed + op.res_bias; }
-        }
-        a.out = const_cast<float*>(buf_ptr(e, op.out, e->work_batch));
-        a.CO = op.CO; a.L_out = op.L_out; a.B = B; a.gs = op.gs;
-        choose_tile(B, op.L_out, op.CO, op.gn ? op.gs : 4, &a.S, &a.NT);
-        if (launch_conv(op.mode, a, st)) return 1;
-    }
+    for (const ConvOp& op : e->ops)
+        if (launch_op(e, op, x, t_dev, t_uniform, B, st)) return 1;
     return 0;
+}
+
+static double op_flops(mpdb_engine* e, const ConvOp& op, int B) {
+    auto chans = [&](int id0, int id1) {
+        int c = 0;
+        if (id0 == -1) c += e->cfg.state_dim; else if (id0 >= 0) c += e->bufs[id0].C;
+        if (id1 >= 0) c += e->bufs[id1].C;
+        return c;
+    };
+    const int cin = chans(op.in0, op.in1);
+    double f;
+    if (op.mode == MODE_UP) f = 2.0 * B * op.L_in * op.CO * (double)cin * 4;       // every input feeds 4 taps
+    else f = 2.0 * B * op.L_out * op.CO * (double)cin * (op.mode == MODE_CONV5 ? 5 : op.mode == MODE_DOWN ? 3 : 1);
+    if (op.res_w >= 0) f += 2.0 * B * op.L_out * op.CO * (double)chans(op.res0, op.res1);
+    return f;
 }
 
 static void fill_final(mpdb_engine* e, FinalArgs& f, const float* x, const long long* t_dev, int t_uniform, int B) {
@@ -645,6 +665,7 @@ extern "C" int mpdb_sample_loop(mpdb_engine* e, mpdb_guide* g, const mpdb_loop_p
         MPDB_CHECK_CUDA(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
         cudaGraph_t graph = nullptr;
         MPDB_CHECK_CUDA(cudaStreamBeginCapture(cs, cudaStreamCaptureModeRelaxed));
+        const long long launches_before = mpdb::g_launch_count.load();
         int rc = enqueue_loop(e, g, p, e->g_noise, e->g_hc, e->xbuf[(n_iters) & 1] /* placeholder, fixed below */,
                               chain_out ? e->g_chain : nullptr, n, (long long)H * D, B, cs);
         cudaError_t ce = cudaStreamEndCapture(cs, &graph);
@@ -663,13 +684,15 @@ extern "C" int mpdb_sample_loop(mpdb_engine* e, mpdb_guide* g, const mpdb_loop_p
             return 1;
         }
         e->graph_key = key;
+        e->graph_kernels = mpdb::g_launch_count.load() - launches_before;
+        mpdb::g_launch_count.store(launches_before);  // capture enqueued nothing; replays are counted below
     }
     MPDB_CHECK_CUDA(cudaMemcpyAsync(e->g_noise, noise, sizeof(float) * (size_t)noise_floats, cudaMemcpyDeviceToDevice, st));
     if (hc_floats > 0)
         MPDB_CHECK_CUDA(cudaMemcpyAsync(e->g_hc, p->hard_cond_vals, sizeof(float) * (size_t)hc_floats,
                                         cudaMemcpyDeviceToDevice, st));
     MPDB_CHECK_CUDA(cudaGraphLaunch(e->graph_exec, st));
-    mpdb::g_launch_count.fetch_add(0);
+    mpdb::g_launch_count.fetch_add(e->graph_kernels);
     // result: the captured loop wrote its last step into xbuf[n_iters & 1]
     MPDB_CHECK_CUDA(cudaMemcpyAsync(x_out, e->xbuf[(n_iters) & 1], sizeof(float) * (size_t)n, cudaMemcpyDeviceToDevice, st));
     if (chain_out) {
@@ -708,4 +731,55 @@ extern "C" int mpdb_engine_read_buffer(mpdb_engine* e, int idx, float* dev_out, 
     MPDB_CHECK_CUDA(cudaSetDevice(e->device));
     return launch_cm_to_bcl(buf_ptr(e, idx, e->work_batch), dev_out, B, e->bufs[idx].C, e->bufs[idx].L,
                             (cudaStream_t)stream);
+}
+
+// Per-layer device timing of one UNet forward (CUDA events on `stream`), for bench.py's roofline object.
+// ms_out/flops_out/mode_out: arrays of at least mpdb_engine_num_ops(e) entries (ops + the fused final kernel,
+// which is reported with mode 4).
+extern "C" int mpdb_engine_num_ops(mpdb_engine* e) { return e ? (int)e->ops.size() + 1 : 0; }
+
+extern "C" int mpdb_profile_forward(mpdb_engine* e, const float* x, int32_t t, int32_t B, int32_t reps, float* ms_out,
+                                    double* flops_out, int32_t* mode_out, void* stream) {
+    MPDB_REQUIRE(e && x && ms_out && flops_out && mode_out && B > 0 && reps > 0, "mpdb_profile_forward: bad argument");
+    MPDB_REQUIRE(e->finalized, "engine not finalized");
+    cudaStream_t st = (cudaStream_t)stream;
+    MPDB_CHECK_CUDA(cudaSetDevice(e->device));
+    if (ensure_workspace(e, B)) return 1;
+    cudaEvent_t ev0, ev1;
+    MPDB_CHECK_CUDA(cudaEventCreate(&ev0));
+    MPDB_CHECK_CUDA(cudaEventCreate(&ev1));
+    if (run_unet_body(e, x, nullptr, t, B, st)) return 1;  // warm-up, fills every buffer
+    int k = 0;
+    for (const ConvOp& op : e->ops) {
+        MPDB_CHECK_CUDA(cudaEventRecord(ev0, st));
+        for (int r = 0; r < reps; ++r)
+            if (launch_op(e, op, x, nullptr, t, B, st)) return 1;
+        MPDB_CHECK_CUDA(cudaEventRecord(ev1, st));
+        MPDB_CHECK_CUDA(cudaEventSynchronize(ev1));
+        float ms = 0.f;
+        MPDB_CHECK_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
+        ms_out[k] = ms / reps;
+        flops_out[k] = op_flops(e, op, B);
+        mode_out[k] = op.mode;
+        ++k;
+    }
+    {
+        FinalArgs f;
+        fill_final(e, f, x, nullptr, t, B);
+        f.mode = 1;
+        f.out = e->xbuf[1];
+        MPDB_CHECK_CUDA(cudaEventRecord(ev0, st));
+        for (int r = 0; r < reps; ++r)
+            if (launch_final(f, st)) return 1;
+        MPDB_CHECK_CUDA(cudaEventRecord(ev1, st));
+        MPDB_CHECK_CUDA(cudaEventSynchronize(ev1));
+        float ms = 0.f;
+        MPDB_CHECK_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
+        ms_out[k] = ms / reps;
+        flops_out[k] = 2.0 * B * e->cfg.horizon * e->cfg.state_dim * (double)e->cfg.unet_input_dim;
+        mode_out[k] = 4;
+    }
+    cudaEventDestroy(ev0);
+    cudaEventDestroy(ev1);
+    return 0;
 }

@@ -556,3 +556,33 @@ extern "C" int mpdb_sdf_grid_build(int32_t dim, const int32_t* shape, const floa
     MPDB_CHECK_CUDA(e2);
     return 0;
 }
+
+// Average device time of one guide evaluation (CUDA events on `stream`), for bench.py's roofline object.
+extern "C" int mpdb_profile_guide(mpdb_guide* g, float* x, int32_t B, int32_t H, int32_t reps, float* ms_out, void* stream) {
+    MPDB_REQUIRE(g && x && ms_out && B > 0 && H > 1 && reps > 0, "mpdb_profile_guide: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    MPDB_CHECK_CUDA(cudaSetDevice(g->device));
+    if (guide_launch_flag(x, (long long)B * H * 2 * g->cfg.q_dim, g->flags, st)) return 1;
+    GuideStepArgs a;
+    memset(&a, 0, sizeof(a));
+    a.x_in = x;
+    a.x_out = x;
+    a.flag_in = g->flags;
+    a.B = B;
+    a.H = H;
+    cudaEvent_t ev0, ev1;
+    MPDB_CHECK_CUDA(cudaEventCreate(&ev0));
+    MPDB_CHECK_CUDA(cudaEventCreate(&ev1));
+    if (guide_launch_step(g, a, st)) return 1;
+    MPDB_CHECK_CUDA(cudaEventRecord(ev0, st));
+    for (int r = 0; r < reps; ++r)
+        if (guide_launch_step(g, a, st)) return 1;
+    MPDB_CHECK_CUDA(cudaEventRecord(ev1, st));
+    MPDB_CHECK_CUDA(cudaEventSynchronize(ev1));
+    float ms = 0.f;
+    MPDB_CHECK_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
+    *ms_out = ms / reps;
+    cudaEventDestroy(ev0);
+    cudaEventDestroy(ev1);
+    return 0;
+}
