@@ -81,7 +81,7 @@ class GuideManagerTrajectoriesWithVelocity(nn.Module):
                             cfg.grid_shape[k] = f.shape[k]
                             cfg.grid_lo[k] = float(f.limits[0][k])
                         cfg.grid_cell = f.cell
-                    elif tuple(cfg.grid_shape[:f.dim]) != f.shape or abs(cfg.grid_cell - f.cell) > 0:
+                    elif tuple(cfg.grid_shape[:f.dim]) != f.shape or abs(cfg.grid_cell - f.cell) > 1e-6 * abs(f.cell):
                         raise NotImplementedError("all grid fields must share one lattice")
                     cfg.grid_texels[n_grid] = f.texels.data_ptr()
                     cfg.weight_grid[n_grid] = float(w)

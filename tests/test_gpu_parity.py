@@ -383,14 +383,17 @@ def test_state_dict_roundtrip_and_reload():
     t = torch.tensor(C.UNET_T).cuda()
     a = model.model(x, t, None)
     # changing a parameter in place is picked up (engine re-packs when parameter versions change)
+    p = dict(model.model.named_parameters())["final_conv.1.bias"]
+    saved = p.detach().clone()
     with torch.no_grad():
-        p = dict(model.model.named_parameters())["final_conv.1.bias"]
         p.add_(1.0)
     b = model.model(x, t, None)
     assert rel(b, a + 1.0) < 1e-5
-    model.load_state_dict(sd)  # sd aliases the live tensors; restore explicitly
     with torch.no_grad():
-        p.sub_(1.0)
+        p.copy_(saved)
+    assert torch.equal(model.model(x, t, None), a)
+    # load_state_dict of a saved copy restores the same function
+    model.load_state_dict({k: v.clone() for k, v in sd.items()})
     assert torch.equal(model.model(x, t, None), a)
 
 
