@@ -362,7 +362,8 @@ def main():
                     "note": "fp32 CUDA-core FMA kernel (exact fp32 parity path); achieved = algorithmic 2*MAC FLOPs of "
                             "its launches / their summed CUDA-event time; share of one UNet forward "
                             f"{conv5_ms / fwd_ms:.3f}",
-                    "unet_forward_ms": fwd_ms, "unet_flops_per_trajectory_per_forward": flops_traj}
+                    "unet_forward_ms": fwd_ms, "unet_flops_per_trajectory_per_forward": flops_traj,
+                    "per_launch_us": [round(float(v) * 1e3, 2) for v in ms], "per_launch_mode": [int(v) for v in md]}
         # guide kernel (HBM-bound by construction; at B=100 it is latency-bound)
         gms = C.c_float()
         xg = noise[1].clamp(-1, 1).contiguous()

@@ -130,6 +130,12 @@ int mpdb_profile_forward(mpdb_engine* e, const float* x, int32_t t, int32_t B, i
 /* average device time of one guide evaluation on x (in place), CUDA events on `stream` */
 int mpdb_profile_guide(mpdb_guide* g, float* x, int32_t B, int32_t H, int32_t reps, float* ms_out, void* stream);
 
+/* unit-test hook for the tcgen05 implicit-GEMM core: raw fp32 accumulators of a k=5 convolution (no bias).
+ * x_cm device [B][CI][L+4] with zero halo, w device [CO][CI][5], raw device [ceil(B/SPT)][CO/32][128][32] with
+ * SPT = 132/(L+4); row r of a tile holds sample (b % SPT), position l at r = (b % SPT)*(L+4) + l. */
+int mpdb_debug_tc_conv5(const float* x_cm, const float* w, float* raw, int32_t B, int32_t CI, int32_t CO, int32_t L,
+                        void* stream);
+
 /* debugging / parity: intermediate activations of the last mpdb_unet_forward */
 int mpdb_engine_num_buffers(mpdb_engine* e);
 int mpdb_engine_buffer_info(mpdb_engine* e, int idx, char* name, int name_cap, int32_t* channels, int32_t* length);

@@ -64,6 +64,7 @@ SYMBOLS = {
     "mpdb_profile_forward": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_float), C.POINTER(C.c_double),
                                        C.POINTER(C.c_int32), _P]),
     "mpdb_profile_guide": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_float), _P]),
+    "mpdb_debug_tc_conv5": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P]),
     "mpdb_engine_num_buffers": (C.c_int, [_P]),
     "mpdb_engine_buffer_info": (C.c_int, [_P, C.c_int, C.c_char_p, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "mpdb_engine_read_buffer": (C.c_int, [_P, C.c_int, _P, C.c_int32, _P]),

@@ -51,7 +51,15 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
-// Mish(x) = x * tanh(softplus(x)); same composition as aten's mish (x * tanh(log1p(exp(x)))).
-__device__ __forceinline__ float mishf(float x) { return x * tanhf(log1pf(expf(x))); }
+// Mish(x) = x * tanh(softplus(x)) (aten: x * tanh(log1p(exp(x)))). With e = exp(x):
+// tanh(log(1 + e)) = ((1+e)^2 - 1) / ((1+e)^2 + 1) = n / (n + 2), n = e * (e + 2)  — one expf, one division,
+// no cancellation for x << 0; for x > 20 tanh(softplus(x)) == 1 in fp32.
+__device__ __forceinline__ float mishf(float x) {
+    const float e = expf(fminf(x, 20.f));
+    const float n = e * (e + 2.f);
+    return x > 20.f ? x : x * __fdiv_rn(n, n + 2.f);
+}
+// reference-composition variant (used once per load for the time tables, where cost does not matter)
+__device__ __forceinline__ float mishf_ref(float x) { return x * tanhf(log1pf(expf(x))); }
 
 }  // namespace mpdb

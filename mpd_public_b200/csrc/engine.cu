@@ -318,7 +318,7 @@ static int launch_op(mpdb_engine* e, const ConvOp& op, const float* x, const lon
     }
     a.out = const_cast<float*>(buf_ptr(e, op.out, e->work_batch));
     a.CO = op.CO; a.L_out = op.L_out; a.B = B; a.gs = op.gs;
-    choose_tile(B, op.L_out, op.CO, op.gn ? op.gs : 4, &a.S, &a.NT);
+    choose_tile(op.mode, &a);
     return launch_conv(op.mode, a, st);
 }
 
@@ -781,5 +781,45 @@ extern "C" int mpdb_profile_forward(mpdb_engine* e, const float* x, int32_t t, i
     }
     cudaEventDestroy(ev0);
     cudaEventDestroy(ev1);
+    return 0;
+}
+
+// Unit-test hook for the tcgen05 implicit-GEMM core (no epilogue): raw accumulators of a k=5 convolution.
+//   x_cm : device fp32 [B][CI][L+4] (zero halo),  w : device fp32 [CO][CI][5]
+//   raw  : device fp32 [ceil(B/SPT)][CO/32][128][32], SPT = 132 / (L+4); row r of a tile = (b % SPT)*(L+4) + l
+extern "C" int mpdb_debug_tc_conv5(const float* x_cm, const float* w, float* raw, int32_t B, int32_t CI, int32_t CO,
+                                   int32_t L, void* stream) {
+    MPDB_REQUIRE(x_cm && w && raw && B > 0, "mpdb_debug_tc_conv5: bad argument");
+    MPDB_REQUIRE(CI % TC_KCH == 0 && CO % TC_NT == 0 && L % 4 == 0 && L + 4 <= TC_RT, "mpdb_debug_tc_conv5: bad shape");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int SPT = TC_RT / (L + 4);
+    const int tiles = (B + SPT - 1) / SPT;
+    const size_t plane = (size_t)tiles * (CI / 8) * TC_RT * 8;
+    float* wp = nullptr;
+    unsigned short *wt = nullptr, *xh = nullptr, *xl = nullptr;
+    MPDB_CHECK_CUDA(cudaMalloc(&wp, sizeof(float) * (size_t)CI * CO * 5));
+    MPDB_CHECK_CUDA(cudaMalloc(&wt, 2 * 2 * (size_t)CI * CO * 5));
+    MPDB_CHECK_CUDA(cudaMalloc(&xh, 2 * plane));
+    MPDB_CHECK_CUDA(cudaMalloc(&xl, 2 * plane));
+    MPDB_CHECK_CUDA(cudaMemsetAsync(xh, 0, 2 * plane, st));
+    MPDB_CHECK_CUDA(cudaMemsetAsync(xl, 0, 2 * plane, st));
+    int rc = launch_repack_conv(w, wp, CO, CI, 5, 0, st);
+    if (!rc) rc = launch_pack_tc_weights(wp, wt, CI, CO, 5, st);
+    if (!rc) rc = launch_cm_to_tc(x_cm, xh, xl, B, CI, L, st);
+    if (!rc) {
+        TcConvArgs a;
+        memset(&a, 0, sizeof(a));
+        a.in0_hi = xh; a.in0_lo = xl; a.c0 = CI;
+        a.w = wt;
+        a.raw_out = raw;
+        a.CO = CO; a.L = L; a.B = B; a.gs = 32;
+        float* dummy = wp;  // gamma/beta/bias are not read in raw mode but must be non-null for the launch checks
+        a.gamma = dummy; a.beta = dummy; a.bias = dummy;
+        rc = launch_conv5_tc(a, st);
+    }
+    cudaError_t e1 = cudaStreamSynchronize(st);
+    cudaFree(wp); cudaFree(wt); cudaFree(xh); cudaFree(xl);
+    if (rc) return rc;
+    MPDB_CHECK_CUDA(e1);
     return 0;
 }

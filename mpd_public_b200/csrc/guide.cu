@@ -163,7 +163,7 @@ __global__ void __launch_bounds__(GUIDE_THREADS) guide_step_kernel(GuideDev g, G
             if (g.robot_kind == 1) {
                 float R[9] = {1.f, 0.f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f, 1.f};  // row-major
                 float o[3] = {0.f, 0.f, 0.f};
-#pragma unroll
+#pragma unroll 1
                 for (int j = 0; j < 7; ++j) {
 #pragma unroll
                     for (int r3 = 0; r3 < 3; ++r3)
@@ -209,51 +209,66 @@ __global__ void __launch_bounds__(GUIDE_THREADS) guide_step_kernel(GuideDev g, G
 
             for (int f = 0; f < n_coll; ++f) {
                 float dq[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-                for (int s = 0; s < g.n_spheres; ++s) {
-                    float p[3] = {cen[(s * 3 + 0) * NTH], cen[(s * 3 + 1) * NTH], cen[(s * 3 + 2) * NTH]};
-                    float sdf, gr[3] = {0.f, 0.f, 0.f};
-                    if (f < g.n_grid) {
-                        long long flat = 0;
-                        for (int d = 0; d < g.ws_dim; ++d) {
-                            float u = rintf(__fdiv_rn(__fsub_rn(p[d], g.glo[d]), g.cell));
-                            u = fminf(fmaxf(u, 0.f), (float)(g.gshape[d] - 1));
-                            flat = flat * g.gshape[d] + (long long)u;
-                        }
-                        if (g.ws_dim == 3) {
-                            float4 t = __ldg(reinterpret_cast<const float4*>(g.tex[f]) + flat);
-                            sdf = t.x; gr[0] = t.y; gr[1] = t.z; gr[2] = t.w;
-                        } else {
-                            const float* t = g.tex[f] + flat * 3;
-                            sdf = __ldg(t); gr[0] = __ldg(t + 1); gr[1] = __ldg(t + 2);
-                        }
-                    } else {
-                        // workspace-boundary field: distance to the nearest wall, positive inside
-                        sdf = 3.4e38f;
-                        int arg = 0; float sgn = 1.f;
-                        for (int d = 0; d < g.ws_dim; ++d) {
-                            float lo = __fsub_rn(p[d], g.blo[d]), hi = __fsub_rn(g.bhi[d], p[d]);
-                            float m = fminf(lo, hi);
-                            if (m < sdf) { sdf = m; arg = d; sgn = (lo <= hi) ? 1.f : -1.f; }
-                        }
-                        gr[arg] = sgn;
-                    }
-                    const float viol = __fsub_rn(__fadd_rn(g.sphere_r[s], g.margin), sdf);
-                    if (viol > 0.f) {
-                        const float gx = -gr[0], gy = -gr[1], gz = -gr[2];  // d cost / d p
-                        if (g.robot_kind == 1) {
-                            int nj = g.sphere_frame[s] < 7 ? g.sphere_frame[s] : 7;
-                            for (int j = 0; j < nj; ++j) {
-                                float rx = p[0] - sc[(j * 3 + 0) * NTH], ry = p[1] - sc[(j * 3 + 1) * NTH],
-                                      rz = p[2] - sc[(j * 3 + 2) * NTH];
-                                float zx = sc[(21 + j * 3 + 0) * NTH], zy = sc[(21 + j * 3 + 1) * NTH],
-                                      zz = sc[(21 + j * 3 + 2) * NTH];
-                                // (z x r) . g
-                                dq[j] += (zy * rz - zz * ry) * gx + (zz * rx - zx * rz) * gy + (zx * ry - zy * rx) * gz;
+                for (int s0 = 0; s0 < g.n_spheres; s0 += 8) {
+                    // all texel gathers of up to 8 spheres are issued before any is consumed (latency overlap)
+                    float tsdf[8], tg[8][3];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int s = s0 + u;
+                        tsdf[u] = 3.4e38f; tg[u][0] = tg[u][1] = tg[u][2] = 0.f;
+                        if (s < g.n_spheres) {
+                            const float p0 = cen[(s * 3 + 0) * NTH], p1 = cen[(s * 3 + 1) * NTH], p2 = cen[(s * 3 + 2) * NTH];
+                            const float p[3] = {p0, p1, p2};
+                            if (f < g.n_grid) {
+                                long long flat = 0;
+                                for (int d = 0; d < g.ws_dim; ++d) {
+                                    float uu = rintf(__fdiv_rn(__fsub_rn(p[d], g.glo[d]), g.cell));
+                                    uu = fminf(fmaxf(uu, 0.f), (float)(g.gshape[d] - 1));
+                                    flat = flat * g.gshape[d] + (long long)uu;
+                                }
+                                if (g.ws_dim == 3) {
+                                    float4 t = __ldg(reinterpret_cast<const float4*>(g.tex[f]) + flat);
+                                    tsdf[u] = t.x; tg[u][0] = t.y; tg[u][1] = t.z; tg[u][2] = t.w;
+                                } else {
+                                    const float* t = g.tex[f] + flat * 3;
+                                    tsdf[u] = __ldg(t); tg[u][0] = __ldg(t + 1); tg[u][1] = __ldg(t + 2);
+                                }
+                            } else {
+                                // workspace-boundary field: distance to the nearest wall, positive inside
+                                int arg = 0; float sgn = 1.f, best = 3.4e38f;
+                                for (int d = 0; d < g.ws_dim; ++d) {
+                                    float lo = __fsub_rn(p[d], g.blo[d]), hi = __fsub_rn(g.bhi[d], p[d]);
+                                    float m = fminf(lo, hi);
+                                    if (m < best) { best = m; arg = d; sgn = (lo <= hi) ? 1.f : -1.f; }
+                                }
+                                tsdf[u] = best;
+                                tg[u][0] = arg == 0 ? sgn : 0.f; tg[u][1] = arg == 1 ? sgn : 0.f; tg[u][2] = arg == 2 ? sgn : 0.f;
                             }
-                        } else {
-                            dq[0] += gx;
-                            if (g.ws_dim > 1) dq[1] += gy;
-                            if (g.ws_dim > 2) dq[2] += gz;
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int s = s0 + u;
+                        if (s >= g.n_spheres) break;
+                        const float viol = __fsub_rn(__fadd_rn(g.sphere_r[s], g.margin), tsdf[u]);
+                        if (viol > 0.f) {
+                            const float gx = -tg[u][0], gy = -tg[u][1], gz = -tg[u][2];  // d cost / d p
+                            if (g.robot_kind == 1) {
+                                const float p0 = cen[(s * 3 + 0) * NTH], p1 = cen[(s * 3 + 1) * NTH], p2 = cen[(s * 3 + 2) * NTH];
+                                int nj = g.sphere_frame[s] < 7 ? g.sphere_frame[s] : 7;
+                                for (int j = 0; j < nj; ++j) {
+                                    float rx = p0 - sc[(j * 3 + 0) * NTH], ry = p1 - sc[(j * 3 + 1) * NTH],
+                                          rz = p2 - sc[(j * 3 + 2) * NTH];
+                                    float zx = sc[(21 + j * 3 + 0) * NTH], zy = sc[(21 + j * 3 + 1) * NTH],
+                                          zz = sc[(21 + j * 3 + 2) * NTH];
+                                    // (z x r) . g
+                                    dq[j] += (zy * rz - zz * ry) * gx + (zz * rx - zx * rz) * gy + (zx * ry - zy * rx) * gz;
+                                }
+                            } else {
+                                dq[0] += gx;
+                                if (g.ws_dim > 1) dq[1] += gy;
+                                if (g.ws_dim > 2) dq[2] += gz;
+                            }
                         }
                     }
                 }

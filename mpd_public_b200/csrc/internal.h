@@ -42,10 +42,45 @@ struct ConvArgs {
     int gs;  // channels per GroupNorm group
     int S;   // samples per CTA
     int NT;  // output channels per CTA
+    int G;   // intra-CTA split-K groups (1, 2 or 4)
+    // optional second copy of the output in the tensor-core ("TC") layout, bf16 hi/lo planes (unet_tc.cu)
+    unsigned short* out_hi;
+    unsigned short* out_lo;
 };
 
-int launch_conv(int mode, const ConvArgs& a, cudaStream_t stream);
-void choose_tile(int B, int L_out, int CO, int gs, int* S, int* NT);
+int launch_conv(int mode, ConvArgs a, cudaStream_t stream);
+void choose_tile(int mode, ConvArgs* a);
+
+// ---- tensor-core path (unet_tc.cu) ----
+constexpr int TC_RT = 132;   // rows of one tile block in the TC layout (128 MMA rows + 4 rows of tap reach)
+constexpr int TC_NT = 32;    // output channels per CTA
+constexpr int TC_KCH = 32;   // input channels per pipeline stage
+
+struct TcConvArgs {
+    // main conv input: up to two concatenated sources in TC layout (bf16 hi / lo planes)
+    const unsigned short *in0_hi, *in0_lo, *in1_hi, *in1_lo;
+    int c0, c1;
+    const unsigned short* w;      // packed [CO/32][CI/32][hi|lo][5][4][32][8]
+    const float* bias;
+    const float* gamma;
+    const float* beta;
+    const float* cond;
+    const long long* t_dev;
+    int t_uniform;
+    // residual: identity (res_cm: fp32 CM tensor with CO channels) or fused 1x1 conv (res_w != null) of r0|r1
+    const float* res_cm;
+    const unsigned short *r0_hi, *r0_lo, *r1_hi, *r1_lo;
+    int rc0, rc1;
+    const unsigned short* res_w;  // packed [CO/32][RC/32][hi|lo][1][4][32][8]
+    const float* res_bias;
+    float* out_cm;                // fp32 CM output (may be null)
+    unsigned short *out_hi, *out_lo;  // TC-layout output (may be null)
+    float* raw_out;               // debug: raw main accumulator [tile][ntile][128][32]
+    int CO, L, B, gs;
+};
+int launch_conv5_tc(const TcConvArgs& a, cudaStream_t stream);
+int launch_pack_tc_weights(const float* src, unsigned short* dst, int CI, int CO, int ntaps, cudaStream_t stream);
+int launch_cm_to_tc(const float* cm, unsigned short* hi, unsigned short* lo, int B, int C, int L, cudaStream_t stream);
 
 struct FinalArgs {
     const float* h;     // CM [B][C][L+4]

@@ -6,6 +6,8 @@
 // so GroupNorm statistics never leave the CTA. Each thread owns a 4 (positions) x 4 (channels) register
 // tile; input channels stream through shared memory in chunks of KC with a 2-stage cp.async pipeline,
 // the k-tap window of a chunk is staged once and reused by all taps.
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 #include "internal.h"
 
@@ -34,17 +36,39 @@ struct TileCtx {
     int b0;      // first sample of the CTA
     int co0;     // first output channel of the CTA
     int S, NT, B;
+    int G;       // intra-CTA split-K: number of K groups (each group = one full set of output tiles)
+    int g;       // this thread's K group
+    int T0;      // threads per K group
+    int logS;    // log2(S)
 };
 
-// Stages one chunk of KC input channels (all S samples, full padded rows) and the matching weights.
+// Decomposition of a flat staging index into (row, col) with col in [0, ncols), advanced by a fixed stride
+// without divisions inside the hot loop.
+struct Walk2 {
+    int row, col, drow, dcol, ncols;
+    __device__ __forceinline__ void init(int idx0, int stride, int ncols_) {
+        ncols = ncols_;
+        row = idx0 / ncols; col = idx0 - row * ncols;
+        drow = stride / ncols; dcol = stride - drow * ncols;
+    }
+    __device__ __forceinline__ void next() {
+        col += dcol; row += drow;
+        if (col >= ncols) { col -= ncols; ++row; }
+    }
+};
+
+// Stages one chunk of KC*G input channels (all S samples, full padded rows) and the matching weights.
+// (kept out of line: the kernel is latency-bound at small batch and instruction-cache footprint matters more
+// than call overhead — ncu showed `stalled_no_instruction` as the top stall with everything inlined)
 template <int NTAPS>
-__device__ __forceinline__ void stage_chunk(float* xs, float* ws, const ConvSrc& src, const float* __restrict__ w,
-                                            int CO, int kbase, const TileCtx& c) {
+__device__ __noinline__ void stage_chunk(float* xs, float* ws, const ConvSrc& src, const float* __restrict__ w,
+                                         int CO, int kbase, const TileCtx& c) {
     const int Lp = src.L + 2 * HALO;
     const int ctot = src.c0 + src.c1;
+    const int KCS = KC * c.G;  // channels per stage
     if (src.blc) {
         // raw trajectory [B][L][C]: transpose into xs[kk][s*Lp + l + HALO], halo written as zeros
-        const int n = KC * c.S * Lp;
+        const int n = KCS * c.S * Lp;
         for (int idx = c.tid; idx < n; idx += c.nthreads) {
             int kk = idx / (c.S * Lp);
             int rem = idx - kk * (c.S * Lp);
@@ -58,42 +82,50 @@ __device__ __forceinline__ void stage_chunk(float* xs, float* ws, const ConvSrc&
             xs[idx] = v;
         }
     } else {
+        // rows = (kk, s) pairs, cols = 16-byte granules of one padded row
         const int Lp4 = Lp >> 2;
-        const int n = KC * c.S * Lp4;
-        for (int idx = c.tid; idx < n; idx += c.nthreads) {
-            int kk = idx / (c.S * Lp4);
-            int rem = idx - kk * (c.S * Lp4);
-            int s = rem / Lp4;
-            int j4 = rem - s * Lp4;
-            int ch = kbase + kk;
-            int b = c.b0 + s;
-            float* dst = xs + (kk * c.S + s) * Lp + j4 * 4;
-            if (ch < ctot && b < c.B) {
-                const float* g = (ch < src.c0) ? src.p0 + ((long long)b * src.c0 + ch) * Lp
-                                               : src.p1 + ((long long)b * src.c1 + (ch - src.c0)) * Lp;
-                cp_async16(dst, g + j4 * 4);
+        const int nrows = KCS * c.S;
+        Walk2 wk;
+        wk.init(c.tid, c.nthreads, Lp4);
+        // a stage never straddles the two concat sources (c0 % KCS == 0 is enforced on the host)
+        const bool second = kbase >= src.c0;
+        const float* base = second ? src.p1 : src.p0;
+        const int csrc = second ? src.c1 : src.c0;
+        const int chb = second ? kbase - src.c0 : kbase;
+        for (; wk.row < nrows; wk.next()) {
+            const int kk = wk.row >> c.logS;  // S is a power of two
+            const int s = wk.row & (c.S - 1);
+            const int b = c.b0 + s;
+            float* dst = xs + wk.row * Lp + wk.col * 4;
+            if (kbase + kk < ctot && b < c.B) {
+                cp_async16(dst, base + ((long long)b * csrc + chb + kk) * Lp + wk.col * 4);
             } else {
                 *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
             }
         }
     }
-    const int NT4 = c.NT >> 2;
-    const int nw = KC * NTAPS * NT4;
-    for (int idx = c.tid; idx < nw; idx += c.nthreads) {
-        int row = idx / NT4;  // kk*NTAPS + tap
-        int n4 = idx - row * NT4;
-        int kk = row / NTAPS;
-        int ch = kbase + kk;
-        float* dst = ws + row * c.NT + n4 * 4;
-        if (ch < ctot) {
-            cp_async16(dst, w + ((long long)(kbase * NTAPS + row)) * CO + c.co0 + n4 * 4);
-        } else {
-            *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+    {
+        // rows = (kk, tap) pairs, cols = 16-byte granules of the CTA's NT output channels
+        const int NT4 = c.NT >> 2;
+        const int nrows = KCS * NTAPS;
+        Walk2 wk;
+        wk.init(c.tid, c.nthreads, NT4);
+        const float* wb = w + (long long)kbase * NTAPS * CO + c.co0;
+        const int rows_valid = (ctot - kbase) * NTAPS;  // rows beyond the last real channel are zero-filled
+        for (; wk.row < nrows; wk.next()) {
+            float* dst = ws + wk.row * c.NT + wk.col * 4;
+            if (wk.row < rows_valid) {
+                cp_async16(dst, wb + (long long)wk.row * CO + wk.col * 4);
+            } else {
+                *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
         }
     }
 }
 
 // acc[i][j] += sum over the source's channels and taps. i = position in the thread tile, j = channel.
+// With G > 1 the K loop is split over G thread groups (each stage holds KC*G channels, group g consumes its
+// KC); the partial sums are then added into group 0 in fixed order g = 1..G-1 (deterministic).
 template <int MODE>
 __device__ __forceinline__ void accumulate(float (&acc)[TP][TC], float* smem, int stage_floats, int xs_floats,
                                            const ConvSrc& src, const float* __restrict__ w, int CO, const TileCtx& c) {
@@ -101,7 +133,8 @@ __device__ __forceinline__ void accumulate(float (&acc)[TP][TC], float* smem, in
     constexpr int XV = ModeTraits<MODE>::XV;
     const int Lp = src.L + 2 * HALO;
     const int ctot = src.c0 + src.c1;
-    const int nchunks = (ctot + KC - 1) / KC;
+    const int KCS = KC * c.G;
+    const int nchunks = (ctot + KCS - 1) / KCS;
     const int xs_stride = c.S * Lp;
 
     // first input column (in padded coordinates) read by this thread
@@ -117,15 +150,16 @@ __device__ __forceinline__ void accumulate(float (&acc)[TP][TC], float* smem, in
         float* cur = smem + (ch & 1) * stage_floats;
         if (ch + 1 < nchunks) {
             float* nxt = smem + ((ch + 1) & 1) * stage_floats;
-            stage_chunk<NTAPS>(nxt, nxt + xs_floats, src, w, CO, (ch + 1) * KC, c);
+            stage_chunk<NTAPS>(nxt, nxt + xs_floats, src, w, CO, (ch + 1) * KCS, c);
             cp_async_commit();
             cp_async_wait<1>();
         } else {
             cp_async_wait<0>();
         }
         __syncthreads();
-        const float* xs = cur;
-        const float* ws = cur + xs_floats;
+        const float* xs = cur + c.g * KC * xs_stride;
+        const float* ws = cur + xs_floats + c.g * KC * NTAPS * c.NT;
+        if (ch * KCS + c.g * KC < ctot) {
 #pragma unroll 4
         for (int kk = 0; kk < KC; ++kk) {
             float xv[XV];
@@ -172,6 +206,29 @@ __device__ __forceinline__ void accumulate(float (&acc)[TP][TC], float* smem, in
                 }
             }
         }
+        }
+        __syncthreads();
+    }
+    if (c.G > 1) {
+        // cross-group reduction through shared memory (the stage buffers are free after the last barrier)
+        float* part = smem;  // [(G-1)][T0][16]
+        const int t0 = c.tid - c.g * c.T0;
+        if (c.g > 0) {
+            float4* dst = reinterpret_cast<float4*>(part + ((size_t)(c.g - 1) * c.T0 + t0) * (TP * TC));
+#pragma unroll
+            for (int i = 0; i < TP; ++i) dst[i] = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+        }
+        __syncthreads();
+        if (c.g == 0) {
+            for (int gg = 1; gg < c.G; ++gg) {
+                const float4* srcp = reinterpret_cast<const float4*>(part + ((size_t)(gg - 1) * c.T0 + t0) * (TP * TC));
+#pragma unroll
+                for (int i = 0; i < TP; ++i) {
+                    float4 v = srcp[i];
+                    acc[i][0] += v.x; acc[i][1] += v.y; acc[i][2] += v.z; acc[i][3] += v.w;
+                }
+            }
+        }
         __syncthreads();
     }
 }
@@ -191,9 +248,15 @@ __global__ void __launch_bounds__(512) conv_kernel(ConvArgs a) {
     c.co0 = blockIdx.y * a.NT;
     const int n_pt = (a.S * a.L_out) / TP;
     const int n_ct = a.NT / TC;
+    c.T0 = n_pt * n_ct;
+    c.logS = 31 - __clz(a.S);
+    c.G = a.G;
+    c.g = c.tid / c.T0;
     const int warp = c.tid >> 5, lane = c.tid & 31;
+    const int warp0 = warp - c.g * (c.T0 >> 5);  // warp index within the K group
     const int pt_blocks = n_pt >> 3;
-    const int ptb = warp % pt_blocks, ctb = warp / pt_blocks;
+    const int ptb = warp0 % pt_blocks, ctb = warp0 / pt_blocks;
+    const bool lead = (c.g == 0);  // group 0 owns the epilogue (statistics, residual, stores)
     const int pt = ptb * 8 + (lane & 7);
     c.ct = ctb * 4 + (lane >> 3);
     c.s = (pt * TP) / a.L_out;
@@ -201,15 +264,14 @@ __global__ void __launch_bounds__(512) conv_kernel(ConvArgs a) {
 
     // shared memory carve-up: 2 stages of {xs, ws}, then the reduction scratch
     const int Lp_in = a.in.L + 2 * HALO;
-    int xs_floats = KC * a.S * Lp_in;
-    int ws_floats = KC * NTAPS * a.NT;
+    int xs_floats = KC * a.G * a.S * Lp_in;
+    int ws_floats = KC * a.G * NTAPS * a.NT;
     if (a.res_w != nullptr) {
-        int xr = KC * a.S * (a.res.L + 2 * HALO);
+        int xr = KC * a.G * a.S * (a.res.L + 2 * HALO);
         xs_floats = xs_floats > xr ? xs_floats : xr;
     }
     const int stage_floats = xs_floats + ws_floats;
     float* red = smem + 2 * stage_floats;          // [n_ct][n_pt]
-    float* stat = red + n_ct * n_pt;               // [n_stats]
 
     float acc[TP][TC];
 #pragma unroll
@@ -231,75 +293,49 @@ __global__ void __launch_bounds__(512) conv_kernel(ConvArgs a) {
     }
 
     if (a.gamma != nullptr) {
-        // GroupNorm over (gs channels x L_out positions) of one sample, two-pass, fixed reduction order.
+        // GroupNorm over (gs channels x L_out positions) of one sample: two-pass (mean, then centred second
+        // moment), every thread adds the per-thread partials of its statistic in the same fixed order.
         const int gpt = a.NT / a.gs;            // groups per CTA tile
-        const int n_stats = a.S * gpt;
         const int ptl = a.L_out / TP;           // position tiles per sample
         const int ctg = a.gs / TC;              // channel tiles per group
-        const int n_el = ptl * ctg;
-        const int my_stat = c.s * gpt + (c.ct * TC) / a.gs;
+        const int ct_first = ((c.ct * TC) / a.gs) * ctg;
+        const int pt_first = c.s * ptl;
         const float inv_n = 1.f / (float)(a.gs * a.L_out);
-        const int nwarps = c.nthreads >> 5;
-        float mean, rstd;
-        {
-            float s1 = 0.f;
+        (void)gpt;
+        float s1 = 0.f;
 #pragma unroll
-            for (int i = 0; i < TP; ++i)
+        for (int i = 0; i < TP; ++i)
 #pragma unroll
-                for (int j = 0; j < TC; ++j) s1 += acc[i][j];
-            red[c.ct * n_pt + pt] = s1;
-            __syncthreads();
-            for (int st = warp; st < n_stats; st += nwarps) {
-                int s = st / gpt, g = st - s * gpt;
-                float v = 0.f;
-                for (int e = lane; e < n_el; e += 32) {
-                    int cti = g * ctg + e / ptl;
-                    int pti = s * ptl + e % ptl;
-                    v += red[cti * n_pt + pti];
-                }
-                v = warp_sum(v);
-                if (lane == 0) stat[st] = v * inv_n;
-            }
-            __syncthreads();
-            mean = stat[my_stat];
-        }
-        {
-            float s2 = 0.f;
-#pragma unroll
-            for (int i = 0; i < TP; ++i)
-#pragma unroll
-                for (int j = 0; j < TC; ++j) {
-                    float d = acc[i][j] - mean;
-                    s2 = fmaf(d, d, s2);
-                }
-            __syncthreads();  // everyone has read stat[] (mean) and red[] is free again
-            red[c.ct * n_pt + pt] = s2;
-            __syncthreads();
-            for (int st = warp; st < n_stats; st += nwarps) {
-                int s = st / gpt, g = st - s * gpt;
-                float v = 0.f;
-                for (int e = lane; e < n_el; e += 32) {
-                    int cti = g * ctg + e / ptl;
-                    int pti = s * ptl + e % ptl;
-                    v += red[cti * n_pt + pti];
-                }
-                v = warp_sum(v);
-                if (lane == 0) stat[st] = 1.0f / sqrtf(v * inv_n + 1e-5f);
-            }
-            __syncthreads();
-            rstd = stat[my_stat];
-        }
-        float4 gv = *reinterpret_cast<const float4*>(a.gamma + co);
-        float4 bev = *reinterpret_cast<const float4*>(a.beta + co);
-        const float ga[4] = {gv.x, gv.y, gv.z, gv.w};
-        const float be[4] = {bev.x, bev.y, bev.z, bev.w};
+            for (int j = 0; j < TC; ++j) s1 += acc[i][j];
+        if (lead) red[c.ct * n_pt + pt] = s1;
+        __syncthreads();
+        float tot = 0.f;
+        for (int cc = 0; cc < ctg; ++cc)
+            for (int pp = 0; pp < ptl; ++pp) tot += red[(ct_first + cc) * n_pt + pt_first + pp];
+        const float mean = tot * inv_n;
+        float s2 = 0.f;
 #pragma unroll
         for (int i = 0; i < TP; ++i)
 #pragma unroll
             for (int j = 0; j < TC; ++j) {
-                float y = (acc[i][j] - mean) * rstd * ga[j] + be[j];
-                acc[i][j] = mishf(y);
+                float d = acc[i][j] - mean;
+                s2 = fmaf(d, d, s2);
             }
+        __syncthreads();  // everyone has consumed the first-pass partials
+        if (lead) red[c.ct * n_pt + pt] = s2;
+        __syncthreads();
+        tot = 0.f;
+        for (int cc = 0; cc < ctg; ++cc)
+            for (int pp = 0; pp < ptl; ++pp) tot += red[(ct_first + cc) * n_pt + pt_first + pp];
+        const float rstd = 1.0f / sqrtf(tot * inv_n + 1e-5f);
+        float4 gv = *reinterpret_cast<const float4*>(a.gamma + co);
+        float4 bev = *reinterpret_cast<const float4*>(a.beta + co);
+        const float ga[4] = {gv.x * rstd, gv.y * rstd, gv.z * rstd, gv.w * rstd};
+        const float be[4] = {bev.x, bev.y, bev.z, bev.w};
+#pragma unroll
+        for (int i = 0; i < TP; ++i)
+#pragma unroll
+            for (int j = 0; j < TC; ++j) acc[i][j] = mishf((acc[i][j] - mean) * ga[j] + be[j]);
     }
 
     if (a.cond != nullptr && b < a.B) {
@@ -327,7 +363,7 @@ __global__ void __launch_bounds__(512) conv_kernel(ConvArgs a) {
             for (int i = 0; i < TP; ++i)
 #pragma unroll
                 for (int j = 0; j < TC; ++j) acc[i][j] += racc[i][j] + bb[j];
-        } else if (b < a.B) {
+        } else if (b < a.B && lead) {
             const int Lp = a.L_out + 2 * HALO;
 #pragma unroll
             for (int j = 0; j < TC; ++j) {
@@ -339,7 +375,7 @@ __global__ void __launch_bounds__(512) conv_kernel(ConvArgs a) {
         }
     }
 
-    if (b < a.B) {
+    if (b < a.B && lead) {
         const int Lp = a.L_out + 2 * HALO;
 #pragma unroll
         for (int j = 0; j < TC; ++j) {
@@ -347,60 +383,103 @@ __global__ void __launch_bounds__(512) conv_kernel(ConvArgs a) {
             *reinterpret_cast<float2*>(op) = make_float2(acc[0][j], acc[1][j]);
             *reinterpret_cast<float2*>(op + 2) = make_float2(acc[2][j], acc[3][j]);
         }
+        if (a.out_hi != nullptr) {
+            // second copy in the tensor-core layout (bf16 hi/lo planes, unet_tc.cu): 4 channels = 8 bytes per row
+            const int SPT = TC_RT / Lp;
+            const int tile = b / SPT, sb = b - tile * SPT;
+#pragma unroll
+            for (int i = 0; i < TP; ++i) {
+                const long long o = (((long long)tile * (a.CO / 8) + co / 8) * TC_RT + (sb * Lp + c.l0 + i + HALO)) * 8 + (co & 7);
+                unsigned short h[4], l[4];
+#pragma unroll
+                for (int j = 0; j < TC; ++j) {
+                    __nv_bfloat16 hb = __float2bfloat16_rn(acc[i][j]);
+                    __nv_bfloat16 lb = __float2bfloat16_rn(acc[i][j] - __bfloat162float(hb));
+                    h[j] = __bfloat16_as_ushort(hb);
+                    l[j] = __bfloat16_as_ushort(lb);
+                }
+                *reinterpret_cast<uint2*>(a.out_hi + o) = make_uint2(h[0] | ((unsigned)h[1] << 16), h[2] | ((unsigned)h[3] << 16));
+                *reinterpret_cast<uint2*>(a.out_lo + o) = make_uint2(l[0] | ((unsigned)l[1] << 16), l[2] | ((unsigned)l[3] << 16));
+            }
+        }
     }
 }
 
 static int ntaps_of(int mode) { return mode == MODE_CONV5 ? 5 : mode == MODE_CONV1 ? 1 : mode == MODE_DOWN ? 3 : 4; }
 
-void choose_tile(int B, int L_out, int CO, int gs, int* S_out, int* NT_out) {
-    // threads = S*L_out*NT/16 in {128, 256}; whole GroupNorm groups per CTA; prefer >= 1 CTA per SM.
+static size_t conv_smem_bytes(int mode, const ConvArgs& a) {
+    const int ntaps = ntaps_of(mode);
+    const int P = a.S * a.L_out;
+    int xs_floats = KC * a.G * a.S * (a.in.L + 2 * HALO);
+    if (a.res_w != nullptr) {
+        int xr = KC * a.G * a.S * (a.res.L + 2 * HALO);
+        xs_floats = xs_floats > xr ? xs_floats : xr;
+    }
+    const int ws_floats = KC * a.G * ntaps * a.NT;
+    const int n_pt = P / TP, n_ct = a.NT / TC;
+    const int n_stats = a.S * (a.gs > 0 ? a.NT / a.gs : 1);
+    size_t fl = (size_t)(2 * (xs_floats + ws_floats) + n_pt * n_ct + n_stats + 4);
+    size_t red = (size_t)(a.G - 1) * n_pt * n_ct * TP * TC;  // cross-group reduction reuses the stage buffers
+    if (red > (size_t)2 * (xs_floats + ws_floats)) fl += red - (size_t)2 * (xs_floats + ws_floats);
+    return fl * sizeof(float);
+}
+
+// Picks (S, NT, G) for a layer. G (intra-CTA split-K) depends ONLY on the layer's input width, never on the
+// batch, so that the summation order of every output element — and therefore the result, bit for bit — is
+// independent of the batch size and of how the batch is sharded. (S, NT) only decide which CTA computes what.
+void choose_tile(int mode, ConvArgs* a) {
+    const int cin = a->in.c0 + a->in.c1;
+    const int gs = a->gamma ? a->gs : 4;
+    a->G = cin >= 64 ? 4 : cin >= 32 ? 2 : 1;
+    while (a->G > 1 && a->in.c1 > 0 && a->in.c0 % (KC * a->G)) a->G /= 2;  // a stage must not straddle concat sources
+    while (a->G > 1 && a->res_w && a->res.c1 > 0 && a->res.c0 % (KC * a->G)) a->G /= 2;
     long long best_cost = -1;
-    int bS = 1, bNT = CO < 16 ? CO : 16;
+    int bS = 0, bNT = 0;
     const int nts[3] = {64, 32, 16};
     for (int k = 0; k < 3; ++k) {
         int NT = nts[k];
-        if (NT > CO || CO % NT || NT % gs) continue;
+        if (NT > a->CO || a->CO % NT || NT % gs) continue;
         for (int S = 1; S <= 32; S *= 2) {
-            int P = S * L_out;
+            int P = S * a->L_out;
             if (P % 32) continue;
-            int threads = P * NT / 16;
-            if (threads < 64 || threads > 512) continue;
-            long long ctas = (long long)((B + S - 1) / S) * (CO / NT);
+            int T0 = P * NT / 16;
+            if (T0 < 32 || T0 * a->G > 512) continue;
+            ConvArgs t = *a;
+            t.S = S;
+            t.NT = NT;
+            if (conv_smem_bytes(mode, t) > 200 * 1024) continue;
+            long long ctas = (long long)((a->B + S - 1) / S) * (a->CO / NT);
             long long waves = (ctas + 147) / 148;
-            long long cost = waves * (long long)(P * NT) * 16 + (threads == 128 ? 0 : threads == 256 ? 1 : 8) +
-                             (NT == 64 ? 0 : NT == 32 ? 2 : 4);
+            int threads = T0 * a->G;
+            long long cost = waves * (long long)(P * NT) * 16 + (threads == 512 ? 0 : threads == 256 ? 2 : 6) +
+                             (NT == 32 ? 0 : NT == 64 ? 1 : 3);
             if (best_cost < 0 || cost < best_cost) { best_cost = cost; bS = S; bNT = NT; }
         }
     }
-    *S_out = bS;
-    *NT_out = bNT;
+    a->S = bS;
+    a->NT = bNT;
 }
 
-int launch_conv(int mode, const ConvArgs& a, cudaStream_t stream) {
-    const int ntaps = ntaps_of(mode);
+int launch_conv(int mode, ConvArgs a, cudaStream_t stream) {
+    MPDB_REQUIRE(a.S > 0 && a.NT > 0, "conv tile: no feasible tiling for this layer shape");
     const int P = a.S * a.L_out;
     MPDB_REQUIRE(P % 32 == 0 && a.NT % 16 == 0 && a.CO % a.NT == 0, "conv tile: unsupported S/NT");
     MPDB_REQUIRE(a.gamma == nullptr || (a.NT % a.gs == 0 && a.gs % TC == 0), "conv tile: GroupNorm group not tile-aligned");
     MPDB_REQUIRE(a.in.L % 4 == 0 && a.L_out % 4 == 0, "conv: lengths must be multiples of 4");
-    const int threads = P * a.NT / 16;
+    MPDB_REQUIRE(a.S > 0 && a.NT > 0, "conv tile: no feasible tiling for this layer shape");
+    MPDB_REQUIRE(a.G == 1 || a.G == 2 || a.G == 4, "conv tile: G must be 1, 2 or 4");
+    const int threads = a.G * P * a.NT / 16;
     MPDB_REQUIRE(threads >= 32 && threads <= 512, "conv tile: thread count out of range");
-    int xs_floats = KC * a.S * (a.in.L + 2 * HALO);
-    if (a.res_w != nullptr) {
-        int xr = KC * a.S * (a.res.L + 2 * HALO);
-        xs_floats = xs_floats > xr ? xs_floats : xr;
-    }
-    const int ws_floats = KC * ntaps * a.NT;
-    const int n_pt = P / TP, n_ct = a.NT / TC;
-    const int n_stats = a.S * (a.gs > 0 ? a.NT / a.gs : 1);
-    const size_t smem = sizeof(float) * (size_t)(2 * (xs_floats + ws_floats) + n_pt * n_ct + n_stats + 4);
+    const size_t smem = conv_smem_bytes(mode, a);
+    MPDB_REQUIRE(smem <= 227 * 1024, "conv tile: shared memory budget exceeded");
     dim3 grid((a.B + a.S - 1) / a.S, a.CO / a.NT);
 #define MPDB_CONV_CASE(M)                                                                                      \
     case M: {                                                                                                  \
-        static size_t configured = 0;                                                                          \
-        if (smem > configured) {                                                                               \
+        static bool configured = false;                                                                        \
+        if (!configured) {                                                                                     \
             MPDB_CHECK_CUDA(cudaFuncSetAttribute(conv_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
-                                                 (int)(smem > 200 * 1024 ? smem : 200 * 1024)));               \
-            configured = 200 * 1024 > smem ? 200 * 1024 : smem;                                                \
+                                                 227 * 1024));                                                 \
+            configured = true;                                                                                 \
         }                                                                                                      \
         conv_kernel<M><<<grid, threads, smem, stream>>>(a);                                                    \
         break;                                                                                                 \
@@ -422,7 +501,9 @@ int launch_conv(int mode, const ConvArgs& a, cudaStream_t stream) {
 // optionally with the noise add + hard conditioning of ddpm_sample_fn / p_sample_loop
 // (sample_functions.py:50-62, 5-8). One thread per (b, l).
 // ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) final_kernel(FinalArgs a) {
+__global__ void __launch_bounds__(256) final_kernel(FinalArgs a) {
+    // one thread per output element (b, l, d): a 32-term dot product over the channels of h, then the
+    // elementwise DDPM update. Small code, all loads of a thread independent.
     extern __shared__ __align__(16) float smem[];
     float* wsm = smem;                 // [D][C]
     float* bsm = smem + a.D * a.C;     // [D]
@@ -430,53 +511,39 @@ __global__ void __launch_bounds__(128) final_kernel(FinalArgs a) {
     for (int i = threadIdx.x; i < a.D; i += blockDim.x) bsm[i] = a.bias[i];
     __syncthreads();
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const int b = (int)(idx / a.L), l = (int)(idx - (long long)b * a.L);
+    const long long n = (long long)a.B * a.L * a.D;
     bool viol = false;
-    if (b < a.B) {
+    if (idx < n) {
+        const int d = (int)(idx % a.D);
+        const long long bl = idx / a.D;
+        const int l = (int)(bl % a.L);
+        const int b = (int)(bl / a.L);
         const int Lp = a.L + 2 * HALO;
-        float eps[MPDB_MAX_STATE_DIM];
-#pragma unroll
-        for (int d = 0; d < MPDB_MAX_STATE_DIM; ++d) eps[d] = 0.f;
         const float* hp = a.h + (long long)b * a.C * Lp + HALO + l;
-        for (int c = 0; c < a.C; ++c) {
-            float hv = hp[(long long)c * Lp];
-#pragma unroll
-            for (int d = 0; d < MPDB_MAX_STATE_DIM; ++d)
-                if (d < a.D) eps[d] = fmaf(wsm[d * a.C + c], hv, eps[d]);
-        }
-        const int tt = a.t_dev ? (int)a.t_dev[b] : a.t_uniform;
-        float sr = 0.f, srm1 = 0.f, c1 = 0.f, c2 = 0.f, sd = 0.f;
-        if (a.mode != 0) { sr = a.sr[tt]; srm1 = a.srm1[tt]; c1 = a.c1[tt]; c2 = a.c2[tt]; sd = a.stdv[tt]; }
-        int hc = -1;
-        if (a.mode == 2)
-            for (int k = 0; k < a.n_hc; ++k)
-                if (a.hc_rows[k] == l) hc = k;  // later entries win, as in the reference's dict iteration
-        const long long o = ((long long)b * a.L + l) * a.D;
-#pragma unroll
-        for (int d = 0; d < MPDB_MAX_STATE_DIM; ++d) {
-            if (d < a.D) {
-                float e = eps[d] + bsm[d];
-                float r;
-                if (a.mode == 0) {
-                    r = e;
-                } else {
-                    const float xv = a.x[o + d];
-                    // same operation order as the reference: sr*x - srm1*eps ; clamp ; c1*x0 + c2*x  (no FMA contraction)
-                    float x0 = a.predict_epsilon ? __fsub_rn(__fmul_rn(sr, xv), __fmul_rn(srm1, e)) : e;
-                    if (a.clip_denoised) x0 = fminf(fmaxf(x0, -1.f), 1.f);
-                    r = __fadd_rn(__fmul_rn(c1, x0), __fmul_rn(c2, xv));
-                    if (a.mode == 2) {
-                        float nz = (tt == 0) ? 0.f : a.noise[o + d];
-                        r = __fadd_rn(r, __fmul_rn(__fmul_rn(sd, nz), a.noise_std));
-                        if (hc >= 0) r = a.hc_vals[((long long)hc * a.B + b) * a.D + d];
-                    } else {
-                        viol |= (r > 1.0001f) || (r < -1.0001f);
-                    }
-                }
-                a.out[o + d] = r;
-                if (a.out2) a.out2[(long long)b * a.out2_bstride + (long long)l * a.D + d] = r;
+        const float* wp = wsm + d * a.C;
+        float e = 0.f;
+#pragma unroll 8
+        for (int c = 0; c < a.C; ++c) e = fmaf(wp[c], hp[(long long)c * Lp], e);
+        e += bsm[d];
+        float r = e;
+        if (a.mode != 0) {
+            const int tt = a.t_dev ? (int)a.t_dev[b] : a.t_uniform;
+            const float xv = a.x[idx];
+            // same operation order as the reference: sr*x - srm1*eps ; clamp ; c1*x0 + c2*x  (no FMA contraction)
+            float x0 = a.predict_epsilon ? __fsub_rn(__fmul_rn(a.sr[tt], xv), __fmul_rn(a.srm1[tt], e)) : e;
+            if (a.clip_denoised) x0 = fminf(fmaxf(x0, -1.f), 1.f);
+            r = __fadd_rn(__fmul_rn(a.c1[tt], x0), __fmul_rn(a.c2[tt], xv));
+            if (a.mode == 2) {
+                const float nz = (tt == 0) ? 0.f : a.noise[idx];
+                r = __fadd_rn(r, __fmul_rn(__fmul_rn(a.stdv[tt], nz), a.noise_std));
+                for (int k = 0; k < a.n_hc; ++k)  // later entries win, as in the reference's dict iteration
+                    if (a.hc_rows[k] == l) r = a.hc_vals[((long long)k * a.B + b) * a.D + d];
+            } else {
+                viol = (r > 1.0001f) || (r < -1.0001f);
             }
         }
+        a.out[idx] = r;
+        if (a.out2) a.out2[(long long)b * a.out2_bstride + (long long)l * a.D + d] = r;
     }
     if (a.flag_out != nullptr) {
         if (__syncthreads_or(viol ? 1 : 0) && threadIdx.x == 0) atomicOr(a.flag_out, 1);
@@ -485,8 +552,8 @@ __global__ void __launch_bounds__(128) final_kernel(FinalArgs a) {
 
 int launch_final(const FinalArgs& a, cudaStream_t stream) {
     MPDB_REQUIRE(a.D <= MPDB_MAX_STATE_DIM, "state_dim too large");
-    const long long n = (long long)a.B * a.L;
-    const int threads = 128;
+    const long long n = (long long)a.B * a.L * a.D;
+    const int threads = 256;
     const int blocks = (int)((n + threads - 1) / threads);
     const size_t smem = sizeof(float) * (size_t)(a.D * a.C + a.D);
     final_kernel<<<blocks, threads, smem, stream>>>(a);
@@ -541,13 +608,13 @@ __global__ void __launch_bounds__(128) time_table_kernel(const float* __restrict
     {
         float acc = 0.f;
         for (int k = 0; k < 32; ++k) acc = fmaf(w1[j * 32 + k], emb[k], acc);
-        hid[j] = mishf(acc + b1[j]);
+        hid[j] = mishf_ref(acc + b1[j]);
     }
     __syncthreads();
     if (j < 32) {
         float acc = 0.f;
         for (int k = 0; k < 128; ++k) acc = fmaf(w3[j * 128 + k], hid[k], acc);
-        temb_mish[t * 32 + j] = mishf(acc + b3[j]);
+        temb_mish[t * 32 + j] = mishf_ref(acc + b3[j]);
     }
 }
 

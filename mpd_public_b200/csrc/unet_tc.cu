@@ -1,0 +1,439 @@
+// TemporalUnet k=5 convolutions on the 5th-generation tensor cores (tcgen05 / TMEM), fed by bulk-async
+// (TMA engine) copies. One kernel = Conv1d(k5) + bias -> GroupNorm -> Mish [+ time cond] [+ residual identity |
+// + fused 1x1 residual conv in a second TMEM accumulator]  — reference layers.py:276-355.
+//
+// Implicit GEMM, "positions on M":
+//   D[r, n] = sum_tap sum_ci A[r + tap, ci] * W_tap[n, ci]
+//   r  = padded row of a tile of SPT whole samples (each sample = 2 zero rows + L rows + 2 zero rows),
+//        128 rows per CTA = the 128 TMEM lanes; rows that fall on a halo are computed and ignored;
+//   n  = 32 output channels per CTA (a whole number of GroupNorm groups);
+//   the k=5 window is NOT materialised: the activation tile is staged ONCE per K-chunk in the canonical
+//   no-swizzle K-major layout [k-group][row][8 x bf16] and each tap is the same tile with the matrix
+//   descriptor's start address advanced by one 16-byte row.
+//
+// Precision: fp32 parity with eps amplified by up to 4602x rules out plain bf16, so operands are split
+// x = hi + lo (two bf16 planes) and each K step issues 3 MMAs (hi*hi, lo*hi, hi*lo) into the same fp32 TMEM
+// accumulator (~2^-16 relative per product). The engine still runs the exact fp32 FMA path at the steps
+// where the schedule amplifies eps by more than `tc_amp_limit` (t = T-1), see engine.cu.
+//
+// Global "TC layout" of an activation [B, C, L] (one tensor per plane):
+//   plane[tile][C/8][132][8]  bf16,  tile = b / SPT, row = (b % SPT) * (L + 4) + l + 2 ; halo / spare rows are
+//   zero forever. A K-chunk of a CTA's tile is ONE contiguous block -> one cp.async.bulk per plane.
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+#include "common.cuh"
+#include "internal.h"
+
+namespace mpdb {
+
+constexpr int TC_STAGES = 4;
+constexpr int TC_THREADS = 128;
+constexpr int TC_A_PLANE_BYTES = (TC_KCH / 8) * TC_RT * 16;  // 8448
+constexpr int TC_B_TAP_BYTES = (TC_KCH / 8) * TC_NT * 16;    // 2048
+constexpr int TC_STAGE_BYTES = 2 * TC_A_PLANE_BYTES + 2 * 5 * TC_B_TAP_BYTES;  // 37376
+constexpr int TC_TMEM_COLS = 64;  // main accumulator [0,32) + residual-conv accumulator [32,64)
+
+// ---------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// Bounded wait: a protocol bug traps (visible CUDA error) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    const long long t0 = clock64();
+    while (true) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (done) break;
+        if (clock64() - t0 > 4000000000LL) __trap();
+    }
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// Shared-memory matrix descriptor, K-major, SWIZZLE_NONE (canonical layout ((8,n),2):((1,SBO),LBO) in 16-byte
+// units): 8 rows of a core matrix are contiguous 16-byte rows; SBO = distance between 8-row groups; LBO =
+// distance between the two 8-element k-groups of one K=16 MMA. Bits: [0,14) addr>>4, [16,30) LBO>>4,
+// [32,46) SBO>>4, [46,48) version = 1 (Blackwell), [61,64) layout type = 0.
+__device__ __forceinline__ uint64_t tc_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    return d;
+}
+// Instruction descriptor for kind::f16: c_format F32 (bit 4), a/b format BF16 (bits 7, 10), K-major A and B,
+// N >> 3 at bits [17,23), M >> 4 at bits [24,29).
+__host__ __device__ constexpr uint32_t tc_idesc(int M, int N) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+__device__ __forceinline__ void split_bf16(float x, unsigned short& hi, unsigned short& lo) {
+    __nv_bfloat16 h = __float2bfloat16_rn(x);
+    __nv_bfloat16 l = __float2bfloat16_rn(x - __bfloat162float(h));
+    hi = __bfloat16_as_ushort(h);
+    lo = __bfloat16_as_ushort(l);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// the kernel
+// ---------------------------------------------------------------------------------------------------
+template <int GS>
+__global__ void __launch_bounds__(TC_THREADS, 1) conv5_tc_kernel(TcConvArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    // carve-up: stages | barriers | tmem slot | epilogue scratch
+    unsigned char* stages = smem_raw;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + TC_STAGES * TC_STAGE_BYTES);  // full[4], empty[4], done
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_STAGES + 1);
+    float* part = reinterpret_cast<float*>(tmem_slot + 4);  // [128][8]
+    float* stat = part + 128 * 8;                           // [12 samples][8 groups]
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tile = blockIdx.x, ntile = blockIdx.y;
+    const int n0 = ntile * TC_NT;
+    const int Lp = a.L + 4;
+    const int SPT = TC_RT / Lp;
+    const int n_main = (a.c0 + a.c1) / TC_KCH;
+    const int n_res = a.res_w ? (a.rc0 + a.rc1) / TC_KCH : 0;
+    const int n_steps = n_main + n_res;
+
+    const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + TC_STAGES), done_bar = smem_u32(bars + 2 * TC_STAGES);
+    if (tid == 0) {
+        for (int s = 0; s < TC_STAGES; ++s) {
+            mbar_init(full0 + 8 * s, 1);
+            mbar_init(empty0 + 8 * s, 1);
+        }
+        mbar_init(done_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {  // TMEM allocation is a warp-wide operation; the same warp frees it at the end
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "r"(TC_TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (tid == 0) {
+        // ===== producer: bulk-async copies of the K-chunks (TMA engine, completion on the stage's mbarrier) =====
+        for (int i = 0; i < n_steps; ++i) {
+            const int s = i % TC_STAGES;
+            const uint32_t ph = (uint32_t)(i / TC_STAGES) & 1u;
+            mbar_wait(empty0 + 8 * s, ph ^ 1u);
+            const bool is_res = i >= n_main;
+            const int c = is_res ? i - n_main : i;
+            const int ntaps = is_res ? 1 : 5;
+            const int C0 = is_res ? a.rc0 : a.c0, C1 = is_res ? a.rc1 : a.c1;
+            const bool second = c * TC_KCH >= C0;
+            const unsigned short* ahi = is_res ? (second ? a.r1_hi : a.r0_hi) : (second ? a.in1_hi : a.in0_hi);
+            const unsigned short* alo = is_res ? (second ? a.r1_lo : a.r0_lo) : (second ? a.in1_lo : a.in0_lo);
+            const int Csrc = second ? C1 : C0;
+            const int kg0 = (c * TC_KCH - (second ? C0 : 0)) / 8;
+            const size_t aoff = ((size_t)tile * (Csrc / 8) + kg0) * TC_RT * 8;  // elements
+            const unsigned short* wsrc = is_res ? a.res_w + ((size_t)ntile * n_res + c) * (2 * 1 * TC_B_TAP_BYTES / 2)
+                                          : a.w + ((size_t)ntile * n_main + c) * (2 * 5 * TC_B_TAP_BYTES / 2);
+            const uint32_t bbytes = 2u * ntaps * TC_B_TAP_BYTES;
+            const uint32_t st = smem_u32(stages + (size_t)s * TC_STAGE_BYTES);
+            mbar_expect_tx(full0 + 8 * s, 2u * TC_A_PLANE_BYTES + bbytes);
+            bulk_g2s(st, ahi + aoff, TC_A_PLANE_BYTES, full0 + 8 * s);
+            bulk_g2s(st + TC_A_PLANE_BYTES, alo + aoff, TC_A_PLANE_BYTES, full0 + 8 * s);
+            bulk_g2s(st + 2 * TC_A_PLANE_BYTES, wsrc, bbytes, full0 + 8 * s);
+        }
+    } else if (tid == 32) {
+        // ===== MMA issuer: one thread drives the tensor core =====
+        constexpr uint32_t idesc = tc_idesc(128, TC_NT);
+        bool first_main = true, first_res = true;
+        for (int i = 0; i < n_steps; ++i) {
+            const int s = i % TC_STAGES;
+            const uint32_t ph = (uint32_t)(i / TC_STAGES) & 1u;
+            mbar_wait(full0 + 8 * s, ph);
+            tc_fence_after();
+            const bool is_res = i >= n_main;
+            const int ntaps = is_res ? 1 : 5;
+            const uint32_t st = smem_u32(stages + (size_t)s * TC_STAGE_BYTES);
+            const uint32_t a_hi = st, a_lo = st + TC_A_PLANE_BYTES;
+            const uint32_t b_hi = st + 2 * TC_A_PLANE_BYTES, b_lo = b_hi + ntaps * TC_B_TAP_BYTES;
+            const uint32_t dcol = tmem_base + (is_res ? TC_NT : 0);
+            for (int tap = 0; tap < ntaps; ++tap) {
+                const uint32_t row_shift = (is_res ? 2 : tap) * 16;  // the 1x1 residual conv reads the centre row
+#pragma unroll
+                for (int kk = 0; kk < TC_KCH / 16; ++kk) {
+                    const uint32_t aofs = kk * 2 * (TC_RT * 16) + row_shift;
+                    const uint32_t bofs = tap * TC_B_TAP_BYTES + kk * 2 * (TC_NT * 16);
+                    const uint64_t dah = tc_desc(a_hi + aofs, TC_RT * 16, 128), dal = tc_desc(a_lo + aofs, TC_RT * 16, 128);
+                    const uint64_t dbh = tc_desc(b_hi + bofs, TC_NT * 16, 128), dbl = tc_desc(b_lo + bofs, TC_NT * 16, 128);
+                    bool& first = is_res ? first_res : first_main;
+                    tc_mma_bf16(dcol, dah, dbh, idesc, first ? 0u : 1u);
+                    first = false;
+                    tc_mma_bf16(dcol, dal, dbh, idesc, 1u);
+                    tc_mma_bf16(dcol, dah, dbl, idesc, 1u);
+                }
+            }
+            tc_commit(empty0 + 8 * s);  // frees the stage when the MMAs that read it have retired
+        }
+        tc_commit(done_bar);  // accumulators complete
+    }
+
+    // ===== epilogue: all 4 warps; warp w owns TMEM lanes [32w, 32w+32) =====
+    mbar_wait(done_bar, 0);
+    __syncwarp();  // lanes 0 of warps 0/1 come from the producer / issuer loops: reconverge before .sync.aligned ops
+    tc_fence_after();
+    const int r = tid;  // padded row of the tile
+    const int s = r / Lp, l = r - s * Lp;
+    const int b = tile * SPT + s;
+    const bool valid = (s < SPT) && (l < a.L) && (b < a.B);
+    const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
+    float v[32];
+    tc_ld32(lane_base, v);
+
+    if (a.raw_out != nullptr) {
+        float* dst = a.raw_out + (((size_t)tile * gridDim.y + ntile) * 128 + r) * 32;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) dst[j] = v[j];
+    } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] += a.bias[n0 + j];
+
+        {
+            constexpr int NG = TC_NT / GS;  // GroupNorm groups inside this CTA's 32 channels
+            const float inv_n = 1.f / (float)(GS * a.L);
+            // ---- pass 1: mean (per-row partials -> fixed-order sum over the sample's rows) ----
+            float p[NG];
+#pragma unroll
+            for (int g = 0; g < NG; ++g) p[g] = 0.f;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) p[j / GS] += v[j];
+#pragma unroll
+            for (int g = 0; g < NG; ++g) part[r * 8 + g] = valid ? p[g] : 0.f;
+            __syncthreads();
+            if (tid < SPT * NG) {
+                const int ss = tid / NG, g = tid - ss * NG;
+                float t = 0.f;
+                for (int q = 0; q < a.L; ++q) t += part[(ss * Lp + q) * 8 + g];
+                stat[ss * 8 + g] = t * inv_n;
+            }
+            __syncthreads();
+            float mean[NG];
+#pragma unroll
+            for (int g = 0; g < NG; ++g) mean[g] = (s < SPT) ? stat[s * 8 + g] : 0.f;
+            __syncthreads();
+            // ---- pass 2: centred second moment ----
+#pragma unroll
+            for (int g = 0; g < NG; ++g) p[g] = 0.f;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const float d = v[j] - mean[j / GS];
+                p[j / GS] = fmaf(d, d, p[j / GS]);
+            }
+#pragma unroll
+            for (int g = 0; g < NG; ++g) part[r * 8 + g] = valid ? p[g] : 0.f;
+            __syncthreads();
+            if (tid < SPT * NG) {
+                const int ss = tid / NG, g = tid - ss * NG;
+                float t = 0.f;
+                for (int q = 0; q < a.L; ++q) t += part[(ss * Lp + q) * 8 + g];
+                stat[ss * 8 + g] = 1.0f / sqrtf(t * inv_n + 1e-5f);
+            }
+            __syncthreads();
+            float rstd[NG];
+#pragma unroll
+            for (int g = 0; g < NG; ++g) rstd[g] = (s < SPT) ? stat[s * 8 + g] : 0.f;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+                v[j] = mishf((v[j] - mean[j / GS]) * (rstd[j / GS] * a.gamma[n0 + j]) + a.beta[n0 + j]);
+        }
+        if (a.cond != nullptr && valid) {
+            const int tt = a.t_dev ? (int)a.t_dev[b] : a.t_uniform;
+            const float* cp = a.cond + (size_t)tt * a.CO + n0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] += cp[j];
+        }
+        if (a.res_w != nullptr) {
+            float rv[32];
+            tc_ld32(lane_base + TC_NT, rv);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] += rv[j] + a.res_bias[n0 + j];
+        } else if (a.res_cm != nullptr && valid) {
+            const float* rp = a.res_cm + ((size_t)b * a.CO + n0) * Lp + 2 + l;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] += rp[(size_t)j * Lp];
+        }
+        if (valid) {
+            if (a.out_cm != nullptr) {
+                float* op = a.out_cm + ((size_t)b * a.CO + n0) * Lp + 2 + l;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) op[(size_t)j * Lp] = v[j];
+            }
+            if (a.out_hi != nullptr) {
+                const size_t base = (((size_t)tile * (a.CO / 8) + n0 / 8) * TC_RT + (s * Lp + l + 2)) * 8;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    unsigned short h[8], lo8[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) split_bf16(v[q * 8 + e], h[e], lo8[e]);
+                    uint4 ph, pl;
+                    ph.x = h[0] | ((uint32_t)h[1] << 16); ph.y = h[2] | ((uint32_t)h[3] << 16);
+                    ph.z = h[4] | ((uint32_t)h[5] << 16); ph.w = h[6] | ((uint32_t)h[7] << 16);
+                    pl.x = lo8[0] | ((uint32_t)lo8[1] << 16); pl.y = lo8[2] | ((uint32_t)lo8[3] << 16);
+                    pl.z = lo8[4] | ((uint32_t)lo8[5] << 16); pl.w = lo8[6] | ((uint32_t)lo8[7] << 16);
+                    const size_t o = base + (size_t)q * TC_RT * 8;
+                    *reinterpret_cast<uint4*>(a.out_hi + o) = ph;
+                    *reinterpret_cast<uint4*>(a.out_lo + o) = pl;
+                }
+            }
+        }
+    }
+
+    // teardown: all TMEM reads done before the allocating warp frees the columns
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TC_TMEM_COLS) : "memory");
+    }
+}
+
+int launch_conv5_tc(const TcConvArgs& a, cudaStream_t stream) {
+    MPDB_REQUIRE(a.CO % TC_NT == 0, "tc conv: C_out must be a multiple of 32");
+    MPDB_REQUIRE(a.c0 % TC_KCH == 0 && a.c1 % TC_KCH == 0 && a.c0 > 0, "tc conv: input widths must be multiples of 32");
+    MPDB_REQUIRE(!a.res_w || (a.rc0 % TC_KCH == 0 && a.rc1 % TC_KCH == 0 && a.rc0 > 0), "tc conv: residual widths");
+    MPDB_REQUIRE(a.L + 4 <= TC_RT && a.L % 4 == 0, "tc conv: L too large for one 128-row tile");
+    MPDB_REQUIRE(a.gamma && a.beta && (a.gs == 4 || a.gs == 8 || a.gs == 16 || a.gs == 32),
+                 "tc conv: GroupNorm group size must be 4, 8, 16 or 32");
+    const int SPT = TC_RT / (a.L + 4);
+    MPDB_REQUIRE(SPT * (TC_NT / a.gs) <= 128 && SPT <= 12, "tc conv: too many statistics per tile");
+    const size_t smem = (size_t)TC_STAGES * TC_STAGE_BYTES + (2 * TC_STAGES + 1) * 8 + 16 + (128 * 8 + 12 * 8) * sizeof(float);
+    dim3 grid((a.B + SPT - 1) / SPT, a.CO / TC_NT);
+#define MPDB_TC_CASE(G)                                                                                         \
+    case G: {                                                                                                   \
+        static bool configured = false;                                                                         \
+        if (!configured) {                                                                                      \
+            MPDB_CHECK_CUDA(cudaFuncSetAttribute(conv5_tc_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                                 200 * 1024));                                                  \
+            configured = true;                                                                                  \
+        }                                                                                                       \
+        conv5_tc_kernel<G><<<grid, TC_THREADS, smem, stream>>>(a);                                              \
+        break;                                                                                                  \
+    }
+    switch (a.gs) {
+        MPDB_TC_CASE(4)
+        MPDB_TC_CASE(8)
+        MPDB_TC_CASE(16)
+        MPDB_TC_CASE(32)
+        default: MPDB_REQUIRE(false, "tc conv: bad group size");
+    }
+#undef MPDB_TC_CASE
+    MPDB_LAUNCH_CHECK();
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// packing helpers
+// ---------------------------------------------------------------------------------------------------
+// weights: src fp32 [ci][ntaps][CO] (the SIMT path's packed layout) ->
+//   dst bf16 [CO/32][CI/32][plane hi|lo][ntaps][kg 4][n 32][8]
+__global__ void pack_tc_weights_kernel(const float* __restrict__ src, unsigned short* __restrict__ dst, int CI, int CO, int ntaps) {
+    const long long n = (long long)CI * CO * ntaps;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int e = (int)(i % 8);
+        const int nn = (int)((i / 8) % TC_NT);
+        const int kg = (int)((i / (8 * TC_NT)) % (TC_KCH / 8));
+        const int tap = (int)((i / (8 * TC_NT * (TC_KCH / 8))) % ntaps);
+        const long long rest = i / ((long long)8 * TC_NT * (TC_KCH / 8) * ntaps);
+        const int chunk = (int)(rest % (CI / TC_KCH));
+        const int ntile = (int)(rest / (CI / TC_KCH));
+        const int ci = chunk * TC_KCH + kg * 8 + e;
+        const int co = ntile * TC_NT + nn;
+        unsigned short hi, lo;
+        split_bf16(src[((long long)ci * ntaps + tap) * CO + co], hi, lo);
+        const long long blk = ((long long)ntile * (CI / TC_KCH) + chunk) * (2LL * ntaps * (TC_KCH / 8) * TC_NT * 8);
+        const long long in_plane = (((long long)tap * (TC_KCH / 8) + kg) * TC_NT + nn) * 8 + e;
+        const long long plane = (long long)ntaps * (TC_KCH / 8) * TC_NT * 8;
+        dst[blk + in_plane] = hi;
+        dst[blk + plane + in_plane] = lo;
+    }
+}
+
+int launch_pack_tc_weights(const float* src, unsigned short* dst, int CI, int CO, int ntaps, cudaStream_t stream) {
+    long long n = (long long)CI * CO * ntaps;
+    int blocks = (int)((n + 255) / 256);
+    if (blocks > 2048) blocks = 2048;
+    pack_tc_weights_kernel<<<blocks, 256, 0, stream>>>(src, dst, CI, CO, ntaps);
+    MPDB_LAUNCH_CHECK();
+    return 0;
+}
+
+// activation fp32 CM [B][C][L+4] -> TC layout planes (used by tests and for inputs produced outside the TC path)
+__global__ void cm_to_tc_kernel(const float* __restrict__ cm, unsigned short* __restrict__ hi, unsigned short* __restrict__ lo, int B,
+                                int C, int L) {
+    const int Lp = L + 4, SPT = TC_RT / Lp;
+    const long long n = (long long)B * C * L;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int l = (int)(i % L);
+        const int c = (int)((i / L) % C);
+        const int b = (int)(i / ((long long)L * C));
+        unsigned short h, lw;
+        split_bf16(cm[((long long)b * C + c) * Lp + 2 + l], h, lw);
+        const int tile = b / SPT, s = b - tile * SPT;
+        const long long o = (((long long)tile * (C / 8) + c / 8) * TC_RT + (s * Lp + l + 2)) * 8 + (c % 8);
+        hi[o] = h;
+        lo[o] = lw;
+    }
+}
+
+int launch_cm_to_tc(const float* cm, unsigned short* hi, unsigned short* lo, int B, int C, int L, cudaStream_t stream) {
+    long long n = (long long)B * C * L;
+    int blocks = (int)((n + 255) / 256);
+    if (blocks > 2048) blocks = 2048;
+    cm_to_tc_kernel<<<blocks, 256, 0, stream>>>(cm, hi, lo, B, C, L);
+    MPDB_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // namespace mpdb
