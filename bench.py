@@ -238,6 +238,7 @@ def main():
     ap.add_argument("--workload", default="cfg4", choices=list(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--tc", default="auto", choices=["auto", "off", "force"])
     args = ap.parse_args()
 
     if args.impl == "reference":
@@ -265,6 +266,7 @@ def main():
     mid, H, B, opt, wc, ws = WORKLOADS[args.workload]
     model, guide, ds, prob, sd, n_grid = build_problem(args.workload, device)
     model.use_cuda_graph = not args.no_graph
+    model.tensor_cores = args.tc
     D = prob.robot.state_dim
     kw = sample_kwargs(guide)
     start_goal_host = torch.vstack((torch.as_tensor(prob.start), torch.as_tensor(prob.goal))).pin_memory()
@@ -343,9 +345,10 @@ def main():
         x0 = noise[0].contiguous()
         _lib.check(lib.mpdb_profile_forward(eng.handle, _lib.fptr(x0), 5, B, 20, ms, fl, md, _lib.stream_ptr(device)))
         ms, fl, md = np.array(ms[:]), np.array(fl[:]), np.array(md[:])
-        conv5 = md == 0
+        tcm = md == 5
+        dom = tcm if tcm.any() else (md == 0)
         fwd_ms = float(ms.sum())
-        conv5_ms, conv5_flops = float(ms[conv5].sum()), float(fl[conv5].sum())
+        dom_ms, dom_flops = float(ms[dom].sum()), float(fl[dom].sum())
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -353,15 +356,22 @@ def main():
             pass
         peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
         peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)"
-        ach_tf = conv5_flops / (conv5_ms * 1e-3) / 1e12
+        ach_tf = dom_flops / (dom_ms * 1e-3) / 1e12
         flops_traj, sdf_bytes = algorithmic_work(H, D, opt, prob.robot.n_spheres, n_grid, prob.robot.ws_dim)
-        roofline = {"kernel": "mpdb::conv_kernel<MODE_CONV5> (Conv1d k5 + GroupNorm + Mish [+cond][+residual]), "
-                              f"{int(conv5.sum())} launches per UNet forward",
-                    "bound": "tensor", "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach_tf / peak_tf,
-                    "traffic": None, "peak_source": peak_src,
-                    "note": "fp32 CUDA-core FMA kernel (exact fp32 parity path); achieved = algorithmic 2*MAC FLOPs of "
-                            "its launches / their summed CUDA-event time; share of one UNet forward "
-                            f"{conv5_ms / fwd_ms:.3f}",
+        if tcm.any():
+            kname = ("mpdb::conv5_tc_kernel (tcgen05.mma kind::f16 split-bf16 x3, TMEM accumulators, cp.async.bulk staging; "
+                     f"Conv1d k5 + GroupNorm + Mish [+cond][+residual]), {int(dom.sum())} launches per UNet forward")
+            note = ("achieved = algorithmic (useful) 2*MAC FLOPs of its launches / their summed CUDA-event time; the tensor "
+                    "pipe issues 3x that (hi*hi + lo*hi + hi*lo); share of one UNet forward "
+                    f"{dom_ms / fwd_ms:.3f}")
+        else:
+            kname = ("mpdb::conv_kernel<MODE_CONV5> (fp32 FMA; Conv1d k5 + GroupNorm + Mish [+cond][+residual]), "
+                     f"{int(dom.sum())} launches per UNet forward")
+            note = ("fp32 CUDA-core FMA kernel (exact fp32 parity path); achieved = algorithmic 2*MAC FLOPs of its launches / "
+                    f"their summed CUDA-event time; share of one UNet forward {dom_ms / fwd_ms:.3f}")
+        roofline = {"kernel": kname, "bound": "tensor", "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s",
+                    "frac": ach_tf / peak_tf, "traffic": None, "peak_source": peak_src, "note": note,
+                    "issued_tflops": ach_tf * (3 if tcm.any() else 1),
                     "unet_forward_ms": fwd_ms, "unet_flops_per_trajectory_per_forward": flops_traj,
                     "per_launch_us": [round(float(v) * 1e3, 2) for v in ms], "per_launch_mode": [int(v) for v in md]}
         # guide kernel (HBM-bound by construction; at B=100 it is latency-bound)
@@ -385,7 +395,7 @@ def main():
                           "note": "run_inference() with start/goal from pinned host memory, noise drawn on the device by "
                                   "the API as in the reference (diffusion_model_base.py:165), plans copied to pinned host"},
                   "gpu_launches": int(launches), "roofline": roofline, "roofline_sdf": roofline_sdf,
-                  "cuda_graph": bool(model.use_cuda_graph)}
+                  "cuda_graph": bool(model.use_cuda_graph), "tensor_cores": model.tensor_cores}
         if n_gpus == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
             run, Bc = cpu_oracle_runner(args.workload, threads)

@@ -104,6 +104,10 @@ int mpdb_engine_set_schedule(mpdb_engine* e, const float* sqrt_recip_alphas_cump
                              const float* sqrt_recipm1_alphas_cumprod, const float* posterior_mean_coef1,
                              const float* posterior_mean_coef2, const float* posterior_log_variance_clipped,
                              const float* posterior_std, const float* posterior_var);
+/* options: "tc_mode" = 0 exact fp32 FMA path only | 1 auto (default: tcgen05 split-bf16 path for the k=5 layers at
+ * every loop step whose sqrt(1/abar_t - 1) <= tc_amp_limit, exact path otherwise and for the per-call entry points)
+ * | 2 force tensor cores everywhere; "tc_amp_limit" (default 64) */
+int mpdb_engine_set_option(mpdb_engine* e, const char* name, double value);
 /* repack weights, precompute the time-conditioning tables; errors if a parameter is missing */
 int mpdb_engine_finalize(mpdb_engine* e, void* stream);
 
@@ -135,6 +139,10 @@ int mpdb_profile_guide(mpdb_guide* g, float* x, int32_t B, int32_t H, int32_t re
  * SPT = 132/(L+4); row r of a tile holds sample (b % SPT), position l at r = (b % SPT)*(L+4) + l. */
 int mpdb_debug_tc_conv5(const float* x_cm, const float* w, float* raw, int32_t B, int32_t CI, int32_t CO, int32_t L,
                         void* stream);
+
+/* debugging: with option "timeline" = 1, clock64 stamps (8 per layer) of CTA (0,0) of every tensor-core conv of the
+ * last forward; host_out holds 8 * max_ops int64 */
+int mpdb_engine_read_timeline(mpdb_engine* e, int64_t* host_out, int32_t max_ops);
 
 /* debugging / parity: intermediate activations of the last mpdb_unet_forward */
 int mpdb_engine_num_buffers(mpdb_engine* e);

@@ -54,6 +54,7 @@ SYMBOLS = {
     "mpdb_engine_destroy": (None, [_P]),
     "mpdb_engine_set_param": (C.c_int, [_P, C.c_char_p, _P, C.c_int64, _P]),
     "mpdb_engine_set_schedule": (C.c_int, [_P] + [C.POINTER(C.c_float)] * 7),
+    "mpdb_engine_set_option": (C.c_int, [_P, C.c_char_p, C.c_double]),
     "mpdb_engine_finalize": (C.c_int, [_P, _P]),
     "mpdb_unet_forward": (C.c_int, [_P, _P, _P, _P, C.c_int32, _P]),
     "mpdb_p_mean": (C.c_int, [_P, _P, _P, _P, C.c_int32, _P]),
@@ -65,6 +66,7 @@ SYMBOLS = {
                                        C.POINTER(C.c_int32), _P]),
     "mpdb_profile_guide": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_float), _P]),
     "mpdb_debug_tc_conv5": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P]),
+    "mpdb_engine_read_timeline": (C.c_int, [_P, C.POINTER(C.c_int64), C.c_int32]),
     "mpdb_engine_num_buffers": (C.c_int, [_P]),
     "mpdb_engine_buffer_info": (C.c_int, [_P, C.c_int, C.c_char_p, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "mpdb_engine_read_buffer": (C.c_int, [_P, C.c_int, _P, C.c_int32, _P]),

@@ -59,6 +59,13 @@ __device__ __forceinline__ float mishf(float x) {
     const float n = e * (e + 2.f);
     return x > 20.f ? x : x * __fdiv_rn(n, n + 2.f);
 }
+// fast variant for the tensor-core epilogue (ex2.approx + rcp.approx, ~1e-6 relative; the split-bf16 MMA itself is
+// ~1e-5): the epilogue is instruction-issue bound, so the ~40-instruction precise version would dominate it.
+__device__ __forceinline__ float mishf_fast(float x) {
+    const float e = __expf(fminf(x, 20.f));
+    const float n = e * (e + 2.f);
+    return x > 20.f ? x : x * __fdividef(n, n + 2.f);
+}
 // reference-composition variant (used once per load for the time tables, where cost does not matter)
 __device__ __forceinline__ float mishf_ref(float x) { return x * tanhf(log1pf(expf(x))); }
 

@@ -55,6 +55,10 @@ struct ConvOp {
     long long w = -1, bias = -1, gamma = -1, beta = -1, cond = -1, res_w = -1, res_bias = -1;  // packed offsets
     int CO = 0, L_in = 0, L_out = 0, gs = 4;
     bool gn = false;
+    // tensor-core path (unet_tc.cu)
+    bool tc_ok = false;
+    int cin = 0, res_cin = 0;
+    long long w_tc = -1, res_w_tc = -1;  // offsets (bf16 elements) into packed_tc
 };
 
 }  // namespace mpdb
@@ -74,7 +78,15 @@ struct mpdb_engine {
     std::vector<ConvOp> ops;
     std::vector<PackJob> packs;
     std::vector<std::pair<std::string, long long>> cond_jobs;  // cond_mlp prefix -> table offset
-    float* work = nullptr;    // activations
+    float* work = nullptr;    // activations (fp32, channel-major with halo)
+    unsigned short* packed_tc = nullptr;  // split-bf16 weights in tensor-core layout
+    long long packed_tc_elems = 0;
+    unsigned short* work_tc = nullptr;    // activations in tensor-core layout (bf16 hi/lo planes)
+    std::vector<long long> tc_off, tc_plane;  // per buffer: offset of the hi plane, elements per plane
+    long long* dbg_buf = nullptr;  // optional per-op timeline stamps (option "timeline")
+    int timeline = 0;
+    int tc_mode = 1;           // 0 = exact fp32 FMA path only, 1 = auto (loop steps below tc_amp_limit), 2 = force
+    float tc_amp_limit = 64.f; // steps whose sqrt(1/abar - 1) exceeds this run the exact path (t = T-1)
     long long work_floats_per_sample = 0;
     int work_batch = 0;
     long long final_w = -1, final_b = -1;
@@ -265,6 +277,31 @@ static int build_plan(mpdb_engine* e, PlanBuilder& pb) {
         pb.packs.push_back({"final_conv.1.bias", e->final_b, c.state_dim, 1, 0, 0});
     }
     MPDB_REQUIRE(L == c.horizon, "internal: plan length mismatch");
+    // which k=5 layers can run on the tensor cores
+    auto chans = [&](int id0, int id1) {
+        int cc = 0;
+        if (id0 == -1) cc += c.state_dim; else if (id0 >= 0) cc += e->bufs[id0].C;
+        if (id1 >= 0) cc += e->bufs[id1].C;
+        return cc;
+    };
+    for (ConvOp& op : e->ops) {
+        op.cin = chans(op.in0, op.in1);
+        op.res_cin = op.res_w >= 0 ? chans(op.res0, op.res1) : 0;
+        const bool main_ok = op.mode == MODE_CONV5 && op.in0 >= 0 && op.cin % TC_KCH == 0 &&
+                             (op.in1 < 0 || e->bufs[op.in0].C % TC_KCH == 0);
+        const bool res_ok = op.res_w < 0 || (op.res0 >= 0 && op.res_cin % TC_KCH == 0 &&
+                                             (op.res1 < 0 || e->bufs[op.res0].C % TC_KCH == 0));
+        const bool gn_ok = op.gn && (op.gs == 4 || op.gs == 8 || op.gs == 16 || op.gs == 32);
+        op.tc_ok = main_ok && res_ok && gn_ok && op.CO % TC_NT == 0 && op.L_out + 4 <= TC_RT;
+        if (op.tc_ok) {
+            op.w_tc = e->packed_tc_elems;
+            e->packed_tc_elems += 2LL * op.cin * op.CO * 5;
+            if (op.res_w >= 0) {
+                op.res_w_tc = e->packed_tc_elems;
+                e->packed_tc_elems += 2LL * op.res_cin * op.CO;
+            }
+        }
+    }
     return 0;
 }
 
@@ -277,6 +314,24 @@ static int ensure_workspace(mpdb_engine* e, int B) {
     size_t bytes = sizeof(float) * (size_t)e->work_floats_per_sample * (size_t)B;
     MPDB_CHECK_CUDA(cudaMalloc(&e->work, bytes));
     MPDB_CHECK_CUDA(cudaMemset(e->work, 0, bytes));  // halo columns stay zero forever
+    {
+        if (e->work_tc) cudaFree(e->work_tc);
+        e->work_tc = nullptr;
+        e->tc_off.assign(e->bufs.size(), 0);
+        e->tc_plane.assign(e->bufs.size(), 0);
+        long long total = 0;
+        for (size_t k = 0; k < e->bufs.size(); ++k) {
+            const int Lp = e->bufs[k].L + 2 * HALO;
+            if (Lp > TC_RT || e->bufs[k].C % 8) continue;  // no TC layout for this buffer
+            const int SPT = TC_RT / Lp;
+            const long long tiles = (B + SPT - 1) / SPT;
+            e->tc_plane[k] = tiles * (e->bufs[k].C / 8) * TC_RT * 8;
+            e->tc_off[k] = total;
+            total += 2 * e->tc_plane[k];
+        }
+        MPDB_CHECK_CUDA(cudaMalloc(&e->work_tc, sizeof(unsigned short) * (size_t)(total > 0 ? total : 8)));
+        MPDB_CHECK_CUDA(cudaMemset(e->work_tc, 0, sizeof(unsigned short) * (size_t)(total > 0 ? total : 8)));
+    }
     for (int k = 0; k < 2; ++k) {
         if (e->xbuf[k]) cudaFree(e->xbuf[k]);
         MPDB_CHECK_CUDA(cudaMalloc(&e->xbuf[k], sizeof(float) * (size_t)B * e->cfg.horizon * e->cfg.state_dim));
@@ -304,7 +359,33 @@ static ConvSrc make_src(mpdb_engine* e, int id0, int id1, const float* x_ext, in
 }
 
 static int launch_op(mpdb_engine* e, const ConvOp& op, const float* x, const long long* t_dev, int t_uniform, int B,
-                     cudaStream_t st) {
+                     cudaStream_t st, bool tc) {
+    auto hi = [&](int id) -> unsigned short* { return e->tc_plane[id] ? e->work_tc + e->tc_off[id] : nullptr; };
+    auto lo = [&](int id) -> unsigned short* { return e->tc_plane[id] ? e->work_tc + e->tc_off[id] + e->tc_plane[id] : nullptr; };
+    if (tc && op.tc_ok) {
+        TcConvArgs a;
+        memset(&a, 0, sizeof(a));
+        a.in0_hi = hi(op.in0); a.in0_lo = lo(op.in0); a.c0 = e->bufs[op.in0].C;
+        if (op.in1 >= 0) { a.in1_hi = hi(op.in1); a.in1_lo = lo(op.in1); a.c1 = e->bufs[op.in1].C; }
+        a.w = e->packed_tc + op.w_tc;
+        a.bias = e->packed + op.bias;
+        a.gamma = e->packed + op.gamma;
+        a.beta = e->packed + op.beta;
+        if (op.cond >= 0) { a.cond = e->packed + op.cond; a.t_dev = t_dev; a.t_uniform = t_uniform; }
+        if (op.res_w >= 0) {
+            a.r0_hi = hi(op.res0); a.r0_lo = lo(op.res0); a.rc0 = e->bufs[op.res0].C;
+            if (op.res1 >= 0) { a.r1_hi = hi(op.res1); a.r1_lo = lo(op.res1); a.rc1 = e->bufs[op.res1].C; }
+            a.res_w = e->packed_tc + op.res_w_tc;
+            a.res_bias = e->packed + op.res_bias;
+        } else if (op.res0 >= 0) {
+            a.res_cm = buf_ptr(e, op.res0, e->work_batch);
+        }
+        a.out_cm = const_cast<float*>(buf_ptr(e, op.out, e->work_batch));
+        a.out_hi = hi(op.out); a.out_lo = lo(op.out);
+        a.CO = op.CO; a.L = op.L_out; a.B = B; a.gs = op.gs;
+        if (e->timeline && e->dbg_buf) a.dbg = e->dbg_buf + (&op - e->ops.data()) * 8;
+        return launch_conv5_tc(a, st);
+    }
     ConvArgs a;
     memset(&a, 0, sizeof(a));
     a.in = make_src(e, op.in0, op.in1, x, op.L_in);
@@ -317,15 +398,17 @@ static int launch_op(mpdb_engine* e, const ConvOp& op, const float* x, const lon
         if (op.res_w >= 0) { a.res_w = e->packed + op.res_w; a.res_bias = e->packed + op.res_bias; }
     }
     a.out = const_cast<float*>(buf_ptr(e, op.out, e->work_batch));
+    if (tc) { a.out_hi = hi(op.out); a.out_lo = lo(op.out); }  // consumers on the tensor-core path read this copy
     a.CO = op.CO; a.L_out = op.L_out; a.B = B; a.gs = op.gs;
     choose_tile(op.mode, &a);
     return launch_conv(op.mode, a, st);
 }
 
 // Runs every layer up to (and including) final_conv.0; the 1x1 projection is fused into launch_final.
-static int run_unet_body(mpdb_engine* e, const float* x, const long long* t_dev, int t_uniform, int B, cudaStream_t st) {
+static int run_unet_body(mpdb_engine* e, const float* x, const long long* t_dev, int t_uniform, int B, cudaStream_t st,
+                         bool tc) {
     for (const ConvOp& op : e->ops)
-        if (launch_op(e, op, x, t_dev, t_uniform, B, st)) return 1;
+        if (launch_op(e, op, x, t_dev, t_uniform, B, st, tc)) return 1;
     return 0;
 }
 
@@ -388,6 +471,7 @@ extern "C" int mpdb_engine_create(const mpdb_engine_config* cfg, int device, mpd
     MPDB_CHECK_CUDA(cudaMalloc(&e->packed, sizeof(float) * (size_t)(e->packed_floats + 32 * cfg->n_diffusion_steps)));
     MPDB_CHECK_CUDA(cudaMemset(e->packed, 0, sizeof(float) * (size_t)(e->packed_floats + 32 * cfg->n_diffusion_steps)));
     MPDB_CHECK_CUDA(cudaMalloc(&e->sched, sizeof(float) * 7 * (size_t)cfg->n_diffusion_steps));
+    MPDB_CHECK_CUDA(cudaMalloc(&e->packed_tc, sizeof(unsigned short) * (size_t)(e->packed_tc_elems > 0 ? e->packed_tc_elems : 8)));
     e->packs = pb.packs;
     e->cond_jobs = pb.cond_jobs;
     if (ensure_workspace(e.get(), cfg->max_batch > 0 ? cfg->max_batch : 1)) return 1;
@@ -401,6 +485,7 @@ extern "C" void mpdb_engine_destroy(mpdb_engine* e) {
     cudaDeviceSynchronize();
     if (e->graph_exec) cudaGraphExecDestroy(e->graph_exec);
     cudaFree(e->raw); cudaFree(e->packed); cudaFree(e->work); cudaFree(e->sched);
+    cudaFree(e->packed_tc); cudaFree(e->work_tc); cudaFree(e->dbg_buf);
     cudaFree(e->xbuf[0]); cudaFree(e->xbuf[1]); cudaFree(e->flags);
     cudaFree(e->g_noise); cudaFree(e->g_hc); cudaFree(e->g_chain);
     delete e;
@@ -433,6 +518,26 @@ extern "C" int mpdb_engine_set_schedule(mpdb_engine* e, const float* sr, const f
     return 0;
 }
 
+extern "C" int mpdb_engine_set_option(mpdb_engine* e, const char* name, double value) {
+    MPDB_REQUIRE(e && name, "mpdb_engine_set_option: null argument");
+    const std::string n(name);
+    if (n == "tc_mode") {
+        MPDB_REQUIRE(value == 0 || value == 1 || value == 2, "tc_mode must be 0 (off), 1 (auto) or 2 (force)");
+        e->tc_mode = (int)value;
+    } else if (n == "timeline") {
+        e->timeline = value != 0;
+        if (e->timeline && !e->dbg_buf) {
+            MPDB_CHECK_CUDA(cudaMalloc(&e->dbg_buf, sizeof(long long) * 8 * e->ops.size()));
+            MPDB_CHECK_CUDA(cudaMemset(e->dbg_buf, 0, sizeof(long long) * 8 * e->ops.size()));
+        }
+    } else if (n == "tc_amp_limit") {
+        e->tc_amp_limit = (float)value;
+    } else {
+        MPDB_REQUIRE(false, "unknown option '" + n + "'");
+    }
+    return 0;
+}
+
 extern "C" int mpdb_engine_finalize(mpdb_engine* e, void* stream) {
     MPDB_REQUIRE(e, "mpdb_engine_finalize: null engine");
     cudaStream_t st = (cudaStream_t)stream;
@@ -449,6 +554,12 @@ extern "C" int mpdb_engine_finalize(mpdb_engine* e, void* stream) {
         } else {
             if (launch_repack_conv(src, dst, j.CO, j.CI, j.K, j.transposed, st)) return 1;
         }
+    }
+    for (const ConvOp& op : e->ops) {
+        if (!op.tc_ok) continue;
+        if (launch_pack_tc_weights(e->packed + op.w, e->packed_tc + op.w_tc, op.cin, op.CO, 5, st)) return 1;
+        if (op.res_w >= 0 && launch_pack_tc_weights(e->packed + op.res_w, e->packed_tc + op.res_w_tc, op.res_cin, op.CO, 1, st))
+            return 1;
     }
     const int T = e->cfg.n_diffusion_steps;
     float* temb = e->packed + e->packed_floats;  // [T][32] scratch behind the packed parameters
@@ -474,7 +585,7 @@ extern "C" int mpdb_unet_forward(mpdb_engine* e, const float* x, const int64_t* 
     cudaStream_t st = (cudaStream_t)stream;
     MPDB_CHECK_CUDA(cudaSetDevice(e->device));
     if (ensure_workspace(e, B)) return 1;
-    if (run_unet_body(e, x, (const long long*)t, 0, B, st)) return 1;
+    if (run_unet_body(e, x, (const long long*)t, 0, B, st, e->tc_mode == 2)) return 1;
     FinalArgs f;
     fill_final(e, f, x, (const long long*)t, 0, B);
     f.mode = 0;
@@ -488,7 +599,7 @@ extern "C" int mpdb_p_mean(mpdb_engine* e, const float* x, const int64_t* t, flo
     cudaStream_t st = (cudaStream_t)stream;
     MPDB_CHECK_CUDA(cudaSetDevice(e->device));
     if (ensure_workspace(e, B)) return 1;
-    if (run_unet_body(e, x, (const long long*)t, 0, B, st)) return 1;
+    if (run_unet_body(e, x, (const long long*)t, 0, B, st, e->tc_mode == 2)) return 1;
     FinalArgs f;
     fill_final(e, f, x, (const long long*)t, 0, B);
     f.mode = 1;
@@ -535,7 +646,10 @@ static int enqueue_loop(mpdb_engine* e, mpdb_guide* g, const mpdb_loop_params* p
         const bool guided = g != nullptr && p->n_guide_steps > 0 && (long long)i < (long long)p->t_start_guide;
         const float ns = p->noise_std ? p->noise_std[it] : 1.0f;
 
-        if (run_unet_body(e, cur, nullptr, t, B, st)) return 1;
+        // condition-aware precision: the split-bf16 tensor-core path everywhere except where the schedule
+        // amplifies eps beyond tc_amp_limit (t = T-1: 4602x), which runs the exact fp32 FMA path
+        const bool tc = e->tc_mode == 2 || (e->tc_mode == 1 && e->sched_host[1 * (size_t)T + t] <= e->tc_amp_limit);
+        if (run_unet_body(e, cur, nullptr, t, B, st, tc)) return 1;
         FinalArgs f;
         fill_final(e, f, cur, nullptr, t, B);
         f.n_hc = p->n_hard_conds;
@@ -642,7 +756,8 @@ extern "C" int mpdb_sample_loop(mpdb_engine* e, mpdb_guide* g, const mpdb_loop_p
     std::string key = std::to_string(B) + "|" + std::to_string((long long)(uintptr_t)g) + "|" +
                       std::to_string(p->n_steps_without_noise) + "|" + std::to_string(p->t_start_guide) + "|" +
                       std::to_string(p->n_guide_steps) + "|" + std::to_string(p->scale_grad_by_std) + "|" +
-                      std::to_string(chain_out != nullptr) + "|" + std::to_string(p->n_hard_conds);
+                      std::to_string(chain_out != nullptr) + "|" + std::to_string(p->n_hard_conds) + "|tc" +
+                      std::to_string(e->tc_mode) + "/" + std::to_string(e->tc_amp_limit);
     for (int k = 0; k < p->n_hard_conds; ++k) key += "," + std::to_string(p->hard_cond_rows[k]);
     for (int k = 0; k < n_iters; ++k) {
         float v = p->noise_std ? p->noise_std[k] : 1.0f;
@@ -748,19 +863,20 @@ extern "C" int mpdb_profile_forward(mpdb_engine* e, const float* x, int32_t t, i
     cudaEvent_t ev0, ev1;
     MPDB_CHECK_CUDA(cudaEventCreate(&ev0));
     MPDB_CHECK_CUDA(cudaEventCreate(&ev1));
-    if (run_unet_body(e, x, nullptr, t, B, st)) return 1;  // warm-up, fills every buffer
+    const bool tc = e->tc_mode != 0;
+    if (run_unet_body(e, x, nullptr, t, B, st, tc)) return 1;  // warm-up, fills every buffer
     int k = 0;
     for (const ConvOp& op : e->ops) {
         MPDB_CHECK_CUDA(cudaEventRecord(ev0, st));
         for (int r = 0; r < reps; ++r)
-            if (launch_op(e, op, x, nullptr, t, B, st)) return 1;
+            if (launch_op(e, op, x, nullptr, t, B, st, tc)) return 1;
         MPDB_CHECK_CUDA(cudaEventRecord(ev1, st));
         MPDB_CHECK_CUDA(cudaEventSynchronize(ev1));
         float ms = 0.f;
         MPDB_CHECK_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
         ms_out[k] = ms / reps;
         flops_out[k] = op_flops(e, op, B);
-        mode_out[k] = op.mode;
+        mode_out[k] = (tc && op.tc_ok) ? 5 : op.mode;  // 5 = tcgen05 conv5
         ++k;
     }
     {
@@ -821,5 +937,15 @@ extern "C" int mpdb_debug_tc_conv5(const float* x_cm, const float* w, float* raw
     cudaFree(wp); cudaFree(wt); cudaFree(xh); cudaFree(xl);
     if (rc) return rc;
     MPDB_CHECK_CUDA(e1);
+    return 0;
+}
+
+// Debug: clock64 stamps (8 per op) of CTA (0,0) of every tensor-core conv of the last forward (option "timeline").
+extern "C" int mpdb_engine_read_timeline(mpdb_engine* e, int64_t* host_out, int32_t max_ops) {
+    MPDB_REQUIRE(e && host_out && e->dbg_buf, "mpdb_engine_read_timeline: timeline not enabled");
+    MPDB_CHECK_CUDA(cudaSetDevice(e->device));
+    MPDB_CHECK_CUDA(cudaDeviceSynchronize());
+    int n = (int)e->ops.size() < max_ops ? (int)e->ops.size() : max_ops;
+    MPDB_CHECK_CUDA(cudaMemcpy(host_out, e->dbg_buf, sizeof(long long) * 8 * n, cudaMemcpyDeviceToHost));
     return 0;
 }

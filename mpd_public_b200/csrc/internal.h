@@ -76,6 +76,7 @@ struct TcConvArgs {
     float* out_cm;                // fp32 CM output (may be null)
     unsigned short *out_hi, *out_lo;  // TC-layout output (may be null)
     float* raw_out;               // debug: raw main accumulator [tile][ntile][128][32]
+    long long* dbg;               // debug: 8 clock64 stamps of CTA (0,0) (null = off)
     int CO, L, B, gs;
 };
 int launch_conv5_tc(const TcConvArgs& a, cudaStream_t stream);

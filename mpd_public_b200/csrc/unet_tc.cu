@@ -12,8 +12,10 @@
 //   descriptor's start address advanced by one 16-byte row.
 //
 // Precision: fp32 parity with eps amplified by up to 4602x rules out plain bf16, so operands are split
-// x = hi + lo (two bf16 planes) and each K step issues 3 MMAs (hi*hi, lo*hi, hi*lo) into the same fp32 TMEM
-// accumulator (~2^-16 relative per product). The engine still runs the exact fp32 FMA path at the steps
+// x = hi + lo (two bf16 planes) and each K step computes hi*hi + lo*hi + hi*lo with fp32 TMEM accumulation
+// (~2^-16 relative per product) in TWO MMAs: the weight tile stores [hi rows | lo rows] as one N=64 operand, so
+// A_hi x [W_hi;W_lo] yields hi*hi and hi*lo with a single shared-memory read of A_hi (SS-mode MMAs at small N are
+// bound by the A-operand read), and A_lo x W_hi accumulates into the hi*hi columns. The engine still runs the exact fp32 FMA path at the steps
 // where the schedule amplifies eps by more than `tc_amp_limit` (t = T-1), see engine.cu.
 //
 // Global "TC layout" of an activation [B, C, L] (one tensor per plane):
@@ -28,11 +30,11 @@
 namespace mpdb {
 
 constexpr int TC_STAGES = 4;
-constexpr int TC_THREADS = 128;
+constexpr int TC_THREADS = 512;  // 16 warps: warp w reads TMEM lane quarter (w & 3), column group (w >> 2)
 constexpr int TC_A_PLANE_BYTES = (TC_KCH / 8) * TC_RT * 16;  // 8448
 constexpr int TC_B_TAP_BYTES = (TC_KCH / 8) * TC_NT * 16;    // 2048
 constexpr int TC_STAGE_BYTES = 2 * TC_A_PLANE_BYTES + 2 * 5 * TC_B_TAP_BYTES;  // 37376
-constexpr int TC_TMEM_COLS = 64;  // main accumulator [0,32) + residual-conv accumulator [32,64)
+constexpr int TC_TMEM_COLS = 128;  // main: [0,32) = hi*hi + lo*hi, [32,64) = hi*lo ; residual conv: [64,96), [96,128)
 
 // ---------------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -112,6 +114,16 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, float (&v)[32]) {
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+__device__ __forceinline__ void tc_ld8(uint32_t taddr, float (&v)[8]) {
+    uint32_t r[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+
 __device__ __forceinline__ void split_bf16(float x, unsigned short& hi, unsigned short& lo) {
     __nv_bfloat16 h = __float2bfloat16_rn(x);
     __nv_bfloat16 l = __float2bfloat16_rn(x - __bfloat162float(h));
@@ -134,6 +146,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv5_tc_kernel(TcConvArgs a) {
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int tile = blockIdx.x, ntile = blockIdx.y;
+    const bool dbg = a.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0;
+    if (dbg && tid == 64) a.dbg[0] = clock64();
     const int n0 = ntile * TC_NT;
     const int Lp = a.L + 4;
     const int SPT = TC_RT / Lp;
@@ -142,6 +156,31 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv5_tc_kernel(TcConvArgs a) {
     const int n_steps = n_main + n_res;
 
     const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + TC_STAGES), done_bar = smem_u32(bars + 2 * TC_STAGES);
+
+    // One pipeline step of the producer: K-chunk i -> stage i % STAGES (bulk-async copies, TMA engine, completion
+    // counted on the stage's mbarrier).
+    auto produce = [&](int i) {
+        const int s = i % TC_STAGES;
+        const bool is_res = i >= n_main;
+        const int c = is_res ? i - n_main : i;
+        const int ntaps = is_res ? 1 : 5;
+        const int C0 = is_res ? a.rc0 : a.c0, C1 = is_res ? a.rc1 : a.c1;
+        const bool second = c * TC_KCH >= C0;
+        const unsigned short* ahi = is_res ? (second ? a.r1_hi : a.r0_hi) : (second ? a.in1_hi : a.in0_hi);
+        const unsigned short* alo = is_res ? (second ? a.r1_lo : a.r0_lo) : (second ? a.in1_lo : a.in0_lo);
+        const int Csrc = second ? C1 : C0;
+        const int kg0 = (c * TC_KCH - (second ? C0 : 0)) / 8;
+        const size_t aoff = ((size_t)tile * (Csrc / 8) + kg0) * TC_RT * 8;  // elements
+        const unsigned short* wsrc = is_res ? a.res_w + ((size_t)ntile * n_res + c) * (2 * 1 * TC_B_TAP_BYTES / 2)
+                                            : a.w + ((size_t)ntile * n_main + c) * (2 * 5 * TC_B_TAP_BYTES / 2);
+        const uint32_t bbytes = 2u * ntaps * TC_B_TAP_BYTES;
+        const uint32_t st = smem_u32(stages + (size_t)s * TC_STAGE_BYTES);
+        mbar_expect_tx(full0 + 8 * s, 2u * TC_A_PLANE_BYTES + bbytes);
+        bulk_g2s(st, ahi + aoff, TC_A_PLANE_BYTES, full0 + 8 * s);
+        bulk_g2s(st + TC_A_PLANE_BYTES, alo + aoff, TC_A_PLANE_BYTES, full0 + 8 * s);
+        bulk_g2s(st + 2 * TC_A_PLANE_BYTES, wsrc, bbytes, full0 + 8 * s);
+    };
+
     if (tid == 0) {
         for (int s = 0; s < TC_STAGES; ++s) {
             mbar_init(full0 + 8 * s, 1);
@@ -149,6 +188,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv5_tc_kernel(TcConvArgs a) {
         }
         mbar_init(done_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        // the first STAGES loads need no free-slot wait: issue them before the CTA-wide setup barrier so that the
+        // copy latency overlaps the TMEM allocation
+        for (int i = 0; i < n_steps && i < TC_STAGES; ++i) produce(i);
     }
     if (warp == 1) {  // TMEM allocation is a warp-wide operation; the same warp frees it at the end
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
@@ -160,35 +202,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv5_tc_kernel(TcConvArgs a) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (dbg && tid == 64) a.dbg[1] = clock64();  // setup done (barriers, TMEM)
 
     if (tid == 0) {
-        // ===== producer: bulk-async copies of the K-chunks (TMA engine, completion on the stage's mbarrier) =====
-        for (int i = 0; i < n_steps; ++i) {
-            const int s = i % TC_STAGES;
-            const uint32_t ph = (uint32_t)(i / TC_STAGES) & 1u;
-            mbar_wait(empty0 + 8 * s, ph ^ 1u);
-            const bool is_res = i >= n_main;
-            const int c = is_res ? i - n_main : i;
-            const int ntaps = is_res ? 1 : 5;
-            const int C0 = is_res ? a.rc0 : a.c0, C1 = is_res ? a.rc1 : a.c1;
-            const bool second = c * TC_KCH >= C0;
-            const unsigned short* ahi = is_res ? (second ? a.r1_hi : a.r0_hi) : (second ? a.in1_hi : a.in0_hi);
-            const unsigned short* alo = is_res ? (second ? a.r1_lo : a.r0_lo) : (second ? a.in1_lo : a.in0_lo);
-            const int Csrc = second ? C1 : C0;
-            const int kg0 = (c * TC_KCH - (second ? C0 : 0)) / 8;
-            const size_t aoff = ((size_t)tile * (Csrc / 8) + kg0) * TC_RT * 8;  // elements
-            const unsigned short* wsrc = is_res ? a.res_w + ((size_t)ntile * n_res + c) * (2 * 1 * TC_B_TAP_BYTES / 2)
-                                          : a.w + ((size_t)ntile * n_main + c) * (2 * 5 * TC_B_TAP_BYTES / 2);
-            const uint32_t bbytes = 2u * ntaps * TC_B_TAP_BYTES;
-            const uint32_t st = smem_u32(stages + (size_t)s * TC_STAGE_BYTES);
-            mbar_expect_tx(full0 + 8 * s, 2u * TC_A_PLANE_BYTES + bbytes);
-            bulk_g2s(st, ahi + aoff, TC_A_PLANE_BYTES, full0 + 8 * s);
-            bulk_g2s(st + TC_A_PLANE_BYTES, alo + aoff, TC_A_PLANE_BYTES, full0 + 8 * s);
-            bulk_g2s(st + 2 * TC_A_PLANE_BYTES, wsrc, bbytes, full0 + 8 * s);
+        // ===== producer: remaining K-chunks, each waits for its stage to be released by the MMA commits =====
+        for (int i = TC_STAGES; i < n_steps; ++i) {
+            mbar_wait(empty0 + 8 * (i % TC_STAGES), ((uint32_t)(i / TC_STAGES) & 1u) ^ 1u);
+            produce(i);
         }
+        if (dbg) a.dbg[2] = clock64();  // all loads issued
     } else if (tid == 32) {
         // ===== MMA issuer: one thread drives the tensor core =====
-        constexpr uint32_t idesc = tc_idesc(128, TC_NT);
+        constexpr uint32_t idesc32 = tc_idesc(128, TC_NT), idesc64 = tc_idesc(128, 2 * TC_NT);
         bool first_main = true, first_res = true;
         for (int i = 0; i < n_steps; ++i) {
             const int s = i % TC_STAGES;
@@ -196,137 +221,177 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv5_tc_kernel(TcConvArgs a) {
             mbar_wait(full0 + 8 * s, ph);
             tc_fence_after();
             const bool is_res = i >= n_main;
-            const int ntaps = is_res ? 1 : 5;
             const uint32_t st = smem_u32(stages + (size_t)s * TC_STAGE_BYTES);
-            const uint32_t a_hi = st, a_lo = st + TC_A_PLANE_BYTES;
-            const uint32_t b_hi = st + 2 * TC_A_PLANE_BYTES, b_lo = b_hi + ntaps * TC_B_TAP_BYTES;
-            const uint32_t dcol = tmem_base + (is_res ? TC_NT : 0);
-            for (int tap = 0; tap < ntaps; ++tap) {
-                const uint32_t row_shift = (is_res ? 2 : tap) * 16;  // the 1x1 residual conv reads the centre row
+            // base descriptors of the stage; every MMA only adds a (16-byte unit) offset to the start-address field
+            const uint64_t dA_hi = tc_desc(st, TC_RT * 16, 128);
+            const uint64_t dA_lo = tc_desc(st + TC_A_PLANE_BYTES, TC_RT * 16, 128);
+            // weight tile per tap: [k-group][64 rows = 32 hi | 32 lo][8]  (LBO = 64 rows * 16 B)
+            const uint64_t dB = tc_desc(st + 2 * TC_A_PLANE_BYTES, 2 * TC_NT * 16, 128);
+            const uint32_t dcol = tmem_base + (is_res ? 2 * TC_NT : 0);
+            if (!is_res) {
+#pragma unroll
+                for (int tap = 0; tap < 5; ++tap) {
+#pragma unroll
+                    for (int kk = 0; kk < TC_KCH / 16; ++kk) {
+                        const uint64_t aofs = (uint64_t)((kk * 2 * (TC_RT * 16) + tap * 16) >> 4);  // tap = one 16-byte row
+                        const uint64_t bofs = (uint64_t)((tap * 2 * TC_B_TAP_BYTES + kk * 2 * (2 * TC_NT * 16)) >> 4);
+                        tc_mma_bf16(dcol, dA_hi + aofs, dB + bofs, idesc64, first_main ? 0u : 1u);  // [hi*hi | hi*lo]
+                        first_main = false;
+                        tc_mma_bf16(dcol, dA_lo + aofs, dB + bofs, idesc32, 1u);                     // += lo*hi
+                    }
+                }
+            } else {
 #pragma unroll
                 for (int kk = 0; kk < TC_KCH / 16; ++kk) {
-                    const uint32_t aofs = kk * 2 * (TC_RT * 16) + row_shift;
-                    const uint32_t bofs = tap * TC_B_TAP_BYTES + kk * 2 * (TC_NT * 16);
-                    const uint64_t dah = tc_desc(a_hi + aofs, TC_RT * 16, 128), dal = tc_desc(a_lo + aofs, TC_RT * 16, 128);
-                    const uint64_t dbh = tc_desc(b_hi + bofs, TC_NT * 16, 128), dbl = tc_desc(b_lo + bofs, TC_NT * 16, 128);
-                    bool& first = is_res ? first_res : first_main;
-                    tc_mma_bf16(dcol, dah, dbh, idesc, first ? 0u : 1u);
-                    first = false;
-                    tc_mma_bf16(dcol, dal, dbh, idesc, 1u);
-                    tc_mma_bf16(dcol, dah, dbl, idesc, 1u);
+                    const uint64_t aofs = (uint64_t)((kk * 2 * (TC_RT * 16) + 2 * 16) >> 4);  // 1x1 conv reads the centre row
+                    const uint64_t bofs = (uint64_t)((kk * 2 * (2 * TC_NT * 16)) >> 4);
+                    tc_mma_bf16(dcol, dA_hi + aofs, dB + bofs, idesc64, first_res ? 0u : 1u);
+                    first_res = false;
+                    tc_mma_bf16(dcol, dA_lo + aofs, dB + bofs, idesc32, 1u);
                 }
             }
             tc_commit(empty0 + 8 * s);  // frees the stage when the MMAs that read it have retired
         }
         tc_commit(done_bar);  // accumulators complete
+        if (dbg) a.dbg[3] = clock64();  // all MMAs issued
     }
 
-    // ===== epilogue: all 4 warps; warp w owns TMEM lanes [32w, 32w+32) =====
-    mbar_wait(done_bar, 0);
-    __syncwarp();  // lanes 0 of warps 0/1 come from the producer / issuer loops: reconverge before .sync.aligned ops
-    tc_fence_after();
-    const int r = tid;  // padded row of the tile
+    // ===== epilogue: 16 warps. TMEM lane quarter q = warp & 3 (hardware rule: a warp reads lanes 32*(warp%4)..+31),
+    // column group cg = warp >> 2 -> each thread owns 8 consecutive channels of one row (short dependency chains,
+    // 4 warps per scheduler to hide latency). =====
+    // per-thread geometry and every parameter / residual value this thread will need are fetched BEFORE waiting for
+    // the accumulators, so their global-memory latency overlaps the MMA main loop
+    const int q = warp & 3, cg = warp >> 2;
+    const int r = q * 32 + lane;  // padded row of the tile = TMEM lane
     const int s = r / Lp, l = r - s * Lp;
     const int b = tile * SPT + s;
     const bool valid = (s < SPT) && (l < a.L) && (b < a.B);
-    const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
-    float v[32];
-    tc_ld32(lane_base, v);
-
-    if (a.raw_out != nullptr) {
-        float* dst = a.raw_out + (((size_t)tile * gridDim.y + ntile) * 128 + r) * 32;
-#pragma unroll
-        for (int j = 0; j < 32; ++j) dst[j] = v[j];
-    } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] += a.bias[n0 + j];
-
-        {
-            constexpr int NG = TC_NT / GS;  // GroupNorm groups inside this CTA's 32 channels
-            const float inv_n = 1.f / (float)(GS * a.L);
-            // ---- pass 1: mean (per-row partials -> fixed-order sum over the sample's rows) ----
-            float p[NG];
-#pragma unroll
-            for (int g = 0; g < NG; ++g) p[g] = 0.f;
-#pragma unroll
-            for (int j = 0; j < 32; ++j) p[j / GS] += v[j];
-#pragma unroll
-            for (int g = 0; g < NG; ++g) part[r * 8 + g] = valid ? p[g] : 0.f;
-            __syncthreads();
-            if (tid < SPT * NG) {
-                const int ss = tid / NG, g = tid - ss * NG;
-                float t = 0.f;
-                for (int q = 0; q < a.L; ++q) t += part[(ss * Lp + q) * 8 + g];
-                stat[ss * 8 + g] = t * inv_n;
-            }
-            __syncthreads();
-            float mean[NG];
-#pragma unroll
-            for (int g = 0; g < NG; ++g) mean[g] = (s < SPT) ? stat[s * 8 + g] : 0.f;
-            __syncthreads();
-            // ---- pass 2: centred second moment ----
-#pragma unroll
-            for (int g = 0; g < NG; ++g) p[g] = 0.f;
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                const float d = v[j] - mean[j / GS];
-                p[j / GS] = fmaf(d, d, p[j / GS]);
-            }
-#pragma unroll
-            for (int g = 0; g < NG; ++g) part[r * 8 + g] = valid ? p[g] : 0.f;
-            __syncthreads();
-            if (tid < SPT * NG) {
-                const int ss = tid / NG, g = tid - ss * NG;
-                float t = 0.f;
-                for (int q = 0; q < a.L; ++q) t += part[(ss * Lp + q) * 8 + g];
-                stat[ss * 8 + g] = 1.0f / sqrtf(t * inv_n + 1e-5f);
-            }
-            __syncthreads();
-            float rstd[NG];
-#pragma unroll
-            for (int g = 0; g < NG; ++g) rstd[g] = (s < SPT) ? stat[s * 8 + g] : 0.f;
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-                v[j] = mishf((v[j] - mean[j / GS]) * (rstd[j / GS] * a.gamma[n0 + j]) + a.beta[n0 + j]);
-        }
+    const int c8 = n0 + cg * 8;  // first of this thread's 8 output channels
+    const bool full = a.raw_out == nullptr;
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 pb0 = z4, pb1 = z4, pg0 = z4, pg1 = z4, pe0 = z4, pe1 = z4, pc0 = z4, pc1 = z4, pr0 = z4, pr1 = z4;
+    float rid[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (full) {
+        pb0 = *reinterpret_cast<const float4*>(a.bias + c8); pb1 = *reinterpret_cast<const float4*>(a.bias + c8 + 4);
+        pg0 = *reinterpret_cast<const float4*>(a.gamma + c8); pg1 = *reinterpret_cast<const float4*>(a.gamma + c8 + 4);
+        pe0 = *reinterpret_cast<const float4*>(a.beta + c8); pe1 = *reinterpret_cast<const float4*>(a.beta + c8 + 4);
         if (a.cond != nullptr && valid) {
             const int tt = a.t_dev ? (int)a.t_dev[b] : a.t_uniform;
-            const float* cp = a.cond + (size_t)tt * a.CO + n0;
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] += cp[j];
+            const float* cp = a.cond + (size_t)tt * a.CO + c8;
+            pc0 = *reinterpret_cast<const float4*>(cp); pc1 = *reinterpret_cast<const float4*>(cp + 4);
         }
         if (a.res_w != nullptr) {
-            float rv[32];
-            tc_ld32(lane_base + TC_NT, rv);
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] += rv[j] + a.res_bias[n0 + j];
+            pr0 = *reinterpret_cast<const float4*>(a.res_bias + c8); pr1 = *reinterpret_cast<const float4*>(a.res_bias + c8 + 4);
         } else if (a.res_cm != nullptr && valid) {
-            const float* rp = a.res_cm + ((size_t)b * a.CO + n0) * Lp + 2 + l;
+            const float* rp = a.res_cm + ((size_t)b * a.CO + c8) * Lp + 2 + l;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] += rp[(size_t)j * Lp];
+            for (int j = 0; j < 8; ++j) rid[j] = rp[(size_t)j * Lp];
+        }
+    }
+
+    // ===== epilogue: 16 warps. TMEM lane quarter q = warp & 3 (hardware rule: a warp reads lanes 32*(warp%4)..+31),
+    // column group cg = warp >> 2 -> each thread owns 8 consecutive channels of one row =====
+    mbar_wait(done_bar, 0);
+    __syncwarp();  // lanes 0 of warps 0/1 come from the producer / issuer loops: reconverge before .sync.aligned ops
+    tc_fence_after();
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + cg * 8;
+    if (dbg && tid == 64) a.dbg[4] = clock64();  // accumulators ready
+    float v[8];
+    {
+        float v2[8];
+        tc_ld8(taddr, v);           // hi*hi + lo*hi
+        tc_ld8(taddr + TC_NT, v2);  // hi*lo
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] += v2[j];
+    }
+    if (dbg && tid == 64) a.dbg[5] = clock64();  // TMEM read
+
+    if (!full) {
+        float* dst = a.raw_out + (((size_t)tile * gridDim.y + ntile) * 128 + r) * 32 + cg * 8;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dst[j] = v[j];
+    } else {
+        v[0] += pb0.x; v[1] += pb0.y; v[2] += pb0.z; v[3] += pb0.w;
+        v[4] += pb1.x; v[5] += pb1.y; v[6] += pb1.z; v[7] += pb1.w;
+        {
+            // GroupNorm: per-(row, 4-channel block) partials in shared memory, one warp per (sample, group) statistic
+            // with a fixed shuffle tree (deterministic), two passes (mean, centred second moment).
+            constexpr int NG = TC_NT / GS;   // groups inside this CTA's 32 channels
+            constexpr int BPG = GS / 4;      // 4-channel blocks per group
+            const int n_stats = SPT * NG;
+            const int n_el = a.L * BPG;
+            const float inv_n = 1.f / (float)(GS * a.L);
+            const int gA = (cg * 8) / GS, gB = (cg * 8 + 4) / GS;  // groups of this thread's two 4-channel blocks
+            part[r * 8 + cg * 2 + 0] = valid ? (v[0] + v[1]) + (v[2] + v[3]) : 0.f;
+            part[r * 8 + cg * 2 + 1] = valid ? (v[4] + v[5]) + (v[6] + v[7]) : 0.f;
+            __syncthreads();
+            for (int st = warp; st < n_stats; st += TC_THREADS / 32) {
+                const int ss = st / NG, g = st - ss * NG;
+                float t = 0.f;
+                for (int e = lane; e < n_el; e += 32) t += part[(ss * Lp + e / BPG) * 8 + g * BPG + e % BPG];
+                t = warp_sum(t);
+                if (lane == 0) stat[ss * 8 + g] = t * inv_n;
+            }
+            __syncthreads();
+            const float mA = (s < SPT) ? stat[s * 8 + gA] : 0.f, mB = (s < SPT) ? stat[s * 8 + gB] : 0.f;
+            float pa = 0.f, pb = 0.f;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float da = v[j] - mA, db = v[4 + j] - mB;
+                pa = fmaf(da, da, pa);
+                pb = fmaf(db, db, pb);
+            }
+            __syncthreads();  // statistics of pass 1 consumed by everyone before `part`/`stat` are reused
+            part[r * 8 + cg * 2 + 0] = valid ? pa : 0.f;
+            part[r * 8 + cg * 2 + 1] = valid ? pb : 0.f;
+            __syncthreads();
+            for (int st = warp; st < n_stats; st += TC_THREADS / 32) {
+                const int ss = st / NG, g = st - ss * NG;
+                float t = 0.f;
+                for (int e = lane; e < n_el; e += 32) t += part[(ss * Lp + e / BPG) * 8 + g * BPG + e % BPG];
+                t = warp_sum(t);
+                if (lane == 0) stat[ss * 8 + g] = 1.0f / sqrtf(t * inv_n + 1e-5f);
+            }
+            __syncthreads();
+            const float rA = (s < SPT) ? stat[s * 8 + gA] : 0.f, rB = (s < SPT) ? stat[s * 8 + gB] : 0.f;
+            const float4 g0 = pg0, g1 = pg1, e0 = pe0, e1 = pe1;
+            v[0] = mishf_fast((v[0] - mA) * (rA * g0.x) + e0.x); v[1] = mishf_fast((v[1] - mA) * (rA * g0.y) + e0.y);
+            v[2] = mishf_fast((v[2] - mA) * (rA * g0.z) + e0.z); v[3] = mishf_fast((v[3] - mA) * (rA * g0.w) + e0.w);
+            v[4] = mishf_fast((v[4] - mB) * (rB * g1.x) + e1.x); v[5] = mishf_fast((v[5] - mB) * (rB * g1.y) + e1.y);
+            v[6] = mishf_fast((v[6] - mB) * (rB * g1.z) + e1.z); v[7] = mishf_fast((v[7] - mB) * (rB * g1.w) + e1.w);
+        }
+        if (dbg && tid == 64) a.dbg[6] = clock64();  // GroupNorm + Mish done
+        // time conditioning (zero when absent), then the residual: fused 1x1 conv accumulators or identity values
+        v[0] += pc0.x; v[1] += pc0.y; v[2] += pc0.z; v[3] += pc0.w;
+        v[4] += pc1.x; v[5] += pc1.y; v[6] += pc1.z; v[7] += pc1.w;
+        if (a.res_w != nullptr) {
+            float rv[8], rv2[8];
+            tc_ld8(taddr + 2 * TC_NT, rv);
+            tc_ld8(taddr + 3 * TC_NT, rv2);
+            v[0] += rv[0] + rv2[0] + pr0.x; v[1] += rv[1] + rv2[1] + pr0.y; v[2] += rv[2] + rv2[2] + pr0.z; v[3] += rv[3] + rv2[3] + pr0.w;
+            v[4] += rv[4] + rv2[4] + pr1.x; v[5] += rv[5] + rv2[5] + pr1.y; v[6] += rv[6] + rv2[6] + pr1.z; v[7] += rv[7] + rv2[7] + pr1.w;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] += rid[j];
         }
         if (valid) {
             if (a.out_cm != nullptr) {
-                float* op = a.out_cm + ((size_t)b * a.CO + n0) * Lp + 2 + l;
+                float* op = a.out_cm + ((size_t)b * a.CO + c8) * Lp + 2 + l;
 #pragma unroll
-                for (int j = 0; j < 32; ++j) op[(size_t)j * Lp] = v[j];
+                for (int j = 0; j < 8; ++j) op[(size_t)j * Lp] = v[j];
             }
             if (a.out_hi != nullptr) {
-                const size_t base = (((size_t)tile * (a.CO / 8) + n0 / 8) * TC_RT + (s * Lp + l + 2)) * 8;
+                const size_t o = (((size_t)tile * (a.CO / 8) + c8 / 8) * TC_RT + (s * Lp + l + 2)) * 8;
+                unsigned short h[8], lo8[8];
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    unsigned short h[8], lo8[8];
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) split_bf16(v[q * 8 + e], h[e], lo8[e]);
-                    uint4 ph, pl;
-                    ph.x = h[0] | ((uint32_t)h[1] << 16); ph.y = h[2] | ((uint32_t)h[3] << 16);
-                    ph.z = h[4] | ((uint32_t)h[5] << 16); ph.w = h[6] | ((uint32_t)h[7] << 16);
-                    pl.x = lo8[0] | ((uint32_t)lo8[1] << 16); pl.y = lo8[2] | ((uint32_t)lo8[3] << 16);
-                    pl.z = lo8[4] | ((uint32_t)lo8[5] << 16); pl.w = lo8[6] | ((uint32_t)lo8[7] << 16);
-                    const size_t o = base + (size_t)q * TC_RT * 8;
-                    *reinterpret_cast<uint4*>(a.out_hi + o) = ph;
-                    *reinterpret_cast<uint4*>(a.out_lo + o) = pl;
-                }
+                for (int e = 0; e < 8; ++e) split_bf16(v[e], h[e], lo8[e]);
+                uint4 ph, pl;
+                ph.x = h[0] | ((uint32_t)h[1] << 16); ph.y = h[2] | ((uint32_t)h[3] << 16);
+                ph.z = h[4] | ((uint32_t)h[5] << 16); ph.w = h[6] | ((uint32_t)h[7] << 16);
+                pl.x = lo8[0] | ((uint32_t)lo8[1] << 16); pl.y = lo8[2] | ((uint32_t)lo8[3] << 16);
+                pl.z = lo8[4] | ((uint32_t)lo8[5] << 16); pl.w = lo8[6] | ((uint32_t)lo8[7] << 16);
+                *reinterpret_cast<uint4*>(a.out_hi + o) = ph;
+                *reinterpret_cast<uint4*>(a.out_lo + o) = pl;
             }
         }
     }
@@ -334,6 +399,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv5_tc_kernel(TcConvArgs a) {
     // teardown: all TMEM reads done before the allocating warp frees the columns
     tc_fence_before();
     __syncthreads();
+    if (dbg && tid == 64) a.dbg[7] = clock64();  // stores issued, CTA done
     if (warp == 1) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TC_TMEM_COLS) : "memory");
     }
@@ -347,7 +413,7 @@ int launch_conv5_tc(const TcConvArgs& a, cudaStream_t stream) {
     MPDB_REQUIRE(a.gamma && a.beta && (a.gs == 4 || a.gs == 8 || a.gs == 16 || a.gs == 32),
                  "tc conv: GroupNorm group size must be 4, 8, 16 or 32");
     const int SPT = TC_RT / (a.L + 4);
-    MPDB_REQUIRE(SPT * (TC_NT / a.gs) <= 128 && SPT <= 12, "tc conv: too many statistics per tile");
+    MPDB_REQUIRE(SPT <= 12, "tc conv: too many samples per tile");
     const size_t smem = (size_t)TC_STAGES * TC_STAGE_BYTES + (2 * TC_STAGES + 1) * 8 + 16 + (128 * 8 + 12 * 8) * sizeof(float);
     dim3 grid((a.B + SPT - 1) / SPT, a.CO / TC_NT);
 #define MPDB_TC_CASE(G)                                                                                         \
@@ -377,7 +443,7 @@ int launch_conv5_tc(const TcConvArgs& a, cudaStream_t stream) {
 // packing helpers
 // ---------------------------------------------------------------------------------------------------
 // weights: src fp32 [ci][ntaps][CO] (the SIMT path's packed layout) ->
-//   dst bf16 [CO/32][CI/32][plane hi|lo][ntaps][kg 4][n 32][8]
+//   dst bf16 [CO/32][CI/32][ntaps][kg 4][64 rows: 32 hi | 32 lo][8]
 __global__ void pack_tc_weights_kernel(const float* __restrict__ src, unsigned short* __restrict__ dst, int CI, int CO, int ntaps) {
     const long long n = (long long)CI * CO * ntaps;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -393,10 +459,9 @@ __global__ void pack_tc_weights_kernel(const float* __restrict__ src, unsigned s
         unsigned short hi, lo;
         split_bf16(src[((long long)ci * ntaps + tap) * CO + co], hi, lo);
         const long long blk = ((long long)ntile * (CI / TC_KCH) + chunk) * (2LL * ntaps * (TC_KCH / 8) * TC_NT * 8);
-        const long long in_plane = (((long long)tap * (TC_KCH / 8) + kg) * TC_NT + nn) * 8 + e;
-        const long long plane = (long long)ntaps * (TC_KCH / 8) * TC_NT * 8;
-        dst[blk + in_plane] = hi;
-        dst[blk + plane + in_plane] = lo;
+        const long long row0 = (((long long)tap * (TC_KCH / 8) + kg) * (2 * TC_NT)) * 8;
+        dst[blk + row0 + (long long)nn * 8 + e] = hi;
+        dst[blk + row0 + (long long)(TC_NT + nn) * 8 + e] = lo;
     }
 }
 

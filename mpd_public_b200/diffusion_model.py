@@ -74,7 +74,17 @@ class Engine:
         self.dev_index = dev_index
         _lib.check(self.lib.mpdb_engine_create(C.byref(cfg), dev_index, C.byref(self.handle)))
         self._param_sig = None
+        self._tc_mode = None
         self._set_schedule(schedule)
+
+    TC_MODES = {"off": 0, "auto": 1, "force": 2}
+
+    def set_tensor_cores(self, mode):
+        """'auto' (default): tcgen05 split-bf16 path for the k=5 layers inside the fused loop, exact fp32 FMA path at
+        the steps where the schedule amplifies eps (t = T-1) and in the per-call entry points; 'force' / 'off'."""
+        if mode != self._tc_mode:
+            _lib.check(self.lib.mpdb_engine_set_option(self.handle, b"tc_mode", float(self.TC_MODES[mode])))
+            self._tc_mode = mode
 
     def __del__(self):
         try:
@@ -266,6 +276,7 @@ class GaussianDiffusionModel(nn.Module):
         self.register_buffer('posterior_mean_coef1', betas * np.sqrt(alphas_cumprod_prev) / (1. - alphas_cumprod))
         self.register_buffer('posterior_mean_coef2', (1. - alphas_cumprod_prev) * np.sqrt(alphas) / (1. - alphas_cumprod))
         self.use_cuda_graph = True
+        self.tensor_cores = "auto"  # 'auto' | 'force' | 'off'  (see Engine.set_tensor_cores)
         if model is not None:
             model.__dict__["_mpdb_default_steps"] = n_diffusion_steps
 
@@ -286,6 +297,7 @@ class GaussianDiffusionModel(nn.Module):
         if eng.__dict__.get("_sched_sig") != sig:  # buffers reloaded by load_state_dict
             eng._set_schedule(sched)
             eng._sched_sig = sig
+        eng.set_tensor_cores(self.tensor_cores)
         return eng
 
     # ------------------------------------------ sampling ------------------------------------------#
