@@ -128,6 +128,8 @@ __global__ void __launch_bounds__(GUIDE_THREADS) guide_step_kernel(GuideDev g, G
     int* i0s = reinterpret_cast<int*>(w1s + NI);  // [NI] lower tap
     float* fk = reinterpret_cast<float*>(i0s + NI);  // [(42 + 3*n_spheres)][NTH] per-thread FK scratch
 
+    pdl_launch_dependents();
+    pdl_wait();  // x and the clip flag come from the previous kernel
     const int flag = a.flag_in ? *a.flag_in : 0;
     const float* xin = a.x_in + (long long)b * H * D;
     for (int i = tid; i < H * D; i += NTH) {
@@ -386,7 +388,7 @@ int guide_launch_step(mpdb_guide* gd, const GuideStepArgs& a, cudaStream_t strea
         MPDB_CHECK_CUDA(cudaFuncSetAttribute(guide_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
         configured = 220 * 1024;
     }
-    guide_step_kernel<<<a.B, GUIDE_THREADS, smem, stream>>>(g, a);
+    MPDB_CHECK_CUDA(launch_kernel(guide_step_kernel, dim3(a.B), dim3(GUIDE_THREADS), smem, stream, g, a));
     MPDB_LAUNCH_CHECK();
     return 0;
 }

@@ -237,6 +237,7 @@ template <int MODE>
 __global__ void __launch_bounds__(512) conv_kernel(ConvArgs a) {
     extern __shared__ __align__(16) float smem[];
     constexpr int NTAPS = ModeTraits<MODE>::NTAPS;
+    pdl_wait();  // our inputs come from the previous kernel
 
     TileCtx c;
     c.tid = threadIdx.x;
@@ -280,6 +281,7 @@ __global__ void __launch_bounds__(512) conv_kernel(ConvArgs a) {
         for (int j = 0; j < TC; ++j) acc[i][j] = 0.f;
 
     accumulate<MODE>(acc, smem, stage_floats, xs_floats, a.in, a.w, a.CO, c);
+    pdl_launch_dependents();  // main loop over: the next kernel may run its prologue under our epilogue
 
     const int b = c.b0 + c.s;
     const int co = c.co0 + c.ct * TC;
@@ -481,7 +483,7 @@ int launch_conv(int mode, ConvArgs a, cudaStream_t stream) {
                                                  227 * 1024));                                                 \
             configured = true;                                                                                 \
         }                                                                                                      \
-        conv_kernel<M><<<grid, threads, smem, stream>>>(a);                                                    \
+        MPDB_CHECK_CUDA(launch_kernel(conv_kernel<M>, grid, dim3(threads), smem, stream, a));                  \
         break;                                                                                                 \
     }
     switch (mode) {
@@ -507,8 +509,10 @@ __global__ void __launch_bounds__(256) final_kernel(FinalArgs a) {
     extern __shared__ __align__(16) float smem[];
     float* wsm = smem;                 // [D][C]
     float* bsm = smem + a.D * a.C;     // [D]
-    for (int i = threadIdx.x; i < a.D * a.C; i += blockDim.x) wsm[i] = a.w[i];
+    pdl_launch_dependents();
+    for (int i = threadIdx.x; i < a.D * a.C; i += blockDim.x) wsm[i] = a.w[i];  // constants: before the dependency wait
     for (int i = threadIdx.x; i < a.D; i += blockDim.x) bsm[i] = a.bias[i];
+    pdl_wait();
     __syncthreads();
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long n = (long long)a.B * a.L * a.D;
@@ -556,7 +560,7 @@ int launch_final(const FinalArgs& a, cudaStream_t stream) {
     const int threads = 256;
     const int blocks = (int)((n + threads - 1) / threads);
     const size_t smem = sizeof(float) * (size_t)(a.D * a.C + a.D);
-    final_kernel<<<blocks, threads, smem, stream>>>(a);
+    MPDB_CHECK_CUDA(launch_kernel(final_kernel, dim3(blocks), dim3(threads), smem, stream, a));
     MPDB_LAUNCH_CHECK();
     return 0;
 }

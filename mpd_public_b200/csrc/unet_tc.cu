@@ -159,26 +159,30 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv5_tc_kernel(TcConvArgs a) {
 
     // One pipeline step of the producer: K-chunk i -> stage i % STAGES (bulk-async copies, TMA engine, completion
     // counted on the stage's mbarrier).
-    auto produce = [&](int i) {
+    auto produce = [&](int i, bool weights, bool acts) {
         const int s = i % TC_STAGES;
         const bool is_res = i >= n_main;
         const int c = is_res ? i - n_main : i;
         const int ntaps = is_res ? 1 : 5;
-        const int C0 = is_res ? a.rc0 : a.c0, C1 = is_res ? a.rc1 : a.c1;
-        const bool second = c * TC_KCH >= C0;
-        const unsigned short* ahi = is_res ? (second ? a.r1_hi : a.r0_hi) : (second ? a.in1_hi : a.in0_hi);
-        const unsigned short* alo = is_res ? (second ? a.r1_lo : a.r0_lo) : (second ? a.in1_lo : a.in0_lo);
-        const int Csrc = second ? C1 : C0;
-        const int kg0 = (c * TC_KCH - (second ? C0 : 0)) / 8;
-        const size_t aoff = ((size_t)tile * (Csrc / 8) + kg0) * TC_RT * 8;  // elements
-        const unsigned short* wsrc = is_res ? a.res_w + ((size_t)ntile * n_res + c) * (2 * 1 * TC_B_TAP_BYTES / 2)
-                                            : a.w + ((size_t)ntile * n_main + c) * (2 * 5 * TC_B_TAP_BYTES / 2);
         const uint32_t bbytes = 2u * ntaps * TC_B_TAP_BYTES;
         const uint32_t st = smem_u32(stages + (size_t)s * TC_STAGE_BYTES);
-        mbar_expect_tx(full0 + 8 * s, 2u * TC_A_PLANE_BYTES + bbytes);
-        bulk_g2s(st, ahi + aoff, TC_A_PLANE_BYTES, full0 + 8 * s);
-        bulk_g2s(st + TC_A_PLANE_BYTES, alo + aoff, TC_A_PLANE_BYTES, full0 + 8 * s);
-        bulk_g2s(st + 2 * TC_A_PLANE_BYTES, wsrc, bbytes, full0 + 8 * s);
+        if (weights) {
+            const unsigned short* wsrc = is_res ? a.res_w + ((size_t)ntile * n_res + c) * (2 * 1 * TC_B_TAP_BYTES / 2)
+                                                : a.w + ((size_t)ntile * n_main + c) * (2 * 5 * TC_B_TAP_BYTES / 2);
+            mbar_expect_tx(full0 + 8 * s, 2u * TC_A_PLANE_BYTES + bbytes);  // covers the activation copies too
+            bulk_g2s(st + 2 * TC_A_PLANE_BYTES, wsrc, bbytes, full0 + 8 * s);
+        }
+        if (acts) {
+            const int C0 = is_res ? a.rc0 : a.c0, C1 = is_res ? a.rc1 : a.c1;
+            const bool second = c * TC_KCH >= C0;
+            const unsigned short* ahi = is_res ? (second ? a.r1_hi : a.r0_hi) : (second ? a.in1_hi : a.in0_hi);
+            const unsigned short* alo = is_res ? (second ? a.r1_lo : a.r0_lo) : (second ? a.in1_lo : a.in0_lo);
+            const int Csrc = second ? C1 : C0;
+            const int kg0 = (c * TC_KCH - (second ? C0 : 0)) / 8;
+            const size_t aoff = ((size_t)tile * (Csrc / 8) + kg0) * TC_RT * 8;  // elements
+            bulk_g2s(st, ahi + aoff, TC_A_PLANE_BYTES, full0 + 8 * s);
+            bulk_g2s(st + TC_A_PLANE_BYTES, alo + aoff, TC_A_PLANE_BYTES, full0 + 8 * s);
+        }
     };
 
     if (tid == 0) {
@@ -188,9 +192,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv5_tc_kernel(TcConvArgs a) {
         }
         mbar_init(done_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        // the first STAGES loads need no free-slot wait: issue them before the CTA-wide setup barrier so that the
-        // copy latency overlaps the TMEM allocation
-        for (int i = 0; i < n_steps && i < TC_STAGES; ++i) produce(i);
+        // Weights are constants: their copies for the first STAGES chunks are issued before the dependency wait, so
+        // under programmatic dependent launch they overlap the previous kernel's epilogue. Activations follow it.
+        for (int i = 0; i < n_steps && i < TC_STAGES; ++i) produce(i, true, false);
+        pdl_wait();
+        for (int i = 0; i < n_steps && i < TC_STAGES; ++i) produce(i, false, true);
     }
     if (warp == 1) {  // TMEM allocation is a warp-wide operation; the same warp frees it at the end
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
@@ -202,13 +208,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv5_tc_kernel(TcConvArgs a) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();  // every thread: nothing produced by the previous kernel is read, and nothing is written, before this
     if (dbg && tid == 64) a.dbg[1] = clock64();  // setup done (barriers, TMEM)
 
     if (tid == 0) {
         // ===== producer: remaining K-chunks, each waits for its stage to be released by the MMA commits =====
         for (int i = TC_STAGES; i < n_steps; ++i) {
             mbar_wait(empty0 + 8 * (i % TC_STAGES), ((uint32_t)(i / TC_STAGES) & 1u) ^ 1u);
-            produce(i);
+            produce(i, true, true);
         }
         if (dbg) a.dbg[2] = clock64();  // all loads issued
     } else if (tid == 32) {
@@ -253,6 +260,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv5_tc_kernel(TcConvArgs a) {
             tc_commit(empty0 + 8 * s);  // frees the stage when the MMAs that read it have retired
         }
         tc_commit(done_bar);  // accumulators complete
+        // main loop over: let the next kernel start its prologue (barriers, TMEM, weight prefetch) under our epilogue
+        pdl_launch_dependents();
         if (dbg) a.dbg[3] = clock64();  // all MMAs issued
     }
 
@@ -424,7 +433,7 @@ int launch_conv5_tc(const TcConvArgs& a, cudaStream_t stream) {
                                                  200 * 1024));                                                  \
             configured = true;                                                                                  \
         }                                                                                                       \
-        conv5_tc_kernel<G><<<grid, TC_THREADS, smem, stream>>>(a);                                              \
+        MPDB_CHECK_CUDA(launch_kernel(conv5_tc_kernel<G>, grid, dim3(TC_THREADS), smem, stream, a));            \
         break;                                                                                                  \
     }
     switch (a.gs) {
