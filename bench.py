@@ -225,11 +225,29 @@ def run_reference_arm(args):
                                       f"{threads} threads; requested steps capped at 10"},
            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
-    print(json.dumps(out), flush=True)
+    emit(out)
 
 
 # ---------------------------------------------------------------------------------------------------
+_REAL_STDOUT = None
+
+
+def emit(obj):
+    """The ONE JSON line goes to the real stdout; everything libraries print (e.g. NCCL's version banner) was
+    redirected to stderr at start-up so that stdout carries nothing else."""
+    line = (json.dumps(obj) + "\n").encode()
+    if _REAL_STDOUT is not None:
+        os.write(_REAL_STDOUT, line)
+    else:
+        sys.stdout.write(line.decode())
+        sys.stdout.flush()
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -319,8 +337,14 @@ def main():
             ms = float(t.item())
         return ms
 
+    def log(msg):
+        if os.environ.get("MPDB_BENCH_VERBOSE"):
+            print(f"[bench rank {rank}] {msg}", file=sys.stderr, flush=True)
+
+    log("setup done")
     for _ in range(W):
         step_resident()
+    log("warmup done")
     launches0 = _lib.launch_count()
     sampler = ClockSampler(local_rank)
     ms_total = timed(step_resident, K, sampler)
@@ -328,9 +352,12 @@ def main():
     launches = _lib.launch_count() - launches0
     value = n_total * K / (ms_total / 1e3)
 
+    log(f"resident timing done: {ms_total:.2f} ms")
     for _ in range(2):
         step_e2e()
+    log("e2e warmup done")
     ms_e2e = timed(step_e2e, K)
+    log(f"e2e timing done: {ms_e2e:.2f} ms")
     e2e_value = n_total * K / (ms_e2e / 1e3)
 
     result = None
@@ -403,7 +430,7 @@ def main():
             result["cpu_baseline"] = {"value": Bc / t, "unit": UNIT, "cores": threads, "kind": "port",
                                       "sample": f"1 full guided loop at B={Bc} (the same workload), oracle port of the "
                                                 f"reference path, PyTorch CPU eager fp32, {threads} threads, {t:.2f} s"}
-        print(json.dumps(result), flush=True)
+        emit(result)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
