@@ -140,8 +140,8 @@ int mpdb_profile_guide(mpdb_guide* g, float* x, int32_t B, int32_t H, int32_t re
 int mpdb_debug_tc_conv5(const float* x_cm, const float* w, float* raw, int32_t B, int32_t CI, int32_t CO, int32_t L,
                         void* stream);
 
-/* debugging: with option "timeline" = 1, clock64 stamps (8 per layer) of CTA (0,0) of every tensor-core conv of the
- * last forward; host_out holds 8 * max_ops int64 */
+/* debugging: with option "timeline" = 1, clock64 stamps (16 per layer) of CTA (0,0) of every tensor-core conv of the
+ * last forward; host_out holds 16 * max_ops int64 */
 int mpdb_engine_read_timeline(mpdb_engine* e, int64_t* host_out, int32_t max_ops);
 
 /* debugging / parity: intermediate activations of the last mpdb_unet_forward */

@@ -388,7 +388,7 @@ static int launch_op(mpdb_engine* e, const ConvOp& op, const float* x, const lon
         a.out_cm = const_cast<float*>(buf_ptr(e, op.out, e->work_batch));
         a.out_hi = hi(op.out); a.out_lo = lo(op.out);
         a.CO = op.CO; a.L = op.L_out; a.B = B; a.gs = op.gs;
-        if (e->timeline && e->dbg_buf) a.dbg = e->dbg_buf + (&op - e->ops.data()) * 8;
+        if (e->timeline && e->dbg_buf) a.dbg = e->dbg_buf + (&op - e->ops.data()) * 16;
         return launch_conv5_tc(a, st);
     }
     ConvArgs a;
@@ -532,8 +532,8 @@ extern "C" int mpdb_engine_set_option(mpdb_engine* e, const char* name, double v
     } else if (n == "timeline") {
         e->timeline = value != 0;
         if (e->timeline && !e->dbg_buf) {
-            MPDB_CHECK_CUDA(cudaMalloc(&e->dbg_buf, sizeof(long long) * 8 * e->ops.size()));
-            MPDB_CHECK_CUDA(cudaMemset(e->dbg_buf, 0, sizeof(long long) * 8 * e->ops.size()));
+            MPDB_CHECK_CUDA(cudaMalloc(&e->dbg_buf, sizeof(long long) * 16 * e->ops.size()));
+            MPDB_CHECK_CUDA(cudaMemset(e->dbg_buf, 0, sizeof(long long) * 16 * e->ops.size()));
         }
     } else if (n == "tc_amp_limit") {
         e->tc_amp_limit = (float)value;
@@ -945,12 +945,12 @@ extern "C" int mpdb_debug_tc_conv5(const float* x_cm, const float* w, float* raw
     return 0;
 }
 
-// Debug: clock64 stamps (8 per op) of CTA (0,0) of every tensor-core conv of the last forward (option "timeline").
+// Debug: clock64 stamps (16 per op) of CTA (0,0) of every tensor-core conv of the last forward (option "timeline").
 extern "C" int mpdb_engine_read_timeline(mpdb_engine* e, int64_t* host_out, int32_t max_ops) {
     MPDB_REQUIRE(e && host_out && e->dbg_buf, "mpdb_engine_read_timeline: timeline not enabled");
     MPDB_CHECK_CUDA(cudaSetDevice(e->device));
     MPDB_CHECK_CUDA(cudaDeviceSynchronize());
     int n = (int)e->ops.size() < max_ops ? (int)e->ops.size() : max_ops;
-    MPDB_CHECK_CUDA(cudaMemcpy(host_out, e->dbg_buf, sizeof(long long) * 8 * n, cudaMemcpyDeviceToHost));
+    MPDB_CHECK_CUDA(cudaMemcpy(host_out, e->dbg_buf, sizeof(long long) * 16 * n, cudaMemcpyDeviceToHost));
     return 0;
 }

@@ -26,7 +26,10 @@ struct mpdb_guide {
 
 namespace mpdb {
 
-constexpr int GUIDE_THREADS = 128;
+constexpr int GUIDE_THREADS = 512;
+constexpr int FK_ROWS = 128;  // interpolated rows per pass (one FK thread each)
+constexpr int NSG = 4;        // sphere groups per row sharing the lookup + adjoint work
+constexpr int SPG = (MPDB_MAX_SPHERES + NSG - 1) / NSG;  // spheres per group (upper bound)
 
 struct GuideDev {
     int robot_kind, q_dim, ws_dim, n_spheres, D;
@@ -123,10 +126,11 @@ __global__ void __launch_bounds__(GUIDE_THREADS) guide_step_kernel(GuideDev g, G
     float* xn = smem;                  // [H][D] normalised input
     float* xu = xn + H * D;            // [H][D] unnormalised
     float* tot = xu + H * D;           // [H][D] sum_c w_c * clipped grad_c
-    float* gq = tot + H * D;           // [n_coll][NI][q] d cost_f / d q_interp
-    float* w1s = gq + n_coll * NI * q; // [NI] interpolation weight of the upper tap
-    int* i0s = reinterpret_cast<int*>(w1s + NI);  // [NI] lower tap
-    float* fk = reinterpret_cast<float*>(i0s + NI);  // [(42 + 3*n_spheres)][NTH] per-thread FK scratch
+    float* gq = tot + H * D;           // [n_coll][NSG][NI][q] partial d cost_f / d q_interp per sphere group
+    float* fgrad = gq + n_coll * NSG * NI * q;      // [n_coll][H][q] clipped, weighted per-field gradients
+    float* w1s = fgrad + n_coll * H * q;            // [NI] interpolation weight of the upper tap
+    int* i0s = reinterpret_cast<int*>(w1s + NI);    // [NI] lower tap
+    float* fk = reinterpret_cast<float*>(i0s + NI); // [(42 + 3*n_spheres)][FK_ROWS] FK scratch of one pass
 
     pdl_launch_dependents();
     pdl_wait();  // x and the clip flag come from the previous kernel
@@ -144,83 +148,96 @@ __global__ void __launch_bounds__(GUIDE_THREADS) guide_step_kernel(GuideDev g, G
     __syncthreads();
 
     // ---------------- collision costs on the interpolated trajectory ----------------
+    // Rows are processed in passes of FK_ROWS: (1) FK_ROWS threads interpolate + run the kinematic chain and park joint
+    // frames / sphere centres in shared memory; (2) ALL threads share the (row, sphere group) lookup + adjoint items —
+    // NSG sphere groups per row — writing partial dq to gq[f][sg][i][.]; the groups are summed in fixed order later.
     if (n_coll > 0) {
         const float ratio = NI > 1 ? (float)(H - 1) / (float)(NI - 1) : 0.f;  // align_corners=True
-        for (int i = tid; i < NI; i += NTH) {
-            float r = ratio * (float)i;
-            int i0 = (int)r;
-            if (i0 > H - 1) i0 = H - 1;
-            float l1 = fminf(fmaxf(r - (float)i0, 0.f), 1.f);
-            float l0 = 1.f - l1;
-            int i1 = i0 + (i0 < H - 1 ? 1 : 0);
-            i0s[i] = i0;
-            w1s[i] = l1;
-            float qv[7];
+        for (int ibase = 0; ibase < NI; ibase += FK_ROWS) {
+            if (tid < FK_ROWS && ibase + tid < NI) {
+                const int i = ibase + tid;
+                float r = ratio * (float)i;
+                int i0 = (int)r;
+                if (i0 > H - 1) i0 = H - 1;
+                float l1 = fminf(fmaxf(r - (float)i0, 0.f), 1.f);
+                float l0 = 1.f - l1;
+                int i1 = i0 + (i0 < H - 1 ? 1 : 0);
+                i0s[i] = i0;
+                w1s[i] = l1;
+                float qv[7];
 #pragma unroll
-            for (int k = 0; k < 7; ++k)
-                qv[k] = k < q ? __fadd_rn(__fmul_rn(l0, xu[i0 * D + k]), __fmul_rn(l1, xu[i1 * D + k])) : 0.f;
+                for (int k = 0; k < 7; ++k)
+                    qv[k] = k < q ? __fadd_rn(__fmul_rn(l0, xu[i0 * D + k]), __fmul_rn(l1, xu[i1 * D + k])) : 0.f;
 
-            float* sc = fk + tid;  // element j at sc[j * NTH]
-            float* cen = sc + 42 * NTH;
-            if (g.robot_kind == 1) {
-                float R[9] = {1.f, 0.f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f, 1.f};  // row-major
-                float o[3] = {0.f, 0.f, 0.f};
+                float* sc = fk + tid;  // element j at sc[j * FK_ROWS]
+                float* cen = sc + 42 * FK_ROWS;
+                if (g.robot_kind == 1) {
+                    float R[9] = {1.f, 0.f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f, 1.f};  // row-major
+                    float o[3] = {0.f, 0.f, 0.f};
 #pragma unroll 1
-                for (int j = 0; j < 7; ++j) {
+                    for (int j = 0; j < 7; ++j) {
+#pragma unroll
+                        for (int r3 = 0; r3 < 3; ++r3)
+                            o[r3] += R[r3 * 3 + 0] * g.joint_xyz[j][0] + R[r3 * 3 + 1] * g.joint_xyz[j][1] +
+                                     R[r3 * 3 + 2] * g.joint_xyz[j][2];
+                        float sq, cq;
+                        sincosf(qv[j], &sq, &cq);
+                        const float cr = g.joint_cr[j], sr = g.joint_sr[j];
+#pragma unroll
+                        for (int r3 = 0; r3 < 3; ++r3) {
+                            float c0 = R[r3 * 3 + 0], c1 = R[r3 * 3 + 1], c2 = R[r3 * 3 + 2];
+                            float a1 = c1 * cr + c2 * sr;   // (R Rx) column 1
+                            float a2 = -c1 * sr + c2 * cr;  // (R Rx) column 2
+                            R[r3 * 3 + 0] = cq * c0 + sq * a1;
+                            R[r3 * 3 + 1] = -sq * c0 + cq * a1;
+                            R[r3 * 3 + 2] = a2;
+                        }
+#pragma unroll
+                        for (int r3 = 0; r3 < 3; ++r3) {
+                            sc[(j * 3 + r3) * FK_ROWS] = o[r3];
+                            sc[(21 + j * 3 + r3) * FK_ROWS] = R[r3 * 3 + 2];  // joint axis = third column
+                        }
+                        for (int s = 0; s < g.n_spheres; ++s)
+                            if (g.sphere_frame[s] == j + 1)
+                                for (int r3 = 0; r3 < 3; ++r3)
+                                    cen[(s * 3 + r3) * FK_ROWS] = o[r3] + R[r3 * 3 + 0] * g.sphere_off[s][0] +
+                                                                  R[r3 * 3 + 1] * g.sphere_off[s][1] +
+                                                                  R[r3 * 3 + 2] * g.sphere_off[s][2];
+                    }
 #pragma unroll
                     for (int r3 = 0; r3 < 3; ++r3)
-                        o[r3] += R[r3 * 3 + 0] * g.joint_xyz[j][0] + R[r3 * 3 + 1] * g.joint_xyz[j][1] +
-                                 R[r3 * 3 + 2] * g.joint_xyz[j][2];
-                    float sq, cq;
-                    sincosf(qv[j], &sq, &cq);
-                    const float cr = g.joint_cr[j], sr = g.joint_sr[j];
-#pragma unroll
-                    for (int r3 = 0; r3 < 3; ++r3) {
-                        float c0 = R[r3 * 3 + 0], c1 = R[r3 * 3 + 1], c2 = R[r3 * 3 + 2];
-                        float a1 = c1 * cr + c2 * sr;   // (R Rx) column 1
-                        float a2 = -c1 * sr + c2 * cr;  // (R Rx) column 2
-                        R[r3 * 3 + 0] = cq * c0 + sq * a1;
-                        R[r3 * 3 + 1] = -sq * c0 + cq * a1;
-                        R[r3 * 3 + 2] = a2;
-                    }
-#pragma unroll
-                    for (int r3 = 0; r3 < 3; ++r3) {
-                        sc[(j * 3 + r3) * NTH] = o[r3];
-                        sc[(21 + j * 3 + r3) * NTH] = R[r3 * 3 + 2];  // joint axis = third column
-                    }
+                        o[r3] += R[r3 * 3 + 0] * g.flange[0] + R[r3 * 3 + 1] * g.flange[1] + R[r3 * 3 + 2] * g.flange[2];
                     for (int s = 0; s < g.n_spheres; ++s)
-                        if (g.sphere_frame[s] == j + 1)
+                        if (g.sphere_frame[s] == 8)
                             for (int r3 = 0; r3 < 3; ++r3)
-                                cen[(s * 3 + r3) * NTH] = o[r3] + R[r3 * 3 + 0] * g.sphere_off[s][0] +
-                                                          R[r3 * 3 + 1] * g.sphere_off[s][1] +
-                                                          R[r3 * 3 + 2] * g.sphere_off[s][2];
+                                cen[(s * 3 + r3) * FK_ROWS] = o[r3] + R[r3 * 3 + 0] * g.sphere_off[s][0] +
+                                                              R[r3 * 3 + 1] * g.sphere_off[s][1] +
+                                                              R[r3 * 3 + 2] * g.sphere_off[s][2];
+                } else {
+                    for (int s = 0; s < g.n_spheres; ++s)
+                        for (int r3 = 0; r3 < 3; ++r3) cen[(s * 3 + r3) * FK_ROWS] = r3 < g.ws_dim ? qv[r3] : 0.f;
                 }
-#pragma unroll
-                for (int r3 = 0; r3 < 3; ++r3)
-                    o[r3] += R[r3 * 3 + 0] * g.flange[0] + R[r3 * 3 + 1] * g.flange[1] + R[r3 * 3 + 2] * g.flange[2];
-                for (int s = 0; s < g.n_spheres; ++s)
-                    if (g.sphere_frame[s] == 8)
-                        for (int r3 = 0; r3 < 3; ++r3)
-                            cen[(s * 3 + r3) * NTH] = o[r3] + R[r3 * 3 + 0] * g.sphere_off[s][0] +
-                                                      R[r3 * 3 + 1] * g.sphere_off[s][1] +
-                                                      R[r3 * 3 + 2] * g.sphere_off[s][2];
-            } else {
-                for (int s = 0; s < g.n_spheres; ++s)
-                    for (int r3 = 0; r3 < 3; ++r3) cen[(s * 3 + r3) * NTH] = r3 < g.ws_dim ? qv[r3] : 0.f;
             }
+            __syncthreads();
 
-            for (int f = 0; f < n_coll; ++f) {
-                float dq[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-                for (int s0 = 0; s0 < g.n_spheres; s0 += 8) {
-                    // all texel gathers of up to 8 spheres are issued before any is consumed (latency overlap)
-                    float tsdf[8], tg[8][3];
+            // (row, sphere group) items: thread -> row = item % FK_ROWS, group = item / FK_ROWS
+            for (int item = tid; item < FK_ROWS * NSG; item += NTH) {
+                const int il = item % FK_ROWS, sg = item / FK_ROWS;
+                const int i = ibase + il;
+                if (i >= NI) continue;
+                const float* sc = fk + il;
+                const float* cen = sc + 42 * FK_ROWS;
+                for (int f = 0; f < n_coll; ++f) {
+                    float dq[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                    // this group's spheres are sg, sg + NSG, ...; all their texel gathers are issued before any is
+                    // consumed (latency overlap)
+                    float tsdf[SPG], tg[SPG][3];
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-                        const int s = s0 + u;
+                    for (int u = 0; u < SPG; ++u) {
+                        const int s = sg + u * NSG;
                         tsdf[u] = 3.4e38f; tg[u][0] = tg[u][1] = tg[u][2] = 0.f;
                         if (s < g.n_spheres) {
-                            const float p0 = cen[(s * 3 + 0) * NTH], p1 = cen[(s * 3 + 1) * NTH], p2 = cen[(s * 3 + 2) * NTH];
-                            const float p[3] = {p0, p1, p2};
+                            const float p[3] = {cen[(s * 3 + 0) * FK_ROWS], cen[(s * 3 + 1) * FK_ROWS], cen[(s * 3 + 2) * FK_ROWS]};
                             if (f < g.n_grid) {
                                 long long flat = 0;
                                 for (int d = 0; d < g.ws_dim; ++d) {
@@ -249,20 +266,20 @@ __global__ void __launch_bounds__(GUIDE_THREADS) guide_step_kernel(GuideDev g, G
                         }
                     }
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-                        const int s = s0 + u;
-                        if (s >= g.n_spheres) break;
+                    for (int u = 0; u < SPG; ++u) {
+                        const int s = sg + u * NSG;
+                        if (s >= g.n_spheres) continue;
                         const float viol = __fsub_rn(__fadd_rn(g.sphere_r[s], g.margin), tsdf[u]);
                         if (viol > 0.f) {
                             const float gx = -tg[u][0], gy = -tg[u][1], gz = -tg[u][2];  // d cost / d p
                             if (g.robot_kind == 1) {
-                                const float p0 = cen[(s * 3 + 0) * NTH], p1 = cen[(s * 3 + 1) * NTH], p2 = cen[(s * 3 + 2) * NTH];
+                                const float p0 = cen[(s * 3 + 0) * FK_ROWS], p1 = cen[(s * 3 + 1) * FK_ROWS], p2 = cen[(s * 3 + 2) * FK_ROWS];
                                 int nj = g.sphere_frame[s] < 7 ? g.sphere_frame[s] : 7;
                                 for (int j = 0; j < nj; ++j) {
-                                    float rx = p0 - sc[(j * 3 + 0) * NTH], ry = p1 - sc[(j * 3 + 1) * NTH],
-                                          rz = p2 - sc[(j * 3 + 2) * NTH];
-                                    float zx = sc[(21 + j * 3 + 0) * NTH], zy = sc[(21 + j * 3 + 1) * NTH],
-                                          zz = sc[(21 + j * 3 + 2) * NTH];
+                                    float rx = p0 - sc[(j * 3 + 0) * FK_ROWS], ry = p1 - sc[(j * 3 + 1) * FK_ROWS],
+                                          rz = p2 - sc[(j * 3 + 2) * FK_ROWS];
+                                    float zx = sc[(21 + j * 3 + 0) * FK_ROWS], zy = sc[(21 + j * 3 + 1) * FK_ROWS],
+                                          zz = sc[(21 + j * 3 + 2) * FK_ROWS];
                                     // (z x r) . g
                                     dq[j] += (zy * rz - zz * ry) * gx + (zz * rx - zx * rz) * gy + (zx * ry - zy * rx) * gz;
                                 }
@@ -273,43 +290,54 @@ __global__ void __launch_bounds__(GUIDE_THREADS) guide_step_kernel(GuideDev g, G
                             }
                         }
                     }
+                    float* dst = gq + (((long long)f * NSG + sg) * NI + i) * q;
+                    for (int k = 0; k < q; ++k) dst[k] = dq[k];
                 }
-                float* dst = gq + ((long long)f * NI + i) * q;
-                for (int k = 0; k < q; ++k) dst[k] = dq[k];
             }
+            __syncthreads();
         }
-        __syncthreads();
 
-        // adjoint of the interpolation (gather form), then per-cost clip / endpoint zero / weight
+        // adjoint of the interpolation (gather form), then per-cost clip / endpoint zero / weight: one thread per
+        // (support row, field); sphere groups are summed in fixed order (deterministic)
         const float inv_ratio = ratio > 0.f ? 1.f / ratio : 0.f;
-        for (int h = tid; h < H; h += NTH) {
+        for (int item = tid; item < H * n_coll; item += NTH) {
+            const int h = item % H, f = item / H;
             int lo_i = (int)floorf((float)(h - 1) * inv_ratio) - 1;
             int hi_i = (int)ceilf((float)(h + 1) * inv_ratio) + 1;
             if (lo_i < 0) lo_i = 0;
             if (hi_i > NI - 1) hi_i = NI - 1;
-            for (int f = 0; f < n_coll; ++f) {
-                float gs[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-                for (int i = lo_i; i <= hi_i; ++i) {
-                    int i0 = i0s[i];
-                    int i1 = i0 + (i0 < H - 1 ? 1 : 0);
-                    float l1 = w1s[i];
-                    float cw = (i0 == h ? 1.f - l1 : 0.f) + (i1 == h ? l1 : 0.f);
-                    if (cw != 0.f) {
-                        const float* src = gq + ((long long)f * NI + i) * q;
-                        for (int k = 0; k < q; ++k) gs[k] = fmaf(cw, src[k], gs[k]);
+            float gs[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            for (int i = lo_i; i <= hi_i; ++i) {
+                int i0 = i0s[i];
+                int i1 = i0 + (i0 < H - 1 ? 1 : 0);
+                float l1 = w1s[i];
+                float cw = (i0 == h ? 1.f - l1 : 0.f) + (i1 == h ? l1 : 0.f);
+                if (cw != 0.f) {
+                    for (int k = 0; k < q; ++k) {
+                        float dqs = 0.f;
+                        for (int sg = 0; sg < NSG; ++sg) dqs += gq[(((long long)f * NSG + sg) * NI + i) * q + k];
+                        gs[k] = fmaf(cw, dqs, gs[k]);
                     }
                 }
-                float scale = 1.f;
-                if (g.clip) {
-                    float n2 = (float)(D - q) * (1e-6f * 1e-6f);
-                    for (int k = 0; k < q; ++k) { float t = gs[k] + 1e-6f; n2 = fmaf(t, t, n2); }
-                    scale = clip_scale(sqrtf(n2), g.max_norm);
-                }
-                const float wgt = f < g.n_grid ? g.w_grid[f] : g.w_border;
-                if (h != 0 && h != H - 1)
-                    for (int k = 0; k < q; ++k) tot[h * D + k] += wgt * (scale * gs[k]);
             }
+            float scale = 1.f;
+            if (g.clip) {
+                float n2 = (float)(D - q) * (1e-6f * 1e-6f);
+                for (int k = 0; k < q; ++k) { float t = gs[k] + 1e-6f; n2 = fmaf(t, t, n2); }
+                scale = clip_scale(sqrtf(n2), g.max_norm);
+            }
+            const float wgt = f < g.n_grid ? g.w_grid[f] : g.w_border;
+            // per-field results are parked in shared memory and added to `tot` in field order below
+            for (int k = 0; k < q; ++k) fgrad[(f * H + h) * q + k] = (h != 0 && h != H - 1) ? wgt * (scale * gs[k]) : 0.f;
         }
+        __syncthreads();
+        for (int idx = tid; idx < H * q; idx += NTH) {
+            const int h = idx / q, k = idx - h * q;
+            float t = tot[h * D + k];
+            for (int f = 0; f < n_coll; ++f) t += fgrad[(f * H + h) * q + k];
+            tot[h * D + k] = t;
+        }
+        __syncthreads();
     }
 
     // ---------------- GP prior (constant-velocity) on the support points ----------------
@@ -372,8 +400,8 @@ __global__ void __launch_bounds__(GUIDE_THREADS) guide_step_kernel(GuideDev g, G
 
 static size_t guide_smem_bytes(const GuideDev& g, int H) {
     const int n_coll = g.n_grid + (g.has_border ? 1 : 0);
-    size_t f = (size_t)3 * H * g.D + (size_t)n_coll * g.n_interp * g.q_dim + 2 * (size_t)g.n_interp +
-               (size_t)(42 + 3 * g.n_spheres) * GUIDE_THREADS;
+    size_t f = (size_t)3 * H * g.D + (size_t)n_coll * NSG * g.n_interp * g.q_dim + (size_t)n_coll * H * g.q_dim +
+               2 * (size_t)g.n_interp + (size_t)(42 + 3 * g.n_spheres) * FK_ROWS;
     return f * sizeof(float);
 }
 

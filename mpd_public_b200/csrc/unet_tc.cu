@@ -29,7 +29,7 @@
 
 namespace mpdb {
 
-constexpr int TC_STAGES = 4;
+constexpr int TC_STAGES = 5;  // 5 x 37,376 B in flight per SM: the wide layers are bound by L2->SM streaming latency
 constexpr int TC_THREADS = 512;  // 16 warps: warp w reads TMEM lane quarter (w & 3), column group (w >> 2)
 constexpr int TC_A_PLANE_BYTES = (TC_KCH / 8) * TC_RT * 16;  // 8448
 constexpr int TC_B_TAP_BYTES = (TC_KCH / 8) * TC_NT * 16;    // 2048
@@ -131,6 +131,26 @@ __device__ __forceinline__ void split_bf16(float x, unsigned short& hi, unsigned
     lo = __bfloat16_as_ushort(l);
 }
 
+// GroupNorm reduction helper. `part` holds one partial per (tile row, 4-channel block). Level 1: thread t < SPT*8 owns
+// one (sample, block) column and adds its L rows (four independent accumulators so the loads pipeline; fixed tree).
+// Level 2 (after a barrier): every thread adds the BPG block sums of its group(s). Deterministic, tiling-independent.
+__device__ __forceinline__ void gn_colsum(const float* __restrict__ part, float* __restrict__ cs, int tid, int SPT, int Lp,
+                                          int L) {
+    if (tid < SPT * 8) {
+        const int ss = tid >> 3, blk = tid & 7;
+        const float* p = part + (size_t)ss * Lp * 8 + blk;
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll 2
+        for (int qq = 0; qq < L; qq += 4) {
+            a0 += p[(qq + 0) * 8];
+            a1 += p[(qq + 1) * 8];
+            a2 += p[(qq + 2) * 8];
+            a3 += p[(qq + 3) * 8];
+        }
+        cs[tid] = (a0 + a1) + (a2 + a3);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------------
@@ -139,10 +159,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv5_tc_kernel(TcConvArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     // carve-up: stages | barriers | tmem slot | epilogue scratch
     unsigned char* stages = smem_raw;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + TC_STAGES * TC_STAGE_BYTES);  // full[4], empty[4], done
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + TC_STAGES * TC_STAGE_BYTES);  // full[S], empty[S], done
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_STAGES + 1);
-    float* part = reinterpret_cast<float*>(tmem_slot + 4);  // [128][8]
-    float* stat = part + 128 * 8;                           // [12 samples][8 groups]
+    float* part = reinterpret_cast<float*>(tmem_slot + 4);  // [128][8] GroupNorm partials, then [12][8] column sums
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int tile = blockIdx.x, ntile = blockIdx.y;
@@ -323,26 +342,26 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv5_tc_kernel(TcConvArgs a) {
         v[0] += pb0.x; v[1] += pb0.y; v[2] += pb0.z; v[3] += pb0.w;
         v[4] += pb1.x; v[5] += pb1.y; v[6] += pb1.z; v[7] += pb1.w;
         {
-            // GroupNorm: per-(row, 4-channel block) partials in shared memory, one warp per (sample, group) statistic
-            // with a fixed shuffle tree (deterministic), two passes (mean, centred second moment).
-            constexpr int NG = TC_NT / GS;   // groups inside this CTA's 32 channels
-            constexpr int BPG = GS / 4;      // 4-channel blocks per group
-            const int n_stats = SPT * NG;
-            const int n_el = a.L * BPG;
+            // GroupNorm, two passes (mean, centred second moment). Every thread parks the partial sums of its two
+            // 4-channel blocks in shared memory and then adds up, in fixed order, the partials of the (sample, group)
+            // it belongs to: the reads are warp-uniform broadcasts, independent of each other, and need no second
+            // barrier. Deterministic and independent of how samples are tiled.
+            constexpr int BPG = GS / 4;  // 4-channel blocks per group
             const float inv_n = 1.f / (float)(GS * a.L);
-            const int gA = (cg * 8) / GS, gB = (cg * 8 + 4) / GS;  // groups of this thread's two 4-channel blocks
+            const int blkA = ((cg * 8) / GS) * BPG, blkB = ((cg * 8 + 4) / GS) * BPG;  // first block of each group
+            float* cs = part + 128 * 8;                                              // [SPT][8] column sums
+            const float* csr = cs + (s < SPT ? s : 0) * 8;
             part[r * 8 + cg * 2 + 0] = valid ? (v[0] + v[1]) + (v[2] + v[3]) : 0.f;
             part[r * 8 + cg * 2 + 1] = valid ? (v[4] + v[5]) + (v[6] + v[7]) : 0.f;
             __syncthreads();
-            for (int st = warp; st < n_stats; st += TC_THREADS / 32) {
-                const int ss = st / NG, g = st - ss * NG;
-                float t = 0.f;
-                for (int e = lane; e < n_el; e += 32) t += part[(ss * Lp + e / BPG) * 8 + g * BPG + e % BPG];
-                t = warp_sum(t);
-                if (lane == 0) stat[ss * 8 + g] = t * inv_n;
-            }
+            gn_colsum(part, cs, tid, SPT, Lp, a.L);
             __syncthreads();
-            const float mA = (s < SPT) ? stat[s * 8 + gA] : 0.f, mB = (s < SPT) ? stat[s * 8 + gB] : 0.f;
+            if (dbg && tid == 64) a.dbg[8] = clock64();
+            float tA = 0.f, tB = 0.f;
+#pragma unroll
+            for (int k = 0; k < BPG; ++k) { tA += csr[blkA + k]; tB += csr[blkB + k]; }
+            const float mA = tA * inv_n, mB = tB * inv_n;
+            if (dbg && tid == 64) a.dbg[9] = clock64();
             float pa = 0.f, pb = 0.f;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -350,19 +369,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv5_tc_kernel(TcConvArgs a) {
                 pa = fmaf(da, da, pa);
                 pb = fmaf(db, db, pb);
             }
-            __syncthreads();  // statistics of pass 1 consumed by everyone before `part`/`stat` are reused
+            __syncthreads();  // pass-1 column sums consumed by everyone before `part` / `cs` are reused
             part[r * 8 + cg * 2 + 0] = valid ? pa : 0.f;
             part[r * 8 + cg * 2 + 1] = valid ? pb : 0.f;
             __syncthreads();
-            for (int st = warp; st < n_stats; st += TC_THREADS / 32) {
-                const int ss = st / NG, g = st - ss * NG;
-                float t = 0.f;
-                for (int e = lane; e < n_el; e += 32) t += part[(ss * Lp + e / BPG) * 8 + g * BPG + e % BPG];
-                t = warp_sum(t);
-                if (lane == 0) stat[ss * 8 + g] = 1.0f / sqrtf(t * inv_n + 1e-5f);
-            }
+            gn_colsum(part, cs, tid, SPT, Lp, a.L);
             __syncthreads();
-            const float rA = (s < SPT) ? stat[s * 8 + gA] : 0.f, rB = (s < SPT) ? stat[s * 8 + gB] : 0.f;
+            if (dbg && tid == 64) a.dbg[10] = clock64();
+            tA = 0.f; tB = 0.f;
+#pragma unroll
+            for (int k = 0; k < BPG; ++k) { tA += csr[blkA + k]; tB += csr[blkB + k]; }
+            const float rA = 1.0f / sqrtf(tA * inv_n + 1e-5f), rB = 1.0f / sqrtf(tB * inv_n + 1e-5f);
+            if (dbg && tid == 64) a.dbg[11] = clock64();
             const float4 g0 = pg0, g1 = pg1, e0 = pe0, e1 = pe1;
             v[0] = mishf_fast((v[0] - mA) * (rA * g0.x) + e0.x); v[1] = mishf_fast((v[1] - mA) * (rA * g0.y) + e0.y);
             v[2] = mishf_fast((v[2] - mA) * (rA * g0.z) + e0.z); v[3] = mishf_fast((v[3] - mA) * (rA * g0.w) + e0.w);
@@ -423,14 +441,14 @@ int launch_conv5_tc(const TcConvArgs& a, cudaStream_t stream) {
                  "tc conv: GroupNorm group size must be 4, 8, 16 or 32");
     const int SPT = TC_RT / (a.L + 4);
     MPDB_REQUIRE(SPT <= 12, "tc conv: too many samples per tile");
-    const size_t smem = (size_t)TC_STAGES * TC_STAGE_BYTES + (2 * TC_STAGES + 1) * 8 + 16 + (128 * 8 + 12 * 8) * sizeof(float);
+    const size_t smem = (size_t)TC_STAGES * TC_STAGE_BYTES + (2 * TC_STAGES + 1) * 8 + 16 + (2 * 128 * 8) * sizeof(float);
     dim3 grid((a.B + SPT - 1) / SPT, a.CO / TC_NT);
 #define MPDB_TC_CASE(G)                                                                                         \
     case G: {                                                                                                   \
         static bool configured = false;                                                                         \
         if (!configured) {                                                                                      \
             MPDB_CHECK_CUDA(cudaFuncSetAttribute(conv5_tc_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                                 200 * 1024));                                                  \
+                                                 220 * 1024));                                                  \
             configured = true;                                                                                  \
         }                                                                                                       \
         MPDB_CHECK_CUDA(launch_kernel(conv5_tc_kernel<G>, grid, dim3(TC_THREADS), smem, stream, a));            \
