@@ -106,7 +106,8 @@ int mpdb_engine_set_schedule(mpdb_engine* e, const float* sqrt_recip_alphas_cump
                              const float* posterior_std, const float* posterior_var);
 /* options: "tc_mode" = 0 exact fp32 FMA path only | 1 auto (default: tcgen05 split-bf16 path for the k=5 layers at
  * every loop step whose sqrt(1/abar_t - 1) <= tc_amp_limit, exact path otherwise and for the per-call entry points)
- * | 2 force tensor cores everywhere; "tc_amp_limit" (default 64) */
+ * | 2 force tensor cores everywhere; "tc_amp_limit" (default 64); "alias_buffers" = 1 (default) shares activation
+ * storage between layers with disjoint lifetimes, 0 keeps one buffer per layer (needed by mpdb_engine_read_buffer) */
 int mpdb_engine_set_option(mpdb_engine* e, const char* name, double value);
 /* repack weights, precompute the time-conditioning tables; errors if a parameter is missing */
 int mpdb_engine_finalize(mpdb_engine* e, void* stream);

@@ -88,6 +88,9 @@ struct mpdb_engine {
     long long packed_tc_elems = 0;
     unsigned short* work_tc = nullptr;    // activations in tensor-core layout (bf16 hi/lo planes)
     std::vector<long long> tc_off, tc_plane;  // per buffer: offset of the hi plane, elements per plane
+    std::vector<long long> cm_off;            // per buffer: float offset of its (possibly shared) physical slot
+    int alias_buffers = 1;     // liveness-based reuse of activation storage (0: one buffer per layer, for debugging)
+    int n_slots = 0;
     long long* dbg_buf = nullptr;  // optional per-op timeline stamps (option "timeline")
     int timeline = 0;
     int tc_mode = 1;           // 0 = exact fp32 FMA path only, 1 = auto (loop steps below tc_amp_limit), 2 = force
@@ -310,33 +313,67 @@ static int build_plan(mpdb_engine* e, PlanBuilder& pb) {
     return 0;
 }
 
+// Activation storage. Every layer output is a logical buffer; physical slots are shared between logical buffers of
+// the same shape whose lifetimes do not overlap (greedy, in write order). Same shape => same halo / spare-row
+// positions, which are never written, so the zero-padding invariant survives the reuse. Keeping the working set of a
+// forward pass at a few tens of MB keeps weights and activations resident in the 126 MB L2.
 static int ensure_workspace(mpdb_engine* e, int B) {
     if (B <= e->work_batch) return 0;
     if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; e->graph_key.clear(); }
     MPDB_CHECK_CUDA(cudaDeviceSynchronize());
+    const size_t nb = e->bufs.size();
+    // liveness: op index of the write, op index of the last read
+    std::vector<int> wr(nb, -1), rd(nb, -1);
+    for (size_t i = 0; i < e->ops.size(); ++i) {
+        const ConvOp& op = e->ops[i];
+        const int ins[4] = {op.in0, op.in1, op.res0, op.res1};
+        for (int id : ins)
+            if (id >= 0) rd[id] = (int)i;
+        wr[op.out] = (int)i;
+    }
+    rd[e->final_in] = (int)e->ops.size() + 1;  // read by the fused final kernel
+    struct Slot { int C, L, free_after; long long cm_off, tc_off, tc_plane; };
+    std::vector<Slot> slots;
+    e->cm_off.assign(nb, 0);
+    e->tc_off.assign(nb, 0);
+    e->tc_plane.assign(nb, 0);
+    long long cm_total = 0, tc_total = 0;
+    for (size_t k = 0; k < nb; ++k) {
+        const ActBuf& b = e->bufs[k];
+        int found = -1;
+        if (e->alias_buffers)
+            for (size_t sidx = 0; sidx < slots.size(); ++sidx)
+                if (slots[sidx].C == b.C && slots[sidx].L == b.L && slots[sidx].free_after < wr[k]) { found = (int)sidx; break; }
+        if (found < 0) {
+            Slot sl;
+            sl.C = b.C; sl.L = b.L;
+            sl.cm_off = cm_total;
+            cm_total += (long long)b.C * (b.L + 2 * HALO) * B;
+            const int Lp = b.L + 2 * HALO;
+            sl.tc_plane = 0; sl.tc_off = tc_total;
+            if (Lp <= TC_RT && b.C % 8 == 0) {
+                const int SPT = TC_RT / Lp;
+                const long long tiles = (B + SPT - 1) / SPT;
+                sl.tc_plane = tiles * (b.C / 8) * TC_RT * 8;
+                tc_total += 2 * sl.tc_plane;
+            }
+            slots.push_back(sl);
+            found = (int)slots.size() - 1;
+        }
+        slots[found].free_after = rd[k] >= 0 ? rd[k] : wr[k];
+        e->cm_off[k] = slots[found].cm_off;
+        e->tc_off[k] = slots[found].tc_off;
+        e->tc_plane[k] = slots[found].tc_plane;
+    }
+    e->n_slots = (int)slots.size();
     if (e->work) cudaFree(e->work);
     e->work = nullptr;
-    size_t bytes = sizeof(float) * (size_t)e->work_floats_per_sample * (size_t)B;
-    MPDB_CHECK_CUDA(cudaMalloc(&e->work, bytes));
-    MPDB_CHECK_CUDA(cudaMemset(e->work, 0, bytes));  // halo columns stay zero forever
-    {
-        if (e->work_tc) cudaFree(e->work_tc);
-        e->work_tc = nullptr;
-        e->tc_off.assign(e->bufs.size(), 0);
-        e->tc_plane.assign(e->bufs.size(), 0);
-        long long total = 0;
-        for (size_t k = 0; k < e->bufs.size(); ++k) {
-            const int Lp = e->bufs[k].L + 2 * HALO;
-            if (Lp > TC_RT || e->bufs[k].C % 8) continue;  // no TC layout for this buffer
-            const int SPT = TC_RT / Lp;
-            const long long tiles = (B + SPT - 1) / SPT;
-            e->tc_plane[k] = tiles * (e->bufs[k].C / 8) * TC_RT * 8;
-            e->tc_off[k] = total;
-            total += 2 * e->tc_plane[k];
-        }
-        MPDB_CHECK_CUDA(cudaMalloc(&e->work_tc, sizeof(unsigned short) * (size_t)(total > 0 ? total : 8)));
-        MPDB_CHECK_CUDA(cudaMemset(e->work_tc, 0, sizeof(unsigned short) * (size_t)(total > 0 ? total : 8)));
-    }
+    MPDB_CHECK_CUDA(cudaMalloc(&e->work, sizeof(float) * (size_t)cm_total));
+    MPDB_CHECK_CUDA(cudaMemset(e->work, 0, sizeof(float) * (size_t)cm_total));  // halo columns stay zero forever
+    if (e->work_tc) cudaFree(e->work_tc);
+    e->work_tc = nullptr;
+    MPDB_CHECK_CUDA(cudaMalloc(&e->work_tc, sizeof(unsigned short) * (size_t)(tc_total > 0 ? tc_total : 8)));
+    MPDB_CHECK_CUDA(cudaMemset(e->work_tc, 0, sizeof(unsigned short) * (size_t)(tc_total > 0 ? tc_total : 8)));
     for (int k = 0; k < 2; ++k) {
         if (e->xbuf[k]) cudaFree(e->xbuf[k]);
         MPDB_CHECK_CUDA(cudaMalloc(&e->xbuf[k], sizeof(float) * (size_t)B * e->cfg.horizon * e->cfg.state_dim));
@@ -345,10 +382,7 @@ static int ensure_workspace(mpdb_engine* e, int B) {
     return 0;
 }
 
-static const float* buf_ptr(mpdb_engine* e, int id, int B_alloc) {
-    // buffers are laid out buffer-major: buffer k occupies [offset_k * B_alloc, ...)
-    return e->work + e->bufs[id].offset * (long long)B_alloc;
-}
+static const float* buf_ptr(mpdb_engine* e, int id, int /*B_alloc*/) { return e->work + e->cm_off[id]; }
 
 static ConvSrc make_src(mpdb_engine* e, int id0, int id1, const float* x_ext, int L) {
     ConvSrc s;
@@ -529,6 +563,12 @@ extern "C" int mpdb_engine_set_option(mpdb_engine* e, const char* name, double v
     if (n == "tc_mode") {
         MPDB_REQUIRE(value == 0 || value == 1 || value == 2, "tc_mode must be 0 (off), 1 (auto) or 2 (force)");
         e->tc_mode = (int)value;
+    } else if (n == "alias_buffers") {
+        if (e->alias_buffers != (value != 0)) {
+            e->alias_buffers = value != 0;
+            e->work_batch = 0;  // re-plan the workspace on the next call
+            if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; e->graph_key.clear(); }
+        }
     } else if (n == "timeline") {
         e->timeline = value != 0;
         if (e->timeline && !e->dbg_buf) {
@@ -848,6 +888,7 @@ extern "C" int mpdb_engine_buffer_info(mpdb_engine* e, int idx, char* name, int 
 extern "C" int mpdb_engine_read_buffer(mpdb_engine* e, int idx, float* dev_out, int32_t B, void* stream) {
     MPDB_REQUIRE(e && dev_out && idx >= 0 && idx < (int)e->bufs.size(), "mpdb_engine_read_buffer: bad argument");
     MPDB_REQUIRE(B > 0 && B <= e->work_batch, "mpdb_engine_read_buffer: batch larger than the workspace");
+    MPDB_REQUIRE(!e->alias_buffers, "mpdb_engine_read_buffer: set option alias_buffers = 0 before the forward pass");
     MPDB_CHECK_CUDA(cudaSetDevice(e->device));
     return launch_cm_to_bcl(buf_ptr(e, idx, e->work_batch), dev_out, B, e->bufs[idx].C, e->bufs[idx].L,
                             (cudaStream_t)stream);

@@ -202,8 +202,12 @@ class Engine:
         del ns
         return x_out, chain
 
+    def set_option(self, name, value):
+        _lib.check(self.lib.mpdb_engine_set_option(self.handle, name.encode(), float(value)))
+
     def read_buffers(self, B):
-        """name -> [B, C, L] activation of the last forward (parity debugging)."""
+        """name -> [B, C, L] activation of the last forward (parity debugging; needs option alias_buffers = 0
+        set before that forward)."""
         out = {}
         n = self.lib.mpdb_engine_num_buffers(self.handle)
         for i in range(n):

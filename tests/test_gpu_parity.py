@@ -101,13 +101,13 @@ def test_unet_layer_by_layer(case, tc):
     fp32 FMA path and on the tcgen05 split-bf16 path."""
     model = cuda_model(case)
     model.tensor_cores = tc
-    model._engine()
+    model._engine().set_option("alias_buffers", 0)  # keep every intermediate activation
     tol = TOL_KERNEL if tc == "off" else TOL_TC
     try:
         _layer_by_layer(case, model, tol)
     finally:
         model.tensor_cores = "auto"
-        model._engine()
+        model._engine().set_option("alias_buffers", 1)
 
 
 def _layer_by_layer(case, model, TOL_KERNEL):
