@@ -42,6 +42,7 @@ struct Param {
 struct ActBuf {
     std::string name;
     int C = 0, L = 0;
+    bool exclusive = false;  // never shares storage (partially written buffers rely on their zero fill)
     long long offset = 0;  // floats into the workspace, per-sample stride = C * (L + 4)
 };
 
@@ -63,6 +64,8 @@ struct ConvOp {
     // tensor-core path (unet_tc.cu)
     bool tc_ok = false;
     int cin = 0, res_cin = 0;
+    int tc_in0 = -2, tc_res0 = -2;  // buffers the tensor-core path reads instead of the external BLC trajectory
+    int cin_tc = 0, res_cin_tc = 0; // input widths on the tensor-core path (trajectory padded to 32 channels)
     long long w_tc = -1, res_w_tc = -1;  // offsets (bf16 elements) into packed_tc
 };
 
@@ -220,6 +223,18 @@ static int build_plan(mpdb_engine* e, PlanBuilder& pb) {
     add_param(e, "time_mlp.encoder.3.weight", 32 * 128);
     add_param(e, "time_mlp.encoder.3.bias", 32);
 
+    // tensor-core path only: the trajectory [B,H,D] re-laid out as a TC-layout activation padded to 32 channels
+    const int c_in_pad = (c.state_dim + TC_KCH - 1) / TC_KCH * TC_KCH;
+    const int input_buf = add_buf(e, "input", c_in_pad, L);
+    e->bufs[input_buf].exclusive = true;  // channels >= state_dim are never written and must stay zero
+    {
+        ConvOp in;
+        in.mode = MODE_INPUT;
+        in.in0 = -1;
+        in.out = input_buf;
+        in.CO = c_in_pad; in.L_in = L; in.L_out = L;
+        e->ops.push_back(in);
+    }
     std::vector<int> skips;
     int cur = -1;  // external x (BLC)
     for (int i = 0; i < n; ++i) {
@@ -293,20 +308,34 @@ static int build_plan(mpdb_engine* e, PlanBuilder& pb) {
         return cc;
     };
     for (ConvOp& op : e->ops) {
+        if (op.mode == MODE_INPUT) continue;
         op.cin = chans(op.in0, op.in1);
         op.res_cin = op.res_w >= 0 ? chans(op.res0, op.res1) : 0;
-        const bool main_ok = op.mode == MODE_CONV5 && op.in0 >= 0 && op.cin % TC_KCH == 0 &&
-                             (op.in1 < 0 || e->bufs[op.in0].C % TC_KCH == 0);
-        const bool res_ok = op.res_w < 0 || (op.res0 >= 0 && op.res_cin % TC_KCH == 0 &&
-                                             (op.res1 < 0 || e->bufs[op.res0].C % TC_KCH == 0));
-        const bool gn_ok = op.gn && (op.gs == 4 || op.gs == 8 || op.gs == 16 || op.gs == 32);
-        op.tc_ok = main_ok && res_ok && gn_ok && op.CO % TC_NT == 0 && op.L_out + 4 <= TC_RT;
+        // the external trajectory is read through its padded TC-layout copy
+        op.tc_in0 = op.in0 == -1 ? input_buf : op.in0;
+        op.tc_res0 = op.res0 == -1 ? input_buf : op.res0;
+        op.cin_tc = (op.in0 == -1 ? c_in_pad : e->bufs[op.in0].C) + (op.in1 >= 0 ? e->bufs[op.in1].C : 0);
+        op.res_cin_tc = op.res_w >= 0 ? (op.res0 == -1 ? c_in_pad : e->bufs[op.res0].C) + (op.res1 >= 0 ? e->bufs[op.res1].C : 0) : 0;
+        const bool width_ok = op.cin_tc % TC_KCH == 0 && (op.in1 < 0 || e->bufs[op.tc_in0].C % TC_KCH == 0) && op.CO % TC_NT == 0 &&
+                              op.L_in + 4 <= TC_RT;
+        bool ok = false;
+        int ntaps = 5;
+        if (op.mode == MODE_CONV5) {
+            const bool res_ok = op.res_w < 0 || (op.res_cin_tc % TC_KCH == 0 && (op.res1 < 0 || e->bufs[op.tc_res0].C % TC_KCH == 0));
+            const bool gn_ok = op.gn && (op.gs == 4 || op.gs == 8 || op.gs == 16 || op.gs == 32);
+            ok = width_ok && res_ok && gn_ok;
+        } else if (op.mode == MODE_DOWN) {
+            ok = width_ok; ntaps = 3;
+        } else if (op.mode == MODE_UP) {
+            ok = width_ok; ntaps = 4;
+        }
+        op.tc_ok = ok;
         if (op.tc_ok) {
             op.w_tc = e->packed_tc_elems;
-            e->packed_tc_elems += 2LL * op.cin * op.CO * 5;
+            e->packed_tc_elems += 2LL * op.cin_tc * op.CO * ntaps;
             if (op.res_w >= 0) {
                 op.res_w_tc = e->packed_tc_elems;
-                e->packed_tc_elems += 2LL * op.res_cin * op.CO;
+                e->packed_tc_elems += 2LL * op.res_cin_tc * op.CO;
             }
         }
     }
@@ -326,7 +355,7 @@ static int ensure_workspace(mpdb_engine* e, int B) {
     std::vector<int> wr(nb, -1), rd(nb, -1);
     for (size_t i = 0; i < e->ops.size(); ++i) {
         const ConvOp& op = e->ops[i];
-        const int ins[4] = {op.in0, op.in1, op.res0, op.res1};
+        const int ins[6] = {op.in0, op.in1, op.res0, op.res1, op.tc_in0, op.res_w >= 0 ? op.tc_res0 : -2};
         for (int id : ins)
             if (id >= 0) rd[id] = (int)i;
         wr[op.out] = (int)i;
@@ -341,7 +370,7 @@ static int ensure_workspace(mpdb_engine* e, int B) {
     for (size_t k = 0; k < nb; ++k) {
         const ActBuf& b = e->bufs[k];
         int found = -1;
-        if (e->alias_buffers)
+        if (e->alias_buffers && !b.exclusive)
             for (size_t sidx = 0; sidx < slots.size(); ++sidx)
                 if (slots[sidx].C == b.C && slots[sidx].L == b.L && slots[sidx].free_after < wr[k]) { found = (int)sidx; break; }
         if (found < 0) {
@@ -360,7 +389,7 @@ static int ensure_workspace(mpdb_engine* e, int B) {
             slots.push_back(sl);
             found = (int)slots.size() - 1;
         }
-        slots[found].free_after = rd[k] >= 0 ? rd[k] : wr[k];
+        slots[found].free_after = b.exclusive ? (1 << 30) : (rd[k] >= 0 ? rd[k] : wr[k]);
         e->cm_off[k] = slots[found].cm_off;
         e->tc_off[k] = slots[found].tc_off;
         e->tc_plane[k] = slots[found].tc_plane;
@@ -401,18 +430,22 @@ static int launch_op(mpdb_engine* e, const ConvOp& op, const float* x, const lon
                      cudaStream_t st, bool tc) {
     auto hi = [&](int id) -> unsigned short* { return e->tc_plane[id] ? e->work_tc + e->tc_off[id] : nullptr; };
     auto lo = [&](int id) -> unsigned short* { return e->tc_plane[id] ? e->work_tc + e->tc_off[id] + e->tc_plane[id] : nullptr; };
+    if (op.mode == MODE_INPUT) {
+        if (!tc) return 0;  // the exact path reads the trajectory directly
+        return launch_blc_to_tc(x, hi(op.out), lo(op.out), B, e->cfg.horizon, e->cfg.state_dim, e->bufs[op.out].C, st);
+    }
     if (tc && op.tc_ok) {
         TcConvArgs a;
         memset(&a, 0, sizeof(a));
-        a.in0_hi = hi(op.in0); a.in0_lo = lo(op.in0); a.c0 = e->bufs[op.in0].C;
+        a.mode = op.mode == MODE_DOWN ? TCM_DOWN : op.mode == MODE_UP ? TCM_UP : TCM_CONV5;
+        a.in0_hi = hi(op.tc_in0); a.in0_lo = lo(op.tc_in0); a.c0 = e->bufs[op.tc_in0].C;
         if (op.in1 >= 0) { a.in1_hi = hi(op.in1); a.in1_lo = lo(op.in1); a.c1 = e->bufs[op.in1].C; }
         a.w = e->packed_tc + op.w_tc;
         a.bias = e->packed + op.bias;
-        a.gamma = e->packed + op.gamma;
-        a.beta = e->packed + op.beta;
+        if (op.gn) { a.gamma = e->packed + op.gamma; a.beta = e->packed + op.beta; }
         if (op.cond >= 0) { a.cond = e->packed + op.cond; a.t_dev = t_dev; a.t_uniform = t_uniform; }
         if (op.res_w >= 0) {
-            a.r0_hi = hi(op.res0); a.r0_lo = lo(op.res0); a.rc0 = e->bufs[op.res0].C;
+            a.r0_hi = hi(op.tc_res0); a.r0_lo = lo(op.tc_res0); a.rc0 = e->bufs[op.tc_res0].C;
             if (op.res1 >= 0) { a.r1_hi = hi(op.res1); a.r1_lo = lo(op.res1); a.rc1 = e->bufs[op.res1].C; }
             a.res_w = e->packed_tc + op.res_w_tc;
             a.res_bias = e->packed + op.res_bias;
@@ -421,7 +454,7 @@ static int launch_op(mpdb_engine* e, const ConvOp& op, const float* x, const lon
         }
         a.out_cm = const_cast<float*>(buf_ptr(e, op.out, e->work_batch));
         a.out_hi = hi(op.out); a.out_lo = lo(op.out);
-        a.CO = op.CO; a.L = op.L_out; a.B = B; a.gs = op.gs;
+        a.CO = op.CO; a.L = op.L_in; a.B = B; a.gs = op.gs;
         if (e->timeline && e->dbg_buf) a.dbg = e->dbg_buf + (&op - e->ops.data()) * 16;
         return launch_conv5_tc(a, st);
     }
@@ -458,6 +491,7 @@ static double op_flops(mpdb_engine* e, const ConvOp& op, int B) {
         if (id1 >= 0) c += e->bufs[id1].C;
         return c;
     };
+    if (op.mode == MODE_INPUT) return 0.0;
     const int cin = chans(op.in0, op.in1);
     double f;
     if (op.mode == MODE_UP) f = 2.0 * B * op.L_in * op.CO * (double)cin * 4;       // every input feeds 4 taps
@@ -602,8 +636,12 @@ extern "C" int mpdb_engine_finalize(mpdb_engine* e, void* stream) {
     }
     for (const ConvOp& op : e->ops) {
         if (!op.tc_ok) continue;
-        if (launch_pack_tc_weights(e->packed + op.w, e->packed_tc + op.w_tc, op.cin, op.CO, 5, st)) return 1;
-        if (op.res_w >= 0 && launch_pack_tc_weights(e->packed + op.res_w, e->packed_tc + op.res_w_tc, op.res_cin, op.CO, 1, st))
+        // destination tap -> source tap: identity for Conv1d; ConvTranspose1d packs [W1, W3 | W0, W2] (even | odd outputs)
+        const int ntaps = op.mode == MODE_DOWN ? 3 : op.mode == MODE_UP ? 4 : 5;
+        const unsigned perm = op.mode == MODE_UP ? 0x2031u : 0x43210u;
+        if (launch_pack_tc_weights(e->packed + op.w, e->packed_tc + op.w_tc, op.cin_tc, op.cin, op.CO, ntaps, perm, st)) return 1;
+        if (op.res_w >= 0 && launch_pack_tc_weights(e->packed + op.res_w, e->packed_tc + op.res_w_tc, op.res_cin_tc, op.res_cin,
+                                                    op.CO, 1, 0u, st))
             return 1;
     }
     const int T = e->cfg.n_diffusion_steps;
@@ -922,7 +960,7 @@ extern "C" int mpdb_profile_forward(mpdb_engine* e, const float* x, int32_t t, i
         MPDB_CHECK_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
         ms_out[k] = ms / reps;
         flops_out[k] = op_flops(e, op, B);
-        mode_out[k] = (tc && op.tc_ok) ? 5 : op.mode;  // 5 = tcgen05 conv5
+        mode_out[k] = op.mode == MODE_INPUT ? 6 : (tc && op.tc_ok) ? 5 : op.mode;  // 5 = tcgen05 conv, 6 = layout conversion
         ++k;
     }
     {
@@ -966,7 +1004,7 @@ extern "C" int mpdb_debug_tc_conv5(const float* x_cm, const float* w, float* raw
     MPDB_CHECK_CUDA(cudaMemsetAsync(xh, 0, 2 * plane, st));
     MPDB_CHECK_CUDA(cudaMemsetAsync(xl, 0, 2 * plane, st));
     int rc = launch_repack_conv(w, wp, CO, CI, 5, 0, st);
-    if (!rc) rc = launch_pack_tc_weights(wp, wt, CI, CO, 5, st);
+    if (!rc) rc = launch_pack_tc_weights(wp, wt, CI, CI, CO, 5, 0x43210u, st);
     if (!rc) rc = launch_cm_to_tc(x_cm, xh, xl, B, CI, L, st);
     if (!rc) {
         TcConvArgs a;
@@ -974,7 +1012,7 @@ extern "C" int mpdb_debug_tc_conv5(const float* x_cm, const float* w, float* raw
         a.in0_hi = xh; a.in0_lo = xl; a.c0 = CI;
         a.w = wt;
         a.raw_out = raw;
-        a.CO = CO; a.L = L; a.B = B; a.gs = 32;
+        a.CO = CO; a.L = L; a.B = B; a.gs = 32; a.mode = TCM_CONV5;
         float* dummy = wp;  // gamma/beta/bias are not read in raw mode but must be non-null for the launch checks
         a.gamma = dummy; a.beta = dummy; a.bias = dummy;
         rc = launch_conv5_tc(a, st);

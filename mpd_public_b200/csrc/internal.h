@@ -21,7 +21,7 @@ struct ConvSrc {
     int L;    // positions per sample of the source
 };
 
-enum ConvMode { MODE_CONV5 = 0, MODE_CONV1 = 1, MODE_DOWN = 2, MODE_UP = 3 };
+enum ConvMode { MODE_CONV5 = 0, MODE_CONV1 = 1, MODE_DOWN = 2, MODE_UP = 3, MODE_INPUT = 7 };
 
 struct ConvArgs {
     ConvSrc in;
@@ -55,6 +55,7 @@ void choose_tile(int mode, ConvArgs* a);
 constexpr int TC_RT = 132;   // rows of one tile block in the TC layout (128 MMA rows + 4 rows of tap reach)
 constexpr int TC_NT = 32;    // output channels per CTA
 constexpr int TC_KCH = 32;   // input channels per pipeline stage
+enum TcMode { TCM_CONV5 = 0, TCM_DOWN = 1, TCM_UP = 2 };
 
 struct TcConvArgs {
     // main conv input: up to two concatenated sources in TC layout (bf16 hi / lo planes)
@@ -78,9 +79,12 @@ struct TcConvArgs {
     float* raw_out;               // debug: raw main accumulator [tile][ntile][128][32]
     long long* dbg;               // debug: 8 clock64 stamps of CTA (0,0) (null = off)
     int CO, L, B, gs;
+    int mode;                     // TcMode; L is the INPUT length (DOWN writes L/2 positions, UP writes 2L)
 };
 int launch_conv5_tc(const TcConvArgs& a, cudaStream_t stream);
-int launch_pack_tc_weights(const float* src, unsigned short* dst, int CI, int CO, int ntaps, cudaStream_t stream);
+int launch_pack_tc_weights(const float* src, unsigned short* dst, int CI, int CI_src, int CO, int ntaps, unsigned perm,
+                           cudaStream_t stream);
+int launch_blc_to_tc(const float* x, unsigned short* hi, unsigned short* lo, int B, int L, int D, int C, cudaStream_t stream);
 int launch_cm_to_tc(const float* cm, unsigned short* hi, unsigned short* lo, int B, int C, int L, cudaStream_t stream);
 
 struct FinalArgs {

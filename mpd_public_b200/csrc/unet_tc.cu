@@ -131,6 +131,32 @@ __device__ __forceinline__ void split_bf16(float x, unsigned short& hi, unsigned
     lo = __bfloat16_as_ushort(l);
 }
 
+// Stores 8 consecutive output channels [c8, c8+8) of sample b at output position lo in the fp32 CM layout and (split
+// into bf16 hi/lo) in the TC layout of an activation with CO channels and L_out positions.
+__device__ __forceinline__ void tc_store_row(const TcConvArgs& a, const float (&v)[8], int b, int lo, int c8, int L_out) {
+    const int Lpo = L_out + 4;
+    if (a.out_cm != nullptr) {
+        float* op = a.out_cm + ((size_t)b * a.CO + c8) * Lpo + 2 + lo;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) op[(size_t)j * Lpo] = v[j];
+    }
+    if (a.out_hi != nullptr) {
+        const int SPTo = TC_RT / Lpo;
+        const int to = b / SPTo, so = b - to * SPTo;
+        const size_t o = (((size_t)to * (a.CO / 8) + c8 / 8) * TC_RT + (so * Lpo + lo + 2)) * 8;
+        unsigned short h[8], lo8[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) split_bf16(v[e], h[e], lo8[e]);
+        uint4 ph, pl;
+        ph.x = h[0] | ((uint32_t)h[1] << 16); ph.y = h[2] | ((uint32_t)h[3] << 16);
+        ph.z = h[4] | ((uint32_t)h[5] << 16); ph.w = h[6] | ((uint32_t)h[7] << 16);
+        pl.x = lo8[0] | ((uint32_t)lo8[1] << 16); pl.y = lo8[2] | ((uint32_t)lo8[3] << 16);
+        pl.z = lo8[4] | ((uint32_t)lo8[5] << 16); pl.w = lo8[6] | ((uint32_t)lo8[7] << 16);
+        *reinterpret_cast<uint4*>(a.out_hi + o) = ph;
+        *reinterpret_cast<uint4*>(a.out_lo + o) = pl;
+    }
+}
+
 // GroupNorm reduction helper. `part` holds one partial per (tile row, 4-channel block). Level 1: thread t < SPT*8 owns
 // one (sample, block) column and adds its L rows (four independent accumulators so the loads pipeline; fixed tree).
 // Level 2 (after a barrier): every thread adds the BPG block sums of its group(s). Deterministic, tiling-independent.
@@ -154,8 +180,12 @@ __device__ __forceinline__ void gn_colsum(const float* __restrict__ part, float*
 // ---------------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------------
-template <int GS>
+// MODE: TCM_CONV5 = Conv1d k5 (+GN+Mish+cond+residual);  TCM_DOWN = Conv1d k3 stride 2 evaluated at every input position
+// (3 taps) with only the even rows written (MMA work is negligible next to the fixed costs);  TCM_UP = ConvTranspose1d
+// k4 stride 2 as two 2-tap accumulators (even / odd outputs).
+template <int MODE, int GS>
 __global__ void __launch_bounds__(TC_THREADS, 1) conv5_tc_kernel(TcConvArgs a) {
+    constexpr int NTAPS = MODE == TCM_CONV5 ? 5 : MODE == TCM_DOWN ? 3 : 4;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     // carve-up: stages | barriers | tmem slot | epilogue scratch
     unsigned char* stages = smem_raw;
@@ -182,12 +212,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv5_tc_kernel(TcConvArgs a) {
         const int s = i % TC_STAGES;
         const bool is_res = i >= n_main;
         const int c = is_res ? i - n_main : i;
-        const int ntaps = is_res ? 1 : 5;
+        const int ntaps = is_res ? 1 : NTAPS;
         const uint32_t bbytes = 2u * ntaps * TC_B_TAP_BYTES;
         const uint32_t st = smem_u32(stages + (size_t)s * TC_STAGE_BYTES);
         if (weights) {
             const unsigned short* wsrc = is_res ? a.res_w + ((size_t)ntile * n_res + c) * (2 * 1 * TC_B_TAP_BYTES / 2)
-                                                : a.w + ((size_t)ntile * n_main + c) * (2 * 5 * TC_B_TAP_BYTES / 2);
+                                                : a.w + ((size_t)ntile * n_main + c) * (2 * NTAPS * TC_B_TAP_BYTES / 2);
             mbar_expect_tx(full0 + 8 * s, 2u * TC_A_PLANE_BYTES + bbytes);  // covers the activation copies too
             bulk_g2s(st + 2 * TC_A_PLANE_BYTES, wsrc, bbytes, full0 + 8 * s);
         }
@@ -256,14 +286,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv5_tc_kernel(TcConvArgs a) {
             const uint32_t dcol = tmem_base + (is_res ? 2 * TC_NT : 0);
             if (!is_res) {
 #pragma unroll
-                for (int tap = 0; tap < 5; ++tap) {
+                for (int tap = 0; tap < NTAPS; ++tap) {
+                    // row shift of the tap (in 16-byte rows; +2 is the centre) and the accumulator it feeds
+                    //   CONV5: taps -2..2 -> shifts 0..4           DOWN (k3, pad 1): taps -1..1 -> shifts 1..3
+                    //   UP  : packed taps [W1, W3 | W0, W2]: even = W1 x[m] + W3 x[m-1], odd = W0 x[m+1] + W2 x[m]
+                    const int shift = MODE == TCM_CONV5 ? tap : MODE == TCM_DOWN ? tap + 1 : (tap == 0 ? 2 : tap == 1 ? 1 : tap == 2 ? 3 : 2);
+                    const bool second_acc = MODE == TCM_UP && tap >= 2;
+                    const uint32_t dc = tmem_base + (second_acc ? 2 * TC_NT : 0);
 #pragma unroll
                     for (int kk = 0; kk < TC_KCH / 16; ++kk) {
-                        const uint64_t aofs = (uint64_t)((kk * 2 * (TC_RT * 16) + tap * 16) >> 4);  // tap = one 16-byte row
+                        const uint64_t aofs = (uint64_t)((kk * 2 * (TC_RT * 16) + shift * 16) >> 4);
                         const uint64_t bofs = (uint64_t)((tap * 2 * TC_B_TAP_BYTES + kk * 2 * (2 * TC_NT * 16)) >> 4);
-                        tc_mma_bf16(dcol, dA_hi + aofs, dB + bofs, idesc64, first_main ? 0u : 1u);  // [hi*hi | hi*lo]
-                        first_main = false;
-                        tc_mma_bf16(dcol, dA_lo + aofs, dB + bofs, idesc32, 1u);                     // += lo*hi
+                        bool& first = second_acc ? first_res : first_main;
+                        tc_mma_bf16(dc, dA_hi + aofs, dB + bofs, idesc64, first ? 0u : 1u);  // [hi*hi | hi*lo]
+                        first = false;
+                        tc_mma_bf16(dc, dA_lo + aofs, dB + bofs, idesc32, 1u);               // += lo*hi
                     }
                 }
             } else {
@@ -301,8 +338,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv5_tc_kernel(TcConvArgs a) {
     float rid[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     if (full) {
         pb0 = *reinterpret_cast<const float4*>(a.bias + c8); pb1 = *reinterpret_cast<const float4*>(a.bias + c8 + 4);
-        pg0 = *reinterpret_cast<const float4*>(a.gamma + c8); pg1 = *reinterpret_cast<const float4*>(a.gamma + c8 + 4);
-        pe0 = *reinterpret_cast<const float4*>(a.beta + c8); pe1 = *reinterpret_cast<const float4*>(a.beta + c8 + 4);
+        if (MODE == TCM_CONV5) {
+            pg0 = *reinterpret_cast<const float4*>(a.gamma + c8); pg1 = *reinterpret_cast<const float4*>(a.gamma + c8 + 4);
+            pe0 = *reinterpret_cast<const float4*>(a.beta + c8); pe1 = *reinterpret_cast<const float4*>(a.beta + c8 + 4);
+        }
         if (a.cond != nullptr && valid) {
             const int tt = a.t_dev ? (int)a.t_dev[b] : a.t_uniform;
             const float* cp = a.cond + (size_t)tt * a.CO + c8;
@@ -338,6 +377,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv5_tc_kernel(TcConvArgs a) {
         float* dst = a.raw_out + (((size_t)tile * gridDim.y + ntile) * 128 + r) * 32 + cg * 8;
 #pragma unroll
         for (int j = 0; j < 8; ++j) dst[j] = v[j];
+    } else if (MODE == TCM_DOWN) {
+        // stride-2 conv: the MMA evaluated every input position; keep the even ones (out[m] = conv at l = 2m)
+        v[0] += pb0.x; v[1] += pb0.y; v[2] += pb0.z; v[3] += pb0.w;
+        v[4] += pb1.x; v[5] += pb1.y; v[6] += pb1.z; v[7] += pb1.w;
+        if (valid && (l & 1) == 0) tc_store_row(a, v, b, l >> 1, c8, a.L >> 1);
+    } else if (MODE == TCM_UP) {
+        // transposed conv: accumulator 0 = even outputs (2l), accumulator 1 = odd outputs (2l + 1)
+        float w[8], w2[8];
+        tc_ld8(taddr + 2 * TC_NT, w);
+        tc_ld8(taddr + 3 * TC_NT, w2);
+        v[0] += pb0.x; v[1] += pb0.y; v[2] += pb0.z; v[3] += pb0.w;
+        v[4] += pb1.x; v[5] += pb1.y; v[6] += pb1.z; v[7] += pb1.w;
+        w[0] += w2[0] + pb0.x; w[1] += w2[1] + pb0.y; w[2] += w2[2] + pb0.z; w[3] += w2[3] + pb0.w;
+        w[4] += w2[4] + pb1.x; w[5] += w2[5] + pb1.y; w[6] += w2[6] + pb1.z; w[7] += w2[7] + pb1.w;
+        if (valid) {
+            tc_store_row(a, v, b, 2 * l, c8, 2 * a.L);
+            tc_store_row(a, w, b, 2 * l + 1, c8, 2 * a.L);
+        }
     } else {
         v[0] += pb0.x; v[1] += pb0.y; v[2] += pb0.z; v[3] += pb0.w;
         v[4] += pb1.x; v[5] += pb1.y; v[6] += pb1.z; v[7] += pb1.w;
@@ -401,26 +458,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv5_tc_kernel(TcConvArgs a) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) v[j] += rid[j];
         }
-        if (valid) {
-            if (a.out_cm != nullptr) {
-                float* op = a.out_cm + ((size_t)b * a.CO + c8) * Lp + 2 + l;
-#pragma unroll
-                for (int j = 0; j < 8; ++j) op[(size_t)j * Lp] = v[j];
-            }
-            if (a.out_hi != nullptr) {
-                const size_t o = (((size_t)tile * (a.CO / 8) + c8 / 8) * TC_RT + (s * Lp + l + 2)) * 8;
-                unsigned short h[8], lo8[8];
-#pragma unroll
-                for (int e = 0; e < 8; ++e) split_bf16(v[e], h[e], lo8[e]);
-                uint4 ph, pl;
-                ph.x = h[0] | ((uint32_t)h[1] << 16); ph.y = h[2] | ((uint32_t)h[3] << 16);
-                ph.z = h[4] | ((uint32_t)h[5] << 16); ph.w = h[6] | ((uint32_t)h[7] << 16);
-                pl.x = lo8[0] | ((uint32_t)lo8[1] << 16); pl.y = lo8[2] | ((uint32_t)lo8[3] << 16);
-                pl.z = lo8[4] | ((uint32_t)lo8[5] << 16); pl.w = lo8[6] | ((uint32_t)lo8[7] << 16);
-                *reinterpret_cast<uint4*>(a.out_hi + o) = ph;
-                *reinterpret_cast<uint4*>(a.out_lo + o) = pl;
-            }
-        }
+        if (valid) tc_store_row(a, v, b, l, c8, a.L);
     }
 
     // teardown: all TMEM reads done before the allocating warp frees the columns
@@ -437,31 +475,33 @@ int launch_conv5_tc(const TcConvArgs& a, cudaStream_t stream) {
     MPDB_REQUIRE(a.c0 % TC_KCH == 0 && a.c1 % TC_KCH == 0 && a.c0 > 0, "tc conv: input widths must be multiples of 32");
     MPDB_REQUIRE(!a.res_w || (a.rc0 % TC_KCH == 0 && a.rc1 % TC_KCH == 0 && a.rc0 > 0), "tc conv: residual widths");
     MPDB_REQUIRE(a.L + 4 <= TC_RT && a.L % 4 == 0, "tc conv: L too large for one 128-row tile");
-    MPDB_REQUIRE(a.gamma && a.beta && (a.gs == 4 || a.gs == 8 || a.gs == 16 || a.gs == 32),
-                 "tc conv: GroupNorm group size must be 4, 8, 16 or 32");
+    MPDB_REQUIRE(a.mode == TCM_CONV5 || a.mode == TCM_DOWN || a.mode == TCM_UP, "tc conv: bad mode");
+    if (a.mode == TCM_CONV5)
+        MPDB_REQUIRE(a.gamma && a.beta && (a.gs == 4 || a.gs == 8 || a.gs == 16 || a.gs == 32),
+                     "tc conv: GroupNorm group size must be 4, 8, 16 or 32");
+    else
+        MPDB_REQUIRE(!a.res_w && !a.res_cm && !a.cond && !a.raw_out, "tc down/up: no residual / conditioning");
     const int SPT = TC_RT / (a.L + 4);
     MPDB_REQUIRE(SPT <= 12, "tc conv: too many samples per tile");
     const size_t smem = (size_t)TC_STAGES * TC_STAGE_BYTES + (2 * TC_STAGES + 1) * 8 + 16 + (2 * 128 * 8) * sizeof(float);
     dim3 grid((a.B + SPT - 1) / SPT, a.CO / TC_NT);
-#define MPDB_TC_CASE(G)                                                                                         \
-    case G: {                                                                                                   \
-        static bool configured = false;                                                                         \
-        if (!configured) {                                                                                      \
-            MPDB_CHECK_CUDA(cudaFuncSetAttribute(conv5_tc_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                                 220 * 1024));                                                  \
-            configured = true;                                                                                  \
-        }                                                                                                       \
-        MPDB_CHECK_CUDA(launch_kernel(conv5_tc_kernel<G>, grid, dim3(TC_THREADS), smem, stream, a));            \
-        break;                                                                                                  \
+#define MPDB_TC_LAUNCH(M, G)                                                                                       \
+    {                                                                                                              \
+        static bool configured = false;                                                                            \
+        if (!configured) {                                                                                         \
+            MPDB_CHECK_CUDA(cudaFuncSetAttribute(conv5_tc_kernel<M, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                                 220 * 1024));                                                     \
+            configured = true;                                                                                     \
+        }                                                                                                          \
+        MPDB_CHECK_CUDA(launch_kernel(conv5_tc_kernel<M, G>, grid, dim3(TC_THREADS), smem, stream, a));            \
     }
-    switch (a.gs) {
-        MPDB_TC_CASE(4)
-        MPDB_TC_CASE(8)
-        MPDB_TC_CASE(16)
-        MPDB_TC_CASE(32)
-        default: MPDB_REQUIRE(false, "tc conv: bad group size");
-    }
-#undef MPDB_TC_CASE
+    if (a.mode == TCM_DOWN) MPDB_TC_LAUNCH(TCM_DOWN, 4)
+    else if (a.mode == TCM_UP) MPDB_TC_LAUNCH(TCM_UP, 4)
+    else if (a.gs == 4) MPDB_TC_LAUNCH(TCM_CONV5, 4)
+    else if (a.gs == 8) MPDB_TC_LAUNCH(TCM_CONV5, 8)
+    else if (a.gs == 16) MPDB_TC_LAUNCH(TCM_CONV5, 16)
+    else MPDB_TC_LAUNCH(TCM_CONV5, 32)
+#undef MPDB_TC_LAUNCH
     MPDB_LAUNCH_CHECK();
     return 0;
 }
@@ -471,7 +511,10 @@ int launch_conv5_tc(const TcConvArgs& a, cudaStream_t stream) {
 // ---------------------------------------------------------------------------------------------------
 // weights: src fp32 [ci][ntaps][CO] (the SIMT path's packed layout) ->
 //   dst bf16 [CO/32][CI/32][ntaps][kg 4][64 rows: 32 hi | 32 lo][8]
-__global__ void pack_tc_weights_kernel(const float* __restrict__ src, unsigned short* __restrict__ dst, int CI, int CO, int ntaps) {
+//   CI is the padded input width (multiple of 32); channels >= CI_src are zero. `perm` maps destination tap -> source tap
+//   (ConvTranspose: [1, 3, 0, 2], see the kernel), packed 4 bits per tap.
+__global__ void pack_tc_weights_kernel(const float* __restrict__ src, unsigned short* __restrict__ dst, int CI, int CI_src,
+                                       int CO, int ntaps, unsigned perm) {
     const long long n = (long long)CI * CO * ntaps;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         const int e = (int)(i % 8);
@@ -483,8 +526,9 @@ __global__ void pack_tc_weights_kernel(const float* __restrict__ src, unsigned s
         const int ntile = (int)(rest / (CI / TC_KCH));
         const int ci = chunk * TC_KCH + kg * 8 + e;
         const int co = ntile * TC_NT + nn;
-        unsigned short hi, lo;
-        split_bf16(src[((long long)ci * ntaps + tap) * CO + co], hi, lo);
+        const int stap = (int)((perm >> (4 * tap)) & 0xF);
+        unsigned short hi = 0, lo = 0;
+        if (ci < CI_src) split_bf16(src[((long long)ci * ntaps + stap) * CO + co], hi, lo);
         const long long blk = ((long long)ntile * (CI / TC_KCH) + chunk) * (2LL * ntaps * (TC_KCH / 8) * TC_NT * 8);
         const long long row0 = (((long long)tap * (TC_KCH / 8) + kg) * (2 * TC_NT)) * 8;
         dst[blk + row0 + (long long)nn * 8 + e] = hi;
@@ -492,11 +536,50 @@ __global__ void pack_tc_weights_kernel(const float* __restrict__ src, unsigned s
     }
 }
 
-int launch_pack_tc_weights(const float* src, unsigned short* dst, int CI, int CO, int ntaps, cudaStream_t stream) {
+int launch_pack_tc_weights(const float* src, unsigned short* dst, int CI, int CI_src, int CO, int ntaps, unsigned perm,
+                           cudaStream_t stream) {
     long long n = (long long)CI * CO * ntaps;
     int blocks = (int)((n + 255) / 256);
     if (blocks > 2048) blocks = 2048;
-    pack_tc_weights_kernel<<<blocks, 256, 0, stream>>>(src, dst, CI, CO, ntaps);
+    pack_tc_weights_kernel<<<blocks, 256, 0, stream>>>(src, dst, CI, CI_src, CO, ntaps, perm);
+    MPDB_LAUNCH_CHECK();
+    return 0;
+}
+
+// trajectory x [B][L][D] (BLC fp32) -> TC layout planes with the channels padded to C (>= D, multiple of 8); the padding
+// channels are never written (zero forever). One thread per (b, l): D split-bf16 values -> 16-byte stores per k-group.
+__global__ void blc_to_tc_kernel(const float* __restrict__ x, unsigned short* __restrict__ hi, unsigned short* __restrict__ lo,
+                                 int B, int L, int D, int C) {
+    pdl_wait();
+    const int Lp = L + 4, SPT = TC_RT / Lp;
+    const long long n = (long long)B * L;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int l = (int)(i % L), b = (int)(i / L);
+        const int tile = b / SPT, s = b - tile * SPT;
+        const float* xp = x + i * D;
+        for (int kg = 0; kg * 8 < D; ++kg) {
+            unsigned short h[8], w[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                h[e] = 0; w[e] = 0;
+                if (kg * 8 + e < D) split_bf16(xp[kg * 8 + e], h[e], w[e]);
+            }
+            const long long o = (((long long)tile * (C / 8) + kg) * TC_RT + (s * Lp + l + 2)) * 8;
+            uint4 ph, pl;
+            ph.x = h[0] | ((uint32_t)h[1] << 16); ph.y = h[2] | ((uint32_t)h[3] << 16);
+            ph.z = h[4] | ((uint32_t)h[5] << 16); ph.w = h[6] | ((uint32_t)h[7] << 16);
+            pl.x = w[0] | ((uint32_t)w[1] << 16); pl.y = w[2] | ((uint32_t)w[3] << 16);
+            pl.z = w[4] | ((uint32_t)w[5] << 16); pl.w = w[6] | ((uint32_t)w[7] << 16);
+            *reinterpret_cast<uint4*>(hi + o) = ph;
+            *reinterpret_cast<uint4*>(lo + o) = pl;
+        }
+    }
+}
+
+int launch_blc_to_tc(const float* x, unsigned short* hi, unsigned short* lo, int B, int L, int D, int C, cudaStream_t stream) {
+    long long n = (long long)B * L;
+    int blocks = (int)((n + 127) / 128);
+    MPDB_CHECK_CUDA(launch_kernel(blc_to_tc_kernel, dim3(blocks), dim3(128), 0, stream, x, hi, lo, B, L, D, C));
     MPDB_LAUNCH_CHECK();
     return 0;
 }
