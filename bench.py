@@ -396,8 +396,14 @@ def main():
                      f"{int(dom.sum())} launches per UNet forward")
             note = ("fp32 CUDA-core FMA kernel (exact fp32 parity path); achieved = algorithmic 2*MAC FLOPs of its launches / "
                     f"their summed CUDA-event time; share of one UNet forward {dom_ms / fwd_ms:.3f}")
+        traffic = {}
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload, {})
+        except Exception:
+            pass
+        tr_conv = traffic.get("conv5_tc_kernel", {}).get("bytes_per_launch") if tcm.any() else None
         roofline = {"kernel": kname, "bound": "tensor", "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s",
-                    "frac": ach_tf / peak_tf, "traffic": None, "peak_source": peak_src, "note": note,
+                    "frac": ach_tf / peak_tf, "traffic": tr_conv, "peak_source": peak_src, "note": note,
                     "issued_tflops": ach_tf * (3 if tcm.any() else 1),
                     "unet_forward_ms": fwd_ms, "unet_flops_per_trajectory_per_forward": flops_traj,
                     "per_launch_us": [round(float(v) * 1e3, 2) for v in ms], "per_launch_mode": [int(v) for v in md]}
@@ -410,7 +416,10 @@ def main():
         ach_gbs = sdf_bytes * B / (gms.value * 1e-3) / 1e9
         roofline_sdf = {"kernel": "mpdb::guide_step_kernel (unnormalise+interp+FK+SDF lookup+adjoint+clip+GP stencil+update)",
                         "bound": "hbm", "achieved": ach_gbs, "peak": peak_hbm, "unit": "GB/s", "frac": ach_gbs / peak_hbm,
-                        "traffic": None, "ms_per_launch": gms.value, "bytes_per_trajectory": sdf_bytes}
+                        "traffic": traffic.get("guide_step_kernel", {}).get("bytes_per_launch"),
+                        "ms_per_launch": gms.value, "bytes_per_trajectory": sdf_bytes,
+                        "note": "algorithmic bytes = 2*H*D*4 + fields*128*spheres*texel per trajectory (SURVEY 8d); at B=100 one "
+                                "launch moves 2.4 MB and is latency-bound, not bandwidth-bound"}
 
         cfg = workload_config(args.workload, n_gpus)
         result = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": K, "warmup": W,
