@@ -159,6 +159,11 @@ int mpdb_guide_grad(mpdb_guide* g, const float* x, float* grad, int32_t B, int32
  * sample_functions.py:65-83. model_var: device [B] or NULL. hard-cond arrays as in mpdb_loop_params. */
 int mpdb_guide_steps(mpdb_guide* g, float* x, int32_t n_steps, const float* model_var, int32_t n_hard_conds,
                      const int32_t* hard_cond_rows, const float* hard_cond_vals, int32_t B, int32_t H, void* stream);
+/* Post-sampling evaluation (inference.py:288-326): per UNNORMALISED trajectory x [B,H,D] ->
+ * stats device [B][4] = {#interpolated waypoints in collision (sdf - radius < margin in any field), smoothness
+ * sum_h |v_{h+1} - v_h|, path length sum_h |p_{h+1} - p_h|, minimum clearance}. Uses the guide's robot / fields. */
+int mpdb_eval_trajectories(mpdb_guide* g, const float* x_unnormalized, float* stats, float margin, int32_t B, int32_t H,
+                           void* stream);
 /* samples analytic primitives (spheres [ns][dim+1], boxes [nb][2*dim], host arrays) onto the voxel grid:
  * texels_out device [prod(shape)][1+dim] */
 int mpdb_sdf_grid_build(int32_t dim, const int32_t* shape, const float* lo, float cell, const float* spheres,

@@ -10,6 +10,7 @@ from .sample_functions import apply_hard_conditioning, extract, ddpm_sample_fn, 
 from .guides import GuideManagerTrajectoriesWithVelocity  # noqa: F401
 from .costs import CostCollision, CostGPTrajectory, CostComposite, GridSDFField, WorkspaceBoundaryField  # noqa: F401
 from .normalization import LimitsNormalizer, DatasetNormalizer  # noqa: F401
-from .planning import TrajectoryDataset, PlanningTask, Robot  # noqa: F401
+from .planning import (TrajectoryDataset, PlanningTask, Robot, compute_smoothness, compute_path_length,  # noqa: F401
+                       compute_variance_waypoints)
 
 __version__ = "0.1.0"

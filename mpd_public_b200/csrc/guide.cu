@@ -112,6 +112,85 @@ static GuideDev make_dev(const mpdb_guide_config& c) {
     return d;
 }
 
+// Forward kinematics of one interpolated row: joint origins (3 x 7), joint axes (3 x 7) and collision-sphere centres
+// (3 x n_spheres) into per-row scratch with stride FK_ROWS. Panda chain: T_i = T_{i-1} Trans(xyz_i) Rx(roll_i) Rz(q_i)
+// (SURVEY Appendix E); point mass: centre = q.
+__device__ __forceinline__ void fk_row(const GuideDev& g, const float (&qv)[7], float* sc, float* cen) {
+    if (g.robot_kind == 1) {
+        float R[9] = {1.f, 0.f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f, 1.f};  // row-major
+        float o[3] = {0.f, 0.f, 0.f};
+#pragma unroll 1
+        for (int j = 0; j < 7; ++j) {
+#pragma unroll
+            for (int r3 = 0; r3 < 3; ++r3)
+                o[r3] += R[r3 * 3 + 0] * g.joint_xyz[j][0] + R[r3 * 3 + 1] * g.joint_xyz[j][1] + R[r3 * 3 + 2] * g.joint_xyz[j][2];
+            float sq, cq;
+            sincosf(qv[j], &sq, &cq);
+            const float cr = g.joint_cr[j], sr = g.joint_sr[j];
+#pragma unroll
+            for (int r3 = 0; r3 < 3; ++r3) {
+                float c0 = R[r3 * 3 + 0], c1 = R[r3 * 3 + 1], c2 = R[r3 * 3 + 2];
+                float a1 = c1 * cr + c2 * sr;   // (R Rx) column 1
+                float a2 = -c1 * sr + c2 * cr;  // (R Rx) column 2
+                R[r3 * 3 + 0] = cq * c0 + sq * a1;
+                R[r3 * 3 + 1] = -sq * c0 + cq * a1;
+                R[r3 * 3 + 2] = a2;
+            }
+#pragma unroll
+            for (int r3 = 0; r3 < 3; ++r3) {
+                sc[(j * 3 + r3) * FK_ROWS] = o[r3];
+                sc[(21 + j * 3 + r3) * FK_ROWS] = R[r3 * 3 + 2];  // joint axis = third column
+            }
+            for (int s = 0; s < g.n_spheres; ++s)
+                if (g.sphere_frame[s] == j + 1)
+                    for (int r3 = 0; r3 < 3; ++r3)
+                        cen[(s * 3 + r3) * FK_ROWS] = o[r3] + R[r3 * 3 + 0] * g.sphere_off[s][0] +
+                                                      R[r3 * 3 + 1] * g.sphere_off[s][1] + R[r3 * 3 + 2] * g.sphere_off[s][2];
+        }
+#pragma unroll
+        for (int r3 = 0; r3 < 3; ++r3)
+            o[r3] += R[r3 * 3 + 0] * g.flange[0] + R[r3 * 3 + 1] * g.flange[1] + R[r3 * 3 + 2] * g.flange[2];
+        for (int s = 0; s < g.n_spheres; ++s)
+            if (g.sphere_frame[s] == 8)
+                for (int r3 = 0; r3 < 3; ++r3)
+                    cen[(s * 3 + r3) * FK_ROWS] = o[r3] + R[r3 * 3 + 0] * g.sphere_off[s][0] + R[r3 * 3 + 1] * g.sphere_off[s][1] +
+                                                  R[r3 * 3 + 2] * g.sphere_off[s][2];
+    } else {
+        for (int s = 0; s < g.n_spheres; ++s)
+            for (int r3 = 0; r3 < 3; ++r3) cen[(s * 3 + r3) * FK_ROWS] = r3 < g.ws_dim ? qv[r3] : 0.f;
+    }
+}
+
+// Signed distance (and stored gradient) of field f at point p: nearest-texel lookup on the voxel grid (Appendix C.5) or
+// the analytic workspace-boundary box (C.4).
+__device__ __forceinline__ void field_lookup(const GuideDev& g, int f, const float (&p)[3], float& sdf, float (&gr)[3]) {
+    gr[0] = gr[1] = gr[2] = 0.f;
+    if (f < g.n_grid) {
+        long long flat = 0;
+        for (int d = 0; d < g.ws_dim; ++d) {
+            float uu = rintf(__fdiv_rn(__fsub_rn(p[d], g.glo[d]), g.cell));
+            uu = fminf(fmaxf(uu, 0.f), (float)(g.gshape[d] - 1));
+            flat = flat * g.gshape[d] + (long long)uu;
+        }
+        if (g.ws_dim == 3) {
+            float4 t = __ldg(reinterpret_cast<const float4*>(g.tex[f]) + flat);
+            sdf = t.x; gr[0] = t.y; gr[1] = t.z; gr[2] = t.w;
+        } else {
+            const float* t = g.tex[f] + flat * 3;
+            sdf = __ldg(t); gr[0] = __ldg(t + 1); gr[1] = __ldg(t + 2);
+        }
+    } else {
+        int arg = 0; float sgn = 1.f, best = 3.4e38f;
+        for (int d = 0; d < g.ws_dim; ++d) {
+            float lo = __fsub_rn(p[d], g.blo[d]), hi = __fsub_rn(g.bhi[d], p[d]);
+            float m = fminf(lo, hi);
+            if (m < best) { best = m; arg = d; sgn = (lo <= hi) ? 1.f : -1.f; }
+        }
+        sdf = best;
+        gr[arg] = sgn;
+    }
+}
+
 __device__ __forceinline__ float clip_scale(float n, float max_norm) {
     // torch.clip(n, 0, max) / n
     return fminf(fmaxf(n, 0.f), max_norm) / n;
@@ -169,54 +248,7 @@ __global__ void __launch_bounds__(GUIDE_THREADS) guide_step_kernel(GuideDev g, G
                 for (int k = 0; k < 7; ++k)
                     qv[k] = k < q ? __fadd_rn(__fmul_rn(l0, xu[i0 * D + k]), __fmul_rn(l1, xu[i1 * D + k])) : 0.f;
 
-                float* sc = fk + tid;  // element j at sc[j * FK_ROWS]
-                float* cen = sc + 42 * FK_ROWS;
-                if (g.robot_kind == 1) {
-                    float R[9] = {1.f, 0.f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f, 1.f};  // row-major
-                    float o[3] = {0.f, 0.f, 0.f};
-#pragma unroll 1
-                    for (int j = 0; j < 7; ++j) {
-#pragma unroll
-                        for (int r3 = 0; r3 < 3; ++r3)
-                            o[r3] += R[r3 * 3 + 0] * g.joint_xyz[j][0] + R[r3 * 3 + 1] * g.joint_xyz[j][1] +
-                                     R[r3 * 3 + 2] * g.joint_xyz[j][2];
-                        float sq, cq;
-                        sincosf(qv[j], &sq, &cq);
-                        const float cr = g.joint_cr[j], sr = g.joint_sr[j];
-#pragma unroll
-                        for (int r3 = 0; r3 < 3; ++r3) {
-                            float c0 = R[r3 * 3 + 0], c1 = R[r3 * 3 + 1], c2 = R[r3 * 3 + 2];
-                            float a1 = c1 * cr + c2 * sr;   // (R Rx) column 1
-                            float a2 = -c1 * sr + c2 * cr;  // (R Rx) column 2
-                            R[r3 * 3 + 0] = cq * c0 + sq * a1;
-                            R[r3 * 3 + 1] = -sq * c0 + cq * a1;
-                            R[r3 * 3 + 2] = a2;
-                        }
-#pragma unroll
-                        for (int r3 = 0; r3 < 3; ++r3) {
-                            sc[(j * 3 + r3) * FK_ROWS] = o[r3];
-                            sc[(21 + j * 3 + r3) * FK_ROWS] = R[r3 * 3 + 2];  // joint axis = third column
-                        }
-                        for (int s = 0; s < g.n_spheres; ++s)
-                            if (g.sphere_frame[s] == j + 1)
-                                for (int r3 = 0; r3 < 3; ++r3)
-                                    cen[(s * 3 + r3) * FK_ROWS] = o[r3] + R[r3 * 3 + 0] * g.sphere_off[s][0] +
-                                                                  R[r3 * 3 + 1] * g.sphere_off[s][1] +
-                                                                  R[r3 * 3 + 2] * g.sphere_off[s][2];
-                    }
-#pragma unroll
-                    for (int r3 = 0; r3 < 3; ++r3)
-                        o[r3] += R[r3 * 3 + 0] * g.flange[0] + R[r3 * 3 + 1] * g.flange[1] + R[r3 * 3 + 2] * g.flange[2];
-                    for (int s = 0; s < g.n_spheres; ++s)
-                        if (g.sphere_frame[s] == 8)
-                            for (int r3 = 0; r3 < 3; ++r3)
-                                cen[(s * 3 + r3) * FK_ROWS] = o[r3] + R[r3 * 3 + 0] * g.sphere_off[s][0] +
-                                                              R[r3 * 3 + 1] * g.sphere_off[s][1] +
-                                                              R[r3 * 3 + 2] * g.sphere_off[s][2];
-                } else {
-                    for (int s = 0; s < g.n_spheres; ++s)
-                        for (int r3 = 0; r3 < 3; ++r3) cen[(s * 3 + r3) * FK_ROWS] = r3 < g.ws_dim ? qv[r3] : 0.f;
-                }
+                fk_row(g, qv, fk + tid, fk + tid + 42 * FK_ROWS);
             }
             __syncthreads();
 
@@ -238,31 +270,7 @@ __global__ void __launch_bounds__(GUIDE_THREADS) guide_step_kernel(GuideDev g, G
                         tsdf[u] = 3.4e38f; tg[u][0] = tg[u][1] = tg[u][2] = 0.f;
                         if (s < g.n_spheres) {
                             const float p[3] = {cen[(s * 3 + 0) * FK_ROWS], cen[(s * 3 + 1) * FK_ROWS], cen[(s * 3 + 2) * FK_ROWS]};
-                            if (f < g.n_grid) {
-                                long long flat = 0;
-                                for (int d = 0; d < g.ws_dim; ++d) {
-                                    float uu = rintf(__fdiv_rn(__fsub_rn(p[d], g.glo[d]), g.cell));
-                                    uu = fminf(fmaxf(uu, 0.f), (float)(g.gshape[d] - 1));
-                                    flat = flat * g.gshape[d] + (long long)uu;
-                                }
-                                if (g.ws_dim == 3) {
-                                    float4 t = __ldg(reinterpret_cast<const float4*>(g.tex[f]) + flat);
-                                    tsdf[u] = t.x; tg[u][0] = t.y; tg[u][1] = t.z; tg[u][2] = t.w;
-                                } else {
-                                    const float* t = g.tex[f] + flat * 3;
-                                    tsdf[u] = __ldg(t); tg[u][0] = __ldg(t + 1); tg[u][1] = __ldg(t + 2);
-                                }
-                            } else {
-                                // workspace-boundary field: distance to the nearest wall, positive inside
-                                int arg = 0; float sgn = 1.f, best = 3.4e38f;
-                                for (int d = 0; d < g.ws_dim; ++d) {
-                                    float lo = __fsub_rn(p[d], g.blo[d]), hi = __fsub_rn(g.bhi[d], p[d]);
-                                    float m = fminf(lo, hi);
-                                    if (m < best) { best = m; arg = d; sgn = (lo <= hi) ? 1.f : -1.f; }
-                                }
-                                tsdf[u] = best;
-                                tg[u][0] = arg == 0 ? sgn : 0.f; tg[u][1] = arg == 1 ? sgn : 0.f; tg[u][2] = arg == 2 ? sgn : 0.f;
-                            }
+                            field_lookup(g, f, p, tsdf[u], tg[u]);
                         }
                     }
 #pragma unroll
@@ -395,6 +403,93 @@ __global__ void __launch_bounds__(GUIDE_THREADS) guide_step_kernel(GuideDev g, G
     }
     if (a.flag_out != nullptr) {
         if (__syncthreads_or(viol ? 1 : 0) && tid == 0) atomicOr(a.flag_out, 1);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Post-sampling evaluation (reference inference.py:288-326: get_trajs_collision_and_free,
+// compute_collision_intensity_trajs, compute_smoothness, compute_path_length): forward-only reuse of the guide's
+// interpolation + FK + field lookups. One CTA per (unnormalised) trajectory.
+//   stats[b] = { #interpolated waypoints in collision, smoothness = sum_h |v_{h+1} - v_h|, path length = sum_h |p_{h+1} - p_h|,
+//                minimum clearance min(sdf - radius) over waypoints, spheres and fields }
+// A waypoint is in collision when any sphere has sdf - radius < margin in any field.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(FK_ROWS) eval_kernel(GuideDev g, const float* __restrict__ x, float* __restrict__ stats,
+                                                       float margin, int B, int H) {
+    extern __shared__ __align__(16) float smem[];
+    const int D = g.D, q = g.q_dim, NI = g.n_interp;
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const int n_coll = g.n_grid + (g.has_border ? 1 : 0);
+    float* xu = smem;                      // [H][D]
+    float* red = xu + H * D;               // [FK_ROWS] reduction scratch
+    float* fk = red + FK_ROWS;             // [(42 + 3*n_spheres)][FK_ROWS]
+    for (int i = tid; i < H * D; i += FK_ROWS) xu[i] = x[(long long)b * H * D + i];
+    __syncthreads();
+    int n_bad = 0;
+    float clearance = 3.4e38f;
+    const float ratio = NI > 1 ? (float)(H - 1) / (float)(NI - 1) : 0.f;
+    for (int ibase = 0; ibase < NI; ibase += FK_ROWS) {
+        const int i = ibase + tid;
+        bool bad = false;
+        if (i < NI) {
+            float r = ratio * (float)i;
+            int i0 = (int)r;
+            if (i0 > H - 1) i0 = H - 1;
+            const float l1 = fminf(fmaxf(r - (float)i0, 0.f), 1.f), l0 = 1.f - l1;
+            const int i1 = i0 + (i0 < H - 1 ? 1 : 0);
+            float qv[7];
+#pragma unroll
+            for (int k = 0; k < 7; ++k)
+                qv[k] = k < q ? __fadd_rn(__fmul_rn(l0, xu[i0 * D + k]), __fmul_rn(l1, xu[i1 * D + k])) : 0.f;
+            float* sc = fk + tid;
+            float* cen = sc + 42 * FK_ROWS;
+            fk_row(g, qv, sc, cen);
+            for (int f = 0; f < n_coll; ++f)
+                for (int s = 0; s < g.n_spheres; ++s) {
+                    const float p[3] = {cen[(s * 3 + 0) * FK_ROWS], cen[(s * 3 + 1) * FK_ROWS], cen[(s * 3 + 2) * FK_ROWS]};
+                    float sdf, gr[3];
+                    field_lookup(g, f, p, sdf, gr);
+                    const float c = __fsub_rn(sdf, g.sphere_r[s]);
+                    clearance = fminf(clearance, c);
+                    bad |= c < margin;
+                }
+        }
+        n_bad += __syncthreads_count(bad ? 1 : 0);
+    }
+    // minimum clearance over the block
+    red[tid] = clearance;
+    __syncthreads();
+    for (int o = FK_ROWS / 2; o > 0; o >>= 1) {
+        if (tid < o) red[tid] = fminf(red[tid], red[tid + o]);
+        __syncthreads();
+    }
+    const float min_clear = red[0];
+    __syncthreads();
+    // smoothness and path length on the support points, fixed-order sums
+    float sm = 0.f, pl = 0.f;
+    for (int h = tid; h < H - 1; h += FK_ROWS) {
+        float dv = 0.f, dp = 0.f;
+        for (int k = 0; k < q; ++k) {
+            const float a = xu[(h + 1) * D + k] - xu[h * D + k];
+            const float c = xu[(h + 1) * D + q + k] - xu[h * D + q + k];
+            dp = fmaf(a, a, dp);
+            dv = fmaf(c, c, dv);
+        }
+        sm += sqrtf(dv);
+        pl += sqrtf(dp);
+    }
+    red[tid] = sm;
+    __syncthreads();
+    if (tid == 0) { float t = 0.f; for (int k = 0; k < FK_ROWS; ++k) t += red[k]; stats[b * 4 + 1] = t; }
+    __syncthreads();
+    red[tid] = pl;
+    __syncthreads();
+    if (tid == 0) {
+        float t = 0.f;
+        for (int k = 0; k < FK_ROWS; ++k) t += red[k];
+        stats[b * 4 + 2] = t;
+        stats[b * 4 + 0] = (float)n_bad;
+        stats[b * 4 + 3] = min_clear;
     }
 }
 
@@ -629,5 +724,23 @@ extern "C" int mpdb_profile_guide(mpdb_guide* g, float* x, int32_t B, int32_t H,
     *ms_out = ms / reps;
     cudaEventDestroy(ev0);
     cudaEventDestroy(ev1);
+    return 0;
+}
+
+extern "C" int mpdb_eval_trajectories(mpdb_guide* gd, const float* x_unnormalized, float* stats, float margin, int32_t B,
+                                      int32_t H, void* stream) {
+    MPDB_REQUIRE(gd && x_unnormalized && stats && B > 0 && H > 1, "mpdb_eval_trajectories: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    MPDB_CHECK_CUDA(cudaSetDevice(gd->device));
+    GuideDev g = make_dev(gd->cfg);
+    const size_t smem = sizeof(float) * ((size_t)H * g.D + FK_ROWS + (size_t)(42 + 3 * g.n_spheres) * FK_ROWS);
+    MPDB_REQUIRE(smem <= 200 * 1024, "mpdb_eval_trajectories: trajectory does not fit in shared memory");
+    static bool configured = false;
+    if (!configured) {
+        MPDB_CHECK_CUDA(cudaFuncSetAttribute(eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        configured = true;
+    }
+    eval_kernel<<<B, FK_ROWS, smem, st>>>(g, x_unnormalized, stats, margin, B, H);
+    MPDB_LAUNCH_CHECK();
     return 0;
 }

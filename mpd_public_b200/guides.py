@@ -17,6 +17,62 @@ from . import _lib
 from .costs import CostCollision, CostComposite, CostGPTrajectory, GridSDFField, WorkspaceBoundaryField
 
 
+def build_guide_config(robot, mins, maxs, collision_fields, gp, cutoff_margin, clip_grad, max_grad_norm, n_interp):
+    """mpdb_guide_config from a robot description, normaliser limits, [(field, weight)] and (dt, sigma_gp, weight) | None.
+    Returns (cfg, tensors kept alive because the config references them by raw pointer)."""
+    cfg = _lib.GuideConfig()
+    cfg.robot_kind = 1 if robot.kind == "panda" else 0
+    cfg.q_dim, cfg.ws_dim, cfg.n_spheres = robot.q_dim, robot.ws_dim, robot.n_spheres
+    for i in range(robot.n_spheres):
+        cfg.sphere_frame[i] = int(robot.sphere_frame[i])
+        for k in range(3):
+            cfg.sphere_offset[i][k] = float(robot.sphere_offset[i][k])
+        cfg.sphere_radius[i] = float(robot.sphere_radius[i])
+    if len(mins) != 2 * robot.q_dim:
+        raise RuntimeError("normaliser limits must cover [q, qdot]")
+    for i in range(len(mins)):
+        cfg.mins[i], cfg.maxs[i] = float(mins[i]), float(maxs[i])
+    keep = []
+    n_grid = 0
+    cfg.has_border = 0
+    for f, w in collision_fields:
+        if isinstance(f, GridSDFField):
+            if n_grid >= _lib.MAX_GRID_FIELDS:
+                raise RuntimeError(f"at most {_lib.MAX_GRID_FIELDS} grid-backed collision fields")
+            if n_grid == 0:
+                for k in range(f.dim):
+                    cfg.grid_shape[k] = f.shape[k]
+                    cfg.grid_lo[k] = float(f.limits[0][k])
+                cfg.grid_cell = f.cell
+            elif tuple(cfg.grid_shape[:f.dim]) != f.shape or abs(cfg.grid_cell - f.cell) > 1e-6 * abs(f.cell):
+                raise NotImplementedError("all grid fields must share one lattice")
+            cfg.grid_texels[n_grid] = f.texels.data_ptr()
+            cfg.weight_grid[n_grid] = float(w)
+            keep.append(f.texels)
+            n_grid += 1
+        elif isinstance(f, WorkspaceBoundaryField):
+            if cfg.has_border:
+                raise NotImplementedError("one workspace-boundary field")
+            cfg.has_border = 1
+            for k in range(f.limits.shape[1]):
+                cfg.border_lo[k], cfg.border_hi[k] = float(f.limits[0][k]), float(f.limits[1][k])
+            cfg.weight_border = float(w)
+        else:
+            raise NotImplementedError(f"unsupported field {type(f).__name__}")
+    cfg.n_grid_fields = n_grid
+    cfg.cutoff_margin = float(cutoff_margin)
+    if gp is not None:
+        cfg.use_gp = 1
+        cfg.dt, cfg.sigma_gp, cfg.weight_gp = float(gp[0]), float(gp[1]), float(gp[2])
+    else:
+        cfg.use_gp = 0
+        cfg.dt, cfg.sigma_gp = 1.0, 1.0
+    cfg.clip_grad = int(bool(clip_grad))
+    cfg.max_grad_norm = float(max_grad_norm)
+    cfg.n_interp = int(n_interp)
+    return cfg, keep
+
+
 def _dataset_limits(dataset):
     """mins/maxs of the trajectory normaliser, as the reference reaches them (trajectories.py:196-197)."""
     nz = dataset.normalizer
@@ -49,64 +105,20 @@ class GuideManagerTrajectoriesWithVelocity(nn.Module):
 
     # ---- C-ABI handle ----
     def _config(self, H):
-        robot = self.cost.robot
-        cfg = _lib.GuideConfig()
-        cfg.robot_kind = 1 if robot.kind == "panda" else 0
-        cfg.q_dim, cfg.ws_dim, cfg.n_spheres = robot.q_dim, robot.ws_dim, robot.n_spheres
-        for i in range(robot.n_spheres):
-            cfg.sphere_frame[i] = int(robot.sphere_frame[i])
-            for k in range(3):
-                cfg.sphere_offset[i][k] = float(robot.sphere_offset[i][k])
-            cfg.sphere_radius[i] = float(robot.sphere_radius[i])
         mins, maxs = _dataset_limits(self.dataset)
-        if len(mins) != 2 * robot.q_dim:
-            raise RuntimeError("normaliser limits must cover [q, qdot]")
-        for i in range(len(mins)):
-            cfg.mins[i], cfg.maxs[i] = float(mins[i]), float(maxs[i])
-        keep = []  # tensors referenced by raw pointer
-        n_grid = 0
-        cfg.has_border = 0
-        cfg.use_gp = 0
+        coll, gp = [], None
         margin = None
         for c, w in zip(self.cost.cost_l, self.cost.weights_cost_l):
             if isinstance(c, CostCollision):
-                f = c.field
-                m = float(getattr(c.robot, "cutoff_margin", 0.05) if getattr(c, "cutoff_margin", None) is None else c.cutoff_margin)
+                coll.append((c.field, float(w)))
+                m = getattr(c, "cutoff_margin", None)
+                m = float(getattr(c.robot, "cutoff_margin", 0.05)) if m is None else float(m)
                 margin = m if margin is None else margin
-                if isinstance(f, GridSDFField):
-                    if n_grid >= _lib.MAX_GRID_FIELDS:
-                        raise RuntimeError(f"at most {_lib.MAX_GRID_FIELDS} grid-backed collision fields")
-                    if n_grid == 0:
-                        for k in range(f.dim):
-                            cfg.grid_shape[k] = f.shape[k]
-                            cfg.grid_lo[k] = float(f.limits[0][k])
-                        cfg.grid_cell = f.cell
-                    elif tuple(cfg.grid_shape[:f.dim]) != f.shape or abs(cfg.grid_cell - f.cell) > 1e-6 * abs(f.cell):
-                        raise NotImplementedError("all grid fields must share one lattice")
-                    cfg.grid_texels[n_grid] = f.texels.data_ptr()
-                    cfg.weight_grid[n_grid] = float(w)
-                    keep.append(f.texels)
-                    n_grid += 1
-                elif isinstance(f, WorkspaceBoundaryField):
-                    if cfg.has_border:
-                        raise NotImplementedError("one workspace-boundary field")
-                    cfg.has_border = 1
-                    for k in range(f.limits.shape[1]):
-                        cfg.border_lo[k], cfg.border_hi[k] = float(f.limits[0][k]), float(f.limits[1][k])
-                    cfg.weight_border = float(w)
-                else:
-                    raise NotImplementedError(f"unsupported field {type(f).__name__}")
             elif isinstance(c, CostGPTrajectory):
-                cfg.use_gp = 1
-                cfg.dt, cfg.sigma_gp, cfg.weight_gp = c.dt, c.sigma_gp, float(w)
-        cfg.n_grid_fields = n_grid
-        cfg.cutoff_margin = 0.05 if margin is None else margin
-        if not cfg.use_gp:
-            cfg.dt, cfg.sigma_gp = 1.0, 1.0
-        cfg.clip_grad = int(bool(self.clip_grad))
-        cfg.max_grad_norm = float(self.max_grad_norm)
-        cfg.n_interp = int(self.num_interpolated_points_for_collision) if self.interpolate_trajectories_for_collision else int(H)
-        return cfg, keep
+                gp = (c.dt, c.sigma_gp, float(w))
+        n_interp = int(self.num_interpolated_points_for_collision) if self.interpolate_trajectories_for_collision else int(H)
+        return build_guide_config(self.cost.robot, mins, maxs, coll, gp, 0.05 if margin is None else margin,
+                                  self.clip_grad, self.max_grad_norm, n_interp)
 
     def _handle(self, device, H):
         device = torch.device(device)

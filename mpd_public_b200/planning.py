@@ -53,6 +53,77 @@ class PlanningTask:
     def get_collision_fields_extra_objects(self):
         return self.get_collision_fields()[1:-1]
 
+    # ---- post-sampling evaluation (reference inference.py:288-326; torch_robotics PlanningTask, sources absent) ----
+    def evaluate_trajectories(self, trajs, margin=0.0, n_interp=128):
+        """One fused kernel over UNNORMALISED trajectories [B, H, D] -> dict of per-trajectory tensors:
+        n_waypoints_in_collision, smoothness, path_length, min_clearance, in_collision (bool)."""
+        import ctypes as C
+        from . import _lib
+        from .guides import build_guide_config
+        _lib.require_cuda(trajs, "trajs")
+        x = trajs.detach().to(torch.float32).contiguous()
+        B, H, D = x.shape
+        idx = x.device.index if x.device.index is not None else torch.cuda.current_device()
+        key = (idx, int(n_interp))
+        cache = self.__dict__.setdefault("_eval_handles", {})
+        if key not in cache:
+            zeros = np.zeros(2 * self.robot.q_dim, dtype=np.float32)
+            cfg, keep = build_guide_config(self.robot, zeros, zeros + 1, [(f, 1.0) for f in self.get_collision_fields()], None,
+                                           0.0, False, 1.0, n_interp)
+            handle = C.c_void_p()
+            _lib.check(_lib.lib().mpdb_guide_create(C.byref(cfg), idx, C.byref(handle)))
+            cache[key] = (handle, keep)
+        stats = torch.empty((B, 4), device=x.device, dtype=torch.float32)
+        _lib.check(_lib.lib().mpdb_eval_trajectories(cache[key][0], _lib.fptr(x), _lib.fptr(stats), float(margin), B, H,
+                                                     _lib.stream_ptr(x.device)))
+        return {"n_waypoints_in_collision": stats[:, 0], "smoothness": stats[:, 1], "path_length": stats[:, 2],
+                "min_clearance": stats[:, 3], "in_collision": stats[:, 0] > 0, "n_interp": n_interp}
+
+    def get_trajs_collision_and_free(self, trajs, return_indices=False, **kw):
+        """(trajs_coll, [idxs_coll], trajs_free, [idxs_free], None) — None in place of an empty set, as upstream."""
+        ev = self.evaluate_trajectories(trajs, **kw)
+        coll = ev["in_collision"]
+        idx_coll, idx_free = torch.nonzero(coll).flatten(), torch.nonzero(~coll).flatten()
+        tc = trajs[idx_coll] if idx_coll.numel() else None
+        tf = trajs[idx_free] if idx_free.numel() else None
+        if return_indices:
+            return tc, idx_coll, tf, idx_free, None
+        return tc, tf, None
+
+    def compute_fraction_free_trajs(self, trajs, **kw):
+        return float((~self.evaluate_trajectories(trajs, **kw)["in_collision"]).float().mean())
+
+    def compute_collision_intensity_trajs(self, trajs, **kw):
+        ev = self.evaluate_trajectories(trajs, **kw)
+        return float(ev["n_waypoints_in_collision"].sum() / (trajs.shape[0] * ev["n_interp"]))
+
+    def compute_success_free_trajs(self, trajs, **kw):
+        return int(bool((~self.evaluate_trajectories(trajs, **kw)["in_collision"]).any()))
+
+    def best_free_trajectory(self, trajs, **kw):
+        """argmin of path length + smoothness over the collision-free plans (inference.py:316-320); (index, cost) or None."""
+        ev = self.evaluate_trajectories(trajs, **kw)
+        cost = ev["path_length"] + ev["smoothness"]
+        cost = torch.where(ev["in_collision"], torch.full_like(cost, float("inf")), cost)
+        i = int(torch.argmin(cost))
+        return None if bool(ev["in_collision"][i]) else (i, float(cost[i]))
+
+
+def compute_smoothness(trajs, robot):
+    """sum_h |v_{h+1} - v_h| per trajectory (torch_robotics metric, call site inference.py:312)."""
+    return torch.linalg.norm(torch.diff(robot.get_velocity(trajs), dim=-2), dim=-1).sum(-1)
+
+
+def compute_path_length(trajs, robot):
+    """sum_h |p_{h+1} - p_h| per trajectory (call site inference.py:315)."""
+    return torch.linalg.norm(torch.diff(robot.get_position(trajs), dim=-2), dim=-1).sum(-1)
+
+
+def compute_variance_waypoints(trajs, robot):
+    """variance of the waypoint positions across the trajectory set, summed over dimensions, averaged over the horizon
+    (call site inference.py:325)."""
+    return float(torch.var(robot.get_position(trajs), dim=0).sum(-1).mean())
+
 
 class TrajectoryDataset:
     """Synthetic dataset: normaliser limits = joint / velocity limits."""

@@ -504,3 +504,27 @@ def make_guide_spec(problem, weight_collision, weight_smoothness, texels_list=No
                      grid_fields=build_grid_fields(problem, texels_list), border_limits=problem.env.limits,
                      cutoff_margin=problem.cutoff_margin, dt=problem.dt, weight_collision=weight_collision,
                      weight_smoothness=weight_smoothness, n_interp=n_interp, **kw)
+
+
+# ------------------------------------------------------------------------------------------------
+# Post-sampling evaluation (reference inference.py:288-326; torch_robotics sources absent -> unpinned)
+# ------------------------------------------------------------------------------------------------
+def eval_trajectories(spec: GuideSpec, x_unnormalized, margin=0.0):
+    """Per trajectory: #interpolated waypoints with sdf - radius < margin in any field, smoothness, path length,
+    minimum clearance."""
+    q = spec.robot.q_dim
+    xi = interpolate_points(x_unnormalized, spec.n_interp)
+    cen = sphere_centers(spec.robot, xi[..., :q])                      # [B, NI, S, ws]
+    r = torch.as_tensor(spec.robot.sphere_radius, dtype=x_unnormalized.dtype)
+    clear = []
+    for g in spec.grid_fields:
+        clear.append(g(cen) - r)
+    if spec.border_limits is not None:
+        clear.append(border_sdf(cen, spec.border_limits) - r)
+    clear = torch.stack(clear, 0)                                      # [F, B, NI, S]
+    bad = (clear < margin).any(0).any(-1)                              # [B, NI]
+    pos, vel = x_unnormalized[..., :q], x_unnormalized[..., q:2 * q]
+    smooth = torch.linalg.norm(torch.diff(vel, dim=-2), dim=-1).sum(-1)
+    length = torch.linalg.norm(torch.diff(pos, dim=-2), dim=-1).sum(-1)
+    return {"n_waypoints_in_collision": bad.sum(-1).float(), "smoothness": smooth, "path_length": length,
+            "min_clearance": clear.amin(dim=(0, 2, 3))}
