@@ -81,6 +81,16 @@ def _dataset_limits(dataset):
     return nz.mins.detach().float().cpu().numpy(), nz.maxs.detach().float().cpu().numpy()
 
 
+class GuideManagerTrajectories(nn.Module):
+    """Position-only guide manager with a persistent velocity trajectory (reference guides.py:15-146). Not used by
+    scripts/inference/inference.py (which builds GuideManagerTrajectoriesWithVelocity, :229); SURVEY §8f.4 — next."""
+
+    def __init__(self, *args, **kwargs):
+        super().__init__()
+        raise NotImplementedError("GuideManagerTrajectories (position-only state) is not on the inference path; "
+                                  "use GuideManagerTrajectoriesWithVelocity")
+
+
 class GuideManagerTrajectoriesWithVelocity(nn.Module):
     _mpdb_fusable = True
 

@@ -158,3 +158,34 @@ def test_sharded_sampling_gloo_world2():
         outs = [p.communicate(timeout=120)[0] for p in procs]
     for p, o in zip(procs, outs):
         assert p.returncode == 0 and "ok" in o, o
+
+
+def test_checkpoint_and_dataset_ingestion_roundtrip():
+    """SURVEY §8f.3 on a synthetic directory with the reference's on-disk layout."""
+    import yaml
+    import mpd_public_b200 as M
+    from mpd_public_b200 import ingest
+    with tempfile.TemporaryDirectory() as d:
+        os.makedirs(os.path.join(d, "model", "checkpoints"))
+        os.makedirs(os.path.join(d, "data", "0"))
+        args = dict(variance_schedule="exponential", n_diffusion_steps=25, predict_epsilon=True, unet_input_dim=32,
+                    unet_dim_mults_option=0, diffusion_model_class="GaussianDiffusionModel", use_ema=True)
+        yaml.dump(args, open(os.path.join(d, "model", "args.yaml"), "w"))
+        unet = M.TemporalUnet(n_support_points=64, state_dim=4, dim_mults=M.UNET_DIM_MULTS[0])
+        ref = M.GaussianDiffusionModel(model=unet, n_diffusion_steps=25, predict_epsilon=True)
+        ref.load_state_dict({"model." + k: torch.as_tensor(v) for k, v in C.unet_weights("pm2d_opt0_h64").items()}, strict=False)
+        torch.save(ref.state_dict(), os.path.join(d, "model", "checkpoints", "ema_model_current_state_dict.pth"))
+        g = torch.Generator().manual_seed(0)
+        trajs = torch.rand((50, 64, 4), generator=g) * 2 - 1
+        torch.save(trajs, os.path.join(d, "data", "0", "trajs-free.pt"))
+
+        model, a = ingest.load_diffusion_model(os.path.join(d, "model"), state_dim=4, n_support_points=64, device="cpu")
+        assert a["n_diffusion_steps"] == 25 and not model.training
+        for (k1, v1), (k2, v2) in zip(model.state_dict().items(), ref.state_dict().items()):
+            assert k1 == k2 and torch.equal(v1, v2)
+        nz, h, dim = ingest.load_trajectory_limits(os.path.join(d, "data"), q_dim=2)
+        assert (h, dim) == (64, 4)
+        lim = nz.normalizers["traj"]
+        assert torch.equal(lim.mins, trajs.reshape(-1, 4).min(0).values) and torch.equal(lim.maxs, trajs.reshape(-1, 4).max(0).values)
+        x = nz.normalize(trajs, "traj")
+        assert float(x.min()) == -1.0 and float(x.max()) == 1.0
