@@ -372,7 +372,7 @@ def main():
         x0 = noise[0].contiguous()
         _lib.check(lib.mpdb_profile_forward(eng.handle, _lib.fptr(x0), 5, B, 20, ms, fl, md, _lib.stream_ptr(device)))
         ms, fl, md = np.array(ms[:]), np.array(fl[:]), np.array(md[:])
-        tcm = md == 5
+        tcm = (md == 5) | (md == 8)  # 5 = tcgen05 conv, 8 = cluster-fused residual block (two convs, one launch)
         dom = tcm if tcm.any() else (md == 0)
         fwd_ms = float(ms.sum())
         dom_ms, dom_flops = float(ms[dom].sum()), float(fl[dom].sum())
@@ -387,7 +387,8 @@ def main():
         flops_traj, sdf_bytes = algorithmic_work(H, D, opt, prob.robot.n_spheres, n_grid, prob.robot.ws_dim)
         if tcm.any():
             kname = ("mpdb::conv5_tc_kernel (tcgen05.mma kind::f16 split-bf16 x3, TMEM accumulators, cp.async.bulk staging; "
-                     f"Conv1d k5 + GroupNorm + Mish [+cond][+residual]), {int(dom.sum())} launches per UNet forward")
+                     f"Conv1d k5 + GroupNorm + Mish [+cond][+residual]; residual blocks with C_out <= 128 are one cluster-fused "
+                     f"launch, rtb_tc_kernel), {int(dom.sum())} launches per UNet forward")
             note = ("achieved = algorithmic (useful) 2*MAC FLOPs of its launches / their summed CUDA-event time; the tensor "
                     "pipe issues 3x that (hi*hi + lo*hi + hi*lo); share of one UNet forward "
                     f"{dom_ms / fwd_ms:.3f}")

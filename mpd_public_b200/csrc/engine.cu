@@ -92,6 +92,8 @@ struct mpdb_engine {
     unsigned short* work_tc = nullptr;    // activations in tensor-core layout (bf16 hi/lo planes)
     std::vector<long long> tc_off, tc_plane;  // per buffer: offset of the hi plane, elements per plane
     std::vector<long long> cm_off;            // per buffer: float offset of its (possibly shared) physical slot
+    int fuse_rtb = 1;          // cluster-fused residual blocks on the tensor-core path
+    int fuse_max_co = []() { const char* v = getenv("MPDB_FUSE_MAX_CO"); return v ? atoi(v) : 128; }();  // widest fused block (measured: 0 -> 11.85, 32 -> 11.67, 64 -> 11.55, 128 -> 11.47 ms per loop)
     int alias_buffers = 1;     // liveness-based reuse of activation storage (0: one buffer per layer, for debugging)
     int n_slots = 0;
     long long* dbg_buf = nullptr;  // optional per-op timeline stamps (option "timeline")
@@ -426,6 +428,46 @@ static ConvSrc make_src(mpdb_engine* e, int id0, int id1, const float* x_ext, in
     return s;
 }
 
+static void fill_tc_args(mpdb_engine* e, const ConvOp& op, const long long* t_dev, int t_uniform, int B, TcConvArgs& a) {
+    auto hi = [&](int id) -> unsigned short* { return e->tc_plane[id] ? e->work_tc + e->tc_off[id] : nullptr; };
+    auto lo = [&](int id) -> unsigned short* { return e->tc_plane[id] ? e->work_tc + e->tc_off[id] + e->tc_plane[id] : nullptr; };
+    memset(&a, 0, sizeof(a));
+    a.mode = op.mode == MODE_DOWN ? TCM_DOWN : op.mode == MODE_UP ? TCM_UP : TCM_CONV5;
+    a.in0_hi = hi(op.tc_in0); a.in0_lo = lo(op.tc_in0); a.c0 = e->bufs[op.tc_in0].C;
+    if (op.in1 >= 0) { a.in1_hi = hi(op.in1); a.in1_lo = lo(op.in1); a.c1 = e->bufs[op.in1].C; }
+    a.w = e->packed_tc + op.w_tc;
+    a.bias = e->packed + op.bias;
+    if (op.gn) { a.gamma = e->packed + op.gamma; a.beta = e->packed + op.beta; }
+    if (op.cond >= 0) { a.cond = e->packed + op.cond; a.t_dev = t_dev; a.t_uniform = t_uniform; }
+    if (op.res_w >= 0) {
+        a.r0_hi = hi(op.tc_res0); a.r0_lo = lo(op.tc_res0); a.rc0 = e->bufs[op.tc_res0].C;
+        if (op.res1 >= 0) { a.r1_hi = hi(op.res1); a.r1_lo = lo(op.res1); a.rc1 = e->bufs[op.res1].C; }
+        a.res_w = e->packed_tc + op.res_w_tc;
+        a.res_bias = e->packed + op.res_bias;
+    } else if (op.res0 >= 0) {
+        a.res_cm = buf_ptr(e, op.res0, e->work_batch);
+    }
+    a.out_cm = const_cast<float*>(buf_ptr(e, op.out, e->work_batch));
+    a.out_hi = hi(op.out); a.out_lo = lo(op.out);
+    a.CO = op.CO; a.L = op.L_in; a.B = B; a.gs = op.gs;
+}
+
+// Can ops[i], ops[i+1] (the two Conv1dBlocks of a ResidualTemporalBlock) run as one cluster-fused launch?
+static bool can_fuse_rtb(mpdb_engine* e, size_t i, bool tc) {
+    if (!tc || !e->fuse_rtb || !e->alias_buffers || e->timeline || i + 1 >= e->ops.size()) return false;
+    const ConvOp& a = e->ops[i];
+    const ConvOp& b = e->ops[i + 1];
+    return a.mode == MODE_CONV5 && b.mode == MODE_CONV5 && a.tc_ok && b.tc_ok && a.cond >= 0 && b.in0 == a.out && b.in1 < 0 &&
+           a.res0 == -2 && a.CO == b.CO && a.CO <= 128 && a.CO <= e->fuse_max_co && a.L_in == b.L_in;
+}
+
+static int launch_rtb(mpdb_engine* e, size_t i, const long long* t_dev, int t_uniform, int B, cudaStream_t st) {
+    TcRtbArgs r;
+    fill_tc_args(e, e->ops[i], t_dev, t_uniform, B, r.c0);
+    fill_tc_args(e, e->ops[i + 1], t_dev, t_uniform, B, r.c1);
+    return launch_rtb_tc(r, st);
+}
+
 static int launch_op(mpdb_engine* e, const ConvOp& op, const float* x, const long long* t_dev, int t_uniform, int B,
                      cudaStream_t st, bool tc) {
     auto hi = [&](int id) -> unsigned short* { return e->tc_plane[id] ? e->work_tc + e->tc_off[id] : nullptr; };
@@ -436,25 +478,7 @@ static int launch_op(mpdb_engine* e, const ConvOp& op, const float* x, const lon
     }
     if (tc && op.tc_ok) {
         TcConvArgs a;
-        memset(&a, 0, sizeof(a));
-        a.mode = op.mode == MODE_DOWN ? TCM_DOWN : op.mode == MODE_UP ? TCM_UP : TCM_CONV5;
-        a.in0_hi = hi(op.tc_in0); a.in0_lo = lo(op.tc_in0); a.c0 = e->bufs[op.tc_in0].C;
-        if (op.in1 >= 0) { a.in1_hi = hi(op.in1); a.in1_lo = lo(op.in1); a.c1 = e->bufs[op.in1].C; }
-        a.w = e->packed_tc + op.w_tc;
-        a.bias = e->packed + op.bias;
-        if (op.gn) { a.gamma = e->packed + op.gamma; a.beta = e->packed + op.beta; }
-        if (op.cond >= 0) { a.cond = e->packed + op.cond; a.t_dev = t_dev; a.t_uniform = t_uniform; }
-        if (op.res_w >= 0) {
-            a.r0_hi = hi(op.tc_res0); a.r0_lo = lo(op.tc_res0); a.rc0 = e->bufs[op.tc_res0].C;
-            if (op.res1 >= 0) { a.r1_hi = hi(op.res1); a.r1_lo = lo(op.res1); a.rc1 = e->bufs[op.res1].C; }
-            a.res_w = e->packed_tc + op.res_w_tc;
-            a.res_bias = e->packed + op.res_bias;
-        } else if (op.res0 >= 0) {
-            a.res_cm = buf_ptr(e, op.res0, e->work_batch);
-        }
-        a.out_cm = const_cast<float*>(buf_ptr(e, op.out, e->work_batch));
-        a.out_hi = hi(op.out); a.out_lo = lo(op.out);
-        a.CO = op.CO; a.L = op.L_in; a.B = B; a.gs = op.gs;
+        fill_tc_args(e, op, t_dev, t_uniform, B, a);
         if (e->timeline && e->dbg_buf) a.dbg = e->dbg_buf + (&op - e->ops.data()) * 16;
         return launch_conv5_tc(a, st);
     }
@@ -479,8 +503,14 @@ static int launch_op(mpdb_engine* e, const ConvOp& op, const float* x, const lon
 // Runs every layer up to (and including) final_conv.0; the 1x1 projection is fused into launch_final.
 static int run_unet_body(mpdb_engine* e, const float* x, const long long* t_dev, int t_uniform, int B, cudaStream_t st,
                          bool tc) {
-    for (const ConvOp& op : e->ops)
-        if (launch_op(e, op, x, t_dev, t_uniform, B, st, tc)) return 1;
+    for (size_t i = 0; i < e->ops.size(); ++i) {
+        if (can_fuse_rtb(e, i, tc)) {
+            if (launch_rtb(e, i, t_dev, t_uniform, B, st)) return 1;
+            ++i;  // the second conv of the block ran inside the fused launch
+            continue;
+        }
+        if (launch_op(e, e->ops[i], x, t_dev, t_uniform, B, st, tc)) return 1;
+    }
     return 0;
 }
 
@@ -597,6 +627,9 @@ extern "C" int mpdb_engine_set_option(mpdb_engine* e, const char* name, double v
     if (n == "tc_mode") {
         MPDB_REQUIRE(value == 0 || value == 1 || value == 2, "tc_mode must be 0 (off), 1 (auto) or 2 (force)");
         e->tc_mode = (int)value;
+    } else if (n == "fuse_rtb") {
+        e->fuse_rtb = value != 0;
+        if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; e->graph_key.clear(); }
     } else if (n == "alias_buffers") {
         if (e->alias_buffers != (value != 0)) {
             e->alias_buffers = value != 0;
@@ -840,7 +873,7 @@ extern "C" int mpdb_sample_loop(mpdb_engine* e, mpdb_guide* g, const mpdb_loop_p
                       std::to_string(p->n_steps_without_noise) + "|" + std::to_string(p->t_start_guide) + "|" +
                       std::to_string(p->n_guide_steps) + "|" + std::to_string(p->scale_grad_by_std) + "|" +
                       std::to_string(chain_out != nullptr) + "|" + std::to_string(p->n_hard_conds) + "|tc" +
-                      std::to_string(e->tc_mode) + "/" + std::to_string(e->tc_amp_limit);
+                      std::to_string(e->tc_mode) + "/" + std::to_string(e->tc_amp_limit) + "/" + std::to_string(e->fuse_rtb);
     for (int k = 0; k < p->n_hard_conds; ++k) key += "," + std::to_string(p->hard_cond_rows[k]);
     for (int k = 0; k < n_iters; ++k) {
         float v = p->noise_std ? p->noise_std[k] : 1.0f;
@@ -950,10 +983,14 @@ extern "C" int mpdb_profile_forward(mpdb_engine* e, const float* x, int32_t t, i
     const bool tc = e->tc_mode != 0;
     if (run_unet_body(e, x, nullptr, t, B, st, tc)) return 1;  // warm-up, fills every buffer
     int k = 0;
-    for (const ConvOp& op : e->ops) {
+    for (size_t i = 0; i < e->ops.size(); ++i) {
+        const ConvOp& op = e->ops[i];
+        const bool fused = can_fuse_rtb(e, i, tc);
         MPDB_CHECK_CUDA(cudaEventRecord(ev0, st));
-        for (int r = 0; r < reps; ++r)
-            if (launch_op(e, op, x, nullptr, t, B, st, tc)) return 1;
+        for (int r = 0; r < reps; ++r) {
+            if (fused) { if (launch_rtb(e, i, nullptr, t, B, st)) return 1; }
+            else if (launch_op(e, op, x, nullptr, t, B, st, tc)) return 1;
+        }
         MPDB_CHECK_CUDA(cudaEventRecord(ev1, st));
         MPDB_CHECK_CUDA(cudaEventSynchronize(ev1));
         float ms = 0.f;
@@ -962,6 +999,13 @@ extern "C" int mpdb_profile_forward(mpdb_engine* e, const float* x, int32_t t, i
         flops_out[k] = op_flops(e, op, B);
         mode_out[k] = op.mode == MODE_INPUT ? 6 : (tc && op.tc_ok) ? 5 : op.mode;  // 5 = tcgen05 conv, 6 = layout conversion
         ++k;
+        if (fused) {  // the pair ran as one launch: its time and FLOPs are reported on the first entry (mode 8)
+            flops_out[k - 1] += op_flops(e, e->ops[i + 1], B);
+            mode_out[k - 1] = 8;
+            ms_out[k] = 0.f; flops_out[k] = 0.0; mode_out[k] = 9;
+            ++k;
+            ++i;
+        }
     }
     {
         FinalArgs f;

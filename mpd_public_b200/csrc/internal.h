@@ -82,6 +82,14 @@ struct TcConvArgs {
     int mode;                     // TcMode; L is the INPUT length (DOWN writes L/2 positions, UP writes 2L)
 };
 int launch_conv5_tc(const TcConvArgs& a, cudaStream_t stream);
+
+// Whole ResidualTemporalBlock in one launch (cluster of CO/32 CTAs per row tile, h1 exchanged through DSMEM):
+//   h1 = Mish(GN(conv5(in) + b0)) + cond ;  out = Mish(GN(conv5(h1) + b1)) + residual
+struct TcRtbArgs {
+    TcConvArgs c0;  // first conv: inputs, w, bias, gamma, beta, cond (+t); outputs unused
+    TcConvArgs c1;  // second conv: w, bias, gamma, beta, residual (res_cm | r0/r1 + res_w + res_bias), outputs
+};
+int launch_rtb_tc(const TcRtbArgs& a, cudaStream_t stream);
 int launch_pack_tc_weights(const float* src, unsigned short* dst, int CI, int CI_src, int CO, int ntaps, unsigned perm,
                            cudaStream_t stream);
 int launch_blc_to_tc(const float* x, unsigned short* hi, unsigned short* lo, int B, int L, int D, int C, cudaStream_t stream);

@@ -470,6 +470,351 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv5_tc_kernel(TcConvArgs a) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Cluster-fused ResidualTemporalBlock (layers.py:323-355) for C_out <= 128: both k=5 convolutions in ONE launch.
+// The CO/32 CTAs that share a row tile form a thread-block cluster. Each runs conv0 for its 32 channels as in
+// conv5_tc_kernel, and its epilogue writes the split-bf16 h1 values straight into the conv1 A-operand buffer ("A2",
+// the full C_out x 132-row tile, both planes) of EVERY CTA of the cluster through distributed shared memory; a
+// cluster-scope mbarrier per CTA counts the writers. conv1 then reads its activations from local shared memory (no
+// global round trip, no second launch) while its weights stream through the same ring. Saves one kernel boundary
+// (launch edge + setup + first-copy wait) per block.
+// Threads: 16 epilogue warps (one of them hosts the MMA issuer lane) + 1 producer warp.
+// ---------------------------------------------------------------------------------------------------
+constexpr int RTB_THREADS = TC_THREADS + 32;
+constexpr int RTB_TMEM_COLS = 256;  // conv0 [0,64), conv1 [64,128), residual conv [128,192)
+
+__device__ __forceinline__ void epi_sync() { asm volatile("bar.sync 1, %0;" ::"n"(TC_THREADS) : "memory"); }
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t local_addr, uint32_t cta) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(cta));
+    return r;
+}
+__device__ __forceinline__ void st_cluster_v4(uint32_t addr, uint4 v) {
+    asm volatile("st.shared::cluster.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t remote_bar) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote_bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    const long long t0 = clock64();
+    while (true) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (done) break;
+        if (clock64() - t0 > 4000000000LL) __trap();
+    }
+}
+
+// GroupNorm (two-pass, two-level fixed-order reduction) + Mish on the 8 channels a thread owns; barriers = epi_sync.
+template <int GS>
+__device__ __forceinline__ void rtb_gn_mish(float (&v)[8], bool valid, int r, int s, int cg, int tid, int SPT, int Lp, int L,
+                                            float* part, const float4& g0, const float4& g1, const float4& e0, const float4& e1) {
+    constexpr int BPG = GS / 4;
+    const float inv_n = 1.f / (float)(GS * L);
+    const int blkA = ((cg * 8) / GS) * BPG, blkB = ((cg * 8 + 4) / GS) * BPG;
+    float* cs = part + 128 * 8;
+    const float* csr = cs + (s < SPT ? s : 0) * 8;
+    part[r * 8 + cg * 2 + 0] = valid ? (v[0] + v[1]) + (v[2] + v[3]) : 0.f;
+    part[r * 8 + cg * 2 + 1] = valid ? (v[4] + v[5]) + (v[6] + v[7]) : 0.f;
+    epi_sync();
+    gn_colsum(part, cs, tid, SPT, Lp, L);
+    epi_sync();
+    float tA = 0.f, tB = 0.f;
+#pragma unroll
+    for (int k = 0; k < BPG; ++k) { tA += csr[blkA + k]; tB += csr[blkB + k]; }
+    const float mA = tA * inv_n, mB = tB * inv_n;
+    float pa = 0.f, pb = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float da = v[j] - mA, db = v[4 + j] - mB;
+        pa = fmaf(da, da, pa);
+        pb = fmaf(db, db, pb);
+    }
+    epi_sync();
+    part[r * 8 + cg * 2 + 0] = valid ? pa : 0.f;
+    part[r * 8 + cg * 2 + 1] = valid ? pb : 0.f;
+    epi_sync();
+    gn_colsum(part, cs, tid, SPT, Lp, L);
+    epi_sync();
+    tA = 0.f; tB = 0.f;
+#pragma unroll
+    for (int k = 0; k < BPG; ++k) { tA += csr[blkA + k]; tB += csr[blkB + k]; }
+    const float rA = 1.0f / sqrtf(tA * inv_n + 1e-5f), rB = 1.0f / sqrtf(tB * inv_n + 1e-5f);
+    v[0] = mishf_fast((v[0] - mA) * (rA * g0.x) + e0.x); v[1] = mishf_fast((v[1] - mA) * (rA * g0.y) + e0.y);
+    v[2] = mishf_fast((v[2] - mA) * (rA * g0.z) + e0.z); v[3] = mishf_fast((v[3] - mA) * (rA * g0.w) + e0.w);
+    v[4] = mishf_fast((v[4] - mB) * (rB * g1.x) + e1.x); v[5] = mishf_fast((v[5] - mB) * (rB * g1.y) + e1.y);
+    v[6] = mishf_fast((v[6] - mB) * (rB * g1.z) + e1.z); v[7] = mishf_fast((v[7] - mB) * (rB * g1.w) + e1.w);
+    epi_sync();  // `part` is reused by the next GroupNorm of this kernel
+}
+
+template <int GS, int NSTAGE>
+__global__ void __launch_bounds__(RTB_THREADS, 1) rtb_tc_kernel(TcRtbArgs args) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const TcConvArgs& a0 = args.c0;
+    const TcConvArgs& a1 = args.c1;
+    const int CO = a0.CO;
+    const int a2_plane = (CO / 8) * TC_RT * 16;  // bytes per plane of the conv1 operand
+    unsigned char* a2 = smem_raw;                // [2 planes][CO/8][132][16 B]
+    unsigned char* stages = a2 + 2 * a2_plane;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(stages + NSTAGE * TC_STAGE_BYTES);  // full[S], empty[S], done1, done2, a2_full
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NSTAGE + 3);
+    float* part = reinterpret_cast<float*>(tmem_slot + 4);  // [128][8] + [12][8]
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tile = blockIdx.x, ntile = blockIdx.y;
+    const int CS = CO / TC_NT;  // cluster size = CTAs per row tile
+    const int n0 = ntile * TC_NT;
+    const int Lp = a0.L + 4;
+    const int SPT = TC_RT / Lp;
+    const int n1 = (a0.c0 + a0.c1) / TC_KCH;                 // conv0 chunks (activations + weights)
+    const int n2 = CO / TC_KCH;                              // conv1 chunks (weights only)
+    const int n3 = a1.res_w ? (a1.rc0 + a1.rc1) / TC_KCH : 0;  // residual 1x1 conv chunks (activations + weights)
+    const int n_steps = n1 + n2 + n3;
+    const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + NSTAGE);
+    const uint32_t done1 = smem_u32(bars + 2 * NSTAGE), done2 = done1 + 8, a2_full = done1 + 16;
+
+    // ---- setup ----
+    if (tid == 0) {
+        for (int s = 0; s < NSTAGE; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+        mbar_init(done1, 1);
+        mbar_init(done2, 1);
+        mbar_init(a2_full, (uint32_t)(CS * TC_THREADS));  // every epilogue thread of every CTA of the cluster arrives once
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(RTB_TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    for (int i = tid; i < 2 * a2_plane / 16; i += RTB_THREADS) reinterpret_cast<uint4*>(a2)[i] = make_uint4(0u, 0u, 0u, 0u);  // halos
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    // peers must have zeroed their A2 and initialised their barriers before anyone writes / arrives remotely
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();
+
+    if (warp == TC_THREADS / 32) {
+        // ===== producer warp (one lane): conv0 chunks, conv1 weight chunks, residual-conv chunks through one ring =====
+        if (lane == 0) {
+            for (int i = 0; i < n_steps; ++i) {
+                const int s = i % NSTAGE;
+                if (i >= NSTAGE) mbar_wait(empty0 + 8 * s, ((uint32_t)(i / NSTAGE) & 1u) ^ 1u);
+                const uint32_t st = smem_u32(stages + (size_t)s * TC_STAGE_BYTES);
+                const int phase = i < n1 ? 0 : i < n1 + n2 ? 1 : 2;
+                const int c = phase == 0 ? i : phase == 1 ? i - n1 : i - n1 - n2;
+                const int ntaps = phase == 2 ? 1 : 5;
+                const uint32_t bbytes = 2u * ntaps * TC_B_TAP_BYTES;
+                const TcConvArgs& A = phase == 0 ? a0 : a1;
+                const unsigned short* wsrc = phase == 0   ? a0.w + ((size_t)ntile * n1 + c) * (2 * 5 * TC_B_TAP_BYTES / 2)
+                                             : phase == 1 ? a1.w + ((size_t)ntile * n2 + c) * (2 * 5 * TC_B_TAP_BYTES / 2)
+                                                          : a1.res_w + ((size_t)ntile * n3 + c) * (2 * 1 * TC_B_TAP_BYTES / 2);
+                mbar_expect_tx(full0 + 8 * s, bbytes + (phase == 1 ? 0u : 2u * TC_A_PLANE_BYTES));
+                bulk_g2s(st + 2 * TC_A_PLANE_BYTES, wsrc, bbytes, full0 + 8 * s);
+                if (phase != 1) {
+                    const int C0 = phase == 0 ? A.c0 : A.rc0, C1 = phase == 0 ? A.c1 : A.rc1;
+                    const bool second = c * TC_KCH >= C0;
+                    const unsigned short* ahi = phase == 0 ? (second ? A.in1_hi : A.in0_hi) : (second ? A.r1_hi : A.r0_hi);
+                    const unsigned short* alo = phase == 0 ? (second ? A.in1_lo : A.in0_lo) : (second ? A.r1_lo : A.r0_lo);
+                    const int Csrc = second ? C1 : C0;
+                    const int kg0 = (c * TC_KCH - (second ? C0 : 0)) / 8;
+                    const size_t aoff = ((size_t)tile * (Csrc / 8) + kg0) * TC_RT * 8;
+                    bulk_g2s(st, ahi + aoff, TC_A_PLANE_BYTES, full0 + 8 * s);
+                    bulk_g2s(st + TC_A_PLANE_BYTES, alo + aoff, TC_A_PLANE_BYTES, full0 + 8 * s);
+                }
+            }
+        }
+        return;  // the producer warp takes no part in the epilogues (their barriers count TC_THREADS threads)
+    }
+
+    constexpr uint32_t idesc32 = tc_idesc(128, TC_NT), idesc64 = tc_idesc(128, 2 * TC_NT);
+    // MMAs of one ring step. a_hi/a_lo: shared addresses of the activation planes for this K-chunk.
+    auto issue_step = [&](int i, uint32_t a_hi, uint32_t a_lo, int ntaps, bool centre, uint32_t dcol, bool& first) {
+        const int s = i % NSTAGE;
+        mbar_wait(full0 + 8 * s, (uint32_t)(i / NSTAGE) & 1u);
+        tc_fence_after();
+        const uint32_t st = smem_u32(stages + (size_t)s * TC_STAGE_BYTES);
+        const uint64_t dA_hi = tc_desc(a_hi ? a_hi : st, TC_RT * 16, 128);
+        const uint64_t dA_lo = tc_desc(a_lo ? a_lo : st + TC_A_PLANE_BYTES, TC_RT * 16, 128);
+        const uint64_t dB = tc_desc(st + 2 * TC_A_PLANE_BYTES, 2 * TC_NT * 16, 128);
+        for (int tap = 0; tap < ntaps; ++tap) {
+            const int shift = centre ? 2 : tap;
+#pragma unroll
+            for (int kk = 0; kk < TC_KCH / 16; ++kk) {
+                const uint64_t aofs = (uint64_t)((kk * 2 * (TC_RT * 16) + shift * 16) >> 4);
+                const uint64_t bofs = (uint64_t)((tap * 2 * TC_B_TAP_BYTES + kk * 2 * (2 * TC_NT * 16)) >> 4);
+                tc_mma_bf16(dcol, dA_hi + aofs, dB + bofs, idesc64, first ? 0u : 1u);
+                first = false;
+                tc_mma_bf16(dcol, dA_lo + aofs, dB + bofs, idesc32, 1u);
+            }
+        }
+        tc_commit(empty0 + 8 * s);
+    };
+
+    // ===== phase 1: conv0 =====
+    if (tid == 32) {
+        bool first = true;
+        for (int i = 0; i < n1; ++i) issue_step(i, 0u, 0u, 5, false, tmem_base, first);
+        tc_commit(done1);
+    }
+    const int q = warp & 3, cg = warp >> 2;
+    const int r = q * 32 + lane;
+    const int s = r / Lp, l = r - s * Lp;
+    const int b = tile * SPT + s;
+    const bool valid = (s < SPT) && (l < a0.L) && (b < a0.B);
+    const int c8 = n0 + cg * 8;
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 pb0 = *reinterpret_cast<const float4*>(a0.bias + c8), pb1 = *reinterpret_cast<const float4*>(a0.bias + c8 + 4);
+    float4 pg0 = *reinterpret_cast<const float4*>(a0.gamma + c8), pg1 = *reinterpret_cast<const float4*>(a0.gamma + c8 + 4);
+    float4 pe0 = *reinterpret_cast<const float4*>(a0.beta + c8), pe1 = *reinterpret_cast<const float4*>(a0.beta + c8 + 4);
+    float4 pc0 = z4, pc1 = z4;
+    if (a0.cond != nullptr && valid) {
+        const int tt = a0.t_dev ? (int)a0.t_dev[b] : a0.t_uniform;
+        const float* cp = a0.cond + (size_t)tt * CO + c8;
+        pc0 = *reinterpret_cast<const float4*>(cp); pc1 = *reinterpret_cast<const float4*>(cp + 4);
+    }
+    mbar_wait(done1, 0);
+    __syncwarp();
+    tc_fence_after();
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + cg * 8;
+    float v[8];
+    {
+        float v2[8];
+        tc_ld8(taddr, v);
+        tc_ld8(taddr + TC_NT, v2);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] += v2[j];
+    }
+    v[0] += pb0.x; v[1] += pb0.y; v[2] += pb0.z; v[3] += pb0.w;
+    v[4] += pb1.x; v[5] += pb1.y; v[6] += pb1.z; v[7] += pb1.w;
+    rtb_gn_mish<GS>(v, valid, r, s, cg, tid, SPT, Lp, a0.L, part, pg0, pg1, pe0, pe1);
+    v[0] += pc0.x; v[1] += pc0.y; v[2] += pc0.z; v[3] += pc0.w;
+    v[4] += pc1.x; v[5] += pc1.y; v[6] += pc1.z; v[7] += pc1.w;
+    {
+        // h1 -> the conv1 operand buffer of every CTA of the cluster (k-group = c8 / 8, row = s*Lp + l + 2)
+        uint4 ph = make_uint4(0u, 0u, 0u, 0u), pl = ph;
+        if (valid) {
+            unsigned short h[8], lo8[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) split_bf16(v[e], h[e], lo8[e]);
+            ph.x = h[0] | ((uint32_t)h[1] << 16); ph.y = h[2] | ((uint32_t)h[3] << 16);
+            ph.z = h[4] | ((uint32_t)h[5] << 16); ph.w = h[6] | ((uint32_t)h[7] << 16);
+            pl.x = lo8[0] | ((uint32_t)lo8[1] << 16); pl.y = lo8[2] | ((uint32_t)lo8[3] << 16);
+            pl.z = lo8[4] | ((uint32_t)lo8[5] << 16); pl.w = lo8[6] | ((uint32_t)lo8[7] << 16);
+        }
+        const uint32_t off = (uint32_t)(((c8 / 8) * TC_RT + (s * Lp + l + 2)) * 16);
+        const uint32_t local_hi = smem_u32(a2) + off, local_lo = local_hi + a2_plane;
+        for (int cta = 0; cta < CS; ++cta) {
+            if (valid) {
+                st_cluster_v4(map_to_cta(local_hi, cta), ph);
+                st_cluster_v4(map_to_cta(local_lo, cta), pl);
+            }
+        }
+        // generic-proxy stores must be visible to the tensor core (async proxy) of the consumer CTAs
+        asm volatile("fence.proxy.async;" ::: "memory");
+        for (int cta = 0; cta < CS; ++cta) mbar_arrive_cluster(map_to_cta(a2_full, cta));
+    }
+
+    // ===== phase 2: conv1 (activations from A2) + residual 1x1 conv =====
+    // parameters of the second epilogue are fetched while the MMAs run
+    pb0 = *reinterpret_cast<const float4*>(a1.bias + c8); pb1 = *reinterpret_cast<const float4*>(a1.bias + c8 + 4);
+    pg0 = *reinterpret_cast<const float4*>(a1.gamma + c8); pg1 = *reinterpret_cast<const float4*>(a1.gamma + c8 + 4);
+    pe0 = *reinterpret_cast<const float4*>(a1.beta + c8); pe1 = *reinterpret_cast<const float4*>(a1.beta + c8 + 4);
+    float4 pr0 = z4, pr1 = z4;
+    float rid[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (a1.res_w != nullptr) {
+        pr0 = *reinterpret_cast<const float4*>(a1.res_bias + c8); pr1 = *reinterpret_cast<const float4*>(a1.res_bias + c8 + 4);
+    } else if (a1.res_cm != nullptr && valid) {
+        const float* rp = a1.res_cm + ((size_t)b * CO + c8) * Lp + 2 + l;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) rid[j] = rp[(size_t)j * Lp];
+    }
+    if (tid == 32) {
+        mbar_wait_cluster(a2_full, 0);  // all h1 rows of all channel tiles have landed in our A2
+        asm volatile("fence.proxy.async;" ::: "memory");
+        tc_fence_after();
+        bool first = true;
+        const uint32_t a2_hi = smem_u32(a2), a2_lo = a2_hi + a2_plane;
+        for (int c = 0; c < n2; ++c)
+            issue_step(n1 + c, a2_hi + c * (TC_KCH / 8) * TC_RT * 16, a2_lo + c * (TC_KCH / 8) * TC_RT * 16, 5, false,
+                       tmem_base + 2 * TC_NT, first);
+        bool first_r = true;
+        for (int c = 0; c < n3; ++c) issue_step(n1 + n2 + c, 0u, 0u, 1, true, tmem_base + 4 * TC_NT, first_r);
+        tc_commit(done2);
+    }
+    mbar_wait(done2, 0);
+    __syncwarp();
+    tc_fence_after();
+    {
+        float v2[8];
+        tc_ld8(taddr + 2 * TC_NT, v);
+        tc_ld8(taddr + 3 * TC_NT, v2);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] += v2[j];
+    }
+    v[0] += pb0.x; v[1] += pb0.y; v[2] += pb0.z; v[3] += pb0.w;
+    v[4] += pb1.x; v[5] += pb1.y; v[6] += pb1.z; v[7] += pb1.w;
+    rtb_gn_mish<GS>(v, valid, r, s, cg, tid, SPT, Lp, a0.L, part, pg0, pg1, pe0, pe1);
+    if (a1.res_w != nullptr) {
+        float rv[8], rv2[8];
+        tc_ld8(taddr + 4 * TC_NT, rv);
+        tc_ld8(taddr + 5 * TC_NT, rv2);
+        v[0] += rv[0] + rv2[0] + pr0.x; v[1] += rv[1] + rv2[1] + pr0.y; v[2] += rv[2] + rv2[2] + pr0.z; v[3] += rv[3] + rv2[3] + pr0.w;
+        v[4] += rv[4] + rv2[4] + pr1.x; v[5] += rv[5] + rv2[5] + pr1.y; v[6] += rv[6] + rv2[6] + pr1.z; v[7] += rv[7] + rv2[7] + pr1.w;
+    } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] += rid[j];
+    }
+    if (valid) tc_store_row(a1, v, b, l, c8, a0.L);
+
+    tc_fence_before();
+    epi_sync();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(RTB_TMEM_COLS) : "memory");
+    }
+}
+
+int launch_rtb_tc(const TcRtbArgs& a, cudaStream_t stream) {
+    const TcConvArgs& a0 = a.c0;
+    const TcConvArgs& a1 = a.c1;
+    MPDB_REQUIRE(a0.CO == a1.CO && a0.L == a1.L && a0.B == a1.B && a0.gs == a1.gs, "rtb: the two convs disagree");
+    MPDB_REQUIRE(a0.CO % TC_NT == 0 && a0.CO <= 128, "rtb: C_out must be 32, 64, 96 or 128");
+    MPDB_REQUIRE(a0.c0 % TC_KCH == 0 && a0.c1 % TC_KCH == 0 && a0.c0 > 0, "rtb: input widths must be multiples of 32");
+    MPDB_REQUIRE(!a1.res_w || (a1.rc0 % TC_KCH == 0 && a1.rc1 % TC_KCH == 0 && a1.rc0 > 0), "rtb: residual widths");
+    MPDB_REQUIRE(a0.L + 4 <= TC_RT && a0.L % 4 == 0, "rtb: L too large for one 128-row tile");
+    MPDB_REQUIRE(a0.gs == 4 || a0.gs == 8 || a0.gs == 16 || a0.gs == 32, "rtb: bad GroupNorm group size");
+    const int SPT = TC_RT / (a0.L + 4);
+    const int CS = a0.CO / TC_NT;
+    const int nstage = a0.CO <= 64 ? 5 : 4;
+    const size_t smem = (size_t)2 * (a0.CO / 8) * TC_RT * 16 + (size_t)nstage * TC_STAGE_BYTES + (2 * nstage + 3) * 8 + 16 +
+                        (128 * 8 + 12 * 8) * sizeof(float);
+    MPDB_REQUIRE(smem <= 227 * 1024, "rtb: shared memory budget exceeded");
+    dim3 grid((a0.B + SPT - 1) / SPT, CS);
+#define MPDB_RTB_LAUNCH(G, S)                                                                                          \
+    {                                                                                                                  \
+        static bool configured = false;                                                                                \
+        if (!configured) {                                                                                             \
+            MPDB_CHECK_CUDA(cudaFuncSetAttribute(rtb_tc_kernel<G, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
+            configured = true;                                                                                         \
+        }                                                                                                              \
+        MPDB_CHECK_CUDA(launch_kernel_cluster(rtb_tc_kernel<G, S>, grid, dim3(RTB_THREADS), smem, stream, (unsigned)CS, a)); \
+    }
+    if (nstage == 5) {
+        if (a0.gs == 4) MPDB_RTB_LAUNCH(4, 5) else if (a0.gs == 8) MPDB_RTB_LAUNCH(8, 5) else if (a0.gs == 16) MPDB_RTB_LAUNCH(16, 5) else MPDB_RTB_LAUNCH(32, 5)
+    } else {
+        if (a0.gs == 4) MPDB_RTB_LAUNCH(4, 4) else if (a0.gs == 8) MPDB_RTB_LAUNCH(8, 4) else if (a0.gs == 16) MPDB_RTB_LAUNCH(16, 4) else MPDB_RTB_LAUNCH(32, 4)
+    }
+#undef MPDB_RTB_LAUNCH
+    MPDB_LAUNCH_CHECK();
+    return 0;
+}
+
 int launch_conv5_tc(const TcConvArgs& a, cudaStream_t stream) {
     MPDB_REQUIRE(a.CO % TC_NT == 0, "tc conv: C_out must be a multiple of 32");
     MPDB_REQUIRE(a.c0 % TC_KCH == 0 && a.c1 % TC_KCH == 0 && a.c0 > 0, "tc conv: input widths must be multiples of 32");
