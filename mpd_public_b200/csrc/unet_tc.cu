@@ -157,24 +157,64 @@ __device__ __forceinline__ void tc_store_row(const TcConvArgs& a, const float (&
     }
 }
 
-// GroupNorm reduction helper. `part` holds one partial per (tile row, 4-channel block). Level 1: thread t < SPT*8 owns
-// one (sample, block) column and adds its L rows (four independent accumulators so the loads pipeline; fixed tree).
-// Level 2 (after a barrier): every thread adds the BPG block sums of its group(s). Deterministic, tiling-independent.
-__device__ __forceinline__ void gn_colsum(const float* __restrict__ part, float* __restrict__ cs, int tid, int SPT, int Lp,
-                                          int L) {
-    if (tid < SPT * 8) {
-        const int ss = tid >> 3, blk = tid & 7;
-        const float* p = part + (size_t)ss * Lp * 8 + blk;
-        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+// One-pass GroupNorm statistics + Mish on the 8 channels a thread owns (both tensor-core epilogues).
+//   level 0: every thread parks sum and sum-of-squares of its two 4-channel blocks: part[0][row][blk], part[1][row][blk]
+//   level 1: thread t < 2*SPT*8 owns one (moment, sample, block) column and adds its L rows in DOUBLE precision
+//            (fixed tree, four accumulators so the loads pipeline) -> cs[moment][sample][blk]
+//   level 2: every thread combines the BPG block sums of its group(s) in double: mean = S/n, var = Q/n - mean^2.
+// Accumulating the cross-row part in fp64 removes the cancellation of the one-pass formula; what remains is the fp32
+// rounding of the per-thread 4-term partials (~6e-8 * (1 + mean^2/var)), far below the split-bf16 MMA error. Two barriers
+// instead of five. Deterministic and independent of how samples are tiled. BAR1: named barrier of the 512 epilogue
+// threads (fused kernel, where a producer warp is not part of the epilogue) instead of __syncthreads.
+template <int GS, bool BAR1>
+__device__ __forceinline__ void gn_mish8(float (&v)[8], bool valid, int r, int s, int cg, int tid, int SPT, int Lp, int L,
+                                         float* part, const float4& g0, const float4& g1, const float4& e0, const float4& e1) {
+    constexpr int BPG = GS / 4;
+    const int blkA = ((cg * 8) / GS) * BPG, blkB = ((cg * 8 + 4) / GS) * BPG;
+    float* part2 = part + 128 * 8;
+    double* cs = reinterpret_cast<double*>(part + 2 * 128 * 8);  // [2][12][8]
+    {
+        const float sA = (v[0] + v[1]) + (v[2] + v[3]), sB = (v[4] + v[5]) + (v[6] + v[7]);
+        const float qA = fmaf(v[0], v[0], fmaf(v[1], v[1], fmaf(v[2], v[2], v[3] * v[3])));
+        const float qB = fmaf(v[4], v[4], fmaf(v[5], v[5], fmaf(v[6], v[6], v[7] * v[7])));
+        part[r * 8 + cg * 2 + 0] = valid ? sA : 0.f;
+        part[r * 8 + cg * 2 + 1] = valid ? sB : 0.f;
+        part2[r * 8 + cg * 2 + 0] = valid ? qA : 0.f;
+        part2[r * 8 + cg * 2 + 1] = valid ? qB : 0.f;
+    }
+    if (BAR1) asm volatile("bar.sync 1, %0;" ::"n"(TC_THREADS) : "memory"); else __syncthreads();
+    if (tid < 2 * SPT * 8) {
+        const int m = tid >= SPT * 8 ? 1 : 0;
+        const int t2 = tid - m * SPT * 8;
+        const int ss = t2 >> 3, blk = t2 & 7;
+        const float* p = (m ? part2 : part) + (size_t)ss * Lp * 8 + blk;
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
 #pragma unroll 2
         for (int qq = 0; qq < L; qq += 4) {
-            a0 += p[(qq + 0) * 8];
-            a1 += p[(qq + 1) * 8];
-            a2 += p[(qq + 2) * 8];
-            a3 += p[(qq + 3) * 8];
+            a0 += (double)p[(qq + 0) * 8];
+            a1 += (double)p[(qq + 1) * 8];
+            a2 += (double)p[(qq + 2) * 8];
+            a3 += (double)p[(qq + 3) * 8];
         }
-        cs[tid] = (a0 + a1) + (a2 + a3);
+        cs[(m * 12 + ss) * 8 + blk] = (a0 + a1) + (a2 + a3);
     }
+    if (BAR1) asm volatile("bar.sync 1, %0;" ::"n"(TC_THREADS) : "memory"); else __syncthreads();
+    const int sc = s < SPT ? s : 0;
+    double SA = 0.0, SB = 0.0, QA = 0.0, QB = 0.0;
+#pragma unroll
+    for (int k = 0; k < BPG; ++k) {
+        SA += cs[(0 * 12 + sc) * 8 + blkA + k]; SB += cs[(0 * 12 + sc) * 8 + blkB + k];
+        QA += cs[(1 * 12 + sc) * 8 + blkA + k]; QB += cs[(1 * 12 + sc) * 8 + blkB + k];
+    }
+    const double inv_n = 1.0 / (double)(GS * L);
+    const double mAd = SA * inv_n, mBd = SB * inv_n;
+    const double vA = fmax(QA * inv_n - mAd * mAd, 0.0), vB = fmax(QB * inv_n - mBd * mBd, 0.0);
+    const float mA = (float)mAd, mB = (float)mBd;
+    const float rA = (float)(1.0 / sqrt(vA + 1e-5)), rB = (float)(1.0 / sqrt(vB + 1e-5));
+    v[0] = mishf_fast((v[0] - mA) * (rA * g0.x) + e0.x); v[1] = mishf_fast((v[1] - mA) * (rA * g0.y) + e0.y);
+    v[2] = mishf_fast((v[2] - mA) * (rA * g0.z) + e0.z); v[3] = mishf_fast((v[3] - mA) * (rA * g0.w) + e0.w);
+    v[4] = mishf_fast((v[4] - mB) * (rB * g1.x) + e1.x); v[5] = mishf_fast((v[5] - mB) * (rB * g1.y) + e1.y);
+    v[6] = mishf_fast((v[6] - mB) * (rB * g1.z) + e1.z); v[7] = mishf_fast((v[7] - mB) * (rB * g1.w) + e1.w);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -191,7 +231,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv5_tc_kernel(TcConvArgs a) {
     unsigned char* stages = smem_raw;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + TC_STAGES * TC_STAGE_BYTES);  // full[S], empty[S], done
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_STAGES + 1);
-    float* part = reinterpret_cast<float*>(tmem_slot + 4);  // [128][8] GroupNorm partials, then [12][8] column sums
+    float* part = reinterpret_cast<float*>(tmem_slot + 4);  // GroupNorm scratch: [2][128][8] floats + [2][12][8] doubles
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int tile = blockIdx.x, ntile = blockIdx.y;
@@ -398,52 +438,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv5_tc_kernel(TcConvArgs a) {
     } else {
         v[0] += pb0.x; v[1] += pb0.y; v[2] += pb0.z; v[3] += pb0.w;
         v[4] += pb1.x; v[5] += pb1.y; v[6] += pb1.z; v[7] += pb1.w;
-        {
-            // GroupNorm, two passes (mean, centred second moment). Every thread parks the partial sums of its two
-            // 4-channel blocks in shared memory and then adds up, in fixed order, the partials of the (sample, group)
-            // it belongs to: the reads are warp-uniform broadcasts, independent of each other, and need no second
-            // barrier. Deterministic and independent of how samples are tiled.
-            constexpr int BPG = GS / 4;  // 4-channel blocks per group
-            const float inv_n = 1.f / (float)(GS * a.L);
-            const int blkA = ((cg * 8) / GS) * BPG, blkB = ((cg * 8 + 4) / GS) * BPG;  // first block of each group
-            float* cs = part + 128 * 8;                                              // [SPT][8] column sums
-            const float* csr = cs + (s < SPT ? s : 0) * 8;
-            part[r * 8 + cg * 2 + 0] = valid ? (v[0] + v[1]) + (v[2] + v[3]) : 0.f;
-            part[r * 8 + cg * 2 + 1] = valid ? (v[4] + v[5]) + (v[6] + v[7]) : 0.f;
-            __syncthreads();
-            gn_colsum(part, cs, tid, SPT, Lp, a.L);
-            __syncthreads();
-            if (dbg && tid == 64) a.dbg[8] = clock64();
-            float tA = 0.f, tB = 0.f;
-#pragma unroll
-            for (int k = 0; k < BPG; ++k) { tA += csr[blkA + k]; tB += csr[blkB + k]; }
-            const float mA = tA * inv_n, mB = tB * inv_n;
-            if (dbg && tid == 64) a.dbg[9] = clock64();
-            float pa = 0.f, pb = 0.f;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const float da = v[j] - mA, db = v[4 + j] - mB;
-                pa = fmaf(da, da, pa);
-                pb = fmaf(db, db, pb);
-            }
-            __syncthreads();  // pass-1 column sums consumed by everyone before `part` / `cs` are reused
-            part[r * 8 + cg * 2 + 0] = valid ? pa : 0.f;
-            part[r * 8 + cg * 2 + 1] = valid ? pb : 0.f;
-            __syncthreads();
-            gn_colsum(part, cs, tid, SPT, Lp, a.L);
-            __syncthreads();
-            if (dbg && tid == 64) a.dbg[10] = clock64();
-            tA = 0.f; tB = 0.f;
-#pragma unroll
-            for (int k = 0; k < BPG; ++k) { tA += csr[blkA + k]; tB += csr[blkB + k]; }
-            const float rA = 1.0f / sqrtf(tA * inv_n + 1e-5f), rB = 1.0f / sqrtf(tB * inv_n + 1e-5f);
-            if (dbg && tid == 64) a.dbg[11] = clock64();
-            const float4 g0 = pg0, g1 = pg1, e0 = pe0, e1 = pe1;
-            v[0] = mishf_fast((v[0] - mA) * (rA * g0.x) + e0.x); v[1] = mishf_fast((v[1] - mA) * (rA * g0.y) + e0.y);
-            v[2] = mishf_fast((v[2] - mA) * (rA * g0.z) + e0.z); v[3] = mishf_fast((v[3] - mA) * (rA * g0.w) + e0.w);
-            v[4] = mishf_fast((v[4] - mB) * (rB * g1.x) + e1.x); v[5] = mishf_fast((v[5] - mB) * (rB * g1.y) + e1.y);
-            v[6] = mishf_fast((v[6] - mB) * (rB * g1.z) + e1.z); v[7] = mishf_fast((v[7] - mB) * (rB * g1.w) + e1.w);
-        }
+        gn_mish8<GS, false>(v, valid, r, s, cg, tid, SPT, Lp, a.L, part, pg0, pg1, pe0, pe1);
         if (dbg && tid == 64) a.dbg[6] = clock64();  // GroupNorm + Mish done
         // time conditioning (zero when absent), then the residual: fused 1x1 conv accumulators or identity values
         v[0] += pc0.x; v[1] += pc0.y; v[2] += pc0.z; v[3] += pc0.w;
@@ -511,48 +506,6 @@ __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity)
     }
 }
 
-// GroupNorm (two-pass, two-level fixed-order reduction) + Mish on the 8 channels a thread owns; barriers = epi_sync.
-template <int GS>
-__device__ __forceinline__ void rtb_gn_mish(float (&v)[8], bool valid, int r, int s, int cg, int tid, int SPT, int Lp, int L,
-                                            float* part, const float4& g0, const float4& g1, const float4& e0, const float4& e1) {
-    constexpr int BPG = GS / 4;
-    const float inv_n = 1.f / (float)(GS * L);
-    const int blkA = ((cg * 8) / GS) * BPG, blkB = ((cg * 8 + 4) / GS) * BPG;
-    float* cs = part + 128 * 8;
-    const float* csr = cs + (s < SPT ? s : 0) * 8;
-    part[r * 8 + cg * 2 + 0] = valid ? (v[0] + v[1]) + (v[2] + v[3]) : 0.f;
-    part[r * 8 + cg * 2 + 1] = valid ? (v[4] + v[5]) + (v[6] + v[7]) : 0.f;
-    epi_sync();
-    gn_colsum(part, cs, tid, SPT, Lp, L);
-    epi_sync();
-    float tA = 0.f, tB = 0.f;
-#pragma unroll
-    for (int k = 0; k < BPG; ++k) { tA += csr[blkA + k]; tB += csr[blkB + k]; }
-    const float mA = tA * inv_n, mB = tB * inv_n;
-    float pa = 0.f, pb = 0.f;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const float da = v[j] - mA, db = v[4 + j] - mB;
-        pa = fmaf(da, da, pa);
-        pb = fmaf(db, db, pb);
-    }
-    epi_sync();
-    part[r * 8 + cg * 2 + 0] = valid ? pa : 0.f;
-    part[r * 8 + cg * 2 + 1] = valid ? pb : 0.f;
-    epi_sync();
-    gn_colsum(part, cs, tid, SPT, Lp, L);
-    epi_sync();
-    tA = 0.f; tB = 0.f;
-#pragma unroll
-    for (int k = 0; k < BPG; ++k) { tA += csr[blkA + k]; tB += csr[blkB + k]; }
-    const float rA = 1.0f / sqrtf(tA * inv_n + 1e-5f), rB = 1.0f / sqrtf(tB * inv_n + 1e-5f);
-    v[0] = mishf_fast((v[0] - mA) * (rA * g0.x) + e0.x); v[1] = mishf_fast((v[1] - mA) * (rA * g0.y) + e0.y);
-    v[2] = mishf_fast((v[2] - mA) * (rA * g0.z) + e0.z); v[3] = mishf_fast((v[3] - mA) * (rA * g0.w) + e0.w);
-    v[4] = mishf_fast((v[4] - mB) * (rB * g1.x) + e1.x); v[5] = mishf_fast((v[5] - mB) * (rB * g1.y) + e1.y);
-    v[6] = mishf_fast((v[6] - mB) * (rB * g1.z) + e1.z); v[7] = mishf_fast((v[7] - mB) * (rB * g1.w) + e1.w);
-    epi_sync();  // `part` is reused by the next GroupNorm of this kernel
-}
-
 template <int GS, int NSTAGE>
 __global__ void __launch_bounds__(RTB_THREADS, 1) rtb_tc_kernel(TcRtbArgs args) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -564,7 +517,7 @@ __global__ void __launch_bounds__(RTB_THREADS, 1) rtb_tc_kernel(TcRtbArgs args) 
     unsigned char* stages = a2 + 2 * a2_plane;
     uint64_t* bars = reinterpret_cast<uint64_t*>(stages + NSTAGE * TC_STAGE_BYTES);  // full[S], empty[S], done1, done2, a2_full
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NSTAGE + 3);
-    float* part = reinterpret_cast<float*>(tmem_slot + 4);  // [128][8] + [12][8]
+    float* part = reinterpret_cast<float*>(tmem_slot + 4);  // GroupNorm scratch: [2][128][8] floats + [2][12][8] doubles
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int tile = blockIdx.x, ntile = blockIdx.y;
@@ -693,7 +646,7 @@ __global__ void __launch_bounds__(RTB_THREADS, 1) rtb_tc_kernel(TcRtbArgs args) 
     }
     v[0] += pb0.x; v[1] += pb0.y; v[2] += pb0.z; v[3] += pb0.w;
     v[4] += pb1.x; v[5] += pb1.y; v[6] += pb1.z; v[7] += pb1.w;
-    rtb_gn_mish<GS>(v, valid, r, s, cg, tid, SPT, Lp, a0.L, part, pg0, pg1, pe0, pe1);
+    gn_mish8<GS, true>(v, valid, r, s, cg, tid, SPT, Lp, a0.L, part, pg0, pg1, pe0, pe1);
     v[0] += pc0.x; v[1] += pc0.y; v[2] += pc0.z; v[3] += pc0.w;
     v[4] += pc1.x; v[5] += pc1.y; v[6] += pc1.z; v[7] += pc1.w;
     {
@@ -760,7 +713,7 @@ __global__ void __launch_bounds__(RTB_THREADS, 1) rtb_tc_kernel(TcRtbArgs args) 
     }
     v[0] += pb0.x; v[1] += pb0.y; v[2] += pb0.z; v[3] += pb0.w;
     v[4] += pb1.x; v[5] += pb1.y; v[6] += pb1.z; v[7] += pb1.w;
-    rtb_gn_mish<GS>(v, valid, r, s, cg, tid, SPT, Lp, a0.L, part, pg0, pg1, pe0, pe1);
+    gn_mish8<GS, true>(v, valid, r, s, cg, tid, SPT, Lp, a0.L, part, pg0, pg1, pe0, pe1);
     if (a1.res_w != nullptr) {
         float rv[8], rv2[8];
         tc_ld8(taddr + 4 * TC_NT, rv);
@@ -793,7 +746,7 @@ int launch_rtb_tc(const TcRtbArgs& a, cudaStream_t stream) {
     const int CS = a0.CO / TC_NT;
     const int nstage = a0.CO <= 64 ? 5 : 4;
     const size_t smem = (size_t)2 * (a0.CO / 8) * TC_RT * 16 + (size_t)nstage * TC_STAGE_BYTES + (2 * nstage + 3) * 8 + 16 +
-                        (128 * 8 + 12 * 8) * sizeof(float);
+                        (2 * 128 * 8) * sizeof(float) + 2 * 12 * 8 * sizeof(double);
     MPDB_REQUIRE(smem <= 227 * 1024, "rtb: shared memory budget exceeded");
     dim3 grid((a0.B + SPT - 1) / SPT, CS);
 #define MPDB_RTB_LAUNCH(G, S)                                                                                          \
@@ -828,7 +781,7 @@ int launch_conv5_tc(const TcConvArgs& a, cudaStream_t stream) {
         MPDB_REQUIRE(!a.res_w && !a.res_cm && !a.cond && !a.raw_out, "tc down/up: no residual / conditioning");
     const int SPT = TC_RT / (a.L + 4);
     MPDB_REQUIRE(SPT <= 12, "tc conv: too many samples per tile");
-    const size_t smem = (size_t)TC_STAGES * TC_STAGE_BYTES + (2 * TC_STAGES + 1) * 8 + 16 + (2 * 128 * 8) * sizeof(float);
+    const size_t smem = (size_t)TC_STAGES * TC_STAGE_BYTES + (2 * TC_STAGES + 1) * 8 + 16 + (2 * 128 * 8) * sizeof(float) + 2 * 12 * 8 * sizeof(double);
     dim3 grid((a.B + SPT - 1) / SPT, a.CO / TC_NT);
 #define MPDB_TC_LAUNCH(M, G)                                                                                       \
     {                                                                                                              \
