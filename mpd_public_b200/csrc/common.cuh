@@ -101,16 +101,18 @@ __device__ __forceinline__ float warp_sum(float v) {
 // tanh(log(1 + e)) = ((1+e)^2 - 1) / ((1+e)^2 + 1) = n / (n + 2), n = e * (e + 2)  — one expf, one division,
 // no cancellation for x << 0; for x > 20 tanh(softplus(x)) == 1 in fp32.
 __device__ __forceinline__ float mishf(float x) {
+    // branch-free: for x >= 20, e = exp(20), n = e(e+2) ~ 2.4e17 and n / (n + 2) == 1.0f exactly, so the clamp alone
+    // reproduces "tanh(softplus(x)) == 1" and independent evaluations can interleave
     const float e = expf(fminf(x, 20.f));
     const float n = e * (e + 2.f);
-    return x > 20.f ? x : x * __fdiv_rn(n, n + 2.f);
+    return x * __fdiv_rn(n, n + 2.f);
 }
 // fast variant for the tensor-core epilogue (ex2.approx + rcp.approx, ~1e-6 relative; the split-bf16 MMA itself is
 // ~1e-5): the epilogue is instruction-issue bound, so the ~40-instruction precise version would dominate it.
 __device__ __forceinline__ float mishf_fast(float x) {
     const float e = __expf(fminf(x, 20.f));
     const float n = e * (e + 2.f);
-    return x > 20.f ? x : x * __fdividef(n, n + 2.f);
+    return x * __fdividef(n, n + 2.f);  // n + 2 <= 2.4e17 < 2^126: inside __fdividef's valid range
 }
 // reference-composition variant (used once per load for the time tables, where cost does not matter)
 __device__ __forceinline__ float mishf_ref(float x) { return x * tanhf(log1pf(expf(x))); }

@@ -161,16 +161,17 @@ __device__ __forceinline__ void tc_store_row(const TcConvArgs& a, const float (&
 //   level 0: every thread parks sum and sum-of-squares of its two 4-channel blocks: part[0][row][blk], part[1][row][blk]
 //   level 1: thread t < 2*SPT*8 owns one (moment, sample, block) column and adds its L rows in DOUBLE precision
 //            (fixed tree, four accumulators so the loads pipeline) -> cs[moment][sample][blk]
-//   level 2: every thread combines the BPG block sums of its group(s) in double: mean = S/n, var = Q/n - mean^2.
+//   level 2: one thread per (sample, group) combines the BPG block sums in double: mean = S/n, var = Q/n - mean^2,
+//            and publishes {mean, rstd}; everyone reads its two groups' values after a third barrier.
 // Accumulating the cross-row part in fp64 removes the cancellation of the one-pass formula; what remains is the fp32
-// rounding of the per-thread 4-term partials (~6e-8 * (1 + mean^2/var)), far below the split-bf16 MMA error. Two barriers
-// instead of five. Deterministic and independent of how samples are tiled. BAR1: named barrier of the 512 epilogue
+// rounding of the per-thread 4-term partials (~6e-8 * (1 + mean^2/var)), far below the split-bf16 MMA error. Three short
+// barriers, no redundant fp64 work. Deterministic and independent of how samples are tiled. BAR1: named barrier of the 512 epilogue
 // threads (fused kernel, where a producer warp is not part of the epilogue) instead of __syncthreads.
 template <int GS, bool BAR1>
 __device__ __forceinline__ void gn_mish8(float (&v)[8], bool valid, int r, int s, int cg, int tid, int SPT, int Lp, int L,
-                                         float* part, const float4& g0, const float4& g1, const float4& e0, const float4& e1) {
+                                         float* part, const float4& g0, const float4& g1, const float4& e0, const float4& e1,
+                                         long long* dbg = nullptr) {
     constexpr int BPG = GS / 4;
-    const int blkA = ((cg * 8) / GS) * BPG, blkB = ((cg * 8 + 4) / GS) * BPG;
     float* part2 = part + 128 * 8;
     double* cs = reinterpret_cast<double*>(part + 2 * 128 * 8);  // [2][12][8]
     {
@@ -183,6 +184,7 @@ __device__ __forceinline__ void gn_mish8(float (&v)[8], bool valid, int r, int s
         part2[r * 8 + cg * 2 + 1] = valid ? qB : 0.f;
     }
     if (BAR1) asm volatile("bar.sync 1, %0;" ::"n"(TC_THREADS) : "memory"); else __syncthreads();
+    if (dbg) dbg[8] = clock64();
     if (tid < 2 * SPT * 8) {
         const int m = tid >= SPT * 8 ? 1 : 0;
         const int t2 = tid - m * SPT * 8;
@@ -199,18 +201,26 @@ __device__ __forceinline__ void gn_mish8(float (&v)[8], bool valid, int r, int s
         cs[(m * 12 + ss) * 8 + blk] = (a0 + a1) + (a2 + a3);
     }
     if (BAR1) asm volatile("bar.sync 1, %0;" ::"n"(TC_THREADS) : "memory"); else __syncthreads();
-    const int sc = s < SPT ? s : 0;
-    double SA = 0.0, SB = 0.0, QA = 0.0, QB = 0.0;
+    if (dbg) dbg[9] = clock64();
+    // level 2: one thread per (sample, group) finishes the statistics in double and publishes {mean, rstd} as floats
+    constexpr int NG = TC_NT / GS;
+    float* stat = reinterpret_cast<float*>(cs + 2 * 12 * 8);  // [12][8][2]
+    if (tid < SPT * NG) {
+        const int ss = tid / NG, g = tid - ss * NG;
+        double S = 0.0, Q = 0.0;
 #pragma unroll
-    for (int k = 0; k < BPG; ++k) {
-        SA += cs[(0 * 12 + sc) * 8 + blkA + k]; SB += cs[(0 * 12 + sc) * 8 + blkB + k];
-        QA += cs[(1 * 12 + sc) * 8 + blkA + k]; QB += cs[(1 * 12 + sc) * 8 + blkB + k];
+        for (int k = 0; k < BPG; ++k) { S += cs[(0 * 12 + ss) * 8 + g * BPG + k]; Q += cs[(1 * 12 + ss) * 8 + g * BPG + k]; }
+        const double inv_n = 1.0 / (double)(GS * L);
+        const double m = S * inv_n;
+        const double var = fmax(Q * inv_n - m * m, 0.0);
+        stat[(ss * 8 + g) * 2 + 0] = (float)m;
+        stat[(ss * 8 + g) * 2 + 1] = 1.0f / sqrtf((float)var + 1e-5f);  // the cancellation-prone part is done; fp32 from here
     }
-    const double inv_n = 1.0 / (double)(GS * L);
-    const double mAd = SA * inv_n, mBd = SB * inv_n;
-    const double vA = fmax(QA * inv_n - mAd * mAd, 0.0), vB = fmax(QB * inv_n - mBd * mBd, 0.0);
-    const float mA = (float)mAd, mB = (float)mBd;
-    const float rA = (float)(1.0 / sqrt(vA + 1e-5)), rB = (float)(1.0 / sqrt(vB + 1e-5));
+    if (BAR1) asm volatile("bar.sync 1, %0;" ::"n"(TC_THREADS) : "memory"); else __syncthreads();
+    const int sc = s < SPT ? s : 0;
+    const int gA = (cg * 8) / GS, gB = (cg * 8 + 4) / GS;
+    const float mA = stat[(sc * 8 + gA) * 2], rA = stat[(sc * 8 + gA) * 2 + 1];
+    const float mB = stat[(sc * 8 + gB) * 2], rB = stat[(sc * 8 + gB) * 2 + 1];
     v[0] = mishf_fast((v[0] - mA) * (rA * g0.x) + e0.x); v[1] = mishf_fast((v[1] - mA) * (rA * g0.y) + e0.y);
     v[2] = mishf_fast((v[2] - mA) * (rA * g0.z) + e0.z); v[3] = mishf_fast((v[3] - mA) * (rA * g0.w) + e0.w);
     v[4] = mishf_fast((v[4] - mB) * (rB * g1.x) + e1.x); v[5] = mishf_fast((v[5] - mB) * (rB * g1.y) + e1.y);
@@ -438,7 +448,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv5_tc_kernel(TcConvArgs a) {
     } else {
         v[0] += pb0.x; v[1] += pb0.y; v[2] += pb0.z; v[3] += pb0.w;
         v[4] += pb1.x; v[5] += pb1.y; v[6] += pb1.z; v[7] += pb1.w;
-        gn_mish8<GS, false>(v, valid, r, s, cg, tid, SPT, Lp, a.L, part, pg0, pg1, pe0, pe1);
+        gn_mish8<GS, false>(v, valid, r, s, cg, tid, SPT, Lp, a.L, part, pg0, pg1, pe0, pe1, (dbg && tid == 64) ? a.dbg : nullptr);
         if (dbg && tid == 64) a.dbg[6] = clock64();  // GroupNorm + Mish done
         // time conditioning (zero when absent), then the residual: fused 1x1 conv accumulators or identity values
         v[0] += pc0.x; v[1] += pc0.y; v[2] += pc0.z; v[3] += pc0.w;
@@ -746,7 +756,7 @@ int launch_rtb_tc(const TcRtbArgs& a, cudaStream_t stream) {
     const int CS = a0.CO / TC_NT;
     const int nstage = a0.CO <= 64 ? 5 : 4;
     const size_t smem = (size_t)2 * (a0.CO / 8) * TC_RT * 16 + (size_t)nstage * TC_STAGE_BYTES + (2 * nstage + 3) * 8 + 16 +
-                        (2 * 128 * 8) * sizeof(float) + 2 * 12 * 8 * sizeof(double);
+                        (2 * 128 * 8 + 12 * 8 * 2) * sizeof(float) + 2 * 12 * 8 * sizeof(double);
     MPDB_REQUIRE(smem <= 227 * 1024, "rtb: shared memory budget exceeded");
     dim3 grid((a0.B + SPT - 1) / SPT, CS);
 #define MPDB_RTB_LAUNCH(G, S)                                                                                          \
@@ -781,7 +791,7 @@ int launch_conv5_tc(const TcConvArgs& a, cudaStream_t stream) {
         MPDB_REQUIRE(!a.res_w && !a.res_cm && !a.cond && !a.raw_out, "tc down/up: no residual / conditioning");
     const int SPT = TC_RT / (a.L + 4);
     MPDB_REQUIRE(SPT <= 12, "tc conv: too many samples per tile");
-    const size_t smem = (size_t)TC_STAGES * TC_STAGE_BYTES + (2 * TC_STAGES + 1) * 8 + 16 + (2 * 128 * 8) * sizeof(float) + 2 * 12 * 8 * sizeof(double);
+    const size_t smem = (size_t)TC_STAGES * TC_STAGE_BYTES + (2 * TC_STAGES + 1) * 8 + 16 + (2 * 128 * 8 + 12 * 8 * 2) * sizeof(float) + 2 * 12 * 8 * sizeof(double);
     dim3 grid((a.B + SPT - 1) / SPT, a.CO / TC_NT);
 #define MPDB_TC_LAUNCH(M, G)                                                                                       \
     {                                                                                                              \

@@ -26,10 +26,10 @@ n = lib.mpdb_engine_num_ops(eng.handle) - 1
 buf = (C.c_int64 * (16 * n))()
 _lib.check(lib.mpdb_engine_read_timeline(eng.handle, buf, n))
 a = np.array(buf[:]).reshape(n, 16)
-names = ["setup", "loads_issued", "mma_issued", "acc_ready", "tmem_ld", "gn_mish", "end", "gn_s1", "gn_mean", "gn_s2", "gn_rstd"]
+names = ["setup", "loads_issued", "mma_issued", "acc_ready", "tmem_ld", "gn_mish", "end", "gn_bar1", "gn_bar2"]
 print("op   " + " ".join(f"{k:>12s}" for k in names) + "   (cycles since kernel start of CTA 0,0; 1965 cycles = 1 us)")
 for i in range(n):
     if a[i, 0] == 0:
         continue
-    d = a[i, 1:12] - a[i, 0]
+    d = a[i, 1:10] - a[i, 0]
     print(f"{i:3d}  " + " ".join(f"{int(v):12d}" for v in d))
