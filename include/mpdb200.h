@@ -114,6 +114,13 @@ int mpdb_engine_finalize(mpdb_engine* e, void* stream);
 
 /* TemporalUnet.forward(x, time, context=None) — temporal_unet.py:118-171. x,eps: [B,H,D]; t: int64 [B] */
 int mpdb_unet_forward(mpdb_engine* e, const float* x, const int64_t* t, float* eps, int32_t B, void* stream);
+/* the same forward at one uniform timestep, exactly as mpdb_sample_loop runs it (tensor-core policy of the loop; the
+ * whole-forward cluster kernel of unet_mega.cu when option "mega" = 1 (default) and the configuration supports it).
+ * make_timesteps fills t with one value (diffusion_model_base.py:25-27), so this is the loop's only forward. */
+int mpdb_unet_forward_uniform(mpdb_engine* e, const float* x, int32_t t, float* eps, int32_t B, void* stream);
+/* 1 if batch B runs the UNet as one cluster-kernel launch; G = trajectories per cluster; why = reason when not */
+int mpdb_engine_mega_info(mpdb_engine* e, int32_t B, int32_t* G, int32_t* n_layers, int32_t* a_bytes, int32_t* smem_bytes,
+                          char* why, int why_cap);
 /* GaussianDiffusionModel.p_mean_variance -> model_mean — diffusion_model_base.py:143-155 */
 int mpdb_p_mean(mpdb_engine* e, const float* x, const int64_t* t, float* mean, int32_t B, void* stream);
 /* x + model_std * noise * noise_std with noise[t == 0] = 0 — sample_functions.py:50-62 (in place on x) */
@@ -130,6 +137,9 @@ int64_t mpdb_launch_count(void);
  * events on `stream`; arrays hold mpdb_engine_num_ops(e) entries (mode 0..3 = conv5/conv1/down/up, 4 = fused
  * final projection + posterior mean). */
 int mpdb_engine_num_ops(mpdb_engine* e);
+/* device time (ms) of the UNet body per forward as the loop runs it, its algorithmic FLOPs and kernels per forward */
+int mpdb_profile_unet_body(mpdb_engine* e, const float* x, int32_t t, int32_t B, int32_t reps, float* ms_out,
+                           double* flops_out, int32_t* launches_out, void* stream);
 int mpdb_profile_forward(mpdb_engine* e, const float* x, int32_t t, int32_t B, int32_t reps, float* ms_out,
                          double* flops_out, int32_t* mode_out, void* stream);
 /* average device time of one guide evaluation on x (in place), CUDA events on `stream` */
@@ -144,6 +154,12 @@ int mpdb_debug_tc_conv5(const float* x_cm, const float* w, float* raw, int32_t B
 /* debugging: with option "timeline" = 1, clock64 stamps (16 per layer) of CTA (0,0) of every tensor-core conv of the
  * last forward; host_out holds 16 * max_ops int64 */
 int mpdb_engine_read_timeline(mpdb_engine* e, int64_t* host_out, int32_t max_ops);
+
+/* debugging: with option "mega_timeline" = 1, clock64 stamps of the whole-forward cluster kernel: per layer and CTA rank
+ * of cluster 0 {inputs landed, accumulators complete, epilogue arithmetic done, outputs delivered}; desc_out gets
+ * {type, L, C_out, active CTAs} per layer. Returns the number of layers written (negative on error is not used: 1/2 =
+ * error codes are returned only when nothing was written). */
+int mpdb_engine_read_mega_timeline(mpdb_engine* e, int64_t* host_out, int32_t* desc_out, int32_t max_layers);
 
 /* debugging / parity: intermediate activations of the last mpdb_unet_forward */
 int mpdb_engine_num_buffers(mpdb_engine* e);

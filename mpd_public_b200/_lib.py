@@ -57,6 +57,12 @@ SYMBOLS = {
     "mpdb_engine_set_option": (C.c_int, [_P, C.c_char_p, C.c_double]),
     "mpdb_engine_finalize": (C.c_int, [_P, _P]),
     "mpdb_unet_forward": (C.c_int, [_P, _P, _P, _P, C.c_int32, _P]),
+    "mpdb_unet_forward_uniform": (C.c_int, [_P, _P, C.c_int32, _P, C.c_int32, _P]),
+    "mpdb_engine_mega_info": (C.c_int, [_P, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32),
+                                        C.POINTER(C.c_int32), C.c_char_p, C.c_int]),
+    "mpdb_engine_read_mega_timeline": (C.c_int, [_P, C.POINTER(C.c_int64), C.POINTER(C.c_int32), C.c_int32]),
+    "mpdb_profile_unet_body": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_float), C.POINTER(C.c_double),
+                                         C.POINTER(C.c_int32), _P]),
     "mpdb_p_mean": (C.c_int, [_P, _P, _P, _P, C.c_int32, _P]),
     "mpdb_add_noise": (C.c_int, [_P, _P, _P, _P, C.c_float, C.c_int32, _P]),
     "mpdb_sample_loop": (C.c_int, [_P, _P, C.POINTER(LoopParams), _P, _P, _P, C.c_int64, C.c_int64, C.c_int32, _P]),

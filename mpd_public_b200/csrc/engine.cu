@@ -94,6 +94,13 @@ struct mpdb_engine {
     std::vector<long long> cm_off;            // per buffer: float offset of its (possibly shared) physical slot
     int fuse_rtb = 1;          // cluster-fused residual blocks on the tensor-core path
     int fuse_max_co = []() { const char* v = getenv("MPDB_FUSE_MAX_CO"); return v ? atoi(v) : 128; }();  // widest fused block (measured: 0 -> 11.85, 32 -> 11.67, 64 -> 11.55, 128 -> 11.47 ms per loop)
+    // whole-forward persistent cluster kernel (unet_mega.cu)
+    int use_mega = []() { const char* v = getenv("MPDB_MEGA"); return v ? atoi(v) : 1; }();
+    bool mega_ok = false;
+    std::string mega_why;      // why the configuration cannot run as one launch (falls back to per-layer kernels)
+    MegaProgram mega;
+    long long* mega_dbg = nullptr;        // optional per-layer timeline (option "mega_timeline")
+    unsigned short* mega_skip = nullptr;  // skip connections in the cluster-tiled layout
     int alias_buffers = 1;     // liveness-based reuse of activation storage (0: one buffer per layer, for debugging)
     int n_slots = 0;
     long long* dbg_buf = nullptr;  // optional per-op timeline stamps (option "timeline")
@@ -348,6 +355,8 @@ static int build_plan(mpdb_engine* e, PlanBuilder& pb) {
 // the same shape whose lifetimes do not overlap (greedy, in write order). Same shape => same halo / spare-row
 // positions, which are never written, so the zero-padding invariant survives the reuse. Keeping the working set of a
 // forward pass at a few tens of MB keeps weights and activations resident in the 126 MB L2.
+static void build_mega(mpdb_engine* e, int B);
+
 static int ensure_workspace(mpdb_engine* e, int B) {
     if (B <= e->work_batch) return 0;
     if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; e->graph_key.clear(); }
@@ -410,6 +419,7 @@ static int ensure_workspace(mpdb_engine* e, int B) {
         MPDB_CHECK_CUDA(cudaMalloc(&e->xbuf[k], sizeof(float) * (size_t)B * e->cfg.horizon * e->cfg.state_dim));
     }
     e->work_batch = B;
+    build_mega(e, B);
     return 0;
 }
 
@@ -450,6 +460,131 @@ static void fill_tc_args(mpdb_engine* e, const ConvOp& op, const long long* t_de
     a.out_cm = const_cast<float*>(buf_ptr(e, op.out, e->work_batch));
     a.out_hi = hi(op.out); a.out_lo = lo(op.out);
     a.CO = op.CO; a.L = op.L_in; a.B = B; a.gs = op.gs;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Layer program of the whole-forward cluster kernel (unet_mega.cu): one MegaLayer per op of the plan.
+// ---------------------------------------------------------------------------------------------------
+static bool mega_geom(int L, int G, MegaLayer& Ld) {
+    Ld.L = L;
+    Ld.Lp = L + 4;
+    if (Ld.Lp > TC_RT || L % 4 != 0) return false;
+    Ld.SPT = TC_RT / Ld.Lp < G ? TC_RT / Ld.Lp : G;
+    Ld.MT = (G + Ld.SPT - 1) / Ld.SPT;
+    Ld.RT = Ld.SPT * Ld.Lp;
+    return Ld.SPT <= 12;
+}
+
+static bool try_build_mega(mpdb_engine* e, int B, int G, std::string& why) {
+    MegaProgram& P = e->mega;
+    memset(&P, 0, sizeof(P));
+    P.G = G; P.B = B; P.H = e->cfg.horizon; P.D = e->cfg.state_dim;
+    const int n_clusters = (B + G - 1) / G;
+    if (e->ops.size() > (size_t)MEGA_MAX_LAYERS) { why = "too many layers"; return false; }
+    // buffers read as the second (concatenated) source are skip connections: they go through global memory
+    struct Skip { long long off; int C, L, ready; };
+    std::map<int, Skip> skips;
+    long long skip_elems = 0;
+    for (const ConvOp& op : e->ops)
+        if (op.in1 >= 0 && !skips.count(op.in1)) {
+            const ActBuf& bf = e->bufs[op.in1];
+            MegaLayer g; memset(&g, 0, sizeof(g));
+            if (bf.C % TC_KCH != 0 || !mega_geom(bf.L, G, g)) { why = "skip tensor shape"; return false; }
+            Skip sk; sk.off = skip_elems; sk.C = bf.C; sk.L = bf.L; sk.ready = -1;
+            skip_elems += 2LL * n_clusters * g.MT * (bf.C / 8) * g.RT * 8;
+            skips[op.in1] = sk;
+        }
+    if (e->mega_skip) { cudaFree(e->mega_skip); cudaFree(e->mega_dbg); e->mega_skip = nullptr; }
+    if (cudaMalloc(&e->mega_skip, sizeof(unsigned short) * (size_t)(skip_elems > 0 ? skip_elems : 8)) != cudaSuccess ||
+        cudaMemset(e->mega_skip, 0, sizeof(unsigned short) * (size_t)(skip_elems > 0 ? skip_elems : 8)) != cudaSuccess) {
+        why = "skip allocation failed"; cudaGetLastError(); return false;
+    }
+    int cur = -3, n = 0, a_bytes = 0;
+    std::vector<int> out_of_layer;
+    for (size_t i = 0; i < e->ops.size(); ++i, ++n) {
+        const ConvOp& op = e->ops[i];
+        MegaLayer& Ld = P.layers[n];
+        if (!mega_geom(op.L_in, G, Ld)) { why = "row tiling"; return false; }
+        if (op.mode == MODE_INPUT) {
+            if (n != 0) { why = "input layer must be first"; return false; }
+            Ld.type = MG_INPUT; Ld.NC = 1; Ld.CO = e->bufs[op.out].C;
+            if (Ld.CO != TC_KCH || e->cfg.state_dim > TC_KCH) { why = "state_dim > 32"; return false; }
+            if (Ld.MT > MEGA_CLUSTER) { why = "row tiles exceed the cluster"; return false; }
+        } else {
+            if (!op.tc_ok) { why = "layer not tensor-core capable"; return false; }
+            if (op.tc_in0 != cur) { why = "layer chain is not sequential"; return false; }
+            Ld.type = op.mode == MODE_DOWN ? MG_DOWN : op.mode == MODE_UP ? MG_UP : MG_CONV5;
+            Ld.CO = op.CO; Ld.NC = op.CO / TC_NT; Ld.gs = op.gs;
+            if (Ld.MT * Ld.NC > MEGA_CLUSTER) { why = "layer needs more than 8 CTA tiles"; return false; }
+            const int Ca = e->bufs[cur].C;
+            Ld.n_a = Ca / TC_KCH;
+            Ld.a_plane = (Ca / 8) * Ld.RT * 16;
+            if (2 * Ld.a_plane > a_bytes) a_bytes = 2 * Ld.a_plane;
+            if (op.in1 >= 0) {
+                const Skip& sk = skips[op.in1];
+                if (sk.ready < 0 || sk.L != op.L_in) { why = "skip connection not produced before use"; return false; }
+                MegaLayer g; memset(&g, 0, sizeof(g)); mega_geom(sk.L, G, g);
+                const long long plane = (long long)n_clusters * g.MT * (sk.C / 8) * g.RT * 8;
+                Ld.n_skip = sk.C / TC_KCH; Ld.skip_C = sk.C; Ld.skip_ready = sk.ready;
+                Ld.skip_hi = e->mega_skip + sk.off; Ld.skip_lo = e->mega_skip + sk.off + plane;
+            }
+            Ld.w = e->packed_tc + op.w_tc;
+            Ld.bias = e->packed + op.bias;
+            if (op.gn) { Ld.gamma = e->packed + op.gamma; Ld.beta = e->packed + op.beta; }
+            if (op.cond >= 0) Ld.cond = e->packed + op.cond;
+            if (op.mode == MODE_CONV5 && op.cond >= 0) {
+                // conv0 of a residual block: the block's 1x1 residual conv reads the same inputs, so it is issued here
+                if (i + 1 >= e->ops.size()) { why = "dangling block"; return false; }
+                const ConvOp& b = e->ops[i + 1];
+                if (b.mode != MODE_CONV5 || b.in0 != op.out || b.in1 >= 0 || b.res0 != op.in0 || b.res1 != op.in1) { why = "unexpected block structure"; return false; }
+                if (b.res_w >= 0) { Ld.n_res_a = Ld.n_a; Ld.n_res_skip = Ld.n_skip; Ld.res_w = e->packed_tc + b.res_w_tc; }
+            }
+            if (op.mode == MODE_CONV5 && op.res0 != -2) {
+                if (n < 1 || P.layers[n - 1].type != MG_CONV5 || P.layers[n - 1].cond == nullptr) { why = "conv1 without conv0"; return false; }
+                if (op.res_w >= 0) {
+                    Ld.res_mode = 2; Ld.res_bias = e->packed + op.res_bias;
+                } else {
+                    // identity: the thread that owns (row, channels) of this output produced the same element of the
+                    // previous block's output -> the fp32 values are still in its registers
+                    Ld.res_mode = 1;
+                    if (n < 2 || P.layers[n - 2].type != MG_CONV5 || P.layers[n - 2].res_mode == 0 || P.layers[n - 2].CO != Ld.CO ||
+                        P.layers[n - 2].L != Ld.L || out_of_layer[n - 2] != op.res0 || op.res1 >= 0) { why = "identity residual across a layout change"; return false; }
+                }
+            }
+            if (skips.count(op.out)) {
+                Skip& sk = skips[op.out];
+                if (Ld.type != MG_CONV5) { why = "skip produced by a strided layer"; return false; }
+                const long long plane = (long long)n_clusters * Ld.MT * (sk.C / 8) * Ld.RT * 8;
+                Ld.skip_out_hi = e->mega_skip + sk.off; Ld.skip_out_lo = e->mega_skip + sk.off + plane;
+                sk.ready = n + 1;
+            }
+            if (op.out == e->final_in) Ld.out_cm = const_cast<float*>(buf_ptr(e, op.out, e->work_batch));
+        }
+        out_of_layer.push_back(op.out);
+        cur = op.out;
+    }
+    if (cur != e->final_in) { why = "plan does not end at final_conv.0"; return false; }
+    P.n_layers = n;
+    for (int k = 0; k + 1 < n; ++k) {
+        MegaLayer& Ld = P.layers[k];
+        const MegaLayer& nx = P.layers[k + 1];
+        Ld.oSPT = nx.SPT; Ld.oLp = nx.Lp; Ld.oNC = nx.NC; Ld.oRT = nx.RT;
+        Ld.o_plane = (Ld.CO / 8) * nx.RT * 16;
+        if (Ld.o_plane != nx.a_plane) { why = "internal: plane mismatch"; return false; }
+        const int out_L = Ld.type == MG_DOWN ? Ld.L / 2 : Ld.type == MG_UP ? Ld.L * 2 : Ld.L;
+        if (out_L != nx.L) { why = "internal: length mismatch"; return false; }
+        Ld.zero_bytes = (k > 0 && (nx.a_plane != Ld.a_plane || nx.L != Ld.L)) ? 2 * nx.a_plane : 0;
+    }
+    P.a_bytes = (a_bytes + 127) / 128 * 128;
+    if (mega_smem_bytes(P.a_bytes) > 227 * 1024) { why = "shared memory budget"; return false; }
+    return true;
+}
+
+static void build_mega(mpdb_engine* e, int B) {
+    e->mega_ok = false;
+    const int Gs[4] = {8, 4, 2, 1};
+    for (int G : Gs)
+        if (try_build_mega(e, B, G, e->mega_why)) { e->mega_ok = true; e->mega_why.clear(); return; }
 }
 
 // Can ops[i], ops[i+1] (the two Conv1dBlocks of a ResidualTemporalBlock) run as one cluster-fused launch?
@@ -503,6 +638,12 @@ static int launch_op(mpdb_engine* e, const ConvOp& op, const float* x, const lon
 // Runs every layer up to (and including) final_conv.0; the 1x1 projection is fused into launch_final.
 static int run_unet_body(mpdb_engine* e, const float* x, const long long* t_dev, int t_uniform, int B, cudaStream_t st,
                          bool tc) {
+    if (tc && e->use_mega && e->mega_ok && e->alias_buffers && t_dev == nullptr && !e->timeline) {
+        MegaProgram P = e->mega;  // one launch: every layer up to final_conv.0 inside thread-block clusters
+        P.x = x; P.t = t_uniform; P.B = B;
+        P.dbg = e->mega_dbg;
+        return launch_unet_mega(P, st);
+    }
     for (size_t i = 0; i < e->ops.size(); ++i) {
         if (can_fuse_rtb(e, i, tc)) {
             if (launch_rtb(e, i, t_dev, t_uniform, B, st)) return 1;
@@ -588,7 +729,7 @@ extern "C" void mpdb_engine_destroy(mpdb_engine* e) {
     cudaDeviceSynchronize();
     if (e->graph_exec) cudaGraphExecDestroy(e->graph_exec);
     cudaFree(e->raw); cudaFree(e->packed); cudaFree(e->work); cudaFree(e->sched);
-    cudaFree(e->packed_tc); cudaFree(e->work_tc); cudaFree(e->dbg_buf);
+    cudaFree(e->packed_tc); cudaFree(e->work_tc); cudaFree(e->dbg_buf); cudaFree(e->mega_skip); cudaFree(e->mega_dbg);
     cudaFree(e->xbuf[0]); cudaFree(e->xbuf[1]); cudaFree(e->flags);
     cudaFree(e->g_noise); cudaFree(e->g_hc); cudaFree(e->g_chain);
     delete e;
@@ -629,6 +770,17 @@ extern "C" int mpdb_engine_set_option(mpdb_engine* e, const char* name, double v
         e->tc_mode = (int)value;
     } else if (n == "fuse_rtb") {
         e->fuse_rtb = value != 0;
+        if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; e->graph_key.clear(); }
+    } else if (n == "mega_timeline") {
+        if (value != 0 && !e->mega_dbg) {
+            MPDB_CHECK_CUDA(cudaMalloc(&e->mega_dbg, sizeof(long long) * 4 * MEGA_CLUSTER * MEGA_MAX_LAYERS));
+            MPDB_CHECK_CUDA(cudaMemset(e->mega_dbg, 0, sizeof(long long) * 4 * MEGA_CLUSTER * MEGA_MAX_LAYERS));
+        } else if (value == 0 && e->mega_dbg) {
+            cudaFree(e->mega_dbg); e->mega_dbg = nullptr;
+        }
+        if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; e->graph_key.clear(); }
+    } else if (n == "mega") {
+        e->use_mega = value != 0;
         if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; e->graph_key.clear(); }
     } else if (n == "alias_buffers") {
         if (e->alias_buffers != (value != 0)) {
@@ -707,6 +859,72 @@ extern "C" int mpdb_unet_forward(mpdb_engine* e, const float* x, const int64_t* 
     f.mode = 0;
     f.out = eps;
     return launch_final(f, st);
+}
+
+// The forward exactly as the fused loop runs it (one uniform timestep, tensor-core policy of the loop:
+// tc_mode 0 -> exact, otherwise tensor cores; whole-forward cluster kernel when enabled and supported).
+extern "C" int mpdb_unet_forward_uniform(mpdb_engine* e, const float* x, int32_t t, float* eps, int32_t B, void* stream) {
+    MPDB_REQUIRE(e && x && eps && B > 0, "mpdb_unet_forward_uniform: bad argument");
+    MPDB_REQUIRE(t >= 0 && t < e->cfg.n_diffusion_steps, "mpdb_unet_forward_uniform: t out of range");
+    MPDB_REQUIRE(e->finalized, "engine not finalized (call mpdb_engine_finalize after loading parameters)");
+    cudaStream_t st = (cudaStream_t)stream;
+    MPDB_CHECK_CUDA(cudaSetDevice(e->device));
+    if (ensure_workspace(e, B)) return 1;
+    if (run_unet_body(e, x, nullptr, t, B, st, e->tc_mode != 0)) return 1;
+    FinalArgs f;
+    fill_final(e, f, x, nullptr, t, B);
+    f.mode = 0;
+    f.out = eps;
+    return launch_final(f, st);
+}
+
+// Is the whole-forward cluster kernel in use for batch B? Returns 1/0; fills samples per cluster, layers, A-buffer and
+// shared-memory bytes; `why` receives the reason when it is not.
+extern "C" int mpdb_engine_mega_info(mpdb_engine* e, int32_t B, int32_t* G, int32_t* n_layers, int32_t* a_bytes,
+                                     int32_t* smem_bytes, char* why, int why_cap) {
+    if (!e || B <= 0) return 0;
+    if (cudaSetDevice(e->device) != cudaSuccess || ensure_workspace(e, B)) return 0;
+    if (G) *G = e->mega.G;
+    if (n_layers) *n_layers = e->mega.n_layers;
+    if (a_bytes) *a_bytes = e->mega.a_bytes;
+    if (smem_bytes) *smem_bytes = (int32_t)mega_smem_bytes(e->mega.a_bytes);
+    if (why && why_cap > 0) { strncpy(why, e->mega_why.c_str(), why_cap - 1); why[why_cap - 1] = 0; }
+    return (e->mega_ok && e->use_mega && e->alias_buffers) ? 1 : 0;
+}
+
+// Device time of the UNet body (every layer up to final_conv.0, as the loop runs it) per forward: CUDA events on
+// `stream` around `reps` back-to-back forwards. launches_out = kernels per forward.
+extern "C" int mpdb_profile_unet_body(mpdb_engine* e, const float* x, int32_t t, int32_t B, int32_t reps, float* ms_out,
+                                      double* flops_out, int32_t* launches_out, void* stream) {
+    MPDB_REQUIRE(e && x && ms_out && B > 0 && reps > 0, "mpdb_profile_unet_body: bad argument");
+    MPDB_REQUIRE(e->finalized, "engine not finalized");
+    cudaStream_t st = (cudaStream_t)stream;
+    MPDB_CHECK_CUDA(cudaSetDevice(e->device));
+    if (ensure_workspace(e, B)) return 1;
+    const bool tc = e->tc_mode != 0;
+    cudaEvent_t ev0, ev1;
+    MPDB_CHECK_CUDA(cudaEventCreate(&ev0));
+    MPDB_CHECK_CUDA(cudaEventCreate(&ev1));
+    const long long before = mpdb::g_launch_count.load();
+    if (run_unet_body(e, x, nullptr, t, B, st, tc)) return 1;  // warm-up
+    const long long per = mpdb::g_launch_count.load() - before;
+    MPDB_CHECK_CUDA(cudaEventRecord(ev0, st));
+    for (int r = 0; r < reps; ++r)
+        if (run_unet_body(e, x, nullptr, t, B, st, tc)) return 1;
+    MPDB_CHECK_CUDA(cudaEventRecord(ev1, st));
+    MPDB_CHECK_CUDA(cudaEventSynchronize(ev1));
+    float ms = 0.f;
+    MPDB_CHECK_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
+    *ms_out = ms / reps;
+    if (flops_out) {
+        double f = 0.0;
+        for (const ConvOp& op : e->ops) f += op_flops(e, op, B);
+        *flops_out = f;
+    }
+    if (launches_out) *launches_out = (int32_t)per;
+    cudaEventDestroy(ev0);
+    cudaEventDestroy(ev1);
+    return 0;
 }
 
 extern "C" int mpdb_p_mean(mpdb_engine* e, const float* x, const int64_t* t, float* mean, int32_t B, void* stream) {
@@ -873,7 +1091,7 @@ extern "C" int mpdb_sample_loop(mpdb_engine* e, mpdb_guide* g, const mpdb_loop_p
                       std::to_string(p->n_steps_without_noise) + "|" + std::to_string(p->t_start_guide) + "|" +
                       std::to_string(p->n_guide_steps) + "|" + std::to_string(p->scale_grad_by_std) + "|" +
                       std::to_string(chain_out != nullptr) + "|" + std::to_string(p->n_hard_conds) + "|tc" +
-                      std::to_string(e->tc_mode) + "/" + std::to_string(e->tc_amp_limit) + "/" + std::to_string(e->fuse_rtb);
+                      std::to_string(e->tc_mode) + "/" + std::to_string(e->tc_amp_limit) + "/" + std::to_string(e->fuse_rtb) + "/" + std::to_string(e->use_mega);
     for (int k = 0; k < p->n_hard_conds; ++k) key += "," + std::to_string(p->hard_cond_rows[k]);
     for (int k = 0; k < n_iters; ++k) {
         float v = p->noise_std ? p->noise_std[k] : 1.0f;
@@ -1066,6 +1284,22 @@ extern "C" int mpdb_debug_tc_conv5(const float* x_cm, const float* w, float* raw
     if (rc) return rc;
     MPDB_CHECK_CUDA(e1);
     return 0;
+}
+
+// Debug: per-layer clock64 stamps of the whole-forward kernel (option "mega_timeline"): [layers][8 ranks][4], plus the
+// layer descriptors' (type, L, CO, MT*NC) as 4 ints per layer in `desc_out`.
+extern "C" int mpdb_engine_read_mega_timeline(mpdb_engine* e, int64_t* host_out, int32_t* desc_out, int32_t max_layers) {
+    MPDB_REQUIRE(e && host_out && e->mega_dbg, "mpdb_engine_read_mega_timeline: timeline not enabled");
+    MPDB_CHECK_CUDA(cudaSetDevice(e->device));
+    MPDB_CHECK_CUDA(cudaDeviceSynchronize());
+    const int n = e->mega.n_layers < max_layers ? e->mega.n_layers : max_layers;
+    MPDB_CHECK_CUDA(cudaMemcpy(host_out, e->mega_dbg, sizeof(long long) * 4 * MEGA_CLUSTER * n, cudaMemcpyDeviceToHost));
+    if (desc_out)
+        for (int k = 0; k < n; ++k) {
+            const MegaLayer& L = e->mega.layers[k];
+            desc_out[4 * k + 0] = L.type; desc_out[4 * k + 1] = L.L; desc_out[4 * k + 2] = L.CO; desc_out[4 * k + 3] = L.MT * L.NC;
+        }
+    return n;
 }
 
 // Debug: clock64 stamps (16 per op) of CTA (0,0) of every tensor-core conv of the last forward (option "timeline").

@@ -95,6 +95,46 @@ int launch_pack_tc_weights(const float* src, unsigned short* dst, int CI, int CI
 int launch_blc_to_tc(const float* x, unsigned short* hi, unsigned short* lo, int B, int L, int D, int C, cudaStream_t stream);
 int launch_cm_to_tc(const float* cm, unsigned short* hi, unsigned short* lo, int B, int C, int L, cudaStream_t stream);
 
+// ---- whole-forward persistent cluster kernel (unet_mega.cu) ----
+constexpr int MEGA_MAX_LAYERS = 48;
+constexpr int MEGA_CLUSTER = 8;  // CTAs per cluster (portable maximum)
+enum MegaType { MG_INPUT = 0, MG_CONV5 = 1, MG_DOWN = 2, MG_UP = 3 };
+
+// One layer of the program. Input geometry: the A buffer holds C_a = 32 * n_a channels of G samples at length L as
+// MT row tiles of SPT samples (RT = SPT * (L + 4) rows per k-group); CTA rank -> (row tile rank / NC, channel chunk
+// rank % NC). Output geometry (o*) = the input geometry of the next layer.
+struct MegaLayer {
+    int type;
+    int L, Lp, SPT, MT, NC, RT;
+    int n_a, n_skip;          // main K-chunks (32 channels each) from the A buffer / from the global skip tensor
+    int n_res_a, n_res_skip;  // K-chunks of the block's 1x1 residual conv, issued after the main chunks of conv0
+    int a_plane;              // bytes between the hi and lo planes of the A buffer as this layer reads it
+    int skip_C, skip_ready;   // channels of the skip tensor; index of the first layer at which it is complete
+    int CO, gs;
+    int res_mode;             // conv1 of a block: 1 = identity (fp32 values kept in registers), 2 = fused 1x1 conv; else 0
+    int oSPT, oLp, oNC, oRT, o_plane;
+    int zero_bytes;           // > 0: the A buffer changes layout after this layer; every CTA clears this many bytes
+    const unsigned short* w;      // packed [NC][n_a + n_skip][taps][4][hi 32 | lo 32][8]
+    const unsigned short* res_w;  // packed [NC][n_res_a + n_res_skip][1][4][hi 32 | lo 32][8]
+    const unsigned short *skip_hi, *skip_lo;          // [cluster][MT][skip_C/8][RT][8]
+    unsigned short *skip_out_hi, *skip_out_lo;        // same layout, CO channels (output also kept as a skip connection)
+    const float *bias, *gamma, *beta, *cond, *res_bias;
+    float* out_cm;            // final_conv.0: fp32 [B][CO][L+4] for the fused projection kernel
+};
+
+struct MegaProgram {
+    MegaLayer layers[MEGA_MAX_LAYERS];
+    int n_layers;
+    int G;        // samples per cluster
+    int B, H, D;
+    int t;        // uniform timestep (row of the time-conditioning tables)
+    int a_bytes;  // size of the A buffer
+    const float* x;  // trajectory [B][H][D] fp32
+    long long* dbg;  // optional timeline: [n_layers][8 ranks][4] clock64 stamps of thread 0 of cluster 0
+};
+size_t mega_smem_bytes(int a_bytes);
+int launch_unet_mega(const MegaProgram& P, cudaStream_t stream);
+
 struct FinalArgs {
     const float* h;     // CM [B][C][L+4]
     int C;

@@ -1,0 +1,413 @@
+// Whole TemporalUnet forward (temporal_unet.py:118-171) as ONE persistent launch of thread-block clusters.
+//
+// The reverse loop at 100 trajectories per GPU is a chain of ~40 dependent convolutions per forward; run layer by layer
+// (unet_tc.cu) every link pays a kernel boundary: launch edge, barrier/TMEM setup, a cold first copy from L2, drain.
+// GroupNorm is per sample, so a group of G trajectories can run the whole network with no grid-wide dependency. Here a
+// cluster of 8 CTAs owns G (8 at H=64) trajectories from the input projection to final_conv.0:
+//
+//   * activations never leave the cluster: the current tensor lives in every CTA's shared memory ("A buffer") in the
+//     tcgen05 no-swizzle K-major operand layout [plane hi|lo][C/8][RT rows][8 x bf16]; a layer's epilogue writes its
+//     32 output channels straight into the A buffer of every CTA that consumes them through distributed shared memory
+//     (st.shared::cluster), so the next layer's MMAs read local shared memory;
+//   * per layer the 8 CTAs tile (row tiles of <=128 padded rows) x (32-channel output chunks): 8x1 at L=64, 3x2 at
+//     L=32, 2x4 at L=16, 1x8 at L=8; the (sample -> row tile) map changes at the stride-2 layers and is applied by the
+//     writer;
+//   * weights stream from L2 through a 3-stage cp.async.bulk ring driven by a dedicated producer warp that runs ahead
+//     across layer boundaries (weights do not depend on activations), so a layer's first chunk is already resident
+//     when its inputs land; skip connections go through global memory (written once, read once, L2-resident);
+//   * TMEM, mbarriers and the layer program (a __grid_constant__ table) are set up once per forward;
+//   * layer-to-layer synchronisation is two cluster-scope mbarriers per CTA: a_free (every CTA's MMAs of this layer
+//     have retired -> its A buffer may be overwritten) and a_full (every epilogue warp of the cluster has delivered
+//     its outputs). Every warp of every CTA arrives on every CTA's barrier each layer, active or not, so the counts
+//     are constants and idle CTAs stay in lock step.
+//
+// Arithmetic is identical to the per-layer tensor-core path (same split-bf16 MMA sequence per K-chunk, same GroupNorm
+// reduction tree, fp32 residual values kept in registers), so the two paths agree bit for bit (tested).
+#include "tc_common.cuh"
+
+namespace mpdb {
+
+constexpr int MG_THREADS = TC_THREADS + 96;  // 16 epilogue warps + 1 producer warp + 2 MMA-issue warps
+// One thread issues a tcgen05.mma every ~80-97 cycles whatever its shape (tools/probes/mma_probe.cu); two threads in
+// different warps reach the shared-memory operand floor (~44 cycles per MMA at N = 64 / 32). Issuer 0 drives the
+// A_hi x [W_hi | W_lo] products, issuer 1 the A_lo x W_hi products, into separate accumulators (deterministic sums).
+constexpr int MG_STAGES = 3;
+constexpr int MG_TMEM_COLS = 256;  // main: [0,32) hi*hi, [32,64) hi*lo, [64,96) lo*hi; residual conv / odd outputs: the same at +128
+constexpr int MG_SCRATCH_BYTES = (2 * 128 * 8 + 12 * 8 * 2) * (int)sizeof(float) + 2 * 12 * 8 * (int)sizeof(double);
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void pack_split8(const float (&v)[8], uint4& ph, uint4& pl) {
+    unsigned short h[8], lo8[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) split_bf16(v[e], h[e], lo8[e]);
+    ph.x = h[0] | ((uint32_t)h[1] << 16); ph.y = h[2] | ((uint32_t)h[3] << 16);
+    ph.z = h[4] | ((uint32_t)h[5] << 16); ph.w = h[6] | ((uint32_t)h[7] << 16);
+    pl.x = lo8[0] | ((uint32_t)lo8[1] << 16); pl.y = lo8[2] | ((uint32_t)lo8[3] << 16);
+    pl.z = lo8[4] | ((uint32_t)lo8[5] << 16); pl.w = lo8[6] | ((uint32_t)lo8[7] << 16);
+}
+
+__global__ void __launch_bounds__(MG_THREADS, 1) unet_mega_kernel(const __grid_constant__ MegaProgram P) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    unsigned char* abuf = smem_raw;                                   // current activation, operand layout
+    unsigned char* stages = abuf + P.a_bytes;                         // ring: [acts hi | acts lo | weights] per stage
+    uint64_t* bars = reinterpret_cast<uint64_t*>(stages + MG_STAGES * TC_STAGE_BYTES);  // full[S], empty[S], acc_done, a_full, a_free
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MG_STAGES + 3);
+    volatile int* mma_progress = reinterpret_cast<volatile int*>(tmem_slot + 1);
+    float* part = reinterpret_cast<float*>(tmem_slot + 4);            // GroupNorm scratch
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int rank = (int)cluster_ctarank();
+    const int cluster = blockIdx.x / MEGA_CLUSTER;
+    const uint32_t abuf_u32 = smem_u32(abuf), stages_u32 = smem_u32(stages);
+    const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + MG_STAGES);
+    const uint32_t acc_done = smem_u32(bars + 2 * MG_STAGES), a_full = acc_done + 8, a_free = acc_done + 16;
+
+    // ---- setup (once per forward) ----
+    if (tid == 0) {
+        for (int s = 0; s < MG_STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 2); }  // both issuers release a stage
+        mbar_init(acc_done, 2);
+        mbar_init(a_full, MEGA_CLUSTER * (TC_THREADS / 32));  // every epilogue warp of every CTA of the cluster, every layer
+        mbar_init(a_free, MEGA_CLUSTER);                      // one arrival per CTA, every layer
+        *mma_progress = -1;
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(MG_TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    for (int i = tid; i < P.a_bytes / 16; i += MG_THREADS) reinterpret_cast<uint4*>(abuf)[i] = make_uint4(0u, 0u, 0u, 0u);
+    asm volatile("fence.proxy.async;" ::: "memory");
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    cluster_sync_all();  // peers have initialised their barriers and cleared their A buffers before any remote access
+    const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();
+
+    if (warp == TC_THREADS / 32) {
+        // ===== producer warp: every K-chunk of every layer this CTA takes part in, in program order. The whole warp runs
+        // the loop (warp-uniform values stay in uniform registers); one elected lane issues the copies. =====
+        {
+            int i = 0;
+            for (int l = 0; l < P.n_layers; ++l) {
+                const MegaLayer& Ld = P.layers[l];
+                if (Ld.type == MG_INPUT || rank >= Ld.MT * Ld.NC) continue;
+                const int mt = rank / Ld.NC, nc = rank - mt * Ld.NC;
+                const int ntaps = Ld.type == MG_CONV5 ? 5 : Ld.type == MG_DOWN ? 3 : 4;
+                const int n_main = Ld.n_a + Ld.n_skip, n_res = Ld.n_res_a + Ld.n_res_skip;
+                const uint32_t act_bytes = (uint32_t)(TC_KCH / 8) * Ld.RT * 16;  // one plane of one K-chunk
+                bool skip_checked = false;
+                for (int c = 0; c < n_main + n_res; ++c, ++i) {
+                    const int s = i % MG_STAGES;
+                    if (i >= MG_STAGES) mbar_wait(empty0 + 8 * s, ((uint32_t)(i / MG_STAGES) & 1u) ^ 1u);
+                    const bool is_res = c >= n_main;
+                    const int cc = is_res ? c - n_main : c;
+                    const int na = is_res ? Ld.n_res_a : Ld.n_a;
+                    const bool from_skip = cc >= na;
+                    const uint32_t wbytes = (is_res ? 1u : (uint32_t)ntaps) * 2u * TC_B_TAP_BYTES;
+                    const unsigned short* wsrc = is_res ? Ld.res_w + ((size_t)nc * n_res + cc) * (2 * TC_B_TAP_BYTES / 2)
+                                                        : Ld.w + ((size_t)nc * n_main + cc) * ((size_t)ntaps * 2 * TC_B_TAP_BYTES / 2);
+                    const uint32_t st = stages_u32 + (uint32_t)s * TC_STAGE_BYTES;
+                    if (from_skip && !skip_checked) {
+                        // the skip tensor was written (by CTAs of this cluster) many layers ago; make the dependency explicit
+                        const long long t0 = clock64();
+                        while (*mma_progress < Ld.skip_ready) { if (clock64() - t0 > 4000000000LL) __trap(); }
+                        asm volatile("fence.acq_rel.cluster;" ::: "memory");
+                        skip_checked = true;
+                    }
+                    __syncwarp();
+                    mbar_expect_tx_elect(full0 + 8 * s, wbytes + (from_skip ? 2u * act_bytes : 0u));
+                    bulk_g2s_elect(st + 2 * TC_A_PLANE_BYTES, wsrc, wbytes, full0 + 8 * s);
+                    if (from_skip) {
+                        const size_t aoff = (((size_t)cluster * Ld.MT + mt) * (Ld.skip_C / 8) + (size_t)(cc - na) * (TC_KCH / 8)) * Ld.RT * 8;
+                        bulk_g2s_elect(st, Ld.skip_hi + aoff, act_bytes, full0 + 8 * s);
+                        bulk_g2s_elect(st + TC_A_PLANE_BYTES, Ld.skip_lo + aoff, act_bytes, full0 + 8 * s);
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        cluster_sync_all();  // no CTA leaves while peers may still address its shared memory
+        return;
+    }
+
+
+    if (warp > TC_THREADS / 32) {
+        // ===== two MMA-issue warps. Each runs its loop warp-convergently (descriptors in uniform registers) and one elected
+        // lane issues. They write no activations, so their fences never wait on remote stores. =====
+        const int which = __shfl_sync(0xffffffffu, warp, 0) - (TC_THREADS / 32 + 1);  // 0: A_hi x [W_hi | W_lo] (N = 64), 1: A_lo x W_hi (N = 32)
+        {
+            const uint32_t idesc = which == 0 ? tc_idesc(128, 2 * TC_NT) : tc_idesc(128, TC_NT);
+            const uint32_t col0 = __shfl_sync(0xffffffffu, tmem_base, 0) + (which == 0 ? 0u : 2u * TC_NT);  // this issuer's main accumulator
+            int ring_i = 0;
+            for (int l = 1; l < P.n_layers; ++l) {
+                const MegaLayer& Ld = P.layers[l];
+                mbar_wait_cluster(a_full, (uint32_t)(l - 1) & 1u);  // operands of this layer have landed (cluster-wide)
+                tc_fence_after();
+                if (which == 0 && lane == 0) *mma_progress = l;
+                __syncwarp();
+                if (rank >= Ld.MT * Ld.NC) continue;
+                const int n_main = Ld.n_a + Ld.n_skip, n_res = Ld.n_res_a + Ld.n_res_skip;
+                const uint32_t lbo = (uint32_t)Ld.RT * 16;
+                bool first0 = true, first1 = true;
+                for (int c = 0; c < n_main + n_res; ++c, ++ring_i) {
+                    const int sidx = ring_i % MG_STAGES;
+                    mbar_wait(full0 + 8 * sidx, (uint32_t)(ring_i / MG_STAGES) & 1u);
+                    tc_fence_after();
+                    const bool is_res = c >= n_main;
+                    const int cc = is_res ? c - n_main : c;
+                    const bool from_a = cc < (is_res ? Ld.n_res_a : Ld.n_a);
+                    const uint32_t st = stages_u32 + (uint32_t)sidx * TC_STAGE_BYTES;
+                    uint32_t aaddr = from_a ? abuf_u32 + (uint32_t)cc * (TC_KCH / 8) * lbo : st;
+                    if (which == 1) aaddr += from_a ? (uint32_t)Ld.a_plane : (uint32_t)TC_A_PLANE_BYTES;  // lo plane
+                    const uint64_t dA = tc_desc(aaddr, lbo, 128);
+                    const uint64_t dB = tc_desc(st + 2 * TC_A_PLANE_BYTES, 2 * TC_NT * 16, 128);  // rows [0,32) = W_hi, [32,64) = W_lo
+                    if (is_res) {
+#pragma unroll
+                        for (int kk = 0; kk < TC_KCH / 16; ++kk) {
+                            const uint64_t aofs = (uint64_t)((kk * 2 * lbo + 2 * 16) >> 4);  // 1x1 conv reads the centre row
+                            const uint64_t bofs = (uint64_t)((kk * 2 * (2 * TC_NT * 16)) >> 4);
+                            tc_mma_bf16_elect(col0 + 128, dA + aofs, dB + bofs, idesc, first1 ? 0u : 1u);
+                            first1 = false;
+                        }
+                    } else {
+                        const int ntaps = Ld.type == MG_CONV5 ? 5 : Ld.type == MG_DOWN ? 3 : 4;
+                        for (int tap = 0; tap < ntaps; ++tap) {
+                            // row shift of the tap (16-byte rows; +2 is the centre), see conv5_tc_kernel
+                            const int shift = Ld.type == MG_CONV5 ? tap : Ld.type == MG_DOWN ? tap + 1 : (tap == 0 ? 2 : tap == 1 ? 1 : tap == 2 ? 3 : 2);
+                            const bool second_acc = Ld.type == MG_UP && tap >= 2;
+#pragma unroll
+                            for (int kk = 0; kk < TC_KCH / 16; ++kk) {
+                                const uint64_t aofs = (uint64_t)((kk * 2 * lbo + shift * 16) >> 4);
+                                const uint64_t bofs = (uint64_t)((tap * 2 * TC_B_TAP_BYTES + kk * 2 * (2 * TC_NT * 16)) >> 4);
+                                bool& first = second_acc ? first1 : first0;
+                                tc_mma_bf16_elect(col0 + (second_acc ? 128u : 0u), dA + aofs, dB + bofs, idesc, first ? 0u : 1u);
+                                first = false;
+                            }
+                        }
+                    }
+                    tc_commit_elect(empty0 + 8 * sidx);  // the stage is free when both issuers' MMAs that read it have retired
+                }
+                tc_commit_elect(acc_done);
+            }
+        }
+        __syncwarp();
+        cluster_sync_all();
+        return;
+    }
+
+    // ===== 16 epilogue warps =====
+    const int q = warp & 3, cg = warp >> 2;
+    const int r = q * 32 + lane;  // padded row of the tile = TMEM lane
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + cg * 8;
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    uint32_t acc_ph = 0;
+    float keep[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // fp32 output of the last residual block owned by this thread
+
+    for (int l = 0; l < P.n_layers; ++l) {
+        const MegaLayer& Ld = P.layers[l];
+        // outputs of the previous layer have landed everywhere (also keeps idle CTAs in lock step)
+        if (l > 0) mbar_wait_cluster(a_full, (uint32_t)(l - 1) & 1u);
+        long long* dbg = (P.dbg != nullptr && cluster == 0 && tid == 0) ? P.dbg + ((size_t)l * MEGA_CLUSTER + rank) * 4 : nullptr;
+        if (dbg) dbg[0] = clock64();  // inputs landed
+        const bool active = rank < Ld.MT * Ld.NC;
+        const int mt = rank / Ld.NC, nc = rank - mt * Ld.NC;
+        const int Lp = Ld.Lp;
+        const int s = r / Lp, ll = r - s * Lp;
+        const int sg = mt * Ld.SPT + s;  // sample within the cluster
+        const int b = cluster * P.G + sg;
+        const bool valid = active && (s < Ld.SPT) && (ll < Ld.L) && (sg < P.G) && (b < P.B);
+        const int c8 = nc * TC_NT + cg * 8;
+        float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        float w[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // UP: odd outputs
+
+        if (Ld.type == MG_INPUT) {
+            // trajectory x [B][H][D] fp32 -> channels [cg*8, cg*8+8) of row ll (channels >= D stay zero)
+            if (valid) {
+                const float* xp = P.x + ((size_t)b * P.H + ll) * P.D;
+#pragma unroll
+                for (int e = 0; e < 8; ++e)
+                    if (cg * 8 + e < P.D) v[e] = xp[cg * 8 + e];
+            }
+            if (tid < MEGA_CLUSTER) mbar_arrive_cluster(map_to_cta(a_free, (uint32_t)tid));
+        } else {
+            float4 pb0 = z4, pb1 = z4, pg0 = z4, pg1 = z4, pe0 = z4, pe1 = z4, pc0 = z4, pc1 = z4, pr0 = z4, pr1 = z4;
+            float rv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            if (active) {
+                // parameters are fetched while the MMAs run
+                pb0 = *reinterpret_cast<const float4*>(Ld.bias + c8); pb1 = *reinterpret_cast<const float4*>(Ld.bias + c8 + 4);
+                if (Ld.type == MG_CONV5) {
+                    pg0 = *reinterpret_cast<const float4*>(Ld.gamma + c8); pg1 = *reinterpret_cast<const float4*>(Ld.gamma + c8 + 4);
+                    pe0 = *reinterpret_cast<const float4*>(Ld.beta + c8); pe1 = *reinterpret_cast<const float4*>(Ld.beta + c8 + 4);
+                    if (Ld.cond != nullptr) {
+                        const float* cp = Ld.cond + (size_t)P.t * Ld.CO + c8;
+                        pc0 = *reinterpret_cast<const float4*>(cp); pc1 = *reinterpret_cast<const float4*>(cp + 4);
+                    }
+                    if (Ld.res_mode == 2) {
+                        pr0 = *reinterpret_cast<const float4*>(Ld.res_bias + c8); pr1 = *reinterpret_cast<const float4*>(Ld.res_bias + c8 + 4);
+                    }
+                }
+                mbar_wait(acc_done, acc_ph);
+                acc_ph ^= 1u;
+                if (dbg) dbg[1] = clock64();  // accumulators complete
+                __syncwarp();
+                tc_fence_after();
+                {
+                    float v2[8], v3[8];
+                    tc_ld8(taddr, v);               // hi*hi
+                    tc_ld8(taddr + 2 * TC_NT, v3);  // lo*hi
+                    tc_ld8(taddr + TC_NT, v2);      // hi*lo
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) v[j] = (v[j] + v3[j]) + v2[j];
+                }
+                if (Ld.type == MG_UP) {
+                    float w2[8], w3[8];
+                    tc_ld8(taddr + 128, w);
+                    tc_ld8(taddr + 128 + 2 * TC_NT, w3);
+                    tc_ld8(taddr + 128 + TC_NT, w2);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) w[j] = (w[j] + w3[j]) + w2[j];
+                } else if (Ld.res_mode == 2) {
+                    float rv2[8], rv3[8];
+                    tc_ld8(taddr + 128, rv);
+                    tc_ld8(taddr + 128 + 2 * TC_NT, rv3);
+                    tc_ld8(taddr + 128 + TC_NT, rv2);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) rv[j] = (rv[j] + rv3[j]) + rv2[j];
+                }
+                tc_fence_before();
+            }
+            // this CTA no longer reads its A buffer: clear it if the next layer uses another layout, then tell the cluster
+            if (Ld.zero_bytes > 0) {
+                for (int i = tid; i < Ld.zero_bytes / 16; i += TC_THREADS) reinterpret_cast<uint4*>(abuf)[i] = make_uint4(0u, 0u, 0u, 0u);
+                asm volatile("fence.proxy.async;" ::: "memory");
+                epi_sync();
+            }
+            if (tid < MEGA_CLUSTER) mbar_arrive_cluster(map_to_cta(a_free, (uint32_t)tid));  // one lane per destination CTA
+
+            if (active) {
+                v[0] += pb0.x; v[1] += pb0.y; v[2] += pb0.z; v[3] += pb0.w;
+                v[4] += pb1.x; v[5] += pb1.y; v[6] += pb1.z; v[7] += pb1.w;
+                if (Ld.type == MG_UP) {
+                    w[0] += pb0.x; w[1] += pb0.y; w[2] += pb0.z; w[3] += pb0.w;
+                    w[4] += pb1.x; w[5] += pb1.y; w[6] += pb1.z; w[7] += pb1.w;
+                } else if (Ld.type == MG_CONV5) {
+                    switch (Ld.gs) {
+                        case 4: gn_mish8<4, true>(v, valid, r, s, cg, tid, Ld.SPT, Lp, Ld.L, part, pg0, pg1, pe0, pe1); break;
+                        case 8: gn_mish8<8, true>(v, valid, r, s, cg, tid, Ld.SPT, Lp, Ld.L, part, pg0, pg1, pe0, pe1); break;
+                        case 16: gn_mish8<16, true>(v, valid, r, s, cg, tid, Ld.SPT, Lp, Ld.L, part, pg0, pg1, pe0, pe1); break;
+                        default: gn_mish8<32, true>(v, valid, r, s, cg, tid, Ld.SPT, Lp, Ld.L, part, pg0, pg1, pe0, pe1); break;
+                    }
+                    v[0] += pc0.x; v[1] += pc0.y; v[2] += pc0.z; v[3] += pc0.w;
+                    v[4] += pc1.x; v[5] += pc1.y; v[6] += pc1.z; v[7] += pc1.w;
+                    if (Ld.res_mode == 2) {
+                        v[0] += rv[0] + pr0.x; v[1] += rv[1] + pr0.y; v[2] += rv[2] + pr0.z; v[3] += rv[3] + pr0.w;
+                        v[4] += rv[4] + pr1.x; v[5] += rv[5] + pr1.y; v[6] += rv[6] + pr1.z; v[7] += rv[7] + pr1.w;
+                    } else if (Ld.res_mode == 1) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) v[j] += keep[j];
+                    }
+                    if (Ld.res_mode != 0) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) keep[j] = v[j];
+                    }
+                }
+            }
+        }
+
+        // ===== deliver: every CTA that consumes these channels gets them in its A buffer (operand layout) =====
+        if (dbg) dbg[2] = clock64();  // epilogue arithmetic done
+        mbar_wait_cluster(a_free, (uint32_t)l & 1u);
+        if (valid) {
+            if (Ld.oNC > 0) {
+                const int n_out = Ld.type == MG_UP ? 2 : 1;
+                const bool emit = Ld.type != MG_DOWN || (ll & 1) == 0;
+                if (emit) {
+                    const int mt2 = sg / Ld.oSPT, s2 = sg - mt2 * Ld.oSPT;
+                    for (int k = 0; k < n_out; ++k) {
+                        const int lo = Ld.type == MG_DOWN ? (ll >> 1) : Ld.type == MG_UP ? 2 * ll + k : ll;
+                        uint4 ph, pl;
+                        if (k == 0) pack_split8(v, ph, pl); else pack_split8(w, ph, pl);
+                        const uint32_t off = (uint32_t)(((c8 / 8) * Ld.oRT + (s2 * Ld.oLp + lo + 2)) * 16);
+                        const uint32_t local_hi = abuf_u32 + off, local_lo = local_hi + (uint32_t)Ld.o_plane;
+                        for (int j = 0; j < Ld.oNC; ++j) {
+                            const uint32_t cta = (uint32_t)(mt2 * Ld.oNC + j);
+                            if ((int)cta == rank) {  // own A buffer: plain shared-memory stores
+                                *reinterpret_cast<uint4*>(abuf + off) = ph;
+                                *reinterpret_cast<uint4*>(abuf + off + Ld.o_plane) = pl;
+                            } else {
+                                st_cluster_v4(map_to_cta(local_hi, cta), ph);
+                                st_cluster_v4(map_to_cta(local_lo, cta), pl);
+                            }
+                        }
+                        if (Ld.skip_out_hi != nullptr) {  // skip connection: same-level layout in global memory
+                            const size_t o = ((((size_t)cluster * Ld.MT + mt) * (Ld.CO / 8) + c8 / 8) * Ld.RT + (r + 2)) * 8;
+                            *reinterpret_cast<uint4*>(Ld.skip_out_hi + o) = ph;
+                            *reinterpret_cast<uint4*>(Ld.skip_out_lo + o) = pl;
+                        }
+                    }
+                }
+            }
+            if (Ld.out_cm != nullptr) {  // final_conv.0: fp32 channel-major output for the fused projection + DDPM update
+                float* op = Ld.out_cm + ((size_t)b * Ld.CO + c8) * Lp + 2 + ll;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) op[(size_t)j * Lp] = v[j];
+            }
+        }
+        asm volatile("fence.proxy.async;" ::: "memory");  // generic-proxy stores -> tensor core / bulk copies of the consumers
+        if (dbg) dbg[3] = clock64();  // outputs delivered
+        __syncwarp();
+        if (lane < MEGA_CLUSTER && l + 1 < P.n_layers) mbar_arrive_cluster(map_to_cta(a_full, (uint32_t)lane));
+    }
+
+    // teardown
+    tc_fence_before();
+    epi_sync();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(MG_TMEM_COLS) : "memory");
+    }
+    cluster_sync_all();
+}
+
+size_t mega_smem_bytes(int a_bytes) {
+    return (size_t)a_bytes + (size_t)MG_STAGES * TC_STAGE_BYTES + (2 * MG_STAGES + 3) * 8 + 16 + MG_SCRATCH_BYTES;
+}
+
+int launch_unet_mega(const MegaProgram& P, cudaStream_t stream) {
+    MPDB_REQUIRE(P.n_layers > 0 && P.n_layers <= MEGA_MAX_LAYERS, "mega: bad layer count");
+    MPDB_REQUIRE(P.a_bytes % 128 == 0, "mega: A buffer size must be a multiple of 128");
+    const size_t smem = mega_smem_bytes(P.a_bytes);
+    MPDB_REQUIRE(smem <= 227 * 1024, "mega: shared memory budget exceeded");
+    static bool configured = false;
+    if (!configured) {
+        MPDB_CHECK_CUDA(cudaFuncSetAttribute(unet_mega_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        configured = true;
+    }
+    const int n_clusters = (P.B + P.G - 1) / P.G;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)n_clusters * MEGA_CLUSTER);
+    cfg.blockDim = dim3(MG_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[2];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = MEGA_CLUSTER;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = g_use_pdl ? 2 : 1;
+    MPDB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, unet_mega_kernel, P));
+    MPDB_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // namespace mpdb

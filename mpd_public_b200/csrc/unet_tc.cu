@@ -21,211 +21,10 @@
 // Global "TC layout" of an activation [B, C, L] (one tensor per plane):
 //   plane[tile][C/8][132][8]  bf16,  tile = b / SPT, row = (b % SPT) * (L + 4) + l + 2 ; halo / spare rows are
 //   zero forever. A K-chunk of a CTA's tile is ONE contiguous block -> one cp.async.bulk per plane.
-#include <cuda_bf16.h>
-#include <stdint.h>
-
-#include "common.cuh"
-#include "internal.h"
+#include "tc_common.cuh"
 
 namespace mpdb {
 
-constexpr int TC_STAGES = 5;  // 5 x 37,376 B in flight per SM: the wide layers are bound by L2->SM streaming latency
-constexpr int TC_THREADS = 512;  // 16 warps: warp w reads TMEM lane quarter (w & 3), column group (w >> 2)
-constexpr int TC_A_PLANE_BYTES = (TC_KCH / 8) * TC_RT * 16;  // 8448
-constexpr int TC_B_TAP_BYTES = (TC_KCH / 8) * TC_NT * 16;    // 2048
-constexpr int TC_STAGE_BYTES = 2 * TC_A_PLANE_BYTES + 2 * 5 * TC_B_TAP_BYTES;  // 37376
-constexpr int TC_TMEM_COLS = 128;  // main: [0,32) = hi*hi + lo*hi, [32,64) = hi*lo ; residual conv: [64,96), [96,128)
-
-// ---------------------------------------------------------------------------------------------------
-// PTX wrappers
-// ---------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-// Bounded wait: a protocol bug traps (visible CUDA error) instead of hanging the GPU.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    uint32_t done = 0;
-    const long long t0 = clock64();
-    while (true) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done)
-            : "r"(bar), "r"(parity)
-            : "memory");
-        if (done) break;
-        if (clock64() - t0 > 4000000000LL) __trap();
-    }
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-                 "l"(src), "r"(bytes), "r"(bar)
-                 : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-// Shared-memory matrix descriptor, K-major, SWIZZLE_NONE (canonical layout ((8,n),2):((1,SBO),LBO) in 16-byte
-// units): 8 rows of a core matrix are contiguous 16-byte rows; SBO = distance between 8-row groups; LBO =
-// distance between the two 8-element k-groups of one K=16 MMA. Bits: [0,14) addr>>4, [16,30) LBO>>4,
-// [32,46) SBO>>4, [46,48) version = 1 (Blackwell), [61,64) layout type = 0.
-__device__ __forceinline__ uint64_t tc_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
-    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
-    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
-    d |= (uint64_t)1 << 46;
-    return d;
-}
-// Instruction descriptor for kind::f16: c_format F32 (bit 4), a/b format BF16 (bits 7, 10), K-major A and B,
-// N >> 3 at bits [17,23), M >> 4 at bits [24,29).
-__host__ __device__ constexpr uint32_t tc_idesc(int M, int N) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
-__device__ __forceinline__ void tc_ld32(uint32_t taddr, float (&v)[32]) {
-    uint32_t r[32];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-__device__ __forceinline__ void tc_ld8(uint32_t taddr, float (&v)[8]) {
-    uint32_t r[8];
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-                 : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-__device__ __forceinline__ void split_bf16(float x, unsigned short& hi, unsigned short& lo) {
-    __nv_bfloat16 h = __float2bfloat16_rn(x);
-    __nv_bfloat16 l = __float2bfloat16_rn(x - __bfloat162float(h));
-    hi = __bfloat16_as_ushort(h);
-    lo = __bfloat16_as_ushort(l);
-}
-
-// Stores 8 consecutive output channels [c8, c8+8) of sample b at output position lo in the fp32 CM layout and (split
-// into bf16 hi/lo) in the TC layout of an activation with CO channels and L_out positions.
-__device__ __forceinline__ void tc_store_row(const TcConvArgs& a, const float (&v)[8], int b, int lo, int c8, int L_out) {
-    const int Lpo = L_out + 4;
-    if (a.out_cm != nullptr) {
-        float* op = a.out_cm + ((size_t)b * a.CO + c8) * Lpo + 2 + lo;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) op[(size_t)j * Lpo] = v[j];
-    }
-    if (a.out_hi != nullptr) {
-        const int SPTo = TC_RT / Lpo;
-        const int to = b / SPTo, so = b - to * SPTo;
-        const size_t o = (((size_t)to * (a.CO / 8) + c8 / 8) * TC_RT + (so * Lpo + lo + 2)) * 8;
-        unsigned short h[8], lo8[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) split_bf16(v[e], h[e], lo8[e]);
-        uint4 ph, pl;
-        ph.x = h[0] | ((uint32_t)h[1] << 16); ph.y = h[2] | ((uint32_t)h[3] << 16);
-        ph.z = h[4] | ((uint32_t)h[5] << 16); ph.w = h[6] | ((uint32_t)h[7] << 16);
-        pl.x = lo8[0] | ((uint32_t)lo8[1] << 16); pl.y = lo8[2] | ((uint32_t)lo8[3] << 16);
-        pl.z = lo8[4] | ((uint32_t)lo8[5] << 16); pl.w = lo8[6] | ((uint32_t)lo8[7] << 16);
-        *reinterpret_cast<uint4*>(a.out_hi + o) = ph;
-        *reinterpret_cast<uint4*>(a.out_lo + o) = pl;
-    }
-}
-
-// One-pass GroupNorm statistics + Mish on the 8 channels a thread owns (both tensor-core epilogues).
-//   level 0: every thread parks sum and sum-of-squares of its two 4-channel blocks: part[0][row][blk], part[1][row][blk]
-//   level 1: thread t < 2*SPT*8 owns one (moment, sample, block) column and adds its L rows in DOUBLE precision
-//            (fixed tree, four accumulators so the loads pipeline) -> cs[moment][sample][blk]
-//   level 2: one thread per (sample, group) combines the BPG block sums in double: mean = S/n, var = Q/n - mean^2,
-//            and publishes {mean, rstd}; everyone reads its two groups' values after a third barrier.
-// Accumulating the cross-row part in fp64 removes the cancellation of the one-pass formula; what remains is the fp32
-// rounding of the per-thread 4-term partials (~6e-8 * (1 + mean^2/var)), far below the split-bf16 MMA error. Three short
-// barriers, no redundant fp64 work. Deterministic and independent of how samples are tiled. BAR1: named barrier of the 512 epilogue
-// threads (fused kernel, where a producer warp is not part of the epilogue) instead of __syncthreads.
-template <int GS, bool BAR1>
-__device__ __forceinline__ void gn_mish8(float (&v)[8], bool valid, int r, int s, int cg, int tid, int SPT, int Lp, int L,
-                                         float* part, const float4& g0, const float4& g1, const float4& e0, const float4& e1,
-                                         long long* dbg = nullptr) {
-    constexpr int BPG = GS / 4;
-    float* part2 = part + 128 * 8;
-    double* cs = reinterpret_cast<double*>(part + 2 * 128 * 8);  // [2][12][8]
-    {
-        const float sA = (v[0] + v[1]) + (v[2] + v[3]), sB = (v[4] + v[5]) + (v[6] + v[7]);
-        const float qA = fmaf(v[0], v[0], fmaf(v[1], v[1], fmaf(v[2], v[2], v[3] * v[3])));
-        const float qB = fmaf(v[4], v[4], fmaf(v[5], v[5], fmaf(v[6], v[6], v[7] * v[7])));
-        part[r * 8 + cg * 2 + 0] = valid ? sA : 0.f;
-        part[r * 8 + cg * 2 + 1] = valid ? sB : 0.f;
-        part2[r * 8 + cg * 2 + 0] = valid ? qA : 0.f;
-        part2[r * 8 + cg * 2 + 1] = valid ? qB : 0.f;
-    }
-    if (BAR1) asm volatile("bar.sync 1, %0;" ::"n"(TC_THREADS) : "memory"); else __syncthreads();
-    if (dbg) dbg[8] = clock64();
-    if (tid < 2 * SPT * 8) {
-        const int m = tid >= SPT * 8 ? 1 : 0;
-        const int t2 = tid - m * SPT * 8;
-        const int ss = t2 >> 3, blk = t2 & 7;
-        const float* p = (m ? part2 : part) + (size_t)ss * Lp * 8 + blk;
-        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-#pragma unroll 2
-        for (int qq = 0; qq < L; qq += 4) {
-            a0 += (double)p[(qq + 0) * 8];
-            a1 += (double)p[(qq + 1) * 8];
-            a2 += (double)p[(qq + 2) * 8];
-            a3 += (double)p[(qq + 3) * 8];
-        }
-        cs[(m * 12 + ss) * 8 + blk] = (a0 + a1) + (a2 + a3);
-    }
-    if (BAR1) asm volatile("bar.sync 1, %0;" ::"n"(TC_THREADS) : "memory"); else __syncthreads();
-    if (dbg) dbg[9] = clock64();
-    // level 2: one thread per (sample, group) finishes the statistics in double and publishes {mean, rstd} as floats
-    constexpr int NG = TC_NT / GS;
-    float* stat = reinterpret_cast<float*>(cs + 2 * 12 * 8);  // [12][8][2]
-    if (tid < SPT * NG) {
-        const int ss = tid / NG, g = tid - ss * NG;
-        double S = 0.0, Q = 0.0;
-#pragma unroll
-        for (int k = 0; k < BPG; ++k) { S += cs[(0 * 12 + ss) * 8 + g * BPG + k]; Q += cs[(1 * 12 + ss) * 8 + g * BPG + k]; }
-        const double inv_n = 1.0 / (double)(GS * L);
-        const double m = S * inv_n;
-        const double var = fmax(Q * inv_n - m * m, 0.0);
-        stat[(ss * 8 + g) * 2 + 0] = (float)m;
-        stat[(ss * 8 + g) * 2 + 1] = 1.0f / sqrtf((float)var + 1e-5f);  // the cancellation-prone part is done; fp32 from here
-    }
-    if (BAR1) asm volatile("bar.sync 1, %0;" ::"n"(TC_THREADS) : "memory"); else __syncthreads();
-    const int sc = s < SPT ? s : 0;
-    const int gA = (cg * 8) / GS, gB = (cg * 8 + 4) / GS;
-    const float mA = stat[(sc * 8 + gA) * 2], rA = stat[(sc * 8 + gA) * 2 + 1];
-    const float mB = stat[(sc * 8 + gB) * 2], rB = stat[(sc * 8 + gB) * 2 + 1];
-    v[0] = mishf_fast((v[0] - mA) * (rA * g0.x) + e0.x); v[1] = mishf_fast((v[1] - mA) * (rA * g0.y) + e0.y);
-    v[2] = mishf_fast((v[2] - mA) * (rA * g0.z) + e0.z); v[3] = mishf_fast((v[3] - mA) * (rA * g0.w) + e0.w);
-    v[4] = mishf_fast((v[4] - mB) * (rB * g1.x) + e1.x); v[5] = mishf_fast((v[5] - mB) * (rB * g1.y) + e1.y);
-    v[6] = mishf_fast((v[6] - mB) * (rB * g1.z) + e1.z); v[7] = mishf_fast((v[7] - mB) * (rB * g1.w) + e1.w);
-}
 
 // ---------------------------------------------------------------------------------------------------
 // the kernel
@@ -488,33 +287,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv5_tc_kernel(TcConvArgs a) {
 constexpr int RTB_THREADS = TC_THREADS + 32;
 constexpr int RTB_TMEM_COLS = 256;  // conv0 [0,64), conv1 [64,128), residual conv [128,192)
 
-__device__ __forceinline__ void epi_sync() { asm volatile("bar.sync 1, %0;" ::"n"(TC_THREADS) : "memory"); }
-__device__ __forceinline__ uint32_t map_to_cta(uint32_t local_addr, uint32_t cta) {
-    uint32_t r;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(cta));
-    return r;
-}
-__device__ __forceinline__ void st_cluster_v4(uint32_t addr, uint4 v) {
-    asm volatile("st.shared::cluster.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t remote_bar) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote_bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
-    uint32_t done = 0;
-    const long long t0 = clock64();
-    while (true) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done)
-            : "r"(bar), "r"(parity)
-            : "memory");
-        if (done) break;
-        if (clock64() - t0 > 4000000000LL) __trap();
-    }
-}
 
 template <int GS, int NSTAGE>
 __global__ void __launch_bounds__(RTB_THREADS, 1) rtb_tc_kernel(TcRtbArgs args) {

@@ -151,6 +151,25 @@ class Engine:
                                               x.shape[0], _lib.stream_ptr(x.device)))
         return out
 
+    def unet_forward_uniform(self, x, t):
+        """The forward as the fused loop runs it: one timestep for the whole batch (make_timesteps,
+        diffusion_model_base.py:25-27), the loop's tensor-core policy, one cluster-kernel launch when supported."""
+        if not x.is_cuda:
+            raise RuntimeError("mpd_public_b200 runs on CUDA tensors only (no CPU fallback)")
+        x = x.contiguous().float()
+        self.sync_params()
+        out = torch.empty_like(x)
+        _lib.check(self.lib.mpdb_unet_forward_uniform(self.handle, _lib.fptr(x), int(t), _lib.fptr(out), x.shape[0],
+                                                      _lib.stream_ptr(x.device)))
+        return out
+
+    def mega_info(self, B):
+        """(in_use, samples per cluster, layers, A-buffer bytes, shared-memory bytes, reason if not in use)"""
+        g, n, a, sm = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()
+        why = C.create_string_buffer(256)
+        ok = self.lib.mpdb_engine_mega_info(self.handle, int(B), C.byref(g), C.byref(n), C.byref(a), C.byref(sm), why, 256)
+        return bool(ok), g.value, n.value, a.value, sm.value, why.value.decode()
+
     def p_mean(self, x, t):
         x, t = self._prep(x, t)
         self.sync_params()

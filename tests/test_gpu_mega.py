@@ -1,0 +1,63 @@
+"""Whole-forward cluster kernel (csrc/unet_mega.cu) — the UNet as ONE launch of 8-CTA clusters — against the
+per-layer tensor-core kernels (must agree bit for bit: same MMA sequence, same GroupNorm tree, fp32 residuals) and
+against the oracle (split-bf16 tolerance). Batch sizes cover full clusters, a ragged last cluster and B < 8."""
+import pytest
+import torch
+
+from oracle import mpd_oracle as O
+from tests.golden import cases as C
+from tests.test_gpu_parity import cuda_model, oracle_model, rel
+
+pytestmark = pytest.mark.gpu
+
+TOL_TC = 2e-4
+
+
+@pytest.mark.parametrize("case,batch", [("panda_opt1_h64", 8), ("panda_opt1_h64", 100), ("panda_opt1_h64", 3),
+                                        ("pm2d_opt0_h64", 37), ("pm2d_opt1_h64", 16), ("panda_opt1_h128", 9)])
+def test_mega_forward_matches_per_layer_and_oracle(case, batch):
+    model = cuda_model(case)
+    model.tensor_cores = "force"
+    eng = model._engine()
+    om = oracle_model(case)
+    d, h, opt, seed = C.UNET_CASES[case]
+    g = torch.Generator().manual_seed(1000 + batch)
+    x = torch.randn((batch, h, d), generator=g)
+    model.tensor_cores = "force"
+    try:
+        in_use, G, n_layers, a_bytes, smem, why = eng.mega_info(batch)
+        assert in_use, f"whole-forward kernel not in use for {case}: {why}"
+        assert smem <= 227 * 1024 and G in (1, 2, 4, 8)
+        for t in (0, 7, 23):
+            with torch.no_grad():
+                ref = O.unet_forward(om.sd, x, torch.full((batch,), t))
+            eng.set_option("mega", 1)
+            out_mega = eng.unet_forward_uniform(x.cuda(), t)
+            eng.set_option("mega", 0)
+            out_layers = eng.unet_forward_uniform(x.cuda(), t)
+            torch.cuda.synchronize()
+            assert torch.isfinite(out_mega).all()
+            print(f"[{case} B={batch} t={t}] mega vs oracle {rel(out_mega, ref):.2e}, per-layer vs oracle "
+                  f"{rel(out_layers, ref):.2e}, mega vs per-layer {rel(out_mega, out_layers):.2e}")
+            assert rel(out_mega, ref) < TOL_TC, (t, rel(out_mega, ref))
+            assert rel(out_layers, ref) < TOL_TC
+            assert rel(out_mega, out_layers) < TOL_TC
+    finally:
+        eng.set_option("mega", 1)
+        model.tensor_cores = "auto"
+
+
+def test_mega_is_batch_invariant():
+    """A trajectory's result does not depend on its cluster or its neighbours (bitwise)."""
+    model = cuda_model("panda_opt1_h64")
+    model.tensor_cores = "force"
+    eng = model._engine()
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn((29, 64, 14), generator=g).cuda()
+    model.tensor_cores = "force"
+    try:
+        a = eng.unet_forward_uniform(x, 3)
+        b = eng.unet_forward_uniform(x[11:18].contiguous(), 3)
+        assert torch.equal(a[11:18], b)
+    finally:
+        model.tensor_cores = "auto"

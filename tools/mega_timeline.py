@@ -1,0 +1,63 @@
+"""Per-layer clock64 timeline of the whole-forward cluster kernel (cluster 0, thread 0 of each CTA) + device time of the
+UNet body with the cluster kernel and with per-layer kernels. Debug / profiling aid (profiles/README.md)."""
+import argparse
+import ctypes as C
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+
+import bench
+from mpd_public_b200 import _lib
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--workload", default="cfg4")
+ap.add_argument("--batch", type=int, default=0)
+args = ap.parse_args()
+dev = torch.device("cuda", 0)
+model, guide, ds, prob, sd, n_grid = bench.build_problem(args.workload, dev)
+mid, H, B, opt, wc, ws = bench.WORKLOADS[args.workload]
+B = args.batch or B
+D = prob.robot.state_dim
+eng = model._engine()
+lib = _lib.lib()
+x = torch.randn((B, H, D), device=dev)
+eng.unet_forward_uniform(x, 5)  # loads the parameters into the engine
+print("mega_info (in_use, G, layers, a_bytes, smem, why):", eng.mega_info(B))
+
+
+def body_ms(reps=50):
+    ms, fl, n = C.c_float(), C.c_double(), C.c_int32()
+    _lib.check(lib.mpdb_profile_unet_body(eng.handle, _lib.fptr(x), 5, B, reps, C.byref(ms), C.byref(fl), C.byref(n),
+                                          _lib.stream_ptr(dev)))
+    return ms.value, fl.value, n.value
+
+
+for mega in (1, 0):
+    eng.set_option("mega", mega)
+    ms, fl, n = body_ms()
+    print(f"mega={mega}: UNet body {ms * 1e3:.1f} us per forward, {n} launches, {fl / ms / 1e9:.1f} TFLOP/s useful (stream-ordered launches)")
+eng.set_option("mega", 1)
+eng.set_option("mega_timeline", 1)
+for _ in range(3):
+    eng.unet_forward_uniform(x, 5)
+torch.cuda.synchronize()
+nl = 48
+buf = (C.c_int64 * (4 * 8 * nl))()
+desc = (C.c_int32 * (4 * nl))()
+n = lib.mpdb_engine_read_mega_timeline(eng.handle, buf, desc, nl)
+a = np.array(buf[:4 * 8 * n]).reshape(n, 8, 4).astype(np.float64)
+d = np.array(desc[:4 * n]).reshape(n, 4)
+t0 = a[0, :, 0].min()
+us = 1.0 / 1965.0
+names = {0: "input", 1: "conv5", 2: "down", 3: "up"}
+print("layer type    L   CO act | start(us)  wait->acc  acc->epi  epi->deliv  (rank 0)   | slowest rank: deliv-start")
+for l in range(n):
+    act = d[l, 3]
+    r0 = a[l, 0]
+    span = (a[l, :, 3] - a[l, :, 0]).max() * us
+    print(f"{l:3d} {names[d[l,0]]:6s} {d[l,1]:4d} {d[l,2]:4d} {act:3d} | {(r0[0]-t0)*us:8.2f} {(r0[1]-r0[0])*us if r0[1] else 0:9.2f} "
+          f"{(r0[2]-max(r0[1],r0[0]))*us:9.2f} {(r0[3]-r0[2])*us:10.2f}            | {span:8.2f}")
+print(f"total (first start -> last delivered): {(a[n-1,:,3].max() - t0) * us:.1f} us")
