@@ -494,7 +494,7 @@ static bool try_build_mega(mpdb_engine* e, int B, int G, std::string& why) {
             skip_elems += 2LL * n_clusters * g.MT * (bf.C / 8) * g.RT * 8;
             skips[op.in1] = sk;
         }
-    if (e->mega_skip) { cudaFree(e->mega_skip); cudaFree(e->mega_dbg); e->mega_skip = nullptr; }
+    if (e->mega_skip) { cudaFree(e->mega_skip); e->mega_skip = nullptr; }
     if (cudaMalloc(&e->mega_skip, sizeof(unsigned short) * (size_t)(skip_elems > 0 ? skip_elems : 8)) != cudaSuccess ||
         cudaMemset(e->mega_skip, 0, sizeof(unsigned short) * (size_t)(skip_elems > 0 ? skip_elems : 8)) != cudaSuccess) {
         why = "skip allocation failed"; cudaGetLastError(); return false;
@@ -773,8 +773,8 @@ extern "C" int mpdb_engine_set_option(mpdb_engine* e, const char* name, double v
         if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; e->graph_key.clear(); }
     } else if (n == "mega_timeline") {
         if (value != 0 && !e->mega_dbg) {
-            MPDB_CHECK_CUDA(cudaMalloc(&e->mega_dbg, sizeof(long long) * 4 * MEGA_CLUSTER * MEGA_MAX_LAYERS));
-            MPDB_CHECK_CUDA(cudaMemset(e->mega_dbg, 0, sizeof(long long) * 4 * MEGA_CLUSTER * MEGA_MAX_LAYERS));
+            MPDB_CHECK_CUDA(cudaMalloc(&e->mega_dbg, sizeof(long long) * MEGA_DBG * MEGA_CLUSTER * MEGA_MAX_LAYERS));
+            MPDB_CHECK_CUDA(cudaMemset(e->mega_dbg, 0, sizeof(long long) * MEGA_DBG * MEGA_CLUSTER * MEGA_MAX_LAYERS));
         } else if (value == 0 && e->mega_dbg) {
             cudaFree(e->mega_dbg); e->mega_dbg = nullptr;
         }
@@ -1293,7 +1293,7 @@ extern "C" int mpdb_engine_read_mega_timeline(mpdb_engine* e, int64_t* host_out,
     MPDB_CHECK_CUDA(cudaSetDevice(e->device));
     MPDB_CHECK_CUDA(cudaDeviceSynchronize());
     const int n = e->mega.n_layers < max_layers ? e->mega.n_layers : max_layers;
-    MPDB_CHECK_CUDA(cudaMemcpy(host_out, e->mega_dbg, sizeof(long long) * 4 * MEGA_CLUSTER * n, cudaMemcpyDeviceToHost));
+    MPDB_CHECK_CUDA(cudaMemcpy(host_out, e->mega_dbg, sizeof(long long) * MEGA_DBG * MEGA_CLUSTER * n, cudaMemcpyDeviceToHost));
     if (desc_out)
         for (int k = 0; k < n; ++k) {
             const MegaLayer& L = e->mega.layers[k];

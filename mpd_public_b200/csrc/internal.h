@@ -98,6 +98,7 @@ int launch_cm_to_tc(const float* cm, unsigned short* hi, unsigned short* lo, int
 // ---- whole-forward persistent cluster kernel (unet_mega.cu) ----
 constexpr int MEGA_MAX_LAYERS = 48;
 constexpr int MEGA_CLUSTER = 8;  // CTAs per cluster (portable maximum)
+constexpr int MEGA_DBG = 16;     // timeline stamps per (layer, CTA rank)
 enum MegaType { MG_INPUT = 0, MG_CONV5 = 1, MG_DOWN = 2, MG_UP = 3 };
 
 // One layer of the program. Input geometry: the A buffer holds C_a = 32 * n_a channels of G samples at length L as
@@ -130,7 +131,7 @@ struct MegaProgram {
     int t;        // uniform timestep (row of the time-conditioning tables)
     int a_bytes;  // size of the A buffer
     const float* x;  // trajectory [B][H][D] fp32
-    long long* dbg;  // optional timeline: [n_layers][8 ranks][4] clock64 stamps of thread 0 of cluster 0
+    long long* dbg;  // optional timeline: [n_layers][8 ranks][MEGA_DBG] clock64 stamps of cluster 0
 };
 size_t mega_smem_bytes(int a_bytes);
 int launch_unet_mega(const MegaProgram& P, cudaStream_t stream);

@@ -73,6 +73,20 @@ __device__ __forceinline__ void tc_mma_bf16_elect(uint32_t tmem_d, uint64_t a_de
         ::"r"(tmem_d), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// Same, descriptors given as (low word, high word): only the 14-bit start-address field in the low word changes between
+// the MMAs of a K-chunk, so the per-instruction arithmetic is one 32-bit add.
+__device__ __forceinline__ void tc_mma_bf16_elect32(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                                    uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t.reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %2};\n\t"
+        "mov.b64 db, {%3, %4};\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
+        ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 __device__ __forceinline__ void tc_commit_elect(uint32_t bar) {
     asm volatile(
         "{\n\t.reg .pred q;\n\t"
@@ -143,6 +157,21 @@ __device__ __forceinline__ void split_bf16(float x, unsigned short& hi, unsigned
     lo = __bfloat16_as_ushort(l);
 }
 
+// 8 fp32 values -> 8 bf16 "hi" and 8 bf16 "lo" (x ~ hi + lo), packed for 16-byte stores. Same values as split_bf16;
+// cvt.rn.bf16x2.f32 converts two at a time and bf16 -> fp32 is a shift.
+__device__ __forceinline__ void pack_split8(const float (&v)[8], uint4& ph, uint4& pl) {
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(h[k]) : "f"(v[2 * k + 1]), "f"(v[2 * k]));  // {hi16: v[2k+1], lo16: v[2k]}
+        const float r0 = v[2 * k] - __uint_as_float(h[k] << 16);
+        const float r1 = v[2 * k + 1] - __uint_as_float(h[k] & 0xffff0000u);
+        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(l[k]) : "f"(r1), "f"(r0));
+    }
+    ph = make_uint4(h[0], h[1], h[2], h[3]);
+    pl = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
 // Stores 8 consecutive output channels [c8, c8+8) of sample b at output position lo in the fp32 CM layout and (split
 // into bf16 hi/lo) in the TC layout of an activation with CO channels and L_out positions.
 __device__ __forceinline__ void tc_store_row(const TcConvArgs& a, const float (&v)[8], int b, int lo, int c8, int L_out) {
@@ -209,8 +238,24 @@ __device__ __forceinline__ void gn_mish8(float (&v)[8], bool valid, int r, int s
     }
     if (BAR1) asm volatile("bar.sync 1, %0;" ::"n"(TC_THREADS) : "memory"); else __syncthreads();
     if (dbg) dbg[8] = clock64();
-    if (tid < 2 * SPT * 8) {
-        // level 1: one thread per (moment, sample, block) adds the sample's L/4 row-group sums in double
+    if (SPT <= 8) {
+        // level 1: four threads per (moment, sample, block) column add the sample's L/4 row-group sums in double (thread j
+        // takes groups j, j+4, ...; the four partial sums meet in a fixed xor-shuffle tree)
+        const int t4 = tid >> 2, j = tid & 3;
+        const bool on = t4 < 2 * SPT * 8;
+        const int m = t4 >= SPT * 8 ? 1 : 0;
+        const int t2 = t4 - m * SPT * 8;
+        const int ss = t2 >> 3, blk = t2 & 7;
+        double a0 = 0.0;
+        if (on) {
+            const float* p = (m ? part2 : part) + (size_t)ss * (Lp >> 2) * 8 + blk;
+            for (int g = j; g < (L >> 2); g += 4) a0 += (double)p[g * 8];
+        }
+        a0 += __shfl_xor_sync(0xffffffffu, a0, 1);
+        a0 += __shfl_xor_sync(0xffffffffu, a0, 2);
+        if (on && j == 0) cs[(m * 12 + ss) * 8 + blk] = a0;
+    } else if (tid < 2 * SPT * 8) {
+        // level 1 (more than 8 samples per tile): one thread per (moment, sample, block) column
         const int m = tid >= SPT * 8 ? 1 : 0;
         const int t2 = tid - m * SPT * 8;
         const int ss = t2 >> 3, blk = t2 & 7;

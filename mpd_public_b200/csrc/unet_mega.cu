@@ -43,16 +43,6 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-__device__ __forceinline__ void pack_split8(const float (&v)[8], uint4& ph, uint4& pl) {
-    unsigned short h[8], lo8[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) split_bf16(v[e], h[e], lo8[e]);
-    ph.x = h[0] | ((uint32_t)h[1] << 16); ph.y = h[2] | ((uint32_t)h[3] << 16);
-    ph.z = h[4] | ((uint32_t)h[5] << 16); ph.w = h[6] | ((uint32_t)h[7] << 16);
-    pl.x = lo8[0] | ((uint32_t)lo8[1] << 16); pl.y = lo8[2] | ((uint32_t)lo8[3] << 16);
-    pl.z = lo8[4] | ((uint32_t)lo8[5] << 16); pl.w = lo8[6] | ((uint32_t)lo8[7] << 16);
-}
-
 __global__ void __launch_bounds__(MG_THREADS, 1) unet_mega_kernel(const __grid_constant__ MegaProgram P) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     unsigned char* abuf = smem_raw;                                   // current activation, operand layout
@@ -146,56 +136,86 @@ __global__ void __launch_bounds__(MG_THREADS, 1) unet_mega_kernel(const __grid_c
         {
             const uint32_t idesc = which == 0 ? tc_idesc(128, 2 * TC_NT) : tc_idesc(128, TC_NT);
             const uint32_t col0 = __shfl_sync(0xffffffffu, tmem_base, 0) + (which == 0 ? 0u : 2u * TC_NT);  // this issuer's main accumulator
+            // descriptor words: low = start address >> 4 | LBO >> 4 << 16 ; high = SBO >> 4 | version 1 << 14
+            constexpr uint32_t desc_hi = (128u >> 4) | (1u << 14);
+            constexpr uint32_t b_lo_fixed = ((2u * TC_NT * 16u) >> 4) << 16;  // weight tile: LBO = 64 rows x 16 B
             int ring_i = 0;
+            uint32_t my_acc_ph = 0;
+            if (which == 0 && lane < MEGA_CLUSTER) mbar_arrive_cluster(map_to_cta(a_free, (uint32_t)lane));  // layer 0 reads no A buffer
             for (int l = 1; l < P.n_layers; ++l) {
                 const MegaLayer& Ld = P.layers[l];
+                // layer parameters first, so that nothing but the issue itself follows the wait
+                const bool active = rank < Ld.MT * Ld.NC;
+                const int n_main = Ld.n_a + Ld.n_skip, n_res = Ld.n_res_a + Ld.n_res_skip;
+                const int n_a = Ld.n_a, n_res_a = Ld.n_res_a, type = Ld.type, zero_bytes = Ld.zero_bytes;
+                const uint32_t lbo = (uint32_t)Ld.RT * 16;
+                const uint32_t lo_plane = which == 1 ? (uint32_t)Ld.a_plane : 0u;
                 mbar_wait_cluster(a_full, (uint32_t)(l - 1) & 1u);  // operands of this layer have landed (cluster-wide)
                 tc_fence_after();
+                long long* mdbg = (P.dbg != nullptr && cluster == 0 && lane == 0 && which == 0) ? P.dbg + ((size_t)l * MEGA_CLUSTER + rank) * MEGA_DBG : nullptr;
+                if (mdbg) mdbg[8] = clock64();
                 if (which == 0 && lane == 0) *mma_progress = l;
-                __syncwarp();
-                if (rank >= Ld.MT * Ld.NC) continue;
-                const int n_main = Ld.n_a + Ld.n_skip, n_res = Ld.n_res_a + Ld.n_res_skip;
-                const uint32_t lbo = (uint32_t)Ld.RT * 16;
-                bool first0 = true, first1 = true;
-                for (int c = 0; c < n_main + n_res; ++c, ++ring_i) {
-                    const int sidx = ring_i % MG_STAGES;
-                    mbar_wait(full0 + 8 * sidx, (uint32_t)(ring_i / MG_STAGES) & 1u);
-                    tc_fence_after();
-                    const bool is_res = c >= n_main;
-                    const int cc = is_res ? c - n_main : c;
-                    const bool from_a = cc < (is_res ? Ld.n_res_a : Ld.n_a);
-                    const uint32_t st = stages_u32 + (uint32_t)sidx * TC_STAGE_BYTES;
-                    uint32_t aaddr = from_a ? abuf_u32 + (uint32_t)cc * (TC_KCH / 8) * lbo : st;
-                    if (which == 1) aaddr += from_a ? (uint32_t)Ld.a_plane : (uint32_t)TC_A_PLANE_BYTES;  // lo plane
-                    const uint64_t dA = tc_desc(aaddr, lbo, 128);
-                    const uint64_t dB = tc_desc(st + 2 * TC_A_PLANE_BYTES, 2 * TC_NT * 16, 128);  // rows [0,32) = W_hi, [32,64) = W_lo
-                    if (is_res) {
-#pragma unroll
-                        for (int kk = 0; kk < TC_KCH / 16; ++kk) {
-                            const uint64_t aofs = (uint64_t)((kk * 2 * lbo + 2 * 16) >> 4);  // 1x1 conv reads the centre row
-                            const uint64_t bofs = (uint64_t)((kk * 2 * (2 * TC_NT * 16)) >> 4);
-                            tc_mma_bf16_elect(col0 + 128, dA + aofs, dB + bofs, idesc, first1 ? 0u : 1u);
-                            first1 = false;
-                        }
-                    } else {
-                        const int ntaps = Ld.type == MG_CONV5 ? 5 : Ld.type == MG_DOWN ? 3 : 4;
-                        for (int tap = 0; tap < ntaps; ++tap) {
-                            // row shift of the tap (16-byte rows; +2 is the centre), see conv5_tc_kernel
-                            const int shift = Ld.type == MG_CONV5 ? tap : Ld.type == MG_DOWN ? tap + 1 : (tap == 0 ? 2 : tap == 1 ? 1 : tap == 2 ? 3 : 2);
-                            const bool second_acc = Ld.type == MG_UP && tap >= 2;
+                if (active) {
+                    uint32_t acc0 = 0u, acc1 = 0u;  // accumulate flags of the main and the second (residual / odd) accumulator
+                    for (int c = 0; c < n_main + n_res; ++c, ++ring_i) {
+                        const int sidx = ring_i % MG_STAGES;
+                        const bool is_res = c >= n_main;
+                        const int cc = is_res ? c - n_main : c;
+                        const bool from_a = cc < (is_res ? n_res_a : n_a);
+                        const uint32_t st = stages_u32 + (uint32_t)sidx * TC_STAGE_BYTES;
+                        const uint32_t aaddr = from_a ? abuf_u32 + (uint32_t)cc * (TC_KCH / 8) * lbo + lo_plane
+                                                      : st + (which == 1 ? (uint32_t)TC_A_PLANE_BYTES : 0u);
+                        const uint32_t a_lo = ((aaddr >> 4) & 0x3FFFu) | ((lbo >> 4) << 16);
+                        const uint32_t b_lo = (((st + 2 * TC_A_PLANE_BYTES) >> 4) & 0x3FFFu) | b_lo_fixed;  // rows [0,32) = W_hi, [32,64) = W_lo
+                        const uint32_t kstep_a = (2 * lbo) >> 4, kstep_b = (2 * (2 * TC_NT * 16)) >> 4, tap_b = (2 * TC_B_TAP_BYTES) >> 4;
+                        mbar_wait(full0 + 8 * sidx, (uint32_t)(ring_i / MG_STAGES) & 1u);
+                        tc_fence_after();
+                        if (mdbg && c == 0) mdbg[9] = clock64();
+                        if (is_res) {  // 1x1 residual conv: centre row (+2)
 #pragma unroll
                             for (int kk = 0; kk < TC_KCH / 16; ++kk) {
-                                const uint64_t aofs = (uint64_t)((kk * 2 * lbo + shift * 16) >> 4);
-                                const uint64_t bofs = (uint64_t)((tap * 2 * TC_B_TAP_BYTES + kk * 2 * (2 * TC_NT * 16)) >> 4);
-                                bool& first = second_acc ? first1 : first0;
-                                tc_mma_bf16_elect(col0 + (second_acc ? 128u : 0u), dA + aofs, dB + bofs, idesc, first ? 0u : 1u);
-                                first = false;
+                                tc_mma_bf16_elect32(col0 + 128, a_lo + kk * kstep_a + 2, desc_hi, b_lo + kk * kstep_b, desc_hi, idesc, acc1);
+                                acc1 = 1u;
+                            }
+                        } else if (type == MG_CONV5) {  // taps -2..2 -> row shifts 0..4
+#pragma unroll
+                            for (int tap = 0; tap < 5; ++tap)
+#pragma unroll
+                                for (int kk = 0; kk < TC_KCH / 16; ++kk) {
+                                    tc_mma_bf16_elect32(col0, a_lo + kk * kstep_a + tap, desc_hi, b_lo + tap * tap_b + kk * kstep_b, desc_hi, idesc, acc0);
+                                    acc0 = 1u;
+                                }
+                        } else if (type == MG_DOWN) {  // k3, pad 1: taps -1..1 -> row shifts 1..3
+#pragma unroll
+                            for (int tap = 0; tap < 3; ++tap)
+#pragma unroll
+                                for (int kk = 0; kk < TC_KCH / 16; ++kk) {
+                                    tc_mma_bf16_elect32(col0, a_lo + kk * kstep_a + tap + 1, desc_hi, b_lo + tap * tap_b + kk * kstep_b, desc_hi, idesc, acc0);
+                                    acc0 = 1u;
+                                }
+                        } else {  // ConvTranspose k4 s2, packed taps [W1, W3 | W0, W2]: even = W1 x[m] + W3 x[m-1], odd = W0 x[m+1] + W2 x[m]
+#pragma unroll
+                            for (int tap = 0; tap < 4; ++tap) {
+                                const int shift = tap == 0 ? 2 : tap == 1 ? 1 : tap == 2 ? 3 : 2;
+#pragma unroll
+                                for (int kk = 0; kk < TC_KCH / 16; ++kk) {
+                                    if (tap < 2) { tc_mma_bf16_elect32(col0, a_lo + kk * kstep_a + shift, desc_hi, b_lo + tap * tap_b + kk * kstep_b, desc_hi, idesc, acc0); acc0 = 1u; }
+                                    else { tc_mma_bf16_elect32(col0 + 128, a_lo + kk * kstep_a + shift, desc_hi, b_lo + tap * tap_b + kk * kstep_b, desc_hi, idesc, acc1); acc1 = 1u; }
+                                }
                             }
                         }
+                        tc_commit_elect(empty0 + 8 * sidx);  // the stage is free when both issuers' MMAs that read it have retired
                     }
-                    tc_commit_elect(empty0 + 8 * sidx);  // the stage is free when both issuers' MMAs that read it have retired
+                    tc_commit_elect(acc_done);
+                    if (mdbg) mdbg[10] = clock64();
                 }
-                tc_commit_elect(acc_done);
+                if (which == 0) {
+                    // a_free: this CTA's MMAs of layer l have retired (and, when the layout changes, the epilogue warps have
+                    // cleared the A buffer) -> peers may overwrite it. Sent from here, off the epilogue's critical path.
+                    if (active) { mbar_wait(acc_done, my_acc_ph); my_acc_ph ^= 1u; }
+                    if (zero_bytes > 0) asm volatile("bar.sync 2, %0;" ::"n"(TC_THREADS + 32) : "memory");
+                    if (lane < MEGA_CLUSTER) mbar_arrive_cluster(map_to_cta(a_free, (uint32_t)lane));
+                }
             }
         }
         __syncwarp();
@@ -215,7 +235,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) unet_mega_kernel(const __grid_c
         const MegaLayer& Ld = P.layers[l];
         // outputs of the previous layer have landed everywhere (also keeps idle CTAs in lock step)
         if (l > 0) mbar_wait_cluster(a_full, (uint32_t)(l - 1) & 1u);
-        long long* dbg = (P.dbg != nullptr && cluster == 0 && tid == 0) ? P.dbg + ((size_t)l * MEGA_CLUSTER + rank) * 4 : nullptr;
+        long long* dbg = (P.dbg != nullptr && cluster == 0 && tid == 0) ? P.dbg + ((size_t)l * MEGA_CLUSTER + rank) * MEGA_DBG : nullptr;
         if (dbg) dbg[0] = clock64();  // inputs landed
         const bool active = rank < Ld.MT * Ld.NC;
         const int mt = rank / Ld.NC, nc = rank - mt * Ld.NC;
@@ -236,7 +256,6 @@ __global__ void __launch_bounds__(MG_THREADS, 1) unet_mega_kernel(const __grid_c
                 for (int e = 0; e < 8; ++e)
                     if (cg * 8 + e < P.D) v[e] = xp[cg * 8 + e];
             }
-            if (tid < MEGA_CLUSTER) mbar_arrive_cluster(map_to_cta(a_free, (uint32_t)tid));
         } else {
             float4 pb0 = z4, pb1 = z4, pg0 = z4, pg1 = z4, pe0 = z4, pe1 = z4, pc0 = z4, pc1 = z4, pr0 = z4, pr1 = z4;
             float rv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -283,14 +302,15 @@ __global__ void __launch_bounds__(MG_THREADS, 1) unet_mega_kernel(const __grid_c
                     for (int j = 0; j < 8; ++j) rv[j] = (rv[j] + rv3[j]) + rv2[j];
                 }
                 tc_fence_before();
+                if (dbg) dbg[4] = clock64();  // accumulators in registers
             }
-            // this CTA no longer reads its A buffer: clear it if the next layer uses another layout, then tell the cluster
+            // this CTA no longer reads its A buffer: clear it if the next layer uses another layout (issuer warp 0 then tells the cluster)
             if (Ld.zero_bytes > 0) {
                 for (int i = tid; i < Ld.zero_bytes / 16; i += TC_THREADS) reinterpret_cast<uint4*>(abuf)[i] = make_uint4(0u, 0u, 0u, 0u);
                 asm volatile("fence.proxy.async;" ::: "memory");
-                epi_sync();
+                asm volatile("bar.arrive 2, %0;" ::"n"(TC_THREADS + 32) : "memory");  // issuer warp 0 sends a_free once all 16 warps are here
             }
-            if (tid < MEGA_CLUSTER) mbar_arrive_cluster(map_to_cta(a_free, (uint32_t)tid));  // one lane per destination CTA
+            if (dbg) dbg[5] = clock64();
 
             if (active) {
                 v[0] += pb0.x; v[1] += pb0.y; v[2] += pb0.z; v[3] += pb0.w;
@@ -300,10 +320,10 @@ __global__ void __launch_bounds__(MG_THREADS, 1) unet_mega_kernel(const __grid_c
                     w[4] += pb1.x; w[5] += pb1.y; w[6] += pb1.z; w[7] += pb1.w;
                 } else if (Ld.type == MG_CONV5) {
                     switch (Ld.gs) {
-                        case 4: gn_mish8<4, true>(v, valid, r, s, cg, tid, Ld.SPT, Lp, Ld.L, part, pg0, pg1, pe0, pe1); break;
-                        case 8: gn_mish8<8, true>(v, valid, r, s, cg, tid, Ld.SPT, Lp, Ld.L, part, pg0, pg1, pe0, pe1); break;
-                        case 16: gn_mish8<16, true>(v, valid, r, s, cg, tid, Ld.SPT, Lp, Ld.L, part, pg0, pg1, pe0, pe1); break;
-                        default: gn_mish8<32, true>(v, valid, r, s, cg, tid, Ld.SPT, Lp, Ld.L, part, pg0, pg1, pe0, pe1); break;
+                        case 4: gn_mish8<4, true>(v, valid, r, s, cg, tid, Ld.SPT, Lp, Ld.L, part, pg0, pg1, pe0, pe1, dbg ? dbg + 4 : nullptr); break;
+                        case 8: gn_mish8<8, true>(v, valid, r, s, cg, tid, Ld.SPT, Lp, Ld.L, part, pg0, pg1, pe0, pe1, dbg ? dbg + 4 : nullptr); break;
+                        case 16: gn_mish8<16, true>(v, valid, r, s, cg, tid, Ld.SPT, Lp, Ld.L, part, pg0, pg1, pe0, pe1, dbg ? dbg + 4 : nullptr); break;
+                        default: gn_mish8<32, true>(v, valid, r, s, cg, tid, Ld.SPT, Lp, Ld.L, part, pg0, pg1, pe0, pe1, dbg ? dbg + 4 : nullptr); break;
                     }
                     v[0] += pc0.x; v[1] += pc0.y; v[2] += pc0.z; v[3] += pc0.w;
                     v[4] += pc1.x; v[5] += pc1.y; v[6] += pc1.z; v[7] += pc1.w;
@@ -325,6 +345,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) unet_mega_kernel(const __grid_c
         // ===== deliver: every CTA that consumes these channels gets them in its A buffer (operand layout) =====
         if (dbg) dbg[2] = clock64();  // epilogue arithmetic done
         mbar_wait_cluster(a_free, (uint32_t)l & 1u);
+        if (dbg) dbg[6] = clock64();  // every CTA's MMAs of this layer have retired
         if (valid) {
             if (Ld.oNC > 0) {
                 const int n_out = Ld.type == MG_UP ? 2 : 1;
@@ -361,6 +382,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) unet_mega_kernel(const __grid_c
                 for (int j = 0; j < 8; ++j) op[(size_t)j * Lp] = v[j];
             }
         }
+        if (dbg) dbg[7] = clock64();  // stores issued
         asm volatile("fence.proxy.async;" ::: "memory");  // generic-proxy stores -> tensor core / bulk copies of the consumers
         if (dbg) dbg[3] = clock64();  // outputs delivered
         __syncwarp();

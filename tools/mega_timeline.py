@@ -45,10 +45,11 @@ for _ in range(3):
     eng.unet_forward_uniform(x, 5)
 torch.cuda.synchronize()
 nl = 48
-buf = (C.c_int64 * (4 * 8 * nl))()
+ND = 16
+buf = (C.c_int64 * (ND * 8 * nl))()
 desc = (C.c_int32 * (4 * nl))()
 n = lib.mpdb_engine_read_mega_timeline(eng.handle, buf, desc, nl)
-a = np.array(buf[:4 * 8 * n]).reshape(n, 8, 4).astype(np.float64)
+a = np.array(buf[:ND * 8 * n]).reshape(n, 8, ND).astype(np.float64)
 d = np.array(desc[:4 * n]).reshape(n, 4)
 t0 = a[0, :, 0].min()
 us = 1.0 / 1965.0
@@ -60,4 +61,9 @@ for l in range(n):
     span = (a[l, :, 3] - a[l, :, 0]).max() * us
     print(f"{l:3d} {names[d[l,0]]:6s} {d[l,1]:4d} {d[l,2]:4d} {act:3d} | {(r0[0]-t0)*us:8.2f} {(r0[1]-r0[0])*us if r0[1] else 0:9.2f} "
           f"{(r0[2]-max(r0[1],r0[0]))*us:9.2f} {(r0[3]-r0[2])*us:10.2f}            | {span:8.2f}")
+print("\nfine stamps, rank 0 (us after 'inputs landed'): mma_wake  w_ready  mma_issued | acc_done  tmem_ld  a_free_sent  gn_bar1  gn_bar2  epi_done  a_free_ok  stores  fenced")
+for l in range(n):
+    r0 = a[l, 0]
+    rel = lambda k: (r0[k] - r0[0]) * us if r0[k] else float('nan')
+    print(f"{l:3d} {names[d[l,0]]:6s} {d[l,1]:4d} {d[l,2]:4d} | {rel(8):7.2f} {rel(9):7.2f} {rel(10):7.2f} | {rel(1):7.2f} {rel(4):7.2f} {rel(5):7.2f} {rel(12):7.2f} {rel(13):7.2f} {rel(2):7.2f} {rel(6):7.2f} {rel(7):7.2f} {rel(3):7.2f}")
 print(f"total (first start -> last delivered): {(a[n-1,:,3].max() - t0) * us:.1f} us")
