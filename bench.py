@@ -403,11 +403,32 @@ def main():
         except Exception:
             pass
         tr_conv = traffic.get("conv5_tc_kernel", {}).get("bytes_per_launch") if tcm.any() else None
+        mega_on, mega_G, mega_layers, mega_a, mega_smem, _why = eng.mega_info(B)
+        per_layer_detail = None
+        if mega_on and tcm.any():
+            # the loop runs the UNet as ONE launch of the whole-forward cluster kernel: time that launch
+            bms, bfl, bn = C.c_float(), C.c_double(), C.c_int32()
+            _lib.check(lib.mpdb_profile_unet_body(eng.handle, _lib.fptr(x0), 5, B, 50, C.byref(bms), C.byref(bfl), C.byref(bn),
+                                                  _lib.stream_ptr(device)))
+            per_layer_detail = {"unet_forward_ms_per_layer_kernels": fwd_ms, "tflops_per_layer_kernels": ach_tf}
+            dom_ms, dom_flops, fwd_ms = float(bms.value), float(bfl.value), float(bms.value)
+            ach_tf = dom_flops / (dom_ms * 1e-3) / 1e12
+            kname = (f"mpdb::unet_mega_kernel (whole TemporalUnet forward in ONE launch: {(B + mega_G - 1) // mega_G} clusters of 8 CTAs x "
+                     f"{mega_G} trajectories, {mega_layers} layers; tcgen05.mma kind::f16 split-bf16 x3 from two issuer warps, TMEM "
+                     "accumulators, activations exchanged through distributed shared memory, weights via cp.async.bulk ring; "
+                     f"{mega_smem} B shared memory per CTA), {bn.value} launch per UNet forward")
+            note = ("achieved = algorithmic (useful) 2*MAC FLOPs of one forward / CUDA-event time of the launch; the tensor pipe "
+                    "issues 3x that (hi*hi + lo*hi + hi*lo). At 100 trajectories per GPU the forward is a chain of 40 dependent "
+                    "layers per cluster and is latency-bound (profiles/README.md: per-layer timeline)")
+            tr_conv = traffic.get("unet_mega_kernel", {}).get("bytes_per_launch")
         roofline = {"kernel": kname, "bound": "tensor", "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s",
                     "frac": ach_tf / peak_tf, "traffic": tr_conv, "peak_source": peak_src, "note": note,
                     "issued_tflops": ach_tf * (3 if tcm.any() else 1),
                     "unet_forward_ms": fwd_ms, "unet_flops_per_trajectory_per_forward": flops_traj,
                     "per_launch_us": [round(float(v) * 1e3, 2) for v in ms], "per_launch_mode": [int(v) for v in md]}
+        if per_layer_detail:
+            roofline.update(per_layer_detail)
+            roofline["per_launch_note"] = "per_launch_us / per_launch_mode describe the per-layer kernels (fallback path), not the cluster kernel"
         # guide kernel (HBM-bound by construction; at B=100 it is latency-bound)
         gms = C.c_float()
         xg = noise[1].clamp(-1, 1).contiguous()

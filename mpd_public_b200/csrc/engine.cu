@@ -583,8 +583,21 @@ static bool try_build_mega(mpdb_engine* e, int B, int G, std::string& why) {
 static void build_mega(mpdb_engine* e, int B) {
     e->mega_ok = false;
     const int Gs[4] = {8, 4, 2, 1};
-    for (int G : Gs)
-        if (try_build_mega(e, B, G, e->mega_why)) { e->mega_ok = true; e->mega_why.clear(); return; }
+    for (int G : Gs) {
+        if (!try_build_mega(e, B, G, e->mega_why)) continue;
+        // one wave only: with more clusters than can be resident at once the latency chain runs twice and the per-layer
+        // kernels are faster (measured: 128 trajectories = 16 clusters = 2 waves = 543 us vs 358 us). use_mega = 2 overrides.
+        const int n_clusters = (B + G - 1) / G;
+        const int max_clusters = mega_max_active_clusters(e->mega.a_bytes);
+        if (e->use_mega != 2 && n_clusters > max_clusters) {
+            e->mega_why = "batch needs " + std::to_string(n_clusters) + " clusters of " + std::to_string(G) + " trajectories, " +
+                          std::to_string(max_clusters) + " fit in one wave";
+            return;
+        }
+        e->mega_ok = true;
+        e->mega_why.clear();
+        return;
+    }
 }
 
 // Can ops[i], ops[i+1] (the two Conv1dBlocks of a ResidualTemporalBlock) run as one cluster-fused launch?
@@ -780,7 +793,9 @@ extern "C" int mpdb_engine_set_option(mpdb_engine* e, const char* name, double v
         }
         if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; e->graph_key.clear(); }
     } else if (n == "mega") {
-        e->use_mega = value != 0;
+        MPDB_REQUIRE(value == 0 || value == 1 || value == 2, "mega must be 0 (off), 1 (when the batch fits one wave) or 2 (always)");
+        if ((e->use_mega == 2) != (value == 2)) e->work_batch = 0;  // re-plan: the one-wave rule is applied when the program is built
+        e->use_mega = (int)value;
         if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; e->graph_key.clear(); }
     } else if (n == "alias_buffers") {
         if (e->alias_buffers != (value != 0)) {

@@ -15,6 +15,8 @@
 
 #include <vector>
 
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "internal.h"
 
@@ -115,46 +117,77 @@ static GuideDev make_dev(const mpdb_guide_config& c) {
 // Forward kinematics of one interpolated row: joint origins (3 x 7), joint axes (3 x 7) and collision-sphere centres
 // (3 x n_spheres) into per-row scratch with stride FK_ROWS. Panda chain: T_i = T_{i-1} Trans(xyz_i) Rx(roll_i) Rz(q_i)
 // (SURVEY Appendix E); point mass: centre = q.
-__device__ __forceinline__ void fk_row(const GuideDev& g, const float (&qv)[7], float* sc, float* cen) {
-    if (g.robot_kind == 1) {
-        float R[9] = {1.f, 0.f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f, 1.f};  // row-major
-        float o[3] = {0.f, 0.f, 0.f};
-#pragma unroll 1
-        for (int j = 0; j < 7; ++j) {
+__device__ __forceinline__ void fk_chain(const GuideDev& g, const float (&sq)[7], const float (&cq)[7], float* sc, float* cen) {
+    float R[9] = {1.f, 0.f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f, 1.f};  // row-major
+    float o[3] = {0.f, 0.f, 0.f};
 #pragma unroll
-            for (int r3 = 0; r3 < 3; ++r3)
-                o[r3] += R[r3 * 3 + 0] * g.joint_xyz[j][0] + R[r3 * 3 + 1] * g.joint_xyz[j][1] + R[r3 * 3 + 2] * g.joint_xyz[j][2];
-            float sq, cq;
-            sincosf(qv[j], &sq, &cq);
-            const float cr = g.joint_cr[j], sr = g.joint_sr[j];
-#pragma unroll
-            for (int r3 = 0; r3 < 3; ++r3) {
-                float c0 = R[r3 * 3 + 0], c1 = R[r3 * 3 + 1], c2 = R[r3 * 3 + 2];
-                float a1 = c1 * cr + c2 * sr;   // (R Rx) column 1
-                float a2 = -c1 * sr + c2 * cr;  // (R Rx) column 2
-                R[r3 * 3 + 0] = cq * c0 + sq * a1;
-                R[r3 * 3 + 1] = -sq * c0 + cq * a1;
-                R[r3 * 3 + 2] = a2;
-            }
-#pragma unroll
-            for (int r3 = 0; r3 < 3; ++r3) {
-                sc[(j * 3 + r3) * FK_ROWS] = o[r3];
-                sc[(21 + j * 3 + r3) * FK_ROWS] = R[r3 * 3 + 2];  // joint axis = third column
-            }
-            for (int s = 0; s < g.n_spheres; ++s)
-                if (g.sphere_frame[s] == j + 1)
-                    for (int r3 = 0; r3 < 3; ++r3)
-                        cen[(s * 3 + r3) * FK_ROWS] = o[r3] + R[r3 * 3 + 0] * g.sphere_off[s][0] +
-                                                      R[r3 * 3 + 1] * g.sphere_off[s][1] + R[r3 * 3 + 2] * g.sphere_off[s][2];
-        }
+    for (int j = 0; j < 7; ++j) {
 #pragma unroll
         for (int r3 = 0; r3 < 3; ++r3)
-            o[r3] += R[r3 * 3 + 0] * g.flange[0] + R[r3 * 3 + 1] * g.flange[1] + R[r3 * 3 + 2] * g.flange[2];
+            o[r3] += R[r3 * 3 + 0] * g.joint_xyz[j][0] + R[r3 * 3 + 1] * g.joint_xyz[j][1] + R[r3 * 3 + 2] * g.joint_xyz[j][2];
+        const float cr = g.joint_cr[j], sr = g.joint_sr[j];
+#pragma unroll
+        for (int r3 = 0; r3 < 3; ++r3) {
+            float c0 = R[r3 * 3 + 0], c1 = R[r3 * 3 + 1], c2 = R[r3 * 3 + 2];
+            float a1 = c1 * cr + c2 * sr;   // (R Rx) column 1
+            float a2 = -c1 * sr + c2 * cr;  // (R Rx) column 2
+            R[r3 * 3 + 0] = cq[j] * c0 + sq[j] * a1;
+            R[r3 * 3 + 1] = -sq[j] * c0 + cq[j] * a1;
+            R[r3 * 3 + 2] = a2;
+        }
+#pragma unroll
+        for (int r3 = 0; r3 < 3; ++r3) {
+            sc[(j * 3 + r3) * FK_ROWS] = o[r3];
+            sc[(21 + j * 3 + r3) * FK_ROWS] = R[r3 * 3 + 2];  // joint axis = third column
+        }
         for (int s = 0; s < g.n_spheres; ++s)
-            if (g.sphere_frame[s] == 8)
+            if (g.sphere_frame[s] == j + 1)
                 for (int r3 = 0; r3 < 3; ++r3)
-                    cen[(s * 3 + r3) * FK_ROWS] = o[r3] + R[r3 * 3 + 0] * g.sphere_off[s][0] + R[r3 * 3 + 1] * g.sphere_off[s][1] +
-                                                  R[r3 * 3 + 2] * g.sphere_off[s][2];
+                    cen[(s * 3 + r3) * FK_ROWS] = o[r3] + R[r3 * 3 + 0] * g.sphere_off[s][0] +
+                                                  R[r3 * 3 + 1] * g.sphere_off[s][1] + R[r3 * 3 + 2] * g.sphere_off[s][2];
+    }
+#pragma unroll
+    for (int r3 = 0; r3 < 3; ++r3)
+        o[r3] += R[r3 * 3 + 0] * g.flange[0] + R[r3 * 3 + 1] * g.flange[1] + R[r3 * 3 + 2] * g.flange[2];
+    for (int s = 0; s < g.n_spheres; ++s)
+        if (g.sphere_frame[s] == 8)
+            for (int r3 = 0; r3 < 3; ++r3)
+                cen[(s * 3 + r3) * FK_ROWS] = o[r3] + R[r3 * 3 + 0] * g.sphere_off[s][0] + R[r3 * 3 + 1] * g.sphere_off[s][1] +
+                                              R[r3 * 3 + 2] * g.sphere_off[s][2];
+}
+
+// One matrix row of the chain: row r3 of R and component r3 of the origin depend only on row r3 of the previous frame,
+// so three threads per interpolated row run the chain independently (3x shorter dependency chain).
+__device__ __forceinline__ void fk_chain_row(const GuideDev& g, int r3, const float (&sq)[7], const float (&cq)[7], float* sc, float* cen) {
+    float c0 = r3 == 0 ? 1.f : 0.f, c1 = r3 == 1 ? 1.f : 0.f, c2 = r3 == 2 ? 1.f : 0.f;  // row r3 of R
+    float o = 0.f;
+#pragma unroll
+    for (int j = 0; j < 7; ++j) {
+        o += c0 * g.joint_xyz[j][0] + c1 * g.joint_xyz[j][1] + c2 * g.joint_xyz[j][2];
+        const float cr = g.joint_cr[j], sr = g.joint_sr[j];
+        const float a1 = c1 * cr + c2 * sr;   // (R Rx) column 1
+        const float a2 = -c1 * sr + c2 * cr;  // (R Rx) column 2
+        const float n0 = cq[j] * c0 + sq[j] * a1;
+        const float n1 = -sq[j] * c0 + cq[j] * a1;
+        c0 = n0; c1 = n1; c2 = a2;
+        sc[(j * 3 + r3) * FK_ROWS] = o;
+        sc[(21 + j * 3 + r3) * FK_ROWS] = c2;  // joint axis = third column
+        for (int s = 0; s < g.n_spheres; ++s)
+            if (g.sphere_frame[s] == j + 1)
+                cen[(s * 3 + r3) * FK_ROWS] = o + c0 * g.sphere_off[s][0] + c1 * g.sphere_off[s][1] + c2 * g.sphere_off[s][2];
+    }
+    o += c0 * g.flange[0] + c1 * g.flange[1] + c2 * g.flange[2];
+    for (int s = 0; s < g.n_spheres; ++s)
+        if (g.sphere_frame[s] == 8)
+            cen[(s * 3 + r3) * FK_ROWS] = o + c0 * g.sphere_off[s][0] + c1 * g.sphere_off[s][1] + c2 * g.sphere_off[s][2];
+}
+
+__device__ __forceinline__ void fk_row(const GuideDev& g, const float (&qv)[7], float* sc, float* cen) {
+    if (g.robot_kind == 1) {
+        float sq[7], cq[7];
+#pragma unroll
+        for (int j = 0; j < 7; ++j) sincosf(qv[j], &sq[j], &cq[j]);
+        fk_chain(g, sq, cq, sc, cen);
     } else {
         for (int s = 0; s < g.n_spheres; ++s)
             for (int r3 = 0; r3 < 3; ++r3) cen[(s * 3 + r3) * FK_ROWS] = r3 < g.ws_dim ? qv[r3] : 0.f;
@@ -211,6 +244,8 @@ __global__ void __launch_bounds__(GUIDE_THREADS) guide_step_kernel(GuideDev g, G
     int* i0s = reinterpret_cast<int*>(w1s + NI);    // [NI] lower tap
     float* fk = reinterpret_cast<float*>(i0s + NI); // [(42 + 3*n_spheres)][FK_ROWS] FK scratch of one pass
 
+    long long* dbg = (a.dbg != nullptr && blockIdx.x == 0 && threadIdx.x == 0) ? a.dbg : nullptr;
+    if (dbg) dbg[0] = clock64();
     pdl_launch_dependents();
     pdl_wait();  // x and the clip flag come from the previous kernel
     const int flag = a.flag_in ? *a.flag_in : 0;
@@ -225,6 +260,7 @@ __global__ void __launch_bounds__(GUIDE_THREADS) guide_step_kernel(GuideDev g, G
         tot[i] = 0.f;
     }
     __syncthreads();
+    if (dbg) dbg[1] = clock64();  // trajectory loaded + unnormalised
 
     // ---------------- collision costs on the interpolated trajectory ----------------
     // Rows are processed in passes of FK_ROWS: (1) FK_ROWS threads interpolate + run the kinematic chain and park joint
@@ -233,24 +269,49 @@ __global__ void __launch_bounds__(GUIDE_THREADS) guide_step_kernel(GuideDev g, G
     if (n_coll > 0) {
         const float ratio = NI > 1 ? (float)(H - 1) / (float)(NI - 1) : 0.f;  // align_corners=True
         for (int ibase = 0; ibase < NI; ibase += FK_ROWS) {
-            if (tid < FK_ROWS && ibase + tid < NI) {
-                const int i = ibase + tid;
+            // (1a) all threads: interpolated joint value of (row, joint) and its sine / cosine -> scratch [2][7][FK_ROWS]
+            float* sc_sin = fk + (42 + 3 * g.n_spheres) * FK_ROWS;
+            float* sc_cos = sc_sin + 7 * FK_ROWS;
+            for (int item = tid; item < FK_ROWS * 7; item += NTH) {
+                const int il = item % FK_ROWS, k = item / FK_ROWS;
+                const int i = ibase + il;
+                if (i >= NI) continue;
                 float r = ratio * (float)i;
                 int i0 = (int)r;
                 if (i0 > H - 1) i0 = H - 1;
                 float l1 = fminf(fmaxf(r - (float)i0, 0.f), 1.f);
                 float l0 = 1.f - l1;
                 int i1 = i0 + (i0 < H - 1 ? 1 : 0);
-                i0s[i] = i0;
-                w1s[i] = l1;
-                float qv[7];
-#pragma unroll
-                for (int k = 0; k < 7; ++k)
-                    qv[k] = k < q ? __fadd_rn(__fmul_rn(l0, xu[i0 * D + k]), __fmul_rn(l1, xu[i1 * D + k])) : 0.f;
-
-                fk_row(g, qv, fk + tid, fk + tid + 42 * FK_ROWS);
+                if (k == 0) { i0s[i] = i0; w1s[i] = l1; }
+                const float qk = k < q ? __fadd_rn(__fmul_rn(l0, xu[i0 * D + k]), __fmul_rn(l1, xu[i1 * D + k])) : 0.f;
+                if (g.robot_kind == 1) {
+                    float sv, cv;
+                    sincosf(qk, &sv, &cv);
+                    sc_sin[k * FK_ROWS + il] = sv;
+                    sc_cos[k * FK_ROWS + il] = cv;
+                } else {
+                    sc_sin[k * FK_ROWS + il] = qk;  // point mass: the interpolated coordinate itself
+                }
             }
             __syncthreads();
+            // (1b) three threads per row (one per matrix row): the kinematic chain on the precomputed sines / cosines
+            if (g.robot_kind == 1) {
+                const int il = tid % FK_ROWS, r3 = tid / FK_ROWS;
+                if (r3 < 3 && ibase + il < NI) {
+                    float sq[7], cq[7];
+#pragma unroll
+                    for (int k = 0; k < 7; ++k) { sq[k] = sc_sin[k * FK_ROWS + il]; cq[k] = sc_cos[k * FK_ROWS + il]; }
+                    fk_chain_row(g, r3, sq, cq, fk + il, fk + il + 42 * FK_ROWS);
+                }
+            } else if (tid < FK_ROWS && ibase + tid < NI) {
+                float* cen = fk + tid + 42 * FK_ROWS;
+                {
+                    for (int sp = 0; sp < g.n_spheres; ++sp)
+                        for (int r3 = 0; r3 < 3; ++r3) cen[(sp * 3 + r3) * FK_ROWS] = r3 < g.ws_dim ? sc_sin[r3 * FK_ROWS + tid] : 0.f;
+                }
+            }
+            __syncthreads();
+            if (dbg) dbg[2] = clock64();  // interpolation + kinematic chain
 
             // (row, sphere group) items: thread -> row = item % FK_ROWS, group = item / FK_ROWS
             for (int item = tid; item < FK_ROWS * NSG; item += NTH) {
@@ -282,8 +343,10 @@ __global__ void __launch_bounds__(GUIDE_THREADS) guide_step_kernel(GuideDev g, G
                             const float gx = -tg[u][0], gy = -tg[u][1], gz = -tg[u][2];  // d cost / d p
                             if (g.robot_kind == 1) {
                                 const float p0 = cen[(s * 3 + 0) * FK_ROWS], p1 = cen[(s * 3 + 1) * FK_ROWS], p2 = cen[(s * 3 + 2) * FK_ROWS];
-                                int nj = g.sphere_frame[s] < 7 ? g.sphere_frame[s] : 7;
-                                for (int j = 0; j < nj; ++j) {
+                                const int nj = g.sphere_frame[s] < 7 ? g.sphere_frame[s] : 7;
+#pragma unroll
+                                for (int j = 0; j < 7; ++j) {
+                                    if (j >= nj) break;
                                     float rx = p0 - sc[(j * 3 + 0) * FK_ROWS], ry = p1 - sc[(j * 3 + 1) * FK_ROWS],
                                           rz = p2 - sc[(j * 3 + 2) * FK_ROWS];
                                     float zx = sc[(21 + j * 3 + 0) * FK_ROWS], zy = sc[(21 + j * 3 + 1) * FK_ROWS],
@@ -303,42 +366,53 @@ __global__ void __launch_bounds__(GUIDE_THREADS) guide_step_kernel(GuideDev g, G
                 }
             }
             __syncthreads();
+            if (dbg) dbg[3] = clock64();  // field lookups + hinge + J^T
         }
 
         // adjoint of the interpolation (gather form), then per-cost clip / endpoint zero / weight: one thread per
         // (support row, field); sphere groups are summed in fixed order (deterministic)
         const float inv_ratio = ratio > 0.f ? 1.f / ratio : 0.f;
-        for (int item = tid; item < H * n_coll; item += NTH) {
-            const int h = item % H, f = item / H;
-            int lo_i = (int)floorf((float)(h - 1) * inv_ratio) - 1;
-            int hi_i = (int)ceilf((float)(h + 1) * inv_ratio) + 1;
-            if (lo_i < 0) lo_i = 0;
-            if (hi_i > NI - 1) hi_i = NI - 1;
-            float gs[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-            for (int i = lo_i; i <= hi_i; ++i) {
-                int i0 = i0s[i];
-                int i1 = i0 + (i0 < H - 1 ? 1 : 0);
-                float l1 = w1s[i];
-                float cw = (i0 == h ? 1.f - l1 : 0.f) + (i1 == h ? l1 : 0.f);
-                if (cw != 0.f) {
-                    for (int k = 0; k < q; ++k) {
+        // 8 lanes per (support row, field): lane k < q owns coordinate k; the clip norm is an xor-shuffle tree over the 8 lanes
+        for (int item0 = 0; item0 < H * n_coll; item0 += NTH / 8) {
+            const int item = item0 + (tid >> 3), k = tid & 7;
+            const bool on = item < H * n_coll;
+            const int h = on ? item % H : 0, f = on ? item / H : 0;
+            float gsk = 0.f;
+            if (on && k < q) {
+                int lo_i = (int)floorf((float)(h - 1) * inv_ratio) - 1;
+                int hi_i = (int)ceilf((float)(h + 1) * inv_ratio) + 1;
+                if (lo_i < 0) lo_i = 0;
+                if (hi_i > NI - 1) hi_i = NI - 1;
+                for (int i = lo_i; i <= hi_i; ++i) {
+                    int i0 = i0s[i];
+                    int i1 = i0 + (i0 < H - 1 ? 1 : 0);
+                    float l1 = w1s[i];
+                    float cw = (i0 == h ? 1.f - l1 : 0.f) + (i1 == h ? l1 : 0.f);
+                    if (cw != 0.f) {
                         float dqs = 0.f;
                         for (int sg = 0; sg < NSG; ++sg) dqs += gq[(((long long)f * NSG + sg) * NI + i) * q + k];
-                        gs[k] = fmaf(cw, dqs, gs[k]);
+                        gsk = fmaf(cw, dqs, gsk);
                     }
                 }
             }
             float scale = 1.f;
             if (g.clip) {
-                float n2 = (float)(D - q) * (1e-6f * 1e-6f);
-                for (int k = 0; k < q; ++k) { float t = gs[k] + 1e-6f; n2 = fmaf(t, t, n2); }
+                float t = (on && k < q) ? gsk + 1e-6f : 0.f;
+                float n2 = t * t;
+                n2 += __shfl_xor_sync(0xffffffffu, n2, 1);
+                n2 += __shfl_xor_sync(0xffffffffu, n2, 2);
+                n2 += __shfl_xor_sync(0xffffffffu, n2, 4);
+                n2 += (float)(D - q) * (1e-6f * 1e-6f);
                 scale = clip_scale(sqrtf(n2), g.max_norm);
             }
-            const float wgt = f < g.n_grid ? g.w_grid[f] : g.w_border;
-            // per-field results are parked in shared memory and added to `tot` in field order below
-            for (int k = 0; k < q; ++k) fgrad[(f * H + h) * q + k] = (h != 0 && h != H - 1) ? wgt * (scale * gs[k]) : 0.f;
+            if (on && k < q) {
+                const float wgt = f < g.n_grid ? g.w_grid[f] : g.w_border;
+                // per-field results are parked in shared memory and added to `tot` in field order below
+                fgrad[(f * H + h) * q + k] = (h != 0 && h != H - 1) ? wgt * (scale * gsk) : 0.f;
+            }
         }
         __syncthreads();
+        if (dbg) dbg[4] = clock64();  // interpolation adjoint + clip
         for (int idx = tid; idx < H * q; idx += NTH) {
             const int h = idx / q, k = idx - h * q;
             float t = tot[h * D + k];
@@ -348,33 +422,37 @@ __global__ void __launch_bounds__(GUIDE_THREADS) guide_step_kernel(GuideDev g, G
         __syncthreads();
     }
 
+    if (dbg) dbg[5] = clock64();  // fields summed
     // ---------------- GP prior (constant-velocity) on the support points ----------------
     if (g.use_gp) {
-        for (int h = tid; h < H; h += NTH) {
-            if (h == 0 || h == H - 1) continue;  // gradient rows zeroed by the guide manager
-            float gp[7], gv[7];
-            float n2 = 0.f;
-            for (int k = 0; k < q; ++k) {
+        for (int h0 = 0; h0 < H; h0 += NTH / 8) {
+            const int h = h0 + (tid >> 3), k = tid & 7;
+            const bool on = h > 0 && h < H - 1 && k < q;  // gradient rows 0 and H-1 are zeroed by the guide manager
+            float gpk = 0.f, gvk = 0.f, n2 = 0.f;
+            if (on) {
                 const float pm = xu[(h - 1) * D + k], pc = xu[h * D + k], pn = xu[(h + 1) * D + k];
                 const float vm = xu[(h - 1) * D + q + k], vc = xu[h * D + q + k], vn = xu[(h + 1) * D + q + k];
                 const float ep0 = pc - pm - g.dt * vm, ev0 = vc - vm;  // e_{h-1}
                 const float ep1 = pn - pc - g.dt * vc, ev1 = vn - vc;  // e_h
                 const float up0 = 2.f * (g.gp_a * ep0 + g.gp_b * ev0), uv0 = 2.f * (g.gp_b * ep0 + g.gp_c * ev0);
                 const float up1 = 2.f * (g.gp_a * ep1 + g.gp_b * ev1), uv1 = 2.f * (g.gp_b * ep1 + g.gp_c * ev1);
-                gp[k] = up0 - up1;
-                gv[k] = uv0 - uv1 - g.dt * up1;
-                float t0 = gp[k] + 1e-6f, t1 = gv[k] + 1e-6f;
-                n2 = fmaf(t0, t0, n2);
-                n2 = fmaf(t1, t1, n2);
+                gpk = up0 - up1;
+                gvk = uv0 - uv1 - g.dt * up1;
+                const float t0 = gpk + 1e-6f, t1 = gvk + 1e-6f;
+                n2 = fmaf(t1, t1, t0 * t0);
             }
-            float scale = g.clip ? clip_scale(sqrtf(n2), g.max_norm) : 1.f;
-            for (int k = 0; k < q; ++k) {
-                tot[h * D + k] += g.w_gp * (scale * gp[k]);
-                tot[h * D + q + k] += g.w_gp * (scale * gv[k]);
+            n2 += __shfl_xor_sync(0xffffffffu, n2, 1);
+            n2 += __shfl_xor_sync(0xffffffffu, n2, 2);
+            n2 += __shfl_xor_sync(0xffffffffu, n2, 4);
+            if (on) {
+                const float scale = g.clip ? clip_scale(sqrtf(n2), g.max_norm) : 1.f;
+                tot[h * D + k] += g.w_gp * (scale * gpk);
+                tot[h * D + q + k] += g.w_gp * (scale * gvk);
             }
         }
     }
     __syncthreads();
+    if (dbg) dbg[6] = clock64();  // GP stencil
 
     // ---------------- output ----------------
     float* xout = a.x_out + (long long)b * H * D;
@@ -404,6 +482,7 @@ __global__ void __launch_bounds__(GUIDE_THREADS) guide_step_kernel(GuideDev g, G
     if (a.flag_out != nullptr) {
         if (__syncthreads_or(viol ? 1 : 0) && tid == 0) atomicOr(a.flag_out, 1);
     }
+    if (dbg) dbg[7] = clock64();  // update written
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -496,7 +575,7 @@ __global__ void __launch_bounds__(FK_ROWS) eval_kernel(GuideDev g, const float* 
 static size_t guide_smem_bytes(const GuideDev& g, int H) {
     const int n_coll = g.n_grid + (g.has_border ? 1 : 0);
     size_t f = (size_t)3 * H * g.D + (size_t)n_coll * NSG * g.n_interp * g.q_dim + (size_t)n_coll * H * g.q_dim +
-               2 * (size_t)g.n_interp + (size_t)(42 + 3 * g.n_spheres) * FK_ROWS;
+               2 * (size_t)g.n_interp + (size_t)(42 + 3 * g.n_spheres + 14) * FK_ROWS;  // + sine / cosine scratch [2][7][FK_ROWS]
     return f * sizeof(float);
 }
 
@@ -724,6 +803,19 @@ extern "C" int mpdb_profile_guide(mpdb_guide* g, float* x, int32_t B, int32_t H,
     *ms_out = ms / reps;
     cudaEventDestroy(ev0);
     cudaEventDestroy(ev1);
+    if (getenv("MPDB_GUIDE_TIMELINE")) {  // debug: phase stamps of CTA 0
+        long long* d = nullptr;
+        long long h[8] = {0};
+        MPDB_CHECK_CUDA(cudaMalloc(&d, sizeof(h)));
+        MPDB_CHECK_CUDA(cudaMemset(d, 0, sizeof(h)));
+        a.dbg = d;
+        if (guide_launch_step(g, a, st)) return 1;
+        MPDB_CHECK_CUDA(cudaStreamSynchronize(st));
+        MPDB_CHECK_CUDA(cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost));
+        cudaFree(d);
+        const char* names[8] = {"start", "loaded", "fk", "lookups", "adjoint+clip", "fields summed", "gp", "written"};
+        for (int k = 1; k < 8; ++k) fprintf(stderr, "[guide timeline] %-14s +%.2f us (t = %.2f)\n", names[k], (h[k] - h[k - 1]) / 1965.0, (h[k] - h[0]) / 1965.0);
+    }
     return 0;
 }
 

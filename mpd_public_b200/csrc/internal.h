@@ -134,6 +134,7 @@ struct MegaProgram {
     long long* dbg;  // optional timeline: [n_layers][8 ranks][MEGA_DBG] clock64 stamps of cluster 0
 };
 size_t mega_smem_bytes(int a_bytes);
+int mega_max_active_clusters(int a_bytes);
 int launch_unet_mega(const MegaProgram& P, cudaStream_t stream);
 
 struct FinalArgs {
@@ -197,6 +198,7 @@ struct GuideStepArgs {
     float* out2;         // chain slot or null
     long long out2_bstride;
     int B, H;
+    long long* dbg;      // optional clock64 stamps of thread 0 of CTA 0 (MPDB_GUIDE_TIMELINE=1 in mpdb_profile_guide)
 };
 int guide_launch_step(mpdb_guide* g, const GuideStepArgs& a, cudaStream_t stream);
 int guide_launch_flag(const float* x, long long n, int* flag, cudaStream_t stream);

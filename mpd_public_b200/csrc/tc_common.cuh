@@ -150,6 +150,20 @@ __device__ __forceinline__ void tc_ld8(uint32_t taddr, float (&v)[8]) {
     for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// Three 8-column loads (the three partial accumulators of one output tile) with a single wait.
+__device__ __forceinline__ void tc_ld8x3(uint32_t t0, uint32_t t1, uint32_t t2, float (&a)[8], float (&b)[8], float (&c)[8]) {
+    uint32_t r[24];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(t0));
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]) : "r"(t1));
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]) : "r"(t2));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { a[i] = __uint_as_float(r[i]); b[i] = __uint_as_float(r[8 + i]); c[i] = __uint_as_float(r[16 + i]); }
+}
+
 __device__ __forceinline__ void split_bf16(float x, unsigned short& hi, unsigned short& lo) {
     __nv_bfloat16 h = __float2bfloat16_rn(x);
     __nv_bfloat16 l = __float2bfloat16_rn(x - __bfloat162float(h));
@@ -203,8 +217,9 @@ __device__ __forceinline__ void tc_store_row(const TcConvArgs& a, const float (&
 //            added with two xor-shuffles (rows = lanes) and parked: part[0][row/4][blk], part[1][row/4][blk]
 //   level 1: thread t < 2*SPT*8 owns one (moment, sample, block) column and adds its L/4 group sums in DOUBLE precision
 //            (fixed tree, two accumulators so the loads pipeline) -> cs[moment][sample][blk]
-//   level 2: one thread per (sample, group) combines the BPG block sums in double: mean = S/n, var = Q/n - mean^2,
-//            and publishes {mean, rstd}; everyone reads its two groups' values after a third barrier.
+//   level 2: the BPG block sums of a group are combined in double: mean = S/n, var = Q/n - mean^2, and {mean, rstd} is
+//            published; everyone reads its two groups' values after the last barrier. With at most 8 samples per tile
+//            levels 1 and 2 are one shuffle-connected pass (two barriers in all), otherwise they are separated by a barrier.
 // Accumulating the cross-row part in fp64 removes the cancellation of the one-pass formula; what remains is the fp32
 // rounding of the 16-term row-group partials (~6e-8 * (1 + mean^2/var)), far below the split-bf16 MMA error. Three short
 // barriers, no redundant fp64 work. Deterministic and independent of how samples are tiled. BAR1: named barrier of the 512 epilogue
@@ -238,51 +253,68 @@ __device__ __forceinline__ void gn_mish8(float (&v)[8], bool valid, int r, int s
     }
     if (BAR1) asm volatile("bar.sync 1, %0;" ::"n"(TC_THREADS) : "memory"); else __syncthreads();
     if (dbg) dbg[8] = clock64();
+    constexpr int NG = TC_NT / GS;
+    float* stat = reinterpret_cast<float*>(cs + 2 * 12 * 8);  // [12][8][2]
     if (SPT <= 8) {
-        // level 1: four threads per (moment, sample, block) column add the sample's L/4 row-group sums in double (thread j
-        // takes groups j, j+4, ...; the four partial sums meet in a fixed xor-shuffle tree)
-        const int t4 = tid >> 2, j = tid & 3;
-        const bool on = t4 < 2 * SPT * 8;
-        const int m = t4 >= SPT * 8 ? 1 : 0;
-        const int t2 = t4 - m * SPT * 8;
-        const int ss = t2 >> 3, blk = t2 & 7;
+        // levels 1 + 2 in one pass, no shared-memory round trip in between: JS threads per (sample, block, moment) column
+        // add the sample's L/4 row-group sums in double (thread j takes groups j, j+JS, ...); fixed xor-shuffle trees then
+        // combine the JS partial sums, bring the two moments together and add the BPG blocks of a GroupNorm group
+        // (lane bits, low to high: j | moment | block), and one lane per (sample, group) publishes {mean, rstd}.
+        constexpr int JS = BPG == 8 ? 2 : 4;
+        const int j = tid % JS, m = (tid / JS) & 1, blk = (tid / (2 * JS)) & 7, ss = tid / (16 * JS);
+        const bool on = ss < SPT;
         double a0 = 0.0;
         if (on) {
             const float* p = (m ? part2 : part) + (size_t)ss * (Lp >> 2) * 8 + blk;
-            for (int g = j; g < (L >> 2); g += 4) a0 += (double)p[g * 8];
+            for (int g = j; g < (L >> 2); g += JS) a0 += (double)p[g * 8];
         }
-        a0 += __shfl_xor_sync(0xffffffffu, a0, 1);
-        a0 += __shfl_xor_sync(0xffffffffu, a0, 2);
-        if (on && j == 0) cs[(m * 12 + ss) * 8 + blk] = a0;
-    } else if (tid < 2 * SPT * 8) {
-        // level 1 (more than 8 samples per tile): one thread per (moment, sample, block) column
-        const int m = tid >= SPT * 8 ? 1 : 0;
-        const int t2 = tid - m * SPT * 8;
-        const int ss = t2 >> 3, blk = t2 & 7;
-        const float* p = (m ? part2 : part) + (size_t)ss * (Lp >> 2) * 8 + blk;
-        double a0 = 0.0, a1 = 0.0;
-#pragma unroll 4
-        for (int g = 0; g < (L >> 2); g += 2) {
-            a0 += (double)p[(g + 0) * 8];
-            a1 += (double)p[(g + 1) * 8];
-        }
-        cs[(m * 12 + ss) * 8 + blk] = a0 + a1;
-    }
-    if (BAR1) asm volatile("bar.sync 1, %0;" ::"n"(TC_THREADS) : "memory"); else __syncthreads();
-    if (dbg) dbg[9] = clock64();
-    // level 2: one thread per (sample, group) finishes the statistics in double and publishes {mean, rstd} as floats
-    constexpr int NG = TC_NT / GS;
-    float* stat = reinterpret_cast<float*>(cs + 2 * 12 * 8);  // [12][8][2]
-    if (tid < SPT * NG) {
-        const int ss = tid / NG, g = tid - ss * NG;
-        double S = 0.0, Q = 0.0;
 #pragma unroll
-        for (int k = 0; k < BPG; ++k) { S += cs[(0 * 12 + ss) * 8 + g * BPG + k]; Q += cs[(1 * 12 + ss) * 8 + g * BPG + k]; }
-        const double inv_n = 1.0 / (double)(GS * L);
-        const double m = S * inv_n;
-        const double var = fmax(Q * inv_n - m * m, 0.0);
-        stat[(ss * 8 + g) * 2 + 0] = (float)m;
-        stat[(ss * 8 + g) * 2 + 1] = 1.0f / sqrtf((float)var + 1e-5f);  // the cancellation-prone part is done; fp32 from here
+        for (int o = 1; o < JS; o <<= 1) a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+        const double other = __shfl_xor_sync(0xffffffffu, a0, JS);  // the other moment of the same (sample, block)
+        double S = m ? other : a0, Q = m ? a0 : other;
+#pragma unroll
+        for (int o = 1; o < BPG; o <<= 1) {
+            S += __shfl_xor_sync(0xffffffffu, S, o * 2 * JS);
+            Q += __shfl_xor_sync(0xffffffffu, Q, o * 2 * JS);
+        }
+        if (on && j == 0 && m == 0 && (blk % BPG) == 0) {
+            const int g = blk / BPG;
+            const double inv_n = (double)(1.0f / (float)(GS * L));  // L = 8 * 2^k, GS = 2^j: exact, and no fp64 division
+            const double mean = S * inv_n;
+            const double var = fmax(Q * inv_n - mean * mean, 0.0);
+            stat[(ss * 8 + g) * 2 + 0] = (float)mean;
+            stat[(ss * 8 + g) * 2 + 1] = 1.0f / sqrtf((float)var + 1e-5f);  // the cancellation-prone part is done; fp32 from here
+        }
+        if (dbg) dbg[9] = clock64();
+    } else {
+        if (tid < 2 * SPT * 8) {
+            // level 1 (more than 8 samples per tile): one thread per (moment, sample, block) column
+            const int m = tid >= SPT * 8 ? 1 : 0;
+            const int t2 = tid - m * SPT * 8;
+            const int ss = t2 >> 3, blk = t2 & 7;
+            const float* p = (m ? part2 : part) + (size_t)ss * (Lp >> 2) * 8 + blk;
+            double a0 = 0.0, a1 = 0.0;
+#pragma unroll 4
+            for (int g = 0; g < (L >> 2); g += 2) {
+                a0 += (double)p[(g + 0) * 8];
+                a1 += (double)p[(g + 1) * 8];
+            }
+            cs[(m * 12 + ss) * 8 + blk] = a0 + a1;
+        }
+        if (BAR1) asm volatile("bar.sync 1, %0;" ::"n"(TC_THREADS) : "memory"); else __syncthreads();
+        if (dbg) dbg[9] = clock64();
+        // level 2: one thread per (sample, group) finishes the statistics in double and publishes {mean, rstd} as floats
+        if (tid < SPT * NG) {
+            const int ss = tid / NG, g = tid - ss * NG;
+            double S = 0.0, Q = 0.0;
+#pragma unroll
+            for (int k = 0; k < BPG; ++k) { S += cs[(0 * 12 + ss) * 8 + g * BPG + k]; Q += cs[(1 * 12 + ss) * 8 + g * BPG + k]; }
+            const double inv_n = (double)(1.0f / (float)(GS * L));
+            const double m = S * inv_n;
+            const double var = fmax(Q * inv_n - m * m, 0.0);
+            stat[(ss * 8 + g) * 2 + 0] = (float)m;
+            stat[(ss * 8 + g) * 2 + 1] = 1.0f / sqrtf((float)var + 1e-5f);
+        }
     }
     if (BAR1) asm volatile("bar.sync 1, %0;" ::"n"(TC_THREADS) : "memory"); else __syncthreads();
     const int sc = s < SPT ? s : 0;

@@ -150,6 +150,8 @@ __global__ void __launch_bounds__(MG_THREADS, 1) unet_mega_kernel(const __grid_c
                 const int n_a = Ld.n_a, n_res_a = Ld.n_res_a, type = Ld.type, zero_bytes = Ld.zero_bytes;
                 const uint32_t lbo = (uint32_t)Ld.RT * 16;
                 const uint32_t lo_plane = which == 1 ? (uint32_t)Ld.a_plane : 0u;
+                // the first chunk's weights do not depend on the previous layer: wait for them first
+                if (active) mbar_wait(full0 + 8 * (ring_i % MG_STAGES), (uint32_t)(ring_i / MG_STAGES) & 1u);
                 mbar_wait_cluster(a_full, (uint32_t)(l - 1) & 1u);  // operands of this layer have landed (cluster-wide)
                 tc_fence_after();
                 long long* mdbg = (P.dbg != nullptr && cluster == 0 && lane == 0 && which == 0) ? P.dbg + ((size_t)l * MEGA_CLUSTER + rank) * MEGA_DBG : nullptr;
@@ -168,8 +170,10 @@ __global__ void __launch_bounds__(MG_THREADS, 1) unet_mega_kernel(const __grid_c
                         const uint32_t a_lo = ((aaddr >> 4) & 0x3FFFu) | ((lbo >> 4) << 16);
                         const uint32_t b_lo = (((st + 2 * TC_A_PLANE_BYTES) >> 4) & 0x3FFFu) | b_lo_fixed;  // rows [0,32) = W_hi, [32,64) = W_lo
                         const uint32_t kstep_a = (2 * lbo) >> 4, kstep_b = (2 * (2 * TC_NT * 16)) >> 4, tap_b = (2 * TC_B_TAP_BYTES) >> 4;
-                        mbar_wait(full0 + 8 * sidx, (uint32_t)(ring_i / MG_STAGES) & 1u);
-                        tc_fence_after();
+                        if (c > 0) {
+                            mbar_wait(full0 + 8 * sidx, (uint32_t)(ring_i / MG_STAGES) & 1u);
+                            tc_fence_after();
+                        }
                         if (mdbg && c == 0) mdbg[9] = clock64();
                         if (is_res) {  // 1x1 residual conv: centre row (+2)
 #pragma unroll
@@ -280,24 +284,18 @@ __global__ void __launch_bounds__(MG_THREADS, 1) unet_mega_kernel(const __grid_c
                 tc_fence_after();
                 {
                     float v2[8], v3[8];
-                    tc_ld8(taddr, v);               // hi*hi
-                    tc_ld8(taddr + 2 * TC_NT, v3);  // lo*hi
-                    tc_ld8(taddr + TC_NT, v2);      // hi*lo
+                    tc_ld8x3(taddr, taddr + 2 * TC_NT, taddr + TC_NT, v, v3, v2);  // hi*hi, lo*hi, hi*lo
 #pragma unroll
                     for (int j = 0; j < 8; ++j) v[j] = (v[j] + v3[j]) + v2[j];
                 }
                 if (Ld.type == MG_UP) {
                     float w2[8], w3[8];
-                    tc_ld8(taddr + 128, w);
-                    tc_ld8(taddr + 128 + 2 * TC_NT, w3);
-                    tc_ld8(taddr + 128 + TC_NT, w2);
+                    tc_ld8x3(taddr + 128, taddr + 128 + 2 * TC_NT, taddr + 128 + TC_NT, w, w3, w2);
 #pragma unroll
                     for (int j = 0; j < 8; ++j) w[j] = (w[j] + w3[j]) + w2[j];
                 } else if (Ld.res_mode == 2) {
                     float rv2[8], rv3[8];
-                    tc_ld8(taddr + 128, rv);
-                    tc_ld8(taddr + 128 + 2 * TC_NT, rv3);
-                    tc_ld8(taddr + 128 + TC_NT, rv2);
+                    tc_ld8x3(taddr + 128, taddr + 128 + 2 * TC_NT, taddr + 128 + TC_NT, rv, rv3, rv2);
 #pragma unroll
                     for (int j = 0; j < 8; ++j) rv[j] = (rv[j] + rv3[j]) + rv2[j];
                 }
@@ -383,7 +381,9 @@ __global__ void __launch_bounds__(MG_THREADS, 1) unet_mega_kernel(const __grid_c
             }
         }
         if (dbg) dbg[7] = clock64();  // stores issued
-        asm volatile("fence.proxy.async;" ::: "memory");  // generic-proxy stores -> tensor core / bulk copies of the consumers
+        // generic-proxy stores -> tensor core (shared memory) / bulk copies (global skip tensor) of the consumers
+        if (Ld.skip_out_hi != nullptr) asm volatile("fence.proxy.async;" ::: "memory");
+        else asm volatile("fence.proxy.async.shared::cluster;" ::: "memory");
         if (dbg) dbg[3] = clock64();  // outputs delivered
         __syncwarp();
         if (lane < MEGA_CLUSTER && l + 1 < P.n_layers) mbar_arrive_cluster(map_to_cta(a_full, (uint32_t)lane));
@@ -400,6 +400,33 @@ __global__ void __launch_bounds__(MG_THREADS, 1) unet_mega_kernel(const __grid_c
 
 size_t mega_smem_bytes(int a_bytes) {
     return (size_t)a_bytes + (size_t)MG_STAGES * TC_STAGE_BYTES + (2 * MG_STAGES + 3) * 8 + 16 + MG_SCRATCH_BYTES;
+}
+
+// How many clusters of the kernel can be resident at once (they must all fit in one wave for the kernel to pay off:
+// a second wave doubles the latency chain, and the per-layer kernels win, profiles/README.md).
+int mega_max_active_clusters(int a_bytes) {
+    static int cached_bytes = -1, cached = 0;
+    if (a_bytes == cached_bytes) return cached;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(MEGA_CLUSTER * 32);
+    cfg.blockDim = dim3(MG_THREADS);
+    cfg.dynamicSmemBytes = mega_smem_bytes(a_bytes);
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = MEGA_CLUSTER;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaFuncSetAttribute(unet_mega_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
+        cudaOccupancyMaxActiveClusters(&n, unet_mega_kernel, &cfg) != cudaSuccess) {
+        cudaGetLastError();
+        n = 0;
+    }
+    cached_bytes = a_bytes;
+    cached = n;
+    return n;
 }
 
 int launch_unet_mega(const MegaProgram& P, cudaStream_t stream) {

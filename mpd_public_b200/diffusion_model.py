@@ -111,8 +111,13 @@ class Engine:
         _lib.check(self.lib.mpdb_engine_set_schedule(self.handle, *ptrs))
 
     def _signature(self):
-        ps = list(self.unet.parameters())
-        return tuple((p.data_ptr(), p._version) for p in ps)
+        # (module, name) slots are cached: walking the module tree costs ~1 ms per call, which would sit in front of every
+        # sampling call; reading the slots still sees replaced Parameter objects, .to() and in-place updates
+        slots = self.__dict__.get("_param_slots")
+        if slots is None:
+            slots = [(m, n) for m in self.unet.modules() for n in m._parameters if m._parameters[n] is not None]
+            self._param_slots = slots
+        return tuple((m._parameters[n].data_ptr(), m._parameters[n]._version) for m, n in slots)
 
     def sync_params(self):
         """(Re)uploads the UNet parameters when they changed (load_state_dict, .to(), optimiser step)."""

@@ -61,3 +61,25 @@ def test_mega_is_batch_invariant():
         assert torch.equal(a[11:18], b)
     finally:
         model.tensor_cores = "auto"
+
+
+def test_mega_one_wave_policy():
+    """Batches that need more clusters than fit in one wave fall back to the per-layer kernels (and say why); option
+    mega = 2 forces the cluster kernel, which must still agree."""
+    model = cuda_model("panda_opt1_h64")
+    model.tensor_cores = "force"
+    eng = model._engine()
+    g = torch.Generator().manual_seed(9)
+    x = torch.randn((256, 64, 14), generator=g).cuda()
+    try:
+        in_use, G, n_layers, a_bytes, smem, why = eng.mega_info(256)
+        assert not in_use and "one wave" in why, (in_use, why)
+        ref = eng.unet_forward_uniform(x, 4)
+        eng.set_option("mega", 2)
+        assert eng.mega_info(256)[0]
+        out = eng.unet_forward_uniform(x, 4)
+        assert rel(out, ref) < TOL_TC
+    finally:
+        eng.set_option("mega", 1)
+        model.tensor_cores = "auto"
+    assert eng.mega_info(100)[0]
