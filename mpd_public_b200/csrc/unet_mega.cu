@@ -21,8 +21,14 @@
 //     its outputs). Every warp of every CTA arrives on every CTA's barrier each layer, active or not, so the counts
 //     are constants and idle CTAs stay in lock step.
 //
-// Arithmetic is identical to the per-layer tensor-core path (same split-bf16 MMA sequence per K-chunk, same GroupNorm
-// reduction tree, fp32 residual values kept in registers), so the two paths agree bit for bit (tested).
+// Tried and dropped (measured, profiles/README.md): per-source "slice landed" barriers so that a K-chunk's MMAs start as soon
+// as its 32 channels have arrived — the incoming DSMEM stores and the tensor core's operand reads share the destination's
+// shared-memory port, so the overlap bought nothing (273 -> 309 us per forward); pushing slices with cp.async.bulk
+// shared::cta -> shared::cluster (14 B/clk per SM in an 8-way all-to-all, the same network limit).
+//
+// Arithmetic follows the per-layer tensor-core path (same split-bf16 products per K-chunk, fp32 residual values kept in
+// registers); the three partial products are summed from separate accumulators, so the two paths agree to the split-bf16
+// rounding level (~1.5e-5 relative, tested), and each is deterministic and independent of the batch composition.
 #include "tc_common.cuh"
 
 namespace mpdb {
@@ -356,7 +362,10 @@ __global__ void __launch_bounds__(MG_THREADS, 1) unet_mega_kernel(const __grid_c
                         if (k == 0) pack_split8(v, ph, pl); else pack_split8(w, ph, pl);
                         const uint32_t off = (uint32_t)(((c8 / 8) * Ld.oRT + (s2 * Ld.oLp + lo + 2)) * 16);
                         const uint32_t local_hi = abuf_u32 + off, local_lo = local_hi + (uint32_t)Ld.o_plane;
-                        for (int j = 0; j < Ld.oNC; ++j) {
+                        for (int jj = 0; jj < Ld.oNC; ++jj) {
+                            // staggered destination order: at any moment the writers of a row tile address different peers
+                            int j = rank + 1 + jj;
+                            j -= (j / Ld.oNC) * Ld.oNC;
                             const uint32_t cta = (uint32_t)(mt2 * Ld.oNC + j);
                             if ((int)cta == rank) {  // own A buffer: plain shared-memory stores
                                 *reinterpret_cast<uint4*>(abuf + off) = ph;

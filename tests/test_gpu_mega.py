@@ -1,6 +1,6 @@
 """Whole-forward cluster kernel (csrc/unet_mega.cu) — the UNet as ONE launch of 8-CTA clusters — against the
-per-layer tensor-core kernels (must agree bit for bit: same MMA sequence, same GroupNorm tree, fp32 residuals) and
-against the oracle (split-bf16 tolerance). Batch sizes cover full clusters, a ragged last cluster and B < 8."""
+per-layer tensor-core kernels (same split-bf16 products, partial sums combined in a different order: agreement at the
+split-bf16 rounding level, bar 2e-4) and against the oracle (same bar). Batch sizes cover full clusters, a ragged last cluster and B < 8."""
 import pytest
 import torch
 
