@@ -32,8 +32,18 @@ namespace mpdb {
 // MODE: TCM_CONV5 = Conv1d k5 (+GN+Mish+cond+residual);  TCM_DOWN = Conv1d k3 stride 2 evaluated at every input position
 // (3 taps) with only the even rows written (MMA work is negligible next to the fixed costs);  TCM_UP = ConvTranspose1d
 // k4 stride 2 as two 2-tap accumulators (even / odd outputs).
+// Warp roles (tools/probes/mma_probe.cu: one thread issues a tcgen05.mma every ~80-100 cycles whatever its shape, two
+// threads in different warps reach the shared-memory operand floor; issued from a single-lane branch every MMA / bulk copy
+// is wrapped in an ELECT + R2UR loop, so the issuing warps run their loops warp-convergently and elect one lane):
+//   warps 0-15  epilogue (warp w reads TMEM lane quarter w & 3, column group w >> 2)
+//   warp  16    producer (cp.async.bulk ring)
+//   warp  17    MMA issuer 0: A_hi x [W_hi | W_lo] (N = 64) -> columns [0,64)   (second accumulator: +128)
+//   warp  18    MMA issuer 1: A_lo x W_hi        (N = 32) -> columns [64,96)  (second accumulator: +128)
+constexpr int TCL_THREADS = TC_THREADS + 96;
+constexpr int TCL_TMEM_COLS = 256;
+
 template <int MODE, int GS>
-__global__ void __launch_bounds__(TC_THREADS, 1) conv5_tc_kernel(TcConvArgs a) {
+__global__ void __launch_bounds__(TCL_THREADS, 1) conv5_tc_kernel(TcConvArgs a) {
     constexpr int NTAPS = MODE == TCM_CONV5 ? 5 : MODE == TCM_DOWN ? 3 : 4;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     // carve-up: stages | barriers | tmem slot | epilogue scratch
@@ -53,52 +63,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv5_tc_kernel(TcConvArgs a) {
     const int n_res = a.res_w ? (a.rc0 + a.rc1) / TC_KCH : 0;
     const int n_steps = n_main + n_res;
 
+    const uint32_t stages_u32 = smem_u32(stages);
     const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + TC_STAGES), done_bar = smem_u32(bars + 2 * TC_STAGES);
-
-    // One pipeline step of the producer: K-chunk i -> stage i % STAGES (bulk-async copies, TMA engine, completion
-    // counted on the stage's mbarrier).
-    auto produce = [&](int i, bool weights, bool acts) {
-        const int s = i % TC_STAGES;
-        const bool is_res = i >= n_main;
-        const int c = is_res ? i - n_main : i;
-        const int ntaps = is_res ? 1 : NTAPS;
-        const uint32_t bbytes = 2u * ntaps * TC_B_TAP_BYTES;
-        const uint32_t st = smem_u32(stages + (size_t)s * TC_STAGE_BYTES);
-        if (weights) {
-            const unsigned short* wsrc = is_res ? a.res_w + ((size_t)ntile * n_res + c) * (2 * 1 * TC_B_TAP_BYTES / 2)
-                                                : a.w + ((size_t)ntile * n_main + c) * (2 * NTAPS * TC_B_TAP_BYTES / 2);
-            mbar_expect_tx(full0 + 8 * s, 2u * TC_A_PLANE_BYTES + bbytes);  // covers the activation copies too
-            bulk_g2s(st + 2 * TC_A_PLANE_BYTES, wsrc, bbytes, full0 + 8 * s);
-        }
-        if (acts) {
-            const int C0 = is_res ? a.rc0 : a.c0, C1 = is_res ? a.rc1 : a.c1;
-            const bool second = c * TC_KCH >= C0;
-            const unsigned short* ahi = is_res ? (second ? a.r1_hi : a.r0_hi) : (second ? a.in1_hi : a.in0_hi);
-            const unsigned short* alo = is_res ? (second ? a.r1_lo : a.r0_lo) : (second ? a.in1_lo : a.in0_lo);
-            const int Csrc = second ? C1 : C0;
-            const int kg0 = (c * TC_KCH - (second ? C0 : 0)) / 8;
-            const size_t aoff = ((size_t)tile * (Csrc / 8) + kg0) * TC_RT * 8;  // elements
-            bulk_g2s(st, ahi + aoff, TC_A_PLANE_BYTES, full0 + 8 * s);
-            bulk_g2s(st + TC_A_PLANE_BYTES, alo + aoff, TC_A_PLANE_BYTES, full0 + 8 * s);
-        }
-    };
 
     if (tid == 0) {
         for (int s = 0; s < TC_STAGES; ++s) {
             mbar_init(full0 + 8 * s, 1);
-            mbar_init(empty0 + 8 * s, 1);
+            mbar_init(empty0 + 8 * s, 2);  // both issuers release a stage
         }
-        mbar_init(done_bar, 1);
+        mbar_init(done_bar, 2);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        // Weights are constants: their copies for the first STAGES chunks are issued before the dependency wait, so
-        // under programmatic dependent launch they overlap the previous kernel's epilogue. Activations follow it.
-        for (int i = 0; i < n_steps && i < TC_STAGES; ++i) produce(i, true, false);
-        pdl_wait();
-        for (int i = 0; i < n_steps && i < TC_STAGES; ++i) produce(i, false, true);
     }
     if (warp == 1) {  // TMEM allocation is a warp-wide operation; the same warp frees it at the end
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                     "r"(TC_TMEM_COLS)
+                     "r"(TCL_TMEM_COLS)
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -106,34 +84,69 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv5_tc_kernel(TcConvArgs a) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    pdl_wait();  // every thread: nothing produced by the previous kernel is read, and nothing is written, before this
     if (dbg && tid == 64) a.dbg[1] = clock64();  // setup done (barriers, TMEM)
 
-    if (tid == 0) {
-        // ===== producer: remaining K-chunks, each waits for its stage to be released by the MMA commits =====
+    if (warp == TC_THREADS / 32) {
+        // ===== producer warp: K-chunk i -> stage i % STAGES (bulk-async copies, completion counted on the stage's mbarrier).
+        // Weights are constants: the first STAGES chunks' weight copies are issued before the dependency wait, so under
+        // programmatic dependent launch they overlap the previous kernel's epilogue. Activations follow it. =====
+        auto produce = [&](int i, bool weights, bool acts) {
+            const int s = i % TC_STAGES;
+            const bool is_res = i >= n_main;
+            const int c = is_res ? i - n_main : i;
+            const int ntaps = is_res ? 1 : NTAPS;
+            const uint32_t bbytes = 2u * ntaps * TC_B_TAP_BYTES;
+            const uint32_t st = stages_u32 + (uint32_t)s * TC_STAGE_BYTES;
+            if (weights) {
+                const unsigned short* wsrc = is_res ? a.res_w + ((size_t)ntile * n_res + c) * (2 * 1 * TC_B_TAP_BYTES / 2)
+                                                    : a.w + ((size_t)ntile * n_main + c) * (2 * NTAPS * TC_B_TAP_BYTES / 2);
+                mbar_expect_tx_elect(full0 + 8 * s, 2u * TC_A_PLANE_BYTES + bbytes);  // covers the activation copies too
+                bulk_g2s_elect(st + 2 * TC_A_PLANE_BYTES, wsrc, bbytes, full0 + 8 * s);
+            }
+            if (acts) {
+                const int C0 = is_res ? a.rc0 : a.c0, C1 = is_res ? a.rc1 : a.c1;
+                const bool second = c * TC_KCH >= C0;
+                const unsigned short* ahi = is_res ? (second ? a.r1_hi : a.r0_hi) : (second ? a.in1_hi : a.in0_hi);
+                const unsigned short* alo = is_res ? (second ? a.r1_lo : a.r0_lo) : (second ? a.in1_lo : a.in0_lo);
+                const int Csrc = second ? C1 : C0;
+                const int kg0 = (c * TC_KCH - (second ? C0 : 0)) / 8;
+                const size_t aoff = ((size_t)tile * (Csrc / 8) + kg0) * TC_RT * 8;  // elements
+                bulk_g2s_elect(st, ahi + aoff, TC_A_PLANE_BYTES, full0 + 8 * s);
+                bulk_g2s_elect(st + TC_A_PLANE_BYTES, alo + aoff, TC_A_PLANE_BYTES, full0 + 8 * s);
+            }
+        };
+        for (int i = 0; i < n_steps && i < TC_STAGES; ++i) produce(i, true, false);
+        pdl_wait();
+        for (int i = 0; i < n_steps && i < TC_STAGES; ++i) produce(i, false, true);
         for (int i = TC_STAGES; i < n_steps; ++i) {
             mbar_wait(empty0 + 8 * (i % TC_STAGES), ((uint32_t)(i / TC_STAGES) & 1u) ^ 1u);
+            __syncwarp();
             produce(i, true, true);
         }
-        if (dbg) a.dbg[2] = clock64();  // all loads issued
-    } else if (tid == 32) {
-        // ===== MMA issuer: one thread drives the tensor core =====
-        constexpr uint32_t idesc32 = tc_idesc(128, TC_NT), idesc64 = tc_idesc(128, 2 * TC_NT);
-        bool first_main = true, first_res = true;
+    } else if (warp > TC_THREADS / 32) {
+        // ===== two MMA-issue warps =====
+        const int which = __shfl_sync(0xffffffffu, warp, 0) - (TC_THREADS / 32 + 1);
+        const uint32_t idesc = which == 0 ? tc_idesc(128, 2 * TC_NT) : tc_idesc(128, TC_NT);
+        const uint32_t col0 = __shfl_sync(0xffffffffu, tmem_base, 0) + (which == 0 ? 0u : 2u * TC_NT);
+        constexpr uint32_t desc_hi = (128u >> 4) | (1u << 14);                      // SBO = 128 B, descriptor version 1
+        constexpr uint32_t a_lo_fixed = ((uint32_t)(TC_RT * 16) >> 4) << 16;        // activation tile: LBO = 132 rows x 16 B
+        constexpr uint32_t b_lo_fixed = ((2u * TC_NT * 16u) >> 4) << 16;            // weight tile: LBO = 64 rows x 16 B
+        constexpr uint32_t kstep_a = (2 * TC_RT * 16) >> 4, kstep_b = (2 * (2 * TC_NT * 16)) >> 4, tap_b = (2 * TC_B_TAP_BYTES) >> 4;
+        uint32_t acc0 = 0u, acc1 = 0u;
         for (int i = 0; i < n_steps; ++i) {
             const int s = i % TC_STAGES;
-            const uint32_t ph = (uint32_t)(i / TC_STAGES) & 1u;
-            mbar_wait(full0 + 8 * s, ph);
+            const uint32_t st = stages_u32 + (uint32_t)s * TC_STAGE_BYTES;
+            const uint32_t a_lo = (((st + (which == 1 ? (uint32_t)TC_A_PLANE_BYTES : 0u)) >> 4) & 0x3FFFu) | a_lo_fixed;
+            const uint32_t b_lo = (((st + 2 * TC_A_PLANE_BYTES) >> 4) & 0x3FFFu) | b_lo_fixed;  // rows [0,32) = W_hi, [32,64) = W_lo
+            mbar_wait(full0 + 8 * s, (uint32_t)(i / TC_STAGES) & 1u);
             tc_fence_after();
-            const bool is_res = i >= n_main;
-            const uint32_t st = smem_u32(stages + (size_t)s * TC_STAGE_BYTES);
-            // base descriptors of the stage; every MMA only adds a (16-byte unit) offset to the start-address field
-            const uint64_t dA_hi = tc_desc(st, TC_RT * 16, 128);
-            const uint64_t dA_lo = tc_desc(st + TC_A_PLANE_BYTES, TC_RT * 16, 128);
-            // weight tile per tap: [k-group][64 rows = 32 hi | 32 lo][8]  (LBO = 64 rows * 16 B)
-            const uint64_t dB = tc_desc(st + 2 * TC_A_PLANE_BYTES, 2 * TC_NT * 16, 128);
-            const uint32_t dcol = tmem_base + (is_res ? 2 * TC_NT : 0);
-            if (!is_res) {
+            if (i >= n_main) {  // fused 1x1 residual conv: centre row (+2), second accumulator
+#pragma unroll
+                for (int kk = 0; kk < TC_KCH / 16; ++kk) {
+                    tc_mma_bf16_elect32(col0 + 128, a_lo + kk * kstep_a + 2, desc_hi, b_lo + kk * kstep_b, desc_hi, idesc, acc1);
+                    acc1 = 1u;
+                }
+            } else {
 #pragma unroll
                 for (int tap = 0; tap < NTAPS; ++tap) {
                     // row shift of the tap (in 16-byte rows; +2 is the centre) and the accumulator it feeds
@@ -141,136 +154,117 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv5_tc_kernel(TcConvArgs a) {
                     //   UP  : packed taps [W1, W3 | W0, W2]: even = W1 x[m] + W3 x[m-1], odd = W0 x[m+1] + W2 x[m]
                     const int shift = MODE == TCM_CONV5 ? tap : MODE == TCM_DOWN ? tap + 1 : (tap == 0 ? 2 : tap == 1 ? 1 : tap == 2 ? 3 : 2);
                     const bool second_acc = MODE == TCM_UP && tap >= 2;
-                    const uint32_t dc = tmem_base + (second_acc ? 2 * TC_NT : 0);
 #pragma unroll
                     for (int kk = 0; kk < TC_KCH / 16; ++kk) {
-                        const uint64_t aofs = (uint64_t)((kk * 2 * (TC_RT * 16) + shift * 16) >> 4);
-                        const uint64_t bofs = (uint64_t)((tap * 2 * TC_B_TAP_BYTES + kk * 2 * (2 * TC_NT * 16)) >> 4);
-                        bool& first = second_acc ? first_res : first_main;
-                        tc_mma_bf16(dc, dA_hi + aofs, dB + bofs, idesc64, first ? 0u : 1u);  // [hi*hi | hi*lo]
-                        first = false;
-                        tc_mma_bf16(dc, dA_lo + aofs, dB + bofs, idesc32, 1u);               // += lo*hi
+                        if (second_acc) { tc_mma_bf16_elect32(col0 + 128, a_lo + kk * kstep_a + shift, desc_hi, b_lo + tap * tap_b + kk * kstep_b, desc_hi, idesc, acc1); acc1 = 1u; }
+                        else { tc_mma_bf16_elect32(col0, a_lo + kk * kstep_a + shift, desc_hi, b_lo + tap * tap_b + kk * kstep_b, desc_hi, idesc, acc0); acc0 = 1u; }
                     }
                 }
+            }
+            tc_commit_elect(empty0 + 8 * s);  // frees the stage when both issuers' MMAs that read it have retired
+        }
+        tc_commit_elect(done_bar);  // accumulators complete
+        // main loop over: let the next kernel start its prologue (barriers, TMEM, weight prefetch) under our epilogue
+        if (which == 0 && lane == 0) pdl_launch_dependents();
+        if (dbg && which == 0 && lane == 0) a.dbg[3] = clock64();  // all MMAs issued
+    } else {
+        // ===== epilogue: 16 warps. TMEM lane quarter q = warp & 3 (hardware rule: a warp reads lanes 32*(warp%4)..+31),
+        // column group cg = warp >> 2 -> each thread owns 8 consecutive channels of one row. Per-thread geometry and
+        // every parameter / residual value this thread will need are fetched BEFORE waiting for the accumulators, so
+        // their global-memory latency overlaps the MMA main loop =====
+        pdl_wait();  // nothing produced by the previous kernel is read, and nothing is written, before this
+        const int q = warp & 3, cg = warp >> 2;
+        const int r = q * 32 + lane;  // padded row of the tile = TMEM lane
+        const int s = r / Lp, l = r - s * Lp;
+        const int b = tile * SPT + s;
+        const bool valid = (s < SPT) && (l < a.L) && (b < a.B);
+        const int c8 = n0 + cg * 8;  // first of this thread's 8 output channels
+        const bool full = a.raw_out == nullptr;
+        const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 pb0 = z4, pb1 = z4, pg0 = z4, pg1 = z4, pe0 = z4, pe1 = z4, pc0 = z4, pc1 = z4, pr0 = z4, pr1 = z4;
+        float rid[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (full) {
+            pb0 = *reinterpret_cast<const float4*>(a.bias + c8); pb1 = *reinterpret_cast<const float4*>(a.bias + c8 + 4);
+            if (MODE == TCM_CONV5) {
+                pg0 = *reinterpret_cast<const float4*>(a.gamma + c8); pg1 = *reinterpret_cast<const float4*>(a.gamma + c8 + 4);
+                pe0 = *reinterpret_cast<const float4*>(a.beta + c8); pe1 = *reinterpret_cast<const float4*>(a.beta + c8 + 4);
+            }
+            if (a.cond != nullptr && valid) {
+                const int tt = a.t_dev ? (int)a.t_dev[b] : a.t_uniform;
+                const float* cp = a.cond + (size_t)tt * a.CO + c8;
+                pc0 = *reinterpret_cast<const float4*>(cp); pc1 = *reinterpret_cast<const float4*>(cp + 4);
+            }
+            if (a.res_w != nullptr) {
+                pr0 = *reinterpret_cast<const float4*>(a.res_bias + c8); pr1 = *reinterpret_cast<const float4*>(a.res_bias + c8 + 4);
+            } else if (a.res_cm != nullptr && valid) {
+                const float* rp = a.res_cm + ((size_t)b * a.CO + c8) * Lp + 2 + l;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) rid[j] = rp[(size_t)j * Lp];
+            }
+        }
+
+        mbar_wait(done_bar, 0);
+        __syncwarp();
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + cg * 8;
+        if (dbg && tid == 64) a.dbg[4] = clock64();  // accumulators ready
+        float v[8];
+        {
+            float v2[8], v3[8];
+            tc_ld8x3(taddr, taddr + 2 * TC_NT, taddr + TC_NT, v, v3, v2);  // hi*hi, lo*hi, hi*lo
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = (v[j] + v3[j]) + v2[j];
+        }
+        if (dbg && tid == 64) a.dbg[5] = clock64();  // TMEM read
+
+        if (!full) {
+            float* dst = a.raw_out + (((size_t)tile * gridDim.y + ntile) * 128 + r) * 32 + cg * 8;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) dst[j] = v[j];
+        } else if (MODE == TCM_DOWN) {
+            // stride-2 conv: the MMA evaluated every input position; keep the even ones (out[m] = conv at l = 2m)
+            v[0] += pb0.x; v[1] += pb0.y; v[2] += pb0.z; v[3] += pb0.w;
+            v[4] += pb1.x; v[5] += pb1.y; v[6] += pb1.z; v[7] += pb1.w;
+            if (valid && (l & 1) == 0) tc_store_row(a, v, b, l >> 1, c8, a.L >> 1);
+        } else if (MODE == TCM_UP) {
+            // transposed conv: accumulator 0 = even outputs (2l), accumulator 1 = odd outputs (2l + 1)
+            float w[8], w2[8], w3[8];
+            tc_ld8x3(taddr + 128, taddr + 128 + 2 * TC_NT, taddr + 128 + TC_NT, w, w3, w2);
+            v[0] += pb0.x; v[1] += pb0.y; v[2] += pb0.z; v[3] += pb0.w;
+            v[4] += pb1.x; v[5] += pb1.y; v[6] += pb1.z; v[7] += pb1.w;
+            w[0] = (w[0] + w3[0]) + w2[0] + pb0.x; w[1] = (w[1] + w3[1]) + w2[1] + pb0.y; w[2] = (w[2] + w3[2]) + w2[2] + pb0.z; w[3] = (w[3] + w3[3]) + w2[3] + pb0.w;
+            w[4] = (w[4] + w3[4]) + w2[4] + pb1.x; w[5] = (w[5] + w3[5]) + w2[5] + pb1.y; w[6] = (w[6] + w3[6]) + w2[6] + pb1.z; w[7] = (w[7] + w3[7]) + w2[7] + pb1.w;
+            if (valid) {
+                tc_store_row(a, v, b, 2 * l, c8, 2 * a.L);
+                tc_store_row(a, w, b, 2 * l + 1, c8, 2 * a.L);
+            }
+        } else {
+            v[0] += pb0.x; v[1] += pb0.y; v[2] += pb0.z; v[3] += pb0.w;
+            v[4] += pb1.x; v[5] += pb1.y; v[6] += pb1.z; v[7] += pb1.w;
+            gn_mish8<GS, true>(v, valid, r, s, cg, tid, SPT, Lp, a.L, part, pg0, pg1, pe0, pe1, (dbg && tid == 64) ? a.dbg : nullptr);
+            if (dbg && tid == 64) a.dbg[6] = clock64();  // GroupNorm + Mish done
+            // time conditioning (zero when absent), then the residual: fused 1x1 conv accumulators or identity values
+            v[0] += pc0.x; v[1] += pc0.y; v[2] += pc0.z; v[3] += pc0.w;
+            v[4] += pc1.x; v[5] += pc1.y; v[6] += pc1.z; v[7] += pc1.w;
+            if (a.res_w != nullptr) {
+                float rv[8], rv2[8], rv3[8];
+                tc_ld8x3(taddr + 128, taddr + 128 + 2 * TC_NT, taddr + 128 + TC_NT, rv, rv3, rv2);
+                v[0] += (rv[0] + rv3[0]) + rv2[0] + pr0.x; v[1] += (rv[1] + rv3[1]) + rv2[1] + pr0.y; v[2] += (rv[2] + rv3[2]) + rv2[2] + pr0.z; v[3] += (rv[3] + rv3[3]) + rv2[3] + pr0.w;
+                v[4] += (rv[4] + rv3[4]) + rv2[4] + pr1.x; v[5] += (rv[5] + rv3[5]) + rv2[5] + pr1.y; v[6] += (rv[6] + rv3[6]) + rv2[6] + pr1.z; v[7] += (rv[7] + rv3[7]) + rv2[7] + pr1.w;
             } else {
 #pragma unroll
-                for (int kk = 0; kk < TC_KCH / 16; ++kk) {
-                    const uint64_t aofs = (uint64_t)((kk * 2 * (TC_RT * 16) + 2 * 16) >> 4);  // 1x1 conv reads the centre row
-                    const uint64_t bofs = (uint64_t)((kk * 2 * (2 * TC_NT * 16)) >> 4);
-                    tc_mma_bf16(dcol, dA_hi + aofs, dB + bofs, idesc64, first_res ? 0u : 1u);
-                    first_res = false;
-                    tc_mma_bf16(dcol, dA_lo + aofs, dB + bofs, idesc32, 1u);
-                }
+                for (int j = 0; j < 8; ++j) v[j] += rid[j];
             }
-            tc_commit(empty0 + 8 * s);  // frees the stage when the MMAs that read it have retired
+            if (valid) tc_store_row(a, v, b, l, c8, a.L);
         }
-        tc_commit(done_bar);  // accumulators complete
-        // main loop over: let the next kernel start its prologue (barriers, TMEM, weight prefetch) under our epilogue
-        pdl_launch_dependents();
-        if (dbg) a.dbg[3] = clock64();  // all MMAs issued
-    }
-
-    // ===== epilogue: 16 warps. TMEM lane quarter q = warp & 3 (hardware rule: a warp reads lanes 32*(warp%4)..+31),
-    // column group cg = warp >> 2 -> each thread owns 8 consecutive channels of one row (short dependency chains,
-    // 4 warps per scheduler to hide latency). =====
-    // per-thread geometry and every parameter / residual value this thread will need are fetched BEFORE waiting for
-    // the accumulators, so their global-memory latency overlaps the MMA main loop
-    const int q = warp & 3, cg = warp >> 2;
-    const int r = q * 32 + lane;  // padded row of the tile = TMEM lane
-    const int s = r / Lp, l = r - s * Lp;
-    const int b = tile * SPT + s;
-    const bool valid = (s < SPT) && (l < a.L) && (b < a.B);
-    const int c8 = n0 + cg * 8;  // first of this thread's 8 output channels
-    const bool full = a.raw_out == nullptr;
-    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    float4 pb0 = z4, pb1 = z4, pg0 = z4, pg1 = z4, pe0 = z4, pe1 = z4, pc0 = z4, pc1 = z4, pr0 = z4, pr1 = z4;
-    float rid[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    if (full) {
-        pb0 = *reinterpret_cast<const float4*>(a.bias + c8); pb1 = *reinterpret_cast<const float4*>(a.bias + c8 + 4);
-        if (MODE == TCM_CONV5) {
-            pg0 = *reinterpret_cast<const float4*>(a.gamma + c8); pg1 = *reinterpret_cast<const float4*>(a.gamma + c8 + 4);
-            pe0 = *reinterpret_cast<const float4*>(a.beta + c8); pe1 = *reinterpret_cast<const float4*>(a.beta + c8 + 4);
-        }
-        if (a.cond != nullptr && valid) {
-            const int tt = a.t_dev ? (int)a.t_dev[b] : a.t_uniform;
-            const float* cp = a.cond + (size_t)tt * a.CO + c8;
-            pc0 = *reinterpret_cast<const float4*>(cp); pc1 = *reinterpret_cast<const float4*>(cp + 4);
-        }
-        if (a.res_w != nullptr) {
-            pr0 = *reinterpret_cast<const float4*>(a.res_bias + c8); pr1 = *reinterpret_cast<const float4*>(a.res_bias + c8 + 4);
-        } else if (a.res_cm != nullptr && valid) {
-            const float* rp = a.res_cm + ((size_t)b * a.CO + c8) * Lp + 2 + l;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) rid[j] = rp[(size_t)j * Lp];
-        }
-    }
-
-    // ===== epilogue: 16 warps. TMEM lane quarter q = warp & 3 (hardware rule: a warp reads lanes 32*(warp%4)..+31),
-    // column group cg = warp >> 2 -> each thread owns 8 consecutive channels of one row =====
-    mbar_wait(done_bar, 0);
-    __syncwarp();  // lanes 0 of warps 0/1 come from the producer / issuer loops: reconverge before .sync.aligned ops
-    tc_fence_after();
-    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + cg * 8;
-    if (dbg && tid == 64) a.dbg[4] = clock64();  // accumulators ready
-    float v[8];
-    {
-        float v2[8];
-        tc_ld8(taddr, v);           // hi*hi + lo*hi
-        tc_ld8(taddr + TC_NT, v2);  // hi*lo
-#pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] += v2[j];
-    }
-    if (dbg && tid == 64) a.dbg[5] = clock64();  // TMEM read
-
-    if (!full) {
-        float* dst = a.raw_out + (((size_t)tile * gridDim.y + ntile) * 128 + r) * 32 + cg * 8;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) dst[j] = v[j];
-    } else if (MODE == TCM_DOWN) {
-        // stride-2 conv: the MMA evaluated every input position; keep the even ones (out[m] = conv at l = 2m)
-        v[0] += pb0.x; v[1] += pb0.y; v[2] += pb0.z; v[3] += pb0.w;
-        v[4] += pb1.x; v[5] += pb1.y; v[6] += pb1.z; v[7] += pb1.w;
-        if (valid && (l & 1) == 0) tc_store_row(a, v, b, l >> 1, c8, a.L >> 1);
-    } else if (MODE == TCM_UP) {
-        // transposed conv: accumulator 0 = even outputs (2l), accumulator 1 = odd outputs (2l + 1)
-        float w[8], w2[8];
-        tc_ld8(taddr + 2 * TC_NT, w);
-        tc_ld8(taddr + 3 * TC_NT, w2);
-        v[0] += pb0.x; v[1] += pb0.y; v[2] += pb0.z; v[3] += pb0.w;
-        v[4] += pb1.x; v[5] += pb1.y; v[6] += pb1.z; v[7] += pb1.w;
-        w[0] += w2[0] + pb0.x; w[1] += w2[1] + pb0.y; w[2] += w2[2] + pb0.z; w[3] += w2[3] + pb0.w;
-        w[4] += w2[4] + pb1.x; w[5] += w2[5] + pb1.y; w[6] += w2[6] + pb1.z; w[7] += w2[7] + pb1.w;
-        if (valid) {
-            tc_store_row(a, v, b, 2 * l, c8, 2 * a.L);
-            tc_store_row(a, w, b, 2 * l + 1, c8, 2 * a.L);
-        }
-    } else {
-        v[0] += pb0.x; v[1] += pb0.y; v[2] += pb0.z; v[3] += pb0.w;
-        v[4] += pb1.x; v[5] += pb1.y; v[6] += pb1.z; v[7] += pb1.w;
-        gn_mish8<GS, false>(v, valid, r, s, cg, tid, SPT, Lp, a.L, part, pg0, pg1, pe0, pe1, (dbg && tid == 64) ? a.dbg : nullptr);
-        if (dbg && tid == 64) a.dbg[6] = clock64();  // GroupNorm + Mish done
-        // time conditioning (zero when absent), then the residual: fused 1x1 conv accumulators or identity values
-        v[0] += pc0.x; v[1] += pc0.y; v[2] += pc0.z; v[3] += pc0.w;
-        v[4] += pc1.x; v[5] += pc1.y; v[6] += pc1.z; v[7] += pc1.w;
-        if (a.res_w != nullptr) {
-            float rv[8], rv2[8];
-            tc_ld8(taddr + 2 * TC_NT, rv);
-            tc_ld8(taddr + 3 * TC_NT, rv2);
-            v[0] += rv[0] + rv2[0] + pr0.x; v[1] += rv[1] + rv2[1] + pr0.y; v[2] += rv[2] + rv2[2] + pr0.z; v[3] += rv[3] + rv2[3] + pr0.w;
-            v[4] += rv[4] + rv2[4] + pr1.x; v[5] += rv[5] + rv2[5] + pr1.y; v[6] += rv[6] + rv2[6] + pr1.z; v[7] += rv[7] + rv2[7] + pr1.w;
-        } else {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] += rid[j];
-        }
-        if (valid) tc_store_row(a, v, b, l, c8, a.L);
+        tc_fence_before();
     }
 
     // teardown: all TMEM reads done before the allocating warp frees the columns
-    tc_fence_before();
     __syncthreads();
     if (dbg && tid == 64) a.dbg[7] = clock64();  // stores issued, CTA done
     if (warp == 1) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TC_TMEM_COLS) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TCL_TMEM_COLS) : "memory");
     }
 }
 
@@ -573,7 +567,7 @@ int launch_conv5_tc(const TcConvArgs& a, cudaStream_t stream) {
                                                  220 * 1024));                                                     \
             configured = true;                                                                                     \
         }                                                                                                          \
-        MPDB_CHECK_CUDA(launch_kernel(conv5_tc_kernel<M, G>, grid, dim3(TC_THREADS), smem, stream, a));            \
+        MPDB_CHECK_CUDA(launch_kernel(conv5_tc_kernel<M, G>, grid, dim3(TCL_THREADS), smem, stream, a));            \
     }
     if (a.mode == TCM_DOWN) MPDB_TC_LAUNCH(TCM_DOWN, 4)
     else if (a.mode == TCM_UP) MPDB_TC_LAUNCH(TCM_UP, 4)
