@@ -96,6 +96,7 @@ struct mpdb_engine {
     int fuse_max_co = []() { const char* v = getenv("MPDB_FUSE_MAX_CO"); return v ? atoi(v) : 128; }();  // widest fused block (measured: 0 -> 11.85, 32 -> 11.67, 64 -> 11.55, 128 -> 11.47 ms per loop)
     // whole-forward persistent cluster kernel (unet_mega.cu)
     int use_mega = []() { const char* v = getenv("MPDB_MEGA"); return v ? atoi(v) : 1; }();
+    int fuse_final = []() { const char* v = getenv("MPDB_FUSE_FINAL"); return v ? atoi(v) : 1; }();  // projection + DDPM update in the cluster kernel
     bool mega_ok = false;
     std::string mega_why;      // why the configuration cannot run as one launch (falls back to per-layer kernels)
     MegaProgram mega;
@@ -649,12 +650,21 @@ static int launch_op(mpdb_engine* e, const ConvOp& op, const float* x, const lon
 }
 
 // Runs every layer up to (and including) final_conv.0; the 1x1 projection is fused into launch_final.
+// `fin` (optional): the projection + DDPM update that follows the body. When the body runs as the cluster kernel it is
+// executed in that kernel's last epilogue and *fused is set; otherwise the caller launches final_kernel.
 static int run_unet_body(mpdb_engine* e, const float* x, const long long* t_dev, int t_uniform, int B, cudaStream_t st,
-                         bool tc) {
+                         bool tc, const FinalArgs* fin = nullptr, bool* fused = nullptr) {
+    if (fused) *fused = false;
     if (tc && e->use_mega && e->mega_ok && e->alias_buffers && t_dev == nullptr && !e->timeline) {
         MegaProgram P = e->mega;  // one launch: every layer up to final_conv.0 inside thread-block clusters
         P.x = x; P.t = t_uniform; P.B = B;
         P.dbg = e->mega_dbg;
+        const long long fuse_bytes = ((((long long)e->cfg.state_dim * e->cfg.unet_input_dim + 3) & ~3LL) + 128LL * 4 * e->cfg.state_dim) * 4;
+        if (fin && fused && e->fuse_final && fin->t_dev == nullptr && fin->x == x && fuse_bytes <= P.a_bytes) {
+            P.fuse_final = 1;
+            P.fin = *fin;
+            *fused = true;
+        }
         return launch_unet_mega(P, st);
     }
     for (size_t i = 0; i < e->ops.size(); ++i) {
@@ -791,6 +801,9 @@ extern "C" int mpdb_engine_set_option(mpdb_engine* e, const char* name, double v
         } else if (value == 0 && e->mega_dbg) {
             cudaFree(e->mega_dbg); e->mega_dbg = nullptr;
         }
+        if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; e->graph_key.clear(); }
+    } else if (n == "fuse_final") {
+        e->fuse_final = value != 0;
         if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; e->graph_key.clear(); }
     } else if (n == "mega") {
         MPDB_REQUIRE(value == 0 || value == 1 || value == 2, "mega must be 0 (off), 1 (when the batch fits one wave) or 2 (always)");
@@ -998,12 +1011,14 @@ static int enqueue_loop(mpdb_engine* e, mpdb_guide* g, const mpdb_loop_params* p
         // condition-aware precision: the split-bf16 tensor-core path everywhere except where the schedule
         // amplifies eps beyond tc_amp_limit (t = T-1: 4602x), which runs the exact fp32 FMA path
         const bool tc = e->tc_mode == 2 || (e->tc_mode == 1 && e->sched_host[1 * (size_t)T + t] <= e->tc_amp_limit);
-        if (run_unet_body(e, cur, nullptr, t, B, st, tc)) return 1;
+        // the projection + DDPM update of this step: fused into the cluster kernel's last epilogue when the body runs as
+        // one launch, a separate final_kernel launch otherwise
         FinalArgs f;
         fill_final(e, f, cur, nullptr, t, B);
         f.n_hc = p->n_hard_conds;
         for (int k = 0; k < p->n_hard_conds; ++k) f.hc_rows[k] = p->hard_cond_rows[k];
         f.hc_vals = hc_vals;
+        int* fl = e->flags + (long long)it * (p->n_guide_steps + 1);
         if (!guided) {
             f.mode = 2;
             f.noise = step_noise;
@@ -1011,13 +1026,15 @@ static int enqueue_loop(mpdb_engine* e, mpdb_guide* g, const mpdb_loop_params* p
             f.out = nxt;
             f.out2 = chain_slot;
             f.out2_bstride = chain_batch_stride;
-            if (launch_final(f, st)) return 1;
         } else {
-            int* fl = e->flags + (long long)it * (p->n_guide_steps + 1);
             f.mode = 1;
             f.out = nxt;  // model mean; guided in place below
             f.flag_out = fl;
-            if (launch_final(f, st)) return 1;
+        }
+        bool fused = false;
+        if (run_unet_body(e, cur, nullptr, t, B, st, tc, &f, &fused)) return 1;
+        if (!fused && launch_final(f, st)) return 1;
+        if (guided) {
             for (int k = 0; k < p->n_guide_steps; ++k) {
                 const bool klast = (k == p->n_guide_steps - 1);
                 GuideStepArgs a;
@@ -1106,7 +1123,7 @@ extern "C" int mpdb_sample_loop(mpdb_engine* e, mpdb_guide* g, const mpdb_loop_p
                       std::to_string(p->n_steps_without_noise) + "|" + std::to_string(p->t_start_guide) + "|" +
                       std::to_string(p->n_guide_steps) + "|" + std::to_string(p->scale_grad_by_std) + "|" +
                       std::to_string(chain_out != nullptr) + "|" + std::to_string(p->n_hard_conds) + "|tc" +
-                      std::to_string(e->tc_mode) + "/" + std::to_string(e->tc_amp_limit) + "/" + std::to_string(e->fuse_rtb) + "/" + std::to_string(e->use_mega);
+                      std::to_string(e->tc_mode) + "/" + std::to_string(e->tc_amp_limit) + "/" + std::to_string(e->fuse_rtb) + "/" + std::to_string(e->use_mega) + "/" + std::to_string(e->fuse_final);
     for (int k = 0; k < p->n_hard_conds; ++k) key += "," + std::to_string(p->hard_cond_rows[k]);
     for (int k = 0; k < n_iters; ++k) {
         float v = p->noise_std ? p->noise_std[k] : 1.0f;

@@ -123,19 +123,7 @@ struct MegaLayer {
     float* out_cm;            // final_conv.0: fp32 [B][CO][L+4] for the fused projection kernel
 };
 
-struct MegaProgram {
-    MegaLayer layers[MEGA_MAX_LAYERS];
-    int n_layers;
-    int G;        // samples per cluster
-    int B, H, D;
-    int t;        // uniform timestep (row of the time-conditioning tables)
-    int a_bytes;  // size of the A buffer
-    const float* x;  // trajectory [B][H][D] fp32
-    long long* dbg;  // optional timeline: [n_layers][8 ranks][MEGA_DBG] clock64 stamps of cluster 0
-};
-size_t mega_smem_bytes(int a_bytes);
-int mega_max_active_clusters(int a_bytes);
-int launch_unet_mega(const MegaProgram& P, cudaStream_t stream);
+
 
 struct FinalArgs {
     const float* h;     // CM [B][C][L+4]
@@ -166,6 +154,24 @@ struct FinalArgs {
     int B, L, D;
 };
 int launch_final(const FinalArgs& a, cudaStream_t stream);
+
+struct MegaProgram {
+    MegaLayer layers[MEGA_MAX_LAYERS];
+    int n_layers;
+    int G;        // samples per cluster
+    int B, H, D;
+    int t;        // uniform timestep (row of the time-conditioning tables)
+    int a_bytes;  // size of the A buffer
+    const float* x;  // trajectory [B][H][D] fp32
+    // final_conv.1 (1x1, C -> D) + DDPM posterior mean [+ noise, hard conditions, chain slot] in the last layer's epilogue
+    // (what final_kernel does as a separate launch): the timed loop passes its FinalArgs here
+    int fuse_final;
+    FinalArgs fin;
+    long long* dbg;  // optional timeline: [n_layers][8 ranks][MEGA_DBG] clock64 stamps of cluster 0
+};
+size_t mega_smem_bytes(int a_bytes);
+int mega_max_active_clusters(int a_bytes);
+int launch_unet_mega(const MegaProgram& P, cudaStream_t stream);
 
 int launch_repack_conv(const float* src, float* dst, int CO, int CI, int K, int transposed, cudaStream_t stream);
 int launch_time_tables(const float* w1, const float* b1, const float* w3, const float* b3, float* temb_mish, int T,

@@ -159,6 +159,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) unet_mega_kernel(const __grid_c
                 // the first chunk's weights do not depend on the previous layer: wait for them first
                 if (active) mbar_wait(full0 + 8 * (ring_i % MG_STAGES), (uint32_t)(ring_i / MG_STAGES) & 1u);
                 mbar_wait_cluster(a_full, (uint32_t)(l - 1) & 1u);  // operands of this layer have landed (cluster-wide)
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // peers' generic-proxy stores -> tensor core reads
                 tc_fence_after();
                 long long* mdbg = (P.dbg != nullptr && cluster == 0 && lane == 0 && which == 0) ? P.dbg + ((size_t)l * MEGA_CLUSTER + rank) * MEGA_DBG : nullptr;
                 if (mdbg) mdbg[8] = clock64();
@@ -383,16 +384,74 @@ __global__ void __launch_bounds__(MG_THREADS, 1) unet_mega_kernel(const __grid_c
                     }
                 }
             }
-            if (Ld.out_cm != nullptr) {  // final_conv.0: fp32 channel-major output for the fused projection + DDPM update
+            if (Ld.out_cm != nullptr && !P.fuse_final) {  // final_conv.0: fp32 channel-major output for final_kernel
                 float* op = Ld.out_cm + ((size_t)b * Ld.CO + c8) * Lp + 2 + ll;
 #pragma unroll
                 for (int j = 0; j < 8; ++j) op[(size_t)j * Lp] = v[j];
             }
         }
+        if (Ld.out_cm != nullptr && P.fuse_final) {
+            // ===== final_conv.1 (1x1, C -> D) + DDPM posterior mean [+ noise, hard conditions, chain slot] (final_kernel's
+            // arithmetic, diffusion_model_base.py:126-150, sample_functions.py:50-62) on the values still in registers.
+            // The A buffer is dead after this layer's MMAs: [0, D*C) holds the projection weights, then one partial dot
+            // product per (row, 8-channel group, d). =====
+            const FinalArgs& F = P.fin;
+            const int D = P.D, C = Ld.CO;
+            float* wsm = reinterpret_cast<float*>(abuf);           // [D][C]
+            float* psm = wsm + ((D * C + 3) & ~3);                 // [128 rows][4 groups][D]
+            if (active) {
+                for (int i = tid; i < D * C; i += TC_THREADS) wsm[i] = F.w[i];
+                epi_sync();
+                for (int d = 0; d < D; ++d) {
+                    const float* wp = wsm + d * C + c8;
+                    float e = 0.f;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) e = fmaf(wp[j], v[j], e);
+                    psm[(r * 4 + cg) * D + d] = e;
+                }
+                epi_sync();
+                const int tt = P.t;
+                const float sr = F.sr[tt], srm1 = F.srm1[tt], c1 = F.c1[tt], c2 = F.c2[tt], sd = F.stdv[tt];
+                bool viol = false;
+                const int n_out = Ld.SPT * Ld.L * D;
+                for (int idx = tid; idx < n_out; idx += TC_THREADS) {
+                    const int d = idx % D;
+                    const int sl = idx / D;
+                    const int lq = sl % Ld.L, ss = sl / Ld.L;
+                    const int sgq = mt * Ld.SPT + ss;
+                    const int bq = cluster * P.G + sgq;
+                    if (sgq >= P.G || bq >= P.B) continue;
+                    const float* pp = psm + ((ss * Lp + lq) * 4) * D + d;
+                    float e = ((pp[0] + pp[D]) + (pp[2 * D] + pp[3 * D])) + F.bias[d];
+                    const long long gi = ((long long)bq * Ld.L + lq) * D + d;
+                    float res = e;
+                    if (F.mode != 0) {
+                        const float xv = F.x[gi];
+                        // same operation order as the reference: sr*x - srm1*eps ; clamp ; c1*x0 + c2*x  (no FMA contraction)
+                        float x0 = F.predict_epsilon ? __fsub_rn(__fmul_rn(sr, xv), __fmul_rn(srm1, e)) : e;
+                        if (F.clip_denoised) x0 = fminf(fmaxf(x0, -1.f), 1.f);
+                        res = __fadd_rn(__fmul_rn(c1, x0), __fmul_rn(c2, xv));
+                        if (F.mode == 2) {
+                            const float nz = (tt == 0) ? 0.f : F.noise[gi];
+                            res = __fadd_rn(res, __fmul_rn(__fmul_rn(sd, nz), F.noise_std));
+                            for (int k = 0; k < F.n_hc; ++k)  // later entries win, as in the reference's dict iteration
+                                if (F.hc_rows[k] == lq) res = F.hc_vals[((long long)k * P.B + bq) * D + d];
+                        } else {
+                            viol |= (res > 1.0001f) || (res < -1.0001f);
+                        }
+                    }
+                    F.out[gi] = res;
+                    if (F.out2) F.out2[(long long)bq * F.out2_bstride + (long long)lq * D + d] = res;
+                }
+                if (F.flag_out != nullptr && __any_sync(0xffffffffu, viol) && lane == 0) atomicOr(F.flag_out, 1);
+            }
+        }
         if (dbg) dbg[7] = clock64();  // stores issued
-        // generic-proxy stores -> tensor core (shared memory) / bulk copies (global skip tensor) of the consumers
+        // generic-proxy stores -> async proxy of the consumers. The skip tensor (global, read by bulk copies several layers
+        // later) is fenced here; the A-buffer slices are fenced by the consuming issuer warp after its acquire (the stores
+        // are complete in the destination's shared memory once the cluster-scope release below is observed), which takes a
+        // store round trip off every layer hand-off.
         if (Ld.skip_out_hi != nullptr) asm volatile("fence.proxy.async;" ::: "memory");
-        else asm volatile("fence.proxy.async.shared::cluster;" ::: "memory");
         if (dbg) dbg[3] = clock64();  // outputs delivered
         __syncwarp();
         if (lane < MEGA_CLUSTER && l + 1 < P.n_layers) mbar_arrive_cluster(map_to_cta(a_full, (uint32_t)lane));

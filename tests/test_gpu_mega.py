@@ -83,3 +83,48 @@ def test_mega_one_wave_policy():
         eng.set_option("mega", 1)
         model.tensor_cores = "auto"
     assert eng.mega_info(100)[0]
+
+
+def test_mega_repeated_runs_are_bit_identical():
+    """Hand-off protocol check (DSMEM stores -> cluster-scope release/acquire -> tensor-core reads): a stale or torn
+    operand read would change some output; 300 back-to-back forwards over two batch shapes must be bit-identical."""
+    model = cuda_model("panda_opt1_h64")
+    model.tensor_cores = "force"
+    eng = model._engine()
+    try:
+        for batch, t in ((100, 5), (37, 17)):
+            g = torch.Generator().manual_seed(batch)
+            x = torch.randn((batch, 64, 14), generator=g).cuda()
+            ref = eng.unet_forward_uniform(x, t)
+            acc = torch.zeros((), device="cuda", dtype=torch.int64)
+            for _ in range(150):
+                out = eng.unet_forward_uniform(x, t)
+                acc += (out != ref).sum()
+            assert int(acc) == 0
+    finally:
+        model.tensor_cores = "auto"
+
+
+def test_fused_projection_and_ddpm_update_match_the_separate_kernel():
+    """final_conv.1 + posterior mean + noise + hard conditions inside the cluster kernel's last epilogue (option
+    fuse_final) against the separate final_kernel launch: same chain up to the rounding of the 32-term projection."""
+    model = cuda_model("panda_opt1_h64")
+    model.tensor_cores = "auto"
+    eng = model._engine()
+    B, H, D = 21, 64, 14
+    n_iters = C.T_DIFF + C.N_EXTRA
+    g = torch.Generator().manual_seed(77)
+    noise = torch.randn((n_iters + 1, B, H, D), generator=g).cuda()
+    hard = {0: torch.linspace(-0.5, 0.5, D).cuda(), H - 1: torch.linspace(0.4, -0.4, D).cuda()}
+    kw = dict(n_diffusion_steps_without_noise=C.N_EXTRA, noise_std_extra_schedule_fn=lambda _t: C.NOISE_STD)
+    chains = {}
+    try:
+        for fuse in (1, 0):
+            eng.set_option("fuse_final", fuse)
+            chains[fuse] = model.run_inference(None, hard, n_samples=B, horizon=H, return_chain=True, noise=noise, **kw)
+    finally:
+        eng.set_option("fuse_final", 1)
+    assert torch.isfinite(chains[1]).all()
+    for k, v in hard.items():
+        assert torch.equal(chains[1][:, :, k, :], v.expand(n_iters + 1, B, D))
+    assert rel(chains[1], chains[0]) < 2e-5, rel(chains[1], chains[0])
