@@ -395,10 +395,18 @@ class GaussianDiffusionModel(nn.Module):
         eng = self._engine()
         steps = list(reversed(range(-n_extra, self.n_diffusion_steps)))
         if noise is None:
-            # identical generator consumption to the reference: randn(shape), then one randn_like per step
-            noise = torch.empty((len(steps) + 1, *shape), device=device, dtype=torch.float32)
-            for k in range(len(steps) + 1):
-                torch.randn(shape, device=device, out=noise[k])
+            # identical generator consumption to the reference: randn(shape), then one randn_like per step (randn is
+            # empty + normal_). The buffer and its per-step views are kept between calls: allocating and slicing them
+            # is most of the host time of a call, and the loop copies the noise into its own staging anyway.
+            key = (len(steps) + 1, tuple(shape), str(device))
+            cache = self.__dict__.get("_noise_cache")
+            if cache is None or cache[0] != key:
+                buf = torch.empty((len(steps) + 1, *shape), device=device, dtype=torch.float32)
+                cache = (key, buf, list(buf.unbind(0)))
+                self.__dict__["_noise_cache"] = cache
+            noise = cache[1]
+            for view in cache[2]:
+                view.normal_()
         else:
             noise = noise.to(device=device, dtype=torch.float32).contiguous()
             if tuple(noise.shape) != (len(steps) + 1, *shape):
@@ -406,7 +414,14 @@ class GaussianDiffusionModel(nn.Module):
         if noise_std_extra_schedule_fn is None:
             ns = [1.0] * len(steps)
         else:
-            ns = [float(noise_std_extra_schedule_fn(torch.tensor(i, dtype=torch.long))) for i in steps]
+            # the reference calls the schedule with the step index as a tensor; the index tensors are cached
+            tcache = self.__dict__.setdefault("_step_tensors", {})
+            ns = []
+            for i in steps:
+                ti = tcache.get(i)
+                if ti is None:
+                    ti = tcache[i] = torch.tensor(i, dtype=torch.long)
+                ns.append(float(noise_std_extra_schedule_fn(ti)))
         tsg = float(t_start_guide)
         handle = guide._handle(device, shape[1]) if guide is not None else None
         x, chain = eng.sample_loop(noise, hard_conds, handle, n_extra, tsg, n_guide_steps if guide is not None else 0,
@@ -492,6 +507,10 @@ class GaussianDiffusionModel(nn.Module):
         if context is not None:
             for k, v in context.items():
                 context[k] = v.unsqueeze(0).repeat(n_samples, 1)
+        if not return_chain:
+            # the reference keeps the whole chain and returns its last entry; the last entry is the sample itself
+            return self.conditional_sample(hard_conds, context=context, batch_size=n_samples, return_chain=False,
+                                           **diffusion_kwargs)
         samples, chain = self.conditional_sample(hard_conds, context=context, batch_size=n_samples, return_chain=True,
                                                  **diffusion_kwargs)
         trajs_chain_normalized = chain.permute(1, 0, 2, 3)  # 'b diffsteps h d -> diffsteps b h d'
