@@ -229,6 +229,11 @@ __device__ __forceinline__ float clip_scale(float n, float max_norm) {
     return fminf(fmaxf(n, 0.f), max_norm) / n;
 }
 
+// KIND: 1 = Panda, 0 = point mass (compile-time copy of g.robot_kind); SPGT: spheres per sphere group actually present
+// (ceil(n_spheres / NSG)). Specialising removes the other robot's code and the unrolled bodies of absent sphere slots: the
+// kernel runs every instruction once per launch, so its time is largely instruction fetch (ncu: 29 % of stall samples
+// "no instruction" before the split), and a smaller kernel is a faster one.
+template <int KIND, int SPGT>
 __global__ void __launch_bounds__(GUIDE_THREADS) guide_step_kernel(GuideDev g, GuideStepArgs a) {
     extern __shared__ __align__(16) float smem[];
     const int H = a.H, D = g.D, q = g.q_dim, NI = g.n_interp, NTH = GUIDE_THREADS;
@@ -284,7 +289,7 @@ __global__ void __launch_bounds__(GUIDE_THREADS) guide_step_kernel(GuideDev g, G
                 int i1 = i0 + (i0 < H - 1 ? 1 : 0);
                 if (k == 0) { i0s[i] = i0; w1s[i] = l1; }
                 const float qk = k < q ? __fadd_rn(__fmul_rn(l0, xu[i0 * D + k]), __fmul_rn(l1, xu[i1 * D + k])) : 0.f;
-                if (g.robot_kind == 1) {
+                if (KIND == 1) {
                     float sv, cv;
                     sincosf(qk, &sv, &cv);
                     sc_sin[k * FK_ROWS + il] = sv;
@@ -295,7 +300,7 @@ __global__ void __launch_bounds__(GUIDE_THREADS) guide_step_kernel(GuideDev g, G
             }
             __syncthreads();
             // (1b) three threads per row (one per matrix row): the kinematic chain on the precomputed sines / cosines
-            if (g.robot_kind == 1) {
+            if (KIND == 1) {
                 const int il = tid % FK_ROWS, r3 = tid / FK_ROWS;
                 if (r3 < 3 && ibase + il < NI) {
                     float sq[7], cq[7];
@@ -324,9 +329,9 @@ __global__ void __launch_bounds__(GUIDE_THREADS) guide_step_kernel(GuideDev g, G
                     float dq[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
                     // this group's spheres are sg, sg + NSG, ...; all their texel gathers are issued before any is
                     // consumed (latency overlap)
-                    float tsdf[SPG], tg[SPG][3];
+                    float tsdf[SPGT], tg[SPGT][3];
 #pragma unroll
-                    for (int u = 0; u < SPG; ++u) {
+                    for (int u = 0; u < SPGT; ++u) {
                         const int s = sg + u * NSG;
                         tsdf[u] = 3.4e38f; tg[u][0] = tg[u][1] = tg[u][2] = 0.f;
                         if (s < g.n_spheres) {
@@ -335,13 +340,13 @@ __global__ void __launch_bounds__(GUIDE_THREADS) guide_step_kernel(GuideDev g, G
                         }
                     }
 #pragma unroll
-                    for (int u = 0; u < SPG; ++u) {
+                    for (int u = 0; u < SPGT; ++u) {
                         const int s = sg + u * NSG;
                         if (s >= g.n_spheres) continue;
                         const float viol = __fsub_rn(__fadd_rn(g.sphere_r[s], g.margin), tsdf[u]);
                         if (viol > 0.f) {
                             const float gx = -tg[u][0], gy = -tg[u][1], gz = -tg[u][2];  // d cost / d p
-                            if (g.robot_kind == 1) {
+                            if (KIND == 1) {
                                 const float p0 = cen[(s * 3 + 0) * FK_ROWS], p1 = cen[(s * 3 + 1) * FK_ROWS], p2 = cen[(s * 3 + 2) * FK_ROWS];
                                 const int nj = g.sphere_frame[s] < 7 ? g.sphere_frame[s] : 7;
 #pragma unroll
@@ -585,12 +590,23 @@ int guide_launch_step(mpdb_guide* gd, const GuideStepArgs& a, cudaStream_t strea
     MPDB_REQUIRE(g.n_interp >= 1, "guide: n_interp must be >= 1");
     const size_t smem = guide_smem_bytes(g, a.H);
     MPDB_REQUIRE(smem <= 220 * 1024, "guide: trajectory does not fit in shared memory");
-    static size_t configured = 0;
-    if (smem > configured) {
-        MPDB_CHECK_CUDA(cudaFuncSetAttribute(guide_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-        configured = 220 * 1024;
+    const int spg = (g.n_spheres + NSG - 1) / NSG;
+    MPDB_REQUIRE(spg >= 1 && spg <= SPG, "guide: bad sphere count");
+#define MPDB_GUIDE_LAUNCH(K, S)                                                                                              \
+    {                                                                                                                        \
+        static bool configured = false;                                                                                      \
+        if (!configured) {                                                                                                   \
+            MPDB_CHECK_CUDA(cudaFuncSetAttribute(guide_step_kernel<K, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)); \
+            configured = true;                                                                                               \
+        }                                                                                                                    \
+        MPDB_CHECK_CUDA(launch_kernel(guide_step_kernel<K, S>, dim3(a.B), dim3(GUIDE_THREADS), smem, stream, g, a));         \
     }
-    MPDB_CHECK_CUDA(launch_kernel(guide_step_kernel, dim3(a.B), dim3(GUIDE_THREADS), smem, stream, g, a));
+    if (g.robot_kind == 1) {
+        if (spg <= 2) MPDB_GUIDE_LAUNCH(1, 2) else MPDB_GUIDE_LAUNCH(1, SPG)
+    } else {
+        if (spg <= 1) MPDB_GUIDE_LAUNCH(0, 1) else MPDB_GUIDE_LAUNCH(0, SPG)
+    }
+#undef MPDB_GUIDE_LAUNCH
     MPDB_LAUNCH_CHECK();
     return 0;
 }
