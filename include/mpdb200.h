@@ -135,6 +135,9 @@ int mpdb_add_noise(mpdb_engine* e, float* x, const int64_t* t, const float* nois
  * chain strides are in floats (so [B,S,H,D] and [S,B,H,D] are both expressible). */
 int mpdb_sample_loop(mpdb_engine* e, mpdb_guide* g, const mpdb_loop_params* p, const float* noise, float* x_out,
                      float* chain_out, int64_t chain_step_stride, int64_t chain_batch_stride, int32_t B, void* stream);
+/* counter bumped whenever the engine reallocates device buffers, reloads parameters or changes an option: a caller that
+ * captured mpdb_sample_loop (use_cuda_graph = 0) into its own CUDA graph must re-capture when it changes */
+int64_t mpdb_engine_generation(mpdb_engine* e);
 /* kernels launched by this engine/guide pair since creation (bench.py's gpu_launches) */
 int64_t mpdb_launch_count(void);
 

@@ -57,6 +57,7 @@ SYMBOLS = {
     "mpdb_engine_set_option": (C.c_int, [_P, C.c_char_p, C.c_double]),
     "mpdb_engine_finalize": (C.c_int, [_P, _P]),
     "mpdb_unet_forward": (C.c_int, [_P, _P, _P, _P, C.c_int32, _P]),
+    "mpdb_engine_generation": (C.c_int64, [_P]),
     "mpdb_unet_forward_uniform": (C.c_int, [_P, _P, C.c_int32, _P, C.c_int32, _P]),
     "mpdb_engine_mega_info": (C.c_int, [_P, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32),
                                         C.POINTER(C.c_int32), C.c_char_p, C.c_int]),

@@ -95,6 +95,8 @@ struct mpdb_engine {
     int fuse_rtb = 1;          // cluster-fused residual blocks on the tensor-core path
     int fuse_max_co = []() { const char* v = getenv("MPDB_FUSE_MAX_CO"); return v ? atoi(v) : 128; }();  // widest fused block (measured: 0 -> 11.85, 32 -> 11.67, 64 -> 11.55, 128 -> 11.47 ms per loop)
     // whole-forward persistent cluster kernel (unet_mega.cu)
+    long long generation = 0;  // bumped whenever device buffers are reallocated or an option changes: launches captured
+                               // by a caller (torch CUDA graph around mpdb_sample_loop) are stale afterwards
     int use_mega = []() { const char* v = getenv("MPDB_MEGA"); return v ? atoi(v) : 1; }();
     int fuse_final = []() { const char* v = getenv("MPDB_FUSE_FINAL"); return v ? atoi(v) : 1; }();  // projection + DDPM update in the cluster kernel
     bool mega_ok = false;
@@ -360,6 +362,7 @@ static void build_mega(mpdb_engine* e, int B);
 
 static int ensure_workspace(mpdb_engine* e, int B) {
     if (B <= e->work_batch) return 0;
+    ++e->generation;
     if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; e->graph_key.clear(); }
     MPDB_CHECK_CUDA(cudaDeviceSynchronize());
     const size_t nb = e->bufs.size();
@@ -785,8 +788,11 @@ extern "C" int mpdb_engine_set_schedule(mpdb_engine* e, const float* sr, const f
     return 0;
 }
 
+extern "C" int64_t mpdb_engine_generation(mpdb_engine* e) { return e ? (int64_t)e->generation : -1; }
+
 extern "C" int mpdb_engine_set_option(mpdb_engine* e, const char* name, double value) {
     MPDB_REQUIRE(e && name, "mpdb_engine_set_option: null argument");
+    ++e->generation;
     const std::string n(name);
     if (n == "tc_mode") {
         MPDB_REQUIRE(value == 0 || value == 1 || value == 2, "tc_mode must be 0 (off), 1 (auto) or 2 (force)");
@@ -872,6 +878,7 @@ extern "C" int mpdb_engine_finalize(mpdb_engine* e, void* stream) {
     }
     MPDB_CHECK_CUDA(cudaStreamSynchronize(st));
     e->finalized = true;
+    ++e->generation;
     return 0;
 }
 
@@ -1103,6 +1110,7 @@ extern "C" int mpdb_sample_loop(mpdb_engine* e, mpdb_guide* g, const mpdb_loop_p
             e->flags = nullptr;
             MPDB_CHECK_CUDA(cudaMalloc(&e->flags, sizeof(int) * (size_t)n_flags_needed));
             e->n_flags = n_flags_needed;
+            ++e->generation;
         }
     }
     if (!p->use_cuda_graph)

@@ -394,6 +394,12 @@ class GaussianDiffusionModel(nn.Module):
         device = self.betas.device
         eng = self._engine()
         steps = list(reversed(range(-n_extra, self.n_diffusion_steps)))
+        if (noise is None and self.use_cuda_graph and self.__dict__.get("graph_rng", True)
+                and not torch.cuda.is_current_stream_capturing()):
+            out = self._graphed_loop(eng, shape, hard_conds, return_chain, n_extra, steps, guide, n_guide_steps,
+                                     scale_grad_by_std, t_start_guide, noise_std_extra_schedule_fn)
+            if out is not None:
+                return out
         if noise is None:
             # identical generator consumption to the reference: randn(shape), then one randn_like per step (randn is
             # empty + normal_). The buffer and its per-step views are kept between calls: allocating and slicing them
@@ -429,6 +435,78 @@ class GaussianDiffusionModel(nn.Module):
         if return_chain:
             return x, chain.transpose(0, 1)  # [B, steps+1, H, D] like torch.stack(chain, dim=1)
         return x
+
+    def _graphed_loop(self, eng, shape, hard_conds, return_chain, n_extra, steps, guide, n_guide_steps, scale_grad_by_std,
+                      t_start_guide, noise_std_extra_schedule_fn):
+        """One CUDA-graph launch per call for the API path that draws its own noise: the per-step `normal_()` draws (the
+        reference's generator consumption, graph-safe Philox offsets) AND the whole reverse loop are captured together, so
+        a call costs one launch on the host instead of 31 RNG launches + the loop. Start/goal are copied into static
+        buffers before the replay; the result is cloned out of the graph's memory. Returns None if capture is impossible."""
+        device = self.betas.device
+        if noise_std_extra_schedule_fn is None:
+            ns = (1.0,) * len(steps)
+        else:
+            tcache = self.__dict__.setdefault("_step_tensors", {})
+            ns = []
+            for i in steps:
+                ti = tcache.get(i)
+                if ti is None:
+                    ti = tcache[i] = torch.tensor(i, dtype=torch.long)
+                ns.append(float(noise_std_extra_schedule_fn(ti)))
+            ns = tuple(ns)
+        handle = guide._handle(device, shape[1]) if guide is not None else None
+        rows = tuple(hard_conds.keys())
+        eng.sync_params()
+        gen = int(eng.lib.mpdb_engine_generation(eng.handle))
+        key = (tuple(shape), n_extra, handle.value if handle is not None else None, id(guide), int(n_guide_steps),
+               bool(scale_grad_by_std), float(t_start_guide), ns, bool(return_chain), rows, str(device), gen,
+               torch.cuda.current_device())
+        cache = self.__dict__.setdefault("_loop_graphs", {})
+        entry = cache.get(key)
+        if entry is None:
+            if len(cache) > 8:
+                cache.clear()
+            try:
+                noise = torch.empty((len(steps) + 1, *shape), device=device, dtype=torch.float32)
+                views = list(noise.unbind(0))
+                static_hc = {r: torch.empty((shape[0], shape[2]), device=device, dtype=torch.float32) for r in rows}
+
+                def run_once():
+                    for v in views:
+                        v.normal_()
+                    return eng.sample_loop(noise, static_hc, handle, n_extra, float(t_start_guide),
+                                           n_guide_steps if guide is not None else 0, scale_grad_by_std, list(ns),
+                                           return_chain, False)
+
+                for r in rows:
+                    static_hc[r].copy_(hard_conds[r].to(device=device, dtype=torch.float32).expand_as(static_hc[r]))
+                rng_state = torch.cuda.get_rng_state(device)
+                side = torch.cuda.Stream(device=device)
+                side.wait_stream(torch.cuda.current_stream(device))
+                with torch.cuda.stream(side):
+                    run_once()  # warm-up: engine workspace, lazily configured kernels
+                torch.cuda.current_stream(device).wait_stream(side)
+                torch.cuda.synchronize(device)
+                torch.cuda.set_rng_state(rng_state, device)  # the warm-up must not consume the caller's generator
+                if int(eng.lib.mpdb_engine_generation(eng.handle)) != gen:  # the warm-up (re)allocated: re-key
+                    gen = int(eng.lib.mpdb_engine_generation(eng.handle))
+                    key = key[:11] + (gen,) + key[12:]
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    x_out, chain = run_once()
+                entry = (graph, static_hc, x_out, chain)
+                cache[key] = entry
+            except Exception as exc:  # capture not possible in this context: the plain path still works
+                self.__dict__["graph_rng"] = False
+                self.__dict__["_graph_rng_error"] = repr(exc)
+                return None
+        graph, static_hc, x_out, chain = entry
+        for r in rows:
+            static_hc[r].copy_(hard_conds[r].to(device=device, dtype=torch.float32).expand_as(static_hc[r]))
+        graph.replay()
+        if return_chain:
+            return x_out.clone(), chain.transpose(0, 1).clone()
+        return x_out.clone()
 
     @torch.no_grad()
     def ddim_sample(self, shape, hard_conds, context=None, return_chain=False, t_start_guide=torch.inf, guide=None,
