@@ -109,7 +109,10 @@ struct mpdb_engine {
     long long* dbg_buf = nullptr;  // optional per-op timeline stamps (option "timeline")
     int timeline = 0;
     int tc_mode = 1;           // 0 = exact fp32 FMA path only, 1 = auto (loop steps below tc_amp_limit), 2 = force
-    float tc_amp_limit = 64.f; // steps whose sqrt(1/abar - 1) exceeds this run the exact path (t = T-1)
+    // steps whose sqrt(1/abar - 1) exceeds this run the exact path. With the 22-bit scaled-fp16 operand split the tensor-core
+    // path matches the fp32 FMA path even at t = T-1 (eps amplified 4602x: step error 3.5e-4 vs 4.4e-4 against the oracle,
+    // profiles/r01c_precision_tlast.txt), so no step is excluded by default; a finite limit restores the carve-out.
+    float tc_amp_limit = 3.0e38f;
     long long work_floats_per_sample = 0;
     int work_batch = 0;
     long long final_w = -1, final_b = -1;
@@ -1016,7 +1019,7 @@ static int enqueue_loop(mpdb_engine* e, mpdb_guide* g, const mpdb_loop_params* p
         const float ns = p->noise_std ? p->noise_std[it] : 1.0f;
 
         // condition-aware precision: the split-bf16 tensor-core path everywhere except where the schedule
-        // amplifies eps beyond tc_amp_limit (t = T-1: 4602x), which runs the exact fp32 FMA path
+        // amplifies eps beyond tc_amp_limit (no step by default, see tc_amp_limit), which runs the exact fp32 FMA path
         const bool tc = e->tc_mode == 2 || (e->tc_mode == 1 && e->sched_host[1 * (size_t)T + t] <= e->tc_amp_limit);
         // the projection + DDPM update of this step: fused into the cluster kernel's last epilogue when the body runs as
         // one launch, a separate final_kernel launch otherwise

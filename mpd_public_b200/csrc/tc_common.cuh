@@ -2,6 +2,7 @@
 // PTX wrappers for mbarrier / cp.async.bulk / tcgen05 / DSMEM, the split-bf16 helpers and the GroupNorm+Mish epilogue.
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 
 #include "common.cuh"
@@ -119,10 +120,14 @@ __device__ __forceinline__ uint64_t tc_desc(uint32_t saddr, uint32_t lbo_bytes, 
     d |= (uint64_t)1 << 46;
     return d;
 }
-// Instruction descriptor for kind::f16: c_format F32 (bit 4), a/b format BF16 (bits 7, 10), K-major A and B,
-// N >> 3 at bits [17,23), M >> 4 at bits [24,29).
+// Instruction descriptor for kind::f16: c_format F32 (bit 4), a/b format F16 (0 at bits [7,10) and [10,13); BF16 would be 1),
+// K-major A and B, N >> 3 at bits [17,23), M >> 4 at bits [24,29).
 __host__ __device__ constexpr uint32_t tc_idesc(int M, int N) {
+#ifdef MPDB_EXP_BF16FMT
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+#else
+    return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+#endif
 }
 __device__ __forceinline__ void tc_ld32(uint32_t taddr, float (&v)[32]) {
     uint32_t r[32];
@@ -164,23 +169,33 @@ __device__ __forceinline__ void tc_ld8x3(uint32_t t0, uint32_t t1, uint32_t t2, 
     for (int i = 0; i < 8; ++i) { a[i] = __uint_as_float(r[i]); b[i] = __uint_as_float(r[8 + i]); c[i] = __uint_as_float(r[16 + i]); }
 }
 
-__device__ __forceinline__ void split_bf16(float x, unsigned short& hi, unsigned short& lo) {
-    __nv_bfloat16 h = __float2bfloat16_rn(x);
-    __nv_bfloat16 l = __float2bfloat16_rn(x - __bfloat162float(h));
-    hi = __bfloat16_as_ushort(h);
-    lo = __bfloat16_as_ushort(l);
+// Operand split x = hi + lo * 2^-11 with hi = fp16(x), lo = fp16((x - hi) * 2^11): 22 significant bits in two fp16 planes.
+// The lo plane is stored scaled by 2^11 so that it stays in fp16's normal range whatever |x| (unscaled it would fall into
+// the subnormals below |x| ~ 0.1 and lose its low bits); the products that contain one lo factor are accumulated in their
+// own TMEM columns and multiplied by 2^-11 (exact) in the epilogue. hi*hi + (hi*lo + lo*hi) * 2^-11 reproduces the fp32
+// product to ~2^-22 (the dropped lo*lo term), 2^5 better than a bf16 split at the same cost. |x| is clamped to the fp16
+// range (activations and weights of this network are O(1)).
+constexpr float TC_LO_SCALE = 2048.f, TC_LO_UNSCALE = 1.f / 2048.f;
+__device__ __forceinline__ void split_hl(float x, unsigned short& hi, unsigned short& lo) {
+    x = fminf(fmaxf(x, -65504.f), 65504.f);
+    const __half h = __float2half_rn(x);
+    const __half l = __float2half_rn((x - __half2float(h)) * TC_LO_SCALE);
+    hi = __half_as_ushort(h);
+    lo = __half_as_ushort(l);
 }
 
-// 8 fp32 values -> 8 bf16 "hi" and 8 bf16 "lo" (x ~ hi + lo), packed for 16-byte stores. Same values as split_bf16;
-// cvt.rn.bf16x2.f32 converts two at a time and bf16 -> fp32 is a shift.
+// 8 fp32 values -> 8 "hi" and 8 scaled "lo" halves, packed for 16-byte stores. Same values as split_hl; cvt.rn.f16x2.f32
+// converts two at a time.
 __device__ __forceinline__ void pack_split8(const float (&v)[8], uint4& ph, uint4& pl) {
     uint32_t h[4], l[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(h[k]) : "f"(v[2 * k + 1]), "f"(v[2 * k]));  // {hi16: v[2k+1], lo16: v[2k]}
-        const float r0 = v[2 * k] - __uint_as_float(h[k] << 16);
-        const float r1 = v[2 * k + 1] - __uint_as_float(h[k] & 0xffff0000u);
-        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(l[k]) : "f"(r1), "f"(r0));
+        const float a = fminf(fmaxf(v[2 * k], -65504.f), 65504.f), b = fminf(fmaxf(v[2 * k + 1], -65504.f), 65504.f);
+        asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(h[k]) : "f"(b), "f"(a));  // {hi16: b, lo16: a}
+        float h0, h1;
+        asm("{\n\t.reg .f16 lo, hi;\n\tmov.b32 {lo, hi}, %2;\n\tcvt.f32.f16 %0, lo;\n\tcvt.f32.f16 %1, hi;\n\t}" : "=f"(h0), "=f"(h1) : "r"(h[k]));
+        const float r0 = (a - h0) * TC_LO_SCALE, r1 = (b - h1) * TC_LO_SCALE;
+        asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(l[k]) : "f"(r1), "f"(r0));
     }
     ph = make_uint4(h[0], h[1], h[2], h[3]);
     pl = make_uint4(l[0], l[1], l[2], l[3]);
@@ -201,7 +216,7 @@ __device__ __forceinline__ void tc_store_row(const TcConvArgs& a, const float (&
         const size_t o = (((size_t)to * (a.CO / 8) + c8 / 8) * TC_RT + (so * Lpo + lo + 2)) * 8;
         unsigned short h[8], lo8[8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) split_bf16(v[e], h[e], lo8[e]);
+        for (int e = 0; e < 8; ++e) split_hl(v[e], h[e], lo8[e]);
         uint4 ph, pl;
         ph.x = h[0] | ((uint32_t)h[1] << 16); ph.y = h[2] | ((uint32_t)h[3] << 16);
         ph.z = h[4] | ((uint32_t)h[5] << 16); ph.w = h[6] | ((uint32_t)h[7] << 16);

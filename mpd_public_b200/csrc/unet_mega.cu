@@ -257,7 +257,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) unet_mega_kernel(const __grid_c
         const bool valid = active && (s < Ld.SPT) && (ll < Ld.L) && (sg < P.G) && (b < P.B);
         const int c8 = nc * TC_NT + cg * 8;
         float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        float w[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // UP: odd outputs
+        float4 pb0 = z4, pb1 = z4;  // bias (also needed when the odd rows of an up-sampling layer are delivered)
 
         if (Ld.type == MG_INPUT) {
             // trajectory x [B][H][D] fp32 -> channels [cg*8, cg*8+8) of row ll (channels >= D stay zero)
@@ -268,8 +268,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) unet_mega_kernel(const __grid_c
                     if (cg * 8 + e < P.D) v[e] = xp[cg * 8 + e];
             }
         } else {
-            float4 pb0 = z4, pb1 = z4, pg0 = z4, pg1 = z4, pe0 = z4, pe1 = z4, pc0 = z4, pc1 = z4, pr0 = z4, pr1 = z4;
-            float rv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            float4 pg0 = z4, pg1 = z4, pe0 = z4, pe1 = z4, pc0 = z4, pc1 = z4, pr0 = z4, pr1 = z4;
             if (active) {
                 // parameters are fetched while the MMAs run
                 pb0 = *reinterpret_cast<const float4*>(Ld.bias + c8); pb1 = *reinterpret_cast<const float4*>(Ld.bias + c8 + 4);
@@ -293,20 +292,11 @@ __global__ void __launch_bounds__(MG_THREADS, 1) unet_mega_kernel(const __grid_c
                     float v2[8], v3[8];
                     tc_ld8x3(taddr, taddr + 2 * TC_NT, taddr + TC_NT, v, v3, v2);  // hi*hi, lo*hi, hi*lo
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) v[j] = (v[j] + v3[j]) + v2[j];
+                    for (int j = 0; j < 8; ++j) v[j] = fmaf(v3[j] + v2[j], TC_LO_UNSCALE, v[j]);
                 }
-                if (Ld.type == MG_UP) {
-                    float w2[8], w3[8];
-                    tc_ld8x3(taddr + 128, taddr + 128 + 2 * TC_NT, taddr + 128 + TC_NT, w, w3, w2);
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) w[j] = (w[j] + w3[j]) + w2[j];
-                } else if (Ld.res_mode == 2) {
-                    float rv2[8], rv3[8];
-                    tc_ld8x3(taddr + 128, taddr + 128 + 2 * TC_NT, taddr + 128 + TC_NT, rv, rv3, rv2);
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) rv[j] = (rv[j] + rv3[j]) + rv2[j];
-                }
-                tc_fence_before();
+                // the second accumulator (odd outputs of an up-sampling layer, the block's 1x1 residual conv) stays in TMEM
+                // until it is needed: it is not overwritten before the next layer's MMAs, and holding it in registers
+                // through GroupNorm costs spills
                 if (dbg) dbg[4] = clock64();  // accumulators in registers
             }
             // this CTA no longer reads its A buffer: clear it if the next layer uses another layout (issuer warp 0 then tells the cluster)
@@ -320,10 +310,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) unet_mega_kernel(const __grid_c
             if (active) {
                 v[0] += pb0.x; v[1] += pb0.y; v[2] += pb0.z; v[3] += pb0.w;
                 v[4] += pb1.x; v[5] += pb1.y; v[6] += pb1.z; v[7] += pb1.w;
-                if (Ld.type == MG_UP) {
-                    w[0] += pb0.x; w[1] += pb0.y; w[2] += pb0.z; w[3] += pb0.w;
-                    w[4] += pb1.x; w[5] += pb1.y; w[6] += pb1.z; w[7] += pb1.w;
-                } else if (Ld.type == MG_CONV5) {
+                if (Ld.type == MG_CONV5) {
                     switch (Ld.gs) {
                         case 4: gn_mish8<4, true>(v, valid, r, s, cg, tid, Ld.SPT, Lp, Ld.L, part, pg0, pg1, pe0, pe1, dbg ? dbg + 4 : nullptr); break;
                         case 8: gn_mish8<8, true>(v, valid, r, s, cg, tid, Ld.SPT, Lp, Ld.L, part, pg0, pg1, pe0, pe1, dbg ? dbg + 4 : nullptr); break;
@@ -333,6 +320,10 @@ __global__ void __launch_bounds__(MG_THREADS, 1) unet_mega_kernel(const __grid_c
                     v[0] += pc0.x; v[1] += pc0.y; v[2] += pc0.z; v[3] += pc0.w;
                     v[4] += pc1.x; v[5] += pc1.y; v[6] += pc1.z; v[7] += pc1.w;
                     if (Ld.res_mode == 2) {
+                        float rv[8], rv2[8], rv3[8];
+                        tc_ld8x3(taddr + 128, taddr + 128 + 2 * TC_NT, taddr + 128 + TC_NT, rv, rv3, rv2);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) rv[j] = fmaf(rv3[j] + rv2[j], TC_LO_UNSCALE, rv[j]);
                         v[0] += rv[0] + pr0.x; v[1] += rv[1] + pr0.y; v[2] += rv[2] + pr0.z; v[3] += rv[3] + pr0.w;
                         v[4] += rv[4] + pr1.x; v[5] += rv[5] + pr1.y; v[6] += rv[6] + pr1.z; v[7] += rv[7] + pr1.w;
                     } else if (Ld.res_mode == 1) {
@@ -351,39 +342,47 @@ __global__ void __launch_bounds__(MG_THREADS, 1) unet_mega_kernel(const __grid_c
         if (dbg) dbg[2] = clock64();  // epilogue arithmetic done
         mbar_wait_cluster(a_free, (uint32_t)l & 1u);
         if (dbg) dbg[6] = clock64();  // every CTA's MMAs of this layer have retired
-        if (valid) {
-            if (Ld.oNC > 0) {
-                const int n_out = Ld.type == MG_UP ? 2 : 1;
-                const bool emit = Ld.type != MG_DOWN || (ll & 1) == 0;
+        if (Ld.oNC > 0) {
+            const int n_out = Ld.type == MG_UP ? 2 : 1;
+            const bool emit = valid && (Ld.type != MG_DOWN || (ll & 1) == 0);
+            const int mt2 = sg / Ld.oSPT, s2 = sg - mt2 * Ld.oSPT;
+            for (int k = 0; k < n_out; ++k) {
+                if (k == 1) {  // up-sampling: the odd output row comes from the second accumulator (warp-wide TMEM load)
+                    float w2[8], w3[8];
+                    tc_ld8x3(taddr + 128, taddr + 128 + 2 * TC_NT, taddr + 128 + TC_NT, v, w3, w2);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) v[j] = fmaf(w3[j] + w2[j], TC_LO_UNSCALE, v[j]);
+                    v[0] += pb0.x; v[1] += pb0.y; v[2] += pb0.z; v[3] += pb0.w;
+                    v[4] += pb1.x; v[5] += pb1.y; v[6] += pb1.z; v[7] += pb1.w;
+                }
                 if (emit) {
-                    const int mt2 = sg / Ld.oSPT, s2 = sg - mt2 * Ld.oSPT;
-                    for (int k = 0; k < n_out; ++k) {
-                        const int lo = Ld.type == MG_DOWN ? (ll >> 1) : Ld.type == MG_UP ? 2 * ll + k : ll;
-                        uint4 ph, pl;
-                        if (k == 0) pack_split8(v, ph, pl); else pack_split8(w, ph, pl);
-                        const uint32_t off = (uint32_t)(((c8 / 8) * Ld.oRT + (s2 * Ld.oLp + lo + 2)) * 16);
-                        const uint32_t local_hi = abuf_u32 + off, local_lo = local_hi + (uint32_t)Ld.o_plane;
-                        for (int jj = 0; jj < Ld.oNC; ++jj) {
-                            // staggered destination order: at any moment the writers of a row tile address different peers
-                            int j = rank + 1 + jj;
-                            j -= (j / Ld.oNC) * Ld.oNC;
-                            const uint32_t cta = (uint32_t)(mt2 * Ld.oNC + j);
-                            if ((int)cta == rank) {  // own A buffer: plain shared-memory stores
-                                *reinterpret_cast<uint4*>(abuf + off) = ph;
-                                *reinterpret_cast<uint4*>(abuf + off + Ld.o_plane) = pl;
-                            } else {
-                                st_cluster_v4(map_to_cta(local_hi, cta), ph);
-                                st_cluster_v4(map_to_cta(local_lo, cta), pl);
-                            }
+                    const int lo = Ld.type == MG_DOWN ? (ll >> 1) : Ld.type == MG_UP ? 2 * ll + k : ll;
+                    uint4 ph, pl;
+                    pack_split8(v, ph, pl);
+                    const uint32_t off = (uint32_t)(((c8 / 8) * Ld.oRT + (s2 * Ld.oLp + lo + 2)) * 16);
+                    const uint32_t local_hi = abuf_u32 + off, local_lo = local_hi + (uint32_t)Ld.o_plane;
+                    for (int jj = 0; jj < Ld.oNC; ++jj) {
+                        // staggered destination order: at any moment the writers of a row tile address different peers
+                        int j = rank + 1 + jj;
+                        j -= (j / Ld.oNC) * Ld.oNC;
+                        const uint32_t cta = (uint32_t)(mt2 * Ld.oNC + j);
+                        if ((int)cta == rank) {  // own A buffer: plain shared-memory stores
+                            *reinterpret_cast<uint4*>(abuf + off) = ph;
+                            *reinterpret_cast<uint4*>(abuf + off + Ld.o_plane) = pl;
+                        } else {
+                            st_cluster_v4(map_to_cta(local_hi, cta), ph);
+                            st_cluster_v4(map_to_cta(local_lo, cta), pl);
                         }
-                        if (Ld.skip_out_hi != nullptr) {  // skip connection: same-level layout in global memory
-                            const size_t o = ((((size_t)cluster * Ld.MT + mt) * (Ld.CO / 8) + c8 / 8) * Ld.RT + (r + 2)) * 8;
-                            *reinterpret_cast<uint4*>(Ld.skip_out_hi + o) = ph;
-                            *reinterpret_cast<uint4*>(Ld.skip_out_lo + o) = pl;
-                        }
+                    }
+                    if (Ld.skip_out_hi != nullptr) {  // skip connection: same-level layout in global memory
+                        const size_t o = ((((size_t)cluster * Ld.MT + mt) * (Ld.CO / 8) + c8 / 8) * Ld.RT + (r + 2)) * 8;
+                        *reinterpret_cast<uint4*>(Ld.skip_out_hi + o) = ph;
+                        *reinterpret_cast<uint4*>(Ld.skip_out_lo + o) = pl;
                     }
                 }
             }
+        }
+        if (valid) {
             if (Ld.out_cm != nullptr && !P.fuse_final) {  // final_conv.0: fp32 channel-major output for final_kernel
                 float* op = Ld.out_cm + ((size_t)b * Ld.CO + c8) * Lp + 2 + ll;
 #pragma unroll
@@ -453,6 +452,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) unet_mega_kernel(const __grid_c
         // store round trip off every layer hand-off.
         if (Ld.skip_out_hi != nullptr) asm volatile("fence.proxy.async;" ::: "memory");
         if (dbg) dbg[3] = clock64();  // outputs delivered
+        tc_fence_before();  // all TMEM reads of this layer precede the hand-off
         __syncwarp();
         if (lane < MEGA_CLUSTER && l + 1 < P.n_layers) mbar_arrive_cluster(map_to_cta(a_full, (uint32_t)lane));
     }

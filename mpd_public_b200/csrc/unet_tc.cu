@@ -213,7 +213,7 @@ __global__ void __launch_bounds__(TCL_THREADS, 1) conv5_tc_kernel(TcConvArgs a) 
             float v2[8], v3[8];
             tc_ld8x3(taddr, taddr + 2 * TC_NT, taddr + TC_NT, v, v3, v2);  // hi*hi, lo*hi, hi*lo
 #pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = (v[j] + v3[j]) + v2[j];
+            for (int j = 0; j < 8; ++j) v[j] = fmaf(v3[j] + v2[j], TC_LO_UNSCALE, v[j]);
         }
         if (dbg && tid == 64) a.dbg[5] = clock64();  // TMEM read
 
@@ -232,8 +232,10 @@ __global__ void __launch_bounds__(TCL_THREADS, 1) conv5_tc_kernel(TcConvArgs a) 
             tc_ld8x3(taddr + 128, taddr + 128 + 2 * TC_NT, taddr + 128 + TC_NT, w, w3, w2);
             v[0] += pb0.x; v[1] += pb0.y; v[2] += pb0.z; v[3] += pb0.w;
             v[4] += pb1.x; v[5] += pb1.y; v[6] += pb1.z; v[7] += pb1.w;
-            w[0] = (w[0] + w3[0]) + w2[0] + pb0.x; w[1] = (w[1] + w3[1]) + w2[1] + pb0.y; w[2] = (w[2] + w3[2]) + w2[2] + pb0.z; w[3] = (w[3] + w3[3]) + w2[3] + pb0.w;
-            w[4] = (w[4] + w3[4]) + w2[4] + pb1.x; w[5] = (w[5] + w3[5]) + w2[5] + pb1.y; w[6] = (w[6] + w3[6]) + w2[6] + pb1.z; w[7] = (w[7] + w3[7]) + w2[7] + pb1.w;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) w[j] = fmaf(w3[j] + w2[j], TC_LO_UNSCALE, w[j]);
+            w[0] += pb0.x; w[1] += pb0.y; w[2] += pb0.z; w[3] += pb0.w;
+            w[4] += pb1.x; w[5] += pb1.y; w[6] += pb1.z; w[7] += pb1.w;
             if (valid) {
                 tc_store_row(a, v, b, 2 * l, c8, 2 * a.L);
                 tc_store_row(a, w, b, 2 * l + 1, c8, 2 * a.L);
@@ -249,8 +251,10 @@ __global__ void __launch_bounds__(TCL_THREADS, 1) conv5_tc_kernel(TcConvArgs a) 
             if (a.res_w != nullptr) {
                 float rv[8], rv2[8], rv3[8];
                 tc_ld8x3(taddr + 128, taddr + 128 + 2 * TC_NT, taddr + 128 + TC_NT, rv, rv3, rv2);
-                v[0] += (rv[0] + rv3[0]) + rv2[0] + pr0.x; v[1] += (rv[1] + rv3[1]) + rv2[1] + pr0.y; v[2] += (rv[2] + rv3[2]) + rv2[2] + pr0.z; v[3] += (rv[3] + rv3[3]) + rv2[3] + pr0.w;
-                v[4] += (rv[4] + rv3[4]) + rv2[4] + pr1.x; v[5] += (rv[5] + rv3[5]) + rv2[5] + pr1.y; v[6] += (rv[6] + rv3[6]) + rv2[6] + pr1.z; v[7] += (rv[7] + rv3[7]) + rv2[7] + pr1.w;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) rv[j] = fmaf(rv3[j] + rv2[j], TC_LO_UNSCALE, rv[j]);
+                v[0] += rv[0] + pr0.x; v[1] += rv[1] + pr0.y; v[2] += rv[2] + pr0.z; v[3] += rv[3] + pr0.w;
+                v[4] += rv[4] + pr1.x; v[5] += rv[5] + pr1.y; v[6] += rv[6] + pr1.z; v[7] += rv[7] + pr1.w;
             } else {
 #pragma unroll
                 for (int j = 0; j < 8; ++j) v[j] += rid[j];
@@ -279,7 +283,7 @@ __global__ void __launch_bounds__(TCL_THREADS, 1) conv5_tc_kernel(TcConvArgs a) 
 // Threads: 16 epilogue warps (one of them hosts the MMA issuer lane) + 1 producer warp.
 // ---------------------------------------------------------------------------------------------------
 constexpr int RTB_THREADS = TC_THREADS + 32;
-constexpr int RTB_TMEM_COLS = 256;  // conv0 [0,64), conv1 [64,128), residual conv [128,192)
+constexpr int RTB_TMEM_COLS = 512;  // hi*hi | hi*lo: conv0 [0,64), conv1 [64,128), residual conv [128,192); lo*hi: the same + 256 ([.., +32))
 
 
 template <int GS, int NSTAGE>
@@ -372,6 +376,7 @@ __global__ void __launch_bounds__(RTB_THREADS, 1) rtb_tc_kernel(TcRtbArgs args) 
         const uint64_t dA_hi = tc_desc(a_hi ? a_hi : st, TC_RT * 16, 128);
         const uint64_t dA_lo = tc_desc(a_lo ? a_lo : st + TC_A_PLANE_BYTES, TC_RT * 16, 128);
         const uint64_t dB = tc_desc(st + 2 * TC_A_PLANE_BYTES, 2 * TC_NT * 16, 128);
+        bool first_lo = first;  // the lo*hi accumulator starts with the same K-chunk as the main one
         for (int tap = 0; tap < ntaps; ++tap) {
             const int shift = centre ? 2 : tap;
 #pragma unroll
@@ -380,7 +385,8 @@ __global__ void __launch_bounds__(RTB_THREADS, 1) rtb_tc_kernel(TcRtbArgs args) 
                 const uint64_t bofs = (uint64_t)((tap * 2 * TC_B_TAP_BYTES + kk * 2 * (2 * TC_NT * 16)) >> 4);
                 tc_mma_bf16(dcol, dA_hi + aofs, dB + bofs, idesc64, first ? 0u : 1u);
                 first = false;
-                tc_mma_bf16(dcol, dA_lo + aofs, dB + bofs, idesc32, 1u);
+                tc_mma_bf16(dcol + 256, dA_lo + aofs, dB + bofs, idesc32, first_lo ? 0u : 1u);  // lo*hi: own columns (scaled sum)
+                first_lo = false;
             }
         }
         tc_commit(empty0 + 8 * s);
@@ -414,11 +420,10 @@ __global__ void __launch_bounds__(RTB_THREADS, 1) rtb_tc_kernel(TcRtbArgs args) 
     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + cg * 8;
     float v[8];
     {
-        float v2[8];
-        tc_ld8(taddr, v);
-        tc_ld8(taddr + TC_NT, v2);
+        float v2[8], v3[8];
+        tc_ld8x3(taddr, taddr + 256, taddr + TC_NT, v, v3, v2);  // hi*hi, lo*hi, hi*lo
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] += v2[j];
+        for (int j = 0; j < 8; ++j) v[j] = fmaf(v3[j] + v2[j], TC_LO_UNSCALE, v[j]);
     }
     v[0] += pb0.x; v[1] += pb0.y; v[2] += pb0.z; v[3] += pb0.w;
     v[4] += pb1.x; v[5] += pb1.y; v[6] += pb1.z; v[7] += pb1.w;
@@ -431,7 +436,7 @@ __global__ void __launch_bounds__(RTB_THREADS, 1) rtb_tc_kernel(TcRtbArgs args) 
         if (valid) {
             unsigned short h[8], lo8[8];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) split_bf16(v[e], h[e], lo8[e]);
+            for (int e = 0; e < 8; ++e) split_hl(v[e], h[e], lo8[e]);
             ph.x = h[0] | ((uint32_t)h[1] << 16); ph.y = h[2] | ((uint32_t)h[3] << 16);
             ph.z = h[4] | ((uint32_t)h[5] << 16); ph.w = h[6] | ((uint32_t)h[7] << 16);
             pl.x = lo8[0] | ((uint32_t)lo8[1] << 16); pl.y = lo8[2] | ((uint32_t)lo8[3] << 16);
@@ -481,21 +486,21 @@ __global__ void __launch_bounds__(RTB_THREADS, 1) rtb_tc_kernel(TcRtbArgs args) 
     __syncwarp();
     tc_fence_after();
     {
-        float v2[8];
-        tc_ld8(taddr + 2 * TC_NT, v);
-        tc_ld8(taddr + 3 * TC_NT, v2);
+        float v2[8], v3[8];
+        tc_ld8x3(taddr + 2 * TC_NT, taddr + 2 * TC_NT + 256, taddr + 3 * TC_NT, v, v3, v2);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] += v2[j];
+        for (int j = 0; j < 8; ++j) v[j] = fmaf(v3[j] + v2[j], TC_LO_UNSCALE, v[j]);
     }
     v[0] += pb0.x; v[1] += pb0.y; v[2] += pb0.z; v[3] += pb0.w;
     v[4] += pb1.x; v[5] += pb1.y; v[6] += pb1.z; v[7] += pb1.w;
     gn_mish8<GS, true>(v, valid, r, s, cg, tid, SPT, Lp, a0.L, part, pg0, pg1, pe0, pe1);
     if (a1.res_w != nullptr) {
-        float rv[8], rv2[8];
-        tc_ld8(taddr + 4 * TC_NT, rv);
-        tc_ld8(taddr + 5 * TC_NT, rv2);
-        v[0] += rv[0] + rv2[0] + pr0.x; v[1] += rv[1] + rv2[1] + pr0.y; v[2] += rv[2] + rv2[2] + pr0.z; v[3] += rv[3] + rv2[3] + pr0.w;
-        v[4] += rv[4] + rv2[4] + pr1.x; v[5] += rv[5] + rv2[5] + pr1.y; v[6] += rv[6] + rv2[6] + pr1.z; v[7] += rv[7] + rv2[7] + pr1.w;
+        float rv[8], rv2[8], rv3[8];
+        tc_ld8x3(taddr + 4 * TC_NT, taddr + 4 * TC_NT + 256, taddr + 5 * TC_NT, rv, rv3, rv2);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) rv[j] = fmaf(rv3[j] + rv2[j], TC_LO_UNSCALE, rv[j]);
+        v[0] += rv[0] + pr0.x; v[1] += rv[1] + pr0.y; v[2] += rv[2] + pr0.z; v[3] += rv[3] + pr0.w;
+        v[4] += rv[4] + pr1.x; v[5] += rv[5] + pr1.y; v[6] += rv[6] + pr1.z; v[7] += rv[7] + pr1.w;
     } else {
 #pragma unroll
         for (int j = 0; j < 8; ++j) v[j] += rid[j];
@@ -602,7 +607,7 @@ __global__ void pack_tc_weights_kernel(const float* __restrict__ src, unsigned s
         const int co = ntile * TC_NT + nn;
         const int stap = (int)((perm >> (4 * tap)) & 0xF);
         unsigned short hi = 0, lo = 0;
-        if (ci < CI_src) split_bf16(src[((long long)ci * ntaps + stap) * CO + co], hi, lo);
+        if (ci < CI_src) split_hl(src[((long long)ci * ntaps + stap) * CO + co], hi, lo);
         const long long blk = ((long long)ntile * (CI / TC_KCH) + chunk) * (2LL * ntaps * (TC_KCH / 8) * TC_NT * 8);
         const long long row0 = (((long long)tap * (TC_KCH / 8) + kg) * (2 * TC_NT)) * 8;
         dst[blk + row0 + (long long)nn * 8 + e] = hi;
@@ -636,7 +641,7 @@ __global__ void blc_to_tc_kernel(const float* __restrict__ x, unsigned short* __
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
                 h[e] = 0; w[e] = 0;
-                if (kg * 8 + e < D) split_bf16(xp[kg * 8 + e], h[e], w[e]);
+                if (kg * 8 + e < D) split_hl(xp[kg * 8 + e], h[e], w[e]);
             }
             const long long o = (((long long)tile * (C / 8) + kg) * TC_RT + (s * Lp + l + 2)) * 8;
             uint4 ph, pl;
@@ -668,7 +673,7 @@ __global__ void cm_to_tc_kernel(const float* __restrict__ cm, unsigned short* __
         const int c = (int)((i / L) % C);
         const int b = (int)(i / ((long long)L * C));
         unsigned short h, lw;
-        split_bf16(cm[((long long)b * C + c) * Lp + 2 + l], h, lw);
+        split_hl(cm[((long long)b * C + c) * Lp + 2 + l], h, lw);
         const int tile = b / SPT, s = b - tile * SPT;
         const long long o = (((long long)tile * (C / 8) + c / 8) * TC_RT + (s * Lp + l + 2)) * 8 + (c % 8);
         hi[o] = h;

@@ -32,6 +32,7 @@ __host__ __device__ constexpr uint32_t idesc(int M, int N) {
 }
 
 // layout: 0 none, 6 = 32B, 4 = 64B, 2 = 128B swizzle
+__device__ int g_fmt_f16;  // 1: a/b format F16 instead of BF16
 __global__ void mma_probe(int M, int N, int layout, int n_mma, int use_test, long long* out, int n_issuers) {
     extern __shared__ __align__(1024) unsigned char sm[];
     __shared__ uint64_t bar;
@@ -56,7 +57,7 @@ __global__ void mma_probe(int M, int N, int layout, int n_mma, int use_test, lon
         uint64_t dA, dB;
         if (layout == 0) { dA = desc(a0, 132 * 16, 128, 0); dB = desc(b0, N * 16, 128, 0); }
         else { dA = desc(a0, 16, 8 * rowb, layout); dB = desc(b0, 16, 8 * rowb, layout); }
-        const uint32_t id = idesc(M, N);
+        const uint32_t id = g_fmt_f16 ? (idesc(M, N) & ~((1u << 7) | (1u << 10))) : idesc(M, N);
         const int ksteps = layout == 0 ? 1 : rowb / 32;  // K16 steps inside one swizzle row
         const long long t0 = clock64();
         for (int i = 0; i < n_mma; ++i) {
@@ -101,6 +102,9 @@ int main() {
                     printf("%-6s %4d %4d  %s | %10.1f %14.1f   (%d)\n", names[li], M, N, use_test ? "test" : "try ", (double)h[0] / n, (double)h[1] / n,
                            (M < 128 ? 128 : M) * N / 256);
                 }
+    for (int fmt = 0; fmt < 2; ++fmt) {
+    cudaMemcpyToSymbol(g_fmt_f16, &fmt, sizeof(int));
+    printf("operand format %s\n", fmt ? "F16" : "BF16");
     printf("issuers  N | issue cyc/mma (per issuer)  total cyc per mma (all issuers)\n");
     for (int ni = 1; ni <= 4; ++ni)
         for (int N : {32, 64}) {
@@ -114,5 +118,6 @@ int main() {
             for (int k = 0; k < ni; ++k) mx = h[2 * k + 1] > mx ? h[2 * k + 1] : mx;
             printf("%7d %3d | %10.1f %24.1f\n", ni, N, (double)h[0] / n, (double)mx / (n * ni));
         }
+    }
     return 0;
 }
