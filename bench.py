@@ -386,7 +386,7 @@ def main():
         ach_tf = dom_flops / (dom_ms * 1e-3) / 1e12
         flops_traj, sdf_bytes = algorithmic_work(H, D, opt, prob.robot.n_spheres, n_grid, prob.robot.ws_dim)
         if tcm.any():
-            kname = ("mpdb::conv5_tc_kernel (tcgen05.mma kind::f16 split-bf16 x3, TMEM accumulators, cp.async.bulk staging; "
+            kname = ("mpdb::conv5_tc_kernel (tcgen05.mma kind::f16 fp16-split x3, TMEM accumulators, cp.async.bulk staging; "
                      f"Conv1d k5 + GroupNorm + Mish [+cond][+residual]; residual blocks with C_out <= 128 are one cluster-fused "
                      f"launch, rtb_tc_kernel), {int(dom.sum())} launches per UNet forward")
             note = ("achieved = algorithmic (useful) 2*MAC FLOPs of its launches / their summed CUDA-event time; the tensor "
@@ -414,7 +414,7 @@ def main():
             dom_ms, dom_flops, fwd_ms = float(bms.value), float(bfl.value), float(bms.value)
             ach_tf = dom_flops / (dom_ms * 1e-3) / 1e12
             kname = (f"mpdb::unet_mega_kernel (whole TemporalUnet forward in ONE launch: {(B + mega_G - 1) // mega_G} clusters of 8 CTAs x "
-                     f"{mega_G} trajectories, {mega_layers} layers; tcgen05.mma kind::f16 split-bf16 x3 from two issuer warps, TMEM "
+                     f"{mega_G} trajectories, {mega_layers} layers; tcgen05.mma kind::f16 fp16-split x3 from two issuer warps, TMEM "
                      "accumulators, activations exchanged through distributed shared memory, weights via cp.async.bulk ring; "
                      f"{mega_smem} B shared memory per CTA), {bn.value} launch per UNet forward")
             note = ("achieved = algorithmic (useful) 2*MAC FLOPs of one forward / CUDA-event time of the launch; the tensor pipe "

@@ -107,7 +107,7 @@ __device__ __forceinline__ float mishf(float x) {
     const float n = e * (e + 2.f);
     return x * __fdiv_rn(n, n + 2.f);
 }
-// fast variant for the tensor-core epilogue (ex2.approx + rcp.approx, ~1e-6 relative; the split-bf16 MMA itself is
+// fast variant for the tensor-core epilogue (ex2.approx + rcp.approx, ~1e-6 relative; the fp16-split MMA itself is
 // ~1e-5): the epilogue is instruction-issue bound, so the ~40-instruction precise version would dominate it.
 __device__ __forceinline__ float mishf_fast(float x) {
     const float e = __expf(fminf(x, 20.f));

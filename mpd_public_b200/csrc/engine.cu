@@ -66,7 +66,7 @@ struct ConvOp {
     int cin = 0, res_cin = 0;
     int tc_in0 = -2, tc_res0 = -2;  // buffers the tensor-core path reads instead of the external BLC trajectory
     int cin_tc = 0, res_cin_tc = 0; // input widths on the tensor-core path (trajectory padded to 32 channels)
-    long long w_tc = -1, res_w_tc = -1;  // offsets (bf16 elements) into packed_tc
+    long long w_tc = -1, res_w_tc = -1;  // offsets (16-bit elements) into packed_tc
 };
 
 }  // namespace mpdb
@@ -87,9 +87,9 @@ struct mpdb_engine {
     std::vector<PackJob> packs;
     std::vector<std::pair<std::string, long long>> cond_jobs;  // cond_mlp prefix -> table offset
     float* work = nullptr;    // activations (fp32, channel-major with halo)
-    unsigned short* packed_tc = nullptr;  // split-bf16 weights in tensor-core layout
+    unsigned short* packed_tc = nullptr;  // fp16-split weights in tensor-core layout
     long long packed_tc_elems = 0;
-    unsigned short* work_tc = nullptr;    // activations in tensor-core layout (bf16 hi/lo planes)
+    unsigned short* work_tc = nullptr;    // activations in tensor-core layout (fp16 hi / scaled-lo planes)
     std::vector<long long> tc_off, tc_plane;  // per buffer: offset of the hi plane, elements per plane
     std::vector<long long> cm_off;            // per buffer: float offset of its (possibly shared) physical slot
     int fuse_rtb = 1;          // cluster-fused residual blocks on the tensor-core path
@@ -1018,7 +1018,7 @@ static int enqueue_loop(mpdb_engine* e, mpdb_guide* g, const mpdb_loop_params* p
         const bool guided = g != nullptr && p->n_guide_steps > 0 && (long long)i < (long long)p->t_start_guide;
         const float ns = p->noise_std ? p->noise_std[it] : 1.0f;
 
-        // condition-aware precision: the split-bf16 tensor-core path everywhere except where the schedule
+        // condition-aware precision: the fp16-split tensor-core path everywhere except where the schedule
         // amplifies eps beyond tc_amp_limit (no step by default, see tc_amp_limit), which runs the exact fp32 FMA path
         const bool tc = e->tc_mode == 2 || (e->tc_mode == 1 && e->sched_host[1 * (size_t)T + t] <= e->tc_amp_limit);
         // the projection + DDPM update of this step: fused into the cluster kernel's last epilogue when the body runs as

@@ -43,7 +43,7 @@ struct ConvArgs {
     int S;   // samples per CTA
     int NT;  // output channels per CTA
     int G;   // intra-CTA split-K groups (1, 2 or 4)
-    // optional second copy of the output in the tensor-core ("TC") layout, bf16 hi/lo planes (unet_tc.cu)
+    // optional second copy of the output in the tensor-core ("TC") layout, fp16 hi / scaled-lo planes (unet_tc.cu)
     unsigned short* out_hi;
     unsigned short* out_lo;
 };
@@ -58,7 +58,7 @@ constexpr int TC_KCH = 32;   // input channels per pipeline stage
 enum TcMode { TCM_CONV5 = 0, TCM_DOWN = 1, TCM_UP = 2 };
 
 struct TcConvArgs {
-    // main conv input: up to two concatenated sources in TC layout (bf16 hi / lo planes)
+    // main conv input: up to two concatenated sources in TC layout (fp16 hi / scaled-lo planes)
     const unsigned short *in0_hi, *in0_lo, *in1_hi, *in1_lo;
     int c0, c1;
     const unsigned short* w;      // packed [CO/32][CI/32][hi|lo][5][4][32][8]

@@ -1,5 +1,5 @@
 // Shared device-side pieces of the tensor-core path (unet_tc.cu per-layer kernels, unet_mega.cu whole-forward kernel):
-// PTX wrappers for mbarrier / cp.async.bulk / tcgen05 / DSMEM, the split-bf16 helpers and the GroupNorm+Mish epilogue.
+// PTX wrappers for mbarrier / cp.async.bulk / tcgen05 / DSMEM, the fp16-split helpers and the GroupNorm+Mish epilogue.
 #pragma once
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
@@ -202,7 +202,7 @@ __device__ __forceinline__ void pack_split8(const float (&v)[8], uint4& ph, uint
 }
 
 // Stores 8 consecutive output channels [c8, c8+8) of sample b at output position lo in the fp32 CM layout and (split
-// into bf16 hi/lo) in the TC layout of an activation with CO channels and L_out positions.
+// into fp16 hi / scaled lo) in the TC layout of an activation with CO channels and L_out positions.
 __device__ __forceinline__ void tc_store_row(const TcConvArgs& a, const float (&v)[8], int b, int lo, int c8, int L_out) {
     const int Lpo = L_out + 4;
     if (a.out_cm != nullptr) {
@@ -236,7 +236,7 @@ __device__ __forceinline__ void tc_store_row(const TcConvArgs& a, const float (&
 //            published; everyone reads its two groups' values after the last barrier. With at most 8 samples per tile
 //            levels 1 and 2 are one shuffle-connected pass (two barriers in all), otherwise they are separated by a barrier.
 // Accumulating the cross-row part in fp64 removes the cancellation of the one-pass formula; what remains is the fp32
-// rounding of the 16-term row-group partials (~6e-8 * (1 + mean^2/var)), far below the split-bf16 MMA error. Three short
+// rounding of the 16-term row-group partials (~6e-8 * (1 + mean^2/var)), far below the fp16-split MMA error. Three short
 // barriers, no redundant fp64 work. Deterministic and independent of how samples are tiled. BAR1: named barrier of the 512 epilogue
 // threads (fused kernel, where a producer warp is not part of the epilogue) instead of __syncthreads.
 template <int GS, bool BAR1>

@@ -10,6 +10,7 @@
 
 #include "common.cuh"
 #include "internal.h"
+#include "tc_common.cuh"
 
 namespace mpdb {
 
@@ -386,7 +387,7 @@ __global__ void __launch_bounds__(512) conv_kernel(ConvArgs a) {
             *reinterpret_cast<float2*>(op + 2) = make_float2(acc[2][j], acc[3][j]);
         }
         if (a.out_hi != nullptr) {
-            // second copy in the tensor-core layout (bf16 hi/lo planes, unet_tc.cu): 4 channels = 8 bytes per row
+            // second copy in the tensor-core layout (fp16 hi / scaled-lo planes, unet_tc.cu): 4 channels = 8 bytes per row
             const int SPT = TC_RT / Lp;
             const int tile = b / SPT, sb = b - tile * SPT;
 #pragma unroll
@@ -394,12 +395,7 @@ __global__ void __launch_bounds__(512) conv_kernel(ConvArgs a) {
                 const long long o = (((long long)tile * (a.CO / 8) + co / 8) * TC_RT + (sb * Lp + c.l0 + i + HALO)) * 8 + (co & 7);
                 unsigned short h[4], l[4];
 #pragma unroll
-                for (int j = 0; j < TC; ++j) {
-                    __nv_bfloat16 hb = __float2bfloat16_rn(acc[i][j]);
-                    __nv_bfloat16 lb = __float2bfloat16_rn(acc[i][j] - __bfloat162float(hb));
-                    h[j] = __bfloat16_as_ushort(hb);
-                    l[j] = __bfloat16_as_ushort(lb);
-                }
+                for (int j = 0; j < TC; ++j) split_hl(acc[i][j], h[j], l[j]);  // the tensor-core path's operand split
                 *reinterpret_cast<uint2*>(a.out_hi + o) = make_uint2(h[0] | ((unsigned)h[1] << 16), h[2] | ((unsigned)h[3] << 16));
                 *reinterpret_cast<uint2*>(a.out_lo + o) = make_uint2(l[0] | ((unsigned)l[1] << 16), l[2] | ((unsigned)l[3] << 16));
             }

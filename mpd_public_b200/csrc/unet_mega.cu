@@ -6,7 +6,7 @@
 // cluster of 8 CTAs owns G (8 at H=64) trajectories from the input projection to final_conv.0:
 //
 //   * activations never leave the cluster: the current tensor lives in every CTA's shared memory ("A buffer") in the
-//     tcgen05 no-swizzle K-major operand layout [plane hi|lo][C/8][RT rows][8 x bf16]; a layer's epilogue writes its
+//     tcgen05 no-swizzle K-major operand layout [plane hi|lo][C/8][RT rows][8 x fp16]; a layer's epilogue writes its
 //     32 output channels straight into the A buffer of every CTA that consumes them through distributed shared memory
 //     (st.shared::cluster), so the next layer's MMAs read local shared memory;
 //   * per layer the 8 CTAs tile (row tiles of <=128 padded rows) x (32-channel output chunks): 8x1 at L=64, 3x2 at
@@ -26,8 +26,8 @@
 // shared-memory port, so the overlap bought nothing (273 -> 309 us per forward); pushing slices with cp.async.bulk
 // shared::cta -> shared::cluster (14 B/clk per SM in an 8-way all-to-all, the same network limit).
 //
-// Arithmetic follows the per-layer tensor-core path (same split-bf16 products per K-chunk, fp32 residual values kept in
-// registers); the three partial products are summed from separate accumulators, so the two paths agree to the split-bf16
+// Arithmetic follows the per-layer tensor-core path (same fp16-split products per K-chunk, fp32 residual values kept in
+// registers); the three partial products are summed from separate accumulators, so the two paths agree to the fp16-split
 // rounding level (~1.5e-5 relative, tested), and each is deterministic and independent of the batch composition.
 #include "tc_common.cuh"
 

@@ -8,18 +8,18 @@
 //        128 rows per CTA = the 128 TMEM lanes; rows that fall on a halo are computed and ignored;
 //   n  = 32 output channels per CTA (a whole number of GroupNorm groups);
 //   the k=5 window is NOT materialised: the activation tile is staged ONCE per K-chunk in the canonical
-//   no-swizzle K-major layout [k-group][row][8 x bf16] and each tap is the same tile with the matrix
+//   no-swizzle K-major layout [k-group][row][8 x fp16] and each tap is the same tile with the matrix
 //   descriptor's start address advanced by one 16-byte row.
 //
-// Precision: fp32 parity with eps amplified by up to 4602x rules out plain bf16, so operands are split
-// x = hi + lo (two bf16 planes) and each K step computes hi*hi + lo*hi + hi*lo with fp32 TMEM accumulation
-// (~2^-16 relative per product) in TWO MMAs: the weight tile stores [hi rows | lo rows] as one N=64 operand, so
-// A_hi x [W_hi;W_lo] yields hi*hi and hi*lo with a single shared-memory read of A_hi (SS-mode MMAs at small N are
-// bound by the A-operand read), and A_lo x W_hi accumulates into the hi*hi columns. The engine still runs the exact fp32 FMA path at the steps
-// where the schedule amplifies eps by more than `tc_amp_limit` (t = T-1), see engine.cu.
+// Precision: fp32 parity with eps amplified by up to 4602x rules out a single 16-bit operand, so operands are split
+// x = hi + lo * 2^-11 (two fp16 planes, the lo plane stored scaled by 2^11 to stay in fp16's normal range: 22 significant
+// bits, tc_common.cuh split_hl) and each K step computes hi*hi, hi*lo and lo*hi with fp32 TMEM accumulation into separate
+// columns, combined as hi*hi + (hi*lo + lo*hi) * 2^-11 in the epilogue (~2^-22 relative per product: the fp32 FMA path's
+// own accuracy). The weight tile stores [hi rows | lo rows] as one N=64 operand, so A_hi x [W_hi;W_lo] yields hi*hi and
+// hi*lo with a single shared-memory read of A_hi; A_lo x W_hi (N=32) is issued by the second issuer warp.
 //
 // Global "TC layout" of an activation [B, C, L] (one tensor per plane):
-//   plane[tile][C/8][132][8]  bf16,  tile = b / SPT, row = (b % SPT) * (L + 4) + l + 2 ; halo / spare rows are
+//   plane[tile][C/8][132][8]  fp16,  tile = b / SPT, row = (b % SPT) * (L + 4) + l + 2 ; halo / spare rows are
 //   zero forever. A K-chunk of a CTA's tile is ONE contiguous block -> one cp.async.bulk per plane.
 #include "tc_common.cuh"
 
@@ -275,7 +275,7 @@ __global__ void __launch_bounds__(TCL_THREADS, 1) conv5_tc_kernel(TcConvArgs a) 
 // ---------------------------------------------------------------------------------------------------
 // Cluster-fused ResidualTemporalBlock (layers.py:323-355) for C_out <= 128: both k=5 convolutions in ONE launch.
 // The CO/32 CTAs that share a row tile form a thread-block cluster. Each runs conv0 for its 32 channels as in
-// conv5_tc_kernel, and its epilogue writes the split-bf16 h1 values straight into the conv1 A-operand buffer ("A2",
+// conv5_tc_kernel, and its epilogue writes the fp16-split h1 values straight into the conv1 A-operand buffer ("A2",
 // the full C_out x 132-row tile, both planes) of EVERY CTA of the cluster through distributed shared memory; a
 // cluster-scope mbarrier per CTA counts the writers. conv1 then reads its activations from local shared memory (no
 // global round trip, no second launch) while its weights stream through the same ring. Saves one kernel boundary
@@ -589,7 +589,7 @@ int launch_conv5_tc(const TcConvArgs& a, cudaStream_t stream) {
 // packing helpers
 // ---------------------------------------------------------------------------------------------------
 // weights: src fp32 [ci][ntaps][CO] (the SIMT path's packed layout) ->
-//   dst bf16 [CO/32][CI/32][ntaps][kg 4][64 rows: 32 hi | 32 lo][8]
+//   dst fp16 [CO/32][CI/32][ntaps][kg 4][64 rows: 32 hi | 32 lo][8]
 //   CI is the padded input width (multiple of 32); channels >= CI_src are zero. `perm` maps destination tap -> source tap
 //   (ConvTranspose: [1, 3, 0, 2], see the kernel), packed 4 bits per tap.
 __global__ void pack_tc_weights_kernel(const float* __restrict__ src, unsigned short* __restrict__ dst, int CI, int CI_src,
@@ -626,7 +626,7 @@ int launch_pack_tc_weights(const float* src, unsigned short* dst, int CI, int CI
 }
 
 // trajectory x [B][L][D] (BLC fp32) -> TC layout planes with the channels padded to C (>= D, multiple of 8); the padding
-// channels are never written (zero forever). One thread per (b, l): D split-bf16 values -> 16-byte stores per k-group.
+// channels are never written (zero forever). One thread per (b, l): D fp16-split values -> 16-byte stores per k-group.
 __global__ void blc_to_tc_kernel(const float* __restrict__ x, unsigned short* __restrict__ hi, unsigned short* __restrict__ lo,
                                  int B, int L, int D, int C) {
     pdl_wait();

@@ -80,7 +80,7 @@ class Engine:
     TC_MODES = {"off": 0, "auto": 1, "force": 2}
 
     def set_tensor_cores(self, mode):
-        """'auto' (default): tcgen05 split-bf16 path for the k=5 layers inside the fused loop, exact fp32 FMA path at
+        """'auto' (default): tcgen05 fp16-split path for the k=5 layers inside the fused loop, exact fp32 FMA path at
         the steps where the schedule amplifies eps (t = T-1) and in the per-call entry points; 'force' / 'off'."""
         if mode != self._tc_mode:
             _lib.check(self.lib.mpdb_engine_set_option(self.handle, b"tc_mode", float(self.TC_MODES[mode])))

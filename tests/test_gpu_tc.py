@@ -1,4 +1,4 @@
-"""tcgen05 implicit-GEMM core (csrc/unet_tc.cu) against torch conv1d: split-bf16 (3 MMAs) must reproduce the
+"""tcgen05 implicit-GEMM core (csrc/unet_tc.cu) against torch conv1d: fp16-split (3 MMAs) must reproduce the
 fp32 convolution to ~1e-5 relative. Raw accumulators, no epilogue."""
 import ctypes as C
 
@@ -34,4 +34,4 @@ def test_tc_conv5_raw(B, CI, CO, L):
         rows = raw[t, :, s * (L + 4): s * (L + 4) + L, :]          # [CO/32, L, 32]
         out[b] = rows.permute(0, 2, 1).reshape(CO, L)
     err = float((out - ref).abs().max() / ref.abs().max())
-    assert err < 5e-5, err
+    assert err < 1e-5, err  # 22-bit fp16 split: measured ~1e-6
