@@ -245,7 +245,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) unet_mega_kernel(const __grid_c
     for (int l = 0; l < P.n_layers; ++l) {
         const MegaLayer& Ld = P.layers[l];
         // outputs of the previous layer have landed everywhere (also keeps idle CTAs in lock step)
-        if (l > 0) mbar_wait_cluster(a_full, (uint32_t)(l - 1) & 1u);
+        if (l > 0) mbar_wait(a_full, (uint32_t)(l - 1) & 1u);  // these warps read nothing the peers wrote: CTA-scope wait
         long long* dbg = (P.dbg != nullptr && cluster == 0 && tid == 0) ? P.dbg + ((size_t)l * MEGA_CLUSTER + rank) * MEGA_DBG : nullptr;
         if (dbg) dbg[0] = clock64();  // inputs landed
         const bool active = rank < Ld.MT * Ld.NC;
@@ -340,7 +340,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) unet_mega_kernel(const __grid_c
 
         // ===== deliver: every CTA that consumes these channels gets them in its A buffer (operand layout) =====
         if (dbg) dbg[2] = clock64();  // epilogue arithmetic done
-        mbar_wait_cluster(a_free, (uint32_t)l & 1u);
+        mbar_wait(a_free, (uint32_t)l & 1u);  // orders our stores after the peers' operand reads: no acquire (L1 invalidate) needed
         if (dbg) dbg[6] = clock64();  // every CTA's MMAs of this layer have retired
         if (Ld.oNC > 0) {
             const int n_out = Ld.type == MG_UP ? 2 : 1;

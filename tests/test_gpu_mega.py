@@ -128,3 +128,45 @@ def test_fused_projection_and_ddpm_update_match_the_separate_kernel():
     for k, v in hard.items():
         assert torch.equal(chains[1][:, :, k, :], v.expand(n_iters + 1, B, D))
     assert rel(chains[1], chains[0]) < 2e-5, rel(chains[1], chains[0])
+
+
+def test_api_path_replayed_as_one_graph_matches_eager_draws():
+    """run_inference() drawing its own noise: the 31 normal_() draws + the loop are replayed as one torch CUDA graph.
+    Same seed => same samples as the eager path (graph-safe Philox offsets), the generator advances identically, new
+    start/goal values reach the static buffers, and an engine option change forces a re-capture."""
+    model = cuda_model("panda_opt1_h64")
+    model.tensor_cores = "auto"
+    eng = model._engine()
+    B, H, D = 17, 64, 14
+    kw = dict(n_diffusion_steps_without_noise=C.N_EXTRA, noise_std_extra_schedule_fn=lambda _t: C.NOISE_STD)
+    hard_a = {0: torch.linspace(-0.5, 0.5, D).cuda(), H - 1: torch.linspace(0.4, -0.4, D).cuda()}
+    hard_b = {0: torch.linspace(0.3, -0.2, D).cuda(), H - 1: torch.linspace(-0.1, 0.6, D).cuda()}
+
+    def run(hard, graphed, chain=False):
+        model.graph_rng = graphed
+        torch.manual_seed(123)
+        out = model.run_inference(None, hard, n_samples=B, horizon=H, return_chain=chain, **kw)
+        tail = torch.randn(4, device="cuda")  # where the generator stands after the call
+        return out, tail
+
+    try:
+        eager, tail_e = run(hard_a, False)
+        graphed, tail_g = run(hard_a, True)
+        assert model.__dict__.get("graph_rng", True), model.__dict__.get("_graph_rng_error")
+        assert torch.equal(eager, graphed)
+        assert torch.equal(tail_e, tail_g), "the graph replay must consume the generator exactly like the eager draws"
+        again, _ = run(hard_a, True)
+        assert torch.equal(again, graphed)
+        other_e, _ = run(hard_b, False)
+        other_g, _ = run(hard_b, True)      # same graph, new start / goal copied into the static buffers
+        assert torch.equal(other_e, other_g) and not torch.equal(other_g, graphed)
+        assert torch.equal(other_g[:, 0, :], hard_b[0].expand(B, D))
+        chain_e, _ = run(hard_a, False, chain=True)
+        chain_g, _ = run(hard_a, True, chain=True)
+        assert torch.equal(chain_e, chain_g) and torch.equal(chain_g[-1], graphed)
+        eng.set_option("fuse_final", 0)     # bumps the engine generation: the cached graph must not be reused
+        refused, _ = run(hard_a, True)
+        assert rel(refused, graphed) < 2e-5
+    finally:
+        eng.set_option("fuse_final", 1)
+        model.graph_rng = True
