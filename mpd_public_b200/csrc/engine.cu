@@ -589,8 +589,12 @@ static bool try_build_mega(mpdb_engine* e, int B, int G, std::string& why) {
 
 static void build_mega(mpdb_engine* e, int B) {
     e->mega_ok = false;
-    const int Gs[4] = {8, 4, 2, 1};
+    // samples per cluster: the largest candidate whose tiling fits 8 CTAs and the shared-memory budget (MPDB_MEGA_G pins it)
+    static const int forced = []() { const char* v = getenv("MPDB_MEGA_G"); return v ? atoi(v) : 0; }();
+    const int Gs[8] = {8, 7, 6, 5, 4, 3, 2, 1};
     for (int G : Gs) {
+        if (forced > 0 && G != forced) continue;
+        if (forced <= 0 && G != 8 && G != 4 && G != 2 && G != 1) continue;
         if (!try_build_mega(e, B, G, e->mega_why)) continue;
         // one wave only: with more clusters than can be resident at once the latency chain runs twice and the per-layer
         // kernels are faster (measured: 128 trajectories = 16 clusters = 2 waves = 543 us vs 358 us). use_mega = 2 overrides.
