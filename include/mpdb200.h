@@ -105,7 +105,8 @@ int mpdb_engine_set_schedule(mpdb_engine* e, const float* sqrt_recip_alphas_cump
                              const float* posterior_mean_coef2, const float* posterior_log_variance_clipped,
                              const float* posterior_std, const float* posterior_var);
 /* options: "tc_mode" = 0 exact fp32 FMA path only | 1 auto (default: tcgen05 path, 22-bit scaled-fp16 operand split, at
- * every loop step whose sqrt(1/abar_t - 1) <= tc_amp_limit, exact path otherwise and for the per-call entry points) | 2
+ * every loop step whose sqrt(1/abar_t - 1) <= tc_amp_limit, exact path otherwise; the per-call entry points use the tensor
+ * cores when no finite limit is set) | 2
  * force tensor cores everywhere; "tc_amp_limit" (default: no limit — the split matches the fp32 path even at t = T-1); "mega" = 1 (default: the UNet runs as ONE launch of the whole-forward cluster
  * kernel, unet_mega.cu, whenever the batch fits one wave of 8-CTA clusters) | 0 per-layer kernels | 2 cluster kernel for
  * any batch; "fuse_final" = 1 (default: final_conv.1 + DDPM update in the cluster kernel's last epilogue inside the loop);

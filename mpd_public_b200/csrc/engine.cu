@@ -889,13 +889,18 @@ extern "C" int mpdb_engine_finalize(mpdb_engine* e, void* stream) {
     return 0;
 }
 
+// Per-call entry points (TemporalUnet.forward, p_mean_variance: per-sample t on the device): tensor cores unless the exact
+// path is requested or a finite tc_amp_limit carve-out is configured (t is not known on the host, so it cannot be applied
+// per step here).
+static bool percall_tc(const mpdb_engine* e) { return e->tc_mode == 2 || (e->tc_mode == 1 && e->tc_amp_limit >= 1.0e30f); }
+
 extern "C" int mpdb_unet_forward(mpdb_engine* e, const float* x, const int64_t* t, float* eps, int32_t B, void* stream) {
     MPDB_REQUIRE(e && x && t && eps && B > 0, "mpdb_unet_forward: bad argument");
     MPDB_REQUIRE(e->finalized, "engine not finalized (call mpdb_engine_finalize after loading parameters)");
     cudaStream_t st = (cudaStream_t)stream;
     MPDB_CHECK_CUDA(cudaSetDevice(e->device));
     if (ensure_workspace(e, B)) return 1;
-    if (run_unet_body(e, x, (const long long*)t, 0, B, st, e->tc_mode == 2)) return 1;
+    if (run_unet_body(e, x, (const long long*)t, 0, B, st, percall_tc(e))) return 1;
     FinalArgs f;
     fill_final(e, f, x, (const long long*)t, 0, B);
     f.mode = 0;
@@ -975,7 +980,7 @@ extern "C" int mpdb_p_mean(mpdb_engine* e, const float* x, const int64_t* t, flo
     cudaStream_t st = (cudaStream_t)stream;
     MPDB_CHECK_CUDA(cudaSetDevice(e->device));
     if (ensure_workspace(e, B)) return 1;
-    if (run_unet_body(e, x, (const long long*)t, 0, B, st, e->tc_mode == 2)) return 1;
+    if (run_unet_body(e, x, (const long long*)t, 0, B, st, percall_tc(e))) return 1;
     FinalArgs f;
     fill_final(e, f, x, (const long long*)t, 0, B);
     f.mode = 1;

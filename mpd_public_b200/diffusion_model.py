@@ -80,8 +80,9 @@ class Engine:
     TC_MODES = {"off": 0, "auto": 1, "force": 2}
 
     def set_tensor_cores(self, mode):
-        """'auto' (default): tcgen05 fp16-split path for the k=5 layers inside the fused loop, exact fp32 FMA path at
-        the steps where the schedule amplifies eps (t = T-1) and in the per-call entry points; 'force' / 'off'."""
+        """'auto' (default): tcgen05 path (22-bit scaled-fp16 operand split, as accurate as the fp32 FMA path) for every
+        convolution, in the fused loop and in the per-call entry points; 'off': exact fp32 FMA path everywhere; 'force':
+        tensor cores even when a finite `tc_amp_limit` carve-out is configured."""
         if mode != self._tc_mode:
             _lib.check(self.lib.mpdb_engine_set_option(self.handle, b"tc_mode", float(self.TC_MODES[mode])))
             self._tc_mode = mode

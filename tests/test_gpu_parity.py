@@ -338,7 +338,7 @@ def test_generic_sample_fn_path_equals_fused():
     model_id, ucase, cell, wc, ws, batch = C.GUIDE_CASES[case]
     model = cuda_model(ucase)
     guide, ds, prob = cuda_guide(case)
-    model.tensor_cores = "off"  # the step-by-step entry points always run the exact path; compare like with like
+    model.tensor_cores = "off"  # both paths on the exact fp32 kernels: compare like with like (bitwise-close chains)
     hard = {k: v.cuda() for k, v in O.hard_conditions(prob).items()}
     kw = dict(guide=guide, n_guide_steps=C.N_GUIDE_STEPS, t_start_guide=C.T_START_GUIDE,
               noise_std_extra_schedule_fn=lambda _t: C.NOISE_STD, n_diffusion_steps_without_noise=C.N_EXTRA)
