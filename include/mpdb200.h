@@ -110,6 +110,8 @@ int mpdb_engine_set_schedule(mpdb_engine* e, const float* sqrt_recip_alphas_cump
  * force tensor cores everywhere; "tc_amp_limit" (default: no limit — the split matches the fp32 path even at t = T-1); "mega" = 1 (default: the UNet runs as ONE launch of the whole-forward cluster
  * kernel, unet_mega.cu, whenever the batch fits one wave of 8-CTA clusters) | 0 per-layer kernels | 2 cluster kernel for
  * any batch; "fuse_final" = 1 (default: final_conv.1 + DDPM update in the cluster kernel's last epilogue inside the loop);
+ * "fuse_guide" = 0 (default; 1: the n_guide_steps evaluations of a loop step in one launch with a grid barrier for the clip
+ * flag when the batch is co-resident — bit-identical, measured neutral at 100 trajectories);
  * "fuse_rtb" = 1 (default: per-layer path runs residual blocks with C_out <= 128 as one cluster-fused launch);
  * "alias_buffers" = 1 (default) shares activation storage between layers with disjoint lifetimes, 0 keeps one buffer
  * per layer (needed by mpdb_engine_read_buffer; disables the cluster kernel); "timeline" / "mega_timeline" = 1 enable the

@@ -98,6 +98,9 @@ struct mpdb_engine {
     long long generation = 0;  // bumped whenever device buffers are reallocated or an option changes: launches captured
                                // by a caller (torch CUDA graph around mpdb_sample_loop) are stale afterwards
     int use_mega = []() { const char* v = getenv("MPDB_MEGA"); return v ? atoi(v) : 1; }();
+    // the guide evaluations of a step in one launch (grid barrier for the batch-global clip flag). Measured neutral at B = 100
+    // (9.08 ms per loop either way: the barrier costs what the launch edges cost), so it is off by default; bit-identical (tested).
+    int fuse_guide = []() { const char* v = getenv("MPDB_FUSE_GUIDE"); return v ? atoi(v) : 0; }();
     int fuse_final = []() { const char* v = getenv("MPDB_FUSE_FINAL"); return v ? atoi(v) : 1; }();  // projection + DDPM update in the cluster kernel
     bool mega_ok = false;
     std::string mega_why;      // why the configuration cannot run as one launch (falls back to per-layer kernels)
@@ -815,6 +818,9 @@ extern "C" int mpdb_engine_set_option(mpdb_engine* e, const char* name, double v
             cudaFree(e->mega_dbg); e->mega_dbg = nullptr;
         }
         if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; e->graph_key.clear(); }
+    } else if (n == "fuse_guide") {
+        e->fuse_guide = value != 0;
+        if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; e->graph_key.clear(); }
     } else if (n == "fuse_final") {
         e->fuse_final = value != 0;
         if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; e->graph_key.clear(); }
@@ -1007,7 +1013,9 @@ static int enqueue_loop(mpdb_engine* e, mpdb_guide* g, const mpdb_loop_params* p
     const int T = e->cfg.n_diffusion_steps, H = e->cfg.horizon, D = e->cfg.state_dim;
     const long long n = (long long)B * H * D;
     const int n_iters = T + p->n_steps_without_noise;
-    const int n_flags_needed = n_iters * (p->n_guide_steps + 1) + 1;
+    // clip flags [n_iters][n_guide + 1] + 1, then the grid-barrier counters of the fused guide launches [n_iters][n_guide]
+    const int n_flag_ints = n_iters * (p->n_guide_steps + 1) + 1;
+    const int n_flags_needed = n_flag_ints + n_iters * (p->n_guide_steps > 0 ? p->n_guide_steps : 1);
     if (g && p->n_guide_steps > 0) {
         MPDB_REQUIRE(e->n_flags >= n_flags_needed, "internal: flag scratch not allocated");
         MPDB_CHECK_CUDA(cudaMemsetAsync(e->flags, 0, sizeof(int) * (size_t)n_flags_needed, st));
@@ -1053,7 +1061,32 @@ static int enqueue_loop(mpdb_engine* e, mpdb_guide* g, const mpdb_loop_params* p
         bool fused = false;
         if (run_unet_body(e, cur, nullptr, t, B, st, tc, &f, &fused)) return 1;
         if (!fused && launch_final(f, st)) return 1;
-        if (guided) {
+        if (guided && e->fuse_guide && p->n_guide_steps > 1 && B <= guide_max_coresident(g, H)) {
+            // the n_guide_steps evaluations of this step in ONE launch: the trajectory stays in shared memory, the
+            // batch-global clip flag goes through a grid barrier (guide.cu)
+            GuideStepArgs a;
+            memset(&a, 0, sizeof(a));
+            a.x_in = nxt;
+            a.x_out = nxt;
+            a.flag_in = fl;
+            a.n_iters = p->n_guide_steps;
+            a.iter_flags = fl;
+            a.iter_counters = reinterpret_cast<unsigned int*>(e->flags + n_flag_ints + (long long)it * p->n_guide_steps);
+            if (p->scale_grad_by_std) { a.use_var_uniform = 1; a.var_uniform = e->sched_host[6 * (size_t)T + t]; }
+            a.n_hc = p->n_hard_conds;
+            for (int q = 0; q < p->n_hard_conds; ++q) a.hc_rows[q] = p->hard_cond_rows[q];
+            a.hc_vals = hc_vals;
+            if (t != 0) {  // noise[t == 0] = 0 (sample_functions.py:52)
+                a.noise = step_noise;
+                a.noise_sd = e->sched_host[5 * (size_t)T + t];
+                a.noise_mult = ns;
+            }
+            a.out2 = chain_slot;
+            a.out2_bstride = chain_batch_stride;
+            a.B = B;
+            a.H = H;
+            if (guide_launch_step(g, a, st)) return 1;
+        } else if (guided) {
             for (int k = 0; k < p->n_guide_steps; ++k) {
                 const bool klast = (k == p->n_guide_steps - 1);
                 GuideStepArgs a;
@@ -1114,7 +1147,7 @@ extern "C" int mpdb_sample_loop(mpdb_engine* e, mpdb_guide* g, const mpdb_loop_p
     const long long n = (long long)B * H * D;
 
     {
-        const int n_flags_needed = n_iters * (p->n_guide_steps + 1) + 1;
+        const int n_flags_needed = n_iters * (p->n_guide_steps + 1) + 1 + n_iters * (p->n_guide_steps > 0 ? p->n_guide_steps : 1);
         if (e->n_flags < n_flags_needed) {
             if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; e->graph_key.clear(); }
             MPDB_CHECK_CUDA(cudaDeviceSynchronize());
@@ -1143,7 +1176,7 @@ extern "C" int mpdb_sample_loop(mpdb_engine* e, mpdb_guide* g, const mpdb_loop_p
                       std::to_string(p->n_steps_without_noise) + "|" + std::to_string(p->t_start_guide) + "|" +
                       std::to_string(p->n_guide_steps) + "|" + std::to_string(p->scale_grad_by_std) + "|" +
                       std::to_string(chain_out != nullptr) + "|" + std::to_string(p->n_hard_conds) + "|tc" +
-                      std::to_string(e->tc_mode) + "/" + std::to_string(e->tc_amp_limit) + "/" + std::to_string(e->fuse_rtb) + "/" + std::to_string(e->use_mega) + "/" + std::to_string(e->fuse_final);
+                      std::to_string(e->tc_mode) + "/" + std::to_string(e->tc_amp_limit) + "/" + std::to_string(e->fuse_rtb) + "/" + std::to_string(e->use_mega) + "/" + std::to_string(e->fuse_final) + "/" + std::to_string(e->fuse_guide);
     for (int k = 0; k < p->n_hard_conds; ++k) key += "," + std::to_string(p->hard_cond_rows[k]);
     for (int k = 0; k < n_iters; ++k) {
         float v = p->noise_std ? p->noise_std[k] : 1.0f;

@@ -253,10 +253,15 @@ __global__ void __launch_bounds__(GUIDE_THREADS) guide_step_kernel(GuideDev g, G
     if (dbg) dbg[0] = clock64();
     pdl_launch_dependents();
     pdl_wait();  // x and the clip flag come from the previous kernel
-    const int flag = a.flag_in ? *a.flag_in : 0;
+    const int n_it = a.n_iters > 1 ? a.n_iters : 1;
+    for (int it = 0; it < n_it; ++it) {
+    const bool last_it = it == n_it - 1;
+    int flag;
+    if (it == 0) flag = a.flag_in ? *a.flag_in : 0;
+    else flag = *reinterpret_cast<volatile int*>(a.iter_flags + it);  // complete: every CTA passed the grid barrier below
     const float* xin = a.x_in + (long long)b * H * D;
     for (int i = tid; i < H * D; i += NTH) {
-        float v = xin[i];
+        float v = it == 0 ? xin[i] : xn[i];  // later evaluations continue from the trajectory kept in shared memory
         xn[i] = v;
         float vc = flag ? fminf(fmaxf(v, -1.f), 1.f) : v;
         int d = i % D;
@@ -480,13 +485,33 @@ __global__ void __launch_bounds__(GUIDE_THREADS) guide_step_kernel(GuideDev g, G
             if (a.hc_rows[k] == h) hc = k;
         if (hc >= 0) v = a.hc_vals[((long long)hc * a.B + b) * D + d];
         viol |= (v > 1.0001f) || (v < -1.0001f);
+        if (!last_it) {  // next evaluation of this launch reads it from shared memory
+            xn[i] = v;
+            continue;
+        }
         if (a.noise != nullptr && hc < 0) v = __fadd_rn(v, __fmul_rn(__fmul_rn(a.noise_sd, a.noise[(long long)b * H * D + i]), a.noise_mult));
         xout[i] = v;
         if (a.out2) a.out2[(long long)b * a.out2_bstride + i] = v;
     }
-    if (a.flag_out != nullptr) {
+    if (!last_it) {
+        // batch-global clip flag of the next evaluation (LimitsNormalizer.unnormalize looks at the whole batch), then a grid
+        // barrier: every CTA has contributed before anyone reads it. Bounded spin: a scheduling problem traps, never hangs.
+        const int any = __syncthreads_or(viol ? 1 : 0);
+        if (tid == 0) {
+            if (any) atomicOr(a.iter_flags + it + 1, 1);
+            __threadfence();
+            atomicAdd(a.iter_counters + it, 1u);
+            const long long t0 = clock64();
+            while (*reinterpret_cast<volatile unsigned int*>(a.iter_counters + it) < gridDim.x) {
+                if (clock64() - t0 > 4000000000LL) __trap();
+            }
+            __threadfence();
+        }
+        __syncthreads();
+    } else if (a.flag_out != nullptr) {
         if (__syncthreads_or(viol ? 1 : 0) && tid == 0) atomicOr(a.flag_out, 1);
     }
+    }  // evaluations
     if (dbg) dbg[7] = clock64();  // update written
 }
 
@@ -584,12 +609,27 @@ static size_t guide_smem_bytes(const GuideDev& g, int H) {
     return f * sizeof(float);
 }
 
+int guide_max_coresident(mpdb_guide* gd, int H) {
+    GuideDev g = make_dev(gd->cfg);
+    const size_t smem = guide_smem_bytes(g, H);
+    int per_sm = 0, sms = 0;
+    cudaFuncSetAttribute(guide_step_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, guide_step_kernel<1, 2>, GUIDE_THREADS, smem) != cudaSuccess ||
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, gd->device) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return (per_sm > 0 ? 1 : 0) * sms;  // one CTA per SM counted: the other kernels of the loop may still hold shared memory
+}
+
 int guide_launch_step(mpdb_guide* gd, const GuideStepArgs& a, cudaStream_t stream) {
     GuideDev g = make_dev(gd->cfg);
     MPDB_REQUIRE(g.D <= MPDB_MAX_STATE_DIM && g.q_dim <= 7, "guide: state dim too large");
     MPDB_REQUIRE(g.n_interp >= 1, "guide: n_interp must be >= 1");
     const size_t smem = guide_smem_bytes(g, a.H);
     MPDB_REQUIRE(smem <= 220 * 1024, "guide: trajectory does not fit in shared memory");
+    MPDB_REQUIRE(a.n_iters <= 1 || (a.iter_flags && a.iter_counters && !a.grad_only && a.B <= guide_max_coresident(gd, a.H)),
+                 "guide: several evaluations per launch need flag / counter scratch and a co-resident grid");
     const int spg = (g.n_spheres + NSG - 1) / NSG;
     MPDB_REQUIRE(spg >= 1 && spg <= SPG, "guide: bad sphere count");
 #define MPDB_GUIDE_LAUNCH(K, S)                                                                                              \

@@ -204,9 +204,17 @@ struct GuideStepArgs {
     float* out2;         // chain slot or null
     long long out2_bstride;
     int B, H;
+    // several guide evaluations in ONE launch (guide_gradient_steps, sample_functions.py:65-83): the trajectory stays in
+    // shared memory between evaluations; the batch-global clip flag of evaluation k+1 is an atomicOr into iter_flags[k+1]
+    // followed by a grid barrier on iter_counters[k] (all CTAs must be co-resident: guide_launch_step checks). n_iters <= 1:
+    // one evaluation, flag_in / flag_out as before. Noise, chain slot and x_out are written by the last evaluation.
+    int n_iters;
+    int* iter_flags;            // [n_iters], [0] written by the producer of x_in; zeroed by the caller
+    unsigned int* iter_counters;  // [n_iters - 1], zeroed by the caller
     long long* dbg;      // optional clock64 stamps of thread 0 of CTA 0 (MPDB_GUIDE_TIMELINE=1 in mpdb_profile_guide)
 };
 int guide_launch_step(mpdb_guide* g, const GuideStepArgs& a, cudaStream_t stream);
+int guide_max_coresident(mpdb_guide* g, int H);  // CTAs of the guide kernel that can be resident at once (grid-barrier bound)
 int guide_launch_flag(const float* x, long long n, int* flag, cudaStream_t stream);
 int guide_device(mpdb_guide* g);
 int guide_state_dim(mpdb_guide* g);

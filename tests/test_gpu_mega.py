@@ -170,3 +170,31 @@ def test_api_path_replayed_as_one_graph_matches_eager_draws():
     finally:
         eng.set_option("fuse_final", 1)
         model.graph_rng = True
+
+
+@pytest.mark.parametrize("case", ["panda3d", "simple2d"])
+def test_guide_evaluations_of_a_step_in_one_launch_are_bit_identical(case):
+    """Option fuse_guide: the n_guide_steps evaluations of a step as ONE launch (trajectory kept in shared memory, the
+    batch-global clip flag through a grid barrier) against one launch per evaluation: the same chain, bit for bit."""
+    from tests.test_gpu_parity import cuda_guide
+    model_id, ucase, cell, wc, ws, batch = C.GUIDE_CASES[case]
+    model = cuda_model(ucase)
+    model.tensor_cores = "auto"
+    eng = model._engine()
+    guide, ds, prob = cuda_guide(case)
+    hard = {k: v.cuda() for k, v in O.hard_conditions(prob).items()}
+    H, D = prob.n_support_points, prob.robot.state_dim
+    n_iters = C.T_DIFF + C.N_EXTRA
+    g = torch.Generator().manual_seed(31)
+    noise = (1.3 * torch.randn((n_iters + 1, batch, H, D), generator=g)).cuda()  # some values beyond [-1, 1]: exercises the clip flag
+    kw = dict(guide=guide, n_guide_steps=C.N_GUIDE_STEPS, t_start_guide=C.T_START_GUIDE,
+              noise_std_extra_schedule_fn=lambda _t: C.NOISE_STD, n_diffusion_steps_without_noise=C.N_EXTRA)
+    chains = {}
+    try:
+        for fuse in (1, 0):
+            eng.set_option("fuse_guide", fuse)
+            chains[fuse] = model.run_inference(None, hard, n_samples=batch, horizon=H, return_chain=True, noise=noise, **kw)
+    finally:
+        eng.set_option("fuse_guide", 0)
+    assert torch.isfinite(chains[1]).all()
+    assert torch.equal(chains[1], chains[0])
