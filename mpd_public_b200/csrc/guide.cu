@@ -393,16 +393,20 @@ __global__ void __launch_bounds__(GUIDE_THREADS) guide_step_kernel(GuideDev g, G
                 int hi_i = (int)ceilf((float)(h + 1) * inv_ratio) + 1;
                 if (lo_i < 0) lo_i = 0;
                 if (hi_i > NI - 1) hi_i = NI - 1;
+                // 32-bit indices, no data-dependent branch (rows that do not touch h contribute with weight 0): the four
+                // 8-lane groups of a warp stay converged
+                const float* gqf = gq + f * NSG * NI * q + k;
+                const int sg_stride = NI * q;
                 for (int i = lo_i; i <= hi_i; ++i) {
-                    int i0 = i0s[i];
-                    int i1 = i0 + (i0 < H - 1 ? 1 : 0);
-                    float l1 = w1s[i];
-                    float cw = (i0 == h ? 1.f - l1 : 0.f) + (i1 == h ? l1 : 0.f);
-                    if (cw != 0.f) {
-                        float dqs = 0.f;
-                        for (int sg = 0; sg < NSG; ++sg) dqs += gq[(((long long)f * NSG + sg) * NI + i) * q + k];
-                        gsk = fmaf(cw, dqs, gsk);
-                    }
+                    const int i0 = i0s[i];
+                    const int i1 = i0 + (i0 < H - 1 ? 1 : 0);
+                    const float l1 = w1s[i];
+                    const float cw = (i0 == h ? 1.f - l1 : 0.f) + (i1 == h ? l1 : 0.f);
+                    const float* gp = gqf + i * q;
+                    float dqs = 0.f;
+#pragma unroll
+                    for (int sg = 0; sg < NSG; ++sg) dqs += gp[sg * sg_stride];
+                    gsk = cw != 0.f ? fmaf(cw, dqs, gsk) : gsk;
                 }
             }
             float scale = 1.f;
