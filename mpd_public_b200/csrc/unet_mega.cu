@@ -3,7 +3,8 @@
 // The reverse loop at 100 trajectories per GPU is a chain of ~40 dependent convolutions per forward; run layer by layer
 // (unet_tc.cu) every link pays a kernel boundary: launch edge, barrier/TMEM setup, a cold first copy from L2, drain.
 // GroupNorm is per sample, so a group of G trajectories can run the whole network with no grid-wide dependency. Here a
-// cluster of 8 CTAs owns G (8 at H=64) trajectories from the input projection to final_conv.0:
+// cluster of 8 CTAs owns G (8 at H=64) trajectories from the input projection to final_conv.0 — and, inside the timed loop,
+// through final_conv.1 and the DDPM update (fuse_final):
 //
 //   * activations never leave the cluster: the current tensor lives in every CTA's shared memory ("A buffer") in the
 //     tcgen05 no-swizzle K-major operand layout [plane hi|lo][C/8][RT rows][8 x fp16]; a layer's epilogue writes its
@@ -19,7 +20,11 @@
 //   * layer-to-layer synchronisation is two cluster-scope mbarriers per CTA: a_free (every CTA's MMAs of this layer
 //     have retired -> its A buffer may be overwritten) and a_full (every epilogue warp of the cluster has delivered
 //     its outputs). Every warp of every CTA arrives on every CTA's barrier each layer, active or not, so the counts
-//     are constants and idle CTAs stay in lock step.
+//     are constants and idle CTAs stay in lock step. a_free is sent by an issuer warp (off the epilogue's critical path);
+//     the consumer's issuer warp executes the generic->async proxy fence after its acquire, so a hand-off costs one
+//     store round trip, not two;
+//   * the second accumulators (odd rows of the transposed convolutions, the blocks' 1x1 residual convs) stay in TMEM until
+//     they are needed — holding them in registers through GroupNorm spilled (96 registers at 608 threads).
 //
 // Tried and dropped (measured, profiles/README.md): per-source "slice landed" barriers so that a K-chunk's MMAs start as soon
 // as its 32 channels have arrived — the incoming DSMEM stores and the tensor core's operand reads share the destination's
@@ -28,7 +33,8 @@
 //
 // Arithmetic follows the per-layer tensor-core path (same fp16-split products per K-chunk, fp32 residual values kept in
 // registers); the three partial products are summed from separate accumulators, so the two paths agree to the fp16-split
-// rounding level (~1.5e-5 relative, tested), and each is deterministic and independent of the batch composition.
+// rounding level (~5e-7 relative with the 22-bit split, tested), and each is deterministic, bit-identical over repeated
+// runs and independent of the batch composition (tested).
 #include "tc_common.cuh"
 
 namespace mpdb {
