@@ -1,0 +1,139 @@
+"""BASELINE.json configs 2 and 3 as parity cases (the bench line is config 4):
+  2  EnvDense2D-RobotPointMass, H=64, B=100, guidance on
+  3  EnvNarrowPassageDense2D-RobotPointMass, H=64, B=512, collision / smoothness weight sweep
+     (w_coll in {1e-2, 3e-2, 1e-1} x w_smooth in {1e-7, 1e-4, 1e-2})
+The guide gradient and guide_gradient_steps are compared with the oracle on the same seeded inputs (the oracle looks up
+the texels the CUDA grid builder produced); one guided reverse step of the full model is compared per configuration, and
+the whole guided loop is checked through size-independent properties (finite, hard conditions exact, chain end == sample).
+B = 512 does not fit one wave of clusters, so config 3 also exercises the per-layer tensor-core kernels inside the loop."""
+import numpy as np
+import pytest
+import torch
+
+from mpd_public_b200 import synthetic as S
+from oracle import mpd_oracle as O
+from tests.golden import cases as C
+from tests.test_gpu_parity import TOL_KERNEL, TOL_STEP, cuda_model, oracle_model, rel
+
+pytestmark = pytest.mark.gpu
+
+CONFIGS = {
+    "cfg2_dense2d": ("EnvDense2D-RobotPointMass", 100, [(3e-2, 1e-2)]),
+    "cfg3_narrow2d": ("EnvNarrowPassageDense2D-RobotPointMass", 512,
+                      [(wc, ws) for wc in (1e-2, 3e-2, 1e-1) for ws in (1e-7, 1e-4, 1e-2)]),
+}
+UCASE = "pm2d_opt0_h64"
+H = 64
+
+_built = {}
+
+
+def build(name, wc, ws):
+    import mpd_public_b200 as M
+    key = (name, wc, ws)
+    if key not in _built:
+        model_id, batch, _ = CONFIGS[name]
+        if name not in _built:
+            prob = S.make_problem_by_id(model_id, n_support_points=H, cell=0.01)
+            _built[name] = (prob, M.TrajectoryDataset(prob, "cuda"))
+        prob, ds = _built[name]
+        robot, task = ds.robot, ds.task
+        robot.dt = prob.dt
+        costs, weights = [], []
+        for f in task.get_collision_fields():
+            costs.append(M.CostCollision(robot, H, field=f, sigma_coll=1.0))
+            weights.append(wc)
+        costs.append(M.CostGPTrajectory(robot, H, prob.dt, sigma_gp=1.0))
+        weights.append(ws)
+        guide = M.GuideManagerTrajectoriesWithVelocity(ds, M.CostComposite(robot, H, costs, weights_cost_l=weights),
+                                                       clip_grad=True, interpolate_trajectories_for_collision=True)
+        texels = [f.texels.cpu() for f in task.get_collision_fields() if hasattr(f, "texels")]
+        _built[key] = (guide, ds, prob, O.make_guide_spec(prob, wc, ws, texels_list=texels))
+    return _built[key]
+
+
+def near_line_input(prob, batch, seed, out_of_range=False):
+    """Normalised trajectories around the straight start -> goal line (costs active), a few beyond [-1, 1] if asked."""
+    d = prob.robot.state_dim
+    rng = np.random.default_rng([seed, batch, d])
+    s = np.concatenate([prob.start, np.zeros(prob.robot.q_dim)])
+    g = np.concatenate([prob.goal, np.zeros(prob.robot.q_dim)])
+    lam = np.linspace(0, 1, H)[None, :, None]
+    x = (1 - lam) * s[None, None, :] + lam * g[None, None, :]
+    x = 2 * (x - prob.mins) / (prob.maxs - prob.mins) - 1
+    x = x + 0.15 * rng.standard_normal((batch, H, d))
+    if out_of_range:
+        x[batch // 2, 7, 1] = -1.4  # one element in the whole batch flips LimitsNormalizer's global clip
+    else:
+        x = np.clip(x, -0.999, 0.999)
+    return torch.as_tensor(x.astype(np.float32))
+
+
+@pytest.mark.parametrize("name", list(CONFIGS))
+def test_guide_gradient_over_the_weight_sweep(name):
+    model_id, batch, sweep = CONFIGS[name]
+    for k, (wc, ws) in enumerate(sweep):
+        guide, ds, prob, spec = build(name, wc, ws)
+        x = near_line_input(prob, batch, seed=40 + k, out_of_range=(k % 2 == 1))
+        ref, parts = O.guide_manager_grad(spec, x, return_parts=True)
+        got = guide(x.cuda())
+        assert float(ref.abs().max()) > 0
+        assert rel(got, ref) < TOL_KERNEL, (wc, ws, rel(got, ref))
+        assert float(got[:, 0].abs().max()) == 0 and float(got[:, -1].abs().max()) == 0  # guides.py:202-203
+
+
+@pytest.mark.parametrize("name", list(CONFIGS))
+def test_guide_gradient_steps(name):
+    import mpd_public_b200 as M
+    model_id, batch, sweep = CONFIGS[name]
+    wc, ws = sweep[len(sweep) // 2]
+    guide, ds, prob, spec = build(name, wc, ws)
+    hard = O.hard_conditions(prob)
+    ohc = {k: v[None].repeat(batch, 1) for k, v in hard.items()}
+    x = near_line_input(prob, batch, seed=7, out_of_range=True)
+    ref = O.OracleDiffusion.guide_gradient_steps(None, x.clone(), ohc, lambda z: O.guide_manager_grad(spec, z), 5)
+    got = M.guide_gradient_steps(x.cuda(), hard_conds={k: v.cuda() for k, v in ohc.items()}, guide=guide, n_guide_steps=5)
+    assert rel(got, ref) < TOL_KERNEL
+
+
+@pytest.mark.parametrize("name", list(CONFIGS))
+def test_guided_loop_properties_and_one_step_parity(name):
+    model_id, batch, sweep = CONFIGS[name]
+    wc, ws = sweep[0]
+    guide, ds, prob, spec = build(name, wc, ws)
+    model = cuda_model(UCASE)
+    model.tensor_cores = "auto"
+    om = oracle_model(UCASE)
+    D = prob.robot.state_dim
+    hard = O.hard_conditions(prob)
+    hard_cuda = {k: v.cuda() for k, v in hard.items()}
+    n_iters = C.T_DIFF + C.N_EXTRA
+    gen = torch.Generator().manual_seed(batch)
+    noise = torch.randn((n_iters + 1, batch, H, D), generator=gen)
+    kw = dict(guide=guide, n_guide_steps=C.N_GUIDE_STEPS, t_start_guide=C.T_START_GUIDE,
+              noise_std_extra_schedule_fn=lambda _t: C.NOISE_STD, n_diffusion_steps_without_noise=C.N_EXTRA)
+    in_use = model._engine().mega_info(batch)[0]
+    assert in_use == (batch <= 104), "config 2 runs the cluster kernel, config 3 (B = 512) the per-layer kernels"
+    chain = model.run_inference(None, hard_cuda, n_samples=batch, horizon=H, return_chain=True, noise=noise.cuda(), **kw).cpu()
+    final = model.run_inference(None, hard_cuda, n_samples=batch, horizon=H, return_chain=False, noise=noise.cuda(), **kw).cpu()
+    assert chain.shape == (n_iters + 1, batch, H, D) and torch.isfinite(chain).all()
+    assert torch.equal(final, chain[-1])
+    for k, v in hard.items():
+        assert torch.equal(chain[:, :, k, :], v.expand(n_iters + 1, batch, D))
+    # one unguided step (t = 12) and one guided step (t = 3), teacher-forced from our own chain, on a slice of the batch
+    ohc = {k: v[None].repeat(batch, 1) for k, v in hard.items()}
+    steps = list(reversed(range(-C.N_EXTRA, C.T_DIFF)))
+    sl = slice(0, 64)
+    for i in (12, 3):
+        k = steps.index(i)
+        t = torch.full((batch,), i, dtype=torch.long)
+        oguide = (lambda z: O.guide_manager_grad(spec, z))
+        with torch.no_grad():
+            ref = om.ddpm_step(chain[k].clone(), ohc, t, noise[k + 1], oguide, C.N_GUIDE_STEPS, False, C.T_START_GUIDE, C.NOISE_STD)
+        ref = O.apply_hard_conditioning(ref, ohc)
+        e = rel(chain[k + 1][sl], ref[sl])
+        if i < C.T_START_GUIDE and e >= TOL_STEP:
+            d = (chain[k + 1] - ref).abs() / ref.abs().max()   # sparse nearest-texel / hinge flips (see test_gpu_parity)
+            assert float((d > TOL_STEP).float().mean()) < 2e-3 and e < 2e-2, (i, e)
+        else:
+            assert e < TOL_STEP, (i, e)
