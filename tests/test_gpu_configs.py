@@ -1,4 +1,4 @@
-"""BASELINE.json configs 2 and 3 as parity cases (the bench line is config 4):
+"""BASELINE.json configs 2, 3 and (one shard of) 5 as parity cases (the bench line is config 4):
   2  EnvDense2D-RobotPointMass, H=64, B=100, guidance on
   3  EnvNarrowPassageDense2D-RobotPointMass, H=64, B=512, collision / smoothness weight sweep
      (w_coll in {1e-2, 3e-2, 1e-1} x w_smooth in {1e-7, 1e-4, 1e-2})
@@ -137,3 +137,52 @@ def test_guided_loop_properties_and_one_step_parity(name):
             assert float((d > TOL_STEP).float().mean()) < 2e-3 and e < 2e-2, (i, e)
         else:
             assert e < TOL_STEP, (i, e)
+
+
+def test_config5_shard_shape_panda_h128_b512():
+    """One GPU's shard of config 5 (EnvSpheres3D-RobotPanda, H = 128, 512 trajectories): guide gradient against the oracle
+    at this horizon (128 interpolation points = the support points themselves), and the guided loop through properties."""
+    import mpd_public_b200 as M
+    h, batch = 128, 512
+    prob = S.make_problem_by_id("EnvSpheres3D-RobotPanda", n_support_points=h, cell=0.04)
+    ds = M.TrajectoryDataset(prob, "cuda")
+    robot, task = ds.robot, ds.task
+    robot.dt = prob.dt
+    costs = [M.CostCollision(robot, h, field=f, sigma_coll=1.0) for f in task.get_collision_fields()]
+    weights = [1e-2] * len(costs)
+    costs.append(M.CostGPTrajectory(robot, h, prob.dt, sigma_gp=1.0))
+    weights.append(1e-7)
+    guide = M.GuideManagerTrajectoriesWithVelocity(ds, M.CostComposite(robot, h, costs, weights_cost_l=weights), clip_grad=True,
+                                                   interpolate_trajectories_for_collision=True)
+    texels = [f.texels.cpu() for f in task.get_collision_fields() if hasattr(f, "texels")]
+    spec = O.make_guide_spec(prob, 1e-2, 1e-7, texels_list=texels)
+    d = prob.robot.state_dim
+    rng = np.random.default_rng(5)
+    s0 = np.concatenate([prob.start, np.zeros(prob.robot.q_dim)])
+    g0 = np.concatenate([prob.goal, np.zeros(prob.robot.q_dim)])
+    lam = np.linspace(0, 1, h)[None, :, None]
+    x = (1 - lam) * s0[None, None, :] + lam * g0[None, None, :]
+    x = 2 * (x - prob.mins) / (prob.maxs - prob.mins) - 1
+    x = torch.as_tensor(np.clip(x + 0.15 * rng.standard_normal((64, h, d)), -0.999, 0.999).astype(np.float32))
+    ref = O.guide_manager_grad(spec, x)
+    assert float(ref.abs().max()) > 0
+    assert rel(guide(x.cuda()), ref) < TOL_KERNEL
+
+    model = cuda_model("panda_opt1_h128")
+    model.tensor_cores = "auto"
+    hard = O.hard_conditions(prob)
+    hard_cuda = {k: v.cuda() for k, v in hard.items()}
+    n_iters = C.T_DIFF + C.N_EXTRA
+    noise = torch.randn((n_iters + 1, batch, h, d), generator=torch.Generator().manual_seed(9))
+    kw = dict(guide=guide, n_guide_steps=C.N_GUIDE_STEPS, t_start_guide=C.T_START_GUIDE,
+              noise_std_extra_schedule_fn=lambda _t: C.NOISE_STD, n_diffusion_steps_without_noise=C.N_EXTRA)
+    chain = model.run_inference(None, hard_cuda, n_samples=batch, horizon=h, return_chain=True, noise=noise.cuda(), **kw)
+    assert chain.shape == (n_iters + 1, batch, h, d) and torch.isfinite(chain).all()
+    for k, v in hard_cuda.items():
+        assert torch.equal(chain[:, :, k, :], v.expand(n_iters + 1, batch, d))
+    # a trajectory's result does not depend on its shard: the first 64 trajectories alone give the same samples (the clip
+    # flag is batch-global, so equality holds when neither run trips it; both report it through the same flag path)
+    sub = model.run_inference(None, hard_cuda, n_samples=64, horizon=h, return_chain=False, noise=noise[:, :64].contiguous().cuda(),
+                              **dict(kw, guide=None))
+    full = model.run_inference(None, hard_cuda, n_samples=batch, horizon=h, return_chain=False, noise=noise.cuda(), **dict(kw, guide=None))
+    assert rel(sub, full[:64]) < 2e-5  # B = 64 runs the cluster kernel, B = 512 the per-layer kernels: same arithmetic up to summation order
