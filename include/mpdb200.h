@@ -182,6 +182,11 @@ int mpdb_guide_create(const mpdb_guide_config* cfg, int device, mpdb_guide** out
 void mpdb_guide_destroy(mpdb_guide* g);
 /* guide(x_normalized) -> grad, [B,H,D] — guides.py:173-211 */
 int mpdb_guide_grad(mpdb_guide* g, const float* x, float* grad, int32_t B, int32_t H, void* stream);
+/* GuideManagerTrajectories.forward (position-only state, guides.py:60-118): x_pos [B,H,q] normalised positions,
+ * velocity [B,H,q] the manager's unnormalised velocity trajectory — read as the velocity half of the state and updated in
+ * place (velocity -= sum_c w_c * clip(d cost_c / d velocity)); grad [B,H,q] = -sum_c w_c * zero_ends(clip(d cost_c / d pos)).
+ * Position and velocity gradients of a cost are clipped separately. The guide config's mins/maxs cover the q positions. */
+int mpdb_guide_grad_pos(mpdb_guide* g, const float* x_pos, float* velocity, float* grad, int32_t B, int32_t H, void* stream);
 /* guide_gradient_steps(x, hard_conds, guide, n_guide_steps, scale_grad_by_std, model_var) in place —
  * sample_functions.py:65-83. model_var: device [B] or NULL. hard-cond arrays as in mpdb_loop_params. */
 int mpdb_guide_steps(mpdb_guide* g, float* x, int32_t n_steps, const float* model_var, int32_t n_hard_conds,

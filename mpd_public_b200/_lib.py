@@ -80,6 +80,7 @@ SYMBOLS = {
     "mpdb_guide_create": (C.c_int, [C.POINTER(GuideConfig), C.c_int, C.POINTER(_P)]),
     "mpdb_guide_destroy": (None, [_P]),
     "mpdb_guide_grad": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, _P]),
+    "mpdb_guide_grad_pos": (C.c_int, [_P, _P, _P, _P, C.c_int32, C.c_int32, _P]),
     "mpdb_guide_steps": (C.c_int, [_P, _P, C.c_int32, _P, C.c_int32, C.POINTER(C.c_int32), _P, C.c_int32, C.c_int32, _P]),
     "mpdb_eval_trajectories": (C.c_int, [_P, _P, _P, C.c_float, C.c_int32, C.c_int32, _P]),
     "mpdb_sdf_grid_build": (C.c_int, [C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_float), C.c_float,

@@ -259,15 +259,22 @@ __global__ void __launch_bounds__(GUIDE_THREADS) guide_step_kernel(GuideDev g, G
     int flag;
     if (it == 0) flag = a.flag_in ? *a.flag_in : 0;
     else flag = *reinterpret_cast<volatile int*>(a.iter_flags + it);  // complete: every CTA passed the grid barrier below
-    const float* xin = a.x_in + (long long)b * H * D;
+    const bool pos_only = a.vel_io != nullptr;  // x holds positions only, velocities come from / go to vel_io
+    const int Dio = pos_only ? q : D;           // columns of x_in / x_out
+    const float* xin = a.x_in + (long long)b * H * Dio;
     for (int i = tid; i < H * D; i += NTH) {
-        float v = it == 0 ? xin[i] : xn[i];  // later evaluations continue from the trajectory kept in shared memory
+        const int d = i % D, hrow = i / D;
+        tot[i] = 0.f;
+        if (pos_only && d >= q) {  // velocity half of the state: already unnormalised, not part of x
+            xn[i] = 0.f;
+            xu[i] = a.vel_io[((long long)b * H + hrow) * q + (d - q)];
+            continue;
+        }
+        float v = it == 0 ? xin[hrow * Dio + d] : xn[i];  // later evaluations continue from the trajectory kept in shared memory
         xn[i] = v;
         float vc = flag ? fminf(fmaxf(v, -1.f), 1.f) : v;
-        int d = i % D;
         // ((x + 1) / 2) * (maxs - mins) + mins, reference operation order (normalization.py:165-167)
         xu[i] = __fadd_rn(__fmul_rn(__fmul_rn(__fadd_rn(vc, 1.f), 0.5f), g.range[d]), g.mins[d]);
-        tot[i] = 0.f;
     }
     __syncthreads();
     if (dbg) dbg[1] = clock64();  // trajectory loaded + unnormalised
@@ -416,7 +423,7 @@ __global__ void __launch_bounds__(GUIDE_THREADS) guide_step_kernel(GuideDev g, G
                 n2 += __shfl_xor_sync(0xffffffffu, n2, 1);
                 n2 += __shfl_xor_sync(0xffffffffu, n2, 2);
                 n2 += __shfl_xor_sync(0xffffffffu, n2, 4);
-                n2 += (float)(D - q) * (1e-6f * 1e-6f);
+                if (!pos_only) n2 += (float)(D - q) * (1e-6f * 1e-6f);  // the zero velocity half of the gradient, + 1e-6 each
                 scale = clip_scale(sqrtf(n2), g.max_norm);
             }
             if (on && k < q) {
@@ -442,7 +449,7 @@ __global__ void __launch_bounds__(GUIDE_THREADS) guide_step_kernel(GuideDev g, G
         for (int h0 = 0; h0 < H; h0 += NTH / 8) {
             const int h = h0 + (tid >> 3), k = tid & 7;
             const bool on = h > 0 && h < H - 1 && k < q;  // gradient rows 0 and H-1 are zeroed by the guide manager
-            float gpk = 0.f, gvk = 0.f, n2 = 0.f;
+            float gpk = 0.f, gvk = 0.f, n2 = 0.f, n2v = 0.f;
             if (on) {
                 const float pm = xu[(h - 1) * D + k], pc = xu[h * D + k], pn = xu[(h + 1) * D + k];
                 const float vm = xu[(h - 1) * D + q + k], vc = xu[h * D + q + k], vn = xu[(h + 1) * D + q + k];
@@ -453,15 +460,20 @@ __global__ void __launch_bounds__(GUIDE_THREADS) guide_step_kernel(GuideDev g, G
                 gpk = up0 - up1;
                 gvk = uv0 - uv1 - g.dt * up1;
                 const float t0 = gpk + 1e-6f, t1 = gvk + 1e-6f;
-                n2 = fmaf(t1, t1, t0 * t0);
+                if (pos_only) { n2 = t0 * t0; n2v = t1 * t1; }  // position and velocity gradients are clipped separately
+                else n2 = fmaf(t1, t1, t0 * t0);
             }
             n2 += __shfl_xor_sync(0xffffffffu, n2, 1);
             n2 += __shfl_xor_sync(0xffffffffu, n2, 2);
             n2 += __shfl_xor_sync(0xffffffffu, n2, 4);
+            n2v += __shfl_xor_sync(0xffffffffu, n2v, 1);
+            n2v += __shfl_xor_sync(0xffffffffu, n2v, 2);
+            n2v += __shfl_xor_sync(0xffffffffu, n2v, 4);
             if (on) {
                 const float scale = g.clip ? clip_scale(sqrtf(n2), g.max_norm) : 1.f;
+                const float scale_v = pos_only ? (g.clip ? clip_scale(sqrtf(n2v), g.max_norm) : 1.f) : scale;
                 tot[h * D + k] += g.w_gp * (scale * gpk);
-                tot[h * D + q + k] += g.w_gp * (scale * gvk);
+                tot[h * D + q + k] += g.w_gp * (scale_v * gvk);
             }
         }
     }
@@ -469,7 +481,7 @@ __global__ void __launch_bounds__(GUIDE_THREADS) guide_step_kernel(GuideDev g, G
     if (dbg) dbg[6] = clock64();  // GP stencil
 
     // ---------------- output ----------------
-    float* xout = a.x_out + (long long)b * H * D;
+    float* xout = a.x_out + (long long)b * H * Dio;
     bool viol = false;
     float var = 1.f;
     const bool use_var = a.model_var != nullptr || a.use_var_uniform;
@@ -477,6 +489,12 @@ __global__ void __launch_bounds__(GUIDE_THREADS) guide_step_kernel(GuideDev g, G
     else if (a.use_var_uniform) var = a.var_uniform;
     for (int i = tid; i < H * D; i += NTH) {
         float grad = -1.f * tot[i];
+        if (pos_only) {  // gradient of the positions out, velocity trajectory updated in place (guides.py:110-112)
+            const int d = i % D, hrow = i / D;
+            if (d < q) xout[hrow * q + d] = grad;
+            else a.vel_io[((long long)b * H + hrow) * q + (d - q)] = __fsub_rn(xu[i], tot[i]);
+            continue;
+        }
         if (a.grad_only) {
             xout[i] = grad;
             continue;
@@ -634,6 +652,7 @@ int guide_launch_step(mpdb_guide* gd, const GuideStepArgs& a, cudaStream_t strea
     MPDB_REQUIRE(smem <= 220 * 1024, "guide: trajectory does not fit in shared memory");
     MPDB_REQUIRE(a.n_iters <= 1 || (a.iter_flags && a.iter_counters && !a.grad_only && a.B <= guide_max_coresident(gd, a.H)),
                  "guide: several evaluations per launch need flag / counter scratch and a co-resident grid");
+    MPDB_REQUIRE(a.vel_io == nullptr || (a.grad_only && a.n_iters <= 1 && g.use_gp >= 0), "guide: position-only mode returns the gradient only");
     const int spg = (g.n_spheres + NSG - 1) / NSG;
     MPDB_REQUIRE(spg >= 1 && spg <= SPG, "guide: bad sphere count");
 #define MPDB_GUIDE_LAUNCH(K, S)                                                                                              \
@@ -778,6 +797,24 @@ extern "C" int mpdb_guide_grad(mpdb_guide* g, const float* x, float* grad, int32
     a.x_in = x;
     a.x_out = grad;
     a.grad_only = 1;
+    a.flag_in = g->flags;
+    a.B = B;
+    a.H = H;
+    return guide_launch_step(g, a, st);
+}
+
+extern "C" int mpdb_guide_grad_pos(mpdb_guide* g, const float* x_pos, float* velocity, float* grad, int32_t B, int32_t H,
+                                   void* stream) {
+    MPDB_REQUIRE(g && x_pos && velocity && grad && B > 0 && H > 1, "mpdb_guide_grad_pos: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    MPDB_CHECK_CUDA(cudaSetDevice(g->device));
+    if (guide_launch_flag(x_pos, (long long)B * H * g->cfg.q_dim, g->flags, st)) return 1;  // the clip looks at the positions only
+    GuideStepArgs a;
+    memset(&a, 0, sizeof(a));
+    a.x_in = x_pos;
+    a.x_out = grad;
+    a.grad_only = 1;
+    a.vel_io = velocity;
     a.flag_in = g->flags;
     a.B = B;
     a.H = H;

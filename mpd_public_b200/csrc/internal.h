@@ -208,6 +208,11 @@ struct GuideStepArgs {
     // shared memory between evaluations; the batch-global clip flag of evaluation k+1 is an atomicOr into iter_flags[k+1]
     // followed by a grid barrier on iter_counters[k] (all CTAs must be co-resident: guide_launch_step checks). n_iters <= 1:
     // one evaluation, flag_in / flag_out as before. Noise, chain slot and x_out are written by the last evaluation.
+    // position-only state (GuideManagerTrajectories, guides.py:15-146): x_in / x_out hold q columns (normalised positions)
+    // and the unnormalised velocity trajectory [B][H][q] lives here; it is read as the velocity half of the state and
+    // updated in place (velocity -= sum_c w_c * clip(d cost_c / d velocity)). Position and velocity gradients of a cost are
+    // clipped separately. grad_only must be set.
+    float* vel_io;
     int n_iters;
     int* iter_flags;            // [n_iters], [0] written by the producer of x_in; zeroed by the caller
     unsigned int* iter_counters;  // [n_iters - 1], zeroed by the caller

@@ -1,4 +1,5 @@
-"""GuideManagerTrajectoriesWithVelocity — mirror of reference `mpd/models/diffusion_models/guides.py:149-236`.
+"""GuideManagerTrajectoriesWithVelocity (reference `mpd/models/diffusion_models/guides.py:149-236`, the manager
+inference.py builds) and the position-only GuideManagerTrajectories (:15-146).
 
 Same constructor arguments (including the **kwargs that swallow inference.py's misspelt
 `num_interpolated_points`) and call convention `guide(x_normalized [B,H,D]) -> grad [B,H,D]`.
@@ -28,8 +29,11 @@ def build_guide_config(robot, mins, maxs, collision_fields, gp, cutoff_margin, c
         for k in range(3):
             cfg.sphere_offset[i][k] = float(robot.sphere_offset[i][k])
         cfg.sphere_radius[i] = float(robot.sphere_radius[i])
+    if len(mins) == robot.q_dim:  # position-only trajectories (GuideManagerTrajectories): the velocity half is not normalised
+        mins = list(mins) + [0.0] * robot.q_dim
+        maxs = list(maxs) + [1.0] * robot.q_dim
     if len(mins) != 2 * robot.q_dim:
-        raise RuntimeError("normaliser limits must cover [q, qdot]")
+        raise RuntimeError("normaliser limits must cover [q, qdot] (or [q] for position-only trajectories)")
     for i in range(len(mins)):
         cfg.mins[i], cfg.maxs[i] = float(mins[i]), float(maxs[i])
     keep = []
@@ -81,14 +85,91 @@ def _dataset_limits(dataset):
     return nz.mins.detach().float().cpu().numpy(), nz.maxs.detach().float().cpu().numpy()
 
 
-class GuideManagerTrajectories(nn.Module):
-    """Position-only guide manager with a persistent velocity trajectory (reference guides.py:15-146). Not used by
-    scripts/inference/inference.py (which builds GuideManagerTrajectoriesWithVelocity, :229); SURVEY §8f.4 — next."""
+def const_vel_trajectory(start_state_pos, goal_state_pos, dt, num_steps, q_dim, set_initial_final_vel_to_zero=False,
+                         device=None):
+    """Restatement of `MultiMPPrior.const_vel_trajectory` (mp_baselines@8a50c3c, source absent; call site guides.py:46-53):
+    num_steps + 1 states on the straight line start -> goal with the constant velocity (goal - start) / (num_steps * dt),
+    optionally zero at both ends. Returns [num_steps + 1, 2 * q_dim]."""
+    start = torch.as_tensor(start_state_pos, dtype=torch.float32, device=device)[:q_dim]
+    goal = torch.as_tensor(goal_state_pos, dtype=torch.float32, device=device)[:q_dim]
+    lam = torch.arange(num_steps + 1, dtype=torch.float32, device=device)[:, None] / float(num_steps)
+    pos = start[None] * (1.0 - lam) + goal[None] * lam
+    vel = ((goal - start) / (num_steps * dt))[None].repeat(num_steps + 1, 1)
+    if set_initial_final_vel_to_zero:
+        vel[0] = 0.0
+        vel[-1] = 0.0
+    return torch.cat((pos, vel), dim=-1)
 
-    def __init__(self, *args, **kwargs):
+
+class GuideManagerTrajectories(nn.Module):
+    """Position-only guide manager with a persistent velocity trajectory — mirror of reference guides.py:15-146
+    (scripts/inference/inference.py itself builds GuideManagerTrajectoriesWithVelocity, :229).
+
+    `guide(x_pos_normalized [B,H,q]) -> grad [B,H,q]`; each call also moves `self.velocity` against the costs' velocity
+    gradients (guides.py:110-112). One CUDA kernel (csrc/guide.cu, position-only mode): unnormalise the positions,
+    interpolate, composite cost on [positions | velocity], per cost clip the position and the velocity gradient separately
+    (norm + 1e-6), zero the end rows, weight, negate. `use_velocity_from_finite_difference=True` needs torch_robotics'
+    `robot.get_velocity` for position-only states (source absent) and is not implemented."""
+    _mpdb_fusable = False  # stateful (velocity): the reverse loop calls it step by step, as the reference does
+
+    def __init__(self, dataset, cost, clip_grad=False, clip_grad_rule='norm', max_grad_norm=1., max_grad_value=0.1,
+                 interpolate_trajectories_for_collision=False, num_interpolated_points_for_collision=128,
+                 use_velocity_from_finite_difference=False, start_state_pos=None, goal_state_pos=None, num_steps=100,
+                 robot=None, n_samples=1, tensor_args=None, **kwargs):
         super().__init__()
-        raise NotImplementedError("GuideManagerTrajectories (position-only state) is not on the inference path; "
-                                  "use GuideManagerTrajectoriesWithVelocity")
+        if not isinstance(cost, CostComposite):
+            raise NotImplementedError("cost must be a mpd_public_b200.CostComposite")
+        if clip_grad and clip_grad_rule != 'norm':
+            raise NotImplementedError("only clip_grad_rule='norm' is implemented (guides.py:127)")
+        if use_velocity_from_finite_difference:
+            raise NotImplementedError("use_velocity_from_finite_difference needs torch_robotics' robot.get_velocity "
+                                      "for position-only states (source absent from the reference tree)")
+        if start_state_pos is None or goal_state_pos is None:
+            raise RuntimeError("start_state_pos and goal_state_pos are required (guides.py:46-53)")
+        self.cost = cost
+        self.dataset = dataset
+        self.interpolate_trajectories_for_collision = interpolate_trajectories_for_collision
+        self.num_interpolated_points_for_collision = num_interpolated_points_for_collision
+        self.clip_grad = clip_grad
+        self.clip_grad_rule = clip_grad_rule
+        self.max_grad_norm = max_grad_norm
+        self.max_grad_value = max_grad_value
+        self.use_velocity_from_finite_difference = use_velocity_from_finite_difference
+        self.robot = robot if robot is not None else cost.robot
+        self.start_state_pos = start_state_pos
+        self.goal_state_pos = goal_state_pos
+        device = (tensor_args or {}).get("device", "cuda")
+        dt = float(getattr(self.robot, "dt", 1.0))
+        traj = const_vel_trajectory(start_state_pos, goal_state_pos, dt, num_steps, self.robot.q_dim,
+                                    set_initial_final_vel_to_zero=True, device=device)
+        vel = traj[:, self.robot.q_dim:]                                   # robot.get_velocity
+        self.velocity = vel[None].repeat(n_samples, 1, 1).contiguous()      # 'H D -> B H D'
+        self._handles = {}
+
+    _config = None  # set below: shared with GuideManagerTrajectoriesWithVelocity
+    _handle = None
+
+    def __del__(self):
+        try:
+            for handle, _, _ in self._handles.values():
+                _lib.lib().mpdb_guide_destroy(handle)
+            self._handles = {}
+        except Exception:
+            pass
+
+    def forward(self, x_pos_normalized):
+        _lib.require_cuda(x_pos_normalized, "x_pos_normalized")
+        x = x_pos_normalized.detach().to(torch.float32).contiguous()
+        B, H, q = x.shape
+        if q != self.robot.q_dim:
+            raise RuntimeError(f"expected position-only trajectories [B, H, {self.robot.q_dim}], got {tuple(x.shape)}")
+        if tuple(self.velocity.shape) != (B, H, q) or self.velocity.device != x.device:
+            raise RuntimeError(f"velocity trajectory is {tuple(self.velocity.shape)} on {self.velocity.device}; the guide was "
+                               f"built for n_samples={self.velocity.shape[0]}, num_steps={self.velocity.shape[1] - 1}")
+        grad = torch.empty_like(x)
+        _lib.check(_lib.lib().mpdb_guide_grad_pos(self._handle(x.device, H), _lib.fptr(x), _lib.fptr(self.velocity),
+                                                  _lib.fptr(grad), B, H, _lib.stream_ptr(x.device)))
+        return grad
 
 
 class GuideManagerTrajectoriesWithVelocity(nn.Module):
@@ -195,3 +276,7 @@ class GuideManagerTrajectoriesWithVelocity(nn.Module):
             scale_ratio = torch.clip(grad_norm, 0., self.max_grad_norm) / grad_norm
             grad = scale_ratio * grad
         return grad
+
+
+GuideManagerTrajectories._config = GuideManagerTrajectoriesWithVelocity._config
+GuideManagerTrajectories._handle = GuideManagerTrajectoriesWithVelocity._handle

@@ -139,9 +139,10 @@ class TrajectoryDataset:
         self.robot = Robot(problem.robot, obstacle_cutoff_margin)
         self.env = problem.env
         self.task = PlanningTask(problem.env, self.robot, device, obstacle_cutoff_margin, use_extra_objects)
-        self.state_dim = problem.robot.state_dim
+        self.state_dim = problem.robot.state_dim if include_velocity else problem.robot.q_dim
         self.threshold_start_goal_pos = 1.83 if problem.robot.kind == "panda" else 1.0
-        lim = torch.stack([torch.as_tensor(problem.mins), torch.as_tensor(problem.maxs)]).to(self.device)
+        # position-only datasets (include_velocity=False, trajectories.py:60-70) normalise the q positions only
+        lim = torch.stack([torch.as_tensor(problem.mins), torch.as_tensor(problem.maxs)])[:, :self.state_dim].to(self.device)
         self.normalizer = DatasetNormalizer({self.field_key_traj: lim}, LimitsNormalizer)
 
     def unnormalize_trajectories(self, x):

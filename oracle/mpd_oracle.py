@@ -17,7 +17,8 @@ Pinning status
   (normalization.py:156-167, including the batch-global clip branch).
 * **Parity unpinned** (sources absent from /root/reference: `mp_baselines@8a50c3c`,
   `torch_robotics@d704c78`, `storm@54543cf`, see .SUBMODULES.json): `interpolate_points`,
-  `panda_sphere_centers`, `GridSDF`, `collision_cost_*`, `gp_cost`. These follow the frozen spec of
+  `panda_sphere_centers`, `GridSDF`, `collision_cost_*`, `gp_cost`, `const_vel_trajectory`; `guide_manager_pos_grad`
+  restates the position-only manager's own lines (guides.py:60-118) on top of them. These follow the frozen spec of
   SURVEY.md Appendix C/E; each choice is a named switch below. The reference holds no tests or
   golden vectors for any of this path.
 """
@@ -378,6 +379,52 @@ def guide_manager_grad(spec: GuideSpec, x_normalized, return_parts=False):
             grad = grad + w * g
     grad = -1.0 * grad
     return (grad, parts) if return_parts else grad
+
+
+def const_vel_trajectory(start_pos, goal_pos, dt, num_steps, q_dim, set_initial_final_vel_to_zero=False, dtype=torch.float32):
+    """`MultiMPPrior.const_vel_trajectory` (mp_baselines@8a50c3c; source absent, call site reference guides.py:46-53) —
+    PARITY UNPINNED. num_steps + 1 states: positions on the straight line, velocity (goal - start) / (num_steps * dt)."""
+    start = torch.as_tensor(start_pos, dtype=dtype)[:q_dim]
+    goal = torch.as_tensor(goal_pos, dtype=dtype)[:q_dim]
+    traj = torch.zeros(num_steps + 1, 2 * q_dim, dtype=dtype)
+    mean_vel = (goal - start) / (num_steps * dt)
+    for i in range(num_steps + 1):
+        traj[i, :q_dim] = start * (num_steps - i) * 1.0 / num_steps + goal * i * 1.0 / num_steps
+    traj[:, q_dim:] = mean_vel[None]
+    if set_initial_final_vel_to_zero:
+        traj[0, q_dim:] = 0.0
+        traj[-1, q_dim:] = 0.0
+    return traj
+
+
+def guide_manager_pos_grad(spec: GuideSpec, x_pos_normalized, velocity):
+    """reference guides.py:60-118 (GuideManagerTrajectories.forward, use_velocity_from_finite_difference=False): the state
+    is [unnormalised positions | the manager's velocity trajectory]; per cost the position and the velocity gradient are
+    clipped separately, end rows zeroed, weighted; returns (-grad_pos, velocity - grad_velocity)."""
+    q = spec.robot.q_dim
+    x_pos = x_pos_normalized.clone()
+    vel = velocity.clone()
+    with torch.enable_grad():
+        x_pos.requires_grad_(True)
+        vel.requires_grad_(True)
+        x_pos = limits_unnormalize(x_pos, spec.mins[:q].to(x_pos.dtype), spec.maxs[:q].to(x_pos.dtype))
+        x_interp = interpolate_points(x_pos, spec.n_interp) if spec.interpolate else x_pos
+        x_pos_vel = torch.cat((x_pos, vel), dim=-1)
+        cost_l, w_l = composite_costs(spec, x_pos_vel, x_interp)
+        grad, grad_velocity = 0, 0
+        for cost, w in zip(cost_l, w_l):
+            g, gv = torch.autograd.grad([cost.sum()], [x_pos, vel], retain_graph=True, allow_unused=True)
+            gv = torch.zeros_like(vel) if gv is None else gv
+            if spec.clip_grad:
+                g = clip_grad_by_norm(g, spec.max_grad_norm)
+                gv = clip_grad_by_norm(gv, spec.max_grad_norm)
+            g[..., 0, :] = 0.0
+            g[..., -1, :] = 0.0
+            gv[..., 0, :] = 0.0
+            gv[..., -1, :] = 0.0
+            grad = grad + w * g
+            grad_velocity = grad_velocity + w * gv
+    return -1.0 * grad, (velocity - grad_velocity).detach()
 
 
 # ------------------------------------------------------------------------------------------------

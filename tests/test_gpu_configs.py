@@ -186,3 +186,50 @@ def test_config5_shard_shape_panda_h128_b512():
                               **dict(kw, guide=None))
     full = model.run_inference(None, hard_cuda, n_samples=batch, horizon=h, return_chain=False, noise=noise.cuda(), **dict(kw, guide=None))
     assert rel(sub, full[:64]) < 2e-5  # B = 64 runs the cluster kernel, B = 512 the per-layer kernels: same arithmetic up to summation order
+
+
+@pytest.mark.parametrize("model_id,batch,wc,ws", [("EnvSimple2D-RobotPointMass", 9, 3e-2, 1e-2), ("EnvSpheres3D-RobotPanda", 5, 1e-2, 1e-4)])
+def test_position_only_guide_manager(model_id, batch, wc, ws):
+    """GuideManagerTrajectories (reference guides.py:15-146): position-only state + the manager's own velocity
+    trajectory, position / velocity gradients clipped separately, velocity updated by every call. Three consecutive calls
+    against the oracle's restatement (gradient and velocity after each)."""
+    import mpd_public_b200 as M
+    prob = S.make_problem_by_id(model_id, n_support_points=H, cell=0.02)
+    ds = M.TrajectoryDataset(prob, "cuda", include_velocity=False)
+    robot, task = ds.robot, ds.task
+    robot.dt = prob.dt
+    q = prob.robot.q_dim
+    assert ds.state_dim == q
+    costs = [M.CostCollision(robot, H, field=f, sigma_coll=1.0) for f in task.get_collision_fields()]
+    weights = [wc] * len(costs)
+    costs.append(M.CostGPTrajectory(robot, H, prob.dt, sigma_gp=1.0))
+    weights.append(ws)
+    guide = M.GuideManagerTrajectories(ds, M.CostComposite(robot, H, costs, weights_cost_l=weights), clip_grad=True,
+                                       interpolate_trajectories_for_collision=True, start_state_pos=torch.as_tensor(prob.start),
+                                       goal_state_pos=torch.as_tensor(prob.goal), num_steps=H - 1, robot=robot, n_samples=batch,
+                                       tensor_args=dict(device="cuda", dtype=torch.float32))
+    texels = [f.texels.cpu() for f in task.get_collision_fields() if hasattr(f, "texels")]
+    spec = O.make_guide_spec(prob, wc, ws, texels_list=texels)
+    vel = O.const_vel_trajectory(prob.start, prob.goal, prob.dt, H - 1, q, set_initial_final_vel_to_zero=True)[:, q:]
+    vel = vel[None].repeat(batch, 1, 1)
+    assert rel(guide.velocity, vel) < 1e-6
+    rng = np.random.default_rng(17)
+    lam = np.linspace(0, 1, H)[None, :, None]
+    x = (1 - lam) * prob.start[None, None, :] + lam * prob.goal[None, None, :]
+    x = 2 * (x - prob.mins[:q]) / (prob.maxs[:q] - prob.mins[:q]) - 1
+    x = torch.as_tensor((x + 0.12 * rng.standard_normal((batch, H, q))).astype(np.float32))
+    x[1, 9, 0] = 1.2  # the batch-global clip of the normaliser looks at the positions
+    xc = x.cuda()
+    for call in range(3):
+        ref, vel = O.guide_manager_pos_grad(spec, x, vel)
+        got = guide(xc)
+        assert got.shape == (batch, H, q)
+        assert float(ref.abs().max()) > 0
+        assert rel(got, ref) < TOL_KERNEL, (call, rel(got, ref))
+        assert rel(guide.velocity, vel) < TOL_KERNEL, (call, rel(guide.velocity, vel))
+        assert float(got[:, 0].abs().max()) == 0 and float(got[:, -1].abs().max()) == 0
+        x = x + ref
+        xc = xc + got
+    with pytest.raises(NotImplementedError):
+        M.GuideManagerTrajectories(ds, guide.cost, use_velocity_from_finite_difference=True, start_state_pos=prob.start,
+                                   goal_state_pos=prob.goal, robot=robot)

@@ -189,3 +189,17 @@ def test_checkpoint_and_dataset_ingestion_roundtrip():
         assert torch.equal(lim.mins, trajs.reshape(-1, 4).min(0).values) and torch.equal(lim.maxs, trajs.reshape(-1, 4).max(0).values)
         x = nz.normalize(trajs, "traj")
         assert float(x.min()) == -1.0 and float(x.max()) == 1.0
+
+
+def test_const_vel_trajectory_matches_the_oracle_restatement():
+    """Velocity trajectory the position-only guide manager starts from (guides.py:46-53)."""
+    import torch
+    from mpd_public_b200.guides import const_vel_trajectory
+    from oracle import mpd_oracle as O
+    start, goal = torch.tensor([0.1, -0.4, 0.3]), torch.tensor([0.9, 0.2, -0.5])
+    for zero_ends in (False, True):
+        a = const_vel_trajectory(start, goal, 0.08, 63, 3, set_initial_final_vel_to_zero=zero_ends, device="cpu")
+        b = O.const_vel_trajectory(start, goal, 0.08, 63, 3, set_initial_final_vel_to_zero=zero_ends)
+        assert a.shape == (64, 6) and torch.allclose(a, b, atol=1e-6)
+        assert torch.equal(a[0, :3], start) and torch.allclose(a[-1, :3], goal)
+        assert (a[0, 3:].abs().sum() == 0) == zero_ends
