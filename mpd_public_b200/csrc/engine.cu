@@ -591,27 +591,37 @@ static bool try_build_mega(mpdb_engine* e, int B, int G, std::string& why) {
 }
 
 static void build_mega(mpdb_engine* e, int B) {
+    // structural build for the workspace batch (skip tensors are sized for it); whether a given launch uses the program is
+    // decided per batch by mega_usable()
     e->mega_ok = false;
-    // samples per cluster: the largest candidate whose tiling fits 8 CTAs and the shared-memory budget (MPDB_MEGA_G pins it)
     static const int forced = []() { const char* v = getenv("MPDB_MEGA_G"); return v ? atoi(v) : 0; }();
     const int Gs[8] = {8, 7, 6, 5, 4, 3, 2, 1};
     for (int G : Gs) {
         if (forced > 0 && G != forced) continue;
         if (forced <= 0 && G != 8 && G != 4 && G != 2 && G != 1) continue;
         if (!try_build_mega(e, B, G, e->mega_why)) continue;
-        // one wave only: with more clusters than can be resident at once the latency chain runs twice and the per-layer
-        // kernels are faster (measured: 128 trajectories = 16 clusters = 2 waves = 543 us vs 358 us). use_mega = 2 overrides.
-        const int n_clusters = (B + G - 1) / G;
-        const int max_clusters = mega_max_active_clusters(e->mega.a_bytes);
-        if (e->use_mega != 2 && n_clusters > max_clusters) {
-            e->mega_why = "batch needs " + std::to_string(n_clusters) + " clusters of " + std::to_string(G) + " trajectories, " +
-                          std::to_string(max_clusters) + " fit in one wave";
-            return;
-        }
         e->mega_ok = true;
         e->mega_why.clear();
         return;
     }
+}
+
+// One wave only: with more clusters than can be resident at once the latency chain runs twice and the per-layer kernels are
+// faster (measured: 128 trajectories = 16 clusters = 2 waves = 543 us vs 358 us). use_mega = 2 overrides.
+static bool mega_usable(mpdb_engine* e, int B, std::string* why = nullptr) {
+    if (!e->mega_ok) { if (why) *why = e->mega_why; return false; }
+    if (!e->use_mega) { if (why) *why = "option mega = 0"; return false; }
+    if (!e->alias_buffers) { if (why) *why = "option alias_buffers = 0 keeps per-layer buffers"; return false; }
+    const int G = e->mega.G;
+    const int n_clusters = (B + G - 1) / G;
+    const int max_clusters = mega_max_active_clusters(e->mega.a_bytes);
+    if (e->use_mega != 2 && n_clusters > max_clusters) {
+        if (why) *why = "batch needs " + std::to_string(n_clusters) + " clusters of " + std::to_string(G) + " trajectories, " +
+                        std::to_string(max_clusters) + " fit in one wave";
+        return false;
+    }
+    if (why) why->clear();
+    return true;
 }
 
 // Can ops[i], ops[i+1] (the two Conv1dBlocks of a ResidualTemporalBlock) run as one cluster-fused launch?
@@ -668,7 +678,7 @@ static int launch_op(mpdb_engine* e, const ConvOp& op, const float* x, const lon
 static int run_unet_body(mpdb_engine* e, const float* x, const long long* t_dev, int t_uniform, int B, cudaStream_t st,
                          bool tc, const FinalArgs* fin = nullptr, bool* fused = nullptr) {
     if (fused) *fused = false;
-    if (tc && e->use_mega && e->mega_ok && e->alias_buffers && t_dev == nullptr && !e->timeline) {
+    if (tc && t_dev == nullptr && !e->timeline && mega_usable(e, B)) {
         MegaProgram P = e->mega;  // one launch: every layer up to final_conv.0 inside thread-block clusters
         P.x = x; P.t = t_uniform; P.B = B;
         P.dbg = e->mega_dbg;
@@ -826,7 +836,6 @@ extern "C" int mpdb_engine_set_option(mpdb_engine* e, const char* name, double v
         if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; e->graph_key.clear(); }
     } else if (n == "mega") {
         MPDB_REQUIRE(value == 0 || value == 1 || value == 2, "mega must be 0 (off), 1 (when the batch fits one wave) or 2 (always)");
-        if ((e->use_mega == 2) != (value == 2)) e->work_batch = 0;  // re-plan: the one-wave rule is applied when the program is built
         e->use_mega = (int)value;
         if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; e->graph_key.clear(); }
     } else if (n == "alias_buffers") {
@@ -941,8 +950,10 @@ extern "C" int mpdb_engine_mega_info(mpdb_engine* e, int32_t B, int32_t* G, int3
     if (n_layers) *n_layers = e->mega.n_layers;
     if (a_bytes) *a_bytes = e->mega.a_bytes;
     if (smem_bytes) *smem_bytes = (int32_t)mega_smem_bytes(e->mega.a_bytes);
-    if (why && why_cap > 0) { strncpy(why, e->mega_why.c_str(), why_cap - 1); why[why_cap - 1] = 0; }
-    return (e->mega_ok && e->use_mega && e->alias_buffers) ? 1 : 0;
+    std::string reason;
+    const bool ok = mega_usable(e, B, &reason);
+    if (why && why_cap > 0) { strncpy(why, reason.c_str(), why_cap - 1); why[why_cap - 1] = 0; }
+    return ok ? 1 : 0;
 }
 
 // Device time of the UNet body (every layer up to final_conv.0, as the loop runs it) per forward: CUDA events on

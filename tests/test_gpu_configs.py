@@ -233,3 +233,39 @@ def test_position_only_guide_manager(model_id, batch, wc, ws):
     with pytest.raises(NotImplementedError):
         M.GuideManagerTrajectories(ds, guide.cost, use_velocity_from_finite_difference=True, start_state_pos=prob.start,
                                    goal_state_pos=prob.goal, robot=robot)
+
+
+def test_position_only_model_runs_the_reverse_loop_with_its_guide():
+    """A position-only diffusion model (state_dim = q_dim) sampled with GuideManagerTrajectories: the stateful guide takes the
+    step-by-step path (ddpm_sample_fn per step on the CUDA entry points). Properties only: finite, hard conditions exact,
+    the guide's velocity trajectory moved."""
+    import mpd_public_b200 as M
+    prob = S.make_problem_by_id("EnvSimple2D-RobotPointMass", n_support_points=H, cell=0.02)
+    ds = M.TrajectoryDataset(prob, "cuda", include_velocity=False)
+    robot, task = ds.robot, ds.task
+    robot.dt = prob.dt
+    q, batch = prob.robot.q_dim, 6
+    sd = S.make_unet_state_dict(3, q, 32, S.UNET_DIM_MULTS[0])
+    unet = M.TemporalUnet(n_support_points=H, state_dim=q, unet_input_dim=32, dim_mults=S.UNET_DIM_MULTS[0])
+    model = M.GaussianDiffusionModel(model=unet, n_diffusion_steps=C.T_DIFF, predict_epsilon=True)
+    model.load_state_dict({"model." + k: torch.as_tensor(v) for k, v in sd.items()}, strict=False)
+    model = model.to("cuda").eval()
+    costs = [M.CostCollision(robot, H, field=f, sigma_coll=1.0) for f in task.get_collision_fields()]
+    weights = [3e-2] * len(costs)
+    costs.append(M.CostGPTrajectory(robot, H, prob.dt, sigma_gp=1.0))
+    weights.append(1e-2)
+    guide = M.GuideManagerTrajectories(ds, M.CostComposite(robot, H, costs, weights_cost_l=weights), clip_grad=True,
+                                       interpolate_trajectories_for_collision=True, start_state_pos=torch.as_tensor(prob.start),
+                                       goal_state_pos=torch.as_tensor(prob.goal), num_steps=H - 1, robot=robot, n_samples=batch,
+                                       tensor_args=dict(device="cuda", dtype=torch.float32))
+    vel0 = guide.velocity.clone()
+    hard = ds.get_hard_conditions(torch.vstack((torch.as_tensor(prob.start), torch.as_tensor(prob.goal))).cuda(), normalize=True)
+    assert hard[0].shape == (q,)
+    torch.manual_seed(4)
+    chain = model.run_inference(None, hard, n_samples=batch, horizon=H, return_chain=True, sample_fn=M.ddpm_sample_fn,
+                                guide=guide, n_guide_steps=2, t_start_guide=C.T_START_GUIDE,
+                                noise_std_extra_schedule_fn=lambda _t: C.NOISE_STD, n_diffusion_steps_without_noise=2)
+    assert chain.shape == (C.T_DIFF + 2 + 1, batch, H, q) and torch.isfinite(chain).all()
+    for k, v in hard.items():
+        assert torch.equal(chain[:, :, k, :], v.expand(chain.shape[0], batch, q))
+    assert not torch.equal(guide.velocity, vel0)
