@@ -349,9 +349,16 @@ __global__ void __launch_bounds__(MG_THREADS, 1) unet_mega_kernel(const __grid_c
         mbar_wait(a_free, (uint32_t)l & 1u);  // orders our stores after the peers' operand reads: no acquire (L1 invalidate) needed
         if (dbg) dbg[6] = clock64();  // every CTA's MMAs of this layer have retired
         if (Ld.oNC > 0) {
-            const int n_out = Ld.type == MG_UP ? 2 : 1;
-            const bool emit = valid && (Ld.type != MG_DOWN || (ll & 1) == 0);
+            // layer constants into registers: inside the loops below every use would be an indexed constant-bank load
+            const int oNC = Ld.oNC, oRT = Ld.oRT, oLp = Ld.oLp, ltype = Ld.type;
+            const uint32_t o_plane = (uint32_t)Ld.o_plane;
+            const int n_out = ltype == MG_UP ? 2 : 1;
+            const bool emit = valid && (ltype != MG_DOWN || (ll & 1) == 0);
             const int mt2 = sg / Ld.oSPT, s2 = sg - mt2 * Ld.oSPT;
+            const int j0 = (rank + 1) % oNC;  // staggered destination order: the writers of a row tile address different peers
+            const uint32_t cta0 = (uint32_t)(mt2 * oNC);
+            unsigned short* const skip_hi = Ld.skip_out_hi;
+            unsigned short* const skip_lo = Ld.skip_out_lo;
             for (int k = 0; k < n_out; ++k) {
                 if (k == 1) {  // up-sampling: the odd output row comes from the second accumulator (warp-wide TMEM load)
                     float w2[8], w3[8];
@@ -362,28 +369,27 @@ __global__ void __launch_bounds__(MG_THREADS, 1) unet_mega_kernel(const __grid_c
                     v[4] += pb1.x; v[5] += pb1.y; v[6] += pb1.z; v[7] += pb1.w;
                 }
                 if (emit) {
-                    const int lo = Ld.type == MG_DOWN ? (ll >> 1) : Ld.type == MG_UP ? 2 * ll + k : ll;
+                    const int lo = ltype == MG_DOWN ? (ll >> 1) : ltype == MG_UP ? 2 * ll + k : ll;
                     uint4 ph, pl;
                     pack_split8(v, ph, pl);
-                    const uint32_t off = (uint32_t)(((c8 / 8) * Ld.oRT + (s2 * Ld.oLp + lo + 2)) * 16);
-                    const uint32_t local_hi = abuf_u32 + off, local_lo = local_hi + (uint32_t)Ld.o_plane;
-                    for (int jj = 0; jj < Ld.oNC; ++jj) {
-                        // staggered destination order: at any moment the writers of a row tile address different peers
-                        int j = rank + 1 + jj;
-                        j -= (j / Ld.oNC) * Ld.oNC;
-                        const uint32_t cta = (uint32_t)(mt2 * Ld.oNC + j);
+                    const uint32_t off = (uint32_t)(((c8 / 8) * oRT + (s2 * oLp + lo + 2)) * 16);
+                    const uint32_t local_hi = abuf_u32 + off, local_lo = local_hi + o_plane;
+                    int j = j0;
+                    for (int jj = 0; jj < oNC; ++jj) {
+                        const uint32_t cta = cta0 + (uint32_t)j;
                         if ((int)cta == rank) {  // own A buffer: plain shared-memory stores
                             *reinterpret_cast<uint4*>(abuf + off) = ph;
-                            *reinterpret_cast<uint4*>(abuf + off + Ld.o_plane) = pl;
+                            *reinterpret_cast<uint4*>(abuf + off + o_plane) = pl;
                         } else {
                             st_cluster_v4(map_to_cta(local_hi, cta), ph);
                             st_cluster_v4(map_to_cta(local_lo, cta), pl);
                         }
+                        if (++j == oNC) j = 0;
                     }
-                    if (Ld.skip_out_hi != nullptr) {  // skip connection: same-level layout in global memory
+                    if (skip_hi != nullptr) {  // skip connection: same-level layout in global memory
                         const size_t o = ((((size_t)cluster * Ld.MT + mt) * (Ld.CO / 8) + c8 / 8) * Ld.RT + (r + 2)) * 8;
-                        *reinterpret_cast<uint4*>(Ld.skip_out_hi + o) = ph;
-                        *reinterpret_cast<uint4*>(Ld.skip_out_lo + o) = pl;
+                        *reinterpret_cast<uint4*>(skip_hi + o) = ph;
+                        *reinterpret_cast<uint4*>(skip_lo + o) = pl;
                     }
                 }
             }
