@@ -682,6 +682,8 @@ static int run_unet_body(mpdb_engine* e, const float* x, const long long* t_dev,
         MegaProgram P = e->mega;  // one launch: every layer up to final_conv.0 inside thread-block clusters
         P.x = x; P.t = t_uniform; P.B = B;
         P.dbg = e->mega_dbg;
+        static const int dbg_cluster = []() { const char* v = getenv("MPDB_MEGA_DBG_CLUSTER"); return v ? atoi(v) : 0; }();
+        P.dbg_cluster = dbg_cluster;
         const long long fuse_bytes = ((((long long)e->cfg.state_dim * e->cfg.unet_input_dim + 3) & ~3LL) + 128LL * 4 * e->cfg.state_dim) * 4;
         if (fin && fused && e->fuse_final && fin->t_dev == nullptr && fin->x == x && fuse_bytes <= P.a_bytes) {
             P.fuse_final = 1;
@@ -1389,7 +1391,9 @@ extern "C" int mpdb_engine_read_mega_timeline(mpdb_engine* e, int64_t* host_out,
     MPDB_CHECK_CUDA(cudaSetDevice(e->device));
     MPDB_CHECK_CUDA(cudaDeviceSynchronize());
     const int n = e->mega.n_layers < max_layers ? e->mega.n_layers : max_layers;
-    MPDB_CHECK_CUDA(cudaMemcpy(host_out, e->mega_dbg, sizeof(long long) * MEGA_DBG * MEGA_CLUSTER * n, cudaMemcpyDeviceToHost));
+    // the slots behind the layers (44..47) hold per-cluster {entry, setup done, exit} stamps on the GPU-wide ns timer
+    const int n_copy = max_layers < MEGA_MAX_LAYERS ? max_layers : MEGA_MAX_LAYERS;
+    MPDB_CHECK_CUDA(cudaMemcpy(host_out, e->mega_dbg, sizeof(long long) * MEGA_DBG * MEGA_CLUSTER * n_copy, cudaMemcpyDeviceToHost));
     if (desc_out)
         for (int k = 0; k < n; ++k) {
             const MegaLayer& L = e->mega.layers[k];

@@ -167,7 +167,8 @@ struct MegaProgram {
     // (what final_kernel does as a separate launch): the timed loop passes its FinalArgs here
     int fuse_final;
     FinalArgs fin;
-    long long* dbg;  // optional timeline: [n_layers][8 ranks][MEGA_DBG] clock64 stamps of cluster 0
+    long long* dbg;  // optional timeline: [n_layers][8 ranks][MEGA_DBG] clock64 stamps of cluster dbg_cluster
+    int dbg_cluster;
 };
 size_t mega_smem_bytes(int a_bytes);
 int mega_max_active_clusters(int a_bytes);

@@ -64,6 +64,8 @@ __global__ void __launch_bounds__(MG_THREADS, 1) unet_mega_kernel(const __grid_c
     volatile int* mma_progress = reinterpret_cast<volatile int*>(tmem_slot + 1);
     float* part = reinterpret_cast<float*>(tmem_slot + 4);            // GroupNorm scratch
 
+    long long t_entry;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_entry));
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int rank = (int)cluster_ctarank();
     const int cluster = blockIdx.x / MEGA_CLUSTER;
@@ -92,6 +94,9 @@ __global__ void __launch_bounds__(MG_THREADS, 1) unet_mega_kernel(const __grid_c
     cluster_sync_all();  // peers have initialised their barriers and cleared their A buffers before any remote access
     const uint32_t tmem_base = *tmem_slot;
     pdl_wait();
+    // debug timeline: per-cluster {kernel entry, setup done, exit} on the GPU-wide nanosecond timer (layer slots 44..47 of the buffer)
+    long long* cdbg = (P.dbg != nullptr && tid == 0 && rank == 0 && cluster < 64) ? P.dbg + (size_t)44 * MEGA_CLUSTER * MEGA_DBG + cluster * 4 : nullptr;
+    if (cdbg) { cdbg[0] = t_entry; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(cdbg[1])); }
 
     if (warp == TC_THREADS / 32) {
         // ===== producer warp: every K-chunk of every layer this CTA takes part in, in program order. The whole warp runs
@@ -167,7 +172,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) unet_mega_kernel(const __grid_c
                 mbar_wait_cluster(a_full, (uint32_t)(l - 1) & 1u);  // operands of this layer have landed (cluster-wide)
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // peers' generic-proxy stores -> tensor core reads
                 tc_fence_after();
-                long long* mdbg = (P.dbg != nullptr && cluster == 0 && lane == 0 && which == 0) ? P.dbg + ((size_t)l * MEGA_CLUSTER + rank) * MEGA_DBG : nullptr;
+                long long* mdbg = (P.dbg != nullptr && cluster == P.dbg_cluster && lane == 0 && which == 0) ? P.dbg + ((size_t)l * MEGA_CLUSTER + rank) * MEGA_DBG : nullptr;
                 if (mdbg) mdbg[8] = clock64();
                 if (which == 0 && lane == 0) *mma_progress = l;
                 if (active) {
@@ -252,7 +257,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) unet_mega_kernel(const __grid_c
         const MegaLayer& Ld = P.layers[l];
         // outputs of the previous layer have landed everywhere (also keeps idle CTAs in lock step)
         if (l > 0) mbar_wait(a_full, (uint32_t)(l - 1) & 1u);  // these warps read nothing the peers wrote: CTA-scope wait
-        long long* dbg = (P.dbg != nullptr && cluster == 0 && tid == 0) ? P.dbg + ((size_t)l * MEGA_CLUSTER + rank) * MEGA_DBG : nullptr;
+        long long* dbg = (P.dbg != nullptr && cluster == P.dbg_cluster && tid == 0) ? P.dbg + ((size_t)l * MEGA_CLUSTER + rank) * MEGA_DBG : nullptr;
         if (dbg) dbg[0] = clock64();  // inputs landed
         const bool active = rank < Ld.MT * Ld.NC;
         const int mt = rank / Ld.NC, nc = rank - mt * Ld.NC;
@@ -470,6 +475,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) unet_mega_kernel(const __grid_c
     }
 
     // teardown
+    if (cdbg) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(cdbg[2]));
     tc_fence_before();
     epi_sync();
     if (warp == 1) {

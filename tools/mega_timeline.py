@@ -66,4 +66,21 @@ for l in range(n):
     r0 = a[l, 0]
     rel = lambda k: (r0[k] - r0[0]) * us if r0[k] else float('nan')
     print(f"{l:3d} {names[d[l,0]]:6s} {d[l,1]:4d} {d[l,2]:4d} | {rel(8):7.2f} {rel(9):7.2f} {rel(10):7.2f} | {rel(1):7.2f} {rel(4):7.2f} {rel(5):7.2f} {rel(12):7.2f} {rel(13):7.2f} {rel(2):7.2f} {rel(6):7.2f} {rel(7):7.2f} {rel(3):7.2f}")
+wa = sum((a[l,0,1]-a[l,0,0])*us for l in range(n) if a[l,0,1])
+ae = sum((a[l,0,2]-max(a[l,0,1],a[l,0,0]))*us for l in range(n))
+ed = sum((a[l,0,3]-a[l,0,2])*us for l in range(n))
+print(f"phase sums rank 0 (us): wait->acc {wa:.1f}  acc->epi {ae:.1f}  epi->deliv {ed:.1f}  cluster {os.environ.get('MPDB_MEGA_DBG_CLUSTER', '0')}")
 print(f"total (first start -> last delivered): {(a[n-1,:,3].max() - t0) * us:.1f} us")
+
+# per-cluster entry / setup / exit on the GPU-wide timer (ns): slots 44..47 of the same buffer
+full = np.array(buf[:]).reshape(48, 8, ND)
+cl = full[44:48].reshape(-1)[:4 * 64].reshape(64, 4).astype(np.float64)
+ids = np.nonzero(cl[:, 0] > 0)[0]
+cl = cl[cl[:, 0] > 0]
+if len(cl):
+    print("per-cluster run (us):", " ".join(f"{i}:{(c[2]-c[1])/1e3:.1f}" for i, c in zip(ids, cl)))
+    t0g = cl[:, 0].min()
+    print(f"clusters: {len(cl)}; kernel entry spread {cl[:,0].max()-t0g:.0f} ns; setup done after entry: "
+          f"{(cl[:,1]-cl[:,0]).min():.0f}..{(cl[:,1]-cl[:,0]).max():.0f} ns; exit after first entry: "
+          f"{(cl[:,2]-t0g).min()/1e3:.1f}..{(cl[:,2]-t0g).max()/1e3:.1f} us; per-cluster run (setup->exit): "
+          f"{((cl[:,2]-cl[:,1])/1e3).min():.1f}..{((cl[:,2]-cl[:,1])/1e3).max():.1f} us")
