@@ -532,7 +532,7 @@ static bool try_build_mega(mpdb_engine* e, int B, int G, std::string& why) {
             if (2 * Ld.a_plane > a_bytes) a_bytes = 2 * Ld.a_plane;
             if (op.in1 >= 0) {
                 const Skip& sk = skips[op.in1];
-                if (sk.ready < 0 || sk.L != op.L_in) { why = "skip connection not produced before use"; return false; }
+                if (sk.ready < 0 || sk.ready > n || sk.L != op.L_in) { why = "skip connection not produced before use"; return false; }
                 MegaLayer g; memset(&g, 0, sizeof(g)); mega_geom(sk.L, G, g);
                 const long long plane = (long long)n_clusters * g.MT * (sk.C / 8) * g.RT * 8;
                 Ld.n_skip = sk.C / TC_KCH; Ld.skip_C = sk.C; Ld.skip_ready = sk.ready;
@@ -566,7 +566,9 @@ static bool try_build_mega(mpdb_engine* e, int B, int G, std::string& why) {
                 if (Ld.type != MG_CONV5) { why = "skip produced by a strided layer"; return false; }
                 const long long plane = (long long)n_clusters * Ld.MT * (sk.C / 8) * Ld.RT * 8;
                 Ld.skip_out_hi = e->mega_skip + sk.off; Ld.skip_out_lo = e->mega_skip + sk.off + plane;
-                sk.ready = n + 1;
+                // complete once every CTA of the cluster has passed the a_free hand-off of the NEXT layer (the writers' issuer
+                // warps arrive there after their own epilogue warps have stored and fenced): mma_progress >= n + 2
+                sk.ready = n + 2;
             }
             if (op.out == e->final_in) Ld.out_cm = const_cast<float*>(buf_ptr(e, op.out, e->work_batch));
         }
@@ -584,6 +586,24 @@ static bool try_build_mega(mpdb_engine* e, int B, int G, std::string& why) {
         const int out_L = Ld.type == MG_DOWN ? Ld.L / 2 : Ld.type == MG_UP ? Ld.L * 2 : Ld.L;
         if (out_L != nx.L) { why = "internal: length mismatch"; return false; }
         Ld.zero_bytes = (k > 0 && (nx.a_plane != Ld.a_plane || nx.L != Ld.L)) ? 2 * nx.a_plane : 0;
+        // remote bytes per destination CTA (mirrors the delivery loop of unet_mega_kernel): producer CTA p = (row tile, chunk)
+        // sends, per sample of its tile and output row, 4 column groups x (16 B hi + 16 B lo) to every CTA of the consuming
+        // row tile; its own share is a plain local store and is not counted
+        for (int p = 0; p < Ld.MT * Ld.NC; ++p) {
+            const int mt = p / Ld.NC;
+            for (int s = 0; s < Ld.SPT; ++s) {
+                const int sg = mt * Ld.SPT + s;
+                if (sg >= G) continue;
+                const int mt2 = sg / Ld.oSPT;
+                for (int j = 0; j < Ld.oNC; ++j) {
+                    const int cta = mt2 * Ld.oNC + j;
+                    if (cta >= MEGA_CLUSTER) { why = "internal: consumer tile outside the cluster"; return false; }
+                    if (cta != p) Ld.tx_in[cta] += out_L * 4 * 32;
+                }
+            }
+        }
+        for (int c = 0; c < MEGA_CLUSTER; ++c)
+            if (Ld.tx_in[c] >= (1 << 20)) { why = "internal: mbarrier tx-count range"; return false; }
     }
     P.a_bytes = (a_bytes + 127) / 128 * 128;
     if (mega_smem_bytes(P.a_bytes) > 227 * 1024) { why = "shared memory budget"; return false; }

@@ -17,12 +17,15 @@
 //     across layer boundaries (weights do not depend on activations), so a layer's first chunk is already resident
 //     when its inputs land; skip connections go through global memory (written once, read once, L2-resident);
 //   * TMEM, mbarriers and the layer program (a __grid_constant__ table) are set up once per forward;
-//   * layer-to-layer synchronisation is two cluster-scope mbarriers per CTA: a_free (every CTA's MMAs of this layer
-//     have retired -> its A buffer may be overwritten) and a_full (every epilogue warp of the cluster has delivered
-//     its outputs). Every warp of every CTA arrives on every CTA's barrier each layer, active or not, so the counts
-//     are constants and idle CTAs stay in lock step. a_free is sent by an issuer warp (off the epilogue's critical path);
-//     the consumer's issuer warp executes the generic->async proxy fence after its acquire, so a hand-off costs one
-//     store round trip, not two;
+//   * layer-to-layer synchronisation is two mbarriers per CTA. a_free (cluster scope): every CTA's MMAs of this layer have
+//     retired -> its A buffer may be overwritten; one arrival per CTA per layer, sent by an issuer warp (off the epilogue's
+//     critical path), active or not, so idle CTAs stay in lock step. a_full (local): the layer's outputs have landed in
+//     THIS CTA's A buffer = its own 16 epilogue warps have arrived + the peers' bytes have been counted: remote slices
+//     are written with st.async, which performs complete_tx on the destination's barrier when the data is there; the
+//     expected byte count per (layer, CTA) is a host-computed constant (MegaLayer::tx_in). No release fence and no
+//     remote arrive on the hand-off (MEMBAR.ALL.GPU waited for the acknowledgement of every remote store: ~0.5 us per
+//     layer, tools/probes/dsmem_probe.cu). The consumer's issuer warp executes the generic->async proxy fence after its
+//     acquire;
 //   * the second accumulators (odd rows of the transposed convolutions, the blocks' 1x1 residual convs) stay in TMEM until
 //     they are needed — holding them in registers through GroupNorm spilled (96 registers at 608 threads).
 //
@@ -77,7 +80,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) unet_mega_kernel(const __grid_c
     if (tid == 0) {
         for (int s = 0; s < MG_STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 2); }  // both issuers release a stage
         mbar_init(acc_done, 2);
-        mbar_init(a_full, MEGA_CLUSTER * (TC_THREADS / 32));  // every epilogue warp of every CTA of the cluster, every layer
+        mbar_init(a_full, TC_THREADS / 32 + 1);  // this CTA's epilogue warps + issuer 0's expect_tx (the peers' st.async bytes), every layer
         mbar_init(a_free, MEGA_CLUSTER);                      // one arrival per CTA, every layer
         *mma_progress = -1;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -158,6 +161,11 @@ __global__ void __launch_bounds__(MG_THREADS, 1) unet_mega_kernel(const __grid_c
             constexpr uint32_t b_lo_fixed = ((2u * TC_NT * 16u) >> 4) << 16;  // weight tile: LBO = 64 rows x 16 B
             int ring_i = 0;
             uint32_t my_acc_ph = 0;
+            // a_full phase l = "the outputs of layer l have landed in this CTA's A buffer": the peers' bytes are counted by
+            // complete_tx (st.async), announced here before any peer can send them (they send after a_free of layer l, which
+            // needs this warp's arrival below)
+            if (which == 0 && lane == 0 && P.n_layers > 1) mbar_expect_tx(a_full, (uint32_t)P.layers[0].tx_in[rank]);
+            __syncwarp();
             if (which == 0 && lane < MEGA_CLUSTER) mbar_arrive_cluster(map_to_cta(a_free, (uint32_t)lane));  // layer 0 reads no A buffer
             for (int l = 1; l < P.n_layers; ++l) {
                 const MegaLayer& Ld = P.layers[l];
@@ -174,7 +182,10 @@ __global__ void __launch_bounds__(MG_THREADS, 1) unet_mega_kernel(const __grid_c
                 tc_fence_after();
                 long long* mdbg = (P.dbg != nullptr && cluster == P.dbg_cluster && lane == 0 && which == 0) ? P.dbg + ((size_t)l * MEGA_CLUSTER + rank) * MEGA_DBG : nullptr;
                 if (mdbg) mdbg[8] = clock64();
-                if (which == 0 && lane == 0) *mma_progress = l;
+                if (which == 0 && lane == 0) {
+                    *mma_progress = l;
+                    if (l + 1 < P.n_layers) mbar_expect_tx(a_full, (uint32_t)Ld.tx_in[rank]);  // phase l (phase l - 1 is complete)
+                }
                 if (active) {
                     uint32_t acc0 = 0u, acc1 = 0u;  // accumulate flags of the main and the second (residual / odd) accumulator
                     for (int c = 0; c < n_main + n_res; ++c, ++ring_i) {
@@ -265,7 +276,10 @@ __global__ void __launch_bounds__(MG_THREADS, 1) unet_mega_kernel(const __grid_c
         const int s = r / Lp, ll = r - s * Lp;
         const int sg = mt * Ld.SPT + s;  // sample within the cluster
         const int b = cluster * P.G + sg;
-        const bool valid = active && (s < Ld.SPT) && (ll < Ld.L) && (sg < P.G) && (b < P.B);
+        // in_tile: this thread owns a real (sample slot, row) of the cluster; slots past the batch end (ragged last cluster)
+        // run as all-zero trajectories so that the delivered byte counts are the same constants in every cluster
+        const bool in_tile = active && (s < Ld.SPT) && (ll < Ld.L) && (sg < P.G);
+        const bool valid = in_tile && (b < P.B);
         const int c8 = nc * TC_NT + cg * 8;
         float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         float4 pb0 = z4, pb1 = z4;  // bias (also needed when the odd rows of an up-sampling layer are delivered)
@@ -323,10 +337,10 @@ __global__ void __launch_bounds__(MG_THREADS, 1) unet_mega_kernel(const __grid_c
                 v[4] += pb1.x; v[5] += pb1.y; v[6] += pb1.z; v[7] += pb1.w;
                 if (Ld.type == MG_CONV5) {
                     switch (Ld.gs) {
-                        case 4: gn_mish8<4, true>(v, valid, r, s, cg, tid, Ld.SPT, Lp, Ld.L, part, pg0, pg1, pe0, pe1, dbg ? dbg + 4 : nullptr); break;
-                        case 8: gn_mish8<8, true>(v, valid, r, s, cg, tid, Ld.SPT, Lp, Ld.L, part, pg0, pg1, pe0, pe1, dbg ? dbg + 4 : nullptr); break;
-                        case 16: gn_mish8<16, true>(v, valid, r, s, cg, tid, Ld.SPT, Lp, Ld.L, part, pg0, pg1, pe0, pe1, dbg ? dbg + 4 : nullptr); break;
-                        default: gn_mish8<32, true>(v, valid, r, s, cg, tid, Ld.SPT, Lp, Ld.L, part, pg0, pg1, pe0, pe1, dbg ? dbg + 4 : nullptr); break;
+                        case 4: gn_mish8<4, true>(v, in_tile, r, s, cg, tid, Ld.SPT, Lp, Ld.L, part, pg0, pg1, pe0, pe1, dbg ? dbg + 4 : nullptr); break;
+                        case 8: gn_mish8<8, true>(v, in_tile, r, s, cg, tid, Ld.SPT, Lp, Ld.L, part, pg0, pg1, pe0, pe1, dbg ? dbg + 4 : nullptr); break;
+                        case 16: gn_mish8<16, true>(v, in_tile, r, s, cg, tid, Ld.SPT, Lp, Ld.L, part, pg0, pg1, pe0, pe1, dbg ? dbg + 4 : nullptr); break;
+                        default: gn_mish8<32, true>(v, in_tile, r, s, cg, tid, Ld.SPT, Lp, Ld.L, part, pg0, pg1, pe0, pe1, dbg ? dbg + 4 : nullptr); break;
                     }
                     v[0] += pc0.x; v[1] += pc0.y; v[2] += pc0.z; v[3] += pc0.w;
                     v[4] += pc1.x; v[5] += pc1.y; v[6] += pc1.z; v[7] += pc1.w;
@@ -358,7 +372,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) unet_mega_kernel(const __grid_c
             const int oNC = Ld.oNC, oRT = Ld.oRT, oLp = Ld.oLp, ltype = Ld.type;
             const uint32_t o_plane = (uint32_t)Ld.o_plane;
             const int n_out = ltype == MG_UP ? 2 : 1;
-            const bool emit = valid && (ltype != MG_DOWN || (ll & 1) == 0);
+            const bool emit = in_tile && (ltype != MG_DOWN || (ll & 1) == 0);
             const int mt2 = sg / Ld.oSPT, s2 = sg - mt2 * Ld.oSPT;
             const int j0 = (rank + 1) % oNC;  // staggered destination order: the writers of a row tile address different peers
             const uint32_t cta0 = (uint32_t)(mt2 * oNC);
@@ -386,8 +400,9 @@ __global__ void __launch_bounds__(MG_THREADS, 1) unet_mega_kernel(const __grid_c
                             *reinterpret_cast<uint4*>(abuf + off) = ph;
                             *reinterpret_cast<uint4*>(abuf + off + o_plane) = pl;
                         } else {
-                            st_cluster_v4(map_to_cta(local_hi, cta), ph);
-                            st_cluster_v4(map_to_cta(local_lo, cta), pl);
+                            const uint32_t bar = map_to_cta(a_full, cta);
+                            st_async_v4(map_to_cta(local_hi, cta), ph, bar);
+                            st_async_v4(map_to_cta(local_lo, cta), pl, bar);
                         }
                         if (++j == oNC) j = 0;
                     }
@@ -467,11 +482,12 @@ __global__ void __launch_bounds__(MG_THREADS, 1) unet_mega_kernel(const __grid_c
         // later) is fenced here; the A-buffer slices are fenced by the consuming issuer warp after its acquire (the stores
         // are complete in the destination's shared memory once the cluster-scope release below is observed), which takes a
         // store round trip off every layer hand-off.
-        if (Ld.skip_out_hi != nullptr) asm volatile("fence.proxy.async;" ::: "memory");
+        if (Ld.skip_out_hi != nullptr) asm volatile("fence.proxy.async;\n\tfence.acq_rel.cluster;" ::: "memory");
         if (dbg) dbg[3] = clock64();  // outputs delivered
         tc_fence_before();  // all TMEM reads of this layer precede the hand-off
         __syncwarp();
-        if (lane < MEGA_CLUSTER && l + 1 < P.n_layers) mbar_arrive_cluster(map_to_cta(a_full, (uint32_t)lane));
+        // local arrive only: the slices sent to the peers complete on THEIR barriers by themselves (st.async)
+        if (lane == 0 && l + 1 < P.n_layers) mbar_arrive_local(a_full);
     }
 
     // teardown

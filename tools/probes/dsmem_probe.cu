@@ -1,5 +1,7 @@
 // Probe: pushing a tile to the 7 peers of an 8-CTA cluster: (a) cp.async.bulk shared::cta -> shared::cluster with
-// complete_tx on the peer's mbarrier, (b) per-thread st.shared::cluster.v4 + fence + mbarrier arrive (512 threads).
+// complete_tx on the peer's mbarrier, (b) per-thread st.shared::cluster.v4 + fence + mbarrier arrive (512 threads),
+// (c) per-thread st.async.v4 with complete_tx on the peer's mbarrier (no release fence, no remote arrive), (d) = (b) without
+// the producer-side proxy fence (what the cluster kernel does: the consumer fences).
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -23,7 +25,7 @@ __global__ void __cluster_dims__(8, 1, 1) dsmem_probe(int bytes, int mode, int i
     unsigned char* dst = sm + 128 + 16384;       // 8 slots of 16 KB
     uint32_t rank; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
     const int tid = threadIdx.x;
-    if (tid == 0) { mbar_init(smem_u32(bar), mode == 0 ? 1 : 7 * 16 + 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    if (tid == 0) { mbar_init(smem_u32(bar), (mode == 0 || mode == 2) ? 1 : 7 * 16 + 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
     for (int i = tid; i < 16384 / 4; i += blockDim.x) ((uint32_t*)src)[i] = i + rank;
     asm volatile("fence.proxy.async;" ::: "memory");
     __syncthreads();
@@ -39,6 +41,16 @@ __global__ void __cluster_dims__(8, 1, 1) dsmem_probe(int bytes, int mode, int i
                                  "r"(smem_u32(src)), "r"(bytes), "r"(mapa(smem_u32(bar), peer)) : "memory");
                 }
             }
+        } else if (mode == 2) {
+            if (tid == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(7 * bytes) : "memory");
+            for (int o = tid * 16; o < bytes; o += blockDim.x * 16) {
+                uint4 v = *reinterpret_cast<uint4*>(src + o);
+                for (uint32_t p = 1; p < 8; ++p) {
+                    const uint32_t peer = (rank + p) & 7;
+                    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(mapa(smem_u32(dst + rank * 16384 + o), peer)),
+                                 "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"(mapa(smem_u32(bar), peer)) : "memory");
+                }
+            }
         } else {
             // 512 threads: each stores its 16-byte pieces to the 7 peers, fence, one arrive per warp per peer
             for (int o = tid * 16; o < bytes; o += blockDim.x * 16) {
@@ -48,7 +60,7 @@ __global__ void __cluster_dims__(8, 1, 1) dsmem_probe(int bytes, int mode, int i
                     asm volatile("st.shared::cluster.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(mapa(smem_u32(dst + rank * 16384 + o), peer)), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
                 }
             }
-            asm volatile("fence.proxy.async;" ::: "memory");
+            if (mode == 1) asm volatile("fence.proxy.async;" ::: "memory");
             __syncwarp();
             const int lane = tid & 31;
             if (lane >= 1 && lane < 8) {
@@ -68,8 +80,8 @@ __global__ void __cluster_dims__(8, 1, 1) dsmem_probe(int bytes, int mode, int i
 int main() {
     long long* out; cudaMalloc(&out, 1024);
     cudaFuncSetAttribute(dsmem_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    printf("mode(0=bulk push,1=st.shared::cluster) bytes | cycles per round (incl. one cluster barrier ~400)\n");
-    for (int mode = 0; mode < 2; ++mode)
+    printf("mode(0=bulk push,1=st.shared::cluster+proxy fence,2=st.async complete_tx,3=st.shared::cluster) bytes | cycles per round (incl. one cluster barrier ~400)\n");
+    for (int mode = 0; mode < 4; ++mode)
         for (int bytes : {1024, 4096, 8192, 12288, 16384}) {
             const int iters = 50;
             dsmem_probe<<<8 * 13, 512, 128 + 16384 * 9>>>(bytes, mode, iters, out);
