@@ -605,6 +605,11 @@ static bool try_build_mega(mpdb_engine* e, int B, int G, std::string& why) {
         for (int c = 0; c < MEGA_CLUSTER; ++c)
             if (Ld.tx_in[c] >= (1 << 20)) { why = "internal: mbarrier tx-count range"; return false; }
     }
+    for (int k = 0; k < n; ++k) {
+        MegaLayer& Ld = P.layers[k];
+        auto inv = [](int d) { return d > 0 ? (65536 + d - 1) / d : 0; };  // exact for x < 512 and d < 512 (x = row, rank, sample index)
+        Ld.inv_Lp = inv(Ld.Lp); Ld.inv_NC = inv(Ld.NC); Ld.inv_oSPT = inv(Ld.oSPT); Ld.inv_oNC = inv(Ld.oNC);
+    }
     P.a_bytes = (a_bytes + 127) / 128 * 128;
     if (mega_smem_bytes(P.a_bytes) > 227 * 1024) { why = "shared memory budget"; return false; }
     return true;

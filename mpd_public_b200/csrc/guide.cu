@@ -38,6 +38,8 @@ struct GuideDev {
     int sphere_frame[MPDB_MAX_SPHERES];
     float sphere_off[MPDB_MAX_SPHERES][3];
     float sphere_r[MPDB_MAX_SPHERES];
+    int frame_begin[10];                   // spheres attached to frame f (1..8) are frame_sphere[frame_begin[f-1] .. frame_begin[f])
+    int frame_sphere[MPDB_MAX_SPHERES];    // sphere indices sorted by frame (stable)
     float mins[MPDB_MAX_STATE_DIM], range[MPDB_MAX_STATE_DIM];
     int n_grid;
     const float* tex[MPDB_MAX_GRID_FIELDS];
@@ -75,6 +77,15 @@ static GuideDev make_dev(const mpdb_guide_config& c) {
         d.sphere_frame[i] = c.sphere_frame[i];
         for (int k = 0; k < 3; ++k) d.sphere_off[i][k] = c.sphere_offset[i][k];
         d.sphere_r[i] = c.sphere_radius[i];
+    }
+    {
+        int n = 0;
+        for (int f = 1; f <= 8; ++f) {
+            d.frame_begin[f - 1] = n;
+            for (int i = 0; i < c.n_spheres; ++i)
+                if (c.sphere_frame[i] == f) d.frame_sphere[n++] = i;
+        }
+        d.frame_begin[8] = d.frame_begin[9] = n;
     }
     for (int i = 0; i < d.D; ++i) {
         d.mins[i] = c.mins[i];
@@ -172,14 +183,17 @@ __device__ __forceinline__ void fk_chain_row(const GuideDev& g, int r3, const fl
         c0 = n0; c1 = n1; c2 = a2;
         sc[(j * 3 + r3) * FK_ROWS] = o;
         sc[(21 + j * 3 + r3) * FK_ROWS] = c2;  // joint axis = third column
-        for (int s = 0; s < g.n_spheres; ++s)
-            if (g.sphere_frame[s] == j + 1)
-                cen[(s * 3 + r3) * FK_ROWS] = o + c0 * g.sphere_off[s][0] + c1 * g.sphere_off[s][1] + c2 * g.sphere_off[s][2];
+        // the spheres attached to this frame (host-sorted list: no scan over all spheres per joint)
+        for (int t = g.frame_begin[j]; t < g.frame_begin[j + 1]; ++t) {
+            const int s = g.frame_sphere[t];
+            cen[(s * 3 + r3) * FK_ROWS] = o + c0 * g.sphere_off[s][0] + c1 * g.sphere_off[s][1] + c2 * g.sphere_off[s][2];
+        }
     }
     o += c0 * g.flange[0] + c1 * g.flange[1] + c2 * g.flange[2];
-    for (int s = 0; s < g.n_spheres; ++s)
-        if (g.sphere_frame[s] == 8)
-            cen[(s * 3 + r3) * FK_ROWS] = o + c0 * g.sphere_off[s][0] + c1 * g.sphere_off[s][1] + c2 * g.sphere_off[s][2];
+    for (int t = g.frame_begin[7]; t < g.frame_begin[8]; ++t) {
+        const int s = g.frame_sphere[t];
+        cen[(s * 3 + r3) * FK_ROWS] = o + c0 * g.sphere_off[s][0] + c1 * g.sphere_off[s][1] + c2 * g.sphere_off[s][2];
+    }
 }
 
 __device__ __forceinline__ void fk_row(const GuideDev& g, const float (&qv)[7], float* sc, float* cen) {
@@ -396,8 +410,10 @@ __global__ void __launch_bounds__(GUIDE_THREADS) guide_step_kernel(GuideDev g, G
             const int h = on ? item % H : 0, f = on ? item / H : 0;
             float gsk = 0.f;
             if (on && k < q) {
-                int lo_i = (int)floorf((float)(h - 1) * inv_ratio) - 1;
-                int hi_i = (int)ceilf((float)(h + 1) * inv_ratio) + 1;
+                // rows i with ratio * i in (h - 1, h + 1) touch h; floor / ceil leave one row of slack on each side for the
+                // rounding of the products (rows that do not touch h contribute with weight 0)
+                int lo_i = (int)floorf((float)(h - 1) * inv_ratio);
+                int hi_i = (int)ceilf((float)(h + 1) * inv_ratio);
                 if (lo_i < 0) lo_i = 0;
                 if (hi_i > NI - 1) hi_i = NI - 1;
                 // 32-bit indices, no data-dependent branch (rows that do not touch h contribute with weight 0): the four

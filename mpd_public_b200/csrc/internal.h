@@ -115,6 +115,7 @@ struct MegaLayer {
     int res_mode;             // conv1 of a block: 1 = identity (fp32 values kept in registers), 2 = fused 1x1 conv; else 0
     int oSPT, oLp, oNC, oRT, o_plane;
     int zero_bytes;           // > 0: the A buffer changes layout after this layer; every CTA clears this many bytes
+    int inv_Lp, inv_NC, inv_oSPT, inv_oNC;  // ceil(65536 / d): x / d == (x * inv) >> 16 for the small operands of the kernel's index math
     int tx_in[MEGA_CLUSTER];  // bytes this layer's epilogues deliver into each CTA's A buffer FROM OTHER CTAs (st.async
                               // complete_tx count the CTA's a_full barrier expects for the layer)
     const unsigned short* w;      // packed [NC][n_a + n_skip][taps][4][hi 32 | lo 32][8]

@@ -271,9 +271,10 @@ __global__ void __launch_bounds__(MG_THREADS, 1) unet_mega_kernel(const __grid_c
         long long* dbg = (P.dbg != nullptr && cluster == P.dbg_cluster && tid == 0) ? P.dbg + ((size_t)l * MEGA_CLUSTER + rank) * MEGA_DBG : nullptr;
         if (dbg) dbg[0] = clock64();  // inputs landed
         const bool active = rank < Ld.MT * Ld.NC;
-        const int mt = rank / Ld.NC, nc = rank - mt * Ld.NC;
+        // small-operand divisions by host-computed reciprocals (a generic 32-bit division is ~35 dependent instructions)
+        const int mt = (rank * Ld.inv_NC) >> 16, nc = rank - mt * Ld.NC;
         const int Lp = Ld.Lp;
-        const int s = r / Lp, ll = r - s * Lp;
+        const int s = (r * Ld.inv_Lp) >> 16, ll = r - s * Lp;
         const int sg = mt * Ld.SPT + s;  // sample within the cluster
         const int b = cluster * P.G + sg;
         // in_tile: this thread owns a real (sample slot, row) of the cluster; slots past the batch end (ragged last cluster)
@@ -281,6 +282,15 @@ __global__ void __launch_bounds__(MG_THREADS, 1) unet_mega_kernel(const __grid_c
         const bool in_tile = active && (s < Ld.SPT) && (ll < Ld.L) && (sg < P.G);
         const bool valid = in_tile && (b < P.B);
         const int c8 = nc * TC_NT + cg * 8;
+        // delivery geometry of this thread (consumer row tile, first destination, byte offset of its row slot): index math
+        // done here, in the shadow of the MMAs, not between the a_free hand-off and the stores
+        uint32_t d_off = 0u, d_meta = 0u;
+        if (Ld.oNC > 0) {
+            const int mt2 = (sg * Ld.inv_oSPT) >> 16, s2 = sg - mt2 * Ld.oSPT;
+            const int j0 = (rank + 1) - (((rank + 1) * Ld.inv_oNC) >> 16) * Ld.oNC;  // staggered destination order: the writers of a row tile address different peers
+            d_off = (uint32_t)(((c8 / 8) * Ld.oRT + (s2 * Ld.oLp + 2)) * 16);
+            d_meta = (uint32_t)(mt2 * Ld.oNC) | ((uint32_t)j0 << 8);
+        }
         float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         float4 pb0 = z4, pb1 = z4;  // bias (also needed when the odd rows of an up-sampling layer are delivered)
 
@@ -369,13 +379,12 @@ __global__ void __launch_bounds__(MG_THREADS, 1) unet_mega_kernel(const __grid_c
         if (dbg) dbg[6] = clock64();  // every CTA's MMAs of this layer have retired
         if (Ld.oNC > 0) {
             // layer constants into registers: inside the loops below every use would be an indexed constant-bank load
-            const int oNC = Ld.oNC, oRT = Ld.oRT, oLp = Ld.oLp, ltype = Ld.type;
+            const int oNC = Ld.oNC, ltype = Ld.type;
             const uint32_t o_plane = (uint32_t)Ld.o_plane;
             const int n_out = ltype == MG_UP ? 2 : 1;
             const bool emit = in_tile && (ltype != MG_DOWN || (ll & 1) == 0);
-            const int mt2 = sg / Ld.oSPT, s2 = sg - mt2 * Ld.oSPT;
-            const int j0 = (rank + 1) % oNC;  // staggered destination order: the writers of a row tile address different peers
-            const uint32_t cta0 = (uint32_t)(mt2 * oNC);
+            const int j0 = (int)(d_meta >> 8);
+            const uint32_t cta0 = d_meta & 0xffu;
             unsigned short* const skip_hi = Ld.skip_out_hi;
             unsigned short* const skip_lo = Ld.skip_out_lo;
             for (int k = 0; k < n_out; ++k) {
@@ -391,7 +400,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) unet_mega_kernel(const __grid_c
                     const int lo = ltype == MG_DOWN ? (ll >> 1) : ltype == MG_UP ? 2 * ll + k : ll;
                     uint4 ph, pl;
                     pack_split8(v, ph, pl);
-                    const uint32_t off = (uint32_t)(((c8 / 8) * oRT + (s2 * oLp + lo + 2)) * 16);
+                    const uint32_t off = d_off + (uint32_t)lo * 16u;
                     const uint32_t local_hi = abuf_u32 + off, local_lo = local_hi + o_plane;
                     int j = j0;
                     for (int jj = 0; jj < oNC; ++jj) {
