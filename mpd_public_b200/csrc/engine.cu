@@ -566,9 +566,10 @@ static bool try_build_mega(mpdb_engine* e, int B, int G, std::string& why) {
                 if (Ld.type != MG_CONV5) { why = "skip produced by a strided layer"; return false; }
                 const long long plane = (long long)n_clusters * Ld.MT * (sk.C / 8) * Ld.RT * 8;
                 Ld.skip_out_hi = e->mega_skip + sk.off; Ld.skip_out_lo = e->mega_skip + sk.off + plane;
-                // complete once every CTA of the cluster has passed the a_free hand-off of the NEXT layer (the writers' issuer
-                // warps arrive there after their own epilogue warps have stored and fenced): mma_progress >= n + 2
-                sk.ready = n + 2;
+                // The writers fence their skip stores in the shadow of the NEXT layer's MMAs and arrive on their a_full after
+                // that; their issuer warps then pass the a_free hand-off of layer n + 2, which every CTA of the cluster
+                // observes before its own mma_progress reaches n + 3
+                sk.ready = n + 3;
             }
             if (op.out == e->final_in) Ld.out_cm = const_cast<float*>(buf_ptr(e, op.out, e->work_batch));
         }
@@ -581,11 +582,18 @@ static bool try_build_mega(mpdb_engine* e, int B, int G, std::string& why) {
         MegaLayer& Ld = P.layers[k];
         const MegaLayer& nx = P.layers[k + 1];
         Ld.oSPT = nx.SPT; Ld.oLp = nx.Lp; Ld.oNC = nx.NC; Ld.oRT = nx.RT;
-        Ld.o_plane = (Ld.CO / 8) * nx.RT * 16;
-        if (Ld.o_plane != nx.a_plane) { why = "internal: plane mismatch"; return false; }
+        if ((Ld.CO / 8) * nx.RT * 16 != nx.a_plane) { why = "internal: plane mismatch"; return false; }
         const int out_L = Ld.type == MG_DOWN ? Ld.L / 2 : Ld.type == MG_UP ? Ld.L * 2 : Ld.L;
         if (out_L != nx.L) { why = "internal: length mismatch"; return false; }
-        Ld.zero_bytes = (k > 0 && (nx.a_plane != Ld.a_plane || nx.L != Ld.L)) ? 2 * nx.a_plane : 0;
+        // The lo plane sits at one fixed offset (the largest plane of the program), so layers of the same length share their
+        // zero halo rows whatever their channel count: the A buffer is cleared only where the LENGTH changes (6 layers, not
+        // 12), over the largest extent any layer of the following same-length run reads.
+        Ld.zero_bytes = 0;
+        if (k > 0 && nx.L != Ld.L) {
+            int zb = 0;
+            for (int m = k + 1; m < n && P.layers[m].L == nx.L; ++m) zb = std::max(zb, P.layers[m].a_plane);
+            Ld.zero_bytes = zb;
+        }
         // remote bytes per destination CTA (mirrors the delivery loop of unet_mega_kernel): producer CTA p = (row tile, chunk)
         // sends, per sample of its tile and output row, 4 column groups x (16 B hi + 16 B lo) to every CTA of the consuming
         // row tile; its own share is a plain local store and is not counted
@@ -605,6 +613,11 @@ static bool try_build_mega(mpdb_engine* e, int B, int G, std::string& why) {
         for (int c = 0; c < MEGA_CLUSTER; ++c)
             if (Ld.tx_in[c] >= (1 << 20)) { why = "internal: mbarrier tx-count range"; return false; }
     }
+    for (int k = 0; k < n; ++k) {  // after the extents have been used above: every layer addresses the lo plane at the same offset
+        P.layers[k].a_plane = a_bytes / 2;
+        P.layers[k].o_plane = a_bytes / 2;
+    }
+    if ((a_bytes / 2) % 16 != 0) { why = "internal: plane alignment"; return false; }
     for (int k = 0; k < n; ++k) {
         MegaLayer& Ld = P.layers[k];
         auto inv = [](int d) { return d > 0 ? (65536 + d - 1) / d : 0; };  // exact for x < 512 and d < 512 (x = row, rank, sample index)

@@ -109,12 +109,12 @@ struct MegaLayer {
     int L, Lp, SPT, MT, NC, RT;
     int n_a, n_skip;          // main K-chunks (32 channels each) from the A buffer / from the global skip tensor
     int n_res_a, n_res_skip;  // K-chunks of the block's 1x1 residual conv, issued after the main chunks of conv0
-    int a_plane;              // bytes between the hi and lo planes of the A buffer as this layer reads it
+    int a_plane;              // bytes between the hi and lo planes of the A buffer (one fixed offset for the whole program)
     int skip_C, skip_ready;   // channels of the skip tensor; index of the first layer at which it is complete
     int CO, gs;
     int res_mode;             // conv1 of a block: 1 = identity (fp32 values kept in registers), 2 = fused 1x1 conv; else 0
     int oSPT, oLp, oNC, oRT, o_plane;
-    int zero_bytes;           // > 0: the A buffer changes layout after this layer; every CTA clears this many bytes
+    int zero_bytes;           // > 0: the sample length changes after this layer; every CTA clears this many bytes of each plane
     int inv_Lp, inv_NC, inv_oSPT, inv_oNC;  // ceil(65536 / d): x / d == (x * inv) >> 16 for the small operands of the kernel's index math
     int tx_in[MEGA_CLUSTER];  // bytes this layer's epilogues deliver into each CTA's A buffer FROM OTHER CTAs (st.async
                               // complete_tx count the CTA's a_full barrier expects for the layer)

@@ -291,6 +291,10 @@ __global__ void __launch_bounds__(MG_THREADS, 1) unet_mega_kernel(const __grid_c
             d_off = (uint32_t)(((c8 / 8) * Ld.oRT + (s2 * Ld.oLp + 2)) * 16);
             d_meta = (uint32_t)(mt2 * Ld.oNC) | ((uint32_t)j0 << 8);
         }
+        // skip tensor written by the previous layer: its global stores are made visible at cluster scope here, in the
+        // shadow of this layer's MMAs (MEMBAR.ALL.GPU waits for their acknowledgement: ~1 us on the hand-off otherwise);
+        // the arrive at the end of this layer publishes it (MegaLayer::skip_ready counts on that)
+        if (l > 0 && P.layers[l - 1].skip_out_hi != nullptr) asm volatile("fence.acq_rel.cluster;" ::: "memory");
         float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         float4 pb0 = z4, pb1 = z4;  // bias (also needed when the odd rows of an up-sampling layer are delivered)
 
@@ -336,8 +340,14 @@ __global__ void __launch_bounds__(MG_THREADS, 1) unet_mega_kernel(const __grid_c
             }
             // this CTA no longer reads its A buffer: clear it if the next layer uses another layout (issuer warp 0 then tells the cluster)
             if (Ld.zero_bytes > 0) {
-                for (int i = tid; i < Ld.zero_bytes / 16; i += TC_THREADS) reinterpret_cast<uint4*>(abuf)[i] = make_uint4(0u, 0u, 0u, 0u);
-                asm volatile("fence.proxy.async;" ::: "memory");
+                // generic-proxy stores, like the delivered slices: made visible to the tensor core by the consuming issuer
+                // warp's proxy fence after its a_full acquire (no fence here, on the epilogue's critical path)
+                const int nz = Ld.zero_bytes / 16;
+                uint4* lo_plane = reinterpret_cast<uint4*>(abuf + Ld.a_plane);
+                for (int i = tid; i < nz; i += TC_THREADS) {
+                    reinterpret_cast<uint4*>(abuf)[i] = make_uint4(0u, 0u, 0u, 0u);
+                    lo_plane[i] = make_uint4(0u, 0u, 0u, 0u);
+                }
                 asm volatile("bar.arrive 2, %0;" ::"n"(TC_THREADS + 32) : "memory");  // issuer warp 0 sends a_free once all 16 warps are here
             }
             if (dbg) dbg[5] = clock64();
@@ -491,7 +501,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) unet_mega_kernel(const __grid_c
         // later) is fenced here; the A-buffer slices are fenced by the consuming issuer warp after its acquire (the stores
         // are complete in the destination's shared memory once the cluster-scope release below is observed), which takes a
         // store round trip off every layer hand-off.
-        if (Ld.skip_out_hi != nullptr) asm volatile("fence.proxy.async;\n\tfence.acq_rel.cluster;" ::: "memory");
+        if (Ld.skip_out_hi != nullptr) asm volatile("fence.proxy.async;" ::: "memory");
         if (dbg) dbg[3] = clock64();  // outputs delivered
         tc_fence_before();  // all TMEM reads of this layer precede the hand-off
         __syncwarp();
