@@ -15,6 +15,10 @@ constexpr int TC_THREADS = 512;  // 16 warps: warp w reads TMEM lane quarter (w 
 constexpr int TC_A_PLANE_BYTES = (TC_KCH / 8) * TC_RT * 16;  // 8448
 constexpr int TC_B_TAP_BYTES = (TC_KCH / 8) * TC_NT * 16;    // 2048
 constexpr int TC_STAGE_BYTES = 2 * TC_A_PLANE_BYTES + 2 * 5 * TC_B_TAP_BYTES;  // 37376
+// GroupNorm scratch (gn_mish8): two moments x [32 row groups of 4][8 blocks] floats, column sums [2][12][8] doubles,
+// {mean, rstd} [12][8][2] floats
+constexpr int TC_GN_PART = 32 * 8;
+constexpr int TC_GN_SCRATCH_BYTES = (2 * TC_GN_PART + 12 * 8 * 2) * (int)sizeof(float) + 2 * 12 * 8 * (int)sizeof(double);
 constexpr int TC_TMEM_COLS = 128;  // main: [0,32) = hi*hi + lo*hi, [32,64) = hi*lo ; residual conv: [64,96), [96,128)
 
 // ---------------------------------------------------------------------------------------------------
@@ -209,8 +213,8 @@ __device__ __forceinline__ void gn_mish8(float (&v)[8], bool valid, int r, int s
                                          float* part, const float4& g0, const float4& g1, const float4& e0, const float4& e1,
                                          long long* dbg = nullptr) {
     constexpr int BPG = GS / 4;
-    float* part2 = part + 128 * 8;
-    double* cs = reinterpret_cast<double*>(part + 2 * 128 * 8);  // [2][12][8]
+    float* part2 = part + TC_GN_PART;
+    double* cs = reinterpret_cast<double*>(part + 2 * TC_GN_PART);  // [2][12][8]
     {
         // level 0: per-thread partials of the two 4-channel blocks, then the 4 rows of an aligned row group are added by
         // two xor-shuffles (rows = lanes; samples start at multiples of 4 rows, so groups never straddle samples and the

@@ -48,7 +48,12 @@ constexpr int MG_THREADS = TC_THREADS + 96;  // 16 epilogue warps + 1 producer w
 // A_hi x [W_hi | W_lo] products, issuer 1 the A_lo x W_hi products, into separate accumulators (deterministic sums).
 constexpr int MG_STAGES = 3;
 constexpr int MG_TMEM_COLS = 256;  // main: [0,32) hi*hi, [32,64) hi*lo, [64,96) lo*hi; residual conv / odd outputs: the same at +128
-constexpr int MG_SCRATCH_BYTES = (2 * 128 * 8 + 12 * 8 * 2) * (int)sizeof(float) + 2 * 12 * 8 * (int)sizeof(double);
+constexpr int MG_SCRATCH_BYTES = TC_GN_SCRATCH_BYTES;
+// A ring stage = [acts hi | acts lo | 5 taps of weights | the block's 1x1 residual weights of the same 32 input channels]: the
+// residual conv rides along with conv0's chunks (same activations, a sixth "tap" into the second accumulator) instead of
+// running as chunks of its own, which were bound by the ring's depth / L2 latency (2 MMA pairs per ~340-cycle chunk) and
+// loaded the skip activations a second time.
+constexpr int MG_STAGE_BYTES = TC_STAGE_BYTES + 2 * TC_B_TAP_BYTES;
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;
@@ -62,7 +67,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) unet_mega_kernel(const __grid_c
     extern __shared__ __align__(128) unsigned char smem_raw[];
     unsigned char* abuf = smem_raw;                                   // current activation, operand layout
     unsigned char* stages = abuf + P.a_bytes;                         // ring: [acts hi | acts lo | weights] per stage
-    uint64_t* bars = reinterpret_cast<uint64_t*>(stages + MG_STAGES * TC_STAGE_BYTES);  // full[S], empty[S], acc_done, a_full, a_free
+    uint64_t* bars = reinterpret_cast<uint64_t*>(stages + MG_STAGES * MG_STAGE_BYTES);  // full[S], empty[S], acc_done, a_full, a_free
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MG_STAGES + 3);
     volatile int* mma_progress = reinterpret_cast<volatile int*>(tmem_slot + 1);
     float* part = reinterpret_cast<float*>(tmem_slot + 4);            // GroupNorm scratch
@@ -111,20 +116,20 @@ __global__ void __launch_bounds__(MG_THREADS, 1) unet_mega_kernel(const __grid_c
                 if (Ld.type == MG_INPUT || rank >= Ld.MT * Ld.NC) continue;
                 const int mt = rank / Ld.NC, nc = rank - mt * Ld.NC;
                 const int ntaps = Ld.type == MG_CONV5 ? 5 : Ld.type == MG_DOWN ? 3 : 4;
-                const int n_main = Ld.n_a + Ld.n_skip, n_res = Ld.n_res_a + Ld.n_res_skip;
+                const int n_main = Ld.n_a + Ld.n_skip;
+                const bool has_res = Ld.n_res_a + Ld.n_res_skip > 0;  // same chunking as the main conv (engine.cu)
                 const uint32_t act_bytes = (uint32_t)(TC_KCH / 8) * Ld.RT * 16;  // one plane of one K-chunk
                 bool skip_checked = false;
-                for (int c = 0; c < n_main + n_res; ++c, ++i) {
+                for (int c = 0; c < n_main; ++c, ++i) {
                     const int s = i % MG_STAGES;
                     if (i >= MG_STAGES) mbar_wait(empty0 + 8 * s, ((uint32_t)(i / MG_STAGES) & 1u) ^ 1u);
-                    const bool is_res = c >= n_main;
-                    const int cc = is_res ? c - n_main : c;
-                    const int na = is_res ? Ld.n_res_a : Ld.n_a;
+                    const int cc = c;
+                    const int na = Ld.n_a;
                     const bool from_skip = cc >= na;
-                    const uint32_t wbytes = (is_res ? 1u : (uint32_t)ntaps) * 2u * TC_B_TAP_BYTES;
-                    const unsigned short* wsrc = is_res ? Ld.res_w + ((size_t)nc * n_res + cc) * (2 * TC_B_TAP_BYTES / 2)
-                                                        : Ld.w + ((size_t)nc * n_main + cc) * ((size_t)ntaps * 2 * TC_B_TAP_BYTES / 2);
-                    const uint32_t st = stages_u32 + (uint32_t)s * TC_STAGE_BYTES;
+                    const uint32_t wbytes = (uint32_t)ntaps * 2u * TC_B_TAP_BYTES;
+                    const uint32_t rbytes = has_res ? 2u * TC_B_TAP_BYTES : 0u;
+                    const unsigned short* wsrc = Ld.w + ((size_t)nc * n_main + cc) * ((size_t)ntaps * 2 * TC_B_TAP_BYTES / 2);
+                    const uint32_t st = stages_u32 + (uint32_t)s * MG_STAGE_BYTES;
                     if (from_skip && !skip_checked) {
                         // the skip tensor was written (by CTAs of this cluster) many layers ago; make the dependency explicit
                         const long long t0 = clock64();
@@ -133,8 +138,11 @@ __global__ void __launch_bounds__(MG_THREADS, 1) unet_mega_kernel(const __grid_c
                         skip_checked = true;
                     }
                     __syncwarp();
-                    mbar_expect_tx_elect(full0 + 8 * s, wbytes + (from_skip ? 2u * act_bytes : 0u));
+                    mbar_expect_tx_elect(full0 + 8 * s, wbytes + rbytes + (from_skip ? 2u * act_bytes : 0u));
                     bulk_g2s_elect(st + 2 * TC_A_PLANE_BYTES, wsrc, wbytes, full0 + 8 * s);
+                    if (has_res)  // the residual conv's weights of this chunk, behind the (at most 5) taps
+                        bulk_g2s_elect(st + 2 * TC_A_PLANE_BYTES + 5 * 2 * TC_B_TAP_BYTES, Ld.res_w + ((size_t)nc * n_main + cc) * (2 * TC_B_TAP_BYTES / 2),
+                                       rbytes, full0 + 8 * s);
                     if (from_skip) {
                         const size_t aoff = (((size_t)cluster * Ld.MT + mt) * (Ld.skip_C / 8) + (size_t)(cc - na) * (TC_KCH / 8)) * Ld.RT * 8;
                         bulk_g2s_elect(st, Ld.skip_hi + aoff, act_bytes, full0 + 8 * s);
@@ -171,8 +179,9 @@ __global__ void __launch_bounds__(MG_THREADS, 1) unet_mega_kernel(const __grid_c
                 const MegaLayer& Ld = P.layers[l];
                 // layer parameters first, so that nothing but the issue itself follows the wait
                 const bool active = rank < Ld.MT * Ld.NC;
-                const int n_main = Ld.n_a + Ld.n_skip, n_res = Ld.n_res_a + Ld.n_res_skip;
-                const int n_a = Ld.n_a, n_res_a = Ld.n_res_a, type = Ld.type, zero_bytes = Ld.zero_bytes;
+                const int n_main = Ld.n_a + Ld.n_skip;
+                const bool has_res = Ld.n_res_a + Ld.n_res_skip > 0;
+                const int n_a = Ld.n_a, type = Ld.type, zero_bytes = Ld.zero_bytes;
                 const uint32_t lbo = (uint32_t)Ld.RT * 16;
                 const uint32_t lo_plane = which == 1 ? (uint32_t)Ld.a_plane : 0u;
                 // the first chunk's weights do not depend on the previous layer: wait for them first
@@ -188,12 +197,11 @@ __global__ void __launch_bounds__(MG_THREADS, 1) unet_mega_kernel(const __grid_c
                 }
                 if (active) {
                     uint32_t acc0 = 0u, acc1 = 0u;  // accumulate flags of the main and the second (residual / odd) accumulator
-                    for (int c = 0; c < n_main + n_res; ++c, ++ring_i) {
+                    for (int c = 0; c < n_main; ++c, ++ring_i) {
                         const int sidx = ring_i % MG_STAGES;
-                        const bool is_res = c >= n_main;
-                        const int cc = is_res ? c - n_main : c;
-                        const bool from_a = cc < (is_res ? n_res_a : n_a);
-                        const uint32_t st = stages_u32 + (uint32_t)sidx * TC_STAGE_BYTES;
+                        const int cc = c;
+                        const bool from_a = cc < n_a;
+                        const uint32_t st = stages_u32 + (uint32_t)sidx * MG_STAGE_BYTES;
                         const uint32_t aaddr = from_a ? abuf_u32 + (uint32_t)cc * (TC_KCH / 8) * lbo + lo_plane
                                                       : st + (which == 1 ? (uint32_t)TC_A_PLANE_BYTES : 0u);
                         const uint32_t a_lo = ((aaddr >> 4) & 0x3FFFu) | ((lbo >> 4) << 16);
@@ -204,13 +212,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) unet_mega_kernel(const __grid_c
                             tc_fence_after();
                         }
                         if (mdbg && c == 0) mdbg[9] = clock64();
-                        if (is_res) {  // 1x1 residual conv: centre row (+2)
-#pragma unroll
-                            for (int kk = 0; kk < TC_KCH / 16; ++kk) {
-                                tc_mma_bf16_elect32(col0 + 128, a_lo + kk * kstep_a + 2, desc_hi, b_lo + kk * kstep_b, desc_hi, idesc, acc1);
-                                acc1 = 1u;
-                            }
-                        } else if (type == MG_CONV5) {  // taps -2..2 -> row shifts 0..4
+                        if (type == MG_CONV5) {  // taps -2..2 -> row shifts 0..4
 #pragma unroll
                             for (int tap = 0; tap < 5; ++tap)
 #pragma unroll
@@ -218,6 +220,13 @@ __global__ void __launch_bounds__(MG_THREADS, 1) unet_mega_kernel(const __grid_c
                                     tc_mma_bf16_elect32(col0, a_lo + kk * kstep_a + tap, desc_hi, b_lo + tap * tap_b + kk * kstep_b, desc_hi, idesc, acc0);
                                     acc0 = 1u;
                                 }
+                            if (has_res) {  // the block's 1x1 residual conv on the same activations: centre row (+2), weights behind the taps
+#pragma unroll
+                                for (int kk = 0; kk < TC_KCH / 16; ++kk) {
+                                    tc_mma_bf16_elect32(col0 + 128, a_lo + kk * kstep_a + 2, desc_hi, b_lo + 5 * tap_b + kk * kstep_b, desc_hi, idesc, acc1);
+                                    acc1 = 1u;
+                                }
+                            }
                         } else if (type == MG_DOWN) {  // k3, pad 1: taps -1..1 -> row shifts 1..3
 #pragma unroll
                             for (int tap = 0; tap < 3; ++tap)
@@ -520,7 +529,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) unet_mega_kernel(const __grid_c
 }
 
 size_t mega_smem_bytes(int a_bytes) {
-    return (size_t)a_bytes + (size_t)MG_STAGES * TC_STAGE_BYTES + (2 * MG_STAGES + 3) * 8 + 16 + MG_SCRATCH_BYTES;
+    return (size_t)a_bytes + (size_t)MG_STAGES * MG_STAGE_BYTES + (2 * MG_STAGES + 3) * 8 + 16 + MG_SCRATCH_BYTES;
 }
 
 // How many clusters of the kernel can be resident at once (they must all fit in one wave for the kernel to pay off:
