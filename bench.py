@@ -415,7 +415,8 @@ def main():
             ach_tf = dom_flops / (dom_ms * 1e-3) / 1e12
             kname = (f"mpdb::unet_mega_kernel (whole TemporalUnet forward in ONE launch: {(B + mega_G - 1) // mega_G} clusters of 8 CTAs x "
                      f"{mega_G} trajectories, {mega_layers} layers; tcgen05.mma kind::f16 fp16-split x3 from two issuer warps, TMEM "
-                     "accumulators, activations exchanged through distributed shared memory, weights via cp.async.bulk ring; "
+                     "accumulators, activations exchanged through distributed shared memory (st.async with complete_tx on the consumer's "
+                     "mbarrier), weights via cp.async.bulk ring; "
                      f"{mega_smem} B shared memory per CTA), {bn.value} launch per UNet forward")
             note = ("achieved = algorithmic (useful) 2*MAC FLOPs of one forward / CUDA-event time of the launch; the tensor pipe "
                     "issues 3x that (hi*hi + lo*hi + hi*lo). At 100 trajectories per GPU the forward is a chain of 40 dependent "

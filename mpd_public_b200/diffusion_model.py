@@ -503,7 +503,10 @@ class GaussianDiffusionModel(nn.Module):
                 return None
         graph, static_hc, x_out, chain = entry
         for r in rows:
-            static_hc[r].copy_(hard_conds[r].to(device=device, dtype=torch.float32).expand_as(static_hc[r]))
+            v = hard_conds[r]
+            if v.device != device or v.dtype != torch.float32:
+                v = v.to(device=device, dtype=torch.float32)
+            static_hc[r].copy_(v)  # broadcasts [D] / [1, D] / [B, D]
         graph.replay()
         if return_chain:
             return x_out.clone(), chain.transpose(0, 1).clone()
@@ -582,7 +585,9 @@ class GaussianDiffusionModel(nn.Module):
         hard_conds = copy(hard_conds)
         context = copy(context)
         for k, v in hard_conds.items():
-            hard_conds[k] = v.unsqueeze(0).repeat(n_samples, 1)  # einops.repeat(v, 'd -> b d', b=n_samples)
+            # einops.repeat(v, 'd -> b d', b=n_samples): the loop only reads the conditions (and copies them into its own
+            # staging), so the broadcast view stands in for the materialised copy (one launch + one allocation less per row)
+            hard_conds[k] = v.unsqueeze(0).expand(n_samples, -1)
         if context is not None:
             for k, v in context.items():
                 context[k] = v.unsqueeze(0).repeat(n_samples, 1)

@@ -29,7 +29,10 @@ class LimitsNormalizer(Normalizer):
     """maps [xmin, xmax] to [-1, 1] (reference :144-167)"""
 
     def normalize(self, x):
-        x = (x - self.mins) / (self.maxs - self.mins)
+        rng = self.__dict__.get("_range")  # maxs - mins, the same fp32 subtraction as the reference's, done once
+        if rng is None or rng.device != self.mins.device:
+            rng = self.__dict__["_range"] = self.maxs - self.mins
+        x = (x - self.mins) / rng
         x = 2 * x - 1
         return x
 
