@@ -7,15 +7,17 @@
 // through final_conv.1 and the DDPM update (fuse_final):
 //
 //   * activations never leave the cluster: the current tensor lives in every CTA's shared memory ("A buffer") in the
-//     tcgen05 no-swizzle K-major operand layout [plane hi|lo][C/8][RT rows][8 x fp16]; a layer's epilogue writes its
-//     32 output channels straight into the A buffer of every CTA that consumes them through distributed shared memory
-//     (st.shared::cluster), so the next layer's MMAs read local shared memory;
+//     tcgen05 no-swizzle K-major operand layout [plane hi|lo][C/8][RT rows][8 x fp16] (the lo plane at one fixed offset,
+//     so layers of one length share their zero halo rows and the buffer is cleared only where the length changes); a
+//     layer's epilogue writes its 32 output channels straight into the A buffer of every CTA that consumes them through
+//     distributed shared memory (st.async), so the next layer's MMAs read local shared memory;
 //   * per layer the 8 CTAs tile (row tiles of <=128 padded rows) x (32-channel output chunks): 8x1 at L=64, 3x2 at
 //     L=32, 2x4 at L=16, 1x8 at L=8; the (sample -> row tile) map changes at the stride-2 layers and is applied by the
 //     writer;
 //   * weights stream from L2 through a 3-stage cp.async.bulk ring driven by a dedicated producer warp that runs ahead
 //     across layer boundaries (weights do not depend on activations), so a layer's first chunk is already resident
-//     when its inputs land; skip connections go through global memory (written once, read once, L2-resident);
+//     when its inputs land; the 1x1 residual conv of a block rides along with conv0's chunks (sixth tap of a stage);
+//     skip connections go through global memory (written once, read once, L2-resident);
 //   * TMEM, mbarriers and the layer program (a __grid_constant__ table) are set up once per forward;
 //   * layer-to-layer synchronisation is two mbarriers per CTA. a_free (cluster scope): every CTA's MMAs of this layer have
 //     retired -> its A buffer may be overwritten; one arrival per CTA per layer, sent by an issuer warp (off the epilogue's
