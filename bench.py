@@ -57,7 +57,7 @@ def workload_config(name, n_gpus):
 class ClockSampler(threading.Thread):
     """Samples SM clock and throttle reasons through NVML while the timed region runs."""
 
-    def __init__(self, index, period=0.1):
+    def __init__(self, index, period=0.025):
         super().__init__(daemon=True)
         self.index, self.period = index, period
         self.samples, self.reasons, self.max_mhz, self.power = [], set(), None, []
