@@ -12,7 +12,7 @@ Pinning status
   `unet_forward` (reference temporal_unet.py:118-171, layers.py:229-355), `make_schedule`
   (diffusion_model_base.py:66-104, helpers.py:40-46), `p_mean_variance` (:143-155),
   `ddpm_step` (sample_functions.py:18-62), `guide_gradient_steps` (:65-83), `p_sample_loop`
-  (diffusion_model_base.py:158-182), `guide_manager_grad` (guides.py:173-236: per-cost autograd,
+  (diffusion_model_base.py:158-182), `ddim_sample` (:184-259), `guide_manager_grad` (guides.py:173-236: per-cost autograd,
   clip-by-norm with +1e-6, endpoint zeroing, weighting, negation), `limits_unnormalize`
   (normalization.py:156-167, including the batch-global clip branch).
 * **Parity unpinned** (sources absent from /root/reference: `mp_baselines@8a50c3c`,
@@ -511,6 +511,56 @@ class OracleDiffusion:
             t = torch.full((shape[0],), i, dtype=torch.long)
             ns = 1.0 if noise_std_fn is None else float(noise_std_fn(t[0]))
             x = self.ddpm_step(x, hard_conds, t, draw(k + 1), guide, n_guide_steps, scale_grad_by_std, t_start_guide, ns)
+            x = apply_hard_conditioning(x, hard_conds)
+            if return_chain:
+                chain.append(x)
+        if return_chain:
+            return x, torch.stack(chain, dim=1)
+        return x
+
+
+    def ddim_sample(self, shape, hard_conds, noise=None, generator=None, return_chain=False, guide=None,
+                    t_start_guide=float("inf"), n_guide_steps=1, **sample_kwargs):
+        """`ddim_sample` (diffusion_model_base.py:184-259): T // 5 steps on a linspace grid of timesteps, eta = 0 (so sigma
+        = 0 and the per-step draw is consumed but multiplied away), no clamp of x_start, guide steps before the noise.
+        As in the reference, `n_guide_steps` is a named argument that is NOT forwarded: `guide_gradient_steps` receives
+        only `**sample_kwargs` (:240-245) and so runs its default single step unless the caller passes it there.
+        `noise`: [T//5 + 1, B, H, D] injected (row 0 = initial x); else drawn in reference order."""
+        b = self.buf
+        total, sampling, eta = self.n_diffusion_steps, self.n_diffusion_steps // 5, 0.0
+        times = torch.linspace(0, total - 1, steps=sampling + 1)
+        times = torch.cat((torch.tensor([-1.0]), times))
+        times = list(reversed(times.int().tolist()))
+        draw = (lambda k: noise[k].to(self.dtype).clone()) if noise is not None else \
+               (lambda k: torch.randn(shape, generator=generator).to(self.dtype))
+        x = apply_hard_conditioning(draw(0), hard_conds)
+        chain = [x] if return_chain else None
+        for k, (time, time_next) in enumerate(zip(times[:-1], times[1:])):
+            t = torch.full((shape[0],), time, dtype=torch.long)
+            model_out = self.model(x, t)
+            # predict_start_from_noise (:121-132) / predict_noise_from_start: with epsilon prediction the model output IS the noise
+            if self.predict_epsilon:
+                x_start = (_extract(b["sqrt_recip_alphas_cumprod"], t, x.ndim) * x
+                           - _extract(b["sqrt_recipm1_alphas_cumprod"], t, x.ndim) * model_out)
+                pred_noise = model_out
+            else:
+                x_start = model_out
+                pred_noise = ((_extract(b["sqrt_recip_alphas_cumprod"], t, x.ndim) * x - model_out)
+                              / _extract(b["sqrt_recipm1_alphas_cumprod"], t, x.ndim))
+            if time_next < 0:
+                x = apply_hard_conditioning(x_start, hard_conds)
+                if return_chain:
+                    chain.append(x)
+                break
+            t_next = torch.full((shape[0],), time_next, dtype=torch.long)
+            alpha = _extract(b["alphas_cumprod"], t, x.ndim)
+            alpha_next = _extract(b["alphas_cumprod"], t_next, x.ndim)
+            sigma = eta * ((1 - alpha / alpha_next) * (1 - alpha_next) / (1 - alpha)).sqrt()
+            c = (1 - alpha_next - sigma ** 2).sqrt()
+            x = x_start * alpha_next.sqrt() + c * pred_noise
+            if guide is not None and time_next < t_start_guide:
+                x = self.guide_gradient_steps(x, hard_conds, guide, **sample_kwargs)
+            x = x + sigma * draw(k + 1)
             x = apply_hard_conditioning(x, hard_conds)
             if return_chain:
                 chain.append(x)

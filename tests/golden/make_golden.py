@@ -109,6 +109,28 @@ def gen_guide_and_steps():
         save(f"guided_{case}", **out)
 
 
+def gen_ddim():
+    """`ddim_sample` of the reference (diffusion_model_base.py:184-259) through `conditional_sample(ddim=True)`: T // 5 steps,
+    RNG = global torch generator (randn(shape), then one randn_like per step). Separate files so that adding them leaves the
+    other fixtures untouched."""
+    ref = ref_shim.load()
+    for case, (model_id, ucase, cell, wc, ws, batch) in C.GUIDE_CASES.items():
+        prob = C.guide_problem(case)
+        spec = O.make_guide_spec(prob, wc, ws)
+        guide = ref_shim.build_reference_guide(spec)
+        model = ref_model(ucase)
+        hard = O.hard_conditions(prob)
+        hc = {k: v[None].repeat(batch, 1) for k, v in hard.items()}
+        out = {}
+        for gtag, g in (("noguide", None), ("guide", guide)):
+            torch.manual_seed(78)
+            x, chain = model.conditional_sample(hc, horizon=prob.n_support_points, batch_size=batch, ddim=True,
+                                                return_chain=True, guide=g, n_guide_steps=C.N_GUIDE_STEPS,
+                                                t_start_guide=C.T_START_GUIDE)
+            out[f"chain_{gtag}"] = chain.numpy()
+        save(f"ddim_{case}", **out)
+
+
 def gen_state_dict_keys():
     import json
     out = {}
@@ -121,8 +143,12 @@ def gen_state_dict_keys():
 
 if __name__ == "__main__":
     assert ref_shim.available(), "reference tree not present"
+    if sys.argv[1:] == ["ddim"]:  # add the DDIM fixtures only (the others are left as committed)
+        gen_ddim()
+        sys.exit(0)
     gen_state_dict_keys()
     gen_schedule()
     gen_unet()
     gen_normalizer()
     gen_guide_and_steps()
+    gen_ddim()
