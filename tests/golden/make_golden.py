@@ -131,6 +131,34 @@ def gen_ddim():
         save(f"ddim_{case}", **out)
 
 
+def gen_scale_grad():
+    """`scale_grad_by_std=True` (sample_functions.py:45-50, :77-78): the guide gradient multiplied by the posterior variance.
+    One guided teacher-forced step per case through the reference's `ddpm_sample_fn`, and `guide_gradient_steps` with an
+    explicit per-sample `model_var`. Separate files: the other fixtures stay as committed."""
+    ref = ref_shim.load()
+    for case, (model_id, ucase, cell, wc, ws, batch) in C.GUIDE_CASES.items():
+        prob = C.guide_problem(case)
+        spec = O.make_guide_spec(prob, wc, ws)
+        guide = ref_shim.build_reference_guide(spec)
+        model = ref_model(ucase)
+        hard = O.hard_conditions(prob)
+        hc = {k: v[None].repeat(batch, 1) for k, v in hard.items()}
+        out = {}
+        x = torch.as_tensor(C.guide_input(case))
+        var = torch.linspace(0.2, 1.7, batch).reshape(batch, 1, 1)
+        out["guide_steps2_var"] = ref.guide_gradient_steps(x.clone(), hard_conds=hc, guide=guide, n_guide_steps=2,
+                                                           scale_grad_by_std=True, model_var=var).numpy()
+        for i in (3, 0):
+            x = torch.as_tensor(C.step_input(case, i))
+            t = torch.full((batch,), i, dtype=torch.long)
+            torch.manual_seed(1000 + i)
+            xn, _ = ref.ddpm_sample_fn(model, x.clone(), hc, None, t, guide=guide, n_guide_steps=C.N_GUIDE_STEPS,
+                                       scale_grad_by_std=True, t_start_guide=C.T_START_GUIDE,
+                                       noise_std_extra_schedule_fn=lambda _t: C.NOISE_STD)
+            out[f"step_scaled_{i}"] = xn.numpy()
+        save(f"scale_grad_{case}", **out)
+
+
 def gen_state_dict_keys():
     import json
     out = {}
@@ -146,9 +174,13 @@ if __name__ == "__main__":
     if sys.argv[1:] == ["ddim"]:  # add the DDIM fixtures only (the others are left as committed)
         gen_ddim()
         sys.exit(0)
+    if sys.argv[1:] == ["scale_grad"]:
+        gen_scale_grad()
+        sys.exit(0)
     gen_state_dict_keys()
     gen_schedule()
     gen_unet()
     gen_normalizer()
     gen_guide_and_steps()
     gen_ddim()
+    gen_scale_grad()

@@ -119,3 +119,27 @@ def test_ddim_sample(case):
             assert max(errs) < 2e-3, (gtag, errs)
             for k, v in hc.items():
                 assert np.array_equal(chain[:, -1, k], v.numpy())
+
+
+@pytest.mark.parametrize("case", list(C.GUIDE_CASES))
+def test_scale_grad_by_std(case):
+    """`scale_grad_by_std=True` (sample_functions.py:45-50, :77-78) against the reference's own `guide_gradient_steps` and
+    `ddpm_sample_fn` (tests/golden/make_golden.py gen_scale_grad)."""
+    model_id, ucase, cell, wc, ws, batch = C.GUIDE_CASES[case]
+    g = C.load(f"scale_grad_{case}")
+    prob = C.guide_problem(case)
+    spec = O.make_guide_spec(prob, wc, ws)
+    guide = lambda x: O.guide_manager_grad(spec, x)
+    hc = {k: v[None].repeat(batch, 1) for k, v in O.hard_conditions(prob).items()}
+    m = oracle_model(ucase)
+    x = torch.as_tensor(C.guide_input(case))
+    var = torch.linspace(0.2, 1.7, batch).reshape(batch, 1, 1)
+    xs = m.guide_gradient_steps(x.clone(), hc, guide, 2, True, var)
+    assert rel(xs.numpy(), g["guide_steps2_var"]) < 1e-6
+    with torch.no_grad():
+        for i in (3, 0):
+            x = torch.as_tensor(C.step_input(case, i))
+            t = torch.full((batch,), i, dtype=torch.long)
+            xn = m.ddpm_step(x.clone(), hc, t, C.step_noise(x.shape, i), guide, C.N_GUIDE_STEPS, True, C.T_START_GUIDE,
+                             C.NOISE_STD)
+            assert rel(xn.numpy(), g[f"step_scaled_{i}"]) < 2e-5, i
