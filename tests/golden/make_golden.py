@@ -159,6 +159,29 @@ def gen_scale_grad():
         save(f"scale_grad_{case}", **out)
 
 
+def gen_predict_x0():
+    """`predict_epsilon=False` (diffusion_model_base.py:121-155): the model output is x0 itself. `p_mean_variance` at a few
+    steps and one unguided `ddpm_sample_fn` step per case."""
+    ref = ref_shim.load()
+    out = {}
+    for case, (model_id, ucase, cell, wc, ws, batch) in C.GUIDE_CASES.items():
+        d, h, opt, seed = C.UNET_CASES[ucase]
+        model = ref_shim.build_reference_model(C.unet_weights(ucase), d, h, 32, S.UNET_DIM_MULTS[opt], C.T_DIFF,
+                                               predict_epsilon=False)
+        prob = C.guide_problem(case)
+        hc = {k: v[None].repeat(batch, 1) for k, v in O.hard_conditions(prob).items()}
+        for i in (24, 12, 3, 0):
+            x = torch.as_tensor(C.step_input(case, i))
+            t = torch.full((batch,), i, dtype=torch.long)
+            with torch.no_grad():
+                mean, _, _ = model.p_mean_variance(x=x.clone(), hard_conds=hc, context=None, t=t)
+            out[f"{case}.mean_{i}"] = mean.numpy()
+            torch.manual_seed(1000 + i)
+            xn, _ = ref.ddpm_sample_fn(model, x.clone(), hc, None, t)
+            out[f"{case}.step_{i}"] = xn.numpy()
+    save("predict_x0", **out)
+
+
 def gen_state_dict_keys():
     import json
     out = {}
@@ -177,6 +200,9 @@ if __name__ == "__main__":
     if sys.argv[1:] == ["scale_grad"]:
         gen_scale_grad()
         sys.exit(0)
+    if sys.argv[1:] == ["predict_x0"]:
+        gen_predict_x0()
+        sys.exit(0)
     gen_state_dict_keys()
     gen_schedule()
     gen_unet()
@@ -184,3 +210,4 @@ if __name__ == "__main__":
     gen_guide_and_steps()
     gen_ddim()
     gen_scale_grad()
+    gen_predict_x0()
