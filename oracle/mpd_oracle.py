@@ -17,8 +17,10 @@ Pinning status
   (normalization.py:156-167, including the batch-global clip branch).
 * **Parity unpinned** (sources absent from /root/reference: `mp_baselines@8a50c3c`,
   `torch_robotics@d704c78`, `storm@54543cf`, see .SUBMODULES.json): `interpolate_points`,
-  `panda_sphere_centers`, `GridSDF`, `collision_cost_*`, `gp_cost`, `const_vel_trajectory`; `guide_manager_pos_grad`
-  restates the position-only manager's own lines (guides.py:60-118) on top of them. These follow the frozen spec of
+  `panda_sphere_centers`, `GridSDF`, `collision_cost_*`, `gp_cost`, `const_vel_trajectory`. `guide_manager_pos_grad`
+  (the position-only manager's own lines, guides.py:60-118) IS pinned, with the GP prior as its single cost: the reference
+  manager differentiates every cost once without `retain_graph` / `allow_unused`, so it cannot run a composite of several
+  costs itself; `ddim_sample`, `scale_grad_by_std` and `predict_epsilon=False` are pinned too. These follow the frozen spec of
   SURVEY.md Appendix C/E; each choice is a named switch below. The reference holds no tests or
   golden vectors for any of this path.
 """

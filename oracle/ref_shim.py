@@ -144,3 +144,40 @@ def build_reference_guide(guide_spec):
         clip_grad=guide_spec.clip_grad, max_grad_norm=guide_spec.max_grad_norm,
         interpolate_trajectories_for_collision=guide_spec.interpolate,
         num_interpolated_points_for_collision=guide_spec.n_interp)
+
+
+def build_reference_pos_guide(guide_spec, start_pos, goal_pos, dt, num_steps, n_samples):
+    """The reference's position-only `GuideManagerTrajectories` (guides.py:15-146) with name-only stand-ins for what is
+    absent: `MultiMPPrior.const_vel_trajectory` -> the oracle's restatement (source absent: unpinned), `robot.get_velocity`
+    -> the velocity half of the state, the cost -> RefCostStub. Every line of the manager itself (velocity trajectory,
+    separate clipping of the position / velocity gradients, end-row zeroing, weighting, velocity update) is reference code.
+    The manager calls `torch.autograd.grad(cost.sum(), [x_pos, velocity])` once per cost without `retain_graph` /
+    `allow_unused` (guides.py:88), so the reference itself runs only with ONE cost that reads both halves of the state
+    (a composite of several costs raises inside autograd): build it with a GP-only spec."""
+    load()
+    from oracle import mpd_oracle
+    gm = sys.modules["mpd.models.diffusion_models.guides"]
+    q = guide_spec.robot.q_dim
+
+    class _Prior:
+        @staticmethod
+        def const_vel_trajectory(start, goal, dt_, n, q_dim, set_initial_final_vel_to_zero=False, tensor_args=None):
+            return mpd_oracle.const_vel_trajectory(start, goal, dt_, n, q_dim, set_initial_final_vel_to_zero)
+
+    class _Robot:
+        q_dim = q
+
+        def __init__(self):
+            self.dt = dt
+
+        def get_velocity(self, x):
+            return x[..., q:]
+
+    gm.MultiMPPrior = _Prior
+    return gm.GuideManagerTrajectories(
+        RefDatasetStub(guide_spec.mins[:q], guide_spec.maxs[:q]), RefCostStub(guide_spec), clip_grad=guide_spec.clip_grad,
+        max_grad_norm=guide_spec.max_grad_norm, interpolate_trajectories_for_collision=guide_spec.interpolate,
+        num_interpolated_points_for_collision=guide_spec.n_interp, start_state_pos=torch.as_tensor(start_pos),
+        goal_state_pos=torch.as_tensor(goal_pos), num_steps=num_steps, robot=_Robot(), n_samples=n_samples,
+        tensor_args=dict(device="cpu", dtype=torch.float32))
+

@@ -78,6 +78,21 @@ def guide_input(case, seed=21, out_of_range=False):
     return x.astype(np.float32)
 
 
+def pos_guide_input(case, seed=41):
+    """Normalised POSITION-only trajectories near the straight start->goal line (GuideManagerTrajectories, guides.py:15-146);
+    one entry out of range so that the normaliser's batch-global clip branch is taken."""
+    model_id, ucase, cell, wc, ws, batch = GUIDE_CASES[case]
+    prob = guide_problem(case)
+    q, h = prob.robot.q_dim, prob.n_support_points
+    rng = np.random.default_rng([seed, q, h])
+    lam = np.linspace(0, 1, h)[None, :, None]
+    x = (1 - lam) * prob.start[None, None, :] + lam * prob.goal[None, None, :]
+    x = 2 * (x - prob.mins[:q]) / (prob.maxs[:q] - prob.mins[:q]) - 1
+    x = x + 0.12 * rng.standard_normal((batch, h, q))
+    x[1, 9, 0] = 1.2
+    return x.astype(np.float32)
+
+
 def step_input(case, i, seed=31):
     """x_t for the teacher-forced step at loop index i (scaled roughly like the marginal at t)."""
     model_id, ucase, cell, wc, ws, batch = GUIDE_CASES[case]

@@ -8,6 +8,7 @@ is the oracle's restatement bound into the reference guide manager ("parity unpi
 """
 from __future__ import annotations
 
+import dataclasses
 import os
 import sys
 
@@ -182,6 +183,26 @@ def gen_predict_x0():
     save("predict_x0", **out)
 
 
+def gen_pos_guide():
+    """The position-only `GuideManagerTrajectories` (guides.py:15-146): gradient and velocity trajectory after each of three
+    consecutive calls of the reference manager (x advanced by the returned gradient, as `guide_gradient_steps` does)."""
+    for case, (model_id, ucase, cell, wc, ws, batch) in C.GUIDE_CASES.items():
+        prob = C.guide_problem(case)
+        # GP prior only: the reference manager differentiates each cost once without retain_graph / allow_unused, so it runs
+        # with a single cost that reads positions and velocities (see ref_shim.build_reference_pos_guide)
+        spec = dataclasses.replace(O.make_guide_spec(prob, wc, ws), grid_fields=[], border_limits=None)
+        h = prob.n_support_points
+        guide = ref_shim.build_reference_pos_guide(spec, prob.start, prob.goal, prob.dt, h - 1, batch)
+        out = {"velocity_init": guide.velocity.detach().numpy()}
+        x = torch.as_tensor(C.pos_guide_input(case))
+        for call in range(3):
+            g = guide(x)
+            out[f"grad_{call}"] = g.detach().numpy()
+            out[f"velocity_{call}"] = guide.velocity.detach().numpy()
+            x = x + g.detach()
+        save(f"pos_guide_{case}", **out)
+
+
 def gen_state_dict_keys():
     import json
     out = {}
@@ -200,6 +221,9 @@ if __name__ == "__main__":
     if sys.argv[1:] == ["scale_grad"]:
         gen_scale_grad()
         sys.exit(0)
+    if sys.argv[1:] == ["pos_guide"]:
+        gen_pos_guide()
+        sys.exit(0)
     if sys.argv[1:] == ["predict_x0"]:
         gen_predict_x0()
         sys.exit(0)
@@ -211,3 +235,4 @@ if __name__ == "__main__":
     gen_ddim()
     gen_scale_grad()
     gen_predict_x0()
+    gen_pos_guide()

@@ -168,3 +168,28 @@ def test_predict_x0_mode(case):
             noise = torch.randn_like(torch.empty_strided((b_, h_, d_), (h_ * d_, 1, h_)))
             xn = m.ddpm_step(x.clone(), hc, t, noise)
             assert rel(xn.numpy(), g[f"{case}.step_{i}"]) < 2e-5, i
+
+
+@pytest.mark.parametrize("case", list(C.GUIDE_CASES))
+def test_position_only_guide_manager(case):
+    """`guide_manager_pos_grad` against the reference's own `GuideManagerTrajectories` (guides.py:15-146) over
+    three consecutive calls — gradient and velocity trajectory after each (gen_pos_guide). The reference manager runs with
+    a single cost only (one `autograd.grad` per cost without retain_graph), so the pin uses the GP prior alone: unnormalise,
+    state assembly, gradients w.r.t. positions and velocities, separate clipping, end-row zeroing, weighting, velocity update,
+    negation are all reference lines; `const_vel_trajectory` under it is the restatement (source absent)."""
+    import dataclasses
+    model_id, ucase, cell, wc, ws, batch = C.GUIDE_CASES[case]
+    g = C.load(f"pos_guide_{case}")
+    prob = C.guide_problem(case)
+    spec = dataclasses.replace(O.make_guide_spec(prob, wc, ws), grid_fields=[], border_limits=None)
+    q, h = prob.robot.q_dim, prob.n_support_points
+    vel = O.const_vel_trajectory(prob.start, prob.goal, prob.dt, h - 1, q, set_initial_final_vel_to_zero=True)[:, q:]
+    vel = vel[None].repeat(batch, 1, 1)
+    assert rel(vel.numpy(), g["velocity_init"]) < 1e-6
+    x = torch.as_tensor(C.pos_guide_input(case))
+    for call in range(3):
+        grad, vel = O.guide_manager_pos_grad(spec, x, vel)
+        assert float(np.abs(g[f"grad_{call}"]).max()) > 0
+        assert rel(grad.detach().numpy(), g[f"grad_{call}"]) < 1e-6, call
+        assert rel(vel.numpy(), g[f"velocity_{call}"]) < 1e-6, call
+        x = x + grad.detach()
