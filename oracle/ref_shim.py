@@ -2,8 +2,8 @@
 
 Works only where `/root/reference` exists (the build container); it never travels to the GPU box and
 nothing in `-m gpu` tests, `smoke()` or `bench.py` uses it. `tests/golden/make_golden.py` uses it to
-generate the committed golden vectors, and `tests/test_oracle_vs_reference.py` (skipped when the
-reference is absent) re-checks the oracle against the live reference.
+generate the committed golden vectors, and `tests/test_golden_reproducible.py` (skipped when the
+reference is absent) re-runs the generators and compares with the committed fixtures.
 
 The shim supplies *names* for modules that are missing here (matplotlib, torch_robotics,
 mp_baselines — SURVEY.md Appendix D); every number still comes from reference code. The single
