@@ -203,6 +203,17 @@ def cpu_oracle_runner(name, threads):
     return run, B
 
 
+def cpu_model_name():
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.lower().startswith("model name"):
+                    return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
 def run_reference_arm(args):
     """CPU arm: the oracle port of the reference path on all host threads; rank 0 only."""
     rank = int(os.environ.get("RANK", "0"))
@@ -220,7 +231,7 @@ def run_reference_arm(args):
     out = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
            "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * total / steps, "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
-           "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+           "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "cpu_model": cpu_model_name(),
                             "sample": f"{steps} full guided loop(s) at B={B} (same workload), PyTorch CPU eager, "
                                       f"{threads} threads; requested steps capped at 10"},
            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -464,6 +475,7 @@ def main():
                 times.append(run())
             t = sum(times)
             result["cpu_baseline"] = {"value": Bc * len(times) / t, "unit": UNIT, "cores": threads, "kind": "port",
+                                      "cpu_model": cpu_model_name(),
                                       "sample": f"{len(times)} full guided loops at B={Bc} (the same workload) after one "
                                                 f"warm-up loop, oracle port of the reference path, PyTorch CPU eager fp32, "
                                                 f"{threads} threads, {t:.2f} s"}
