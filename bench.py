@@ -468,17 +468,20 @@ def main():
                   "cuda_graph": bool(model.use_cuda_graph), "tensor_cores": model.tensor_cores}
         if n_gpus == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
-            run, Bc = cpu_oracle_runner(args.workload, threads)
-            run()  # warm-up (thread pool, allocator)
-            times = []
-            while sum(times) < 10.0 and len(times) < 12:  # bounded sample: about 10 s of CPU work
-                times.append(run())
-            t = sum(times)
-            result["cpu_baseline"] = {"value": Bc * len(times) / t, "unit": UNIT, "cores": threads, "kind": "port",
-                                      "cpu_model": cpu_model_name(),
-                                      "sample": f"{len(times)} full guided loops at B={Bc} (the same workload) after one "
-                                                f"warm-up loop, oracle port of the reference path, PyTorch CPU eager fp32, "
-                                                f"{threads} threads, {t:.2f} s"}
+            try:
+                run, Bc = cpu_oracle_runner(args.workload, threads)
+                run()  # warm-up (thread pool, allocator)
+                times = []
+                while sum(times) < 10.0 and len(times) < 12:  # bounded sample: about 10 s of CPU work
+                    times.append(run())
+                t = sum(times)
+                result["cpu_baseline"] = {"value": Bc * len(times) / t, "unit": UNIT, "cores": threads, "kind": "port",
+                                          "cpu_model": cpu_model_name(),
+                                          "sample": f"{len(times)} full guided loops at B={Bc} (the same workload) after one "
+                                                    f"warm-up loop, oracle port of the reference path, PyTorch CPU eager fp32, "
+                                                    f"{threads} threads, {t:.2f} s"}
+            except Exception as exc:  # the GPU line is still worth printing if the CPU leg fails on this host
+                result["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": threads, "kind": "port", "error": repr(exc)}
         emit(result)
     if world > 1:
         dist.barrier()
