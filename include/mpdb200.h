@@ -46,7 +46,9 @@ typedef struct {
 
 /* What CostComposite([CostCollision(field)..., CostGPTrajectory]) and the guide manager hold
  * (inference.py:195-236, guides.py:149-171). Arithmetic of the absent cost/robot/field classes follows
- * SURVEY.md Appendix C/E. */
+ * SURVEY.md Appendix C/E. One CostCollision per field of task.get_collision_fields() (inference.py:193-204): grid-backed
+ * object fields (each with its own lattice), the workspace-boundary box, the robot's self-collision field; every one
+ * carries its own cutoff margin, sigma_coll and gradient weight. */
 typedef struct {
     int32_t robot_kind; /* 0 = point mass (FK identity), 1 = Panda 7-DoF chain */
     int32_t q_dim;
@@ -59,22 +61,30 @@ typedef struct {
     float maxs[MPDB_MAX_STATE_DIM];
     int32_t n_grid_fields;
     const float* grid_texels[MPDB_MAX_GRID_FIELDS]; /* device; [cells][1+ws_dim] = {sdf, grad} */
-    int32_t grid_shape[3];
-    float grid_lo[3];
-    float grid_cell;
+    int32_t grid_shape[MPDB_MAX_GRID_FIELDS][3];
+    float grid_lo[MPDB_MAX_GRID_FIELDS][3];
+    float grid_cell[MPDB_MAX_GRID_FIELDS];
+    float margin_grid[MPDB_MAX_GRID_FIELDS];     /* cutoff margin of the field's CostCollision */
+    float sigma_grid[MPDB_MAX_GRID_FIELDS];      /* sigma_coll: cost = sum hinge / sigma^2 */
+    float weight_grid[MPDB_MAX_GRID_FIELDS];
     int32_t has_border; /* workspace-boundary field */
     float border_lo[3];
     float border_hi[3];
-    float cutoff_margin;
+    float margin_border, sigma_border, weight_border;
+    /* robot self-collision field: cost = sum over interpolated rows and listed sphere pairs (a, b) of
+     * relu(margin - (|c_a - c_b| - r_a - r_b)) / sigma^2; bit b of self_pairs[a] lists the pair (a, b), symmetric */
+    int32_t has_self;
+    uint32_t self_pairs[MPDB_MAX_SPHERES];
+    float margin_self, sigma_self, weight_self;
     float dt;
     float sigma_gp;
-    float weight_grid[MPDB_MAX_GRID_FIELDS];
-    float weight_border;
     float weight_gp;
     int32_t use_gp;
     int32_t clip_grad;
     float max_grad_norm;
     int32_t n_interp; /* num_interpolated_points_for_collision (guides.py:153); == horizon when off */
+    int32_t vel_from_fd; /* position-only manager with use_velocity_from_finite_difference (guides.py:77-79): the velocity
+                          * half of the state is the central difference of the positions (zero at both ends) */
 } mpdb_guide_config;
 
 /* p_sample_loop(..., sample_fn=ddpm_sample_fn, n_diffusion_steps_without_noise, **sample_kwargs)
@@ -89,7 +99,28 @@ typedef struct {
     int32_t hard_cond_rows[MPDB_MAX_HARD_CONDS];
     const float* hard_cond_vals; /* device [n_hard_conds][B][D] */
     int32_t use_cuda_graph;
+    int32_t horizon;   /* H and D of the noise / x_out / chain tensors: must equal the engine's (checked; a mismatch would */
+    int32_t state_dim; /* read and write past the caller's buffers) */
 } mpdb_loop_params;
+
+/* ddim_sample(shape, hard_conds, t_start_guide, guide, **sample_kwargs) — diffusion_model_base.py:184-259 (eta = 0).
+ * The host computes the time pairs and the two per-step coefficients with the reference's own torch expressions
+ * (:203-209, :232-236) so that they are bit-identical; the device runs, per pair, UNet -> x_start / pred_noise ->
+ * x_start * sqrt(alpha_next) + c * pred_noise [-> guide_gradient_steps when time_next < t_start_guide] -> hard conditions. */
+typedef struct {
+    int32_t n_steps;              /* number of (time, time_next) pairs */
+    const int32_t* times;         /* host [n_steps] */
+    const int32_t* times_next;    /* host [n_steps]; -1 ends the loop with x = x_start (:223-230) */
+    const float* sqrt_alpha_next; /* host [n_steps]: alpha_next.sqrt() */
+    const float* coef_noise;      /* host [n_steps]: (1 - alpha_next - sigma ** 2).sqrt() */
+    int32_t t_start_guide;        /* INT32_MAX for +inf */
+    int32_t n_guide_steps;        /* what guide_gradient_steps receives through **sample_kwargs (its default is 1) */
+    int32_t n_hard_conds;
+    int32_t hard_cond_rows[MPDB_MAX_HARD_CONDS];
+    const float* hard_cond_vals;  /* device [n_hard_conds][B][D] */
+    int32_t horizon;
+    int32_t state_dim;
+} mpdb_ddim_params;
 
 const char* mpdb_last_error(void);
 int mpdb_version(void);
@@ -110,8 +141,11 @@ int mpdb_engine_set_schedule(mpdb_engine* e, const float* sqrt_recip_alphas_cump
  * force tensor cores everywhere; "tc_amp_limit" (default: no limit — the split matches the fp32 path even at t = T-1); "mega" = 1 (default: the UNet runs as ONE launch of the whole-forward cluster
  * kernel, unet_mega.cu, whenever the batch fits one wave of 8-CTA clusters) | 0 per-layer kernels | 2 cluster kernel for
  * any batch; "fuse_final" = 1 (default: final_conv.1 + DDPM update in the cluster kernel's last epilogue inside the loop);
- * "fuse_guide" = 0 (default; 1: the n_guide_steps evaluations of a loop step in one launch with a grid barrier for the clip
- * flag when the batch is co-resident — bit-identical, measured neutral at 100 trajectories);
+ * "fuse_guide" = 1 (default: the n_guide_steps evaluations of a loop step in one launch when the batch is co-resident — the
+ * trajectory stays in shared memory, the batch-global clip flag is resolved per CTA, bit-identical to one launch per
+ * evaluation; 0: one launch per evaluation); "prec1_amp_limit" (default 0.11; 0 disables): loop steps whose eps-to-mean
+ * amplification posterior_mean_coef1[t] * sqrt(1/abar_t - 1) is at most this issue one fp16 product per MMA step instead of
+ * the three of the 22-bit split ("tc_mode" = 2 always uses the split);
  * "fuse_rtb" = 1 (default: per-layer path runs residual blocks with C_out <= 128 as one cluster-fused launch);
  * "alias_buffers" = 1 (default) shares activation storage between layers with disjoint lifetimes, 0 keeps one buffer
  * per layer (needed by mpdb_engine_read_buffer; disables the cluster kernel); "timeline" / "mega_timeline" = 1 enable the
@@ -138,6 +172,10 @@ int mpdb_add_noise(mpdb_engine* e, float* x, const int64_t* t, const float* nois
  * chain strides are in floats (so [B,S,H,D] and [S,B,H,D] are both expressible). */
 int mpdb_sample_loop(mpdb_engine* e, mpdb_guide* g, const mpdb_loop_params* p, const float* noise, float* x_out,
                      float* chain_out, int64_t chain_step_stride, int64_t chain_batch_stride, int32_t B, void* stream);
+/* the DDIM loop, fused: x_init [B][H][D] (= randn with hard conditions not yet applied), x_out [B][H][D]; chain_out (may be
+ * NULL) receives n_steps + 1 entries (x_T with hard conditions, then every step), strides in floats as above. */
+int mpdb_ddim_loop(mpdb_engine* e, mpdb_guide* g, const mpdb_ddim_params* p, const float* x_init, float* x_out,
+                   float* chain_out, int64_t chain_step_stride, int64_t chain_batch_stride, int32_t B, void* stream);
 /* counter bumped whenever the engine reallocates device buffers, reloads parameters or changes an option: a caller that
  * captured mpdb_sample_loop (use_cuda_graph = 0) into its own CUDA graph must re-capture when it changes */
 int64_t mpdb_engine_generation(mpdb_engine* e);
@@ -185,12 +223,37 @@ int mpdb_guide_grad(mpdb_guide* g, const float* x, float* grad, int32_t B, int32
 /* GuideManagerTrajectories.forward (position-only state, guides.py:60-118): x_pos [B,H,q] normalised positions,
  * velocity [B,H,q] the manager's unnormalised velocity trajectory — read as the velocity half of the state and updated in
  * place (velocity -= sum_c w_c * clip(d cost_c / d velocity)); grad [B,H,q] = -sum_c w_c * zero_ends(clip(d cost_c / d pos)).
- * Position and velocity gradients of a cost are clipped separately. The guide config's mins/maxs cover the q positions. */
+ * Position and velocity gradients of a cost are clipped separately. The guide config's mins/maxs cover the q positions.
+ * A guide configured with vel_from_fd (use_velocity_from_finite_difference, guides.py:77-79) takes velocity = NULL: the
+ * velocity half of the state is the central difference of the positions and only the position gradient exists. */
 int mpdb_guide_grad_pos(mpdb_guide* g, const float* x_pos, float* velocity, float* grad, int32_t B, int32_t H, void* stream);
 /* guide_gradient_steps(x, hard_conds, guide, n_guide_steps, scale_grad_by_std, model_var) in place —
  * sample_functions.py:65-83. model_var: device [B] or NULL. hard-cond arrays as in mpdb_loop_params. */
 int mpdb_guide_steps(mpdb_guide* g, float* x, int32_t n_steps, const float* model_var, int32_t n_hard_conds,
                      const int32_t* hard_cond_rows, const float* hard_cond_vals, int32_t B, int32_t H, void* stream);
+/* the diffusion_prior_then_guide post-loop (inference.py:263-282): n_steps x { x <- x + guide(x); hard conditioning }, every
+ * iterate also written to chain_out [n_steps][B][H][D] (step stride in floats; may be NULL). x is updated in place. */
+int mpdb_guide_steps_chain(mpdb_guide* g, float* x, int32_t n_steps, const float* model_var, int32_t n_hard_conds,
+                           const int32_t* hard_cond_rows, const float* hard_cond_vals, float* chain_out,
+                           int64_t chain_step_stride, int32_t B, int32_t H, void* stream);
+/* Parity instrumentation: every guide evaluation launched for `g` after this call records the discrete decisions of its
+ * collision costs into dev_buf (int32 [capacity_evals][B][n_costs][n_interp][n_spheres], cost order = grid fields, border,
+ * self): grid field -> (flat texel index << 1) | hinge active; border -> (axis << 2) | (low wall ? 2 : 0) | hinge active;
+ * self -> bit mask of the partner spheres whose hinge is active. Evaluations take consecutive slots from 0; the call
+ * fails when the capacity is exceeded. dev_buf = NULL switches recording off. Loops run without CUDA graphs while recording. */
+int mpdb_guide_record_decisions(mpdb_guide* g, int32_t* dev_buf, int64_t capacity_evals, int32_t B);
+/* evaluations recorded since the last mpdb_guide_record_decisions call */
+int64_t mpdb_guide_decisions_recorded(mpdb_guide* g);
+/* How many (trajectory, evaluation) pairs had their LimitsNormalizer clamp (normalization.py:160-162, a batch-global
+ * branch) decided by OTHER trajectories of the batch since the guide was created / last reset: the batch's flag was set while
+ * the trajectory itself had elements in (1, 1 + 1e-4] and none beyond. 0 means every result so far is independent of how
+ * the batch was composed or sharded (what the multi-GPU equivalence tests check). Synchronises the device. */
+int64_t mpdb_guide_batch_dependent_clamps(mpdb_guide* g, int32_t reset);
+/* collision costs of this guide (grid fields + border + self) */
+int mpdb_guide_num_collision_costs(mpdb_guide* g);
+/* forward kinematics of the guide's robot: q device [N][q_dim] -> sphere centres device [N][n_spheres][3] (tests: known
+ * answers of the Panda chain) */
+int mpdb_debug_fk(mpdb_guide* g, const float* q, float* centers, int32_t N, void* stream);
 /* Post-sampling evaluation (inference.py:288-326): per UNNORMALISED trajectory x [B,H,D] ->
  * stats device [B][4] = {#interpolated waypoints in collision (sdf - radius < margin in any field), smoothness
  * sum_h |v_{h+1} - v_h|, path length sum_h |p_{h+1} - p_h|, minimum clearance}. Uses the guide's robot / fields. */

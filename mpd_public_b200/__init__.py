@@ -8,7 +8,8 @@ from .temporal_unet import TemporalUnet  # noqa: F401
 from .diffusion_model import GaussianDiffusionModel, make_timesteps  # noqa: F401
 from .sample_functions import apply_hard_conditioning, extract, ddpm_sample_fn, guide_gradient_steps  # noqa: F401
 from .guides import GuideManagerTrajectoriesWithVelocity, GuideManagerTrajectories  # noqa: F401
-from .costs import CostCollision, CostGPTrajectory, CostComposite, GridSDFField, WorkspaceBoundaryField  # noqa: F401
+from .costs import (CostCollision, CostGPTrajectory, CostComposite, GridSDFField, WorkspaceBoundaryField,  # noqa: F401
+                    SelfCollisionField)
 from .normalization import LimitsNormalizer, DatasetNormalizer  # noqa: F401
 from .planning import (TrajectoryDataset, PlanningTask, Robot, compute_smoothness, compute_path_length,  # noqa: F401
                        compute_variance_waypoints)

@@ -29,11 +29,17 @@ class GuideConfig(C.Structure):
         ("robot_kind", C.c_int32), ("q_dim", C.c_int32), ("ws_dim", C.c_int32), ("n_spheres", C.c_int32),
         ("sphere_frame", C.c_int32 * MAX_SPHERES), ("sphere_offset", (C.c_float * 3) * MAX_SPHERES),
         ("sphere_radius", C.c_float * MAX_SPHERES), ("mins", C.c_float * MAX_STATE_DIM), ("maxs", C.c_float * MAX_STATE_DIM),
-        ("n_grid_fields", C.c_int32), ("grid_texels", C.c_void_p * MAX_GRID_FIELDS), ("grid_shape", C.c_int32 * 3),
-        ("grid_lo", C.c_float * 3), ("grid_cell", C.c_float), ("has_border", C.c_int32), ("border_lo", C.c_float * 3),
-        ("border_hi", C.c_float * 3), ("cutoff_margin", C.c_float), ("dt", C.c_float), ("sigma_gp", C.c_float),
-        ("weight_grid", C.c_float * MAX_GRID_FIELDS), ("weight_border", C.c_float), ("weight_gp", C.c_float),
+        ("n_grid_fields", C.c_int32), ("grid_texels", C.c_void_p * MAX_GRID_FIELDS),
+        ("grid_shape", (C.c_int32 * 3) * MAX_GRID_FIELDS), ("grid_lo", (C.c_float * 3) * MAX_GRID_FIELDS),
+        ("grid_cell", C.c_float * MAX_GRID_FIELDS), ("margin_grid", C.c_float * MAX_GRID_FIELDS),
+        ("sigma_grid", C.c_float * MAX_GRID_FIELDS), ("weight_grid", C.c_float * MAX_GRID_FIELDS),
+        ("has_border", C.c_int32), ("border_lo", C.c_float * 3), ("border_hi", C.c_float * 3),
+        ("margin_border", C.c_float), ("sigma_border", C.c_float), ("weight_border", C.c_float),
+        ("has_self", C.c_int32), ("self_pairs", C.c_uint32 * MAX_SPHERES),
+        ("margin_self", C.c_float), ("sigma_self", C.c_float), ("weight_self", C.c_float),
+        ("dt", C.c_float), ("sigma_gp", C.c_float), ("weight_gp", C.c_float),
         ("use_gp", C.c_int32), ("clip_grad", C.c_int32), ("max_grad_norm", C.c_float), ("n_interp", C.c_int32),
+        ("vel_from_fd", C.c_int32),
     ]
 
 
@@ -42,6 +48,16 @@ class LoopParams(C.Structure):
         ("n_steps_without_noise", C.c_int32), ("t_start_guide", C.c_int32), ("n_guide_steps", C.c_int32),
         ("scale_grad_by_std", C.c_int32), ("noise_std", C.POINTER(C.c_float)), ("n_hard_conds", C.c_int32),
         ("hard_cond_rows", C.c_int32 * MAX_HARD_CONDS), ("hard_cond_vals", C.c_void_p), ("use_cuda_graph", C.c_int32),
+        ("horizon", C.c_int32), ("state_dim", C.c_int32),
+    ]
+
+
+class DdimParams(C.Structure):
+    _fields_ = [
+        ("n_steps", C.c_int32), ("times", C.POINTER(C.c_int32)), ("times_next", C.POINTER(C.c_int32)),
+        ("sqrt_alpha_next", C.POINTER(C.c_float)), ("coef_noise", C.POINTER(C.c_float)), ("t_start_guide", C.c_int32),
+        ("n_guide_steps", C.c_int32), ("n_hard_conds", C.c_int32), ("hard_cond_rows", C.c_int32 * MAX_HARD_CONDS),
+        ("hard_cond_vals", C.c_void_p), ("horizon", C.c_int32), ("state_dim", C.c_int32),
     ]
 
 
@@ -67,6 +83,9 @@ SYMBOLS = {
     "mpdb_p_mean": (C.c_int, [_P, _P, _P, _P, C.c_int32, _P]),
     "mpdb_add_noise": (C.c_int, [_P, _P, _P, _P, C.c_float, C.c_int32, _P]),
     "mpdb_sample_loop": (C.c_int, [_P, _P, C.POINTER(LoopParams), _P, _P, _P, C.c_int64, C.c_int64, C.c_int32, _P]),
+    "mpdb_ddim_loop": (C.c_int, [_P, _P, C.POINTER(DdimParams), _P, _P, _P, C.c_int64, C.c_int64, C.c_int32, _P]),
+    "mpdb_guide_steps_chain": (C.c_int, [_P, _P, C.c_int32, _P, C.c_int32, C.POINTER(C.c_int32), _P, _P, C.c_int64, C.c_int32,
+                                         C.c_int32, _P]),
     "mpdb_launch_count": (C.c_int64, []),
     "mpdb_engine_num_ops": (C.c_int, [_P]),
     "mpdb_profile_forward": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_float), C.POINTER(C.c_double),
@@ -82,6 +101,11 @@ SYMBOLS = {
     "mpdb_guide_grad": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, _P]),
     "mpdb_guide_grad_pos": (C.c_int, [_P, _P, _P, _P, C.c_int32, C.c_int32, _P]),
     "mpdb_guide_steps": (C.c_int, [_P, _P, C.c_int32, _P, C.c_int32, C.POINTER(C.c_int32), _P, C.c_int32, C.c_int32, _P]),
+    "mpdb_guide_record_decisions": (C.c_int, [_P, _P, C.c_int64, C.c_int32]),
+    "mpdb_guide_decisions_recorded": (C.c_int64, [_P]),
+    "mpdb_guide_num_collision_costs": (C.c_int, [_P]),
+    "mpdb_guide_batch_dependent_clamps": (C.c_int64, [_P, C.c_int32]),
+    "mpdb_debug_fk": (C.c_int, [_P, _P, _P, C.c_int32, _P]),
     "mpdb_eval_trajectories": (C.c_int, [_P, _P, _P, C.c_float, C.c_int32, C.c_int32, _P]),
     "mpdb_sdf_grid_build": (C.c_int, [C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_float), C.c_float,
                                       C.POINTER(C.c_float), C.c_int32, C.POINTER(C.c_float), C.c_int32, _P, _P]),

@@ -29,6 +29,33 @@ extern std::atomic<long long> g_launch_count;
         }                                        \
     } while (0)
 
+// Every extern "C" entry runs on its handle's device and restores the caller's current device on return (a call on a
+// cuda:1 model must not change torch's current device behind the caller's back).
+struct DeviceGuard {
+    int prev = -1, target = -1;
+    bool ok = false;
+    explicit DeviceGuard(int dev) : target(dev) {
+        ok = cudaGetDevice(&prev) == cudaSuccess && (prev == dev || cudaSetDevice(dev) == cudaSuccess);
+    }
+    ~DeviceGuard() {
+        if (ok && prev != target) cudaSetDevice(prev);
+    }
+    DeviceGuard(const DeviceGuard&) = delete;
+    DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+#define MPDB_ENTER_DEVICE(dev)       \
+    mpdb::DeviceGuard _mpdb_dg(dev); \
+    MPDB_REQUIRE(_mpdb_dg.ok, "cudaSetDevice(" + std::to_string(dev) + ") failed")
+
+// cudaFuncSetAttribute is per DEVICE: true the first time the calling site runs on the current device (one bit per ordinal).
+inline bool first_use_on_device(unsigned long long& mask) {
+    int d = 0;
+    if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d > 63) return true;
+    if ((mask >> d) & 1ull) return false;
+    mask |= 1ull << d;
+    return true;
+}
+
 #define MPDB_LAUNCH_CHECK()                      \
     do {                                         \
         mpdb::g_launch_count.fetch_add(1);       \

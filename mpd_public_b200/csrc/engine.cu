@@ -98,9 +98,10 @@ struct mpdb_engine {
     long long generation = 0;  // bumped whenever device buffers are reallocated or an option changes: launches captured
                                // by a caller (torch CUDA graph around mpdb_sample_loop) are stale afterwards
     int use_mega = []() { const char* v = getenv("MPDB_MEGA"); return v ? atoi(v) : 1; }();
-    // the guide evaluations of a step in one launch (grid barrier for the batch-global clip flag). Measured neutral at B = 100
-    // (9.08 ms per loop either way: the barrier costs what the launch edges cost), so it is off by default; bit-identical (tested).
-    int fuse_guide = []() { const char* v = getenv("MPDB_FUSE_GUIDE"); return v ? atoi(v) : 0; }();
+    // the guide evaluations of a step in one launch: the trajectory stays in shared memory, the batch-global clip flag is
+    // resolved per CTA and only an undecidable CTA waits for the grid (guide.cu); bit-identical to one launch per evaluation
+    // (tested). Used whenever the batch is co-resident; otherwise one launch per evaluation.
+    int fuse_guide = []() { const char* v = getenv("MPDB_FUSE_GUIDE"); return v ? atoi(v) : 1; }();
     int fuse_final = []() { const char* v = getenv("MPDB_FUSE_FINAL"); return v ? atoi(v) : 1; }();  // projection + DDPM update in the cluster kernel
     bool mega_ok = false;
     std::string mega_why;      // why the configuration cannot run as one launch (falls back to per-layer kernels)
@@ -116,6 +117,13 @@ struct mpdb_engine {
     // path matches the fp32 FMA path even at t = T-1 (eps amplified 4602x: step error 3.5e-4 vs 4.4e-4 against the oracle,
     // profiles/r01c_precision_tlast.txt), so no step is excluded by default; a finite limit restores the carve-out.
     float tc_amp_limit = 3.0e38f;
+    // Per-timestep precision policy of the loop (tensor-core path): a step whose eps-to-mean amplification
+    // posterior_mean_coef1[t] * sqrt(1/abar_t - 1) (predict_epsilon) is at most this limit issues ONE fp16 product per MMA
+    // step instead of the three of the 22-bit split (unet_mega.cu / unet_tc.cu "precision 1"): an eps error of ~1e-3
+    // relative then moves the posterior mean by <= limit * 1e-3, an order of magnitude under the 1e-3 per-step bar.
+    // Exponential schedule, T = 25: 0.01 at t = 0, 0.104 at t = 15, 0.34 at t = 20, 1.24 at t = 23, 1095 at t = 24. 0 disables.
+    bool force_prec3 = false;  // set by run_unet_body for the duration of one forward
+    float prec1_amp_limit = []() { const char* v = getenv("MPDB_PREC1_AMP"); return v ? (float)atof(v) : 0.11f; }();
     long long work_floats_per_sample = 0;
     int work_batch = 0;
     long long final_w = -1, final_b = -1;
@@ -448,6 +456,15 @@ static ConvSrc make_src(mpdb_engine* e, int id0, int id1, const float* x_ext, in
     return s;
 }
 
+// 1 (one fp16 product) or 3 (22-bit split) for a forward at uniform timestep t, see prec1_amp_limit
+static int step_prec(const mpdb_engine* e, int t) {
+    const int T = e->cfg.n_diffusion_steps;
+    if (e->force_prec3 || e->tc_mode == 2 || e->prec1_amp_limit <= 0.f || !e->sched_set || t < 0 || t >= T) return 3;  // tc_mode 2 ("force") = full split everywhere
+    const float c1 = e->sched_host[2 * (size_t)T + t], srm1 = e->sched_host[1 * (size_t)T + t];
+    const float amp = e->cfg.predict_epsilon ? c1 * srm1 : c1;
+    return amp <= e->prec1_amp_limit ? 1 : 3;
+}
+
 static void fill_tc_args(mpdb_engine* e, const ConvOp& op, const long long* t_dev, int t_uniform, int B, TcConvArgs& a) {
     auto hi = [&](int id) -> unsigned short* { return e->tc_plane[id] ? e->work_tc + e->tc_off[id] : nullptr; };
     auto lo = [&](int id) -> unsigned short* { return e->tc_plane[id] ? e->work_tc + e->tc_off[id] + e->tc_plane[id] : nullptr; };
@@ -470,6 +487,7 @@ static void fill_tc_args(mpdb_engine* e, const ConvOp& op, const long long* t_de
     a.out_cm = const_cast<float*>(buf_ptr(e, op.out, e->work_batch));
     a.out_hi = hi(op.out); a.out_lo = lo(op.out);
     a.CO = op.CO; a.L = op.L_in; a.B = B; a.gs = op.gs;
+    a.prec = t_dev == nullptr ? step_prec(e, t_uniform) : 3;  // per-sample t (per-call entry points): always the full split
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -714,11 +732,13 @@ static int launch_op(mpdb_engine* e, const ConvOp& op, const float* x, const lon
 // `fin` (optional): the projection + DDPM update that follows the body. When the body runs as the cluster kernel it is
 // executed in that kernel's last epilogue and *fused is set; otherwise the caller launches final_kernel.
 static int run_unet_body(mpdb_engine* e, const float* x, const long long* t_dev, int t_uniform, int B, cudaStream_t st,
-                         bool tc, const FinalArgs* fin = nullptr, bool* fused = nullptr) {
+                         bool tc, const FinalArgs* fin = nullptr, bool* fused = nullptr, bool ddim = false) {
+    e->force_prec3 = ddim;  // DDIM steps have no clamp / posterior damping: always the full 22-bit split
     if (fused) *fused = false;
     if (tc && t_dev == nullptr && !e->timeline && mega_usable(e, B)) {
         MegaProgram P = e->mega;  // one launch: every layer up to final_conv.0 inside thread-block clusters
         P.x = x; P.t = t_uniform; P.B = B;
+        P.prec = step_prec(e, t_uniform);
         P.dbg = e->mega_dbg;
         static const int dbg_cluster = []() { const char* v = getenv("MPDB_MEGA_DBG_CLUSTER"); return v ? atoi(v) : 0; }();
         P.dbg_cluster = dbg_cluster;
@@ -790,7 +810,7 @@ extern "C" int mpdb_engine_create(const mpdb_engine_config* cfg, int device, mpd
                  "engine: horizon must be divisible by 8 * 2^(n_levels-1)");
     MPDB_REQUIRE(cfg->n_diffusion_steps >= 1, "engine: n_diffusion_steps must be >= 1");
     for (int i = 0; i < cfg->n_levels; ++i) MPDB_REQUIRE(cfg->dim_mults[i] >= 1, "engine: bad dim_mults");
-    MPDB_CHECK_CUDA(cudaSetDevice(device));
+    MPDB_ENTER_DEVICE(device);
     std::unique_ptr<mpdb_engine> e(new mpdb_engine());
     e->cfg = *cfg;
     e->device = device;
@@ -811,7 +831,7 @@ extern "C" int mpdb_engine_create(const mpdb_engine_config* cfg, int device, mpd
 
 extern "C" void mpdb_engine_destroy(mpdb_engine* e) {
     if (!e) return;
-    cudaSetDevice(e->device);
+    mpdb::DeviceGuard dg(e->device);
     cudaDeviceSynchronize();
     if (e->graph_exec) cudaGraphExecDestroy(e->graph_exec);
     cudaFree(e->raw); cudaFree(e->packed); cudaFree(e->work); cudaFree(e->sched);
@@ -827,7 +847,7 @@ extern "C" int mpdb_engine_set_param(mpdb_engine* e, const char* name, const flo
     MPDB_REQUIRE(it != e->params.end(), std::string("unexpected parameter '") + name + "' for this TemporalUnet configuration");
     MPDB_REQUIRE(it->second.numel == numel, std::string("size mismatch for parameter '") + name + "': expected " +
                                                 std::to_string(it->second.numel) + ", got " + std::to_string(numel));
-    MPDB_CHECK_CUDA(cudaSetDevice(e->device));
+    MPDB_ENTER_DEVICE(e->device);
     MPDB_CHECK_CUDA(cudaMemcpyAsync(e->raw + it->second.offset, dev_ptr, sizeof(float) * (size_t)numel,
                                     cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
     it->second.set = true;
@@ -842,8 +862,11 @@ extern "C" int mpdb_engine_set_schedule(mpdb_engine* e, const float* sr, const f
     e->sched_host.resize(7 * (size_t)T);
     const float* src[7] = {sr, srm1, c1, c2, logvar, stdv, var};
     for (int k = 0; k < 7; ++k) memcpy(e->sched_host.data() + (size_t)k * T, src[k], sizeof(float) * T);
-    MPDB_CHECK_CUDA(cudaSetDevice(e->device));
+    MPDB_ENTER_DEVICE(e->device);
     MPDB_CHECK_CUDA(cudaMemcpy(e->sched, e->sched_host.data(), sizeof(float) * 7 * (size_t)T, cudaMemcpyHostToDevice));
+    // captured loops bake schedule values (std, var, the per-step tensor-core decision) into kernel arguments
+    if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; e->graph_key.clear(); }
+    ++e->generation;
     e->sched_set = true;
     return 0;
 }
@@ -892,6 +915,10 @@ extern "C" int mpdb_engine_set_option(mpdb_engine* e, const char* name, double v
         }
     } else if (n == "tc_amp_limit") {
         e->tc_amp_limit = (float)value;
+    } else if (n == "prec1_amp_limit") {
+        MPDB_REQUIRE(value >= 0, "prec1_amp_limit must be >= 0 (0 disables the one-product steps)");
+        e->prec1_amp_limit = (float)value;
+        if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; e->graph_key.clear(); }
     } else {
         MPDB_REQUIRE(false, "unknown option '" + n + "'");
     }
@@ -901,7 +928,7 @@ extern "C" int mpdb_engine_set_option(mpdb_engine* e, const char* name, double v
 extern "C" int mpdb_engine_finalize(mpdb_engine* e, void* stream) {
     MPDB_REQUIRE(e, "mpdb_engine_finalize: null engine");
     cudaStream_t st = (cudaStream_t)stream;
-    MPDB_CHECK_CUDA(cudaSetDevice(e->device));
+    MPDB_ENTER_DEVICE(e->device);
     for (auto& kv : e->params)
         MPDB_REQUIRE(kv.second.set, std::string("missing parameter '") + kv.first + "' (load_state_dict incomplete)");
     MPDB_REQUIRE(e->sched_set, "schedule tables not set");
@@ -953,7 +980,7 @@ extern "C" int mpdb_unet_forward(mpdb_engine* e, const float* x, const int64_t* 
     MPDB_REQUIRE(e && x && t && eps && B > 0, "mpdb_unet_forward: bad argument");
     MPDB_REQUIRE(e->finalized, "engine not finalized (call mpdb_engine_finalize after loading parameters)");
     cudaStream_t st = (cudaStream_t)stream;
-    MPDB_CHECK_CUDA(cudaSetDevice(e->device));
+    MPDB_ENTER_DEVICE(e->device);
     if (ensure_workspace(e, B)) return 1;
     if (run_unet_body(e, x, (const long long*)t, 0, B, st, percall_tc(e))) return 1;
     FinalArgs f;
@@ -970,7 +997,7 @@ extern "C" int mpdb_unet_forward_uniform(mpdb_engine* e, const float* x, int32_t
     MPDB_REQUIRE(t >= 0 && t < e->cfg.n_diffusion_steps, "mpdb_unet_forward_uniform: t out of range");
     MPDB_REQUIRE(e->finalized, "engine not finalized (call mpdb_engine_finalize after loading parameters)");
     cudaStream_t st = (cudaStream_t)stream;
-    MPDB_CHECK_CUDA(cudaSetDevice(e->device));
+    MPDB_ENTER_DEVICE(e->device);
     if (ensure_workspace(e, B)) return 1;
     if (run_unet_body(e, x, nullptr, t, B, st, e->tc_mode != 0)) return 1;
     FinalArgs f;
@@ -985,7 +1012,8 @@ extern "C" int mpdb_unet_forward_uniform(mpdb_engine* e, const float* x, int32_t
 extern "C" int mpdb_engine_mega_info(mpdb_engine* e, int32_t B, int32_t* G, int32_t* n_layers, int32_t* a_bytes,
                                      int32_t* smem_bytes, char* why, int why_cap) {
     if (!e || B <= 0) return 0;
-    if (cudaSetDevice(e->device) != cudaSuccess || ensure_workspace(e, B)) return 0;
+    mpdb::DeviceGuard dg(e->device);
+    if (!dg.ok || ensure_workspace(e, B)) return 0;
     if (G) *G = e->mega.G;
     if (n_layers) *n_layers = e->mega.n_layers;
     if (a_bytes) *a_bytes = e->mega.a_bytes;
@@ -1003,7 +1031,7 @@ extern "C" int mpdb_profile_unet_body(mpdb_engine* e, const float* x, int32_t t,
     MPDB_REQUIRE(e && x && ms_out && B > 0 && reps > 0, "mpdb_profile_unet_body: bad argument");
     MPDB_REQUIRE(e->finalized, "engine not finalized");
     cudaStream_t st = (cudaStream_t)stream;
-    MPDB_CHECK_CUDA(cudaSetDevice(e->device));
+    MPDB_ENTER_DEVICE(e->device);
     if (ensure_workspace(e, B)) return 1;
     const bool tc = e->tc_mode != 0;
     cudaEvent_t ev0, ev1;
@@ -1035,7 +1063,7 @@ extern "C" int mpdb_p_mean(mpdb_engine* e, const float* x, const int64_t* t, flo
     MPDB_REQUIRE(e && x && t && mean && B > 0, "mpdb_p_mean: bad argument");
     MPDB_REQUIRE(e->finalized, "engine not finalized (call mpdb_engine_finalize after loading parameters)");
     cudaStream_t st = (cudaStream_t)stream;
-    MPDB_CHECK_CUDA(cudaSetDevice(e->device));
+    MPDB_ENTER_DEVICE(e->device);
     if (ensure_workspace(e, B)) return 1;
     if (run_unet_body(e, x, (const long long*)t, 0, B, st, percall_tc(e))) return 1;
     FinalArgs f;
@@ -1049,7 +1077,7 @@ extern "C" int mpdb_add_noise(mpdb_engine* e, float* x, const int64_t* t, const 
                               int32_t B, void* stream) {
     MPDB_REQUIRE(e && x && t && noise && B > 0, "mpdb_add_noise: bad argument");
     MPDB_REQUIRE(e->sched_set, "schedule tables not set");
-    MPDB_CHECK_CUDA(cudaSetDevice(e->device));
+    MPDB_ENTER_DEVICE(e->device);
     const int T = e->cfg.n_diffusion_steps;
     return launch_add_noise(x, (const long long*)t, e->sched + 5 * T, noise, noise_std, B,
                             e->cfg.horizon * e->cfg.state_dim, (cudaStream_t)stream);
@@ -1169,6 +1197,18 @@ static int enqueue_loop(mpdb_engine* e, mpdb_guide* g, const mpdb_loop_params* p
     return 0;
 }
 
+static int ensure_flags(mpdb_engine* e, int n_flags_needed) {
+    if (e->n_flags >= n_flags_needed) return 0;
+    if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; e->graph_key.clear(); }
+    MPDB_CHECK_CUDA(cudaDeviceSynchronize());
+    if (e->flags) cudaFree(e->flags);
+    e->flags = nullptr;
+    MPDB_CHECK_CUDA(cudaMalloc(&e->flags, sizeof(int) * (size_t)n_flags_needed));
+    e->n_flags = n_flags_needed;
+    ++e->generation;
+    return 0;
+}
+
 static int ensure_staging(float** buf, long long* have, long long need) {
     if (need <= *have) return 0;
     if (*buf) cudaFree(*buf);
@@ -1191,25 +1231,19 @@ extern "C" int mpdb_sample_loop(mpdb_engine* e, mpdb_guide* g, const mpdb_loop_p
     MPDB_REQUIRE(!g || guide_state_dim(g) == e->cfg.state_dim, "guide and model disagree on state_dim");
     MPDB_REQUIRE(!g || guide_device(g) == e->device, "guide and model live on different devices");
     cudaStream_t st = (cudaStream_t)stream;
-    MPDB_CHECK_CUDA(cudaSetDevice(e->device));
+    MPDB_ENTER_DEVICE(e->device);
     if (ensure_workspace(e, B)) return 1;
     const int T = e->cfg.n_diffusion_steps, H = e->cfg.horizon, D = e->cfg.state_dim;
     const int n_iters = T + p->n_steps_without_noise;
     const long long n = (long long)B * H * D;
 
-    {
-        const int n_flags_needed = n_iters * (p->n_guide_steps + 1) + 1 + n_iters * (p->n_guide_steps > 0 ? p->n_guide_steps : 1);
-        if (e->n_flags < n_flags_needed) {
-            if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; e->graph_key.clear(); }
-            MPDB_CHECK_CUDA(cudaDeviceSynchronize());
-            if (e->flags) cudaFree(e->flags);
-            e->flags = nullptr;
-            MPDB_CHECK_CUDA(cudaMalloc(&e->flags, sizeof(int) * (size_t)n_flags_needed));
-            e->n_flags = n_flags_needed;
-            ++e->generation;
-        }
-    }
-    if (!p->use_cuda_graph)
+    MPDB_REQUIRE(p->horizon == H && p->state_dim == D,
+                 "mpdb_sample_loop: tensors of horizon " + std::to_string(p->horizon) + " x state_dim " + std::to_string(p->state_dim) +
+                     " given to an engine built for " + std::to_string(H) + " x " + std::to_string(D));
+    MPDB_REQUIRE(!chain_out || (chain_batch_stride >= (int64_t)H * D && chain_step_stride >= (int64_t)H * D),
+                 "mpdb_sample_loop: chain strides smaller than one trajectory");
+    if (ensure_flags(e, n_iters * (p->n_guide_steps + 1) + 1 + n_iters * (p->n_guide_steps > 0 ? p->n_guide_steps : 1))) return 1;
+    if (!p->use_cuda_graph || (g && guide_recording(g)))  // recording decisions assigns buffer slots per launch: no replay
         return enqueue_loop(e, g, p, noise, p->hard_cond_vals, x_out, chain_out, chain_step_stride, chain_batch_stride,
                             B, st);
 
@@ -1227,7 +1261,7 @@ extern "C" int mpdb_sample_loop(mpdb_engine* e, mpdb_guide* g, const mpdb_loop_p
                       std::to_string(p->n_steps_without_noise) + "|" + std::to_string(p->t_start_guide) + "|" +
                       std::to_string(p->n_guide_steps) + "|" + std::to_string(p->scale_grad_by_std) + "|" +
                       std::to_string(chain_out != nullptr) + "|" + std::to_string(p->n_hard_conds) + "|tc" +
-                      std::to_string(e->tc_mode) + "/" + std::to_string(e->tc_amp_limit) + "/" + std::to_string(e->fuse_rtb) + "/" + std::to_string(e->use_mega) + "/" + std::to_string(e->fuse_final) + "/" + std::to_string(e->fuse_guide);
+                      std::to_string(e->tc_mode) + "/" + std::to_string(e->tc_amp_limit) + "/" + std::to_string(e->fuse_rtb) + "/" + std::to_string(e->use_mega) + "/" + std::to_string(e->fuse_final) + "/" + std::to_string(e->fuse_guide) + "/" + std::to_string(e->prec1_amp_limit);
     for (int k = 0; k < p->n_hard_conds; ++k) key += "," + std::to_string(p->hard_cond_rows[k]);
     for (int k = 0; k < n_iters; ++k) {
         float v = p->noise_std ? p->noise_std[k] : 1.0f;
@@ -1296,6 +1330,91 @@ extern "C" int mpdb_sample_loop(mpdb_engine* e, mpdb_guide* g, const mpdb_loop_p
     return 0;
 }
 
+// ddim_sample (diffusion_model_base.py:184-259), fused: per (time, time_next) pair one UNet forward whose last epilogue (or
+// final_kernel) applies the DDIM update, then the guide evaluations when time_next < t_start_guide. No host synchronisation.
+extern "C" int mpdb_ddim_loop(mpdb_engine* e, mpdb_guide* g, const mpdb_ddim_params* p, const float* x_init, float* x_out,
+                              float* chain_out, int64_t chain_step_stride, int64_t chain_batch_stride, int32_t B, void* stream) {
+    MPDB_REQUIRE(e && p && x_init && x_out && B > 0, "mpdb_ddim_loop: bad argument");
+    MPDB_REQUIRE(e->finalized, "engine not finalized (call mpdb_engine_finalize after loading parameters)");
+    MPDB_REQUIRE(p->n_steps >= 1 && p->times && p->times_next && p->sqrt_alpha_next && p->coef_noise, "mpdb_ddim_loop: missing step tables");
+    MPDB_REQUIRE(p->n_hard_conds >= 0 && p->n_hard_conds <= MPDB_MAX_HARD_CONDS, "too many hard conditions");
+    MPDB_REQUIRE(p->n_hard_conds == 0 || p->hard_cond_vals, "hard_cond_vals is null");
+    MPDB_REQUIRE(p->n_guide_steps >= 0, "negative step count");
+    MPDB_REQUIRE(!g || guide_state_dim(g) == e->cfg.state_dim, "guide and model disagree on state_dim");
+    MPDB_REQUIRE(!g || guide_device(g) == e->device, "guide and model live on different devices");
+    const int T = e->cfg.n_diffusion_steps, H = e->cfg.horizon, D = e->cfg.state_dim;
+    MPDB_REQUIRE(p->horizon == H && p->state_dim == D,
+                 "mpdb_ddim_loop: tensors of horizon " + std::to_string(p->horizon) + " x state_dim " + std::to_string(p->state_dim) +
+                     " given to an engine built for " + std::to_string(H) + " x " + std::to_string(D));
+    MPDB_REQUIRE(!chain_out || (chain_batch_stride >= (int64_t)H * D && chain_step_stride >= (int64_t)H * D),
+                 "mpdb_ddim_loop: chain strides smaller than one trajectory");
+    for (int k = 0; k < p->n_steps; ++k) {
+        MPDB_REQUIRE(p->times[k] >= 0 && p->times[k] < T && p->times_next[k] < T, "mpdb_ddim_loop: time index out of range");
+        MPDB_REQUIRE(p->times_next[k] >= 0 || k == p->n_steps - 1, "mpdb_ddim_loop: only the last pair may end at time_next < 0");
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    MPDB_ENTER_DEVICE(e->device);
+    if (ensure_workspace(e, B)) return 1;
+    const int ng = g ? p->n_guide_steps : 0;
+    if (ensure_flags(e, p->n_steps * (ng + 1) + 1)) return 1;
+    if (ng > 0) MPDB_CHECK_CUDA(cudaMemsetAsync(e->flags, 0, sizeof(int) * (size_t)(p->n_steps * (ng + 1) + 1), st));
+    const long long n = (long long)B * H * D;
+    float* cur = e->xbuf[0];
+    MPDB_CHECK_CUDA(cudaMemcpyAsync(cur, x_init, sizeof(float) * (size_t)n, cudaMemcpyDeviceToDevice, st));
+    if (launch_copy_hc(cur, chain_out, chain_batch_stride, p->n_hard_conds, p->hard_cond_rows, p->hard_cond_vals, B, H, D, st)) return 1;
+    for (int k = 0; k < p->n_steps; ++k) {
+        const int t = p->times[k], t_next = p->times_next[k];
+        const bool last = (k == p->n_steps - 1);
+        float* nxt = last ? x_out : e->xbuf[(k + 1) & 1];
+        float* chain_slot = chain_out ? chain_out + (long long)(k + 1) * chain_step_stride : nullptr;
+        const bool guided = ng > 0 && t_next >= 0 && (long long)t_next < (long long)p->t_start_guide;
+        // the DDIM update has no clamp and no posterior damping (eps reaches x scaled by |c - sqrt_recipm1[t] * sqrt(alpha_next)|,
+        // ~3600 at the first pair): every DDIM forward uses the full 22-bit split (run_unet_body(..., ddim = true))
+        const bool tc = e->tc_mode == 2 || (e->tc_mode == 1 && e->sched_host[1 * (size_t)T + t] <= e->tc_amp_limit);
+        FinalArgs f;
+        fill_final(e, f, cur, nullptr, t, B);
+        f.n_hc = p->n_hard_conds;
+        for (int q = 0; q < p->n_hard_conds; ++q) f.hc_rows[q] = p->hard_cond_rows[q];
+        f.hc_vals = p->hard_cond_vals;
+        f.ddim_san = p->sqrt_alpha_next[k];
+        f.ddim_c = p->coef_noise[k];
+        f.ddim_last = t_next < 0 ? 1 : 0;
+        f.out = nxt;
+        int* fl = e->flags + (long long)k * (ng + 1);
+        if (guided) {
+            f.mode = 4;
+            f.flag_out = fl;
+        } else {
+            f.mode = 3;
+            f.out2 = chain_slot;
+            f.out2_bstride = chain_batch_stride;
+        }
+        bool fused = false;
+        if (run_unet_body(e, cur, nullptr, t, B, st, tc, &f, &fused, /*ddim=*/true)) return 1;
+        if (!fused && launch_final(f, st)) return 1;
+        if (guided) {
+            for (int it = 0; it < ng; ++it) {
+                const bool klast = (it == ng - 1);
+                GuideStepArgs a;
+                memset(&a, 0, sizeof(a));
+                a.x_in = nxt;
+                a.x_out = nxt;
+                a.flag_in = fl + it;
+                a.flag_out = klast ? nullptr : fl + it + 1;
+                a.n_hc = p->n_hard_conds;
+                for (int q = 0; q < p->n_hard_conds; ++q) a.hc_rows[q] = p->hard_cond_rows[q];
+                a.hc_vals = p->hard_cond_vals;
+                if (klast) { a.out2 = chain_slot; a.out2_bstride = chain_batch_stride; }  // + sigma * noise with sigma = 0 (eta = 0)
+                a.B = B;
+                a.H = H;
+                if (guide_launch_step(g, a, st)) return 1;
+            }
+        }
+        cur = nxt;
+    }
+    return 0;
+}
+
 extern "C" int mpdb_engine_num_buffers(mpdb_engine* e) { return e ? (int)e->bufs.size() : 0; }
 
 extern "C" int mpdb_engine_buffer_info(mpdb_engine* e, int idx, char* name, int name_cap, int32_t* channels,
@@ -1314,7 +1433,7 @@ extern "C" int mpdb_engine_read_buffer(mpdb_engine* e, int idx, float* dev_out, 
     MPDB_REQUIRE(e && dev_out && idx >= 0 && idx < (int)e->bufs.size(), "mpdb_engine_read_buffer: bad argument");
     MPDB_REQUIRE(B > 0 && B <= e->work_batch, "mpdb_engine_read_buffer: batch larger than the workspace");
     MPDB_REQUIRE(!e->alias_buffers, "mpdb_engine_read_buffer: set option alias_buffers = 0 before the forward pass");
-    MPDB_CHECK_CUDA(cudaSetDevice(e->device));
+    MPDB_ENTER_DEVICE(e->device);
     return launch_cm_to_bcl(buf_ptr(e, idx, e->work_batch), dev_out, B, e->bufs[idx].C, e->bufs[idx].L,
                             (cudaStream_t)stream);
 }
@@ -1329,7 +1448,7 @@ extern "C" int mpdb_profile_forward(mpdb_engine* e, const float* x, int32_t t, i
     MPDB_REQUIRE(e && x && ms_out && flops_out && mode_out && B > 0 && reps > 0, "mpdb_profile_forward: bad argument");
     MPDB_REQUIRE(e->finalized, "engine not finalized");
     cudaStream_t st = (cudaStream_t)stream;
-    MPDB_CHECK_CUDA(cudaSetDevice(e->device));
+    MPDB_ENTER_DEVICE(e->device);
     if (ensure_workspace(e, B)) return 1;
     cudaEvent_t ev0, ev1;
     MPDB_CHECK_CUDA(cudaEventCreate(&ev0));
@@ -1426,7 +1545,7 @@ extern "C" int mpdb_debug_tc_conv5(const float* x_cm, const float* w, float* raw
 // layer descriptors' (type, L, CO, MT*NC) as 4 ints per layer in `desc_out`.
 extern "C" int mpdb_engine_read_mega_timeline(mpdb_engine* e, int64_t* host_out, int32_t* desc_out, int32_t max_layers) {
     MPDB_REQUIRE(e && host_out && e->mega_dbg, "mpdb_engine_read_mega_timeline: timeline not enabled");
-    MPDB_CHECK_CUDA(cudaSetDevice(e->device));
+    MPDB_ENTER_DEVICE(e->device);
     MPDB_CHECK_CUDA(cudaDeviceSynchronize());
     const int n = e->mega.n_layers < max_layers ? e->mega.n_layers : max_layers;
     // the slots behind the layers (44..47) hold per-cluster {entry, setup done, exit} stamps on the GPU-wide ns timer
@@ -1443,7 +1562,7 @@ extern "C" int mpdb_engine_read_mega_timeline(mpdb_engine* e, int64_t* host_out,
 // Debug: clock64 stamps (16 per op) of CTA (0,0) of every tensor-core conv of the last forward (option "timeline").
 extern "C" int mpdb_engine_read_timeline(mpdb_engine* e, int64_t* host_out, int32_t max_ops) {
     MPDB_REQUIRE(e && host_out && e->dbg_buf, "mpdb_engine_read_timeline: timeline not enabled");
-    MPDB_CHECK_CUDA(cudaSetDevice(e->device));
+    MPDB_ENTER_DEVICE(e->device);
     MPDB_CHECK_CUDA(cudaDeviceSynchronize());
     int n = (int)e->ops.size() < max_ops ? (int)e->ops.size() : max_ops;
     MPDB_CHECK_CUDA(cudaMemcpy(host_out, e->dbg_buf, sizeof(long long) * 16 * n, cudaMemcpyDeviceToHost));

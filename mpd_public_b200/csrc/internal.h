@@ -80,6 +80,7 @@ struct TcConvArgs {
     long long* dbg;               // debug: 8 clock64 stamps of CTA (0,0) (null = off)
     int CO, L, B, gs;
     int mode;                     // TcMode; L is the INPUT length (DOWN writes L/2 positions, UP writes 2L)
+    int prec;                     // 1: one fp16 product per MMA step (hi planes only); otherwise the 22-bit three-product split
 };
 int launch_conv5_tc(const TcConvArgs& a, cudaStream_t stream);
 
@@ -144,7 +145,11 @@ struct FinalArgs {
     const float* stdv;
     int predict_epsilon;
     int clip_denoised;
-    int mode;           // 0: write eps; 1: write mean; 2: write mean + std*noise*noise_std, hard conds applied
+    int mode;           // 0: write eps; 1: write mean; 2: write mean + std*noise*noise_std, hard conds applied;
+                        // 3: DDIM step (ddim_sample, diffusion_model_base.py:184-259; eta = 0), hard conds applied;
+                        // 4: DDIM step whose result is guided next (out-of-range flag written, no hard conds)
+    float ddim_san, ddim_c;  // sqrt(alpha_next), sqrt(1 - alpha_next - sigma^2) of this DDIM step (host fp32, torch op order)
+    int ddim_last;           // time_next < 0: the step returns x_start
     const float* noise; // BLC (mode 2)
     float noise_std;
     int n_hc;
@@ -158,6 +163,27 @@ struct FinalArgs {
 };
 int launch_final(const FinalArgs& a, cudaStream_t stream);
 
+#ifdef __CUDACC__
+// The elementwise update that follows the UNet output e at one element (xv = x_t there, tt = its timestep), shared by
+// final_kernel and the cluster kernel's fused epilogue. Same fp32 operation order as the reference, no FMA contraction:
+//   modes 1/2  p_mean_variance (diffusion_model_base.py:143-155): x0 = sr*x - srm1*eps ; clamp ; c1*x0 + c2*x
+//   modes 3/4  ddim_sample (:228-248, eta = 0): x_start = sr*x - srm1*eps (NOT clamped) ; pred_noise = eps ;
+//              x = x_start * sqrt(alpha_next) + c * pred_noise, or x_start itself on the last step
+__device__ __forceinline__ float final_update_value(const FinalArgs& F, float e, float xv, int tt) {
+    const float sr = F.sr[tt], srm1 = F.srm1[tt];
+    if (F.mode >= 3) {
+        float x0, pn;
+        if (F.predict_epsilon) { x0 = __fsub_rn(__fmul_rn(sr, xv), __fmul_rn(srm1, e)); pn = e; }
+        else { x0 = e; pn = __fdiv_rn(__fsub_rn(__fmul_rn(sr, xv), e), srm1); }
+        if (F.ddim_last) return x0;
+        return __fadd_rn(__fmul_rn(x0, F.ddim_san), __fmul_rn(F.ddim_c, pn));
+    }
+    float x0 = F.predict_epsilon ? __fsub_rn(__fmul_rn(sr, xv), __fmul_rn(srm1, e)) : e;
+    if (F.clip_denoised) x0 = fminf(fmaxf(x0, -1.f), 1.f);
+    return __fadd_rn(__fmul_rn(F.c1[tt], x0), __fmul_rn(F.c2[tt], xv));
+}
+#endif
+
 struct MegaProgram {
     MegaLayer layers[MEGA_MAX_LAYERS];
     int n_layers;
@@ -165,6 +191,7 @@ struct MegaProgram {
     int B, H, D;
     int t;        // uniform timestep (row of the time-conditioning tables)
     int a_bytes;  // size of the A buffer
+    int prec;     // 3: 22-bit fp16-split operands (three products per MMA step); 1: fp16 operands (one product), engine.cu
     const float* x;  // trajectory [B][H][D] fp32
     // final_conv.1 (1x1, C -> D) + DDPM posterior mean [+ noise, hard conditions, chain slot] in the last layer's epilogue
     // (what final_kernel does as a separate launch): the timed loop passes its FinalArgs here
@@ -221,11 +248,14 @@ struct GuideStepArgs {
     int* iter_flags;            // [n_iters], [0] written by the producer of x_in; zeroed by the caller
     unsigned int* iter_counters;  // [n_iters - 1], zeroed by the caller
     long long* dbg;      // optional clock64 stamps of thread 0 of CTA 0 (MPDB_GUIDE_TIMELINE=1 in mpdb_profile_guide)
+    unsigned int* dep_count;  // counts (trajectory, evaluation) pairs whose clamp was decided by OTHER trajectories (set by the launcher)
+    int32_t* dec;        // parity instrumentation (mpdb_guide_record_decisions): [n_iters][B][n_costs][n_interp][n_spheres], else null
 };
 int guide_launch_step(mpdb_guide* g, const GuideStepArgs& a, cudaStream_t stream);
 int guide_max_coresident(mpdb_guide* g, int H);  // CTAs of the guide kernel that can be resident at once (grid-barrier bound)
 int guide_launch_flag(const float* x, long long n, int* flag, cudaStream_t stream);
 int guide_device(mpdb_guide* g);
 int guide_state_dim(mpdb_guide* g);
+bool guide_recording(mpdb_guide* g);  // decisions are being recorded: loops run without CUDA graphs
 
 }  // namespace mpdb

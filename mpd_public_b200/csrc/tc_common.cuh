@@ -138,6 +138,18 @@ __device__ __forceinline__ void tc_ld8x3(uint32_t t0, uint32_t t1, uint32_t t2, 
     for (int i = 0; i < 8; ++i) { a[i] = __uint_as_float(r[i]); b[i] = __uint_as_float(r[8 + i]); c[i] = __uint_as_float(r[16 + i]); }
 }
 
+// Two 8-column loads with a single wait (precision-1 mode: the two K-group halves of one product).
+__device__ __forceinline__ void tc_ld8x2(uint32_t t0, uint32_t t1, float (&a)[8], float (&b)[8]) {
+    uint32_t r[16];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(t0));
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]) : "r"(t1));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { a[i] = __uint_as_float(r[i]); b[i] = __uint_as_float(r[8 + i]); }
+}
+
 // Operand split x = hi + lo * 2^-11 with hi = fp16(x), lo = fp16((x - hi) * 2^11): 22 significant bits in two fp16 planes.
 // The lo plane is stored scaled by 2^11 so that it stays in fp16's normal range whatever |x| (unscaled it would fall into
 // the subnormals below |x| ~ 0.1 and lose its low bits); the products that contain one lo factor are accumulated in their
@@ -170,6 +182,32 @@ __device__ __forceinline__ void pack_split8(const float (&v)[8], uint4& ph, uint
     pl = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
+// precision-1 mode: fp16(x) only (the hi plane of pack_split8)
+__device__ __forceinline__ uint4 pack_hi8(const float (&v)[8]) {
+    uint32_t h[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const float a = fminf(fmaxf(v[2 * k], -65504.f), 65504.f), b = fminf(fmaxf(v[2 * k + 1], -65504.f), 65504.f);
+        asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(h[k]) : "f"(b), "f"(a));
+    }
+    return make_uint4(h[0], h[1], h[2], h[3]);
+}
+// One output tile's accumulator out of TMEM. Columns (relative to t): [0,32) hi*hi, [32,64) hi*lo, [64,96) lo*hi with the
+// 22-bit split; in precision-1 mode [0,32) and [64,96) hold the two K-group halves of the single fp16 product.
+__device__ __forceinline__ void tc_load_acc(uint32_t t, bool p1, float (&v)[8]) {
+    if (p1) {
+        float b[8];
+        tc_ld8x2(t, t + 2 * TC_NT, v, b);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] += b[j];
+    } else {
+        float v2[8], v3[8];
+        tc_ld8x3(t, t + 2 * TC_NT, t + TC_NT, v, v3, v2);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = fmaf(v3[j] + v2[j], 1.f / 2048.f, v[j]);
+    }
+}
+
 // Stores 8 consecutive output channels [c8, c8+8) of sample b at output position lo in the fp32 CM layout and (split
 // into fp16 hi / scaled lo) in the TC layout of an activation with CO channels and L_out positions.
 __device__ __forceinline__ void tc_store_row(const TcConvArgs& a, const float (&v)[8], int b, int lo, int c8, int L_out) {
@@ -192,7 +230,7 @@ __device__ __forceinline__ void tc_store_row(const TcConvArgs& a, const float (&
         pl.x = lo8[0] | ((uint32_t)lo8[1] << 16); pl.y = lo8[2] | ((uint32_t)lo8[3] << 16);
         pl.z = lo8[4] | ((uint32_t)lo8[5] << 16); pl.w = lo8[6] | ((uint32_t)lo8[7] << 16);
         *reinterpret_cast<uint4*>(a.out_hi + o) = ph;
-        *reinterpret_cast<uint4*>(a.out_lo + o) = pl;
+        if (a.prec != 1) *reinterpret_cast<uint4*>(a.out_lo + o) = pl;  // precision 1 reads the hi plane only
     }
 }
 

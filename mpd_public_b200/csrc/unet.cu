@@ -473,11 +473,10 @@ int launch_conv(int mode, ConvArgs a, cudaStream_t stream) {
     dim3 grid((a.B + a.S - 1) / a.S, a.CO / a.NT);
 #define MPDB_CONV_CASE(M)                                                                                      \
     case M: {                                                                                                  \
-        static bool configured = false;                                                                        \
-        if (!configured) {                                                                                     \
+        static unsigned long long configured = 0ull;                                                                        \
+        if (mpdb::first_use_on_device(configured)) {                                                                                     \
             MPDB_CHECK_CUDA(cudaFuncSetAttribute(conv_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
                                                  227 * 1024));                                                 \
-            configured = true;                                                                                 \
         }                                                                                                      \
         MPDB_CHECK_CUDA(launch_kernel(conv_kernel<M>, grid, dim3(threads), smem, stream, a));                  \
         break;                                                                                                 \
@@ -529,13 +528,12 @@ __global__ void __launch_bounds__(256) final_kernel(FinalArgs a) {
         if (a.mode != 0) {
             const int tt = a.t_dev ? (int)a.t_dev[b] : a.t_uniform;
             const float xv = a.x[idx];
-            // same operation order as the reference: sr*x - srm1*eps ; clamp ; c1*x0 + c2*x  (no FMA contraction)
-            float x0 = a.predict_epsilon ? __fsub_rn(__fmul_rn(a.sr[tt], xv), __fmul_rn(a.srm1[tt], e)) : e;
-            if (a.clip_denoised) x0 = fminf(fmaxf(x0, -1.f), 1.f);
-            r = __fadd_rn(__fmul_rn(a.c1[tt], x0), __fmul_rn(a.c2[tt], xv));
-            if (a.mode == 2) {
-                const float nz = (tt == 0) ? 0.f : a.noise[idx];
-                r = __fadd_rn(r, __fmul_rn(__fmul_rn(a.stdv[tt], nz), a.noise_std));
+            r = final_update_value(a, e, xv, tt);
+            if (a.mode == 2 || a.mode == 3) {
+                if (a.mode == 2) {
+                    const float nz = (tt == 0) ? 0.f : a.noise[idx];
+                    r = __fadd_rn(r, __fmul_rn(__fmul_rn(a.stdv[tt], nz), a.noise_std));
+                }
                 for (int k = 0; k < a.n_hc; ++k)  // later entries win, as in the reference's dict iteration
                     if (a.hc_rows[k] == l) r = a.hc_vals[((long long)k * a.B + b) * a.D + d];
             } else {

@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) unet_mega_kernel(const __grid_c
                         skip_checked = true;
                     }
                     __syncwarp();
-                    mbar_expect_tx_elect(full0 + 8 * s, wbytes + rbytes + (from_skip ? 2u * act_bytes : 0u));
+                    mbar_expect_tx_elect(full0 + 8 * s, wbytes + rbytes + (from_skip ? (P.prec == 1 ? act_bytes : 2u * act_bytes) : 0u));
                     bulk_g2s_elect(st + 2 * TC_A_PLANE_BYTES, wsrc, wbytes, full0 + 8 * s);
                     if (has_res)  // the residual conv's weights of this chunk, behind the (at most 5) taps
                         bulk_g2s_elect(st + 2 * TC_A_PLANE_BYTES + 5 * 2 * TC_B_TAP_BYTES, Ld.res_w + ((size_t)nc * n_main + cc) * (2 * TC_B_TAP_BYTES / 2),
@@ -148,7 +148,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) unet_mega_kernel(const __grid_c
                     if (from_skip) {
                         const size_t aoff = (((size_t)cluster * Ld.MT + mt) * (Ld.skip_C / 8) + (size_t)(cc - na) * (TC_KCH / 8)) * Ld.RT * 8;
                         bulk_g2s_elect(st, Ld.skip_hi + aoff, act_bytes, full0 + 8 * s);
-                        bulk_g2s_elect(st + TC_A_PLANE_BYTES, Ld.skip_lo + aoff, act_bytes, full0 + 8 * s);
+                        if (P.prec != 1) bulk_g2s_elect(st + TC_A_PLANE_BYTES, Ld.skip_lo + aoff, act_bytes, full0 + 8 * s);
                     }
                 }
             }
@@ -164,7 +164,12 @@ __global__ void __launch_bounds__(MG_THREADS, 1) unet_mega_kernel(const __grid_c
         // lane issues. They write no activations, so their fences never wait on remote stores. =====
         const int which = __shfl_sync(0xffffffffu, warp, 0) - (TC_THREADS / 32 + 1);  // 0: A_hi x [W_hi | W_lo] (N = 64), 1: A_lo x W_hi (N = 32)
         {
-            const uint32_t idesc = which == 0 ? tc_idesc(128, 2 * TC_NT) : tc_idesc(128, TC_NT);
+            // precision 3 (22-bit operands): issuer 0 drives A_hi x [W_hi | W_lo] (N = 64), issuer 1 A_lo x W_hi (N = 32).
+            // precision 1 (fp16 operands, steps where the schedule damps eps errors, engine.cu): only A_hi x W_hi is issued; the
+            // two issuers split it by K-group (issuer k takes the k-th 16 channels of every 32-channel chunk) into separate
+            // accumulators, so the MMA phase reads 5 KB of operands per (tap, K16) instead of 11 KB and the sum stays ordered.
+            const bool p1 = P.prec == 1;
+            const uint32_t idesc = (which == 0 && !p1) ? tc_idesc(128, 2 * TC_NT) : tc_idesc(128, TC_NT);
             const uint32_t col0 = __shfl_sync(0xffffffffu, tmem_base, 0) + (which == 0 ? 0u : 2u * TC_NT);  // this issuer's main accumulator
             // descriptor words: low = start address >> 4 | LBO >> 4 << 16 ; high = SBO >> 4 | version 1 << 14
             constexpr uint32_t desc_hi = (128u >> 4) | (1u << 14);
@@ -174,7 +179,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) unet_mega_kernel(const __grid_c
             // a_full phase l = "the outputs of layer l have landed in this CTA's A buffer": the peers' bytes are counted by
             // complete_tx (st.async), announced here before any peer can send them (they send after a_free of layer l, which
             // needs this warp's arrival below)
-            if (which == 0 && lane == 0 && P.n_layers > 1) mbar_expect_tx(a_full, (uint32_t)P.layers[0].tx_in[rank]);
+            if (which == 0 && lane == 0 && P.n_layers > 1) mbar_expect_tx(a_full, (uint32_t)P.layers[0].tx_in[rank] >> (p1 ? 1 : 0));
             __syncwarp();
             if (which == 0 && lane < MEGA_CLUSTER) mbar_arrive_cluster(map_to_cta(a_free, (uint32_t)lane));  // layer 0 reads no A buffer
             for (int l = 1; l < P.n_layers; ++l) {
@@ -185,7 +190,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) unet_mega_kernel(const __grid_c
                 const bool has_res = Ld.n_res_a + Ld.n_res_skip > 0;
                 const int n_a = Ld.n_a, type = Ld.type, zero_bytes = Ld.zero_bytes;
                 const uint32_t lbo = (uint32_t)Ld.RT * 16;
-                const uint32_t lo_plane = which == 1 ? (uint32_t)Ld.a_plane : 0u;
+                const uint32_t lo_plane = (which == 1 && !p1) ? (uint32_t)Ld.a_plane : 0u;
                 // the first chunk's weights do not depend on the previous layer: wait for them first
                 if (active) mbar_wait(full0 + 8 * (ring_i % MG_STAGES), (uint32_t)(ring_i / MG_STAGES) & 1u);
                 mbar_wait_cluster(a_full, (uint32_t)(l - 1) & 1u);  // operands of this layer have landed (cluster-wide)
@@ -195,7 +200,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) unet_mega_kernel(const __grid_c
                 if (mdbg) mdbg[8] = clock64();
                 if (which == 0 && lane == 0) {
                     *mma_progress = l;
-                    if (l + 1 < P.n_layers) mbar_expect_tx(a_full, (uint32_t)Ld.tx_in[rank]);  // phase l (phase l - 1 is complete)
+                    if (l + 1 < P.n_layers) mbar_expect_tx(a_full, (uint32_t)Ld.tx_in[rank] >> (p1 ? 1 : 0));  // phase l (phase l - 1 is complete)
                 }
                 if (active) {
                     uint32_t acc0 = 0u, acc1 = 0u;  // accumulate flags of the main and the second (residual / odd) accumulator
@@ -205,7 +210,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) unet_mega_kernel(const __grid_c
                         const bool from_a = cc < n_a;
                         const uint32_t st = stages_u32 + (uint32_t)sidx * MG_STAGE_BYTES;
                         const uint32_t aaddr = from_a ? abuf_u32 + (uint32_t)cc * (TC_KCH / 8) * lbo + lo_plane
-                                                      : st + (which == 1 ? (uint32_t)TC_A_PLANE_BYTES : 0u);
+                                                      : st + ((which == 1 && !p1) ? (uint32_t)TC_A_PLANE_BYTES : 0u);
                         const uint32_t a_lo = ((aaddr >> 4) & 0x3FFFu) | ((lbo >> 4) << 16);
                         const uint32_t b_lo = (((st + 2 * TC_A_PLANE_BYTES) >> 4) & 0x3FFFu) | b_lo_fixed;  // rows [0,32) = W_hi, [32,64) = W_lo
                         const uint32_t kstep_a = (2 * lbo) >> 4, kstep_b = (2 * (2 * TC_NT * 16)) >> 4, tap_b = (2 * TC_B_TAP_BYTES) >> 4;
@@ -219,12 +224,14 @@ __global__ void __launch_bounds__(MG_THREADS, 1) unet_mega_kernel(const __grid_c
                             for (int tap = 0; tap < 5; ++tap)
 #pragma unroll
                                 for (int kk = 0; kk < TC_KCH / 16; ++kk) {
+                                    if (p1 && kk != which) continue;
                                     tc_mma_bf16_elect32(col0, a_lo + kk * kstep_a + tap, desc_hi, b_lo + tap * tap_b + kk * kstep_b, desc_hi, idesc, acc0);
                                     acc0 = 1u;
                                 }
                             if (has_res) {  // the block's 1x1 residual conv on the same activations: centre row (+2), weights behind the taps
 #pragma unroll
                                 for (int kk = 0; kk < TC_KCH / 16; ++kk) {
+                                    if (p1 && kk != which) continue;
                                     tc_mma_bf16_elect32(col0 + 128, a_lo + kk * kstep_a + 2, desc_hi, b_lo + 5 * tap_b + kk * kstep_b, desc_hi, idesc, acc1);
                                     acc1 = 1u;
                                 }
@@ -234,6 +241,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) unet_mega_kernel(const __grid_c
                             for (int tap = 0; tap < 3; ++tap)
 #pragma unroll
                                 for (int kk = 0; kk < TC_KCH / 16; ++kk) {
+                                    if (p1 && kk != which) continue;
                                     tc_mma_bf16_elect32(col0, a_lo + kk * kstep_a + tap + 1, desc_hi, b_lo + tap * tap_b + kk * kstep_b, desc_hi, idesc, acc0);
                                     acc0 = 1u;
                                 }
@@ -243,6 +251,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) unet_mega_kernel(const __grid_c
                                 const int shift = tap == 0 ? 2 : tap == 1 ? 1 : tap == 2 ? 3 : 2;
 #pragma unroll
                                 for (int kk = 0; kk < TC_KCH / 16; ++kk) {
+                                    if (p1 && kk != which) continue;
                                     if (tap < 2) { tc_mma_bf16_elect32(col0, a_lo + kk * kstep_a + shift, desc_hi, b_lo + tap * tap_b + kk * kstep_b, desc_hi, idesc, acc0); acc0 = 1u; }
                                     else { tc_mma_bf16_elect32(col0 + 128, a_lo + kk * kstep_a + shift, desc_hi, b_lo + tap * tap_b + kk * kstep_b, desc_hi, idesc, acc1); acc1 = 1u; }
                                 }
@@ -273,6 +282,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) unet_mega_kernel(const __grid_c
     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + cg * 8;
     const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
     uint32_t acc_ph = 0;
+    const bool p1e = P.prec == 1;
     float keep[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // fp32 output of the last residual block owned by this thread
 
     for (int l = 0; l < P.n_layers; ++l) {
@@ -338,12 +348,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) unet_mega_kernel(const __grid_c
                 if (dbg) dbg[1] = clock64();  // accumulators complete
                 __syncwarp();
                 tc_fence_after();
-                {
-                    float v2[8], v3[8];
-                    tc_ld8x3(taddr, taddr + 2 * TC_NT, taddr + TC_NT, v, v3, v2);  // hi*hi, lo*hi, hi*lo
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) v[j] = fmaf(v3[j] + v2[j], TC_LO_UNSCALE, v[j]);
-                }
+                tc_load_acc(taddr, p1e, v);  // hi*hi + (lo*hi + hi*lo) * 2^-11, or the two K-group halves of hi*hi
                 // the second accumulator (odd outputs of an up-sampling layer, the block's 1x1 residual conv) stays in TMEM
                 // until it is needed: it is not overwritten before the next layer's MMAs, and holding it in registers
                 // through GroupNorm costs spills
@@ -357,7 +362,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) unet_mega_kernel(const __grid_c
                 uint4* lo_plane = reinterpret_cast<uint4*>(abuf + Ld.a_plane);
                 for (int i = tid; i < nz; i += TC_THREADS) {
                     reinterpret_cast<uint4*>(abuf)[i] = make_uint4(0u, 0u, 0u, 0u);
-                    lo_plane[i] = make_uint4(0u, 0u, 0u, 0u);
+                    if (!p1e) lo_plane[i] = make_uint4(0u, 0u, 0u, 0u);
                 }
                 asm volatile("bar.arrive 2, %0;" ::"n"(TC_THREADS + 32) : "memory");  // issuer warp 0 sends a_free once all 16 warps are here
             }
@@ -376,10 +381,8 @@ __global__ void __launch_bounds__(MG_THREADS, 1) unet_mega_kernel(const __grid_c
                     v[0] += pc0.x; v[1] += pc0.y; v[2] += pc0.z; v[3] += pc0.w;
                     v[4] += pc1.x; v[5] += pc1.y; v[6] += pc1.z; v[7] += pc1.w;
                     if (Ld.res_mode == 2) {
-                        float rv[8], rv2[8], rv3[8];
-                        tc_ld8x3(taddr + 128, taddr + 128 + 2 * TC_NT, taddr + 128 + TC_NT, rv, rv3, rv2);
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) rv[j] = fmaf(rv3[j] + rv2[j], TC_LO_UNSCALE, rv[j]);
+                        float rv[8];
+                        tc_load_acc(taddr + 128, p1e, rv);
                         v[0] += rv[0] + pr0.x; v[1] += rv[1] + pr0.y; v[2] += rv[2] + pr0.z; v[3] += rv[3] + pr0.w;
                         v[4] += rv[4] + pr1.x; v[5] += rv[5] + pr1.y; v[6] += rv[6] + pr1.z; v[7] += rv[7] + pr1.w;
                     } else if (Ld.res_mode == 1) {
@@ -410,17 +413,14 @@ __global__ void __launch_bounds__(MG_THREADS, 1) unet_mega_kernel(const __grid_c
             unsigned short* const skip_lo = Ld.skip_out_lo;
             for (int k = 0; k < n_out; ++k) {
                 if (k == 1) {  // up-sampling: the odd output row comes from the second accumulator (warp-wide TMEM load)
-                    float w2[8], w3[8];
-                    tc_ld8x3(taddr + 128, taddr + 128 + 2 * TC_NT, taddr + 128 + TC_NT, v, w3, w2);
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) v[j] = fmaf(w3[j] + w2[j], TC_LO_UNSCALE, v[j]);
+                    tc_load_acc(taddr + 128, p1e, v);
                     v[0] += pb0.x; v[1] += pb0.y; v[2] += pb0.z; v[3] += pb0.w;
                     v[4] += pb1.x; v[5] += pb1.y; v[6] += pb1.z; v[7] += pb1.w;
                 }
                 if (emit) {
                     const int lo = ltype == MG_DOWN ? (ll >> 1) : ltype == MG_UP ? 2 * ll + k : ll;
-                    uint4 ph, pl;
-                    pack_split8(v, ph, pl);
+                    uint4 ph, pl = make_uint4(0u, 0u, 0u, 0u);
+                    if (p1e) ph = pack_hi8(v); else pack_split8(v, ph, pl);
                     const uint32_t off = d_off + (uint32_t)lo * 16u;
                     const uint32_t local_hi = abuf_u32 + off, local_lo = local_hi + o_plane;
                     int j = j0;
@@ -428,18 +428,18 @@ __global__ void __launch_bounds__(MG_THREADS, 1) unet_mega_kernel(const __grid_c
                         const uint32_t cta = cta0 + (uint32_t)j;
                         if ((int)cta == rank) {  // own A buffer: plain shared-memory stores
                             *reinterpret_cast<uint4*>(abuf + off) = ph;
-                            *reinterpret_cast<uint4*>(abuf + off + o_plane) = pl;
+                            if (!p1e) *reinterpret_cast<uint4*>(abuf + off + o_plane) = pl;
                         } else {
                             const uint32_t bar = map_to_cta(a_full, cta);
                             st_async_v4(map_to_cta(local_hi, cta), ph, bar);
-                            st_async_v4(map_to_cta(local_lo, cta), pl, bar);
+                            if (!p1e) st_async_v4(map_to_cta(local_lo, cta), pl, bar);
                         }
                         if (++j == oNC) j = 0;
                     }
                     if (skip_hi != nullptr) {  // skip connection: same-level layout in global memory
                         const size_t o = ((((size_t)cluster * Ld.MT + mt) * (Ld.CO / 8) + c8 / 8) * Ld.RT + (r + 2)) * 8;
                         *reinterpret_cast<uint4*>(skip_hi + o) = ph;
-                        *reinterpret_cast<uint4*>(skip_lo + o) = pl;
+                        if (!p1e) *reinterpret_cast<uint4*>(skip_lo + o) = pl;
                     }
                 }
             }
@@ -472,7 +472,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) unet_mega_kernel(const __grid_c
                 }
                 epi_sync();
                 const int tt = P.t;
-                const float sr = F.sr[tt], srm1 = F.srm1[tt], c1 = F.c1[tt], c2 = F.c2[tt], sd = F.stdv[tt];
+                const float sd = F.stdv[tt];
                 bool viol = false;
                 const int n_out = Ld.SPT * Ld.L * D;
                 for (int idx = tid; idx < n_out; idx += TC_THREADS) {
@@ -488,13 +488,12 @@ __global__ void __launch_bounds__(MG_THREADS, 1) unet_mega_kernel(const __grid_c
                     float res = e;
                     if (F.mode != 0) {
                         const float xv = F.x[gi];
-                        // same operation order as the reference: sr*x - srm1*eps ; clamp ; c1*x0 + c2*x  (no FMA contraction)
-                        float x0 = F.predict_epsilon ? __fsub_rn(__fmul_rn(sr, xv), __fmul_rn(srm1, e)) : e;
-                        if (F.clip_denoised) x0 = fminf(fmaxf(x0, -1.f), 1.f);
-                        res = __fadd_rn(__fmul_rn(c1, x0), __fmul_rn(c2, xv));
-                        if (F.mode == 2) {
-                            const float nz = (tt == 0) ? 0.f : F.noise[gi];
-                            res = __fadd_rn(res, __fmul_rn(__fmul_rn(sd, nz), F.noise_std));
+                        res = final_update_value(F, e, xv, tt);
+                        if (F.mode == 2 || F.mode == 3) {
+                            if (F.mode == 2) {
+                                const float nz = (tt == 0) ? 0.f : F.noise[gi];
+                                res = __fadd_rn(res, __fmul_rn(__fmul_rn(sd, nz), F.noise_std));
+                            }
                             for (int k = 0; k < F.n_hc; ++k)  // later entries win, as in the reference's dict iteration
                                 if (F.hc_rows[k] == lq) res = F.hc_vals[((long long)k * P.B + bq) * D + d];
                         } else {
@@ -566,10 +565,9 @@ int launch_unet_mega(const MegaProgram& P, cudaStream_t stream) {
     MPDB_REQUIRE(P.a_bytes % 128 == 0, "mega: A buffer size must be a multiple of 128");
     const size_t smem = mega_smem_bytes(P.a_bytes);
     MPDB_REQUIRE(smem <= 227 * 1024, "mega: shared memory budget exceeded");
-    static bool configured = false;
-    if (!configured) {
+    static unsigned long long configured = 0ull;
+    if (mpdb::first_use_on_device(configured)) {
         MPDB_CHECK_CUDA(cudaFuncSetAttribute(unet_mega_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        configured = true;
     }
     const int n_clusters = (P.B + P.G - 1) / P.G;
     cudaLaunchConfig_t cfg = {};

@@ -62,6 +62,9 @@ __global__ void __launch_bounds__(TCL_THREADS, 1) conv5_tc_kernel(TcConvArgs a) 
     const int n_main = (a.c0 + a.c1) / TC_KCH;
     const int n_res = a.res_w ? (a.rc0 + a.rc1) / TC_KCH : 0;
     const int n_steps = n_main + n_res;
+    // precision 1 (a.prec == 1, engine.cu step_prec): one fp16 product per MMA step; the two issuers split it by K-group
+    // into separate accumulators ([0,32) and [64,96)), the lo planes are neither loaded nor written
+    const bool p1 = a.prec == 1;
 
     const uint32_t stages_u32 = smem_u32(stages);
     const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + TC_STAGES), done_bar = smem_u32(bars + 2 * TC_STAGES);
@@ -100,7 +103,7 @@ __global__ void __launch_bounds__(TCL_THREADS, 1) conv5_tc_kernel(TcConvArgs a) 
             if (weights) {
                 const unsigned short* wsrc = is_res ? a.res_w + ((size_t)ntile * n_res + c) * (2 * 1 * TC_B_TAP_BYTES / 2)
                                                     : a.w + ((size_t)ntile * n_main + c) * (2 * NTAPS * TC_B_TAP_BYTES / 2);
-                mbar_expect_tx_elect(full0 + 8 * s, 2u * TC_A_PLANE_BYTES + bbytes);  // covers the activation copies too
+                mbar_expect_tx_elect(full0 + 8 * s, (p1 ? 1u : 2u) * TC_A_PLANE_BYTES + bbytes);  // covers the activation copies too
                 bulk_g2s_elect(st + 2 * TC_A_PLANE_BYTES, wsrc, bbytes, full0 + 8 * s);
             }
             if (acts) {
@@ -112,7 +115,7 @@ __global__ void __launch_bounds__(TCL_THREADS, 1) conv5_tc_kernel(TcConvArgs a) 
                 const int kg0 = (c * TC_KCH - (second ? C0 : 0)) / 8;
                 const size_t aoff = ((size_t)tile * (Csrc / 8) + kg0) * TC_RT * 8;  // elements
                 bulk_g2s_elect(st, ahi + aoff, TC_A_PLANE_BYTES, full0 + 8 * s);
-                bulk_g2s_elect(st + TC_A_PLANE_BYTES, alo + aoff, TC_A_PLANE_BYTES, full0 + 8 * s);
+                if (!p1) bulk_g2s_elect(st + TC_A_PLANE_BYTES, alo + aoff, TC_A_PLANE_BYTES, full0 + 8 * s);
             }
         };
         for (int i = 0; i < n_steps && i < TC_STAGES; ++i) produce(i, true, false);
@@ -126,7 +129,7 @@ __global__ void __launch_bounds__(TCL_THREADS, 1) conv5_tc_kernel(TcConvArgs a) 
     } else if (warp > TC_THREADS / 32) {
         // ===== two MMA-issue warps =====
         const int which = __shfl_sync(0xffffffffu, warp, 0) - (TC_THREADS / 32 + 1);
-        const uint32_t idesc = which == 0 ? tc_idesc(128, 2 * TC_NT) : tc_idesc(128, TC_NT);
+        const uint32_t idesc = (which == 0 && !p1) ? tc_idesc(128, 2 * TC_NT) : tc_idesc(128, TC_NT);
         const uint32_t col0 = __shfl_sync(0xffffffffu, tmem_base, 0) + (which == 0 ? 0u : 2u * TC_NT);
         constexpr uint32_t desc_hi = (128u >> 4) | (1u << 14);                      // SBO = 128 B, descriptor version 1
         constexpr uint32_t a_lo_fixed = ((uint32_t)(TC_RT * 16) >> 4) << 16;        // activation tile: LBO = 132 rows x 16 B
@@ -136,13 +139,14 @@ __global__ void __launch_bounds__(TCL_THREADS, 1) conv5_tc_kernel(TcConvArgs a) 
         for (int i = 0; i < n_steps; ++i) {
             const int s = i % TC_STAGES;
             const uint32_t st = stages_u32 + (uint32_t)s * TC_STAGE_BYTES;
-            const uint32_t a_lo = (((st + (which == 1 ? (uint32_t)TC_A_PLANE_BYTES : 0u)) >> 4) & 0x3FFFu) | a_lo_fixed;
+            const uint32_t a_lo = (((st + ((which == 1 && !p1) ? (uint32_t)TC_A_PLANE_BYTES : 0u)) >> 4) & 0x3FFFu) | a_lo_fixed;
             const uint32_t b_lo = (((st + 2 * TC_A_PLANE_BYTES) >> 4) & 0x3FFFu) | b_lo_fixed;  // rows [0,32) = W_hi, [32,64) = W_lo
             mbar_wait(full0 + 8 * s, (uint32_t)(i / TC_STAGES) & 1u);
             tc_fence_after();
             if (i >= n_main) {  // fused 1x1 residual conv: centre row (+2), second accumulator
 #pragma unroll
                 for (int kk = 0; kk < TC_KCH / 16; ++kk) {
+                    if (p1 && kk != which) continue;
                     tc_mma_bf16_elect32(col0 + 128, a_lo + kk * kstep_a + 2, desc_hi, b_lo + kk * kstep_b, desc_hi, idesc, acc1);
                     acc1 = 1u;
                 }
@@ -156,6 +160,7 @@ __global__ void __launch_bounds__(TCL_THREADS, 1) conv5_tc_kernel(TcConvArgs a) 
                     const bool second_acc = MODE == TCM_UP && tap >= 2;
 #pragma unroll
                     for (int kk = 0; kk < TC_KCH / 16; ++kk) {
+                        if (p1 && kk != which) continue;
                         if (second_acc) { tc_mma_bf16_elect32(col0 + 128, a_lo + kk * kstep_a + shift, desc_hi, b_lo + tap * tap_b + kk * kstep_b, desc_hi, idesc, acc1); acc1 = 1u; }
                         else { tc_mma_bf16_elect32(col0, a_lo + kk * kstep_a + shift, desc_hi, b_lo + tap * tap_b + kk * kstep_b, desc_hi, idesc, acc0); acc0 = 1u; }
                     }
@@ -209,12 +214,7 @@ __global__ void __launch_bounds__(TCL_THREADS, 1) conv5_tc_kernel(TcConvArgs a) 
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + cg * 8;
         if (dbg && tid == 64) a.dbg[4] = clock64();  // accumulators ready
         float v[8];
-        {
-            float v2[8], v3[8];
-            tc_ld8x3(taddr, taddr + 2 * TC_NT, taddr + TC_NT, v, v3, v2);  // hi*hi, lo*hi, hi*lo
-#pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = fmaf(v3[j] + v2[j], TC_LO_UNSCALE, v[j]);
-        }
+        tc_load_acc(taddr, p1, v);
         if (dbg && tid == 64) a.dbg[5] = clock64();  // TMEM read
 
         if (!full) {
@@ -228,12 +228,10 @@ __global__ void __launch_bounds__(TCL_THREADS, 1) conv5_tc_kernel(TcConvArgs a) 
             if (valid && (l & 1) == 0) tc_store_row(a, v, b, l >> 1, c8, a.L >> 1);
         } else if (MODE == TCM_UP) {
             // transposed conv: accumulator 0 = even outputs (2l), accumulator 1 = odd outputs (2l + 1)
-            float w[8], w2[8], w3[8];
-            tc_ld8x3(taddr + 128, taddr + 128 + 2 * TC_NT, taddr + 128 + TC_NT, w, w3, w2);
+            float w[8];
+            tc_load_acc(taddr + 128, p1, w);
             v[0] += pb0.x; v[1] += pb0.y; v[2] += pb0.z; v[3] += pb0.w;
             v[4] += pb1.x; v[5] += pb1.y; v[6] += pb1.z; v[7] += pb1.w;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) w[j] = fmaf(w3[j] + w2[j], TC_LO_UNSCALE, w[j]);
             w[0] += pb0.x; w[1] += pb0.y; w[2] += pb0.z; w[3] += pb0.w;
             w[4] += pb1.x; w[5] += pb1.y; w[6] += pb1.z; w[7] += pb1.w;
             if (valid) {
@@ -249,10 +247,8 @@ __global__ void __launch_bounds__(TCL_THREADS, 1) conv5_tc_kernel(TcConvArgs a) 
             v[0] += pc0.x; v[1] += pc0.y; v[2] += pc0.z; v[3] += pc0.w;
             v[4] += pc1.x; v[5] += pc1.y; v[6] += pc1.z; v[7] += pc1.w;
             if (a.res_w != nullptr) {
-                float rv[8], rv2[8], rv3[8];
-                tc_ld8x3(taddr + 128, taddr + 128 + 2 * TC_NT, taddr + 128 + TC_NT, rv, rv3, rv2);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) rv[j] = fmaf(rv3[j] + rv2[j], TC_LO_UNSCALE, rv[j]);
+                float rv[8];
+                tc_load_acc(taddr + 128, p1, rv);
                 v[0] += rv[0] + pr0.x; v[1] += rv[1] + pr0.y; v[2] += rv[2] + pr0.z; v[3] += rv[3] + pr0.w;
                 v[4] += rv[4] + pr1.x; v[5] += rv[5] + pr1.y; v[6] += rv[6] + pr1.z; v[7] += rv[7] + pr1.w;
             } else {
@@ -286,6 +282,24 @@ constexpr int RTB_THREADS = TC_THREADS + 32;
 constexpr int RTB_TMEM_COLS = 512;  // hi*hi | hi*lo: conv0 [0,64), conv1 [64,128), residual conv [128,192); lo*hi: the same + 256 ([.., +32))
 
 
+// accumulator of one tile of the block kernel: [t, t+32) hi*hi, [t+32, t+64) hi*lo, [t+256, t+288) lo*hi; precision 1: the
+// single product sits in [t, t+32)
+__device__ __forceinline__ void rtb_load_acc(uint32_t t, bool p1, float (&v)[8]) {
+    if (p1) {
+        uint32_t r[8];
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                     : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(t));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+    } else {
+        float v2[8], v3[8];
+        tc_ld8x3(t, t + 256, t + TC_NT, v, v3, v2);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = fmaf(v3[j] + v2[j], TC_LO_UNSCALE, v[j]);
+    }
+}
+
 template <int GS, int NSTAGE>
 __global__ void __launch_bounds__(RTB_THREADS, 1) rtb_tc_kernel(TcRtbArgs args) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -309,6 +323,7 @@ __global__ void __launch_bounds__(RTB_THREADS, 1) rtb_tc_kernel(TcRtbArgs args) 
     const int n2 = CO / TC_KCH;                              // conv1 chunks (weights only)
     const int n3 = a1.res_w ? (a1.rc0 + a1.rc1) / TC_KCH : 0;  // residual 1x1 conv chunks (activations + weights)
     const int n_steps = n1 + n2 + n3;
+    const bool p1 = a0.prec == 1;  // one fp16 product per MMA step (see conv5_tc_kernel); the lo planes are not touched
     const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + NSTAGE);
     const uint32_t done1 = smem_u32(bars + 2 * NSTAGE), done2 = done1 + 8, a2_full = done1 + 16;
 
@@ -348,7 +363,7 @@ __global__ void __launch_bounds__(RTB_THREADS, 1) rtb_tc_kernel(TcRtbArgs args) 
                 const unsigned short* wsrc = phase == 0   ? a0.w + ((size_t)ntile * n1 + c) * (2 * 5 * TC_B_TAP_BYTES / 2)
                                              : phase == 1 ? a1.w + ((size_t)ntile * n2 + c) * (2 * 5 * TC_B_TAP_BYTES / 2)
                                                           : a1.res_w + ((size_t)ntile * n3 + c) * (2 * 1 * TC_B_TAP_BYTES / 2);
-                mbar_expect_tx(full0 + 8 * s, bbytes + (phase == 1 ? 0u : 2u * TC_A_PLANE_BYTES));
+                mbar_expect_tx(full0 + 8 * s, bbytes + (phase == 1 ? 0u : (p1 ? 1u : 2u) * TC_A_PLANE_BYTES));
                 bulk_g2s(st + 2 * TC_A_PLANE_BYTES, wsrc, bbytes, full0 + 8 * s);
                 if (phase != 1) {
                     const int C0 = phase == 0 ? A.c0 : A.rc0, C1 = phase == 0 ? A.c1 : A.rc1;
@@ -359,7 +374,7 @@ __global__ void __launch_bounds__(RTB_THREADS, 1) rtb_tc_kernel(TcRtbArgs args) 
                     const int kg0 = (c * TC_KCH - (second ? C0 : 0)) / 8;
                     const size_t aoff = ((size_t)tile * (Csrc / 8) + kg0) * TC_RT * 8;
                     bulk_g2s(st, ahi + aoff, TC_A_PLANE_BYTES, full0 + 8 * s);
-                    bulk_g2s(st + TC_A_PLANE_BYTES, alo + aoff, TC_A_PLANE_BYTES, full0 + 8 * s);
+                    if (!p1) bulk_g2s(st + TC_A_PLANE_BYTES, alo + aoff, TC_A_PLANE_BYTES, full0 + 8 * s);
                 }
             }
         }
@@ -383,9 +398,9 @@ __global__ void __launch_bounds__(RTB_THREADS, 1) rtb_tc_kernel(TcRtbArgs args) 
             for (int kk = 0; kk < TC_KCH / 16; ++kk) {
                 const uint64_t aofs = (uint64_t)((kk * 2 * (TC_RT * 16) + shift * 16) >> 4);
                 const uint64_t bofs = (uint64_t)((tap * 2 * TC_B_TAP_BYTES + kk * 2 * (2 * TC_NT * 16)) >> 4);
-                tc_mma_bf16(dcol, dA_hi + aofs, dB + bofs, idesc64, first ? 0u : 1u);
+                tc_mma_bf16(dcol, dA_hi + aofs, dB + bofs, p1 ? idesc32 : idesc64, first ? 0u : 1u);
                 first = false;
-                tc_mma_bf16(dcol + 256, dA_lo + aofs, dB + bofs, idesc32, first_lo ? 0u : 1u);  // lo*hi: own columns (scaled sum)
+                if (!p1) tc_mma_bf16(dcol + 256, dA_lo + aofs, dB + bofs, idesc32, first_lo ? 0u : 1u);  // lo*hi: own columns (scaled sum)
                 first_lo = false;
             }
         }
@@ -419,12 +434,7 @@ __global__ void __launch_bounds__(RTB_THREADS, 1) rtb_tc_kernel(TcRtbArgs args) 
     tc_fence_after();
     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + cg * 8;
     float v[8];
-    {
-        float v2[8], v3[8];
-        tc_ld8x3(taddr, taddr + 256, taddr + TC_NT, v, v3, v2);  // hi*hi, lo*hi, hi*lo
-#pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = fmaf(v3[j] + v2[j], TC_LO_UNSCALE, v[j]);
-    }
+    rtb_load_acc(taddr, p1, v);  // hi*hi, lo*hi, hi*lo
     v[0] += pb0.x; v[1] += pb0.y; v[2] += pb0.z; v[3] += pb0.w;
     v[4] += pb1.x; v[5] += pb1.y; v[6] += pb1.z; v[7] += pb1.w;
     gn_mish8<GS, true>(v, valid, r, s, cg, tid, SPT, Lp, a0.L, part, pg0, pg1, pe0, pe1);
@@ -447,7 +457,7 @@ __global__ void __launch_bounds__(RTB_THREADS, 1) rtb_tc_kernel(TcRtbArgs args) 
         for (int cta = 0; cta < CS; ++cta) {
             if (valid) {
                 st_cluster_v4(map_to_cta(local_hi, cta), ph);
-                st_cluster_v4(map_to_cta(local_lo, cta), pl);
+                if (!p1) st_cluster_v4(map_to_cta(local_lo, cta), pl);
             }
         }
         // generic-proxy stores must be visible to the tensor core (async proxy) of the consumer CTAs
@@ -485,20 +495,13 @@ __global__ void __launch_bounds__(RTB_THREADS, 1) rtb_tc_kernel(TcRtbArgs args) 
     mbar_wait(done2, 0);
     __syncwarp();
     tc_fence_after();
-    {
-        float v2[8], v3[8];
-        tc_ld8x3(taddr + 2 * TC_NT, taddr + 2 * TC_NT + 256, taddr + 3 * TC_NT, v, v3, v2);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = fmaf(v3[j] + v2[j], TC_LO_UNSCALE, v[j]);
-    }
+    rtb_load_acc(taddr + 2 * TC_NT, p1, v);
     v[0] += pb0.x; v[1] += pb0.y; v[2] += pb0.z; v[3] += pb0.w;
     v[4] += pb1.x; v[5] += pb1.y; v[6] += pb1.z; v[7] += pb1.w;
     gn_mish8<GS, true>(v, valid, r, s, cg, tid, SPT, Lp, a0.L, part, pg0, pg1, pe0, pe1);
     if (a1.res_w != nullptr) {
-        float rv[8], rv2[8], rv3[8];
-        tc_ld8x3(taddr + 4 * TC_NT, taddr + 4 * TC_NT + 256, taddr + 5 * TC_NT, rv, rv3, rv2);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) rv[j] = fmaf(rv3[j] + rv2[j], TC_LO_UNSCALE, rv[j]);
+        float rv[8];
+        rtb_load_acc(taddr + 4 * TC_NT, p1, rv);
         v[0] += rv[0] + pr0.x; v[1] += rv[1] + pr0.y; v[2] += rv[2] + pr0.z; v[3] += rv[3] + pr0.w;
         v[4] += rv[4] + pr1.x; v[5] += rv[5] + pr1.y; v[6] += rv[6] + pr1.z; v[7] += rv[7] + pr1.w;
     } else {
@@ -532,10 +535,9 @@ int launch_rtb_tc(const TcRtbArgs& a, cudaStream_t stream) {
     dim3 grid((a0.B + SPT - 1) / SPT, CS);
 #define MPDB_RTB_LAUNCH(G, S)                                                                                          \
     {                                                                                                                  \
-        static bool configured = false;                                                                                \
-        if (!configured) {                                                                                             \
+        static unsigned long long configured = 0ull;                                                                                \
+        if (mpdb::first_use_on_device(configured)) {                                                                                             \
             MPDB_CHECK_CUDA(cudaFuncSetAttribute(rtb_tc_kernel<G, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
-            configured = true;                                                                                         \
         }                                                                                                              \
         MPDB_CHECK_CUDA(launch_kernel_cluster(rtb_tc_kernel<G, S>, grid, dim3(RTB_THREADS), smem, stream, (unsigned)CS, a)); \
     }
@@ -566,11 +568,10 @@ int launch_conv5_tc(const TcConvArgs& a, cudaStream_t stream) {
     dim3 grid((a.B + SPT - 1) / SPT, a.CO / TC_NT);
 #define MPDB_TC_LAUNCH(M, G)                                                                                       \
     {                                                                                                              \
-        static bool configured = false;                                                                            \
-        if (!configured) {                                                                                         \
+        static unsigned long long configured = 0ull;                                                                            \
+        if (mpdb::first_use_on_device(configured)) {                                                                                         \
             MPDB_CHECK_CUDA(cudaFuncSetAttribute(conv5_tc_kernel<M, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                                  220 * 1024));                                                     \
-            configured = true;                                                                                     \
         }                                                                                                          \
         MPDB_CHECK_CUDA(launch_kernel(conv5_tc_kernel<M, G>, grid, dim3(TCL_THREADS), smem, stream, a));            \
     }

@@ -51,16 +51,19 @@ def make_timesteps(batch_size, i, device):
 class Engine:
     """Owns an `mpdb_engine*`: packed weights, time-conditioning tables, schedule tables, workspace."""
 
-    def __init__(self, unet, device, n_steps, schedule, predict_epsilon, clip_denoised):
+    def __init__(self, unet, device, n_steps, schedule, predict_epsilon, clip_denoised, horizon=None):
         self.lib = _lib.lib()
         self.unet = unet
+        # the UNet is fully convolutional (temporal_unet.py:118-171): the reference accepts any horizon divisible by
+        # 2^(levels-1); the device plan (buffers, tiles, cluster program) is per horizon, so each horizon gets its own engine
+        self.horizon = int(horizon if horizon is not None else unet.n_support_points)
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise RuntimeError("mpd_public_b200 has no CPU path: move the model to a CUDA device")
         self.n_steps = int(n_steps)
         cfg = _lib.EngineConfig()
         cfg.state_dim = unet.state_dim
-        cfg.horizon = unet.n_support_points
+        cfg.horizon = self.horizon
         cfg.unet_input_dim = unet.unet_input_dim
         cfg.n_levels = len(unet.dim_mults)
         for i, m in enumerate(unet.dim_mults):
@@ -138,8 +141,8 @@ class Engine:
     # ---- entry points ----
     def _prep(self, x, t=None):
         _lib.require_cuda(x, "x")
-        if x.dim() != 3 or x.shape[1] != self.unet.n_support_points or x.shape[2] != self.unet.state_dim:
-            raise RuntimeError(f"expected x of shape [B, {self.unet.n_support_points}, {self.unet.state_dim}], got {tuple(x.shape)}")
+        if x.dim() != 3 or x.shape[1] != self.horizon or x.shape[2] != self.unet.state_dim:
+            raise RuntimeError(f"expected x of shape [B, {self.horizon}, {self.unet.state_dim}], got {tuple(x.shape)}")
         x = x.detach().to(torch.float32).contiguous()
         if t is not None:
             t = t.to(device=x.device, dtype=torch.long).contiguous()
@@ -162,7 +165,7 @@ class Engine:
         diffusion_model_base.py:25-27), the loop's tensor-core policy, one cluster-kernel launch when supported."""
         if not x.is_cuda:
             raise RuntimeError("mpd_public_b200 runs on CUDA tensors only (no CPU fallback)")
-        x = x.contiguous().float()
+        x, _ = self._prep(x)
         self.sync_params()
         out = torch.empty_like(x)
         _lib.check(self.lib.mpdb_unet_forward_uniform(self.handle, _lib.fptr(x), int(t), _lib.fptr(out), x.shape[0],
@@ -199,7 +202,11 @@ class Engine:
         n_iters = self.n_steps + n_extra
         S, B, H, D = noise.shape
         assert S == n_iters + 1
+        if H != self.horizon or D != self.unet.state_dim:
+            raise RuntimeError(f"this engine was built for trajectories [B, {self.horizon}, {self.unet.state_dim}], got "
+                               f"[{B}, {H}, {D}]")
         p = _lib.LoopParams()
+        p.horizon, p.state_dim = H, D
         p.n_steps_without_noise = n_extra
         p.t_start_guide = _lib.INT32_MAX if t_start_guide == float("inf") or t_start_guide >= _lib.INT32_MAX else int(
             np.ceil(t_start_guide))
@@ -227,6 +234,43 @@ class Engine:
         del ns
         return x_out, chain
 
+    def ddim_loop(self, x_init, hard_conds, guide_handle, times, times_next, sqrt_alpha_next, coef_noise, t_start_guide,
+                  n_guide_steps, return_chain):
+        """x_init: [B, H, D] (randn, hard conditions not yet applied). Returns (x [B,H,D], chain [n+1, B, H, D] or None)."""
+        self.sync_params()
+        x_init, _ = self._prep(x_init)
+        B, H, D = x_init.shape
+        n = len(times)
+        p = _lib.DdimParams()
+        p.n_steps = n
+        t_arr = (C.c_int32 * n)(*[int(v) for v in times])
+        tn_arr = (C.c_int32 * n)(*[int(v) for v in times_next])
+        sa_arr = (C.c_float * n)(*[float(v) for v in sqrt_alpha_next])
+        cn_arr = (C.c_float * n)(*[float(v) for v in coef_noise])
+        p.times, p.times_next = C.cast(t_arr, C.POINTER(C.c_int32)), C.cast(tn_arr, C.POINTER(C.c_int32))
+        p.sqrt_alpha_next, p.coef_noise = C.cast(sa_arr, C.POINTER(C.c_float)), C.cast(cn_arr, C.POINTER(C.c_float))
+        p.t_start_guide = _lib.INT32_MAX if t_start_guide == float("inf") or t_start_guide >= _lib.INT32_MAX else int(
+            np.ceil(t_start_guide))
+        p.n_guide_steps = int(n_guide_steps)
+        rows = list(hard_conds.keys())
+        if len(rows) > _lib.MAX_HARD_CONDS:
+            raise RuntimeError(f"at most {_lib.MAX_HARD_CONDS} hard conditions are supported")
+        p.n_hard_conds = len(rows)
+        hc = None
+        if rows:
+            for k, r in enumerate(rows):
+                p.hard_cond_rows[k] = int(r) % H
+            hc = torch.stack([hard_conds[r].to(device=x_init.device, dtype=torch.float32).expand(B, D) for r in rows]).contiguous()
+            p.hard_cond_vals = hc.data_ptr()
+        p.horizon, p.state_dim = H, D
+        x_out = torch.empty_like(x_init)
+        chain = torch.empty((n + 1, B, H, D), device=x_init.device, dtype=torch.float32) if return_chain else None
+        _lib.check(self.lib.mpdb_ddim_loop(
+            self.handle, guide_handle, C.byref(p), _lib.fptr(x_init), _lib.fptr(x_out),
+            _lib.fptr(chain) if chain is not None else None, B * H * D, H * D, B, _lib.stream_ptr(x_init.device)))
+        del t_arr, tn_arr, sa_arr, cn_arr
+        return x_out, chain
+
     def set_option(self, name, value):
         _lib.check(self.lib.mpdb_engine_set_option(self.handle, name.encode(), float(value)))
 
@@ -245,22 +289,23 @@ class Engine:
         return out
 
 
-def _engine_for_unet(unet, device, n_steps=None, schedule=None, predict_epsilon=True, clip_denoised=True):
+def _engine_for_unet(unet, device, n_steps=None, schedule=None, predict_epsilon=True, clip_denoised=True, horizon=None):
     device = torch.device(device)
     if device.type != "cuda":
         raise RuntimeError("mpd_public_b200 has no CPU path: move the model and its inputs to a CUDA device")
     idx = device.index if device.index is not None else torch.cuda.current_device()
+    horizon = int(horizon if horizon is not None else unet.n_support_points)
     cache = unet.__dict__.setdefault("_mpdb_engines", {})
     if n_steps is None:
-        # stand-alone UNet call: reuse any engine of this device, else a table of 1000 time steps
-        for (d, _t, _pe, _cd), eng in cache.items():
-            if d == idx:
+        # stand-alone UNet call: reuse any engine of this device and horizon, else a table of 1000 time steps
+        for (d, _t, _pe, _cd, h), eng in cache.items():
+            if d == idx and h == horizon:
                 return eng
         n_steps = unet.__dict__.get("_mpdb_default_steps", 1000)
-    key = (idx, int(n_steps), bool(predict_epsilon), bool(clip_denoised))
+    key = (idx, int(n_steps), bool(predict_epsilon), bool(clip_denoised), horizon)
     eng = cache.get(key)
     if eng is None:
-        eng = Engine(unet, torch.device("cuda", idx), n_steps, schedule, predict_epsilon, clip_denoised)
+        eng = Engine(unet, torch.device("cuda", idx), n_steps, schedule, predict_epsilon, clip_denoised, horizon)
         cache[key] = eng
     return eng
 
@@ -314,14 +359,15 @@ class GaussianDiffusionModel(nn.Module):
         b = self.posterior_mean_coef1
         return (b.data_ptr(), b._version, self.sqrt_recip_alphas_cumprod._version)
 
-    def _engine(self):
+    def _engine(self, horizon=None):
         device = self.betas.device
         if device.type != "cuda":
             raise RuntimeError("mpd_public_b200 has no CPU path: call .to('cuda') on the model first")
         sched = {k: getattr(self, k) for k in (
             'sqrt_recip_alphas_cumprod', 'sqrt_recipm1_alphas_cumprod', 'posterior_mean_coef1', 'posterior_mean_coef2',
             'posterior_log_variance_clipped')}
-        eng = _engine_for_unet(self.model, device, self.n_diffusion_steps, sched, self.predict_epsilon, self.clip_denoised)
+        eng = _engine_for_unet(self.model, device, self.n_diffusion_steps, sched, self.predict_epsilon, self.clip_denoised,
+                               horizon)
         sig = self._schedule_sig()
         if eng.__dict__.get("_sched_sig") != sig:  # buffers reloaded by load_state_dict
             eng._set_schedule(sched)
@@ -354,7 +400,7 @@ class GaussianDiffusionModel(nn.Module):
         """reference :143-155. UNet + x0 reconstruction + clamp + posterior mean run in one fused kernel chain."""
         if context is not None:
             raise NotImplementedError("context conditioning is not on the guided-sampling path")
-        model_mean = self._engine().p_mean(x, t)
+        model_mean = self._engine(x.shape[1]).p_mean(x, t)
         posterior_variance = extract(self.posterior_variance, t, x.shape)
         posterior_log_variance = extract(self.posterior_log_variance_clipped, t, x.shape)
         return model_mean, posterior_variance, posterior_log_variance
@@ -393,7 +439,9 @@ class GaussianDiffusionModel(nn.Module):
                              scale_grad_by_std=False, t_start_guide=torch.inf, noise_std_extra_schedule_fn=None,
                              debug=False, noise=None, **kwargs):
         device = self.betas.device
-        eng = self._engine()
+        if len(shape) != 3 or shape[2] != self.state_dim:
+            raise RuntimeError(f"expected shape (batch, horizon, {self.state_dim}), got {tuple(shape)}")
+        eng = self._engine(shape[1])
         steps = list(reversed(range(-n_extra, self.n_diffusion_steps)))
         if (noise is None and self.use_cuda_graph and self.__dict__.get("graph_rng", True)
                 and not torch.cuda.is_current_stream_capturing()):
@@ -512,51 +560,69 @@ class GaussianDiffusionModel(nn.Module):
             return x_out.clone(), chain.transpose(0, 1).clone()
         return x_out.clone()
 
+    def ddim_schedule(self):
+        """The (time, time_next) pairs of `ddim_sample` and the two coefficients of each update, computed with the torch
+        expressions the reference evaluates per step (diffusion_model_base.py:196-209, :232-236; eta = 0) so that the fp32
+        values the device multiplies by are bit-identical: (times, times_next, sqrt(alpha_next), sqrt(1 - alpha_next - sigma^2))."""
+        total_timesteps, sampling_timesteps, eta = self.n_diffusion_steps, self.n_diffusion_steps // 5, 0.
+        times = torch.linspace(0, total_timesteps - 1, steps=sampling_timesteps + 1)
+        times = torch.cat((torch.tensor([-1]), times))
+        times = list(reversed(times.int().tolist()))
+        ac = self.alphas_cumprod.detach().cpu()
+        t_l, tn_l, sa_l, cn_l = [], [], [], []
+        for time, time_next in zip(times[:-1], times[1:]):
+            t_l.append(time)
+            tn_l.append(time_next)
+            if time_next < 0:
+                sa_l.append(1.0)
+                cn_l.append(0.0)
+                break
+            alpha, alpha_next = ac[time], ac[time_next]
+            sigma = eta * ((1 - alpha / alpha_next) * (1 - alpha_next) / (1 - alpha)).sqrt()
+            sa_l.append(float(alpha_next.sqrt()))
+            cn_l.append(float((1 - alpha_next - sigma ** 2).sqrt()))
+        return t_l, tn_l, sa_l, cn_l
+
     @torch.no_grad()
     def ddim_sample(self, shape, hard_conds, context=None, return_chain=False, t_start_guide=torch.inf, guide=None,
-                    n_guide_steps=1, **sample_kwargs):
-        """reference :184-259 (T/5 steps, eta = 0). UNet forward and guide steps are CUDA kernels; the few
-        per-step scalar combinations use torch elementwise ops exactly as the reference does."""
+                    n_guide_steps=1, noise=None, **sample_kwargs):
+        """reference :184-259 (T // 5 steps, eta = 0) as ONE C-ABI call (`mpdb_ddim_loop`): per time pair a UNet forward whose
+        last epilogue forms x_start / pred_noise and the DDIM update, then the guide evaluations when time_next <
+        t_start_guide, then the hard conditions; no host synchronisation inside.
+
+        As in the reference, the named argument `n_guide_steps` is NOT what the guide receives: `guide_gradient_steps` is
+        called with `**sample_kwargs` only (:240-245), i.e. one step unless the caller passes n_guide_steps there — which
+        Python routes to the named argument, so the reference always runs a single guide step per DDIM step; so does this.
+        The generator is consumed like the reference's: randn(shape), then one randn_like per step (multiplied by sigma = 0).
+        `noise` (optional, [B, H, D]) replaces the initial draw (parity tests)."""
         device = self.betas.device
-        batch_size = shape[0]
-        total_timesteps = self.n_diffusion_steps
-        sampling_timesteps = self.n_diffusion_steps // 5
-        eta = 0.
-        times = torch.linspace(0, total_timesteps - 1, steps=sampling_timesteps + 1, device=device)
-        times = torch.cat((torch.tensor([-1], device=device), times))
-        times = list(reversed(times.int().tolist()))
-        time_pairs = list(zip(times[:-1], times[1:]))
-        x = torch.randn(shape, device=device)
-        x = apply_hard_conditioning(x, hard_conds)
-        chain = [x] if return_chain else None
-        for time, time_next in time_pairs:
-            t = make_timesteps(batch_size, time, device)
-            t_next = make_timesteps(batch_size, time_next, device)
-            model_out = self.model(x, t, context)
-            x_start = self.predict_start_from_noise(x, t=t, noise=model_out)
-            pred_noise = self.predict_noise_from_start(x, t=t, x0=model_out)
-            if time_next < 0:
-                x = x_start
-                x = apply_hard_conditioning(x, hard_conds)
-                if return_chain:
-                    chain.append(x)
-                break
-            alpha = extract(self.alphas_cumprod, t, x.shape)
-            alpha_next = extract(self.alphas_cumprod, t_next, x.shape)
-            sigma = eta * ((1 - alpha / alpha_next) * (1 - alpha_next) / (1 - alpha)).sqrt()
-            c = (1 - alpha_next - sigma ** 2).sqrt()
-            x = x_start * alpha_next.sqrt() + c * pred_noise
-            if guide is not None:
-                if torch.all(t_next < t_start_guide):
-                    x = guide_gradient_steps(x, hard_conds=hard_conds, guide=guide, **sample_kwargs)
-            noise = torch.randn_like(x)
-            x = x + sigma * noise
-            x = apply_hard_conditioning(x, hard_conds)
-            if return_chain:
-                chain.append(x)
+        if device.type != "cuda":
+            raise RuntimeError("mpd_public_b200 has no CPU path: call .to('cuda') on the model first")
+        if context is not None:
+            raise NotImplementedError("context conditioning is not on the guided-sampling path")
+        if len(shape) != 3 or shape[2] != self.state_dim:
+            raise RuntimeError(f"expected shape (batch, horizon, {self.state_dim}), got {tuple(shape)}")
+        if guide is not None and not getattr(guide, "_mpdb_fusable", False):
+            raise NotImplementedError("ddim_sample runs with this package's GuideManagerTrajectoriesWithVelocity (or guide=None)")
+        if sample_kwargs.get("scale_grad_by_std", False):
+            raise NotImplementedError("ddim_sample passes no model_var to guide_gradient_steps (the reference would fail too)")
+        eng = self._engine(shape[1])
+        t_l, tn_l, sa_l, cn_l = self.ddim_schedule()
+        if noise is None:
+            x = torch.randn(shape, device=device)
+            scratch = torch.empty_like(x)
+            for tn in tn_l:
+                if tn >= 0:
+                    scratch.normal_()  # the reference's per-step randn_like (times sigma = 0)
+        else:
+            x = noise.to(device=device, dtype=torch.float32)
+            if tuple(x.shape) != tuple(shape):
+                raise RuntimeError(f"injected noise must have shape {tuple(shape)}")
+        handle = guide._handle(device, shape[1]) if guide is not None else None
+        x, chain = eng.ddim_loop(x, hard_conds, handle, t_l, tn_l, sa_l, cn_l, float(t_start_guide),
+                                 1 if guide is not None else 0, return_chain)
         if return_chain:
-            chain = torch.stack(chain, dim=1)
-            return x, chain
+            return x, chain.transpose(0, 1)  # [B, steps + 1, H, D] like torch.stack(chain, dim=1)
         return x
 
     @torch.no_grad()

@@ -15,12 +15,13 @@ import torch
 import torch.nn as nn
 
 from . import _lib
-from .costs import CostCollision, CostComposite, CostGPTrajectory, GridSDFField, WorkspaceBoundaryField
+from .costs import (CostCollision, CostComposite, CostGPTrajectory, GridSDFField, SelfCollisionField,
+                    WorkspaceBoundaryField)
 
 
-def build_guide_config(robot, mins, maxs, collision_fields, gp, cutoff_margin, clip_grad, max_grad_norm, n_interp):
-    """mpdb_guide_config from a robot description, normaliser limits, [(field, weight)] and (dt, sigma_gp, weight) | None.
-    Returns (cfg, tensors kept alive because the config references them by raw pointer)."""
+def build_guide_config(robot, mins, maxs, collision_costs, gp, clip_grad, max_grad_norm, n_interp, vel_from_fd=False):
+    """mpdb_guide_config from a robot description, normaliser limits, [(field, weight, cutoff margin, sigma_coll)] and
+    (dt, sigma_gp, weight) | None. Returns (cfg, tensors kept alive because the config references them by raw pointer)."""
     cfg = _lib.GuideConfig()
     cfg.robot_kind = 1 if robot.kind == "panda" else 0
     cfg.q_dim, cfg.ws_dim, cfg.n_spheres = robot.q_dim, robot.ws_dim, robot.n_spheres
@@ -38,21 +39,22 @@ def build_guide_config(robot, mins, maxs, collision_fields, gp, cutoff_margin, c
         cfg.mins[i], cfg.maxs[i] = float(mins[i]), float(maxs[i])
     keep = []
     n_grid = 0
-    cfg.has_border = 0
-    for f, w in collision_fields:
+    cfg.has_border = cfg.has_self = 0
+    order = []  # position of every cost in the kernel's order (grids, border, self): the reference sums them in list order
+    for f, w, margin, sigma in collision_costs:
         if isinstance(f, GridSDFField):
             if n_grid >= _lib.MAX_GRID_FIELDS:
                 raise RuntimeError(f"at most {_lib.MAX_GRID_FIELDS} grid-backed collision fields")
-            if n_grid == 0:
-                for k in range(f.dim):
-                    cfg.grid_shape[k] = f.shape[k]
-                    cfg.grid_lo[k] = float(f.limits[0][k])
-                cfg.grid_cell = f.cell
-            elif tuple(cfg.grid_shape[:f.dim]) != f.shape or abs(cfg.grid_cell - f.cell) > 1e-6 * abs(f.cell):
-                raise NotImplementedError("all grid fields must share one lattice")
+            if f.dim != robot.ws_dim:
+                raise RuntimeError("grid field and robot disagree on the workspace dimension")
+            for k in range(f.dim):
+                cfg.grid_shape[n_grid][k] = f.shape[k]
+                cfg.grid_lo[n_grid][k] = float(f.limits[0][k])
+            cfg.grid_cell[n_grid] = f.cell
             cfg.grid_texels[n_grid] = f.texels.data_ptr()
-            cfg.weight_grid[n_grid] = float(w)
+            cfg.weight_grid[n_grid], cfg.margin_grid[n_grid], cfg.sigma_grid[n_grid] = float(w), float(margin), float(sigma)
             keep.append(f.texels)
+            order.append(("grid", n_grid))
             n_grid += 1
         elif isinstance(f, WorkspaceBoundaryField):
             if cfg.has_border:
@@ -60,20 +62,36 @@ def build_guide_config(robot, mins, maxs, collision_fields, gp, cutoff_margin, c
             cfg.has_border = 1
             for k in range(f.limits.shape[1]):
                 cfg.border_lo[k], cfg.border_hi[k] = float(f.limits[0][k]), float(f.limits[1][k])
-            cfg.weight_border = float(w)
+            cfg.weight_border, cfg.margin_border, cfg.sigma_border = float(w), float(margin), float(sigma)
+            order.append(("border", 0))
+        elif isinstance(f, SelfCollisionField):
+            if cfg.has_self:
+                raise NotImplementedError("one self-collision field")
+            if robot.kind != "panda":
+                continue  # a point mass has nothing to collide with
+            cfg.has_self = 1
+            for a, m in enumerate(f.pair_masks(robot.n_spheres)):
+                cfg.self_pairs[a] = m
+            cfg.weight_self, cfg.margin_self, cfg.sigma_self = float(w), float(margin), float(sigma)
+            order.append(("self", 0))
         else:
             raise NotImplementedError(f"unsupported field {type(f).__name__}")
+    # the kernel adds the weighted cost gradients as grids, border, self; fp32 addition is not associative, so a composite
+    # listing them in another order is refused rather than silently summed differently from the reference's list order
+    rank = {"grid": 0, "border": 1, "self": 2}
+    if [rank[k] for k, _ in order] != sorted(rank[k] for k, _ in order):
+        raise NotImplementedError("collision costs must be listed as: grid-backed fields, workspace boundary, self-collision")
     cfg.n_grid_fields = n_grid
-    cfg.cutoff_margin = float(cutoff_margin)
     if gp is not None:
         cfg.use_gp = 1
         cfg.dt, cfg.sigma_gp, cfg.weight_gp = float(gp[0]), float(gp[1]), float(gp[2])
     else:
         cfg.use_gp = 0
-        cfg.dt, cfg.sigma_gp = 1.0, 1.0
+        cfg.dt, cfg.sigma_gp = float(getattr(robot, "dt", 0.0) or 1.0), 1.0
     cfg.clip_grad = int(bool(clip_grad))
     cfg.max_grad_norm = float(max_grad_norm)
     cfg.n_interp = int(n_interp)
+    cfg.vel_from_fd = int(bool(vel_from_fd))
     return cfg, keep
 
 
@@ -108,8 +126,10 @@ class GuideManagerTrajectories(nn.Module):
     `guide(x_pos_normalized [B,H,q]) -> grad [B,H,q]`; each call also moves `self.velocity` against the costs' velocity
     gradients (guides.py:110-112). One CUDA kernel (csrc/guide.cu, position-only mode): unnormalise the positions,
     interpolate, composite cost on [positions | velocity], per cost clip the position and the velocity gradient separately
-    (norm + 1e-6), zero the end rows, weight, negate. `use_velocity_from_finite_difference=True` needs torch_robotics'
-    `robot.get_velocity` for position-only states (source absent) and is not implemented."""
+    (norm + 1e-6), zero the end rows, weight, negate. With `use_velocity_from_finite_difference=True` (guides.py:77-79) the
+    velocity half of the state is `robot.get_velocity(x_pos)` — torch_robotics' source is absent; restated as the central
+    difference (p[h+1] - p[h-1]) / (2 dt) with zero end rows (oracle switch FD_CENTRAL, parity unpinned) — the costs reach the
+    positions through it as well, a single position gradient is clipped per cost and the velocity trajectory is left alone."""
     _mpdb_fusable = False  # stateful (velocity): the reverse loop calls it step by step, as the reference does
 
     def __init__(self, dataset, cost, clip_grad=False, clip_grad_rule='norm', max_grad_norm=1., max_grad_value=0.1,
@@ -121,9 +141,6 @@ class GuideManagerTrajectories(nn.Module):
             raise NotImplementedError("cost must be a mpd_public_b200.CostComposite")
         if clip_grad and clip_grad_rule != 'norm':
             raise NotImplementedError("only clip_grad_rule='norm' is implemented (guides.py:127)")
-        if use_velocity_from_finite_difference:
-            raise NotImplementedError("use_velocity_from_finite_difference needs torch_robotics' robot.get_velocity "
-                                      "for position-only states (source absent from the reference tree)")
         if start_state_pos is None or goal_state_pos is None:
             raise RuntimeError("start_state_pos and goal_state_pos are required (guides.py:46-53)")
         self.cost = cost
@@ -151,8 +168,8 @@ class GuideManagerTrajectories(nn.Module):
 
     def __del__(self):
         try:
-            for handle, _, _ in self._handles.values():
-                _lib.lib().mpdb_guide_destroy(handle)
+            for h in self._handles.values():
+                _lib.lib().mpdb_guide_destroy(h[0])
             self._handles = {}
         except Exception:
             pass
@@ -163,10 +180,14 @@ class GuideManagerTrajectories(nn.Module):
         B, H, q = x.shape
         if q != self.robot.q_dim:
             raise RuntimeError(f"expected position-only trajectories [B, H, {self.robot.q_dim}], got {tuple(x.shape)}")
+        grad = torch.empty_like(x)
+        if self.use_velocity_from_finite_difference:
+            _lib.check(_lib.lib().mpdb_guide_grad_pos(self._handle(x.device, H), _lib.fptr(x), None, _lib.fptr(grad), B, H,
+                                                      _lib.stream_ptr(x.device)))
+            return grad
         if tuple(self.velocity.shape) != (B, H, q) or self.velocity.device != x.device:
             raise RuntimeError(f"velocity trajectory is {tuple(self.velocity.shape)} on {self.velocity.device}; the guide was "
                                f"built for n_samples={self.velocity.shape[0]}, num_steps={self.velocity.shape[1] - 1}")
-        grad = torch.empty_like(x)
         _lib.check(_lib.lib().mpdb_guide_grad_pos(self._handle(x.device, H), _lib.fptr(x), _lib.fptr(self.velocity),
                                                   _lib.fptr(grad), B, H, _lib.stream_ptr(x.device)))
         return grad
@@ -195,27 +216,40 @@ class GuideManagerTrajectoriesWithVelocity(nn.Module):
         self._handles = {}
 
     # ---- C-ABI handle ----
+    def _signature(self):
+        """Everything the device-side configuration is built from, cheap to compare: the reference re-reads these attributes
+        on every call, so a handle built from older values must not be reused (weights, clip settings, limits, ...)."""
+        mins_t = self.dataset.normalizer
+        if hasattr(mins_t, "normalizers"):
+            mins_t = mins_t.normalizers[self.dataset.field_key_traj]
+        costs = tuple((id(c), getattr(c, "sigma_coll", None), getattr(c, "cutoff_margin", None), getattr(c, "dt", None),
+                       getattr(c, "sigma_gp", None)) for c in self.cost.cost_l)
+        return (costs, tuple(float(w) for w in self.cost.weights_cost_l), bool(self.clip_grad), float(self.max_grad_norm),
+                bool(self.interpolate_trajectories_for_collision), int(self.num_interpolated_points_for_collision),
+                mins_t.mins.data_ptr(), mins_t.mins._version, mins_t.maxs.data_ptr(), mins_t.maxs._version,
+                bool(getattr(self, "use_velocity_from_finite_difference", False)), float(getattr(self.cost.robot, "dt", 0.0) or 0.0))
+
     def _config(self, H):
         mins, maxs = _dataset_limits(self.dataset)
         coll, gp = [], None
-        margin = None
         for c, w in zip(self.cost.cost_l, self.cost.weights_cost_l):
             if isinstance(c, CostCollision):
-                coll.append((c.field, float(w)))
-                m = getattr(c, "cutoff_margin", None)
-                m = float(getattr(c.robot, "cutoff_margin", 0.05)) if m is None else float(m)
-                margin = m if margin is None else margin
+                coll.append((c.field, float(w), c.cutoff_margin, c.sigma_coll))
             elif isinstance(c, CostGPTrajectory):
                 gp = (c.dt, c.sigma_gp, float(w))
         n_interp = int(self.num_interpolated_points_for_collision) if self.interpolate_trajectories_for_collision else int(H)
-        return build_guide_config(self.cost.robot, mins, maxs, coll, gp, 0.05 if margin is None else margin,
-                                  self.clip_grad, self.max_grad_norm, n_interp)
+        return build_guide_config(self.cost.robot, mins, maxs, coll, gp, self.clip_grad, self.max_grad_norm, n_interp,
+                                  vel_from_fd=getattr(self, "use_velocity_from_finite_difference", False))
 
     def _handle(self, device, H):
         device = torch.device(device)
         idx = device.index if device.index is not None else torch.cuda.current_device()
         key = (idx, int(H))
+        sig = self._signature()
         h = self._handles.get(key)
+        if h is not None and h[3] != sig:  # an attribute changed since the handle was built: rebuild (captured graphs are
+            _lib.lib().mpdb_guide_destroy(h[0])  # keyed on the handle value + the config hash, so they are re-captured too)
+            h = None
         if h is None:
             cfg, keep = self._config(H)
             for t in keep:
@@ -223,14 +257,41 @@ class GuideManagerTrajectoriesWithVelocity(nn.Module):
                     raise RuntimeError("collision grids live on a different device than the trajectories")
             handle = C.c_void_p()
             _lib.check(_lib.lib().mpdb_guide_create(C.byref(cfg), idx, C.byref(handle)))
-            h = (handle, keep, cfg)
+            h = (handle, keep, cfg, sig)
             self._handles[key] = h
         return h[0]
 
+    def batch_dependent_clamps(self, reset=False):
+        """(trajectory, evaluation) pairs, over all handles of this guide, whose normaliser clamp was decided by other
+        trajectories of the batch (normalization.py:160-162 looks at the whole tensor). 0 = results so far do not depend
+        on the batch composition, i.e. any sharding of the batch reproduces them bit for bit."""
+        return sum(int(_lib.lib().mpdb_guide_batch_dependent_clamps(h[0], int(bool(reset)))) for h in self._handles.values())
+
+    # ---- parity instrumentation: the discrete decisions (texel index, hinge / wall / pair activity) of every evaluation ----
+    def record_decisions(self, device, H, B, capacity_evals):
+        """Starts recording into a fresh int32 buffer [capacity_evals, B, n_costs, n_interp, n_spheres]; returns it. Loops run
+        without CUDA graphs while recording. `stop_recording` ends it."""
+        handle = self._handle(device, H)
+        cfg = self._handles[(torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device(), int(H))][2]
+        n_costs = int(_lib.lib().mpdb_guide_num_collision_costs(handle))
+        buf = torch.zeros((int(capacity_evals), int(B), n_costs, int(cfg.n_interp), int(cfg.n_spheres)), device=device, dtype=torch.int32)
+        _lib.check(_lib.lib().mpdb_guide_record_decisions(handle, C.c_void_p(buf.data_ptr()), int(capacity_evals), int(B)))
+        self._recording = (handle, buf)
+        return buf
+
+    def decisions_recorded(self):
+        return int(_lib.lib().mpdb_guide_decisions_recorded(self._recording[0])) if getattr(self, "_recording", None) else 0
+
+    def stop_recording(self):
+        rec = getattr(self, "_recording", None)
+        if rec is not None:
+            _lib.check(_lib.lib().mpdb_guide_record_decisions(rec[0], None, 0, 0))
+            self._recording = None
+
     def __del__(self):
         try:
-            for handle, _, _ in self._handles.values():
-                _lib.lib().mpdb_guide_destroy(handle)
+            for h in self._handles.values():
+                _lib.lib().mpdb_guide_destroy(h[0])
             self._handles = {}
         except Exception:
             pass
@@ -245,11 +306,13 @@ class GuideManagerTrajectoriesWithVelocity(nn.Module):
                                               _lib.stream_ptr(x.device)))
         return grad
 
-    def guide_steps(self, x, hard_conds, n_guide_steps, model_var=None):
-        """n x {x <- x + guide(x) [* model_var]; hard conditioning} as n kernel launches; returns a new tensor."""
+    def guide_steps(self, x, hard_conds, n_guide_steps, model_var=None, return_chain=False):
+        """n x {x <- x + guide(x) [* model_var]; hard conditioning} as n kernel launches; returns a new tensor — with
+        `return_chain` also every iterate [n, B, H, D] (the diffusion_prior_then_guide post-loop, inference.py:263-282)."""
         _lib.require_cuda(x, "x")
         x = x.detach().to(torch.float32).clone(memory_format=torch.contiguous_format)
         B, H, D = x.shape
+        chain = torch.empty((int(n_guide_steps), B, H, D), device=x.device, dtype=torch.float32) if return_chain else None
         rows = list(hard_conds.keys())
         hc_rows = (C.c_int32 * max(len(rows), 1))(*[int(r) % H for r in rows])
         hc = torch.stack([hard_conds[r].to(device=x.device, dtype=torch.float32).expand(B, D) for r in rows]).contiguous() \
@@ -257,10 +320,11 @@ class GuideManagerTrajectoriesWithVelocity(nn.Module):
         mv = None
         if model_var is not None:
             mv = model_var.to(device=x.device, dtype=torch.float32).reshape(-1).expand(B).contiguous()
-        _lib.check(_lib.lib().mpdb_guide_steps(
+        _lib.check(_lib.lib().mpdb_guide_steps_chain(
             self._handle(x.device, H), _lib.fptr(x), int(n_guide_steps), _lib.fptr(mv) if mv is not None else None,
-            len(rows), hc_rows, _lib.fptr(hc) if hc is not None else None, B, H, _lib.stream_ptr(x.device)))
-        return x
+            len(rows), hc_rows, _lib.fptr(hc) if hc is not None else None,
+            _lib.fptr(chain) if chain is not None and chain.numel() else None, B * H * D, B, H, _lib.stream_ptr(x.device)))
+        return (x, chain) if return_chain else x
 
     def clip_gradient(self, grad):
         if self.clip_grad:
@@ -278,5 +342,6 @@ class GuideManagerTrajectoriesWithVelocity(nn.Module):
         return grad
 
 
+GuideManagerTrajectories._signature = GuideManagerTrajectoriesWithVelocity._signature
 GuideManagerTrajectories._config = GuideManagerTrajectoriesWithVelocity._config
 GuideManagerTrajectories._handle = GuideManagerTrajectoriesWithVelocity._handle

@@ -9,7 +9,7 @@ import numpy as np
 import torch
 
 from . import synthetic as S
-from .costs import GridSDFField, WorkspaceBoundaryField
+from .costs import GridSDFField, SelfCollisionField, WorkspaceBoundaryField
 from .normalization import DatasetNormalizer, LimitsNormalizer
 
 
@@ -32,14 +32,18 @@ class Robot:
 
 
 class PlanningTask:
-    def __init__(self, env: S.EnvSpec, robot: Robot, device, obstacle_cutoff_margin=0.05, use_extra_objects=True):
+    def __init__(self, env: S.EnvSpec, robot: Robot, device, obstacle_cutoff_margin=0.05, use_extra_objects=True,
+                 use_self_collision=True, self_collision_margin=0.05):
         self.env, self.robot, self.device = env, robot, torch.device(device)
         robot.cutoff_margin = obstacle_cutoff_margin
         self.use_extra_objects = use_extra_objects
+        self.use_self_collision = use_self_collision
+        self.self_collision_margin = self_collision_margin
         self._fields = None
 
     def get_collision_fields(self):
-        """[objects grid, (extra objects grid), workspace boundaries] — inference.py:193 (Appendix C.4)."""
+        """[objects grid, (extra objects grid), workspace boundaries, (robot self-collision: articulated robots only)] —
+        inference.py:193."""
         if self._fields is None:
             e = self.env
             f = [GridSDFField.from_primitives(e.limits, e.cell, e.grid_shape, e.spheres, e.boxes, self.device)]
@@ -47,11 +51,13 @@ class PlanningTask:
                 f.append(GridSDFField.from_primitives(e.limits, e.cell, e.grid_shape, e.extra_spheres, e.extra_boxes,
                                                       self.device))
             f.append(WorkspaceBoundaryField(e.limits))
+            if self.use_self_collision and self.robot.kind == "panda":
+                f.append(SelfCollisionField(self.robot, cutoff_margin=self.self_collision_margin))
             self._fields = f
         return self._fields
 
     def get_collision_fields_extra_objects(self):
-        return self.get_collision_fields()[1:-1]
+        return [f for f in self.get_collision_fields()[1:] if isinstance(f, GridSDFField)]
 
     # ---- post-sampling evaluation (reference inference.py:288-326; torch_robotics PlanningTask, sources absent) ----
     def evaluate_trajectories(self, trajs, margin=0.0, n_interp=128):
@@ -68,8 +74,9 @@ class PlanningTask:
         cache = self.__dict__.setdefault("_eval_handles", {})
         if key not in cache:
             zeros = np.zeros(2 * self.robot.q_dim, dtype=np.float32)
-            cfg, keep = build_guide_config(self.robot, zeros, zeros + 1, [(f, 1.0) for f in self.get_collision_fields()], None,
-                                           0.0, False, 1.0, n_interp)
+            fields = [f for f in self.get_collision_fields() if not isinstance(f, SelfCollisionField)]
+            cfg, keep = build_guide_config(self.robot, zeros, zeros + 1, [(f, 1.0, 0.0, 1.0) for f in fields], None, False, 1.0,
+                                           n_interp)
             handle = C.c_void_p()
             _lib.check(_lib.lib().mpdb_guide_create(C.byref(cfg), idx, C.byref(handle)))
             cache[key] = (handle, keep)
@@ -131,14 +138,15 @@ class TrajectoryDataset:
     field_key_traj = 'traj'
 
     def __init__(self, problem: S.ProblemSpec, device, include_velocity=True, use_extra_objects=True,
-                 obstacle_cutoff_margin=0.05, **kwargs):
+                 obstacle_cutoff_margin=0.05, use_self_collision=True, **kwargs):
         self.problem = problem
         self.device = torch.device(device)
         self.include_velocity = include_velocity
         self.n_support_points = problem.n_support_points
         self.robot = Robot(problem.robot, obstacle_cutoff_margin)
         self.env = problem.env
-        self.task = PlanningTask(problem.env, self.robot, device, obstacle_cutoff_margin, use_extra_objects)
+        self.task = PlanningTask(problem.env, self.robot, device, obstacle_cutoff_margin, use_extra_objects,
+                                 use_self_collision=use_self_collision)
         self.state_dim = problem.robot.state_dim if include_velocity else problem.robot.q_dim
         self.threshold_start_goal_pos = 1.83 if problem.robot.kind == "panda" else 1.0
         # position-only datasets (include_velocity=False, trajectories.py:60-70) normalise the q positions only

@@ -49,7 +49,7 @@ def ddpm_sample_fn(model, x, hard_conds, context, t, guide=None, n_guide_steps=1
         noise_std = noise_std_extra_schedule_fn(t_single)
 
     values = None
-    x = model._engine().add_noise_(x if x.is_contiguous() else x.contiguous(), t, noise, float(noise_std))
+    x = model._engine(x.shape[1]).add_noise_(x if x.is_contiguous() else x.contiguous(), t, noise, float(noise_std))
     return x, values
 
 

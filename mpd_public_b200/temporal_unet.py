@@ -72,5 +72,7 @@ class TemporalUnet(nn.Module):
         _lib.require_cuda(x, "x")
         if context is not None:
             raise NotImplementedError("context conditioning is not on the guided-sampling path")
-        eng = _engine_for_unet(self, x.device)
+        if x.dim() != 3:
+            raise RuntimeError(f"expected x of shape [batch, horizon, {self.state_dim}], got {tuple(x.shape)}")
+        eng = _engine_for_unet(self, x.device, horizon=x.shape[1])  # fully convolutional: one device plan per horizon
         return eng.unet_forward(x, time)

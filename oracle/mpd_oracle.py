@@ -38,6 +38,23 @@ import torch.nn.functional as F
 # ------------------------------------------------------------------------------------------------
 SWITCH_C3_COLLISION_ON_INTERPOLATED = True   # C3: collision costs see the interpolated trajectory
 SWITCH_C5_NEAREST_CELL = True                # C5: nearest-cell lookup, gradient from the stored texel
+SWITCH_C4_SELF_SUM_OVER_PAIRS = True         # C4: self-collision cost = sum over listed sphere pairs of the hinge (not a min)
+SWITCH_FD_CENTRAL = True                     # robot.get_velocity(x_pos) of a position-only trajectory = central difference, zero end rows
+
+# Panda kinematic chain — SURVEY Appendix E (public Franka URDF values), written out HERE and not imported from the product
+# (`mpd_public_b200.synthetic` holds its own copy; tests/test_host_cpu.py compares the two and checks both against the known
+# flange pose of the zero configuration), so a wrong joint origin cannot pass on both sides unnoticed.
+PANDA_JOINT_XYZ = (
+    (0.0, 0.0, 0.333),       # J1
+    (0.0, 0.0, 0.0),         # J2
+    (0.0, -0.316, 0.0),      # J3
+    (0.0825, 0.0, 0.0),      # J4
+    (-0.0825, 0.384, 0.0),   # J5
+    (0.0, 0.0, 0.0),         # J6
+    (0.088, 0.0, 0.0),       # J7
+)
+PANDA_JOINT_ROLL = (0.0, -math.pi / 2, math.pi / 2, math.pi / 2, -math.pi / 2, math.pi / 2, math.pi / 2)
+PANDA_FLANGE_XYZ = (0.0, 0.0, 0.107)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -218,8 +235,7 @@ def sphere_centers(robot, q):
     """C2/E1: world positions of the robot's collision spheres, [..., S, ws_dim]."""
     if robot.kind == "pointmass":
         return q[..., None, :]
-    from mpd_public_b200 import synthetic as S
-    o, R = panda_frames(q, S.PANDA_JOINT_XYZ, S.PANDA_JOINT_ROLL, S.PANDA_FLANGE_XYZ)
+    o, R = panda_frames(q, PANDA_JOINT_XYZ, PANDA_JOINT_ROLL, PANDA_FLANGE_XYZ)
     f = torch.as_tensor(robot.sphere_frame.astype(np.int64) - 1)
     off = torch.as_tensor(robot.sphere_offset, dtype=q.dtype)
     return o[..., f, :] + torch.einsum("...sij,sj->...si", R[..., f, :, :], off)
@@ -283,13 +299,23 @@ class GridSDF:
         tex = torch.cat([torch.cat(vals)[:, None], torch.cat(grads)], dim=1).to(torch.float32)
         return cls(limits, cell, tex, shape)
 
-    def __call__(self, p):
-        """sdf(p) with value from the nearest node and gradient = stored texel (surrogate)."""
-        tex = self.texels.to(p.dtype)
-        idx = torch.round((p.detach() - self.lo.to(p.dtype)) / torch.as_tensor(self.cell, dtype=p.dtype)).long()
+    def cell_coords(self, p):
+        """(p - lo) / cell, the quantity whose rounding picks the node"""
+        return (p.detach() - self.lo.to(p.dtype)) / torch.as_tensor(self.cell, dtype=p.dtype)
+
+    def flat_index(self, p):
+        idx = torch.round(self.cell_coords(p)).long()
         flat = torch.zeros(p.shape[:-1], dtype=torch.long)
         for d in range(self.dim):
             flat = flat * self.shape[d] + idx[..., d].clamp(0, self.shape[d] - 1)
+        return flat
+
+    def __call__(self, p, flat=None):
+        """sdf(p) with value from the nearest node and gradient = stored texel (surrogate). `flat`: node indices decided
+        elsewhere (parity instrumentation: the CUDA kernel's own choice), else the nearest node."""
+        tex = self.texels.to(p.dtype)
+        if flat is None:
+            flat = self.flat_index(p)
         t = tex[flat]
         return t[..., 0] + ((p - p.detach()) * t[..., 1:]).sum(-1)
 
@@ -301,11 +327,35 @@ def border_sdf(p, limits):
     return torch.minimum(p - lo, hi - p).min(dim=-1).values
 
 
-def collision_cost(sdf_fn, centers, radii, cutoff_margin):
-    """C4: sum over horizon rows and link spheres of relu(r + margin - sdf(p)); sigma_coll = 1."""
+def border_sdf_forced(p, limits, axis, low):
+    """border_sdf with the wall decided elsewhere: axis [...], low [...] bool (low wall = p - lo, else hi - p)"""
+    lo = torch.as_tensor(np.asarray(limits)[0], dtype=p.dtype)
+    hi = torch.as_tensor(np.asarray(limits)[1], dtype=p.dtype)
+    pa = torch.gather(p, -1, axis[..., None])[..., 0]
+    return torch.where(low, pa - lo[axis], hi[axis] - pa)
+
+
+def collision_cost(sdf_fn, centers, radii, cutoff_margin, sigma_coll=1.0, active=None):
+    """C4: sum over horizon rows and link spheres of relu(r + margin - sdf(p)) / sigma_coll^2. `active` (bool, same shape as
+    the hinge argument): hinge branches decided elsewhere (parity instrumentation) instead of by the sign."""
     d = sdf_fn(centers)
     r = torch.as_tensor(radii, dtype=centers.dtype)
-    return torch.relu(r + cutoff_margin - d).sum(dim=(-1, -2))
+    v = r + cutoff_margin - d
+    h = torch.relu(v) if active is None else torch.where(active, v, torch.zeros_like(v))
+    return h.sum(dim=(-1, -2)) / (sigma_coll ** 2)
+
+
+def self_collision_cost(centers, radii, pairs, margin, sigma_coll=1.0, active=None):
+    """C4 (restated, unpinned): sum over rows and listed sphere pairs (a, b) of relu(margin - (|c_a - c_b| - r_a - r_b)).
+    `active`: [..., rows, n_pairs] bool, hinge branches decided elsewhere. Returns (cost, hinge argument [..., rows, n_pairs])."""
+    r = torch.as_tensor(radii, dtype=centers.dtype)
+    a = torch.as_tensor([p[0] for p in pairs], dtype=torch.long)
+    b = torch.as_tensor([p[1] for p in pairs], dtype=torch.long)
+    diff = centers[..., a, :] - centers[..., b, :]
+    n = torch.sqrt((diff * diff).sum(-1))
+    v = margin - (n - r[a] - r[b])
+    h = torch.relu(v) if active is None else torch.where(active, v, torch.zeros_like(v))
+    return h.sum(dim=(-1, -2)) / (sigma_coll ** 2), v
 
 
 def gp_cost(x, q_dim, dt, sigma_gp=1.0):
@@ -335,21 +385,82 @@ class GuideSpec:
     max_grad_norm: float = 1.0
     n_interp: int = 128
     interpolate: bool = True
+    self_pairs: object = None     # list of (a, b) sphere pairs of the self-collision field, or None
+    self_margin: float = 0.05
+    sigma_coll: float = 1.0
 
 
-def composite_costs(spec: GuideSpec, x, x_interp):
-    """C3: CostComposite(trajs, x_interpolated=..., return_invidual_costs_and_weights=True)."""
+def n_collision_costs(spec: GuideSpec):
+    return len(spec.grid_fields) + (spec.border_limits is not None) + (spec.self_pairs is not None and spec.robot.kind == "panda")
+
+
+def decode_decisions(spec: GuideSpec, dec):
+    """int32 [B, n_costs, NI, S] as recorded by the CUDA guide (include/mpdb200.h, mpdb_guide_record_decisions) ->
+    list per cost of dicts: grid {flat, active}; border {axis, low, active}; self {active [B, NI, n_pairs]}."""
+    dec = torch.as_tensor(dec).long()
+    out, k = [], 0
+    for _ in spec.grid_fields:
+        out.append({"flat": dec[:, k] >> 1, "active": (dec[:, k] & 1).bool()})
+        k += 1
+    if spec.border_limits is not None:
+        out.append({"axis": dec[:, k] >> 2, "low": ((dec[:, k] >> 1) & 1).bool(), "active": (dec[:, k] & 1).bool()})
+        k += 1
+    if spec.self_pairs is not None and spec.robot.kind == "panda":
+        a = torch.as_tensor([p[0] for p in spec.self_pairs], dtype=torch.long)
+        b = torch.as_tensor([p[1] for p in spec.self_pairs], dtype=torch.long)
+        m = dec[:, k]                                                   # [B, NI, S] partner masks
+        act_ab = ((m[..., a] >> b) & 1).bool()                          # [B, NI, n_pairs]: a sees b active
+        act_ba = ((m[..., b] >> a) & 1).bool()
+        out.append({"active": act_ab, "active_sym": act_ba})
+        k += 1
+    return out
+
+
+def composite_costs(spec: GuideSpec, x, x_interp, decisions=None, report=None):
+    """C3: CostComposite(trajs, x_interpolated=..., return_invidual_costs_and_weights=True).
+    `decisions` (decode_decisions output): discrete choices taken from the CUDA kernel instead of made here.
+    `report` (list): receives per cost the quantities whose sign / rounding makes those choices."""
     q = spec.robot.q_dim
     xs = x_interp if SWITCH_C3_COLLISION_ON_INTERPOLATED else x
     centers = sphere_centers(spec.robot, xs[..., :q])
+    r = torch.as_tensor(spec.robot.sphere_radius, dtype=centers.dtype)
     costs, weights = [], []
+    k = 0
     for g in spec.grid_fields:
-        costs.append(collision_cost(g, centers, spec.robot.sphere_radius, spec.cutoff_margin))
+        d = decisions[k] if decisions is not None else None
+        fn = (lambda p, g=g, d=d: g(p, flat=d["flat"])) if d is not None else g
+        costs.append(collision_cost(fn, centers, spec.robot.sphere_radius, spec.cutoff_margin, spec.sigma_coll,
+                                    d["active"] if d is not None else None))
+        if report is not None:
+            with torch.no_grad():
+                cc = g.cell_coords(centers)
+                report.append({"kind": "grid", "flat": g.flat_index(centers), "round_dist": 0.5 - (cc - torch.round(cc)).abs().amax(-1),
+                               "hinge": r + spec.cutoff_margin - g(centers), "cell_coords": cc})
         weights.append(spec.weight_collision)
+        k += 1
     if spec.border_limits is not None:
-        costs.append(collision_cost(lambda p: border_sdf(p, spec.border_limits), centers,
-                                    spec.robot.sphere_radius, spec.cutoff_margin))
+        d = decisions[k] if decisions is not None else None
+        fn = (lambda p, d=d: border_sdf_forced(p, spec.border_limits, d["axis"], d["low"])) if d is not None else \
+            (lambda p: border_sdf(p, spec.border_limits))
+        costs.append(collision_cost(fn, centers, spec.robot.sphere_radius, spec.cutoff_margin, spec.sigma_coll,
+                                    d["active"] if d is not None else None))
+        if report is not None:
+            with torch.no_grad():
+                lo = torch.as_tensor(np.asarray(spec.border_limits)[0], dtype=centers.dtype)
+                hi = torch.as_tensor(np.asarray(spec.border_limits)[1], dtype=centers.dtype)
+                walls = torch.cat((centers - lo, hi - centers), dim=-1)      # [.., 2 * dim]: low walls then high walls
+                report.append({"kind": "border", "walls": walls, "hinge": r + spec.cutoff_margin - border_sdf(centers, spec.border_limits)})
         weights.append(spec.weight_collision)
+        k += 1
+    if spec.self_pairs is not None and spec.robot.kind == "panda":
+        d = decisions[k] if decisions is not None else None
+        c, v = self_collision_cost(centers, spec.robot.sphere_radius, spec.self_pairs, spec.self_margin, spec.sigma_coll,
+                                   d["active"] if d is not None else None)
+        costs.append(c)
+        if report is not None:
+            report.append({"kind": "self", "hinge": v.detach()})
+        weights.append(spec.weight_collision)
+        k += 1
     costs.append(gp_cost(x, q, spec.dt, spec.sigma_gp))
     weights.append(spec.weight_smoothness)
     return costs, weights
@@ -361,14 +472,18 @@ def clip_grad_by_norm(grad, max_grad_norm):
     return torch.clip(n, 0.0, max_grad_norm) / n * grad
 
 
-def guide_manager_grad(spec: GuideSpec, x_normalized, return_parts=False):
-    """reference guides.py:173-211 — returns -sum_c w_c * zero_ends(clip(d cost_c / d x_unnormalized))."""
+def guide_manager_grad(spec: GuideSpec, x_normalized, return_parts=False, decisions=None, report=None):
+    """reference guides.py:173-211 — returns -sum_c w_c * zero_ends(clip(d cost_c / d x_unnormalized)).
+    `decisions`: int32 [B, n_costs, NI, S] recorded by the CUDA guide for this very evaluation — its texel / wall / hinge
+    choices are taken over, so that the comparison is exact away from AND at the discontinuities of the cost (the choices
+    themselves are audited separately, `audit_decisions`)."""
     x = x_normalized.clone()
     with torch.enable_grad():
         x.requires_grad_(True)
         x = limits_unnormalize(x, spec.mins.to(x.dtype), spec.maxs.to(x.dtype))
         x_interp = interpolate_points(x, spec.n_interp) if spec.interpolate else x
-        cost_l, w_l = composite_costs(spec, x, x_interp)
+        cost_l, w_l = composite_costs(spec, x, x_interp, decode_decisions(spec, decisions) if decisions is not None else None,
+                                      report)
         grad = 0
         parts = []
         for cost, w in zip(cost_l, w_l):
@@ -381,6 +496,61 @@ def guide_manager_grad(spec: GuideSpec, x_normalized, return_parts=False):
             grad = grad + w * g
     grad = -1.0 * grad
     return (grad, parts) if return_parts else grad
+
+
+def audit_decisions(spec: GuideSpec, x_normalized, decisions, cell_tol=2e-3, hinge_tol=2e-5):
+    """Are the CUDA guide's discrete decisions for this evaluation the oracle's own, except where the oracle's deciding
+    quantity sits on the boundary? Returns a dict of counts; `unexplained` must be 0:
+      * a texel index may differ only where some coordinate of (p - lo) / cell is within `cell_tol` of a rounding boundary,
+      * a wall may differ only where the two walls' distances agree within `hinge_tol`,
+      * a hinge branch (grid, border, self pair) may differ only where |hinge argument| <= `hinge_tol`
+        (or, for a grid field, where the texel itself differs for the reason above)."""
+    rep = []
+    with torch.no_grad():
+        pass
+    guide_manager_grad(spec, x_normalized, report=rep)
+    dec = decode_decisions(spec, decisions)
+    out = {"n": 0, "index_diff": 0, "hinge_diff": 0, "wall_diff": 0, "unexplained": 0}
+    for d, rp in zip(dec, rep):
+        if rp["kind"] == "grid":
+            idx_diff = d["flat"] != rp["flat"]
+            near = rp["round_dist"] <= cell_tol
+            out["index_diff"] += int(idx_diff.sum())
+            out["unexplained"] += int((idx_diff & ~near).sum())
+            own = rp["hinge"] > 0
+            hd = (d["active"] != own) & ~idx_diff
+            out["hinge_diff"] += int(hd.sum())
+            out["unexplained"] += int((hd & (rp["hinge"].abs() > hinge_tol)).sum())
+            out["n"] += d["flat"].numel()
+        elif rp["kind"] == "border":
+            walls = rp["walls"]
+            dim = walls.shape[-1] // 2
+            own = walls.argmin(-1)                                            # first minimum, low walls first
+            theirs = torch.where(d["low"], d["axis"], d["axis"] + dim)
+            wd = own != theirs
+            tie = (torch.gather(walls, -1, theirs[..., None])[..., 0] - walls.amin(-1)).abs() <= hinge_tol
+            out["wall_diff"] += int(wd.sum())
+            out["unexplained"] += int((wd & ~tie).sum())
+            hd = d["active"] != (rp["hinge"] > 0)
+            out["hinge_diff"] += int(hd.sum())
+            out["unexplained"] += int((hd & (rp["hinge"].abs() > hinge_tol)).sum())
+            out["n"] += own.numel()
+        else:
+            own = rp["hinge"] > 0
+            for act in (d["active"], d["active_sym"]):
+                hd = act != own
+                out["hinge_diff"] += int(hd.sum())
+                out["unexplained"] += int((hd & (rp["hinge"].abs() > hinge_tol)).sum())
+            out["n"] += own.numel()
+    return out
+
+
+def finite_difference_velocity(x_pos, dt):
+    """robot.get_velocity of a position-only trajectory (reference guides.py:78; torch_robotics source absent -> restated,
+    PARITY UNPINNED, switch FD_CENTRAL): central difference, zero at both ends."""
+    v = torch.zeros_like(x_pos)
+    v[..., 1:-1, :] = (x_pos[..., 2:, :] - x_pos[..., :-2, :]) / (2 * dt)
+    return v
 
 
 def const_vel_trajectory(start_pos, goal_pos, dt, num_steps, q_dim, set_initial_final_vel_to_zero=False, dtype=torch.float32):
@@ -397,6 +567,29 @@ def const_vel_trajectory(start_pos, goal_pos, dt, num_steps, q_dim, set_initial_
         traj[0, q_dim:] = 0.0
         traj[-1, q_dim:] = 0.0
     return traj
+
+
+def guide_manager_pos_grad_fd(spec: GuideSpec, x_pos_normalized):
+    """reference guides.py:60-118 with use_velocity_from_finite_difference=True: the velocity half of the state is
+    robot.get_velocity(x_pos) (restated: finite_difference_velocity), one gradient w.r.t. the positions per cost (the costs
+    reach them through the velocities as well), clipped, end rows zeroed, weighted; returns -grad_pos."""
+    q = spec.robot.q_dim
+    x_pos = x_pos_normalized.clone()
+    with torch.enable_grad():
+        x_pos.requires_grad_(True)
+        x_pos = limits_unnormalize(x_pos, spec.mins[:q].to(x_pos.dtype), spec.maxs[:q].to(x_pos.dtype))
+        x_interp = interpolate_points(x_pos, spec.n_interp) if spec.interpolate else x_pos
+        x_pos_vel = torch.cat((x_pos, finite_difference_velocity(x_pos, spec.dt)), dim=-1)
+        cost_l, w_l = composite_costs(spec, x_pos_vel, x_interp)
+        grad = 0
+        for cost, w in zip(cost_l, w_l):
+            g = torch.autograd.grad([cost.sum()], [x_pos], retain_graph=True)[0]
+            if spec.clip_grad:
+                g = clip_grad_by_norm(g, spec.max_grad_norm)
+            g[..., 0, :] = 0.0
+            g[..., -1, :] = 0.0
+            grad = grad + w * g
+    return -1.0 * grad
 
 
 def guide_manager_pos_grad(spec: GuideSpec, x_pos_normalized, velocity):
@@ -598,7 +791,17 @@ def build_grid_fields(problem, texels_list=None):
     return fields
 
 
-def make_guide_spec(problem, weight_collision, weight_smoothness, texels_list=None, n_interp=128, **kw) -> GuideSpec:
+def default_self_pairs(robot, min_frame_gap=4):
+    """every pair of collision spheres whose frames are at least four links apart (nearer frames of the Panda sit at fixed or nearly fixed distances: their hinge would be a constant)"""
+    fr = [int(f) for f in robot.sphere_frame]
+    n = len(fr)
+    return [(a, b) for a in range(n) for b in range(a + 1, n) if abs(fr[a] - fr[b]) >= min_frame_gap]
+
+
+def make_guide_spec(problem, weight_collision, weight_smoothness, texels_list=None, n_interp=128, self_collision=True,
+                    **kw) -> GuideSpec:
+    if self_collision and problem.robot.kind == "panda" and "self_pairs" not in kw:
+        kw["self_pairs"] = default_self_pairs(problem.robot)
     return GuideSpec(robot=problem.robot, mins=torch.as_tensor(problem.mins), maxs=torch.as_tensor(problem.maxs),
                      grid_fields=build_grid_fields(problem, texels_list), border_limits=problem.env.limits,
                      cutoff_margin=problem.cutoff_margin, dt=problem.dt, weight_collision=weight_collision,

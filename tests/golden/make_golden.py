@@ -190,7 +190,7 @@ def gen_pos_guide():
         prob = C.guide_problem(case)
         # GP prior only: the reference manager differentiates each cost once without retain_graph / allow_unused, so it runs
         # with a single cost that reads positions and velocities (see ref_shim.build_reference_pos_guide)
-        spec = dataclasses.replace(O.make_guide_spec(prob, wc, ws), grid_fields=[], border_limits=None)
+        spec = dataclasses.replace(O.make_guide_spec(prob, wc, ws), grid_fields=[], border_limits=None, self_pairs=None)
         h = prob.n_support_points
         guide = ref_shim.build_reference_pos_guide(spec, prob.start, prob.goal, prob.dt, h - 1, batch)
         out = {"velocity_init": guide.velocity.detach().numpy()}

@@ -181,7 +181,7 @@ def test_position_only_guide_manager(case):
     model_id, ucase, cell, wc, ws, batch = C.GUIDE_CASES[case]
     g = C.load(f"pos_guide_{case}")
     prob = C.guide_problem(case)
-    spec = dataclasses.replace(O.make_guide_spec(prob, wc, ws), grid_fields=[], border_limits=None)
+    spec = dataclasses.replace(O.make_guide_spec(prob, wc, ws), grid_fields=[], border_limits=None, self_pairs=None)
     q, h = prob.robot.q_dim, prob.n_support_points
     vel = O.const_vel_trajectory(prob.start, prob.goal, prob.dt, h - 1, q, set_initial_final_vel_to_zero=True)[:, q:]
     vel = vel[None].repeat(batch, 1, 1)
