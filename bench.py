@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py — trajectories/s of the full guided p_sample_loop (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg4|cfg2|cfg5]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg4|cfg2|cfg3|cfg5|cfg4_ddim]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
         bench.py --gpus N --steps K --warmup W
 
@@ -38,19 +38,29 @@ WORKLOADS = {
     # name: (model id, H, B per GPU, dim_mults option, w_collision, w_smoothness)   (BASELINE.json configs)
     "cfg4": ("EnvSpheres3D-RobotPanda", 64, 100, 1, 1e-2, 1e-7),
     "cfg2": ("EnvDense2D-RobotPointMass", 64, 100, 1, 3e-2, 1e-2),
+    # config 3: the collision / smoothness weight sweep: step k of a run uses weight pair k mod 9
+    "cfg3": ("EnvNarrowPassageDense2D-RobotPointMass", 64, 512, 1, 3e-2, 1e-2),
     "cfg5": ("EnvSpheres3D-RobotPanda", 128, 512, 1, 1e-2, 1e-7),
+    # DDIM sampler (diffusion_model_base.py:184-259, T // 5 steps) on the config-4 problem: SURVEY 8f.2
+    "cfg4_ddim": ("EnvSpheres3D-RobotPanda", 64, 100, 1, 1e-2, 1e-7),
 }
+CFG3_SWEEP = [(wc, ws) for wc in (1e-2, 3e-2, 1e-1) for ws in (1e-7, 1e-4, 1e-2)]
 T_DIFF, N_EXTRA, N_GUIDE, T_START_GUIDE, NOISE_STD, N_INTERP = 25, 5, 5, 7, 0.5, 128
 
 
 def workload_config(name, n_gpus):
     mid, H, B, opt, wc, ws = WORKLOADS[name]
-    return {"workload": f"{mid} H={H} B={B}/GPU guided p_sample_loop (T=25+5, n_guide_steps=5, t_start_guide=7, "
+    what = "guided p_sample_loop (T=25+5, n_guide_steps=5, t_start_guide=7, " if name != "cfg4_ddim" else \
+        "guided ddim_sample (T//5 = 5 steps + final, one guide step per DDIM step below t_start_guide=7, "
+    if name == "cfg3":
+        what = "weight sweep w_coll x w_smooth in {1e-2,3e-2,1e-1} x {1e-7,1e-4,1e-2} (step k uses pair k mod 9), " + what
+    return {"workload": f"{mid} H={H} B={B}/GPU {what}"
                         f"128 interp points, dim_mults option {opt})",
             "model_id": mid, "horizon": H, "batch_per_gpu": B, "global_batch": B * n_gpus,
             "parallelism": f"batch-sharded x{n_gpus}, one final all-gather" if n_gpus > 1 else "single GPU",
             "weights": "seeded synthetic (reference state-dict layout)", "l2_flush": "256 MiB memset between timed steps",
-            "precision": "fp32 end to end"}
+            "precision": "fp32 interface; UNet MMAs: fp16 operands, fp32 accumulate, 22-bit operand split (3 products) on the steps "
+                         "that amplify eps, one product where the schedule damps it (per-step parity 1e-3 vs the oracle, tested)"}
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -142,11 +152,13 @@ def algorithmic_work(H, D, opt, L_spheres, n_grid_fields, ws_dim):
     return flops, sdf_bytes
 
 
-def build_problem(name, device):
+def build_problem(name, device, weights_override=None):
     """Model + guide + hard conditions for a workload, the way inference.py:127-245 builds them."""
     import mpd_public_b200 as M
     from mpd_public_b200 import synthetic as S
     mid, H, B, opt, wc, ws = WORKLOADS[name]
+    if weights_override is not None:
+        wc, ws = weights_override
     prob = S.make_problem_by_id(mid, H)
     D = prob.robot.state_dim
     sd = S.make_unet_state_dict(0, D, 32, S.UNET_DIM_MULTS[opt])
@@ -159,15 +171,18 @@ def build_problem(name, device):
     ds = M.TrajectoryDataset(prob, device)
     robot = ds.robot
     fields = ds.task.get_collision_fields()
-    costs = [M.CostCollision(robot, H, field=f, sigma_coll=1.0) for f in fields]
-    weights = [wc] * len(costs)
-    costs.append(M.CostGPTrajectory(robot, H, prob.dt, sigma_gp=1.0))
-    weights.append(ws)
-    guide = M.GuideManagerTrajectoriesWithVelocity(ds, M.CostComposite(robot, H, costs, weights_cost_l=weights),
-                                                   clip_grad=True, interpolate_trajectories_for_collision=True,
-                                                   num_interpolated_points=int(np.ceil(H * 1.5)))  # swallowed, as upstream
+
+    def make_guide(wc_, ws_):
+        costs = [M.CostCollision(robot, H, field=f, sigma_coll=1.0) for f in fields]
+        weights = [wc_] * len(costs)
+        costs.append(M.CostGPTrajectory(robot, H, prob.dt, sigma_gp=1.0))
+        weights.append(ws_)
+        return M.GuideManagerTrajectoriesWithVelocity(ds, M.CostComposite(robot, H, costs, weights_cost_l=weights),
+                                                      clip_grad=True, interpolate_trajectories_for_collision=True,
+                                                      num_interpolated_points=int(np.ceil(H * 1.5)))  # swallowed, as upstream
+    guide = make_guide(wc, ws)
     n_grid = sum(hasattr(f, "texels") for f in fields)
-    return model, guide, ds, prob, sd, n_grid
+    return model, guide, ds, prob, sd, n_grid, make_guide
 
 
 def sample_kwargs(guide):
@@ -192,13 +207,20 @@ def cpu_oracle_runner(name, threads):
     hc = {k: v[None].repeat(B, 1) for k, v in hard.items()}
     gen = torch.Generator().manual_seed(3)
     noise = torch.randn((T_DIFF + N_EXTRA + 1, B, H, D), generator=gen)
+    calls = [0]
 
     def run():
+        if name == "cfg3":  # the sweep: the weights change from loop to loop, nothing else does
+            spec.weight_collision, spec.weight_smoothness = CFG3_SWEEP[calls[0] % len(CFG3_SWEEP)]
+        calls[0] += 1
         t0 = time.perf_counter()
         with torch.no_grad():
-            om.p_sample_loop((B, H, D), hc, noise=noise, n_diffusion_steps_without_noise=N_EXTRA,
-                             guide=lambda z: O.guide_manager_grad(spec, z), n_guide_steps=N_GUIDE,
-                             t_start_guide=T_START_GUIDE, noise_std_fn=lambda _t: NOISE_STD)
+            if name == "cfg4_ddim":
+                om.ddim_sample((B, H, D), hc, noise=noise, guide=lambda z: O.guide_manager_grad(spec, z), t_start_guide=T_START_GUIDE)
+            else:
+                om.p_sample_loop((B, H, D), hc, noise=noise, n_diffusion_steps_without_noise=N_EXTRA,
+                                 guide=lambda z: O.guide_manager_grad(spec, z), n_guide_steps=N_GUIDE,
+                                 t_start_guide=T_START_GUIDE, noise_std_fn=lambda _t: NOISE_STD)
         return time.perf_counter() - t0
     return run, B
 
@@ -221,19 +243,32 @@ def run_reference_arm(args):
         return
     threads = os.cpu_count() or 1
     run, B = cpu_oracle_runner(args.workload, threads)
-    for _ in range(min(args.warmup, 1)):
+    # --steps / --warmup are honoured as long as the run stays within a few minutes: every step is one full CPU loop at the
+    # workload's batch (seconds each), so a wall-clock budget bounds the run instead of a fixed cap on the step count
+    budget_s = float(os.environ.get("MPDB_REF_BUDGET_S", "240"))
+    t_start = time.perf_counter()
+    warm = 0
+    for _ in range(max(args.warmup, 0)):
+        if warm >= 1 and time.perf_counter() - t_start > 0.2 * budget_s:
+            break
         run()
-    steps = max(1, min(args.steps, 10))  # bounded: each step is a full CPU loop (seconds)
-    times = [run() for _ in range(steps)]
+        warm += 1
+    times = []
+    for _ in range(max(args.steps, 1)):
+        if times and time.perf_counter() - t_start + max(times) > budget_s:
+            break
+        times.append(run())
+    steps = len(times)
     total = sum(times)
     value = B * steps / total
     cfg = workload_config(args.workload, 1)
     out = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
-           "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * total / steps, "higher_is_better": True, "scaling": "weak",
+           "warmup": warm, "ms_per_step": 1e3 * total / steps, "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "cpu_model": cpu_model_name(),
-                            "sample": f"{steps} full guided loop(s) at B={B} (same workload), PyTorch CPU eager, "
-                                      f"{threads} threads; requested steps capped at 10"},
+                            "sample": f"{steps} full guided loop(s) at B={B} (same workload; requested {args.steps} steps / "
+                                      f"{args.warmup} warm-up, bounded by a {budget_s:.0f} s wall-clock budget), oracle port of the "
+                                      f"reference path, PyTorch CPU eager fp32, {threads} threads"},
            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
     emit(out)
@@ -293,11 +328,15 @@ def main():
     K = max(args.steps, 1)
 
     mid, H, B, opt, wc, ws = WORKLOADS[args.workload]
-    model, guide, ds, prob, sd, n_grid = build_problem(args.workload, device)
+    model, guide, ds, prob, sd, n_grid, make_guide = build_problem(args.workload, device)
+    ddim = args.workload == "cfg4_ddim"
+    guides = [make_guide(wc_, ws_) for wc_, ws_ in CFG3_SWEEP] if args.workload == "cfg3" else [guide]
+    counter = {"resident": 0, "e2e": 0}
     model.use_cuda_graph = not args.no_graph
     model.tensor_cores = args.tc
     D = prob.robot.state_dim
-    kw = sample_kwargs(guide)
+    kws = [sample_kwargs(g_) for g_ in guides]
+    kw = kws[0]
     start_goal_host = torch.vstack((torch.as_tensor(prob.start), torch.as_tensor(prob.goal))).pin_memory()
     hard = ds.get_hard_conditions(start_goal_host.to(device), normalize=True)
     n_iters = T_DIFF + N_EXTRA
@@ -308,20 +347,40 @@ def main():
 
     def step_resident():
         """Inputs (noise, hard conditions) already in HBM."""
-        x = model.sample(hard, B, noise=noise, **kw)
+        k = kws[counter["resident"] % len(kws)]
+        counter["resident"] += 1
+        if ddim:
+            x = model.ddim_sample((B, H, D), hard_b, guide=k["guide"], t_start_guide=T_START_GUIDE, noise=noise[0])
+        else:
+            x = model.sample(hard, B, noise=noise, **k)
         return allgather_plans(x, n_total) if world > 1 else x
 
-    out_host = torch.empty((n_total, H, D), dtype=torch.float32).pin_memory()
+    hard_b = {k_: v.unsqueeze(0).repeat(B, 1) for k_, v in hard.items()}
+    out_host = torch.empty((B, H, D), dtype=torch.float32).pin_memory()
+    copy_stream = torch.cuda.Stream(device=device)
 
     def step_e2e():
         """The public call a user makes (inference.py:248-257): start/goal from pinned host memory, noise drawn
-        by the API on the device exactly as the reference does, plans read back to the host."""
+        by the API on the device exactly as the reference does, plans read back to the host. With several GPUs every
+        process reads back ITS shard (the N hosts-side results together are the job's result) while the all-gather that
+        leaves the full set of plans on every GPU runs on the NCCL stream."""
+        k = kws[counter["e2e"] % len(kws)]
+        counter["e2e"] += 1
         sg = start_goal_host.to(device, non_blocking=True)
         hc = ds.get_hard_conditions(sg, normalize=True)
-        x = model.run_inference(None, hc, n_samples=B, horizon=H, return_chain=False, **kw)
+        if ddim:
+            hcb = {k_: v.unsqueeze(0).expand(B, -1) for k_, v in hc.items()}
+            x = model.conditional_sample(hcb, horizon=H, batch_size=B, ddim=True, guide=k["guide"], t_start_guide=T_START_GUIDE)
+        else:
+            x = model.run_inference(None, hc, n_samples=B, horizon=H, return_chain=False, **k)
         if world > 1:
-            x = allgather_plans(x, n_total)
-        out_host.copy_(x, non_blocking=True)
+            copy_stream.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(copy_stream):
+                out_host.copy_(x, non_blocking=True)
+            allgather_plans(x, n_total)
+            torch.cuda.current_stream().wait_stream(copy_stream)
+        else:
+            out_host.copy_(x, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         return out_host
 
@@ -373,20 +432,10 @@ def main():
 
     result = None
     if rank == 0:
-        # ---- roofline of the dominant kernel: per-layer CUDA-event timing of one UNet forward ----
+        # ---- roofline of the dominant kernel: CUDA-event timing of the UNet forward as the loop runs it ----
         lib = _lib.lib()
-        eng = model._engine()
-        n_ops = lib.mpdb_engine_num_ops(eng.handle)
-        ms = (C.c_float * n_ops)()
-        fl = (C.c_double * n_ops)()
-        md = (C.c_int32 * n_ops)()
+        eng = model._engine(H)
         x0 = noise[0].contiguous()
-        _lib.check(lib.mpdb_profile_forward(eng.handle, _lib.fptr(x0), 5, B, 20, ms, fl, md, _lib.stream_ptr(device)))
-        ms, fl, md = np.array(ms[:]), np.array(fl[:]), np.array(md[:])
-        tcm = (md == 5) | (md == 8)  # 5 = tcgen05 conv, 8 = cluster-fused residual block (two convs, one launch)
-        dom = tcm if tcm.any() else (md == 0)
-        fwd_ms = float(ms.sum())
-        dom_ms, dom_flops = float(ms[dom].sum()), float(fl[dom].sum())
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -394,66 +443,97 @@ def main():
             pass
         peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
         peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)"
-        ach_tf = dom_flops / (dom_ms * 1e-3) / 1e12
         flops_traj, sdf_bytes = algorithmic_work(H, D, opt, prob.robot.n_spheres, n_grid, prob.robot.ws_dim)
-        if tcm.any():
-            kname = ("mpdb::conv5_tc_kernel (tcgen05.mma kind::f16 fp16-split x3, TMEM accumulators, cp.async.bulk staging; "
-                     f"Conv1d k5 + GroupNorm + Mish [+cond][+residual]; residual blocks with C_out <= 128 are one cluster-fused "
-                     f"launch, rtb_tc_kernel), {int(dom.sum())} launches per UNet forward")
-            note = ("achieved = algorithmic (useful) 2*MAC FLOPs of its launches / their summed CUDA-event time; the tensor "
-                    "pipe issues 3x that (hi*hi + lo*hi + hi*lo); share of one UNet forward "
-                    f"{dom_ms / fwd_ms:.3f}")
+        # the loop's forwards by precision (engine.cu step_prec): 1 = one fp16 product per MMA step, 3 = 22-bit split, 0 = fp32 FMA path
+        if ddim:
+            loop_ts = model.ddim_schedule()[0]
+            precs = [3 if args.tc != "off" else 0 for _ in loop_ts]
         else:
-            kname = ("mpdb::conv_kernel<MODE_CONV5> (fp32 FMA; Conv1d k5 + GroupNorm + Mish [+cond][+residual]), "
-                     f"{int(dom.sum())} launches per UNet forward")
-            note = ("fp32 CUDA-core FMA kernel (exact fp32 parity path); achieved = algorithmic 2*MAC FLOPs of its launches / "
-                    f"their summed CUDA-event time; share of one UNet forward {dom_ms / fwd_ms:.3f}")
+            loop_ts = [max(i, 0) for i in reversed(range(-N_EXTRA, T_DIFF))]
+            precs = [int(lib.mpdb_engine_step_precision(eng.handle, t)) for t in loop_ts]
+
+        def body(t):
+            bms, bfl, bn = C.c_float(), C.c_double(), C.c_int32()
+            _lib.check(lib.mpdb_profile_unet_body(eng.handle, _lib.fptr(x0), int(t), B, 50, C.byref(bms), C.byref(bfl), C.byref(bn),
+                                                  _lib.stream_ptr(device)))
+            return float(bms.value), float(bfl.value), int(bn.value)
+
+        by_prec = {}
+        for pr in sorted(set(precs)):
+            t_rep = loop_ts[precs.index(pr)]
+            by_prec[pr] = body(t_rep) + (precs.count(pr), t_rep)
+        n_fwd = len(precs)
+        fwd_ms = sum(v[0] * v[3] for v in by_prec.values()) / n_fwd           # loop-average forward
+        dom_flops = next(iter(by_prec.values()))[1]
+        launches_per_fwd = next(iter(by_prec.values()))[2]
+        issued_mult = sum((pr if pr else 1) * v[3] for pr, v in by_prec.items()) / n_fwd
+        ach_tf = dom_flops / (fwd_ms * 1e-3) / 1e12
         traffic = {}
         try:
             traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload, {})
         except Exception:
             pass
-        tr_conv = traffic.get("conv5_tc_kernel", {}).get("bytes_per_launch") if tcm.any() else None
         mega_on, mega_G, mega_layers, mega_a, mega_smem, _why = eng.mega_info(B)
-        per_layer_detail = None
-        if mega_on and tcm.any():
-            # the loop runs the UNet as ONE launch of the whole-forward cluster kernel: time that launch
-            bms, bfl, bn = C.c_float(), C.c_double(), C.c_int32()
-            _lib.check(lib.mpdb_profile_unet_body(eng.handle, _lib.fptr(x0), 5, B, 50, C.byref(bms), C.byref(bfl), C.byref(bn),
-                                                  _lib.stream_ptr(device)))
-            per_layer_detail = {"unet_forward_ms_per_layer_kernels": fwd_ms, "tflops_per_layer_kernels": ach_tf}
-            dom_ms, dom_flops, fwd_ms = float(bms.value), float(bfl.value), float(bms.value)
-            ach_tf = dom_flops / (dom_ms * 1e-3) / 1e12
+        tc_on = args.tc != "off"
+        prec_note = "; ".join(f"precision {pr}: {v[3]} of {n_fwd} forwards, {v[0] * 1e3:.1f} us each (timed at t = {v[4]})" for pr, v in by_prec.items())
+        if mega_on and tc_on:
             kname = (f"mpdb::unet_mega_kernel (whole TemporalUnet forward in ONE launch: {(B + mega_G - 1) // mega_G} clusters of 8 CTAs x "
-                     f"{mega_G} trajectories, {mega_layers} layers; tcgen05.mma kind::f16 fp16-split x3 from two issuer warps, TMEM "
-                     "accumulators, activations exchanged through distributed shared memory (st.async with complete_tx on the consumer's "
-                     "mbarrier), weights via cp.async.bulk ring; "
-                     f"{mega_smem} B shared memory per CTA), {bn.value} launch per UNet forward")
-            note = ("achieved = algorithmic (useful) 2*MAC FLOPs of one forward / CUDA-event time of the launch; the tensor pipe "
-                    "issues 3x that (hi*hi + lo*hi + hi*lo). At 100 trajectories per GPU the forward is a chain of 40 dependent "
-                    "layers per cluster and is latency-bound (profiles/README.md: per-layer timeline)")
+                     f"{mega_G} trajectories, {mega_layers} layers; tcgen05.mma kind::f16 from two issuer warps, TMEM accumulators, activations "
+                     "exchanged through distributed shared memory (st.async with complete_tx on the consumer's mbarrier), weights via "
+                     f"cp.async.bulk ring; {mega_smem} B shared memory per CTA), {launches_per_fwd} launch per UNet forward")
             tr_conv = traffic.get("unet_mega_kernel", {}).get("bytes_per_launch")
+        elif tc_on:
+            kname = ("mpdb::conv5_tc_kernel / rtb_tc_kernel (tcgen05.mma kind::f16, TMEM accumulators, cp.async.bulk staging; Conv1d k5 + "
+                     "GroupNorm + Mish [+cond][+residual]; residual blocks with C_out <= 128 are one cluster-fused launch), "
+                     f"{launches_per_fwd} launches per UNet forward")
+            tr_conv = traffic.get("conv5_tc_kernel", {}).get("bytes_per_launch")
+        else:
+            kname = f"mpdb::conv_kernel (fp32 FMA; Conv1d k5 + GroupNorm + Mish [+cond][+residual]), {launches_per_fwd} launches per UNet forward"
+            tr_conv = None
+        note = ("achieved = algorithmic (useful) 2*MAC FLOPs of one UNet forward / the loop-average CUDA-event time of a forward. "
+                "Per-timestep precision policy (DESIGN.md §4): a step whose eps-to-mean amplification c1[t]*sqrt(1/abar_t - 1) is <= "
+                "0.11 issues ONE fp16 product per MMA step, the others the three products of the 22-bit split: " + prec_note +
+                f"; issued FLOPs = {issued_mult:.2f} x useful on average. At 100 trajectories per GPU the forward is a chain of 40 "
+                "dependent layers per cluster and is latency-bound (profiles/README.md: per-layer timeline)")
         roofline = {"kernel": kname, "bound": "tensor", "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s",
                     "frac": ach_tf / peak_tf, "traffic": tr_conv, "peak_source": peak_src, "note": note,
-                    "issued_tflops": ach_tf * (3 if tcm.any() else 1),
+                    "issued_tflops": ach_tf * issued_mult, "issued_frac": ach_tf * issued_mult / peak_tf,
                     "unet_forward_ms": fwd_ms, "unet_flops_per_trajectory_per_forward": flops_traj,
-                    "per_launch_us": [round(float(v) * 1e3, 2) for v in ms], "per_launch_mode": [int(v) for v in md]}
-        if per_layer_detail:
-            roofline.update(per_layer_detail)
-            roofline["per_launch_note"] = "per_launch_us / per_launch_mode describe the per-layer kernels (fallback path), not the cluster kernel"
+                    "forward_us_by_precision": {str(pr): round(v[0] * 1e3, 2) for pr, v in by_prec.items()},
+                    "forwards_by_precision": {str(pr): v[3] for pr, v in by_prec.items()}}
+        if not mega_on and tc_on:  # per-layer detail of the fallback / large-batch path
+            n_ops = lib.mpdb_engine_num_ops(eng.handle)
+            ms = (C.c_float * n_ops)()
+            fl = (C.c_double * n_ops)()
+            md = (C.c_int32 * n_ops)()
+            _lib.check(lib.mpdb_profile_forward(eng.handle, _lib.fptr(x0), 5, B, 20, ms, fl, md, _lib.stream_ptr(device)))
+            roofline["per_launch_us"] = [round(float(v) * 1e3, 2) for v in ms]
+            roofline["per_launch_mode"] = [int(v) for v in md]
         # guide kernel (HBM-bound by construction; at B=100 it is latency-bound)
-        gms = C.c_float()
+        gh = guide._handle(device, H)
         xg = noise[1].clamp(-1, 1).contiguous()
-        _lib.check(lib.mpdb_profile_guide(guide._handle(device, H), _lib.fptr(xg), B, H, 50, C.byref(gms),
-                                          _lib.stream_ptr(device)))
+        gms = C.c_float()
+        _lib.check(lib.mpdb_profile_guide(gh, _lib.fptr(xg.clone()), B, H, 50, C.byref(gms), _lib.stream_ptr(device)))
         peak_hbm = float(peaks.get("hbm_gbs", 6650.0))
-        ach_gbs = sdf_bytes * B / (gms.value * 1e-3) / 1e9
-        roofline_sdf = {"kernel": "mpdb::guide_step_kernel (unnormalise+interp+FK+SDF lookup+adjoint+clip+GP stencil+update)",
+        texel_bytes = sdf_bytes - 2 * H * D * 4
+        fused_ok = (not ddim) and int(lib.mpdb_guide_max_coresident(gh, H)) >= B
+        if fused_ok:
+            fms = C.c_float()
+            _lib.check(lib.mpdb_profile_guide_steps(gh, _lib.fptr(xg.clone()), N_GUIDE, B, H, 50, C.byref(fms), _lib.stream_ptr(device)))
+            launch_bytes = (2 * H * D * 4 + N_GUIDE * texel_bytes) * B
+            launch_ms, evals = fms.value, N_GUIDE
+        else:
+            launch_bytes, launch_ms, evals = sdf_bytes * B, gms.value, 1
+        ach_gbs = launch_bytes / (launch_ms * 1e-3) / 1e9
+        roofline_sdf = {"kernel": "mpdb::guide_step_kernel (unnormalise+interp+FK+SDF lookup / workspace box / self-collision+adjoint+"
+                                  f"clip+GP stencil+update; {evals} evaluation(s) per launch as the loop runs it)",
                         "bound": "hbm", "achieved": ach_gbs, "peak": peak_hbm, "unit": "GB/s", "frac": ach_gbs / peak_hbm,
                         "traffic": traffic.get("guide_step_kernel", {}).get("bytes_per_launch"),
-                        "ms_per_launch": gms.value, "bytes_per_trajectory": sdf_bytes,
-                        "note": "algorithmic bytes = 2*H*D*4 + fields*128*spheres*texel per trajectory (SURVEY 8d); at B=100 one "
-                                "launch moves 2.4 MB and is latency-bound, not bandwidth-bound"}
+                        "ms_per_launch": launch_ms, "evaluations_per_launch": evals, "ms_single_evaluation_launch": gms.value,
+                        "bytes_per_launch": launch_bytes, "bytes_per_trajectory_per_evaluation": sdf_bytes,
+                        "note": "algorithmic bytes per trajectory per evaluation = 2*H*D*4 + grid fields*128*spheres*texel (SURVEY 8d); "
+                                "a fused launch reads and writes x once and gathers the texels of each of its evaluations: "
+                                "2*H*D*4 + evaluations*texels. At B=100 a launch moves a few MB and is latency-bound, not bandwidth-bound"}
 
         cfg = workload_config(args.workload, n_gpus)
         result = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": K, "warmup": W,
@@ -461,11 +541,14 @@ def main():
                   "dtype": "f32", "data": "synthetic", "config": cfg, "clocks": clocks,
                   "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / K,
                           "h2d_bytes_per_step": int(start_goal_host.numel() * 4),
-                          "d2h_bytes_per_step": int(n_total * H * D * 4),
+                          "d2h_bytes_per_step": int(B * H * D * 4),
                           "note": "run_inference() with start/goal from pinned host memory, noise drawn on the device by "
-                                  "the API as in the reference (diffusion_model_base.py:165), plans copied to pinned host"},
+                                  "the API as in the reference (diffusion_model_base.py:165), plans copied to pinned host "
+                                  "(per process: its own shard; d2h_bytes_per_step is per process)"},
                   "gpu_launches": int(launches), "roofline": roofline, "roofline_sdf": roofline_sdf,
-                  "cuda_graph": bool(model.use_cuda_graph), "tensor_cores": model.tensor_cores}
+                  "cuda_graph": bool(model.use_cuda_graph), "tensor_cores": model.tensor_cores,
+                  "precision_policy": {"prec1_amp_limit": 0.11 if args.tc == "auto" else None,
+                                       "products_per_mma_step_by_loop_step": precs}}
         if n_gpus == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
             try:

@@ -194,6 +194,15 @@ int mpdb_profile_forward(mpdb_engine* e, const float* x, int32_t t, int32_t B, i
 /* average device time of one guide evaluation on x (in place), CUDA events on `stream` */
 int mpdb_profile_guide(mpdb_guide* g, float* x, int32_t B, int32_t H, int32_t reps, float* ms_out, void* stream);
 
+/* average device time of ONE launch that runs n_evals guide evaluations on x in place, as mpdb_sample_loop launches them when
+ * the batch is co-resident (option "fuse_guide") */
+int mpdb_profile_guide_steps(mpdb_guide* g, float* x, int32_t n_evals, int32_t B, int32_t H, int32_t reps, float* ms_out,
+                             void* stream);
+/* 1 / 3: MMA products per step the loop issues for a forward at timestep t (option "prec1_amp_limit") */
+int mpdb_engine_step_precision(mpdb_engine* e, int32_t t);
+/* trajectories the fused guide launch can hold at once (0: never fused) */
+int mpdb_guide_max_coresident(mpdb_guide* g, int32_t H);
+
 /* unit-test hook for the tcgen05 implicit-GEMM core: raw fp32 accumulators of a k=5 convolution (no bias).
  * x_cm device [B][CI][L+4] with zero halo, w device [CO][CI][5], raw device [ceil(B/SPT)][CO/32][128][32] with
  * SPT = 132/(L+4); row r of a tile holds sample (b % SPT), position l at r = (b % SPT)*(L+4) + l. */

@@ -91,6 +91,9 @@ SYMBOLS = {
     "mpdb_profile_forward": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_float), C.POINTER(C.c_double),
                                        C.POINTER(C.c_int32), _P]),
     "mpdb_profile_guide": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_float), _P]),
+    "mpdb_profile_guide_steps": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_float), _P]),
+    "mpdb_engine_step_precision": (C.c_int, [_P, C.c_int32]),
+    "mpdb_guide_max_coresident": (C.c_int, [_P, C.c_int32]),
     "mpdb_debug_tc_conv5": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P]),
     "mpdb_engine_read_timeline": (C.c_int, [_P, C.POINTER(C.c_int64), C.c_int32]),
     "mpdb_engine_num_buffers": (C.c_int, [_P]),

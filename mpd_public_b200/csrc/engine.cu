@@ -138,10 +138,11 @@ struct mpdb_engine {
     int* flags = nullptr;
     int n_flags = 0;
     int loop_batch = 0;
-    // CUDA graph cache for the fused loop
-    cudaGraphExec_t graph_exec = nullptr;
-    long long graph_kernels = 0;  // kernel nodes in the captured loop
-    std::string graph_key;
+    // CUDA graph cache for the fused loop: one instantiated graph per configuration key (batch, guide handle + config hash,
+    // loop parameters, options), a handful kept (a weight sweep alternates between guides; BASELINE config 3 has nine)
+    struct LoopGraph { cudaGraphExec_t exec = nullptr; long long kernels = 0; long long last_use = 0; };
+    std::map<std::string, LoopGraph> graphs;
+    long long graph_clock = 0;
     float* g_noise = nullptr;   // staging owned by the engine (stable addresses for the graph)
     float* g_hc = nullptr;
     float* g_chain = nullptr;
@@ -149,6 +150,12 @@ struct mpdb_engine {
 };
 
 namespace mpdb {
+
+static void drop_graphs(mpdb_engine* e) {
+    for (auto& kv : e->graphs)
+        if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+    e->graphs.clear();
+}
 
 static long long add_param(mpdb_engine* e, const std::string& name, long long numel) {
     Param p;
@@ -377,7 +384,7 @@ static void build_mega(mpdb_engine* e, int B);
 static int ensure_workspace(mpdb_engine* e, int B) {
     if (B <= e->work_batch) return 0;
     ++e->generation;
-    if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; e->graph_key.clear(); }
+    drop_graphs(e);
     MPDB_CHECK_CUDA(cudaDeviceSynchronize());
     const size_t nb = e->bufs.size();
     // liveness: op index of the write, op index of the last read
@@ -833,7 +840,7 @@ extern "C" void mpdb_engine_destroy(mpdb_engine* e) {
     if (!e) return;
     mpdb::DeviceGuard dg(e->device);
     cudaDeviceSynchronize();
-    if (e->graph_exec) cudaGraphExecDestroy(e->graph_exec);
+    mpdb::drop_graphs(e);
     cudaFree(e->raw); cudaFree(e->packed); cudaFree(e->work); cudaFree(e->sched);
     cudaFree(e->packed_tc); cudaFree(e->work_tc); cudaFree(e->dbg_buf); cudaFree(e->mega_skip); cudaFree(e->mega_dbg);
     cudaFree(e->xbuf[0]); cudaFree(e->xbuf[1]); cudaFree(e->flags);
@@ -865,10 +872,16 @@ extern "C" int mpdb_engine_set_schedule(mpdb_engine* e, const float* sr, const f
     MPDB_ENTER_DEVICE(e->device);
     MPDB_CHECK_CUDA(cudaMemcpy(e->sched, e->sched_host.data(), sizeof(float) * 7 * (size_t)T, cudaMemcpyHostToDevice));
     // captured loops bake schedule values (std, var, the per-step tensor-core decision) into kernel arguments
-    if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; e->graph_key.clear(); }
+    drop_graphs(e);
     ++e->generation;
     e->sched_set = true;
     return 0;
+}
+
+extern "C" int mpdb_engine_step_precision(mpdb_engine* e, int32_t t) {
+    if (!e) return 0;
+    e->force_prec3 = false;
+    return e->tc_mode == 0 ? 0 : mpdb::step_prec(e, t);
 }
 
 extern "C" int64_t mpdb_engine_generation(mpdb_engine* e) { return e ? (int64_t)e->generation : -1; }
@@ -882,7 +895,7 @@ extern "C" int mpdb_engine_set_option(mpdb_engine* e, const char* name, double v
         e->tc_mode = (int)value;
     } else if (n == "fuse_rtb") {
         e->fuse_rtb = value != 0;
-        if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; e->graph_key.clear(); }
+        drop_graphs(e);
     } else if (n == "mega_timeline") {
         if (value != 0 && !e->mega_dbg) {
             MPDB_CHECK_CUDA(cudaMalloc(&e->mega_dbg, sizeof(long long) * MEGA_DBG * MEGA_CLUSTER * MEGA_MAX_LAYERS));
@@ -890,22 +903,22 @@ extern "C" int mpdb_engine_set_option(mpdb_engine* e, const char* name, double v
         } else if (value == 0 && e->mega_dbg) {
             cudaFree(e->mega_dbg); e->mega_dbg = nullptr;
         }
-        if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; e->graph_key.clear(); }
+        drop_graphs(e);
     } else if (n == "fuse_guide") {
         e->fuse_guide = value != 0;
-        if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; e->graph_key.clear(); }
+        drop_graphs(e);
     } else if (n == "fuse_final") {
         e->fuse_final = value != 0;
-        if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; e->graph_key.clear(); }
+        drop_graphs(e);
     } else if (n == "mega") {
         MPDB_REQUIRE(value == 0 || value == 1 || value == 2, "mega must be 0 (off), 1 (when the batch fits one wave) or 2 (always)");
         e->use_mega = (int)value;
-        if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; e->graph_key.clear(); }
+        drop_graphs(e);
     } else if (n == "alias_buffers") {
         if (e->alias_buffers != (value != 0)) {
             e->alias_buffers = value != 0;
             e->work_batch = 0;  // re-plan the workspace on the next call
-            if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; e->graph_key.clear(); }
+            drop_graphs(e);
         }
     } else if (n == "timeline") {
         e->timeline = value != 0;
@@ -918,7 +931,7 @@ extern "C" int mpdb_engine_set_option(mpdb_engine* e, const char* name, double v
     } else if (n == "prec1_amp_limit") {
         MPDB_REQUIRE(value >= 0, "prec1_amp_limit must be >= 0 (0 disables the one-product steps)");
         e->prec1_amp_limit = (float)value;
-        if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; e->graph_key.clear(); }
+        drop_graphs(e);
     } else {
         MPDB_REQUIRE(false, "unknown option '" + n + "'");
     }
@@ -932,7 +945,7 @@ extern "C" int mpdb_engine_finalize(mpdb_engine* e, void* stream) {
     for (auto& kv : e->params)
         MPDB_REQUIRE(kv.second.set, std::string("missing parameter '") + kv.first + "' (load_state_dict incomplete)");
     MPDB_REQUIRE(e->sched_set, "schedule tables not set");
-    if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; e->graph_key.clear(); }
+    drop_graphs(e);
     for (const PackJob& j : e->packs) {
         const float* src = e->raw + e->params[j.src].offset;
         float* dst = e->packed + j.dst;
@@ -1199,7 +1212,7 @@ static int enqueue_loop(mpdb_engine* e, mpdb_guide* g, const mpdb_loop_params* p
 
 static int ensure_flags(mpdb_engine* e, int n_flags_needed) {
     if (e->n_flags >= n_flags_needed) return 0;
-    if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; e->graph_key.clear(); }
+    drop_graphs(e);
     MPDB_CHECK_CUDA(cudaDeviceSynchronize());
     if (e->flags) cudaFree(e->flags);
     e->flags = nullptr;
@@ -1252,7 +1265,7 @@ extern "C" int mpdb_sample_loop(mpdb_engine* e, mpdb_guide* g, const mpdb_loop_p
     const long long hc_floats = (long long)p->n_hard_conds * B * D;
     const long long chain_floats = chain_out ? (long long)(n_iters + 1) * n : 0;
     const bool grow = noise_floats > e->g_noise_floats || hc_floats > e->g_hc_floats || chain_floats > e->g_chain_floats;
-    if (grow && e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; e->graph_key.clear(); }
+    if (grow) drop_graphs(e);
     if (ensure_staging(&e->g_noise, &e->g_noise_floats, noise_floats)) return 1;
     if (ensure_staging(&e->g_hc, &e->g_hc_floats, hc_floats > 0 ? hc_floats : 1)) return 1;
     if (ensure_staging(&e->g_chain, &e->g_chain_floats, chain_floats > 0 ? chain_floats : 1)) return 1;
@@ -1277,8 +1290,15 @@ extern "C" int mpdb_sample_loop(mpdb_engine* e, mpdb_guide* g, const mpdb_loop_p
         key += "|" + std::to_string(hsh);
     }
 
-    if (e->graph_exec == nullptr || key != e->graph_key) {
-        if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; }
+    auto git = e->graphs.find(key);
+    if (git == e->graphs.end()) {
+        if (e->graphs.size() >= 16) {  // evict the least recently used entry
+            auto victim = e->graphs.begin();
+            for (auto it2 = e->graphs.begin(); it2 != e->graphs.end(); ++it2)
+                if (it2->second.last_use < victim->second.last_use) victim = it2;
+            if (victim->second.exec) cudaGraphExecDestroy(victim->second.exec);
+            e->graphs.erase(victim);
+        }
         // internal chain staging is always [S][B][H][D]
         cudaStream_t cs;
         MPDB_CHECK_CUDA(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
@@ -1294,24 +1314,25 @@ extern "C" int mpdb_sample_loop(mpdb_engine* e, mpdb_guide* g, const mpdb_loop_p
             if (rc == 0) mpdb::set_error(std::string("graph capture failed: ") + cudaGetErrorString(ce));
             return 1;
         }
-        ce = cudaGraphInstantiate(&e->graph_exec, graph, 0);
+        mpdb_engine::LoopGraph lg;
+        ce = cudaGraphInstantiate(&lg.exec, graph, 0);
         cudaGraphDestroy(graph);
         cudaStreamDestroy(cs);
         if (ce != cudaSuccess) {
-            e->graph_exec = nullptr;
             mpdb::set_error(std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ce));
             return 1;
         }
-        e->graph_key = key;
-        e->graph_kernels = mpdb::g_launch_count.load() - launches_before;
+        lg.kernels = mpdb::g_launch_count.load() - launches_before;
         mpdb::g_launch_count.store(launches_before);  // capture enqueued nothing; replays are counted below
+        git = e->graphs.emplace(key, lg).first;
     }
+    git->second.last_use = ++e->graph_clock;
     MPDB_CHECK_CUDA(cudaMemcpyAsync(e->g_noise, noise, sizeof(float) * (size_t)noise_floats, cudaMemcpyDeviceToDevice, st));
     if (hc_floats > 0)
         MPDB_CHECK_CUDA(cudaMemcpyAsync(e->g_hc, p->hard_cond_vals, sizeof(float) * (size_t)hc_floats,
                                         cudaMemcpyDeviceToDevice, st));
-    MPDB_CHECK_CUDA(cudaGraphLaunch(e->graph_exec, st));
-    mpdb::g_launch_count.fetch_add(e->graph_kernels);
+    MPDB_CHECK_CUDA(cudaGraphLaunch(git->second.exec, st));
+    mpdb::g_launch_count.fetch_add(git->second.kernels);
     // result: the captured loop wrote its last step into xbuf[n_iters & 1]
     MPDB_CHECK_CUDA(cudaMemcpyAsync(x_out, e->xbuf[(n_iters) & 1], sizeof(float) * (size_t)n, cudaMemcpyDeviceToDevice, st));
     if (chain_out) {

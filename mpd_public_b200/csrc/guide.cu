@@ -36,11 +36,13 @@
 struct mpdb_guide {
     mpdb_guide_config cfg;
     int device;
-    int* flags;  // device scratch: [2] flags for the standalone entry points
+    int* flags;  // device scratch [64]: [0,2) flags of the standalone entry points, [8] batch-dependent-clamp counter,
+                 // [16,37) per-evaluation flags and [40,60) grid counters of a fused mpdb_guide_steps launch
     // parity instrumentation (mpdb_guide_record_decisions)
     int32_t* dec_buf = nullptr;
     long long dec_capacity = 0, dec_count = 0;
     int dec_batch = 0;
+    int coresident_H = -1, coresident = 0;  // cached guide_max_coresident(H)
 };
 
 namespace mpdb {
@@ -732,11 +734,14 @@ static int guide_occupancy(const GuideDev& g, int H, int device) {
 // CTAs of the guide kernel that can be resident at once (the selective grid wait of the multi-evaluation launch needs every
 // CTA scheduled). One CTA per SM is left out of the count: the neighbouring kernels of the loop may still hold resources.
 int guide_max_coresident(mpdb_guide* gd, int H) {
+    if (gd->coresident_H == H) return gd->coresident;
     GuideDev g = make_dev(gd->cfg);
     const int n = g.robot_kind == 1 ? guide_occupancy<1>(g, H, gd->device) : guide_occupancy<0>(g, H, gd->device);
     int sms = 0;
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, gd->device) != cudaSuccess) { cudaGetLastError(); return 0; }
-    return n >= 2 * sms ? n - sms : (n >= sms ? sms : 0);  // the one-per-SM instantiation (B <= #SMs) always fits when this is > 0
+    gd->coresident_H = H;
+    gd->coresident = n >= 2 * sms ? n - sms : (n >= sms ? sms : 0);  // the one-per-SM instantiation (B <= #SMs) always fits when this is > 0
+    return gd->coresident;
 }
 
 int guide_launch_step(mpdb_guide* gd, const GuideStepArgs& a_in, cudaStream_t stream) {
@@ -890,7 +895,7 @@ extern "C" int mpdb_guide_create(const mpdb_guide_config* cfg, int device, mpdb_
     g->cfg = *cfg;
     g->device = device;
     g->flags = nullptr;
-    if (cudaMalloc(&g->flags, 16 * sizeof(int)) != cudaSuccess || cudaMemset(g->flags, 0, 16 * sizeof(int)) != cudaSuccess) {
+    if (cudaMalloc(&g->flags, 64 * sizeof(int)) != cudaSuccess || cudaMemset(g->flags, 0, 64 * sizeof(int)) != cudaSuccess) {
         delete g;
         mpdb::set_error("mpdb_guide_create: cudaMalloc failed");
         return 1;
@@ -957,6 +962,26 @@ extern "C" int mpdb_guide_steps_chain(mpdb_guide* g, float* x, int32_t n_steps, 
     MPDB_ENTER_DEVICE(g->device);
     if (n_steps == 0) return 0;
     if (guide_launch_flag(x, (long long)B * H * 2 * g->cfg.q_dim, g->flags, st)) return 1;
+    if (chain_out == nullptr && n_steps >= 2 && n_steps <= 20 && g->dec_buf == nullptr && B <= guide_max_coresident(g, H)) {
+        // all evaluations in ONE launch (the trajectory stays in shared memory; guide_step_kernel resolves the clip flag per CTA)
+        MPDB_CHECK_CUDA(cudaMemsetAsync(g->flags + 16, 0, sizeof(int) * 44, st));
+        MPDB_CHECK_CUDA(cudaMemcpyAsync(g->flags + 16, g->flags, sizeof(int), cudaMemcpyDeviceToDevice, st));
+        GuideStepArgs a;
+        memset(&a, 0, sizeof(a));
+        a.x_in = x;
+        a.x_out = x;
+        a.flag_in = g->flags + 16;
+        a.n_iters = n_steps;
+        a.iter_flags = g->flags + 16;
+        a.iter_counters = reinterpret_cast<unsigned int*>(g->flags + 40);
+        a.model_var = model_var;
+        a.n_hc = n_hc;
+        for (int k = 0; k < n_hc; ++k) a.hc_rows[k] = hc_rows[k];
+        a.hc_vals = hc_vals;
+        a.B = B;
+        a.H = H;
+        return guide_launch_step(g, a, st);
+    }
     for (int it = 0; it < n_steps; ++it) {
         GuideStepArgs a;
         memset(&a, 0, sizeof(a));
@@ -1047,6 +1072,42 @@ extern "C" int mpdb_profile_guide(mpdb_guide* g, float* x, int32_t B, int32_t H,
     return 0;
 }
 
+// Average device time of ONE LAUNCH running n_evals guide evaluations in place (the loop's fused guide_gradient_steps launch).
+extern "C" int mpdb_profile_guide_steps(mpdb_guide* g, float* x, int32_t n_evals, int32_t B, int32_t H, int32_t reps, float* ms_out,
+                                        void* stream) {
+    MPDB_REQUIRE(g && x && ms_out && B > 0 && H > 1 && reps > 0 && n_evals >= 2 && n_evals <= 20, "mpdb_profile_guide_steps: bad argument");
+    MPDB_REQUIRE(B <= guide_max_coresident(g, H), "mpdb_profile_guide_steps: the batch is not co-resident (the loop launches one evaluation at a time)");
+    cudaStream_t st = (cudaStream_t)stream;
+    MPDB_ENTER_DEVICE(g->device);
+    cudaEvent_t ev0, ev1;
+    MPDB_CHECK_CUDA(cudaEventCreate(&ev0));
+    MPDB_CHECK_CUDA(cudaEventCreate(&ev1));
+    for (int r = -1; r < reps; ++r) {
+        if (r == 0) MPDB_CHECK_CUDA(cudaEventRecord(ev0, st));
+        // what the loop does per guided step: zero the flag / counter scratch (part of one memset per loop there), one launch
+        MPDB_CHECK_CUDA(cudaMemsetAsync(g->flags + 16, 0, sizeof(int) * 44, st));
+        GuideStepArgs a;
+        memset(&a, 0, sizeof(a));
+        a.x_in = x;
+        a.x_out = x;
+        a.flag_in = g->flags + 16;
+        a.n_iters = n_evals;
+        a.iter_flags = g->flags + 16;
+        a.iter_counters = reinterpret_cast<unsigned int*>(g->flags + 40);
+        a.B = B;
+        a.H = H;
+        if (guide_launch_step(g, a, st)) return 1;
+    }
+    MPDB_CHECK_CUDA(cudaEventRecord(ev1, st));
+    MPDB_CHECK_CUDA(cudaEventSynchronize(ev1));
+    float ms = 0.f;
+    MPDB_CHECK_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
+    *ms_out = ms / reps;
+    cudaEventDestroy(ev0);
+    cudaEventDestroy(ev1);
+    return 0;
+}
+
 extern "C" int mpdb_eval_trajectories(mpdb_guide* gd, const float* x_unnormalized, float* stats, float margin, int32_t B,
                                       int32_t H, void* stream) {
     MPDB_REQUIRE(gd && x_unnormalized && stats && B > 0 && H > 1, "mpdb_eval_trajectories: bad argument");
@@ -1084,6 +1145,12 @@ extern "C" int64_t mpdb_guide_batch_dependent_clamps(mpdb_guide* g, int32_t rese
     if (!dg.ok || cudaDeviceSynchronize() != cudaSuccess || cudaMemcpy(&n, g->flags + 8, sizeof(n), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
     if (reset) cudaMemset(g->flags + 8, 0, sizeof(n));
     return (int64_t)n;
+}
+
+extern "C" int mpdb_guide_max_coresident(mpdb_guide* g, int32_t H) {
+    if (!g) return 0;
+    mpdb::DeviceGuard dg(g->device);
+    return dg.ok ? guide_max_coresident(g, H) : 0;
 }
 
 extern "C" int mpdb_guide_num_collision_costs(mpdb_guide* g) {

@@ -120,23 +120,15 @@ def test_guided_loop_properties_and_one_step_parity(name):
     assert torch.equal(final, chain[-1])
     for k, v in hard.items():
         assert torch.equal(chain[:, :, k, :], v.expand(n_iters + 1, batch, D))
-    # one unguided step (t = 12) and one guided step (t = 3), teacher-forced from our own chain, on a slice of the batch
-    ohc = {k: v[None].repeat(batch, 1) for k, v in hard.items()}
-    steps = list(reversed(range(-C.N_EXTRA, C.T_DIFF)))
-    sl = slice(0, 64)
-    for i in (12, 3):
-        k = steps.index(i)
-        t = torch.full((batch,), i, dtype=torch.long)
-        oguide = (lambda z: O.guide_manager_grad(spec, z))
-        with torch.no_grad():
-            ref = om.ddpm_step(chain[k].clone(), ohc, t, noise[k + 1], oguide, C.N_GUIDE_STEPS, False, C.T_START_GUIDE, C.NOISE_STD)
-        ref = O.apply_hard_conditioning(ref, ohc)
-        e = rel(chain[k + 1][sl], ref[sl])
-        if i < C.T_START_GUIDE and e >= TOL_STEP:
-            d = (chain[k + 1] - ref).abs() / ref.abs().max()   # sparse nearest-texel / hinge flips (see test_gpu_parity)
-            assert float((d > TOL_STEP).float().mean()) < 2e-3 and e < 2e-2, (i, e)
-        else:
-            assert e < TOL_STEP, (i, e)
+    # every step of the chain, teacher-forced, against the oracle at 1e-3 — guided steps with the guide's recorded decisions
+    # taken over and audited (oracle/parity.py); the recorded run must reproduce the graph run bit for bit
+    from oracle import parity as P
+    chain_rec, dec = P.run_recorded(model, guide, hard_cuda, noise.cuda(), batch, H, C.T_DIFF, C.N_EXTRA, C.T_START_GUIDE,
+                                    C.N_GUIDE_STEPS, C.NOISE_STD)
+    assert torch.equal(chain_rec, chain)
+    res = P.check_loop_per_step(om, spec, chain, noise, hard, dec, C.T_DIFF, C.N_EXTRA, C.T_START_GUIDE, C.N_GUIDE_STEPS,
+                                C.NOISE_STD, tol=TOL_STEP)
+    print(f"[{name} B={batch}] worst per-step rel err {res['worst']:.3e}, t = T-1 {res['t_last']:.3e}, audit {res['audit']}")
 
 
 def test_config5_shard_shape_panda_h128_b512():
@@ -185,7 +177,18 @@ def test_config5_shard_shape_panda_h128_b512():
     sub = model.run_inference(None, hard_cuda, n_samples=64, horizon=h, return_chain=False, noise=noise[:, :64].contiguous().cuda(),
                               **dict(kw, guide=None))
     full = model.run_inference(None, hard_cuda, n_samples=batch, horizon=h, return_chain=False, noise=noise.cuda(), **dict(kw, guide=None))
-    assert rel(sub, full[:64]) < 2e-5  # B = 64 runs the cluster kernel, B = 512 the per-layer kernels: same arithmetic up to summation order
+    assert rel(sub, full[:64]) < 5e-5  # B = 64 runs the cluster kernel, B = 512 the per-layer kernels: same products and the same
+    # per-step precision policy, partial sums combined in a different order (30 free-running steps)
+
+
+def C_pos_input(prob, batch, q, seed=23):
+    rng = np.random.default_rng(seed)
+    lam = np.linspace(0, 1, H)[None, :, None]
+    x = (1 - lam) * prob.start[None, None, :] + lam * prob.goal[None, None, :]
+    x = 2 * (x - prob.mins[:q]) / (prob.maxs[:q] - prob.mins[:q]) - 1
+    x = (x + 0.12 * rng.standard_normal((batch, H, q))).astype(np.float32)
+    x[0, 11, 1] = -1.3  # trips the normaliser's batch-global clip
+    return x
 
 
 @pytest.mark.parametrize("model_id,batch,wc,ws", [("EnvSimple2D-RobotPointMass", 9, 3e-2, 1e-2), ("EnvSpheres3D-RobotPanda", 5, 1e-2, 1e-4)])
@@ -230,9 +233,22 @@ def test_position_only_guide_manager(model_id, batch, wc, ws):
         assert float(got[:, 0].abs().max()) == 0 and float(got[:, -1].abs().max()) == 0
         x = x + ref
         xc = xc + got
-    with pytest.raises(NotImplementedError):
-        M.GuideManagerTrajectories(ds, guide.cost, use_velocity_from_finite_difference=True, start_state_pos=prob.start,
-                                   goal_state_pos=prob.goal, robot=robot)
+    # use_velocity_from_finite_difference=True (guides.py:77-79): velocities = central differences of the positions, the costs
+    # reach the positions through them as well, one clipped position gradient per cost, the velocity trajectory is left alone
+    guide_fd = M.GuideManagerTrajectories(ds, guide.cost, clip_grad=True, interpolate_trajectories_for_collision=True,
+                                          use_velocity_from_finite_difference=True, start_state_pos=torch.as_tensor(prob.start),
+                                          goal_state_pos=torch.as_tensor(prob.goal), num_steps=H - 1, robot=robot, n_samples=batch,
+                                          tensor_args=dict(device="cuda", dtype=torch.float32))
+    vel_before = guide_fd.velocity.clone()
+    x = torch.as_tensor(C_pos_input(prob, batch, q))
+    for call in range(2):
+        ref = O.guide_manager_pos_grad_fd(spec, x)
+        got = guide_fd(x.cuda())
+        assert float(ref.abs().max()) > 0
+        assert rel(got, ref) < TOL_KERNEL, (call, rel(got, ref))
+        assert float(got[:, 0].abs().max()) == 0 and float(got[:, -1].abs().max()) == 0
+        x = x + ref
+    assert torch.equal(guide_fd.velocity, vel_before)
 
 
 def test_position_only_model_runs_the_reverse_loop_with_its_guide():

@@ -37,9 +37,11 @@ def test_struct_layouts_match_c():
 #include <stddef.h>
 #include "mpdb200.h"
 int main(void) {
-  printf("%zu %zu %zu %zu %zu %zu %zu\n", sizeof(mpdb_engine_config), sizeof(mpdb_guide_config), sizeof(mpdb_loop_params),
+  printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(mpdb_engine_config), sizeof(mpdb_guide_config), sizeof(mpdb_loop_params),
          offsetof(mpdb_guide_config, grid_texels), offsetof(mpdb_guide_config, n_interp),
-         offsetof(mpdb_loop_params, noise_std), offsetof(mpdb_loop_params, hard_cond_vals));
+         offsetof(mpdb_loop_params, noise_std), offsetof(mpdb_loop_params, hard_cond_vals),
+         offsetof(mpdb_guide_config, self_pairs), offsetof(mpdb_guide_config, margin_grid), offsetof(mpdb_guide_config, vel_from_fd),
+         offsetof(mpdb_loop_params, state_dim), sizeof(mpdb_ddim_params), offsetof(mpdb_ddim_params, hard_cond_vals));
   return 0; }
 '''
     with tempfile.TemporaryDirectory() as d:
@@ -47,9 +49,10 @@ int main(void) {
         subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), "-o", os.path.join(d, "t"), os.path.join(d, "t.c")], check=True)
         out = subprocess.run([os.path.join(d, "t")], check=True, capture_output=True, text=True).stdout.split()
     got = [int(v) for v in out]
-    G, L = _lib.GuideConfig, _lib.LoopParams
+    G, L, Dd = _lib.GuideConfig, _lib.LoopParams, _lib.DdimParams
     want = [ctypes.sizeof(_lib.EngineConfig), ctypes.sizeof(G), ctypes.sizeof(L), G.grid_texels.offset, G.n_interp.offset,
-            L.noise_std.offset, L.hard_cond_vals.offset]
+            L.noise_std.offset, L.hard_cond_vals.offset, G.self_pairs.offset, G.margin_grid.offset, G.vel_from_fd.offset,
+            L.state_dim.offset, ctypes.sizeof(Dd), Dd.hard_cond_vals.offset]
     assert got == want
 
 
@@ -85,6 +88,81 @@ def test_normalizer_matches_reference_golden():
     nz = M.LimitsNormalizer(torch.stack([torch.as_tensor(prob.mins), torch.as_tensor(prob.maxs)]))
     assert np.array_equal(nz.unnormalize(torch.as_tensor(C.guide_input("panda3d"))).numpy(), g["un_in"])
     assert np.array_equal(nz.unnormalize(torch.as_tensor(C.guide_input("panda3d", out_of_range=True))).numpy(), g["un_out"])
+
+
+def test_panda_kinematic_constants_are_pinned_independently():
+    """the oracle and the product each hold their own copy of the Panda chain constants (the oracle does not
+    import the product's). Both are checked against each other AND against answers from outside this repository: the public
+    Franka Panda geometry puts the flange of the zero configuration at (0.088, 0, 0.926) and the link origins at the sums
+    below. A wrong joint origin on both sides would have to be the same wrong number twice and still hit these."""
+    import math
+    from mpd_public_b200 import synthetic as S
+    from oracle import mpd_oracle as O
+    assert np.allclose(np.asarray(O.PANDA_JOINT_XYZ), S.PANDA_JOINT_XYZ, atol=0) and np.allclose(O.PANDA_JOINT_ROLL, S.PANDA_JOINT_ROLL, atol=0)
+    assert np.allclose(O.PANDA_FLANGE_XYZ, S.PANDA_FLANGE_XYZ, atol=0)
+    import inspect
+    src = inspect.getsource(O)
+    assert "synthetic" not in src.split("def sphere_centers")[1].split("def sdf_and_grad_analytic")[0], "the oracle's FK must not import product constants"
+    zero = np.array([[0, 0, 0.333], [0, 0, 0.333], [0, 0, 0.649], [0.0825, 0, 0.649], [0, 0, 1.033], [0, 0, 1.033],
+                     [0.088, 0, 1.033], [0.088, 0, 0.926]])
+    robot = S.robot_panda()
+    q0 = torch.zeros(1, 7, dtype=torch.float64)
+    assert np.abs(O.sphere_centers(robot, q0)[0].numpy() - zero).max() < 1e-12
+    assert np.abs(S.robot_sphere_centers_numpy(robot, np.zeros(7)) - zero).max() < 1e-12
+    # joint 1 turns everything about the world z axis; joint 4 at -pi/2 folds the forearm: link 5 origin known in closed form
+    q = torch.zeros(1, 7, dtype=torch.float64)
+    q[0, 0] = math.pi / 2
+    rotz = np.array([[0.0, -1.0, 0.0], [1.0, 0.0, 0.0], [0.0, 0.0, 1.0]])
+    assert np.abs(O.sphere_centers(robot, q)[0].numpy() - zero @ rotz.T).max() < 1e-12
+    q = torch.zeros(1, 7, dtype=torch.float64)
+    q[0, 3] = -math.pi / 2
+    c = O.sphere_centers(robot, q)[0].numpy()
+    # link 4 frame at q4 = -pi/2: the (-0.0825, 0.384) offset of link 5 (in link 4's x / y, i.e. world x / z at q = 0) turns by -90 deg about
+    # link 4's axis (world -y at q = 0): world offset (0.384, 0, 0.0825)
+    assert np.abs(c[4] - (zero[3] + np.array([0.384, 0.0, 0.0825]))).max() < 1e-12, c[4]
+    # rigid link lengths for a random configuration
+    q = torch.tensor([[0.3, -0.5, 0.2, -1.9, 0.4, 1.7, -0.6]], dtype=torch.float64)
+    c = O.sphere_centers(robot, q)[0].numpy()
+    assert abs(np.linalg.norm(c[2] - c[0]) - 0.316) < 1e-12 and abs(np.linalg.norm(c[4] - c[3]) - math.hypot(0.0825, 0.384)) < 1e-12
+    assert abs(np.linalg.norm(c[7] - c[6]) - 0.107) < 1e-12 and abs(np.linalg.norm(c[6] - c[5]) - 0.088) < 1e-12
+    assert np.abs(c - S.robot_sphere_centers_numpy(robot, q[0].numpy())).max() < 1e-12
+
+
+def test_oracle_decision_audit_and_forced_decisions():
+    """oracle/parity.py's machinery on the CPU: decisions encoded the way the CUDA guide records them (include/mpdb200.h),
+    produced here from the oracle's own choices, must (a) decode, (b) reproduce the free-running gradient exactly when taken
+    over, (c) pass the audit; a corrupted decision away from any boundary must fail it."""
+    from oracle import mpd_oracle as O
+    prob = C.guide_problem("panda3d")
+    spec = O.make_guide_spec(prob, 1e-2, 1e-7)
+    spec.self_margin = 0.35
+    x = torch.as_tensor(C.guide_input("panda3d"))
+    rep = []
+    ref = O.guide_manager_grad(spec, x, report=rep)
+    B, NI, S_ = x.shape[0], spec.n_interp, prob.robot.n_spheres
+    dec = torch.zeros((B, 3, NI, S_), dtype=torch.int64)
+    dec[:, 0] = (rep[0]["flat"] << 1) | (rep[0]["hinge"] > 0).long()
+    walls = rep[1]["walls"]
+    w = walls.argmin(-1)
+    dec[:, 1] = ((w % 3) << 2) | ((w < 3).long() << 1) | (rep[1]["hinge"] > 0).long()
+    act = rep[2]["hinge"] > 0                                   # [B, NI, n_pairs]
+    for k, (a, b) in enumerate(spec.self_pairs):
+        dec[:, 2, :, a] |= act[..., k].long() << b
+        dec[:, 2, :, b] |= act[..., k].long() << a
+    assert int(act.sum()) > 0 and int((rep[0]["hinge"] > 0).sum()) > 0
+    dec = dec.to(torch.int32)
+    forced = O.guide_manager_grad(spec, x, decisions=dec)
+    assert torch.equal(forced, ref)
+    audit = O.audit_decisions(spec, x, dec)
+    assert audit["unexplained"] == 0 and audit["index_diff"] == 0 and audit["hinge_diff"] == 0 and audit["wall_diff"] == 0
+    bad = dec.clone()
+    far = (rep[0]["hinge"].abs() > 0.01).nonzero()[0]
+    bad[far[0], 0, far[1], far[2]] ^= 1                         # flip a hinge far from its boundary
+    assert O.audit_decisions(spec, x, bad)["unexplained"] >= 1
+    moved = dec.clone()
+    inner = (rep[0]["round_dist"] > 0.1).nonzero()[0]
+    moved[inner[0], 0, inner[1], inner[2]] += 2                 # neighbouring texel although the point sits well inside its cell
+    assert O.audit_decisions(spec, x, moved)["unexplained"] >= 1
 
 
 def test_no_cpu_fallback():

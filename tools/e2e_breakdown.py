@@ -9,7 +9,7 @@ import torch
 import bench
 
 dev = torch.device("cuda", 0)
-model, guide, ds, prob, sd, n_grid = bench.build_problem("cfg4", dev)
+model, guide, ds, prob, sd, n_grid, _mk = bench.build_problem("cfg4", dev)
 mid, H, B, opt, wc, ws = bench.WORKLOADS["cfg4"]
 kw = bench.sample_kwargs(guide)
 sg_host = torch.vstack((torch.as_tensor(prob.start), torch.as_tensor(prob.goal))).pin_memory()

@@ -15,22 +15,24 @@ from mpd_public_b200 import _lib
 ap = argparse.ArgumentParser()
 ap.add_argument("--workload", default="cfg4")
 ap.add_argument("--batch", type=int, default=0)
+ap.add_argument("--t", type=int, default=5, help="timestep of the forward: selects the precision (t = 5: one product, t = 20: 22-bit split)")
 args = ap.parse_args()
 dev = torch.device("cuda", 0)
-model, guide, ds, prob, sd, n_grid = bench.build_problem(args.workload, dev)
+model, guide, ds, prob, sd, n_grid, _mk = bench.build_problem(args.workload, dev)
 mid, H, B, opt, wc, ws = bench.WORKLOADS[args.workload]
 B = args.batch or B
 D = prob.robot.state_dim
 eng = model._engine()
 lib = _lib.lib()
 x = torch.randn((B, H, D), device=dev)
-eng.unet_forward_uniform(x, 5)  # loads the parameters into the engine
+eng.unet_forward_uniform(x, args.t)  # loads the parameters into the engine
 print("mega_info (in_use, G, layers, a_bytes, smem, why):", eng.mega_info(B))
+print(f"t = {args.t}: MMA products per step = {lib.mpdb_engine_step_precision(eng.handle, args.t)}")
 
 
 def body_ms(reps=50):
     ms, fl, n = C.c_float(), C.c_double(), C.c_int32()
-    _lib.check(lib.mpdb_profile_unet_body(eng.handle, _lib.fptr(x), 5, B, reps, C.byref(ms), C.byref(fl), C.byref(n),
+    _lib.check(lib.mpdb_profile_unet_body(eng.handle, _lib.fptr(x), args.t, B, reps, C.byref(ms), C.byref(fl), C.byref(n),
                                           _lib.stream_ptr(dev)))
     return ms.value, fl.value, n.value
 
@@ -42,7 +44,7 @@ for mega in (1, 0):
 eng.set_option("mega", 1)
 eng.set_option("mega_timeline", 1)
 for _ in range(3):
-    eng.unet_forward_uniform(x, 5)
+    eng.unet_forward_uniform(x, args.t)
 torch.cuda.synchronize()
 nl = 48
 ND = 16

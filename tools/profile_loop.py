@@ -14,7 +14,7 @@ ap.add_argument("--loops", type=int, default=1)
 ap.add_argument("--graph", action="store_true")
 args = ap.parse_args()
 dev = torch.device("cuda", 0)
-model, guide, ds, prob, sd, n_grid = bench.build_problem(args.workload, dev)
+model, guide, ds, prob, sd, n_grid, _mk = bench.build_problem(args.workload, dev)
 mid, H, B, opt, wc, ws = bench.WORKLOADS[args.workload]
 model.use_cuda_graph = args.graph
 hard = ds.get_hard_conditions(torch.vstack((torch.as_tensor(prob.start), torch.as_tensor(prob.goal))).to(dev), normalize=True)

@@ -11,7 +11,7 @@ import bench
 from mpd_public_b200 import _lib
 
 dev = torch.device("cuda", 0)
-model, guide, ds, prob, sd, n_grid = bench.build_problem("cfg4", dev)
+model, guide, ds, prob, sd, n_grid, _mk = bench.build_problem("cfg4", dev)
 B = 100
 model.tensor_cores = "force"
 eng = model._engine()
