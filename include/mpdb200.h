@@ -176,6 +176,13 @@ int mpdb_sample_loop(mpdb_engine* e, mpdb_guide* g, const mpdb_loop_params* p, c
  * NULL) receives n_steps + 1 entries (x_T with hard conditions, then every step), strides in floats as above. */
 int mpdb_ddim_loop(mpdb_engine* e, mpdb_guide* g, const mpdb_ddim_params* p, const float* x_init, float* x_out,
                    float* chain_out, int64_t chain_step_stride, int64_t chain_batch_stride, int32_t B, void* stream);
+/* The loop's noise — x = torch.randn(shape) (diffusion_model_base.py:165) and noise = torch.randn_like(x) per step
+ * (sample_functions.py:51) — drawn in ONE launch, bit-identical to n_draws consecutive `normal_()` calls of torch's CUDA
+ * generator on contiguous fp32 tensors of `numel` elements: out device [n_draws][numel]; state_dev device int64[2] = {seed,
+ * Philox offset of the first draw} (read when the kernel runs, so the launch can sit in a CUDA graph). The caller advances
+ * the torch generator by n_draws * mpdb_normal_offset_increment(numel, device). */
+int mpdb_normal_fill(float* out, int64_t numel, int32_t n_draws, const int64_t* state_dev, int device, void* stream);
+int64_t mpdb_normal_offset_increment(int64_t numel, int device);
 /* counter bumped whenever the engine reallocates device buffers, reloads parameters or changes an option: a caller that
  * captured mpdb_sample_loop (use_cuda_graph = 0) into its own CUDA graph must re-capture when it changes */
 int64_t mpdb_engine_generation(mpdb_engine* e);

@@ -41,6 +41,43 @@ def cosine_beta_schedule(n_diffusion_steps, s=0.008, a_min=0, a_max=0.999, dtype
     return torch.tensor(np.clip(betas, a_min=a_min, a_max=a_max), dtype=dtype)
 
 
+class _DeviceNormal:
+    """The loop's draws — randn(shape) + one randn_like per step (diffusion_model_base.py:165, sample_functions.py:51) — in
+    ONE kernel (csrc/rng.cu) that reproduces, bit for bit, what those `normal_()` calls would have drawn from torch's CUDA
+    generator, and advances that generator by exactly what they would have consumed. (seed, offset) travel through a small
+    device tensor so the launch can be replayed inside a CUDA graph."""
+
+    def __init__(self, device):
+        self.device = torch.device(device)
+        self.index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        self.state = torch.zeros(2, dtype=torch.int64, device=self.device)
+        self.lib = _lib.lib()
+
+    @staticmethod
+    def supported(device):
+        idx = torch.device(device).index
+        gen = torch.cuda.default_generators[idx if idx is not None else torch.cuda.current_device()]
+        return hasattr(gen, "get_offset") and hasattr(gen, "set_offset")
+
+    def advance(self, numel, n_draws):
+        """Reserve n_draws normal_() calls of `numel` elements in torch's generator; uploads (seed, first offset)."""
+        gen = torch.cuda.default_generators[self.index]
+        inc = int(self.lib.mpdb_normal_offset_increment(int(numel), self.index))
+        if inc <= 0:
+            raise RuntimeError("mpdb_normal_offset_increment failed")
+        seed, off = int(gen.initial_seed()), int(gen.get_offset())
+        gen.set_offset(off + n_draws * inc)
+        # the seed may use all 64 bits: reinterpret as int64 for the tensor
+        self.state.copy_(torch.tensor([seed - (1 << 64) if seed >= (1 << 63) else seed, off], dtype=torch.int64))
+
+    def fill(self, buf):
+        """buf: contiguous fp32 [n_draws, ...]; enqueues the fill on the current stream (reads self.state when it runs)."""
+        n_draws = buf.shape[0]
+        numel = buf[0].numel()
+        _lib.check(self.lib.mpdb_normal_fill(_lib.fptr(buf), int(numel), int(n_draws), C.c_void_p(self.state.data_ptr()),
+                                             self.index, _lib.stream_ptr(self.device)))
+
+
 def make_timesteps(batch_size, i, device):
     return torch.full((batch_size,), i, device=device, dtype=torch.long)
 
@@ -375,6 +412,16 @@ class GaussianDiffusionModel(nn.Module):
         eng.set_tensor_cores(self.tensor_cores)
         return eng
 
+    def _device_rng(self, device):
+        """csrc/rng.cu generator for `device` (None: `self.device_rng = False`, or a torch without generator offsets)."""
+        if not self.__dict__.get("device_rng", True) or not _DeviceNormal.supported(device):
+            return None
+        cache = self.__dict__.setdefault("_device_rngs", {})
+        key = str(torch.device(device))
+        if key not in cache:
+            cache[key] = _DeviceNormal(device)
+        return cache[key]
+
     # ------------------------------------------ sampling ------------------------------------------#
     def predict_noise_from_start(self, x_t, t, x0):
         if self.predict_epsilon:
@@ -460,8 +507,13 @@ class GaussianDiffusionModel(nn.Module):
                 cache = (key, buf, list(buf.unbind(0)))
                 self.__dict__["_noise_cache"] = cache
             noise = cache[1]
-            for view in cache[2]:
-                view.normal_()
+            rng = self._device_rng(device)
+            if rng is not None:
+                rng.advance(noise[0].numel(), noise.shape[0])
+                rng.fill(noise)
+            else:
+                for view in cache[2]:
+                    view.normal_()
         else:
             noise = noise.to(device=device, dtype=torch.float32).contiguous()
             if tuple(noise.shape) != (len(steps) + 1, *shape):
@@ -520,9 +572,14 @@ class GaussianDiffusionModel(nn.Module):
                 views = list(noise.unbind(0))
                 static_hc = {r: torch.empty((shape[0], shape[2]), device=device, dtype=torch.float32) for r in rows}
 
+                rng = self._device_rng(device)
+
                 def run_once():
-                    for v in views:
-                        v.normal_()
+                    if rng is not None:
+                        rng.fill(noise)  # one launch; (seed, offset) are read from rng.state at replay time
+                    else:
+                        for v in views:
+                            v.normal_()
                     return eng.sample_loop(noise, static_hc, handle, n_extra, float(t_start_guide),
                                            n_guide_steps if guide is not None else 0, scale_grad_by_std, list(ns),
                                            return_chain, False)
@@ -543,13 +600,15 @@ class GaussianDiffusionModel(nn.Module):
                 graph = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(graph):
                     x_out, chain = run_once()
-                entry = (graph, static_hc, x_out, chain)
+                entry = (graph, static_hc, x_out, chain, rng, noise)
                 cache[key] = entry
             except Exception as exc:  # capture not possible in this context: the plain path still works
                 self.__dict__["graph_rng"] = False
                 self.__dict__["_graph_rng_error"] = repr(exc)
                 return None
-        graph, static_hc, x_out, chain = entry
+        graph, static_hc, x_out, chain, rng, noise_buf = entry
+        if rng is not None:  # what the reference's eager draws would consume; torch's own graph-safe offsets otherwise
+            rng.advance(noise_buf[0].numel(), noise_buf.shape[0])
         for r in rows:
             v = hard_conds[r]
             if v.device != device or v.dtype != torch.float32:

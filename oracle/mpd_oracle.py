@@ -498,23 +498,25 @@ def guide_manager_grad(spec: GuideSpec, x_normalized, return_parts=False, decisi
     return (grad, parts) if return_parts else grad
 
 
-def audit_decisions(spec: GuideSpec, x_normalized, decisions, cell_tol=2e-3, hinge_tol=2e-5):
+def audit_decisions(spec: GuideSpec, x_normalized, decisions, pos_tol=1e-5):
     """Are the CUDA guide's discrete decisions for this evaluation the oracle's own, except where the oracle's deciding
-    quantity sits on the boundary? Returns a dict of counts; `unexplained` must be 0:
-      * a texel index may differ only where some coordinate of (p - lo) / cell is within `cell_tol` of a rounding boundary,
-      * a wall may differ only where the two walls' distances agree within `hinge_tol`,
-      * a hinge branch (grid, border, self pair) may differ only where |hinge argument| <= `hinge_tol`
+    quantity sits within `pos_tol` (metres: how far the two sides' sphere centres may differ, given how far their inputs
+    differ) of the decision boundary? Returns a dict of counts; `unexplained` must be 0:
+      * a texel index may differ only where some coordinate of (p - lo) / cell is within pos_tol / cell of a rounding boundary,
+      * a wall may differ only where the two walls' distances agree within 2 pos_tol,
+      * a hinge branch (grid, border, self pair) may differ only where |hinge argument| <= 2 pos_tol (sdf is 1-Lipschitz)
         (or, for a grid field, where the texel itself differs for the reason above)."""
+    hinge_tol = 2.0 * pos_tol
     rep = []
-    with torch.no_grad():
-        pass
     guide_manager_grad(spec, x_normalized, report=rep)
     dec = decode_decisions(spec, decisions)
     out = {"n": 0, "index_diff": 0, "hinge_diff": 0, "wall_diff": 0, "unexplained": 0}
-    for d, rp in zip(dec, rep):
+    grid_cells = [g.cell for g in spec.grid_fields]
+    for k, (d, rp) in enumerate(zip(dec, rep)):
+        k_cell = grid_cells[k] if k < len(grid_cells) else 1.0
         if rp["kind"] == "grid":
             idx_diff = d["flat"] != rp["flat"]
-            near = rp["round_dist"] <= cell_tol
+            near = rp["round_dist"] <= pos_tol / k_cell
             out["index_diff"] += int(idx_diff.sum())
             out["unexplained"] += int((idx_diff & ~near).sum())
             own = rp["hinge"] > 0

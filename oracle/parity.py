@@ -65,23 +65,31 @@ def check_loop_per_step(om, spec, chain, noise, hard, decisions, n_diffusion_ste
             if steps_subset is not None and i not in steps_subset:
                 continue
             t = torch.full((B,), i, dtype=torch.long)
-            oguide = None
+            oguide, pending = None, []
             if guided:
                 calls = iter(range(n_guide_steps))
 
-                def oguide(z, decs=decs, calls=calls):
+                def oguide(z, decs=decs, calls=calls, pending=pending):
                     j = next(calls)
-                    if audit:
-                        a = O.audit_decisions(spec, z, decs[j])
-                        for key in totals:
-                            totals[key] += a[key]
-                        assert a["unexplained"] == 0, (f"step i={i}, guide evaluation {j}: decisions of the CUDA guide that the "
-                                                       f"oracle cannot explain by a boundary", a)
+                    pending.append((z.clone(), decs[j]))
                     return O.guide_manager_grad(spec, z, decisions=decs[j])
             ref = om.ddpm_step(chain[k].clone(), ohc, t, noise[k + 1], oguide, n_guide_steps, scale_grad_by_std, t_start_guide,
                                noise_std)
             ref = O.apply_hard_conditioning(ref, ohc)
             e = rel(chain[k + 1], ref)
+            if guided and audit:
+                # The two sides' iterates inside this step differ by about as much as their results do (relative e, measured just
+                # above; the guide moves x by small steps): in joint space e * range / 2, at a sphere centre times the arm's reach.
+                # Decisions may differ only within that distance of their boundary — 4x margin, 1e-5 m floor.
+                reach = 1.2 if spec.robot.kind == "panda" else 1.0
+                half_range = float(((spec.maxs - spec.mins) / 2)[:spec.robot.q_dim].max())
+                pos_tol = 1e-5 + 4.0 * e * half_range * reach
+                for j, (z, dj) in enumerate(pending):
+                    a = O.audit_decisions(spec, z, dj, pos_tol=pos_tol)
+                    for key in totals:
+                        totals[key] += a[key]
+                    assert a["unexplained"] == 0, (f"step i={i}, guide evaluation {j}: decisions of the CUDA guide that the oracle "
+                                                   f"cannot explain by a boundary within {pos_tol:.2e} m", a)
             if i == n_diffusion_steps - 1:
                 t_last = e
                 assert e < tol_t_last, (i, e)

@@ -322,3 +322,52 @@ def test_prior_then_guide_post_loop_chain():
     ref_chain = torch.stack(post, dim=0)
     out, chain = guide.guide_steps(x, hc, n, return_chain=True)
     assert chain.shape == ref_chain.shape and torch.equal(chain, ref_chain) and torch.equal(out, ref_chain[-1])
+
+
+@pytest.mark.parametrize("shape", [(7,), (100, 64, 14), (512, 128, 14), (3, 1000, 1001)])
+def test_device_normal_reproduces_torch_cuda_generator(shape):
+    """csrc/rng.cu: all the loop's draws in ONE launch, bit-identical to consecutive `torch.randn(shape, device='cuda')` /
+    `randn_like` calls (the reference's generator consumption, diffusion_model_base.py:165 + sample_functions.py:51), and the
+    torch generator ends up exactly where those calls would have left it."""
+    from mpd_public_b200.diffusion_model import _DeviceNormal
+    dev = torch.device("cuda", 0)
+    assert _DeviceNormal.supported(dev)
+    n_draws = 5 if np.prod(shape) > 1e6 else 31
+    for seed in (0, 123456789, 2 ** 63 + 11):
+        torch.manual_seed(seed)
+        torch.randn(33, device=dev)                       # a draw before: the offset does not start at zero
+        ref = torch.stack([torch.randn(shape, device=dev) for _ in range(n_draws)])
+        tail_ref = torch.randn(5, device=dev)
+        torch.manual_seed(seed)
+        torch.randn(33, device=dev)
+        rng = _DeviceNormal(dev)
+        buf = torch.empty((n_draws, *shape), device=dev)
+        rng.advance(buf[0].numel(), n_draws)
+        rng.fill(buf)
+        tail = torch.randn(5, device=dev)
+        assert torch.equal(buf, ref), (shape, seed, float((buf - ref).abs().max()))
+        assert torch.equal(tail, tail_ref), "the generator must advance exactly as the eager draws advance it"
+
+
+def test_run_inference_same_seed_with_and_without_device_rng():
+    """Identical seeds => identical samples whether the noise comes from torch's own normal_() launches or from the one-launch
+    generator, eager or graph-replayed (north-star: 'outputs match the reference on identical seeds')."""
+    model = cuda_model("pm2d_opt0_h64")
+    model.tensor_cores = "auto"
+    B, H, D = 9, 64, 4
+    hard = {0: torch.linspace(-0.5, 0.5, D).cuda(), H - 1: torch.linspace(0.4, -0.4, D).cuda()}
+    kw = dict(n_diffusion_steps_without_noise=C.N_EXTRA, noise_std_extra_schedule_fn=lambda _t: C.NOISE_STD)
+    outs = {}
+    try:
+        for dev_rng in (False, True):
+            for graphed in (False, True):
+                model.device_rng, model.graph_rng = dev_rng, graphed
+                torch.manual_seed(2024)
+                outs[(dev_rng, graphed)] = (model.run_inference(None, hard, n_samples=B, horizon=H, return_chain=True, **kw),
+                                            torch.randn(3, device="cuda"))
+    finally:
+        model.device_rng, model.graph_rng = True, True
+    base = outs[(False, False)]
+    for key, (chain, tail) in outs.items():
+        assert torch.equal(chain, base[0]), key
+        assert torch.equal(tail, base[1]), key

@@ -107,9 +107,12 @@ def test_mega_repeated_runs_are_bit_identical():
 
 def test_fused_projection_and_ddpm_update_match_the_separate_kernel():
     """final_conv.1 + posterior mean + noise + hard conditions inside the cluster kernel's last epilogue (option
-    fuse_final) against the separate final_kernel launch: same chain up to the rounding of the 32-term projection."""
+    fuse_final) against the separate final_kernel launch: same chain up to the rounding of the 32-term projection. Run with
+    the 22-bit split on every step ('force'): a one-product step rounds activations to fp16, which turns a last-bit difference
+    of its input into a difference of the size of its own rounding error (~1e-3 * amplification), so alternative code paths
+    agree to ~1e-4 there instead of ~1e-6 (checked below with that bound)."""
     model = cuda_model("panda_opt1_h64")
-    model.tensor_cores = "auto"
+    model.tensor_cores = "force"
     eng = model._engine()
     B, H, D = 21, 64, 14
     n_iters = C.T_DIFF + C.N_EXTRA
@@ -124,10 +127,19 @@ def test_fused_projection_and_ddpm_update_match_the_separate_kernel():
             chains[fuse] = model.run_inference(None, hard, n_samples=B, horizon=H, return_chain=True, noise=noise, **kw)
     finally:
         eng.set_option("fuse_final", 1)
+        model.tensor_cores = "auto"
     assert torch.isfinite(chains[1]).all()
     for k, v in hard.items():
         assert torch.equal(chains[1][:, :, k, :], v.expand(n_iters + 1, B, D))
     assert rel(chains[1], chains[0]) < 2e-5, rel(chains[1], chains[0])
+    model.tensor_cores = "auto"
+    try:
+        for fuse in (1, 0):
+            eng.set_option("fuse_final", fuse)
+            chains[fuse] = model.run_inference(None, hard, n_samples=B, horizon=H, return_chain=True, noise=noise, **kw)
+    finally:
+        eng.set_option("fuse_final", 1)
+    assert rel(chains[1], chains[0]) < 2e-3, rel(chains[1], chains[0])
 
 
 def test_api_path_replayed_as_one_graph_matches_eager_draws():
@@ -166,7 +178,7 @@ def test_api_path_replayed_as_one_graph_matches_eager_draws():
         assert torch.equal(chain_e, chain_g) and torch.equal(chain_g[-1], graphed)
         eng.set_option("fuse_final", 0)     # bumps the engine generation: the cached graph must not be reused
         refused, _ = run(hard_a, True)
-        assert rel(refused, graphed) < 2e-5
+        assert rel(refused, graphed) < 2e-3  # another code path for the projection; one-product steps: see the test above
     finally:
         eng.set_option("fuse_final", 1)
         model.graph_rng = True
@@ -195,6 +207,6 @@ def test_guide_evaluations_of_a_step_in_one_launch_are_bit_identical(case):
             eng.set_option("fuse_guide", fuse)
             chains[fuse] = model.run_inference(None, hard, n_samples=batch, horizon=H, return_chain=True, noise=noise, **kw)
     finally:
-        eng.set_option("fuse_guide", 0)
+        eng.set_option("fuse_guide", 1)
     assert torch.isfinite(chains[1]).all()
     assert torch.equal(chains[1], chains[0])

@@ -435,7 +435,9 @@ def test_errors_are_loud():
     with pytest.raises(RuntimeError):
         model.model(torch.zeros(2, 64, 4), torch.zeros(2, dtype=torch.long), None)  # CPU tensor: no fallback
     with pytest.raises(RuntimeError):
-        model.model(torch.zeros(2, 32, 4, device="cuda"), torch.zeros(2, dtype=torch.long, device="cuda"), None)
+        model.model(torch.zeros(2, 36, 4, device="cuda"), torch.zeros(2, dtype=torch.long, device="cuda"), None)  # 36 % 8 != 0
+    with pytest.raises(RuntimeError):
+        model.model(torch.zeros(2, 64, 5, device="cuda"), torch.zeros(2, dtype=torch.long, device="cuda"), None)  # state_dim
     with pytest.raises(RuntimeError):
         model.model(torch.zeros(2, 64, 4, device="cuda"), torch.full((2,), 99, dtype=torch.long, device="cuda"), None)
     with pytest.raises(NotImplementedError):
