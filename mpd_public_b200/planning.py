@@ -56,6 +56,25 @@ class PlanningTask:
             self._fields = f
         return self._fields
 
+    def random_coll_free_q(self, n_samples=1, max_tries=10000, clearance=0.08, seed=None):
+        """torch_robotics PlanningTask.random_coll_free_q (call site inference.py:161): uniformly sampled configurations whose
+        collision spheres keep `clearance` from every object and stay inside the workspace. Host-side rejection sampling on the
+        analytic primitives (not on the timed path). Returns [n_samples, q_dim] on the task's device."""
+        rng = np.random.default_rng(seed if seed is not None else int(torch.randint(0, 2 ** 31 - 1, (1,))))
+        spec, e = self.robot.spec, self.env
+        sph = np.concatenate([np.asarray(e.spheres).reshape(-1, e.dim + 1), np.asarray(e.extra_spheres).reshape(-1, e.dim + 1)])
+        box = np.concatenate([np.asarray(e.boxes).reshape(-1, 2 * e.dim), np.asarray(e.extra_boxes).reshape(-1, 2 * e.dim)])
+        out = []
+        for _ in range(max_tries):
+            q = rng.uniform(spec.q_min, spec.q_max)
+            c = S.robot_sphere_centers_numpy(spec, q)
+            d = S.sdf_analytic_numpy(c, sph, box) - spec.sphere_radius
+            if d.min() > clearance and np.all((c > e.limits[0] + 0.05) & (c < e.limits[1] - 0.05)):
+                out.append(q)
+                if len(out) == n_samples:
+                    return torch.as_tensor(np.stack(out), dtype=torch.float32, device=self.device)
+        raise ValueError("No collision free configuration was found")
+
     def get_collision_fields_extra_objects(self):
         return [f for f in self.get_collision_fields()[1:] if isinstance(f, GridSDFField)]
 
