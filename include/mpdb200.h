@@ -146,7 +146,8 @@ int mpdb_engine_set_schedule(mpdb_engine* e, const float* sqrt_recip_alphas_cump
  * evaluation; 0: one launch per evaluation); "prec1_amp_limit" (default 0.11; 0 disables): loop steps whose eps-to-mean
  * amplification posterior_mean_coef1[t] * sqrt(1/abar_t - 1) is at most this issue one fp16 product per MMA step instead of
  * the three of the 22-bit split ("tc_mode" = 2 always uses the split);
- * "fuse_rtb" = 1 (default: per-layer path runs residual blocks with C_out <= 128 as one cluster-fused launch);
+ * "fuse_rtb" = 1 (default: the per-layer path runs a residual block with C_out <= 128 as one cluster-fused launch while its
+ * CTAs fit one wave; larger batches run every layer as a persistent kernel with double-buffered accumulators) | 2 always | 0 never;
  * "alias_buffers" = 1 (default) shares activation storage between layers with disjoint lifetimes, 0 keeps one buffer
  * per layer (needed by mpdb_engine_read_buffer; disables the cluster kernel); "timeline" / "mega_timeline" = 1 enable the
  * clock64 stamps read by mpdb_engine_read_timeline / mpdb_engine_read_mega_timeline */

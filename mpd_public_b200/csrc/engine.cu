@@ -92,7 +92,8 @@ struct mpdb_engine {
     unsigned short* work_tc = nullptr;    // activations in tensor-core layout (fp16 hi / scaled-lo planes)
     std::vector<long long> tc_off, tc_plane;  // per buffer: offset of the hi plane, elements per plane
     std::vector<long long> cm_off;            // per buffer: float offset of its (possibly shared) physical slot
-    int fuse_rtb = 1;          // cluster-fused residual blocks on the tensor-core path
+    int fuse_rtb = 1;          // cluster-fused residual blocks on the tensor-core path (see can_fuse_rtb)
+    int sm_count = 148;
     int fuse_max_co = []() { const char* v = getenv("MPDB_FUSE_MAX_CO"); return v ? atoi(v) : 128; }();  // widest fused block (measured: 0 -> 11.85, 32 -> 11.67, 64 -> 11.55, 128 -> 11.47 ms per loop)
     // whole-forward persistent cluster kernel (unet_mega.cu)
     long long generation = 0;  // bumped whenever device buffers are reallocated or an option changes: launches captured
@@ -688,10 +689,16 @@ static bool mega_usable(mpdb_engine* e, int B, std::string* why = nullptr) {
 }
 
 // Can ops[i], ops[i+1] (the two Conv1dBlocks of a ResidualTemporalBlock) run as one cluster-fused launch?
-static bool can_fuse_rtb(mpdb_engine* e, size_t i, bool tc) {
+// fuse_rtb = 1 (default): only while the block's CTAs fit one wave — beyond that the persistent per-layer kernel (operand
+// prefetch across work items, double-buffered accumulators) beats one cluster launch per block; 2: always; 0: never.
+static bool can_fuse_rtb(mpdb_engine* e, size_t i, bool tc, int B) {
     if (!tc || !e->fuse_rtb || !e->alias_buffers || e->timeline || i + 1 >= e->ops.size()) return false;
     const ConvOp& a = e->ops[i];
     const ConvOp& b = e->ops[i + 1];
+    if (e->fuse_rtb == 1) {
+        const int SPT = TC_RT / (a.L_in + 4);
+        if (SPT < 1 || (long long)((B + SPT - 1) / SPT) * (a.CO / TC_NT) > e->sm_count) return false;
+    }
     return a.mode == MODE_CONV5 && b.mode == MODE_CONV5 && a.tc_ok && b.tc_ok && a.cond >= 0 && b.in0 == a.out && b.in1 < 0 &&
            a.res0 == -2 && a.CO == b.CO && a.CO <= 128 && a.CO <= e->fuse_max_co && a.L_in == b.L_in;
 }
@@ -758,7 +765,7 @@ static int run_unet_body(mpdb_engine* e, const float* x, const long long* t_dev,
         return launch_unet_mega(P, st);
     }
     for (size_t i = 0; i < e->ops.size(); ++i) {
-        if (can_fuse_rtb(e, i, tc)) {
+        if (can_fuse_rtb(e, i, tc, B)) {
             if (launch_rtb(e, i, t_dev, t_uniform, B, st)) return 1;
             ++i;  // the second conv of the block ran inside the fused launch
             continue;
@@ -821,6 +828,7 @@ extern "C" int mpdb_engine_create(const mpdb_engine_config* cfg, int device, mpd
     std::unique_ptr<mpdb_engine> e(new mpdb_engine());
     e->cfg = *cfg;
     e->device = device;
+    MPDB_CHECK_CUDA(cudaDeviceGetAttribute(&e->sm_count, cudaDevAttrMultiProcessorCount, device));
     PlanBuilder pb;
     pb.e = e.get();
     if (build_plan(e.get(), pb)) return 2;
@@ -894,7 +902,8 @@ extern "C" int mpdb_engine_set_option(mpdb_engine* e, const char* name, double v
         MPDB_REQUIRE(value == 0 || value == 1 || value == 2, "tc_mode must be 0 (off), 1 (auto) or 2 (force)");
         e->tc_mode = (int)value;
     } else if (n == "fuse_rtb") {
-        e->fuse_rtb = value != 0;
+        MPDB_REQUIRE(value == 0 || value == 1 || value == 2, "fuse_rtb must be 0 (never), 1 (while the block fits one wave) or 2 (always)");
+        e->fuse_rtb = (int)value;
         drop_graphs(e);
     } else if (n == "mega_timeline") {
         if (value != 0 && !e->mega_dbg) {
@@ -1479,7 +1488,7 @@ extern "C" int mpdb_profile_forward(mpdb_engine* e, const float* x, int32_t t, i
     int k = 0;
     for (size_t i = 0; i < e->ops.size(); ++i) {
         const ConvOp& op = e->ops[i];
-        const bool fused = can_fuse_rtb(e, i, tc);
+        const bool fused = can_fuse_rtb(e, i, tc, B);
         MPDB_CHECK_CUDA(cudaEventRecord(ev0, st));
         for (int r = 0; r < reps; ++r) {
             if (fused) { if (launch_rtb(e, i, nullptr, t, B, st)) return 1; }

@@ -394,9 +394,8 @@ __global__ void __launch_bounds__(GUIDE_THREADS, OCC) guide_step_kernel(const __
                             code = (bc << 1) | (act ? 1 : 0);
                         } else {
                             // self-collision: every listed partner t with |c_s - c_t| - r_s - r_t < margin pushes s away
-                            const unsigned mask = g.self_pairs[s];
-                            for (int t = 0; t < S; ++t) {
-                                if (!((mask >> t) & 1u)) continue;
+                            for (unsigned mask = g.self_pairs[s]; mask != 0u; mask &= mask - 1u) {
+                                const int t = __ffs((int)mask) - 1;  // listed partners only
                                 const float dx = __fsub_rn(p0, cen[(t * 3 + 0) * FK_ROWS]), dy = __fsub_rn(p1, cen[(t * 3 + 1) * FK_ROWS]),
                                             dz = __fsub_rn(p2, cen[(t * 3 + 2) * FK_ROWS]);
                                 const float n = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));

@@ -40,41 +40,52 @@ namespace mpdb {
 //   warp  17    MMA issuer 0: A_hi x [W_hi | W_lo] (N = 64) -> columns [0,64)   (second accumulator: +128)
 //   warp  18    MMA issuer 1: A_lo x W_hi        (N = 32) -> columns [64,96)  (second accumulator: +128)
 constexpr int TCL_THREADS = TC_THREADS + 96;
-constexpr int TCL_TMEM_COLS = 256;
+constexpr int TCL_ACC_COLS = 256;   // one accumulator stage: main [0,96) + second accumulator [128,224)
+constexpr int TCL_TMEM_COLS = 512;  // two stages: the MMAs of work item k+1 run under the epilogue of item k
 
+// PERSISTENT: a CTA walks the work items (row tile, 32-channel chunk) it = blockIdx.x, blockIdx.x + gridDim.x, ... of the layer
+// (grid = min(#items, #SMs)). The operand ring runs on across items (the producer prefetches the next item's chunks while
+// the current one is in its epilogue), the accumulators are double-buffered in TMEM (acc_full / acc_empty barriers per
+// stage; the epilogue releases a stage as soon as its values are in registers), so per item the CTA pays
+// max(MMA + operand streaming, epilogue) instead of setup + first-copy latency + MMA + epilogue + teardown: at 512
+// trajectories per GPU a layer is 500-1000 items on 148 SMs and one-CTA-per-item launches spent ~10 us per item on ~2 us of work.
 template <int MODE, int GS>
-__global__ void __launch_bounds__(TCL_THREADS, 1) conv5_tc_kernel(TcConvArgs a) {
+__global__ void __launch_bounds__(TCL_THREADS, 1) conv5_tc_kernel(const __grid_constant__ TcConvArgs a) {
     constexpr int NTAPS = MODE == TCM_CONV5 ? 5 : MODE == TCM_DOWN ? 3 : 4;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     // carve-up: stages | barriers | tmem slot | epilogue scratch
     unsigned char* stages = smem_raw;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + TC_STAGES * TC_STAGE_BYTES);  // full[S], empty[S], done
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_STAGES + 1);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + TC_STAGES * TC_STAGE_BYTES);  // full[S], empty[S], acc_full[2], acc_empty[2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_STAGES + 4);
     float* part = reinterpret_cast<float*>(tmem_slot + 4);  // GroupNorm scratch: [2][128][8] floats + [2][12][8] doubles
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int tile = blockIdx.x, ntile = blockIdx.y;
-    const bool dbg = a.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0;
+    const bool dbg = a.dbg != nullptr && blockIdx.x == 0;
     if (dbg && tid == 64) a.dbg[0] = clock64();
-    const int n0 = ntile * TC_NT;
     const int Lp = a.L + 4;
     const int SPT = TC_RT / Lp;
     const int n_main = (a.c0 + a.c1) / TC_KCH;
     const int n_res = a.res_w ? (a.rc0 + a.rc1) / TC_KCH : 0;
     const int n_steps = n_main + n_res;
+    const int NC = a.CO / TC_NT;
+    const int n_items = ((a.B + SPT - 1) / SPT) * NC;  // item = tile * NC + ntile
     // precision 1 (a.prec == 1, engine.cu step_prec): one fp16 product per MMA step; the two issuers split it by K-group
     // into separate accumulators ([0,32) and [64,96)), the lo planes are neither loaded nor written
     const bool p1 = a.prec == 1;
 
     const uint32_t stages_u32 = smem_u32(stages);
-    const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + TC_STAGES), done_bar = smem_u32(bars + 2 * TC_STAGES);
+    const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + TC_STAGES);
+    const uint32_t acc_full0 = smem_u32(bars + 2 * TC_STAGES), acc_empty0 = acc_full0 + 16;
 
     if (tid == 0) {
         for (int s = 0; s < TC_STAGES; ++s) {
             mbar_init(full0 + 8 * s, 1);
             mbar_init(empty0 + 8 * s, 2);  // both issuers release a stage
         }
-        mbar_init(done_bar, 2);
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(acc_full0 + 8 * s, 2);                  // both issuers' MMAs of the item have retired
+            mbar_init(acc_empty0 + 8 * s, TC_THREADS / 32);   // every epilogue warp has read its part of the stage
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {  // TMEM allocation is a warp-wide operation; the same warp frees it at the end
@@ -90,13 +101,14 @@ __global__ void __launch_bounds__(TCL_THREADS, 1) conv5_tc_kernel(TcConvArgs a) 
     if (dbg && tid == 64) a.dbg[1] = clock64();  // setup done (barriers, TMEM)
 
     if (warp == TC_THREADS / 32) {
-        // ===== producer warp: K-chunk i -> stage i % STAGES (bulk-async copies, completion counted on the stage's mbarrier).
-        // Weights are constants: the first STAGES chunks' weight copies are issued before the dependency wait, so under
-        // programmatic dependent launch they overlap the previous kernel's epilogue. Activations follow it. =====
-        auto produce = [&](int i, bool weights, bool acts) {
+        // ===== producer warp: K-chunk i of the CTA's item sequence -> stage i % STAGES (bulk-async copies, completion counted on
+        // the stage's mbarrier). Weights are constants: the first chunks' weight copies are issued before the dependency wait,
+        // so under programmatic dependent launch they overlap the previous kernel's epilogue. Activations follow it. =====
+        auto produce = [&](int i, int item, int c_step, bool weights, bool acts) {
+            const int tile = item / NC, ntile = item - tile * NC;
             const int s = i % TC_STAGES;
-            const bool is_res = i >= n_main;
-            const int c = is_res ? i - n_main : i;
+            const bool is_res = c_step >= n_main;
+            const int c = is_res ? c_step - n_main : c_step;
             const int ntaps = is_res ? 1 : NTAPS;
             const uint32_t bbytes = 2u * ntaps * TC_B_TAP_BYTES;
             const uint32_t st = stages_u32 + (uint32_t)s * TC_STAGE_BYTES;
@@ -118,144 +130,168 @@ __global__ void __launch_bounds__(TCL_THREADS, 1) conv5_tc_kernel(TcConvArgs a) 
                 if (!p1) bulk_g2s_elect(st + TC_A_PLANE_BYTES, alo + aoff, TC_A_PLANE_BYTES, full0 + 8 * s);
             }
         };
-        for (int i = 0; i < n_steps && i < TC_STAGES; ++i) produce(i, true, false);
+        // the first min(STAGES, chunks of this CTA) chunks: weights before the dependency wait, activations after it
+        int i = 0, pre = 0;
+        for (int item = blockIdx.x; item < n_items && pre < TC_STAGES; item += gridDim.x)
+            for (int c = 0; c < n_steps && pre < TC_STAGES; ++c, ++pre) produce(pre, item, c, true, false);
         pdl_wait();
-        for (int i = 0; i < n_steps && i < TC_STAGES; ++i) produce(i, false, true);
-        for (int i = TC_STAGES; i < n_steps; ++i) {
-            mbar_wait(empty0 + 8 * (i % TC_STAGES), ((uint32_t)(i / TC_STAGES) & 1u) ^ 1u);
-            __syncwarp();
-            produce(i, true, true);
-        }
+        pre = 0;
+        for (int item = blockIdx.x; item < n_items && pre < TC_STAGES; item += gridDim.x)
+            for (int c = 0; c < n_steps && pre < TC_STAGES; ++c, ++pre) produce(pre, item, c, false, true);
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x)
+            for (int c = 0; c < n_steps; ++c, ++i) {
+                if (i < TC_STAGES) continue;  // issued above
+                mbar_wait(empty0 + 8 * (i % TC_STAGES), ((uint32_t)(i / TC_STAGES) & 1u) ^ 1u);
+                __syncwarp();
+                produce(i, item, c, true, true);
+            }
     } else if (warp > TC_THREADS / 32) {
         // ===== two MMA-issue warps =====
         const int which = __shfl_sync(0xffffffffu, warp, 0) - (TC_THREADS / 32 + 1);
         const uint32_t idesc = (which == 0 && !p1) ? tc_idesc(128, 2 * TC_NT) : tc_idesc(128, TC_NT);
-        const uint32_t col0 = __shfl_sync(0xffffffffu, tmem_base, 0) + (which == 0 ? 0u : 2u * TC_NT);
+        const uint32_t colw = __shfl_sync(0xffffffffu, tmem_base, 0) + (which == 0 ? 0u : 2u * TC_NT);
         constexpr uint32_t desc_hi = (128u >> 4) | (1u << 14);                      // SBO = 128 B, descriptor version 1
         constexpr uint32_t a_lo_fixed = ((uint32_t)(TC_RT * 16) >> 4) << 16;        // activation tile: LBO = 132 rows x 16 B
         constexpr uint32_t b_lo_fixed = ((2u * TC_NT * 16u) >> 4) << 16;            // weight tile: LBO = 64 rows x 16 B
         constexpr uint32_t kstep_a = (2 * TC_RT * 16) >> 4, kstep_b = (2 * (2 * TC_NT * 16)) >> 4, tap_b = (2 * TC_B_TAP_BYTES) >> 4;
-        uint32_t acc0 = 0u, acc1 = 0u;
-        for (int i = 0; i < n_steps; ++i) {
-            const int s = i % TC_STAGES;
-            const uint32_t st = stages_u32 + (uint32_t)s * TC_STAGE_BYTES;
-            const uint32_t a_lo = (((st + ((which == 1 && !p1) ? (uint32_t)TC_A_PLANE_BYTES : 0u)) >> 4) & 0x3FFFu) | a_lo_fixed;
-            const uint32_t b_lo = (((st + 2 * TC_A_PLANE_BYTES) >> 4) & 0x3FFFu) | b_lo_fixed;  // rows [0,32) = W_hi, [32,64) = W_lo
-            mbar_wait(full0 + 8 * s, (uint32_t)(i / TC_STAGES) & 1u);
+        int i = 0, k = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++k) {
+            const int stage = k & 1;
+            const uint32_t col0 = colw + (uint32_t)stage * TCL_ACC_COLS;
+            // the epilogue of the item that used this stage two items ago has emptied it (the first use of a stage passes)
+            mbar_wait(acc_empty0 + 8 * stage, (((uint32_t)k >> 1) & 1u) ^ 1u);
             tc_fence_after();
-            if (i >= n_main) {  // fused 1x1 residual conv: centre row (+2), second accumulator
-#pragma unroll
-                for (int kk = 0; kk < TC_KCH / 16; ++kk) {
-                    if (p1 && kk != which) continue;
-                    tc_mma_bf16_elect32(col0 + 128, a_lo + kk * kstep_a + 2, desc_hi, b_lo + kk * kstep_b, desc_hi, idesc, acc1);
-                    acc1 = 1u;
-                }
-            } else {
-#pragma unroll
-                for (int tap = 0; tap < NTAPS; ++tap) {
-                    // row shift of the tap (in 16-byte rows; +2 is the centre) and the accumulator it feeds
-                    //   CONV5: taps -2..2 -> shifts 0..4           DOWN (k3, pad 1): taps -1..1 -> shifts 1..3
-                    //   UP  : packed taps [W1, W3 | W0, W2]: even = W1 x[m] + W3 x[m-1], odd = W0 x[m+1] + W2 x[m]
-                    const int shift = MODE == TCM_CONV5 ? tap : MODE == TCM_DOWN ? tap + 1 : (tap == 0 ? 2 : tap == 1 ? 1 : tap == 2 ? 3 : 2);
-                    const bool second_acc = MODE == TCM_UP && tap >= 2;
+            uint32_t acc0 = 0u, acc1 = 0u;
+            for (int c = 0; c < n_steps; ++c, ++i) {
+                const int s = i % TC_STAGES;
+                const uint32_t st = stages_u32 + (uint32_t)s * TC_STAGE_BYTES;
+                const uint32_t a_lo = (((st + ((which == 1 && !p1) ? (uint32_t)TC_A_PLANE_BYTES : 0u)) >> 4) & 0x3FFFu) | a_lo_fixed;
+                const uint32_t b_lo = (((st + 2 * TC_A_PLANE_BYTES) >> 4) & 0x3FFFu) | b_lo_fixed;  // rows [0,32) = W_hi, [32,64) = W_lo
+                mbar_wait(full0 + 8 * s, (uint32_t)(i / TC_STAGES) & 1u);
+                tc_fence_after();
+                if (c >= n_main) {  // fused 1x1 residual conv: centre row (+2), second accumulator
 #pragma unroll
                     for (int kk = 0; kk < TC_KCH / 16; ++kk) {
                         if (p1 && kk != which) continue;
-                        if (second_acc) { tc_mma_bf16_elect32(col0 + 128, a_lo + kk * kstep_a + shift, desc_hi, b_lo + tap * tap_b + kk * kstep_b, desc_hi, idesc, acc1); acc1 = 1u; }
-                        else { tc_mma_bf16_elect32(col0, a_lo + kk * kstep_a + shift, desc_hi, b_lo + tap * tap_b + kk * kstep_b, desc_hi, idesc, acc0); acc0 = 1u; }
+                        tc_mma_bf16_elect32(col0 + 128, a_lo + kk * kstep_a + 2, desc_hi, b_lo + kk * kstep_b, desc_hi, idesc, acc1);
+                        acc1 = 1u;
+                    }
+                } else {
+#pragma unroll
+                    for (int tap = 0; tap < NTAPS; ++tap) {
+                        // row shift of the tap (in 16-byte rows; +2 is the centre) and the accumulator it feeds
+                        //   CONV5: taps -2..2 -> shifts 0..4           DOWN (k3, pad 1): taps -1..1 -> shifts 1..3
+                        //   UP  : packed taps [W1, W3 | W0, W2]: even = W1 x[m] + W3 x[m-1], odd = W0 x[m+1] + W2 x[m]
+                        const int shift = MODE == TCM_CONV5 ? tap : MODE == TCM_DOWN ? tap + 1 : (tap == 0 ? 2 : tap == 1 ? 1 : tap == 2 ? 3 : 2);
+                        const bool second_acc = MODE == TCM_UP && tap >= 2;
+#pragma unroll
+                        for (int kk = 0; kk < TC_KCH / 16; ++kk) {
+                            if (p1 && kk != which) continue;
+                            if (second_acc) { tc_mma_bf16_elect32(col0 + 128, a_lo + kk * kstep_a + shift, desc_hi, b_lo + tap * tap_b + kk * kstep_b, desc_hi, idesc, acc1); acc1 = 1u; }
+                            else { tc_mma_bf16_elect32(col0, a_lo + kk * kstep_a + shift, desc_hi, b_lo + tap * tap_b + kk * kstep_b, desc_hi, idesc, acc0); acc0 = 1u; }
+                        }
                     }
                 }
+                tc_commit_elect(empty0 + 8 * s);  // frees the stage when both issuers' MMAs that read it have retired
             }
-            tc_commit_elect(empty0 + 8 * s);  // frees the stage when both issuers' MMAs that read it have retired
+            tc_commit_elect(acc_full0 + 8 * stage);  // accumulators of this item complete
         }
-        tc_commit_elect(done_bar);  // accumulators complete
-        // main loop over: let the next kernel start its prologue (barriers, TMEM, weight prefetch) under our epilogue
+        // main loop over: let the next kernel start its prologue (barriers, TMEM, weight prefetch) under our last epilogues
         if (which == 0 && lane == 0) pdl_launch_dependents();
         if (dbg && which == 0 && lane == 0) a.dbg[3] = clock64();  // all MMAs issued
     } else {
         // ===== epilogue: 16 warps. TMEM lane quarter q = warp & 3 (hardware rule: a warp reads lanes 32*(warp%4)..+31),
-        // column group cg = warp >> 2 -> each thread owns 8 consecutive channels of one row. Per-thread geometry and
+        // column group cg = warp >> 2 -> each thread owns 8 consecutive channels of one row. Per-item geometry and
         // every parameter / residual value this thread will need are fetched BEFORE waiting for the accumulators, so
         // their global-memory latency overlaps the MMA main loop =====
         pdl_wait();  // nothing produced by the previous kernel is read, and nothing is written, before this
         const int q = warp & 3, cg = warp >> 2;
         const int r = q * 32 + lane;  // padded row of the tile = TMEM lane
         const int s = r / Lp, l = r - s * Lp;
-        const int b = tile * SPT + s;
-        const bool valid = (s < SPT) && (l < a.L) && (b < a.B);
-        const int c8 = n0 + cg * 8;  // first of this thread's 8 output channels
         const bool full = a.raw_out == nullptr;
         const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        float4 pb0 = z4, pb1 = z4, pg0 = z4, pg1 = z4, pe0 = z4, pe1 = z4, pc0 = z4, pc1 = z4, pr0 = z4, pr1 = z4;
-        float rid[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        if (full) {
-            pb0 = *reinterpret_cast<const float4*>(a.bias + c8); pb1 = *reinterpret_cast<const float4*>(a.bias + c8 + 4);
-            if (MODE == TCM_CONV5) {
-                pg0 = *reinterpret_cast<const float4*>(a.gamma + c8); pg1 = *reinterpret_cast<const float4*>(a.gamma + c8 + 4);
-                pe0 = *reinterpret_cast<const float4*>(a.beta + c8); pe1 = *reinterpret_cast<const float4*>(a.beta + c8 + 4);
-            }
-            if (a.cond != nullptr && valid) {
-                const int tt = a.t_dev ? (int)a.t_dev[b] : a.t_uniform;
-                const float* cp = a.cond + (size_t)tt * a.CO + c8;
-                pc0 = *reinterpret_cast<const float4*>(cp); pc1 = *reinterpret_cast<const float4*>(cp + 4);
-            }
-            if (a.res_w != nullptr) {
-                pr0 = *reinterpret_cast<const float4*>(a.res_bias + c8); pr1 = *reinterpret_cast<const float4*>(a.res_bias + c8 + 4);
-            } else if (a.res_cm != nullptr && valid) {
-                const float* rp = a.res_cm + ((size_t)b * a.CO + c8) * Lp + 2 + l;
+        int k = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++k) {
+            const int tile = item / NC, ntile = item - tile * NC;
+            const int stage = k & 1;
+            const int b = tile * SPT + s;
+            const bool valid = (s < SPT) && (l < a.L) && (b < a.B);
+            const int c8 = ntile * TC_NT + cg * 8;  // first of this thread's 8 output channels
+            float4 pb0 = z4, pb1 = z4, pg0 = z4, pg1 = z4, pe0 = z4, pe1 = z4, pc0 = z4, pc1 = z4, pr0 = z4, pr1 = z4;
+            float rid[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            if (full) {
+                pb0 = *reinterpret_cast<const float4*>(a.bias + c8); pb1 = *reinterpret_cast<const float4*>(a.bias + c8 + 4);
+                if (MODE == TCM_CONV5) {
+                    pg0 = *reinterpret_cast<const float4*>(a.gamma + c8); pg1 = *reinterpret_cast<const float4*>(a.gamma + c8 + 4);
+                    pe0 = *reinterpret_cast<const float4*>(a.beta + c8); pe1 = *reinterpret_cast<const float4*>(a.beta + c8 + 4);
+                }
+                if (a.cond != nullptr && valid) {
+                    const int tt = a.t_dev ? (int)a.t_dev[b] : a.t_uniform;
+                    const float* cp = a.cond + (size_t)tt * a.CO + c8;
+                    pc0 = *reinterpret_cast<const float4*>(cp); pc1 = *reinterpret_cast<const float4*>(cp + 4);
+                }
+                if (a.res_w != nullptr) {
+                    pr0 = *reinterpret_cast<const float4*>(a.res_bias + c8); pr1 = *reinterpret_cast<const float4*>(a.res_bias + c8 + 4);
+                } else if (a.res_cm != nullptr && valid) {
+                    const float* rp = a.res_cm + ((size_t)b * a.CO + c8) * Lp + 2 + l;
 #pragma unroll
-                for (int j = 0; j < 8; ++j) rid[j] = rp[(size_t)j * Lp];
+                    for (int j = 0; j < 8; ++j) rid[j] = rp[(size_t)j * Lp];
+                }
             }
-        }
 
-        mbar_wait(done_bar, 0);
-        __syncwarp();
-        tc_fence_after();
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + cg * 8;
-        if (dbg && tid == 64) a.dbg[4] = clock64();  // accumulators ready
-        float v[8];
-        tc_load_acc(taddr, p1, v);
-        if (dbg && tid == 64) a.dbg[5] = clock64();  // TMEM read
+            mbar_wait(acc_full0 + 8 * stage, ((uint32_t)k >> 1) & 1u);
+            __syncwarp();
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)stage * TCL_ACC_COLS + cg * 8;
+            if (dbg && tid == 64 && k == 0) a.dbg[4] = clock64();  // accumulators ready
+            float v[8], w[8];  // main accumulator; second accumulator (odd outputs of UP, the block's 1x1 residual conv)
+            tc_load_acc(taddr, p1, v);
+            if (MODE == TCM_UP || (MODE == TCM_CONV5 && a.res_w != nullptr)) tc_load_acc(taddr + 128, p1, w);
+            // the stage is in registers: hand it back to the issuers (the MMAs of the item after next may start)
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_local(acc_empty0 + 8 * stage);
+            if (dbg && tid == 64 && k == 0) a.dbg[5] = clock64();  // TMEM read
 
-        if (!full) {
-            float* dst = a.raw_out + (((size_t)tile * gridDim.y + ntile) * 128 + r) * 32 + cg * 8;
+            if (!full) {
+                float* dst = a.raw_out + (((size_t)tile * NC + ntile) * 128 + r) * 32 + cg * 8;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) dst[j] = v[j];
-        } else if (MODE == TCM_DOWN) {
-            // stride-2 conv: the MMA evaluated every input position; keep the even ones (out[m] = conv at l = 2m)
-            v[0] += pb0.x; v[1] += pb0.y; v[2] += pb0.z; v[3] += pb0.w;
-            v[4] += pb1.x; v[5] += pb1.y; v[6] += pb1.z; v[7] += pb1.w;
-            if (valid && (l & 1) == 0) tc_store_row(a, v, b, l >> 1, c8, a.L >> 1);
-        } else if (MODE == TCM_UP) {
-            // transposed conv: accumulator 0 = even outputs (2l), accumulator 1 = odd outputs (2l + 1)
-            float w[8];
-            tc_load_acc(taddr + 128, p1, w);
-            v[0] += pb0.x; v[1] += pb0.y; v[2] += pb0.z; v[3] += pb0.w;
-            v[4] += pb1.x; v[5] += pb1.y; v[6] += pb1.z; v[7] += pb1.w;
-            w[0] += pb0.x; w[1] += pb0.y; w[2] += pb0.z; w[3] += pb0.w;
-            w[4] += pb1.x; w[5] += pb1.y; w[6] += pb1.z; w[7] += pb1.w;
-            if (valid) {
-                tc_store_row(a, v, b, 2 * l, c8, 2 * a.L);
-                tc_store_row(a, w, b, 2 * l + 1, c8, 2 * a.L);
-            }
-        } else {
-            v[0] += pb0.x; v[1] += pb0.y; v[2] += pb0.z; v[3] += pb0.w;
-            v[4] += pb1.x; v[5] += pb1.y; v[6] += pb1.z; v[7] += pb1.w;
-            gn_mish8<GS, true>(v, valid, r, s, cg, tid, SPT, Lp, a.L, part, pg0, pg1, pe0, pe1, (dbg && tid == 64) ? a.dbg : nullptr);
-            if (dbg && tid == 64) a.dbg[6] = clock64();  // GroupNorm + Mish done
-            // time conditioning (zero when absent), then the residual: fused 1x1 conv accumulators or identity values
-            v[0] += pc0.x; v[1] += pc0.y; v[2] += pc0.z; v[3] += pc0.w;
-            v[4] += pc1.x; v[5] += pc1.y; v[6] += pc1.z; v[7] += pc1.w;
-            if (a.res_w != nullptr) {
-                float rv[8];
-                tc_load_acc(taddr + 128, p1, rv);
-                v[0] += rv[0] + pr0.x; v[1] += rv[1] + pr0.y; v[2] += rv[2] + pr0.z; v[3] += rv[3] + pr0.w;
-                v[4] += rv[4] + pr1.x; v[5] += rv[5] + pr1.y; v[6] += rv[6] + pr1.z; v[7] += rv[7] + pr1.w;
+                for (int j = 0; j < 8; ++j) dst[j] = v[j];
+            } else if (MODE == TCM_DOWN) {
+                // stride-2 conv: the MMA evaluated every input position; keep the even ones (out[m] = conv at l = 2m)
+                v[0] += pb0.x; v[1] += pb0.y; v[2] += pb0.z; v[3] += pb0.w;
+                v[4] += pb1.x; v[5] += pb1.y; v[6] += pb1.z; v[7] += pb1.w;
+                if (valid && (l & 1) == 0) tc_store_row(a, v, b, l >> 1, c8, a.L >> 1);
+            } else if (MODE == TCM_UP) {
+                // transposed conv: accumulator 0 = even outputs (2l), accumulator 1 = odd outputs (2l + 1)
+                v[0] += pb0.x; v[1] += pb0.y; v[2] += pb0.z; v[3] += pb0.w;
+                v[4] += pb1.x; v[5] += pb1.y; v[6] += pb1.z; v[7] += pb1.w;
+                w[0] += pb0.x; w[1] += pb0.y; w[2] += pb0.z; w[3] += pb0.w;
+                w[4] += pb1.x; w[5] += pb1.y; w[6] += pb1.z; w[7] += pb1.w;
+                if (valid) {
+                    tc_store_row(a, v, b, 2 * l, c8, 2 * a.L);
+                    tc_store_row(a, w, b, 2 * l + 1, c8, 2 * a.L);
+                }
             } else {
+                v[0] += pb0.x; v[1] += pb0.y; v[2] += pb0.z; v[3] += pb0.w;
+                v[4] += pb1.x; v[5] += pb1.y; v[6] += pb1.z; v[7] += pb1.w;
+                gn_mish8<GS, true>(v, valid, r, s, cg, tid, SPT, Lp, a.L, part, pg0, pg1, pe0, pe1, (dbg && tid == 64 && k == 0) ? a.dbg : nullptr);
+                if (dbg && tid == 64 && k == 0) a.dbg[6] = clock64();  // GroupNorm + Mish done
+                // time conditioning (zero when absent), then the residual: fused 1x1 conv accumulator or identity values
+                v[0] += pc0.x; v[1] += pc0.y; v[2] += pc0.z; v[3] += pc0.w;
+                v[4] += pc1.x; v[5] += pc1.y; v[6] += pc1.z; v[7] += pc1.w;
+                if (a.res_w != nullptr) {
+                    v[0] += w[0] + pr0.x; v[1] += w[1] + pr0.y; v[2] += w[2] + pr0.z; v[3] += w[3] + pr0.w;
+                    v[4] += w[4] + pr1.x; v[5] += w[5] + pr1.y; v[6] += w[6] + pr1.z; v[7] += w[7] + pr1.w;
+                } else {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] += rid[j];
+                    for (int j = 0; j < 8; ++j) v[j] += rid[j];
+                }
+                if (valid) tc_store_row(a, v, b, l, c8, a.L);
+                // gn_mish8's scratch is reused by the next item: everyone is past its last read (the statistics) before anyone
+                // writes the next item's partial sums
+                epi_sync();
             }
-            if (valid) tc_store_row(a, v, b, l, c8, a.L);
         }
         tc_fence_before();
     }
@@ -564,8 +600,15 @@ int launch_conv5_tc(const TcConvArgs& a, cudaStream_t stream) {
         MPDB_REQUIRE(!a.res_w && !a.res_cm && !a.cond && !a.raw_out, "tc down/up: no residual / conditioning");
     const int SPT = TC_RT / (a.L + 4);
     MPDB_REQUIRE(SPT <= 12, "tc conv: too many samples per tile");
-    const size_t smem = (size_t)TC_STAGES * TC_STAGE_BYTES + (2 * TC_STAGES + 1) * 8 + 16 + (2 * 128 * 8 + 12 * 8 * 2) * sizeof(float) + 2 * 12 * 8 * sizeof(double);
-    dim3 grid((a.B + SPT - 1) / SPT, a.CO / TC_NT);
+    const size_t smem = (size_t)TC_STAGES * TC_STAGE_BYTES + (2 * TC_STAGES + 4) * 8 + 16 + (2 * 128 * 8 + 12 * 8 * 2) * sizeof(float) + 2 * 12 * 8 * sizeof(double);
+    // persistent: one CTA per SM (TMEM holds two accumulator stages) walking the (row tile, channel chunk) items
+    static int sm_count[64] = {0};
+    int dev = 0;
+    MPDB_CHECK_CUDA(cudaGetDevice(&dev));
+    if (dev >= 0 && dev < 64 && sm_count[dev] == 0) MPDB_CHECK_CUDA(cudaDeviceGetAttribute(&sm_count[dev], cudaDevAttrMultiProcessorCount, dev));
+    const int sms = (dev >= 0 && dev < 64 && sm_count[dev] > 0) ? sm_count[dev] : 148;
+    const long long n_items = (long long)((a.B + SPT - 1) / SPT) * (a.CO / TC_NT);
+    dim3 grid((unsigned)(n_items < sms ? n_items : sms));
 #define MPDB_TC_LAUNCH(M, G)                                                                                       \
     {                                                                                                              \
         static unsigned long long configured = 0ull;                                                                            \
