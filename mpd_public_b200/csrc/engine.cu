@@ -88,11 +88,12 @@ struct mpdb_engine {
     std::vector<std::pair<std::string, long long>> cond_jobs;  // cond_mlp prefix -> table offset
     float* work = nullptr;    // activations (fp32, channel-major with halo)
     unsigned short* packed_tc = nullptr;  // fp16-split weights in tensor-core layout
+    unsigned short* packed_tc_hi = nullptr;  // their hi halves alone (half the bytes): streamed by precision-1 steps
     long long packed_tc_elems = 0;
     unsigned short* work_tc = nullptr;    // activations in tensor-core layout (fp16 hi / scaled-lo planes)
     std::vector<long long> tc_off, tc_plane;  // per buffer: offset of the hi plane, elements per plane
     std::vector<long long> cm_off;            // per buffer: float offset of its (possibly shared) physical slot
-    int fuse_rtb = 1;          // cluster-fused residual blocks on the tensor-core path (see can_fuse_rtb)
+    int fuse_rtb = []() { const char* v = getenv("MPDB_FUSE_RTB"); return v ? atoi(v) : 1; }();  // cluster-fused residual blocks on the tensor-core path (see can_fuse_rtb)
     int sm_count = 148;
     int fuse_max_co = []() { const char* v = getenv("MPDB_FUSE_MAX_CO"); return v ? atoi(v) : 128; }();  // widest fused block (measured: 0 -> 11.85, 32 -> 11.67, 64 -> 11.55, 128 -> 11.47 ms per loop)
     // whole-forward persistent cluster kernel (unet_mega.cu)
@@ -481,6 +482,7 @@ static void fill_tc_args(mpdb_engine* e, const ConvOp& op, const long long* t_de
     a.in0_hi = hi(op.tc_in0); a.in0_lo = lo(op.tc_in0); a.c0 = e->bufs[op.tc_in0].C;
     if (op.in1 >= 0) { a.in1_hi = hi(op.in1); a.in1_lo = lo(op.in1); a.c1 = e->bufs[op.in1].C; }
     a.w = e->packed_tc + op.w_tc;
+    a.w_hi = e->packed_tc_hi + op.w_tc / 2;
     a.bias = e->packed + op.bias;
     if (op.gn) { a.gamma = e->packed + op.gamma; a.beta = e->packed + op.beta; }
     if (op.cond >= 0) { a.cond = e->packed + op.cond; a.t_dev = t_dev; a.t_uniform = t_uniform; }
@@ -488,6 +490,7 @@ static void fill_tc_args(mpdb_engine* e, const ConvOp& op, const long long* t_de
         a.r0_hi = hi(op.tc_res0); a.r0_lo = lo(op.tc_res0); a.rc0 = e->bufs[op.tc_res0].C;
         if (op.res1 >= 0) { a.r1_hi = hi(op.res1); a.r1_lo = lo(op.res1); a.rc1 = e->bufs[op.res1].C; }
         a.res_w = e->packed_tc + op.res_w_tc;
+        a.res_w_hi = e->packed_tc_hi + op.res_w_tc / 2;
         a.res_bias = e->packed + op.res_bias;
     } else if (op.res0 >= 0) {
         a.res_cm = buf_ptr(e, op.res0, e->work_batch);
@@ -565,6 +568,7 @@ static bool try_build_mega(mpdb_engine* e, int B, int G, std::string& why) {
                 Ld.skip_hi = e->mega_skip + sk.off; Ld.skip_lo = e->mega_skip + sk.off + plane;
             }
             Ld.w = e->packed_tc + op.w_tc;
+            Ld.w_hi = e->packed_tc_hi + op.w_tc / 2;
             Ld.bias = e->packed + op.bias;
             if (op.gn) { Ld.gamma = e->packed + op.gamma; Ld.beta = e->packed + op.beta; }
             if (op.cond >= 0) Ld.cond = e->packed + op.cond;
@@ -573,7 +577,7 @@ static bool try_build_mega(mpdb_engine* e, int B, int G, std::string& why) {
                 if (i + 1 >= e->ops.size()) { why = "dangling block"; return false; }
                 const ConvOp& b = e->ops[i + 1];
                 if (b.mode != MODE_CONV5 || b.in0 != op.out || b.in1 >= 0 || b.res0 != op.in0 || b.res1 != op.in1) { why = "unexpected block structure"; return false; }
-                if (b.res_w >= 0) { Ld.n_res_a = Ld.n_a; Ld.n_res_skip = Ld.n_skip; Ld.res_w = e->packed_tc + b.res_w_tc; }
+                if (b.res_w >= 0) { Ld.n_res_a = Ld.n_a; Ld.n_res_skip = Ld.n_skip; Ld.res_w = e->packed_tc + b.res_w_tc; Ld.res_w_hi = e->packed_tc_hi + b.res_w_tc / 2; }
             }
             if (op.mode == MODE_CONV5 && op.res0 != -2) {
                 if (n < 1 || P.layers[n - 1].type != MG_CONV5 || P.layers[n - 1].cond == nullptr) { why = "conv1 without conv0"; return false; }
@@ -837,6 +841,7 @@ extern "C" int mpdb_engine_create(const mpdb_engine_config* cfg, int device, mpd
     MPDB_CHECK_CUDA(cudaMemset(e->packed, 0, sizeof(float) * (size_t)(e->packed_floats + 32 * cfg->n_diffusion_steps)));
     MPDB_CHECK_CUDA(cudaMalloc(&e->sched, sizeof(float) * 7 * (size_t)cfg->n_diffusion_steps));
     MPDB_CHECK_CUDA(cudaMalloc(&e->packed_tc, sizeof(unsigned short) * (size_t)(e->packed_tc_elems > 0 ? e->packed_tc_elems : 8)));
+    MPDB_CHECK_CUDA(cudaMalloc(&e->packed_tc_hi, sizeof(unsigned short) * (size_t)(e->packed_tc_elems > 0 ? e->packed_tc_elems / 2 : 8)));
     e->packs = pb.packs;
     e->cond_jobs = pb.cond_jobs;
     if (ensure_workspace(e.get(), cfg->max_batch > 0 ? cfg->max_batch : 1)) return 1;
@@ -850,7 +855,7 @@ extern "C" void mpdb_engine_destroy(mpdb_engine* e) {
     cudaDeviceSynchronize();
     mpdb::drop_graphs(e);
     cudaFree(e->raw); cudaFree(e->packed); cudaFree(e->work); cudaFree(e->sched);
-    cudaFree(e->packed_tc); cudaFree(e->work_tc); cudaFree(e->dbg_buf); cudaFree(e->mega_skip); cudaFree(e->mega_dbg);
+    cudaFree(e->packed_tc); cudaFree(e->packed_tc_hi); cudaFree(e->work_tc); cudaFree(e->dbg_buf); cudaFree(e->mega_skip); cudaFree(e->mega_dbg);
     cudaFree(e->xbuf[0]); cudaFree(e->xbuf[1]); cudaFree(e->flags);
     cudaFree(e->g_noise); cudaFree(e->g_hc); cudaFree(e->g_chain);
     delete e;
@@ -969,9 +974,9 @@ extern "C" int mpdb_engine_finalize(mpdb_engine* e, void* stream) {
         // destination tap -> source tap: identity for Conv1d; ConvTranspose1d packs [W1, W3 | W0, W2] (even | odd outputs)
         const int ntaps = op.mode == MODE_DOWN ? 3 : op.mode == MODE_UP ? 4 : 5;
         const unsigned perm = op.mode == MODE_UP ? 0x2031u : 0x43210u;
-        if (launch_pack_tc_weights(e->packed + op.w, e->packed_tc + op.w_tc, op.cin_tc, op.cin, op.CO, ntaps, perm, st)) return 1;
-        if (op.res_w >= 0 && launch_pack_tc_weights(e->packed + op.res_w, e->packed_tc + op.res_w_tc, op.res_cin_tc, op.res_cin,
-                                                    op.CO, 1, 0u, st))
+        if (launch_pack_tc_weights(e->packed + op.w, e->packed_tc + op.w_tc, e->packed_tc_hi + op.w_tc / 2, op.cin_tc, op.cin, op.CO, ntaps, perm, st)) return 1;
+        if (op.res_w >= 0 && launch_pack_tc_weights(e->packed + op.res_w, e->packed_tc + op.res_w_tc, e->packed_tc_hi + op.res_w_tc / 2,
+                                                    op.res_cin_tc, op.res_cin, op.CO, 1, 0u, st))
             return 1;
     }
     const int T = e->cfg.n_diffusion_steps;
@@ -1551,7 +1556,7 @@ extern "C" int mpdb_debug_tc_conv5(const float* x_cm, const float* w, float* raw
     MPDB_CHECK_CUDA(cudaMemsetAsync(xh, 0, 2 * plane, st));
     MPDB_CHECK_CUDA(cudaMemsetAsync(xl, 0, 2 * plane, st));
     int rc = launch_repack_conv(w, wp, CO, CI, 5, 0, st);
-    if (!rc) rc = launch_pack_tc_weights(wp, wt, CI, CI, CO, 5, 0x43210u, st);
+    if (!rc) rc = launch_pack_tc_weights(wp, wt, nullptr, CI, CI, CO, 5, 0x43210u, st);
     if (!rc) rc = launch_cm_to_tc(x_cm, xh, xl, B, CI, L, st);
     if (!rc) {
         TcConvArgs a;

@@ -72,6 +72,7 @@ struct GuideDev {
     int use_gp, clip;
     float max_norm;
     int n_interp, vel_fd;
+    int simple_spheres;  // sphere i rides on frame i + 1 with zero offset (the default Panda model): centres = frame origins
     float gp_a, gp_b, gp_c;
     float joint_xyz[7][3];
     float joint_cr[7], joint_sr[7];
@@ -107,6 +108,10 @@ static GuideDev make_dev(const mpdb_guide_config& c) {
         }
         d.frame_begin[8] = d.frame_begin[9] = n;
     }
+    d.simple_spheres = c.robot_kind == 1 && c.n_spheres <= 8;
+    for (int i = 0; i < c.n_spheres; ++i)
+        if (c.sphere_frame[i] != i + 1 || c.sphere_offset[i][0] != 0.f || c.sphere_offset[i][1] != 0.f || c.sphere_offset[i][2] != 0.f)
+            d.simple_spheres = 0;
     for (int i = 0; i < d.D; ++i) {
         d.mins[i] = c.mins[i];
         d.range[i] = c.maxs[i] - c.mins[i];  // fp32 subtraction, as `self.maxs - self.mins`
@@ -167,13 +172,21 @@ __device__ __forceinline__ void fk_chain_row(const GuideDev& g, int r3, const fl
         c0 = n0; c1 = n1; c2 = a2;
         sc[(j * 3 + r3) * FK_ROWS] = o;
         sc[(21 + j * 3 + r3) * FK_ROWS] = c2;  // joint axis = third column
-        // the spheres attached to this frame (host-sorted list: no scan over all spheres per joint)
-        for (int t = g.frame_begin[j]; t < g.frame_begin[j + 1]; ++t) {
-            const int s = g.frame_sphere[t];
-            cen[(s * 3 + r3) * FK_ROWS] = o + c0 * g.sphere_off[s][0] + c1 * g.sphere_off[s][1] + c2 * g.sphere_off[s][2];
+        if (g.simple_spheres) {
+            if (j < g.n_spheres) cen[(j * 3 + r3) * FK_ROWS] = o;  // sphere j sits on this frame's origin
+        } else {
+            // the spheres attached to this frame (host-sorted list: no scan over all spheres per joint)
+            for (int t = g.frame_begin[j]; t < g.frame_begin[j + 1]; ++t) {
+                const int s = g.frame_sphere[t];
+                cen[(s * 3 + r3) * FK_ROWS] = o + c0 * g.sphere_off[s][0] + c1 * g.sphere_off[s][1] + c2 * g.sphere_off[s][2];
+            }
         }
     }
     o += c0 * g.flange[0] + c1 * g.flange[1] + c2 * g.flange[2];
+    if (g.simple_spheres) {
+        if (g.n_spheres > 7) cen[(7 * 3 + r3) * FK_ROWS] = o;
+        return;
+    }
     for (int t = g.frame_begin[7]; t < g.frame_begin[8]; ++t) {
         const int s = g.frame_sphere[t];
         cen[(s * 3 + r3) * FK_ROWS] = o + c0 * g.sphere_off[s][0] + c1 * g.sphere_off[s][1] + c2 * g.sphere_off[s][2];
@@ -452,7 +465,10 @@ __global__ void __launch_bounds__(GUIDE_THREADS, OCC) guide_step_kernel(const __
         for (int item0 = 0; item0 < H * n_coll; item0 += NTH / 8) {
             const int item = item0 + (tid >> 3), k = tid & 7;
             const bool on = item < H * n_coll;
-            const int h = on ? item % H : 0, f = on ? item / H : 0;
+            // H is a multiple of 64 for every horizon the UNet accepts with 4 levels: a round of 64 items stays inside one cost
+            const int f0 = item0 / H;
+            const int f = !on ? 0 : (H & 63) == 0 ? f0 : item / H;
+            const int h = on ? item - f * H : 0;
             float gsk = 0.f;
             if (on && k < q) {
                 // rows i with ratio * i in (h - 1, h + 1) touch h; floor / ceil leave one row of slack on each side for the

@@ -61,7 +61,8 @@ struct TcConvArgs {
     // main conv input: up to two concatenated sources in TC layout (fp16 hi / scaled-lo planes)
     const unsigned short *in0_hi, *in0_lo, *in1_hi, *in1_lo;
     int c0, c1;
-    const unsigned short* w;      // packed [CO/32][CI/32][hi|lo][5][4][32][8]
+    const unsigned short* w;      // packed [CO/32][CI/32][taps][4][hi 32 | lo 32][8]
+    const unsigned short *w_hi, *res_w_hi;  // the hi halves alone ([..][4][32][8]): what precision-1 steps stream
     const float* bias;
     const float* gamma;
     const float* beta;
@@ -91,8 +92,8 @@ struct TcRtbArgs {
     TcConvArgs c1;  // second conv: w, bias, gamma, beta, residual (res_cm | r0/r1 + res_w + res_bias), outputs
 };
 int launch_rtb_tc(const TcRtbArgs& a, cudaStream_t stream);
-int launch_pack_tc_weights(const float* src, unsigned short* dst, int CI, int CI_src, int CO, int ntaps, unsigned perm,
-                           cudaStream_t stream);
+int launch_pack_tc_weights(const float* src, unsigned short* dst, unsigned short* dst_hi, int CI, int CI_src, int CO, int ntaps,
+                           unsigned perm, cudaStream_t stream);
 int launch_blc_to_tc(const float* x, unsigned short* hi, unsigned short* lo, int B, int L, int D, int C, cudaStream_t stream);
 int launch_cm_to_tc(const float* cm, unsigned short* hi, unsigned short* lo, int B, int C, int L, cudaStream_t stream);
 
@@ -121,6 +122,7 @@ struct MegaLayer {
                               // complete_tx count the CTA's a_full barrier expects for the layer)
     const unsigned short* w;      // packed [NC][n_a + n_skip][taps][4][hi 32 | lo 32][8]
     const unsigned short* res_w;  // packed [NC][n_res_a + n_res_skip][1][4][hi 32 | lo 32][8]
+    const unsigned short *w_hi, *res_w_hi;            // hi halves alone (precision-1 steps)
     const unsigned short *skip_hi, *skip_lo;          // [cluster][MT][skip_C/8][RT][8]
     unsigned short *skip_out_hi, *skip_out_lo;        // same layout, CO channels (output also kept as a skip connection)
     const float *bias, *gamma, *beta, *cond, *res_bias;

@@ -128,9 +128,11 @@ __global__ void __launch_bounds__(MG_THREADS, 1) unet_mega_kernel(const __grid_c
                     const int cc = c;
                     const int na = Ld.n_a;
                     const bool from_skip = cc >= na;
-                    const uint32_t wbytes = (uint32_t)ntaps * 2u * TC_B_TAP_BYTES;
-                    const uint32_t rbytes = has_res ? 2u * TC_B_TAP_BYTES : 0u;
-                    const unsigned short* wsrc = Ld.w + ((size_t)nc * n_main + cc) * ((size_t)ntaps * 2 * TC_B_TAP_BYTES / 2);
+                    const uint32_t wmul = P.prec == 1 ? 1u : 2u;  // precision 1 streams the hi halves of the weights only
+                    const uint32_t wbytes = (uint32_t)ntaps * wmul * TC_B_TAP_BYTES;
+                    const uint32_t rbytes = has_res ? wmul * TC_B_TAP_BYTES : 0u;
+                    const size_t welems = ((size_t)nc * n_main + cc) * ((size_t)ntaps * 2 * TC_B_TAP_BYTES / 2);
+                    const unsigned short* wsrc = P.prec == 1 ? Ld.w_hi + welems / 2 : Ld.w + welems;
                     const uint32_t st = stages_u32 + (uint32_t)s * MG_STAGE_BYTES;
                     if (from_skip && !skip_checked) {
                         // the skip tensor was written (by CTAs of this cluster) many layers ago; make the dependency explicit
@@ -143,7 +145,9 @@ __global__ void __launch_bounds__(MG_THREADS, 1) unet_mega_kernel(const __grid_c
                     mbar_expect_tx_elect(full0 + 8 * s, wbytes + rbytes + (from_skip ? (P.prec == 1 ? act_bytes : 2u * act_bytes) : 0u));
                     bulk_g2s_elect(st + 2 * TC_A_PLANE_BYTES, wsrc, wbytes, full0 + 8 * s);
                     if (has_res)  // the residual conv's weights of this chunk, behind the (at most 5) taps
-                        bulk_g2s_elect(st + 2 * TC_A_PLANE_BYTES + 5 * 2 * TC_B_TAP_BYTES, Ld.res_w + ((size_t)nc * n_main + cc) * (2 * TC_B_TAP_BYTES / 2),
+                        bulk_g2s_elect(st + 2 * TC_A_PLANE_BYTES + 5 * wmul * TC_B_TAP_BYTES,
+                                       P.prec == 1 ? Ld.res_w_hi + ((size_t)nc * n_main + cc) * (TC_B_TAP_BYTES / 2)
+                                                   : Ld.res_w + ((size_t)nc * n_main + cc) * (2 * TC_B_TAP_BYTES / 2),
                                        rbytes, full0 + 8 * s);
                     if (from_skip) {
                         const size_t aoff = (((size_t)cluster * Ld.MT + mt) * (Ld.skip_C / 8) + (size_t)(cc - na) * (TC_KCH / 8)) * Ld.RT * 8;
@@ -173,7 +177,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) unet_mega_kernel(const __grid_c
             const uint32_t col0 = __shfl_sync(0xffffffffu, tmem_base, 0) + (which == 0 ? 0u : 2u * TC_NT);  // this issuer's main accumulator
             // descriptor words: low = start address >> 4 | LBO >> 4 << 16 ; high = SBO >> 4 | version 1 << 14
             constexpr uint32_t desc_hi = (128u >> 4) | (1u << 14);
-            constexpr uint32_t b_lo_fixed = ((2u * TC_NT * 16u) >> 4) << 16;  // weight tile: LBO = 64 rows x 16 B
+            const uint32_t b_lo_fixed = (((p1 ? 1u : 2u) * TC_NT * 16u) >> 4) << 16;  // weight tile: LBO = 64 rows x 16 B (W_hi | W_lo), 32 rows when only W_hi is streamed
             int ring_i = 0;
             uint32_t my_acc_ph = 0;
             // a_full phase l = "the outputs of layer l have landed in this CTA's A buffer": the peers' bytes are counted by
@@ -213,7 +217,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) unet_mega_kernel(const __grid_c
                                                       : st + ((which == 1 && !p1) ? (uint32_t)TC_A_PLANE_BYTES : 0u);
                         const uint32_t a_lo = ((aaddr >> 4) & 0x3FFFu) | ((lbo >> 4) << 16);
                         const uint32_t b_lo = (((st + 2 * TC_A_PLANE_BYTES) >> 4) & 0x3FFFu) | b_lo_fixed;  // rows [0,32) = W_hi, [32,64) = W_lo
-                        const uint32_t kstep_a = (2 * lbo) >> 4, kstep_b = (2 * (2 * TC_NT * 16)) >> 4, tap_b = (2 * TC_B_TAP_BYTES) >> 4;
+                        const uint32_t kstep_a = (2 * lbo) >> 4, kstep_b = ((p1 ? 1u : 2u) * (2 * TC_NT * 16)) >> 4, tap_b = ((p1 ? 1u : 2u) * TC_B_TAP_BYTES) >> 4;
                         if (c > 0) {
                             mbar_wait(full0 + 8 * sidx, (uint32_t)(ring_i / MG_STAGES) & 1u);
                             tc_fence_after();

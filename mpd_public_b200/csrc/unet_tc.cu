@@ -110,11 +110,12 @@ __global__ void __launch_bounds__(TCL_THREADS, 1) conv5_tc_kernel(const __grid_c
             const bool is_res = c_step >= n_main;
             const int c = is_res ? c_step - n_main : c_step;
             const int ntaps = is_res ? 1 : NTAPS;
-            const uint32_t bbytes = 2u * ntaps * TC_B_TAP_BYTES;
+            const uint32_t bbytes = (p1 ? 1u : 2u) * ntaps * TC_B_TAP_BYTES;  // precision 1 streams the hi halves only
             const uint32_t st = stages_u32 + (uint32_t)s * TC_STAGE_BYTES;
             if (weights) {
-                const unsigned short* wsrc = is_res ? a.res_w + ((size_t)ntile * n_res + c) * (2 * 1 * TC_B_TAP_BYTES / 2)
-                                                    : a.w + ((size_t)ntile * n_main + c) * (2 * NTAPS * TC_B_TAP_BYTES / 2);
+                const size_t welems = is_res ? ((size_t)ntile * n_res + c) * (2 * 1 * TC_B_TAP_BYTES / 2)
+                                             : ((size_t)ntile * n_main + c) * (2 * NTAPS * TC_B_TAP_BYTES / 2);
+                const unsigned short* wsrc = p1 ? (is_res ? a.res_w_hi : a.w_hi) + welems / 2 : (is_res ? a.res_w : a.w) + welems;
                 mbar_expect_tx_elect(full0 + 8 * s, (p1 ? 1u : 2u) * TC_A_PLANE_BYTES + bbytes);  // covers the activation copies too
                 bulk_g2s_elect(st + 2 * TC_A_PLANE_BYTES, wsrc, bbytes, full0 + 8 * s);
             }
@@ -152,8 +153,10 @@ __global__ void __launch_bounds__(TCL_THREADS, 1) conv5_tc_kernel(const __grid_c
         const uint32_t colw = __shfl_sync(0xffffffffu, tmem_base, 0) + (which == 0 ? 0u : 2u * TC_NT);
         constexpr uint32_t desc_hi = (128u >> 4) | (1u << 14);                      // SBO = 128 B, descriptor version 1
         constexpr uint32_t a_lo_fixed = ((uint32_t)(TC_RT * 16) >> 4) << 16;        // activation tile: LBO = 132 rows x 16 B
-        constexpr uint32_t b_lo_fixed = ((2u * TC_NT * 16u) >> 4) << 16;            // weight tile: LBO = 64 rows x 16 B
-        constexpr uint32_t kstep_a = (2 * TC_RT * 16) >> 4, kstep_b = (2 * (2 * TC_NT * 16)) >> 4, tap_b = (2 * TC_B_TAP_BYTES) >> 4;
+        // weight tile: rows [0,32) = W_hi, [32,64) = W_lo per k-group (LBO = 64 rows x 16 B); precision 1: W_hi only (LBO = 32 rows)
+        const uint32_t b_lo_fixed = (((p1 ? 1u : 2u) * TC_NT * 16u) >> 4) << 16;
+        constexpr uint32_t kstep_a = (2 * TC_RT * 16) >> 4;
+        const uint32_t kstep_b = ((p1 ? 1u : 2u) * (2 * TC_NT * 16)) >> 4, tap_b = ((p1 ? 1u : 2u) * TC_B_TAP_BYTES) >> 4;
         int i = 0, k = 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++k) {
             const int stage = k & 1;
@@ -166,7 +169,7 @@ __global__ void __launch_bounds__(TCL_THREADS, 1) conv5_tc_kernel(const __grid_c
                 const int s = i % TC_STAGES;
                 const uint32_t st = stages_u32 + (uint32_t)s * TC_STAGE_BYTES;
                 const uint32_t a_lo = (((st + ((which == 1 && !p1) ? (uint32_t)TC_A_PLANE_BYTES : 0u)) >> 4) & 0x3FFFu) | a_lo_fixed;
-                const uint32_t b_lo = (((st + 2 * TC_A_PLANE_BYTES) >> 4) & 0x3FFFu) | b_lo_fixed;  // rows [0,32) = W_hi, [32,64) = W_lo
+                const uint32_t b_lo = (((st + 2 * TC_A_PLANE_BYTES) >> 4) & 0x3FFFu) | b_lo_fixed;
                 mbar_wait(full0 + 8 * s, (uint32_t)(i / TC_STAGES) & 1u);
                 tc_fence_after();
                 if (c >= n_main) {  // fused 1x1 residual conv: centre row (+2), second accumulator
@@ -636,8 +639,9 @@ int launch_conv5_tc(const TcConvArgs& a, cudaStream_t stream) {
 //   dst fp16 [CO/32][CI/32][ntaps][kg 4][64 rows: 32 hi | 32 lo][8]
 //   CI is the padded input width (multiple of 32); channels >= CI_src are zero. `perm` maps destination tap -> source tap
 //   (ConvTranspose: [1, 3, 0, 2], see the kernel), packed 4 bits per tap.
-__global__ void pack_tc_weights_kernel(const float* __restrict__ src, unsigned short* __restrict__ dst, int CI, int CI_src,
-                                       int CO, int ntaps, unsigned perm) {
+// dst_hi (optional): the hi halves alone, [CO/32][CI/32][ntaps][kg 4][32 rows][8] — what a precision-1 step streams
+__global__ void pack_tc_weights_kernel(const float* __restrict__ src, unsigned short* __restrict__ dst, unsigned short* __restrict__ dst_hi,
+                                       int CI, int CI_src, int CO, int ntaps, unsigned perm) {
     const long long n = (long long)CI * CO * ntaps;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         const int e = (int)(i % 8);
@@ -656,15 +660,16 @@ __global__ void pack_tc_weights_kernel(const float* __restrict__ src, unsigned s
         const long long row0 = (((long long)tap * (TC_KCH / 8) + kg) * (2 * TC_NT)) * 8;
         dst[blk + row0 + (long long)nn * 8 + e] = hi;
         dst[blk + row0 + (long long)(TC_NT + nn) * 8 + e] = lo;
+        if (dst_hi != nullptr) dst_hi[blk / 2 + row0 / 2 + (long long)nn * 8 + e] = hi;
     }
 }
 
-int launch_pack_tc_weights(const float* src, unsigned short* dst, int CI, int CI_src, int CO, int ntaps, unsigned perm,
-                           cudaStream_t stream) {
+int launch_pack_tc_weights(const float* src, unsigned short* dst, unsigned short* dst_hi, int CI, int CI_src, int CO, int ntaps,
+                           unsigned perm, cudaStream_t stream) {
     long long n = (long long)CI * CO * ntaps;
     int blocks = (int)((n + 255) / 256);
     if (blocks > 2048) blocks = 2048;
-    pack_tc_weights_kernel<<<blocks, 256, 0, stream>>>(src, dst, CI, CI_src, CO, ntaps, perm);
+    pack_tc_weights_kernel<<<blocks, 256, 0, stream>>>(src, dst, dst_hi, CI, CI_src, CO, ntaps, perm);
     MPDB_LAUNCH_CHECK();
     return 0;
 }
