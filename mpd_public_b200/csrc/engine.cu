@@ -93,6 +93,8 @@ struct mpdb_engine {
     unsigned short* work_tc = nullptr;    // activations in tensor-core layout (fp16 hi / scaled-lo planes)
     std::vector<long long> tc_off, tc_plane;  // per buffer: offset of the hi plane, elements per plane
     std::vector<long long> cm_off;            // per buffer: float offset of its (possibly shared) physical slot
+    std::vector<char> need_cm;                // per buffer: some consumer reads the fp32 channel-major copy (identity residual, final
+                                              // projection, a layer without a tensor-core path); otherwise the tensor-core kernels skip writing it
     int fuse_rtb = []() { const char* v = getenv("MPDB_FUSE_RTB"); return v ? atoi(v) : 1; }();  // cluster-fused residual blocks on the tensor-core path (see can_fuse_rtb)
     int sm_count = 148;
     int fuse_max_co = []() { const char* v = getenv("MPDB_FUSE_MAX_CO"); return v ? atoi(v) : 128; }();  // widest fused block (measured: 0 -> 11.85, 32 -> 11.67, 64 -> 11.55, 128 -> 11.47 ms per loop)
@@ -335,6 +337,7 @@ static int build_plan(mpdb_engine* e, PlanBuilder& pb) {
         pb.packs.push_back({"final_conv.1.bias", e->final_b, c.state_dim, 1, 0, 0});
     }
     MPDB_REQUIRE(L == c.horizon, "internal: plan length mismatch");
+    e->need_cm.assign(e->bufs.size(), 0);
     // which k=5 layers can run on the tensor cores
     auto chans = [&](int id0, int id1) {
         int cc = 0;
@@ -374,6 +377,14 @@ static int build_plan(mpdb_engine* e, PlanBuilder& pb) {
             }
         }
     }
+    for (const ConvOp& op : e->ops) {
+        if (op.mode == MODE_INPUT) continue;
+        if (op.res_w < 0 && op.res0 >= 0) e->need_cm[op.res0] = 1;  // identity residual: fp32 values
+        if (!op.tc_ok)
+            for (int id : {op.in0, op.in1, op.res0, op.res1})
+                if (id >= 0) e->need_cm[id] = 1;
+    }
+    e->need_cm[e->final_in] = 1;
     return 0;
 }
 
@@ -495,7 +506,7 @@ static void fill_tc_args(mpdb_engine* e, const ConvOp& op, const long long* t_de
     } else if (op.res0 >= 0) {
         a.res_cm = buf_ptr(e, op.res0, e->work_batch);
     }
-    a.out_cm = const_cast<float*>(buf_ptr(e, op.out, e->work_batch));
+    a.out_cm = (!e->alias_buffers || e->need_cm.empty() || e->need_cm[op.out]) ? const_cast<float*>(buf_ptr(e, op.out, e->work_batch)) : nullptr;
     a.out_hi = hi(op.out); a.out_lo = lo(op.out);
     a.CO = op.CO; a.L = op.L_in; a.B = B; a.gs = op.gs;
     a.prec = t_dev == nullptr ? step_prec(e, t_uniform) : 3;  // per-sample t (per-call entry points): always the full split

@@ -58,6 +58,10 @@ __global__ void __launch_bounds__(TCL_THREADS, 1) conv5_tc_kernel(const __grid_c
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + TC_STAGES * TC_STAGE_BYTES);  // full[S], empty[S], acc_full[2], acc_empty[2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_STAGES + 4);
     float* part = reinterpret_cast<float*>(tmem_slot + 4);  // GroupNorm scratch: [2][128][8] floats + [2][12][8] doubles
+    // per-item epilogue parameters of the item's 32 output channels {bias, gamma, beta, residual bias, time-conditioning row at
+    // uniform t}, double-buffered like the accumulators and filled by the producer warp one item ahead: in the item loop the
+    // epilogue warps would otherwise pay a global-memory round trip per item with nothing to hide it behind
+    float* ptab = part + (TC_GN_SCRATCH_BYTES / (int)sizeof(float));  // [2][5][32]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const bool dbg = a.dbg != nullptr && blockIdx.x == 0;
@@ -83,7 +87,7 @@ __global__ void __launch_bounds__(TCL_THREADS, 1) conv5_tc_kernel(const __grid_c
             mbar_init(empty0 + 8 * s, 2);  // both issuers release a stage
         }
         for (int s = 0; s < 2; ++s) {
-            mbar_init(acc_full0 + 8 * s, 2);                  // both issuers' MMAs of the item have retired
+            mbar_init(acc_full0 + 8 * s, 3);                  // both issuers' MMAs of the item have retired + the producer's parameter rows are in place
             mbar_init(acc_empty0 + 8 * s, TC_THREADS / 32);   // every epilogue warp has read its part of the stage
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -139,13 +143,28 @@ __global__ void __launch_bounds__(TCL_THREADS, 1) conv5_tc_kernel(const __grid_c
         pre = 0;
         for (int item = blockIdx.x; item < n_items && pre < TC_STAGES; item += gridDim.x)
             for (int c = 0; c < n_steps && pre < TC_STAGES; ++c, ++pre) produce(pre, item, c, false, true);
-        for (int item = blockIdx.x; item < n_items; item += gridDim.x)
+        int kk = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++kk) {
+            {   // parameter rows of this item -> ptab[stage]; the stage's previous user has read its rows before it released the accumulators
+                const int stage = kk & 1, ntile = item % NC;
+                mbar_wait(acc_empty0 + 8 * stage, (((uint32_t)kk >> 1) & 1u) ^ 1u);
+                float* pt = ptab + stage * 160;
+                const int c = ntile * TC_NT + lane;
+                pt[lane] = a.bias ? a.bias[c] : 0.f;
+                pt[32 + lane] = (MODE == TCM_CONV5 && a.gamma) ? a.gamma[c] : 0.f;
+                pt[64 + lane] = (MODE == TCM_CONV5 && a.beta) ? a.beta[c] : 0.f;
+                pt[96 + lane] = a.res_w ? a.res_bias[c] : 0.f;
+                pt[128 + lane] = (a.cond && !a.t_dev) ? a.cond[(size_t)a.t_uniform * a.CO + c] : 0.f;
+                __syncwarp();
+                if (lane == 0) mbar_arrive_local(acc_full0 + 8 * stage);  // release: the rows are visible to whoever sees the phase complete
+            }
             for (int c = 0; c < n_steps; ++c, ++i) {
                 if (i < TC_STAGES) continue;  // issued above
                 mbar_wait(empty0 + 8 * (i % TC_STAGES), ((uint32_t)(i / TC_STAGES) & 1u) ^ 1u);
                 __syncwarp();
                 produce(i, item, c, true, true);
             }
+        }
     } else if (warp > TC_THREADS / 32) {
         // ===== two MMA-issue warps =====
         const int which = __shfl_sync(0xffffffffu, warp, 0) - (TC_THREADS / 32 + 1);
@@ -213,6 +232,15 @@ __global__ void __launch_bounds__(TCL_THREADS, 1) conv5_tc_kernel(const __grid_c
         const int s = r / Lp, l = r - s * Lp;
         const bool full = a.raw_out == nullptr;
         const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        float rid_next[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (full && MODE == TCM_CONV5 && a.res_w == nullptr && a.res_cm != nullptr && (int)blockIdx.x < n_items) {
+            const int tile0 = blockIdx.x / NC, ntile0 = blockIdx.x - tile0 * NC, b0 = tile0 * SPT + s;
+            if ((s < SPT) && (l < a.L) && (b0 < a.B)) {
+                const float* rp = a.res_cm + ((size_t)b0 * a.CO + ntile0 * TC_NT + cg * 8) * Lp + 2 + l;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) rid_next[j] = rp[(size_t)j * Lp];
+            }
+        }
         int k = 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++k) {
             const int tile = item / NC, ntile = item - tile * NC;
@@ -220,27 +248,15 @@ __global__ void __launch_bounds__(TCL_THREADS, 1) conv5_tc_kernel(const __grid_c
             const int b = tile * SPT + s;
             const bool valid = (s < SPT) && (l < a.L) && (b < a.B);
             const int c8 = ntile * TC_NT + cg * 8;  // first of this thread's 8 output channels
-            float4 pb0 = z4, pb1 = z4, pg0 = z4, pg1 = z4, pe0 = z4, pe1 = z4, pc0 = z4, pc1 = z4, pr0 = z4, pr1 = z4;
-            float rid[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-            if (full) {
-                pb0 = *reinterpret_cast<const float4*>(a.bias + c8); pb1 = *reinterpret_cast<const float4*>(a.bias + c8 + 4);
-                if (MODE == TCM_CONV5) {
-                    pg0 = *reinterpret_cast<const float4*>(a.gamma + c8); pg1 = *reinterpret_cast<const float4*>(a.gamma + c8 + 4);
-                    pe0 = *reinterpret_cast<const float4*>(a.beta + c8); pe1 = *reinterpret_cast<const float4*>(a.beta + c8 + 4);
-                }
-                if (a.cond != nullptr && valid) {
-                    const int tt = a.t_dev ? (int)a.t_dev[b] : a.t_uniform;
-                    const float* cp = a.cond + (size_t)tt * a.CO + c8;
-                    pc0 = *reinterpret_cast<const float4*>(cp); pc1 = *reinterpret_cast<const float4*>(cp + 4);
-                }
-                if (a.res_w != nullptr) {
-                    pr0 = *reinterpret_cast<const float4*>(a.res_bias + c8); pr1 = *reinterpret_cast<const float4*>(a.res_bias + c8 + 4);
-                } else if (a.res_cm != nullptr && valid) {
-                    const float* rp = a.res_cm + ((size_t)b * a.CO + c8) * Lp + 2 + l;
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) rid[j] = rp[(size_t)j * Lp];
-                }
+            float4 pc0 = z4, pc1 = z4;
+            if (full && a.cond != nullptr && a.t_dev != nullptr && valid) {  // per-sample t (per-call entry points): the row depends on the sample
+                const float* cp = a.cond + (size_t)a.t_dev[b] * a.CO + c8;
+                pc0 = *reinterpret_cast<const float4*>(cp); pc1 = *reinterpret_cast<const float4*>(cp + 4);
             }
+            // identity residual of THIS item: requested one item ahead (below), so its latency hid behind the previous epilogue
+            float rid[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) rid[j] = rid_next[j];
 
             mbar_wait(acc_full0 + 8 * stage, ((uint32_t)k >> 1) & 1u);
             __syncwarp();
@@ -250,10 +266,32 @@ __global__ void __launch_bounds__(TCL_THREADS, 1) conv5_tc_kernel(const __grid_c
             float v[8], w[8];  // main accumulator; second accumulator (odd outputs of UP, the block's 1x1 residual conv)
             tc_load_acc(taddr, p1, v);
             if (MODE == TCM_UP || (MODE == TCM_CONV5 && a.res_w != nullptr)) tc_load_acc(taddr + 128, p1, w);
-            // the stage is in registers: hand it back to the issuers (the MMAs of the item after next may start)
+            // parameter rows of the item's channels (producer-filled table)
+            const float* pt = ptab + stage * 160 + cg * 8;
+            const float4 pb0 = *reinterpret_cast<const float4*>(pt), pb1 = *reinterpret_cast<const float4*>(pt + 4);
+            const float4 pg0 = *reinterpret_cast<const float4*>(pt + 32), pg1 = *reinterpret_cast<const float4*>(pt + 36);
+            const float4 pe0 = *reinterpret_cast<const float4*>(pt + 64), pe1 = *reinterpret_cast<const float4*>(pt + 68);
+            const float4 pr0 = *reinterpret_cast<const float4*>(pt + 96), pr1 = *reinterpret_cast<const float4*>(pt + 100);
+            if (a.t_dev == nullptr) { pc0 = *reinterpret_cast<const float4*>(pt + 128); pc1 = *reinterpret_cast<const float4*>(pt + 132); }
+            // the stage (accumulators and parameter rows) is in registers: hand it back (the MMAs of the item after next may start)
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_local(acc_empty0 + 8 * stage);
+            // identity residual of the NEXT item of this CTA
+            if (full && MODE == TCM_CONV5 && a.res_w == nullptr && a.res_cm != nullptr) {
+                const int item_n = item + (int)gridDim.x;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) rid_next[j] = 0.f;
+                if (item_n < n_items) {
+                    const int tile_n = item_n / NC, ntile_n = item_n - tile_n * NC;
+                    const int b_n = tile_n * SPT + s;
+                    if ((s < SPT) && (l < a.L) && (b_n < a.B)) {
+                        const float* rp = a.res_cm + ((size_t)b_n * a.CO + ntile_n * TC_NT + cg * 8) * Lp + 2 + l;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) rid_next[j] = rp[(size_t)j * Lp];
+                    }
+                }
+            }
             if (dbg && tid == 64 && k == 0) a.dbg[5] = clock64();  // TMEM read
 
             if (!full) {
@@ -603,7 +641,7 @@ int launch_conv5_tc(const TcConvArgs& a, cudaStream_t stream) {
         MPDB_REQUIRE(!a.res_w && !a.res_cm && !a.cond && !a.raw_out, "tc down/up: no residual / conditioning");
     const int SPT = TC_RT / (a.L + 4);
     MPDB_REQUIRE(SPT <= 12, "tc conv: too many samples per tile");
-    const size_t smem = (size_t)TC_STAGES * TC_STAGE_BYTES + (2 * TC_STAGES + 4) * 8 + 16 + (2 * 128 * 8 + 12 * 8 * 2) * sizeof(float) + 2 * 12 * 8 * sizeof(double);
+    const size_t smem = (size_t)TC_STAGES * TC_STAGE_BYTES + (2 * TC_STAGES + 4) * 8 + 16 + TC_GN_SCRATCH_BYTES + 2 * 160 * sizeof(float) + 64;
     // persistent: one CTA per SM (TMEM holds two accumulator stages) walking the (row tile, channel chunk) items
     static int sm_count[64] = {0};
     int dev = 0;

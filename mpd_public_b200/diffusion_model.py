@@ -565,7 +565,7 @@ class GaussianDiffusionModel(nn.Module):
         cache = self.__dict__.setdefault("_loop_graphs", {})
         entry = cache.get(key)
         if entry is None:
-            if len(cache) > 8:
+            if len(cache) > 32:
                 cache.clear()
             try:
                 noise = torch.empty((len(steps) + 1, *shape), device=device, dtype=torch.float32)

@@ -174,11 +174,17 @@ def test_config5_shard_shape_panda_h128_b512():
         assert torch.equal(chain[:, :, k, :], v.expand(n_iters + 1, batch, d))
     # a trajectory's result does not depend on its shard: the first 64 trajectories alone give the same samples (the clip
     # flag is batch-global, so equality holds when neither run trips it; both report it through the same flag path)
-    sub = model.run_inference(None, hard_cuda, n_samples=64, horizon=h, return_chain=False, noise=noise[:, :64].contiguous().cuda(),
-                              **dict(kw, guide=None))
-    full = model.run_inference(None, hard_cuda, n_samples=batch, horizon=h, return_chain=False, noise=noise.cuda(), **dict(kw, guide=None))
-    assert rel(sub, full[:64]) < 5e-5  # B = 64 runs the cluster kernel, B = 512 the per-layer kernels: same products and the same
-    # per-step precision policy, partial sums combined in a different order (30 free-running steps)
+    # 22-bit split on every step for this comparison: a one-product step rounds activations to fp16, which turns the last-bit
+    # differences between the two code paths into differences of the size of its own rounding error (tests/test_gpu_mega.py)
+    model.tensor_cores = "force"
+    try:
+        sub = model.run_inference(None, hard_cuda, n_samples=64, horizon=h, return_chain=False, noise=noise[:, :64].contiguous().cuda(),
+                                  **dict(kw, guide=None))
+        full = model.run_inference(None, hard_cuda, n_samples=batch, horizon=h, return_chain=False, noise=noise.cuda(), **dict(kw, guide=None))
+    finally:
+        model.tensor_cores = "auto"
+    assert rel(sub, full[:64]) < 5e-5  # B = 64 runs the cluster kernel, B = 512 the per-layer kernels: same products, partial sums
+    # combined in a different order (30 free-running steps)
 
 
 def C_pos_input(prob, batch, q, seed=23):
