@@ -65,6 +65,10 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+// K-chunks of weights per ring stage (see the producer loop)
+__device__ __forceinline__ int mega_chunks_per_stage(const MegaLayer& Ld, int prec) {
+    return (Ld.n_skip == 0 && Ld.n_res_a + Ld.n_res_skip == 0) ? (prec == 1 ? 4 : 2) : 1;
+}
 __global__ void __launch_bounds__(MG_THREADS, 1) unet_mega_kernel(const __grid_constant__ MegaProgram P) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     unsigned char* abuf = smem_raw;                                   // current activation, operand layout
@@ -122,14 +126,20 @@ __global__ void __launch_bounds__(MG_THREADS, 1) unet_mega_kernel(const __grid_c
                 const bool has_res = Ld.n_res_a + Ld.n_res_skip > 0;  // same chunking as the main conv (engine.cu)
                 const uint32_t act_bytes = (uint32_t)(TC_KCH / 8) * Ld.RT * 16;  // one plane of one K-chunk
                 bool skip_checked = false;
-                for (int c = 0; c < n_main; ++c, ++i) {
+                // A bulk copy costs ~800 cycles whatever its size (tools/probes/bulk_probe.cu), so the wide layers were bound by the
+                // NUMBER of copies, not their bytes. Where a stage needs no room for activations (all K-chunks come from the A
+                // buffer, no residual conv riding along) it takes several K-chunks of weights in ONE copy: 2 with the 22-bit
+                // split, 4 when only the hi halves are streamed (40 KB either way).
+                const int cps = mega_chunks_per_stage(Ld, P.prec);
+                for (int c = 0; c < n_main; c += cps, ++i) {
                     const int s = i % MG_STAGES;
                     if (i >= MG_STAGES) mbar_wait(empty0 + 8 * s, ((uint32_t)(i / MG_STAGES) & 1u) ^ 1u);
                     const int cc = c;
                     const int na = Ld.n_a;
                     const bool from_skip = cc >= na;
+                    const int nch = n_main - c < cps ? n_main - c : cps;
                     const uint32_t wmul = P.prec == 1 ? 1u : 2u;  // precision 1 streams the hi halves of the weights only
-                    const uint32_t wbytes = (uint32_t)ntaps * wmul * TC_B_TAP_BYTES;
+                    const uint32_t wbytes = (uint32_t)nch * ntaps * wmul * TC_B_TAP_BYTES;
                     const uint32_t rbytes = has_res ? wmul * TC_B_TAP_BYTES : 0u;
                     const size_t welems = ((size_t)nc * n_main + cc) * ((size_t)ntaps * 2 * TC_B_TAP_BYTES / 2);
                     const unsigned short* wsrc = P.prec == 1 ? Ld.w_hi + welems / 2 : Ld.w + welems;
@@ -143,7 +153,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) unet_mega_kernel(const __grid_c
                     }
                     __syncwarp();
                     mbar_expect_tx_elect(full0 + 8 * s, wbytes + rbytes + (from_skip ? (P.prec == 1 ? act_bytes : 2u * act_bytes) : 0u));
-                    bulk_g2s_elect(st + 2 * TC_A_PLANE_BYTES, wsrc, wbytes, full0 + 8 * s);
+                    bulk_g2s_elect(st + (cps > 1 ? 0u : 2u * TC_A_PLANE_BYTES), wsrc, wbytes, full0 + 8 * s);
                     if (has_res)  // the residual conv's weights of this chunk, behind the (at most 5) taps
                         bulk_g2s_elect(st + 2 * TC_A_PLANE_BYTES + 5 * wmul * TC_B_TAP_BYTES,
                                        P.prec == 1 ? Ld.res_w_hi + ((size_t)nc * n_main + cc) * (TC_B_TAP_BYTES / 2)
@@ -208,21 +218,27 @@ __global__ void __launch_bounds__(MG_THREADS, 1) unet_mega_kernel(const __grid_c
                 }
                 if (active) {
                     uint32_t acc0 = 0u, acc1 = 0u;  // accumulate flags of the main and the second (residual / odd) accumulator
-                    for (int c = 0; c < n_main; ++c, ++ring_i) {
+                    const int cps = mega_chunks_per_stage(Ld, P.prec);
+                    const int ntaps_l = type == MG_CONV5 ? 5 : type == MG_DOWN ? 3 : 4;
+                    for (int c = 0; c < n_main; c += cps, ++ring_i) {
                         const int sidx = ring_i % MG_STAGES;
-                        const int cc = c;
-                        const bool from_a = cc < n_a;
                         const uint32_t st = stages_u32 + (uint32_t)sidx * MG_STAGE_BYTES;
-                        const uint32_t aaddr = from_a ? abuf_u32 + (uint32_t)cc * (TC_KCH / 8) * lbo + lo_plane
-                                                      : st + ((which == 1 && !p1) ? (uint32_t)TC_A_PLANE_BYTES : 0u);
-                        const uint32_t a_lo = ((aaddr >> 4) & 0x3FFFu) | ((lbo >> 4) << 16);
-                        const uint32_t b_lo = (((st + 2 * TC_A_PLANE_BYTES) >> 4) & 0x3FFFu) | b_lo_fixed;  // rows [0,32) = W_hi, [32,64) = W_lo
                         const uint32_t kstep_a = (2 * lbo) >> 4, kstep_b = ((p1 ? 1u : 2u) * (2 * TC_NT * 16)) >> 4, tap_b = ((p1 ? 1u : 2u) * TC_B_TAP_BYTES) >> 4;
                         if (c > 0) {
                             mbar_wait(full0 + 8 * sidx, (uint32_t)(ring_i / MG_STAGES) & 1u);
                             tc_fence_after();
                         }
                         if (mdbg && c == 0) mdbg[9] = clock64();
+                        const int nch = n_main - c < cps ? n_main - c : cps;
+                        for (int u = 0; u < nch; ++u) {
+                        const int cc = c + u;
+                        const bool from_a = cc < n_a;
+                        const uint32_t aaddr = from_a ? abuf_u32 + (uint32_t)cc * (TC_KCH / 8) * lbo + lo_plane
+                                                      : st + ((which == 1 && !p1) ? (uint32_t)TC_A_PLANE_BYTES : 0u);
+                        const uint32_t a_lo = ((aaddr >> 4) & 0x3FFFu) | ((lbo >> 4) << 16);
+                        // weights: behind the activation planes of a single-chunk stage, from the stage's start in a multi-chunk one
+                        const uint32_t wst = cps > 1 ? st + (uint32_t)u * (uint32_t)ntaps_l * (p1 ? 1u : 2u) * TC_B_TAP_BYTES : st + 2 * TC_A_PLANE_BYTES;
+                        const uint32_t b_lo = ((wst >> 4) & 0x3FFFu) | b_lo_fixed;  // rows [0,32) = W_hi, [32,64) = W_lo
                         if (type == MG_CONV5) {  // taps -2..2 -> row shifts 0..4
 #pragma unroll
                             for (int tap = 0; tap < 5; ++tap)
@@ -261,6 +277,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) unet_mega_kernel(const __grid_c
                                 }
                             }
                         }
+                        }  // K-chunks of this stage
                         tc_commit_elect(empty0 + 8 * sidx);  // the stage is free when both issuers' MMAs that read it have retired
                     }
                     tc_commit_elect(acc_done);
