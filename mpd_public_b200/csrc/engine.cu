@@ -25,6 +25,32 @@ std::atomic<long long> g_launch_count{0};
 bool g_use_pdl = []() { const char* v = getenv("MPDB_PDL"); return v && v[0] == '1'; }();
 void set_error(const std::string& msg) { g_error = msg; }
 
+// TMA tensor map of one activation in the TC layout (plane[tile][C/8][132][8] fp16, hi plane followed by the lo plane at
+// `plane_elems`): 5-D {8 elements, 132 rows, C/8 k-groups, tiles, 2 planes}, box = {8, 132, 4 * nch, 1, planes} — nch K-chunks
+// of one tile, both planes or the hi plane alone, in one cp.async.bulk.tensor; lands as [plane][k-group][row][8], which is
+// the tcgen05 no-swizzle K-major operand layout. cuTensorMapEncodeTiled is fetched through the runtime (no libcuda link).
+int make_act_tensor_map(CUtensorMap* out, const unsigned short* hi_plane, long long plane_elems, int C, long long tiles, int nch, int planes) {
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                 const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn encode = nullptr;
+    if (!encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        MPDB_CHECK_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        MPDB_REQUIRE(fn != nullptr && qres == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled is not available in this driver");
+        encode = (EncodeFn)fn;
+    }
+    const cuuint64_t dims[5] = {8, (cuuint64_t)TC_RT, (cuuint64_t)(C / 8), (cuuint64_t)tiles, 2};
+    const cuuint64_t strides[4] = {16, (cuuint64_t)TC_RT * 16, (cuuint64_t)(C / 8) * TC_RT * 16, (cuuint64_t)plane_elems * 2};  // bytes, dims 1..4
+    const cuuint32_t box[5] = {8, (cuuint32_t)TC_RT, (cuuint32_t)(4 * nch), 1, (cuuint32_t)planes};
+    const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    const CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_UINT16, 5, const_cast<unsigned short*>(hi_plane), dims, strides, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    MPDB_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
+    return 0;
+}
+
 static int group_norm_n_groups(int c) {  // reference layers.py:389-395
     if (c < 8) return 1;
     for (int g = 8; g < 18; ++g)
@@ -93,6 +119,8 @@ struct mpdb_engine {
     unsigned short* work_tc = nullptr;    // activations in tensor-core layout (fp16 hi / scaled-lo planes)
     std::vector<long long> tc_off, tc_plane;  // per buffer: offset of the hi plane, elements per plane
     std::vector<long long> cm_off;            // per buffer: float offset of its (possibly shared) physical slot
+    std::vector<CUtensorMap> tmap3, tmap1;    // per buffer: TMA tensor maps of its TC-layout copy (22-bit split: both planes, 2 K-chunks
+    std::vector<int> tm_nch3, tm_nch1;        // per box; precision 1: hi plane, 4 K-chunks), and the K-chunks per box
     std::vector<char> need_cm;                // per buffer: some consumer reads the fp32 channel-major copy (identity residual, final
                                               // projection, a layer without a tensor-core path); otherwise the tensor-core kernels skip writing it
     int fuse_rtb = []() { const char* v = getenv("MPDB_FUSE_RTB"); return v ? atoi(v) : 1; }();  // cluster-fused residual blocks on the tensor-core path (see can_fuse_rtb)
@@ -456,6 +484,21 @@ static int ensure_workspace(mpdb_engine* e, int B) {
         if (e->xbuf[k]) cudaFree(e->xbuf[k]);
         MPDB_CHECK_CUDA(cudaMalloc(&e->xbuf[k], sizeof(float) * (size_t)B * e->cfg.horizon * e->cfg.state_dim));
     }
+    e->tmap3.assign(nb, CUtensorMap());
+    e->tmap1.assign(nb, CUtensorMap());
+    e->tm_nch3.assign(nb, 0);
+    e->tm_nch1.assign(nb, 0);
+    for (size_t k = 0; k < nb; ++k) {
+        const ActBuf& b = e->bufs[k];
+        if (e->tc_plane[k] == 0 || b.C % TC_KCH != 0) continue;
+        const int Lp = b.L + 2 * HALO, SPT = TC_RT / Lp;
+        const long long tiles = (B + SPT - 1) / SPT;
+        const int chunks = b.C / TC_KCH;
+        e->tm_nch3[k] = chunks < 2 ? chunks : 2;
+        e->tm_nch1[k] = chunks < 4 ? chunks : 4;
+        if (make_act_tensor_map(&e->tmap3[k], e->work_tc + e->tc_off[k], e->tc_plane[k], b.C, tiles, e->tm_nch3[k], 2)) return 1;
+        if (make_act_tensor_map(&e->tmap1[k], e->work_tc + e->tc_off[k], e->tc_plane[k], b.C, tiles, e->tm_nch1[k], 1)) return 1;
+    }
     e->work_batch = B;
     build_mega(e, B);
     return 0;
@@ -510,6 +553,13 @@ static void fill_tc_args(mpdb_engine* e, const ConvOp& op, const long long* t_de
     a.out_hi = hi(op.out); a.out_lo = lo(op.out);
     a.CO = op.CO; a.L = op.L_in; a.B = B; a.gs = op.gs;
     a.prec = t_dev == nullptr ? step_prec(e, t_uniform) : 3;  // per-sample t (per-call entry points): always the full split
+    const int src_ids[4] = {op.tc_in0, op.in1, op.res_w >= 0 ? op.tc_res0 : -2, op.res_w >= 0 ? op.res1 : -2};
+    for (int i = 0; i < 4; ++i) {
+        const int id = src_ids[i];
+        if (id < 0 || e->tc_plane[id] == 0) continue;
+        a.tm[i] = a.prec == 1 ? e->tmap1[id] : e->tmap3[id];
+        a.tm_nch[i] = a.prec == 1 ? e->tm_nch1[id] : e->tm_nch3[id];
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -1562,10 +1612,9 @@ extern "C" int mpdb_debug_tc_conv5(const float* x_cm, const float* w, float* raw
     unsigned short *wt = nullptr, *xh = nullptr, *xl = nullptr;
     MPDB_CHECK_CUDA(cudaMalloc(&wp, sizeof(float) * (size_t)CI * CO * 5));
     MPDB_CHECK_CUDA(cudaMalloc(&wt, 2 * 2 * (size_t)CI * CO * 5));
-    MPDB_CHECK_CUDA(cudaMalloc(&xh, 2 * plane));
-    MPDB_CHECK_CUDA(cudaMalloc(&xl, 2 * plane));
-    MPDB_CHECK_CUDA(cudaMemsetAsync(xh, 0, 2 * plane, st));
-    MPDB_CHECK_CUDA(cudaMemsetAsync(xl, 0, 2 * plane, st));
+    MPDB_CHECK_CUDA(cudaMalloc(&xh, 2 * 2 * plane));  // hi plane followed by the lo plane (one tensor map covers both)
+    xl = xh + plane;
+    MPDB_CHECK_CUDA(cudaMemsetAsync(xh, 0, 2 * 2 * plane, st));
     int rc = launch_repack_conv(w, wp, CO, CI, 5, 0, st);
     if (!rc) rc = launch_pack_tc_weights(wp, wt, nullptr, CI, CI, CO, 5, 0x43210u, st);
     if (!rc) rc = launch_cm_to_tc(x_cm, xh, xl, B, CI, L, st);
@@ -1576,12 +1625,15 @@ extern "C" int mpdb_debug_tc_conv5(const float* x_cm, const float* w, float* raw
         a.w = wt;
         a.raw_out = raw;
         a.CO = CO; a.L = L; a.B = B; a.gs = 32; a.mode = TCM_CONV5;
+        a.prec = 3;
+        a.tm_nch[0] = CI / TC_KCH < 2 ? CI / TC_KCH : 2;
+        rc = make_act_tensor_map(&a.tm[0], xh, (long long)plane, CI, tiles, a.tm_nch[0], 2);
         float* dummy = wp;  // gamma/beta/bias are not read in raw mode but must be non-null for the launch checks
         a.gamma = dummy; a.beta = dummy; a.bias = dummy;
-        rc = launch_conv5_tc(a, st);
+        if (!rc) rc = launch_conv5_tc(a, st);
     }
     cudaError_t e1 = cudaStreamSynchronize(st);
-    cudaFree(wp); cudaFree(wt); cudaFree(xh); cudaFree(xl);
+    cudaFree(wp); cudaFree(wt); cudaFree(xh);
     if (rc) return rc;
     MPDB_CHECK_CUDA(e1);
     return 0;

@@ -1,5 +1,6 @@
 // Internal (non-ABI) declarations shared between the translation units of libmpdb200.
 #pragma once
+#include <cuda.h>  // CUtensorMap (type only; cuTensorMapEncodeTiled is resolved at run time through the runtime API)
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -82,7 +83,17 @@ struct TcConvArgs {
     int CO, L, B, gs;
     int mode;                     // TcMode; L is the INPUT length (DOWN writes L/2 positions, UP writes 2L)
     int prec;                     // 1: one fp16 product per MMA step (hi planes only); otherwise the 22-bit three-product split
+    // TMA tensor maps of the four activation sources (in0, in1, r0, r1) for conv5_tc_kernel: 5-D views
+    // {8 elements, 132 rows, C/8 k-groups, tiles, 2 planes} of the TC layout whose box brings tm_nch[i] K-chunks of a tile —
+    // both planes with the 22-bit split, the hi plane alone in precision 1 — in ONE cp.async.bulk.tensor (UTMALDG)
+    CUtensorMap tm[4];
+    int tm_nch[4];
 };
+constexpr int TC_PS_STAGES = 2;                                       // ring depth of the persistent kernel
+constexpr int TC_PS_ACT_BYTES = 2 * 2 * (TC_KCH / 8) * TC_RT * 16;   // activation area of a stage: 2 chunks x 2 planes (or 4 chunks x hi plane)
+constexpr int TC_PS_W_BYTES = 2 * 5 * 2 * (TC_KCH / 8) * TC_NT * 16; // weight area: 2 chunks x 5 taps x (hi|lo) (or 4 chunks x hi)
+constexpr int TC_PS_STAGE_BYTES = TC_PS_ACT_BYTES + TC_PS_W_BYTES;   // 74,752
+int make_act_tensor_map(CUtensorMap* out, const unsigned short* hi_plane, long long plane_elems, int C, long long tiles, int nch, int planes);
 int launch_conv5_tc(const TcConvArgs& a, cudaStream_t stream);
 
 // Whole ResidualTemporalBlock in one launch (cluster of CO/32 CTAs per row tile, h1 exchanged through DSMEM):

@@ -49,15 +49,30 @@ constexpr int TCL_TMEM_COLS = 512;  // two stages: the MMAs of work item k+1 run
 // stage; the epilogue releases a stage as soon as its values are in registers), so per item the CTA pays
 // max(MMA + operand streaming, epilogue) instead of setup + first-copy latency + MMA + epilogue + teardown: at 512
 // trajectories per GPU a layer is 500-1000 items on 148 SMs and one-CTA-per-item launches spent ~10 us per item on ~2 us of work.
+// Operand ring: TC_PS_STAGES stages of 74,752 B = [activations | weights]. A stage holds a GROUP of K-chunks of one source
+// tensor — 2 with the 22-bit split (both planes), 4 in precision 1 (hi plane only; fewer when the tensor is narrower) —
+// brought by TWO asynchronous copies: one cp.async.bulk.tensor (TMA tensor map, 5-D box {8, 132 rows, 4 * chunks k-groups, 1
+// tile, planes}: lands as [plane][k-group][row][8], the tcgen05 operand layout) and one cp.async.bulk for the group's weights
+// (contiguous in the packed layout). A bulk copy costs ~800 cycles of the copy engine whatever its size
+// (tools/probes/bulk_probe.cu), so the wide layers were bound by the NUMBER of copies: 3 per K-chunk before, 2 per group now.
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, int c2, int c3, int c4, uint32_t bar) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "@q cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];\n\t}"
+        ::"r"(dst), "l"(reinterpret_cast<unsigned long long>(tm)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "r"(bar)
+        : "memory");
+}
+
 template <int MODE, int GS>
 __global__ void __launch_bounds__(TCL_THREADS, 1) conv5_tc_kernel(const __grid_constant__ TcConvArgs a) {
     constexpr int NTAPS = MODE == TCM_CONV5 ? 5 : MODE == TCM_DOWN ? 3 : 4;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     // carve-up: stages | barriers | tmem slot | epilogue scratch
     unsigned char* stages = smem_raw;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + TC_STAGES * TC_STAGE_BYTES);  // full[S], empty[S], acc_full[2], acc_empty[2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_STAGES + 4);
-    float* part = reinterpret_cast<float*>(tmem_slot + 4);  // GroupNorm scratch: [2][128][8] floats + [2][12][8] doubles
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + TC_PS_STAGES * TC_PS_STAGE_BYTES);  // full[S], empty[S], acc_full[2], acc_empty[2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_PS_STAGES + 4);
+    float* part = reinterpret_cast<float*>(tmem_slot + 4);  // GroupNorm scratch
     // per-item epilogue parameters of the item's 32 output channels {bias, gamma, beta, residual bias, time-conditioning row at
     // uniform t}, double-buffered like the accumulators and filled by the producer warp one item ahead: in the item loop the
     // epilogue warps would otherwise pay a global-memory round trip per item with nothing to hide it behind
@@ -68,21 +83,29 @@ __global__ void __launch_bounds__(TCL_THREADS, 1) conv5_tc_kernel(const __grid_c
     if (dbg && tid == 64) a.dbg[0] = clock64();
     const int Lp = a.L + 4;
     const int SPT = TC_RT / Lp;
-    const int n_main = (a.c0 + a.c1) / TC_KCH;
-    const int n_res = a.res_w ? (a.rc0 + a.rc1) / TC_KCH : 0;
-    const int n_steps = n_main + n_res;
     const int NC = a.CO / TC_NT;
     const int n_items = ((a.B + SPT - 1) / SPT) * NC;  // item = tile * NC + ntile
     // precision 1 (a.prec == 1, engine.cu step_prec): one fp16 product per MMA step; the two issuers split it by K-group
     // into separate accumulators ([0,32) and [64,96)), the lo planes are neither loaded nor written
     const bool p1 = a.prec == 1;
+    // K-chunk groups of an item, in order: main conv over source 0, source 1 (concatenated input), then the fused 1x1 residual
+    // conv over its sources 2, 3. Source i: Cs[i] channels in groups of gsz[i] chunks (the box of its tensor map).
+    const int Cs[4] = {a.c0, a.c1, a.res_w ? a.rc0 : 0, a.res_w ? a.rc1 : 0};
+    int ng[4], n_groups = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int ch = Cs[i] / TC_KCH;
+        ng[i] = ch > 0 ? (ch + a.tm_nch[i] - 1) / a.tm_nch[i] : 0;
+        n_groups += ng[i];
+    }
+    const int n_main_ch = (a.c0 + a.c1) / TC_KCH, n_res_ch = a.res_w ? (a.rc0 + a.rc1) / TC_KCH : 0;
 
     const uint32_t stages_u32 = smem_u32(stages);
-    const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + TC_STAGES);
-    const uint32_t acc_full0 = smem_u32(bars + 2 * TC_STAGES), acc_empty0 = acc_full0 + 16;
+    const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + TC_PS_STAGES);
+    const uint32_t acc_full0 = smem_u32(bars + 2 * TC_PS_STAGES), acc_empty0 = acc_full0 + 16;
 
     if (tid == 0) {
-        for (int s = 0; s < TC_STAGES; ++s) {
+        for (int s = 0; s < TC_PS_STAGES; ++s) {
             mbar_init(full0 + 8 * s, 1);
             mbar_init(empty0 + 8 * s, 2);  // both issuers release a stage
         }
@@ -104,45 +127,48 @@ __global__ void __launch_bounds__(TCL_THREADS, 1) conv5_tc_kernel(const __grid_c
     const uint32_t tmem_base = *tmem_slot;
     if (dbg && tid == 64) a.dbg[1] = clock64();  // setup done (barriers, TMEM)
 
+    // group gi of an item -> (source, first chunk within the source, chunks in the group, first chunk within main / residual conv)
+    auto group_geom = [&](int gi, int& src, int& c_src, int& nch, int& c_conv) {
+        src = 0;
+        int g = gi;
+        while (g >= ng[src]) { g -= ng[src]; ++src; }
+        c_src = g * a.tm_nch[src];
+        const int ch = Cs[src] / TC_KCH;
+        nch = ch - c_src < a.tm_nch[src] ? ch - c_src : a.tm_nch[src];
+        c_conv = c_src + ((src == 1) ? a.c0 / TC_KCH : (src == 3) ? a.rc0 / TC_KCH : 0);
+    };
+
     if (warp == TC_THREADS / 32) {
-        // ===== producer warp: K-chunk i of the CTA's item sequence -> stage i % STAGES (bulk-async copies, completion counted on
-        // the stage's mbarrier). Weights are constants: the first chunks' weight copies are issued before the dependency wait,
-        // so under programmatic dependent launch they overlap the previous kernel's epilogue. Activations follow it. =====
-        auto produce = [&](int i, int item, int c_step, bool weights, bool acts) {
+        // ===== producer warp: group i of the CTA's item sequence -> stage i % STAGES. Weights are constants: the first groups'
+        // weight copies are issued before the dependency wait, so under programmatic dependent launch they overlap the
+        // previous kernel's epilogue. Activations follow it. =====
+        auto produce = [&](int i, int item, int gi, bool weights, bool acts) {
             const int tile = item / NC, ntile = item - tile * NC;
-            const int s = i % TC_STAGES;
-            const bool is_res = c_step >= n_main;
-            const int c = is_res ? c_step - n_main : c_step;
+            const int s = i % TC_PS_STAGES;
+            int src, c_src, nch, c_conv;
+            group_geom(gi, src, c_src, nch, c_conv);
+            const bool is_res = src >= 2;
             const int ntaps = is_res ? 1 : NTAPS;
-            const uint32_t bbytes = (p1 ? 1u : 2u) * ntaps * TC_B_TAP_BYTES;  // precision 1 streams the hi halves only
-            const uint32_t st = stages_u32 + (uint32_t)s * TC_STAGE_BYTES;
+            const uint32_t wmul = p1 ? 1u : 2u;  // precision 1 streams the hi halves only
+            const uint32_t bbytes = (uint32_t)nch * wmul * ntaps * TC_B_TAP_BYTES;
+            const uint32_t abytes = (uint32_t)a.tm_nch[src] * wmul * TC_A_PLANE_BYTES;  // the whole box (rows past the tensor are zero-filled)
+            const uint32_t st = stages_u32 + (uint32_t)s * TC_PS_STAGE_BYTES;
             if (weights) {
-                const size_t welems = is_res ? ((size_t)ntile * n_res + c) * (2 * 1 * TC_B_TAP_BYTES / 2)
-                                             : ((size_t)ntile * n_main + c) * (2 * NTAPS * TC_B_TAP_BYTES / 2);
+                const size_t welems = is_res ? ((size_t)ntile * n_res_ch + c_conv) * (2 * 1 * TC_B_TAP_BYTES / 2)
+                                             : ((size_t)ntile * n_main_ch + c_conv) * (2 * NTAPS * TC_B_TAP_BYTES / 2);
                 const unsigned short* wsrc = p1 ? (is_res ? a.res_w_hi : a.w_hi) + welems / 2 : (is_res ? a.res_w : a.w) + welems;
-                mbar_expect_tx_elect(full0 + 8 * s, (p1 ? 1u : 2u) * TC_A_PLANE_BYTES + bbytes);  // covers the activation copies too
-                bulk_g2s_elect(st + 2 * TC_A_PLANE_BYTES, wsrc, bbytes, full0 + 8 * s);
+                mbar_expect_tx_elect(full0 + 8 * s, abytes + bbytes);  // covers the activation copy too
+                bulk_g2s_elect(st + TC_PS_ACT_BYTES, wsrc, bbytes, full0 + 8 * s);
             }
-            if (acts) {
-                const int C0 = is_res ? a.rc0 : a.c0, C1 = is_res ? a.rc1 : a.c1;
-                const bool second = c * TC_KCH >= C0;
-                const unsigned short* ahi = is_res ? (second ? a.r1_hi : a.r0_hi) : (second ? a.in1_hi : a.in0_hi);
-                const unsigned short* alo = is_res ? (second ? a.r1_lo : a.r0_lo) : (second ? a.in1_lo : a.in0_lo);
-                const int Csrc = second ? C1 : C0;
-                const int kg0 = (c * TC_KCH - (second ? C0 : 0)) / 8;
-                const size_t aoff = ((size_t)tile * (Csrc / 8) + kg0) * TC_RT * 8;  // elements
-                bulk_g2s_elect(st, ahi + aoff, TC_A_PLANE_BYTES, full0 + 8 * s);
-                if (!p1) bulk_g2s_elect(st + TC_A_PLANE_BYTES, alo + aoff, TC_A_PLANE_BYTES, full0 + 8 * s);
-            }
+            if (acts) tma_load_5d(st, &a.tm[src], 0, 0, c_src * (TC_KCH / 8), tile, 0, full0 + 8 * s);
         };
-        // the first min(STAGES, chunks of this CTA) chunks: weights before the dependency wait, activations after it
         int i = 0, pre = 0;
-        for (int item = blockIdx.x; item < n_items && pre < TC_STAGES; item += gridDim.x)
-            for (int c = 0; c < n_steps && pre < TC_STAGES; ++c, ++pre) produce(pre, item, c, true, false);
+        for (int item = blockIdx.x; item < n_items && pre < TC_PS_STAGES; item += gridDim.x)
+            for (int gi = 0; gi < n_groups && pre < TC_PS_STAGES; ++gi, ++pre) produce(pre, item, gi, true, false);
         pdl_wait();
         pre = 0;
-        for (int item = blockIdx.x; item < n_items && pre < TC_STAGES; item += gridDim.x)
-            for (int c = 0; c < n_steps && pre < TC_STAGES; ++c, ++pre) produce(pre, item, c, false, true);
+        for (int item = blockIdx.x; item < n_items && pre < TC_PS_STAGES; item += gridDim.x)
+            for (int gi = 0; gi < n_groups && pre < TC_PS_STAGES; ++gi, ++pre) produce(pre, item, gi, false, true);
         int kk = 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++kk) {
             {   // parameter rows of this item -> ptab[stage]; the stage's previous user has read its rows before it released the accumulators
@@ -158,11 +184,11 @@ __global__ void __launch_bounds__(TCL_THREADS, 1) conv5_tc_kernel(const __grid_c
                 __syncwarp();
                 if (lane == 0) mbar_arrive_local(acc_full0 + 8 * stage);  // release: the rows are visible to whoever sees the phase complete
             }
-            for (int c = 0; c < n_steps; ++c, ++i) {
-                if (i < TC_STAGES) continue;  // issued above
-                mbar_wait(empty0 + 8 * (i % TC_STAGES), ((uint32_t)(i / TC_STAGES) & 1u) ^ 1u);
+            for (int gi = 0; gi < n_groups; ++gi, ++i) {
+                if (i < TC_PS_STAGES) continue;  // issued above
+                mbar_wait(empty0 + 8 * (i % TC_PS_STAGES), ((uint32_t)(i / TC_PS_STAGES) & 1u) ^ 1u);
                 __syncwarp();
-                produce(i, item, c, true, true);
+                produce(i, item, gi, true, true);
             }
         }
     } else if (warp > TC_THREADS / 32) {
@@ -184,33 +210,41 @@ __global__ void __launch_bounds__(TCL_THREADS, 1) conv5_tc_kernel(const __grid_c
             mbar_wait(acc_empty0 + 8 * stage, (((uint32_t)k >> 1) & 1u) ^ 1u);
             tc_fence_after();
             uint32_t acc0 = 0u, acc1 = 0u;
-            for (int c = 0; c < n_steps; ++c, ++i) {
-                const int s = i % TC_STAGES;
-                const uint32_t st = stages_u32 + (uint32_t)s * TC_STAGE_BYTES;
-                const uint32_t a_lo = (((st + ((which == 1 && !p1) ? (uint32_t)TC_A_PLANE_BYTES : 0u)) >> 4) & 0x3FFFu) | a_lo_fixed;
-                const uint32_t b_lo = (((st + 2 * TC_A_PLANE_BYTES) >> 4) & 0x3FFFu) | b_lo_fixed;
-                mbar_wait(full0 + 8 * s, (uint32_t)(i / TC_STAGES) & 1u);
+            for (int gi = 0; gi < n_groups; ++gi, ++i) {
+                const int s = i % TC_PS_STAGES;
+                const uint32_t st = stages_u32 + (uint32_t)s * TC_PS_STAGE_BYTES;
+                int src, c_src, nch, c_conv;
+                group_geom(gi, src, c_src, nch, c_conv);
+                const bool is_res = src >= 2;
+                // the box lands as [plane][k-group][row][8]: the lo plane starts after the box's chunks of the hi plane
+                const uint32_t plane_off = (which == 1 && !p1) ? (uint32_t)a.tm_nch[src] * TC_A_PLANE_BYTES : 0u;
+                mbar_wait(full0 + 8 * s, (uint32_t)(i / TC_PS_STAGES) & 1u);
                 tc_fence_after();
-                if (c >= n_main) {  // fused 1x1 residual conv: centre row (+2), second accumulator
-#pragma unroll
-                    for (int kk = 0; kk < TC_KCH / 16; ++kk) {
-                        if (p1 && kk != which) continue;
-                        tc_mma_bf16_elect32(col0 + 128, a_lo + kk * kstep_a + 2, desc_hi, b_lo + kk * kstep_b, desc_hi, idesc, acc1);
-                        acc1 = 1u;
-                    }
-                } else {
-#pragma unroll
-                    for (int tap = 0; tap < NTAPS; ++tap) {
-                        // row shift of the tap (in 16-byte rows; +2 is the centre) and the accumulator it feeds
-                        //   CONV5: taps -2..2 -> shifts 0..4           DOWN (k3, pad 1): taps -1..1 -> shifts 1..3
-                        //   UP  : packed taps [W1, W3 | W0, W2]: even = W1 x[m] + W3 x[m-1], odd = W0 x[m+1] + W2 x[m]
-                        const int shift = MODE == TCM_CONV5 ? tap : MODE == TCM_DOWN ? tap + 1 : (tap == 0 ? 2 : tap == 1 ? 1 : tap == 2 ? 3 : 2);
-                        const bool second_acc = MODE == TCM_UP && tap >= 2;
+                for (int u = 0; u < nch; ++u) {
+                    const uint32_t a_lo = (((st + plane_off + (uint32_t)u * TC_A_PLANE_BYTES) >> 4) & 0x3FFFu) | a_lo_fixed;
+                    const uint32_t wst = st + TC_PS_ACT_BYTES + (uint32_t)u * (uint32_t)(is_res ? 1 : NTAPS) * (p1 ? 1u : 2u) * TC_B_TAP_BYTES;
+                    const uint32_t b_lo = ((wst >> 4) & 0x3FFFu) | b_lo_fixed;
+                    if (is_res) {  // fused 1x1 residual conv: centre row (+2), second accumulator
 #pragma unroll
                         for (int kk = 0; kk < TC_KCH / 16; ++kk) {
                             if (p1 && kk != which) continue;
-                            if (second_acc) { tc_mma_bf16_elect32(col0 + 128, a_lo + kk * kstep_a + shift, desc_hi, b_lo + tap * tap_b + kk * kstep_b, desc_hi, idesc, acc1); acc1 = 1u; }
-                            else { tc_mma_bf16_elect32(col0, a_lo + kk * kstep_a + shift, desc_hi, b_lo + tap * tap_b + kk * kstep_b, desc_hi, idesc, acc0); acc0 = 1u; }
+                            tc_mma_bf16_elect32(col0 + 128, a_lo + kk * kstep_a + 2, desc_hi, b_lo + kk * kstep_b, desc_hi, idesc, acc1);
+                            acc1 = 1u;
+                        }
+                    } else {
+#pragma unroll
+                        for (int tap = 0; tap < NTAPS; ++tap) {
+                            // row shift of the tap (in 16-byte rows; +2 is the centre) and the accumulator it feeds
+                            //   CONV5: taps -2..2 -> shifts 0..4           DOWN (k3, pad 1): taps -1..1 -> shifts 1..3
+                            //   UP  : packed taps [W1, W3 | W0, W2]: even = W1 x[m] + W3 x[m-1], odd = W0 x[m+1] + W2 x[m]
+                            const int shift = MODE == TCM_CONV5 ? tap : MODE == TCM_DOWN ? tap + 1 : (tap == 0 ? 2 : tap == 1 ? 1 : tap == 2 ? 3 : 2);
+                            const bool second_acc = MODE == TCM_UP && tap >= 2;
+#pragma unroll
+                            for (int kk = 0; kk < TC_KCH / 16; ++kk) {
+                                if (p1 && kk != which) continue;
+                                if (second_acc) { tc_mma_bf16_elect32(col0 + 128, a_lo + kk * kstep_a + shift, desc_hi, b_lo + tap * tap_b + kk * kstep_b, desc_hi, idesc, acc1); acc1 = 1u; }
+                                else { tc_mma_bf16_elect32(col0, a_lo + kk * kstep_a + shift, desc_hi, b_lo + tap * tap_b + kk * kstep_b, desc_hi, idesc, acc0); acc0 = 1u; }
+                            }
                         }
                     }
                 }
@@ -641,7 +675,11 @@ int launch_conv5_tc(const TcConvArgs& a, cudaStream_t stream) {
         MPDB_REQUIRE(!a.res_w && !a.res_cm && !a.cond && !a.raw_out, "tc down/up: no residual / conditioning");
     const int SPT = TC_RT / (a.L + 4);
     MPDB_REQUIRE(SPT <= 12, "tc conv: too many samples per tile");
-    const size_t smem = (size_t)TC_STAGES * TC_STAGE_BYTES + (2 * TC_STAGES + 4) * 8 + 16 + TC_GN_SCRATCH_BYTES + 2 * 160 * sizeof(float) + 64;
+    const size_t smem = (size_t)TC_PS_STAGES * TC_PS_STAGE_BYTES + (2 * TC_PS_STAGES + 4) * 8 + 16 + TC_GN_SCRATCH_BYTES + 2 * 160 * sizeof(float) + 64;
+    for (int i = 0; i < 4; ++i) {
+        const int Ci = i == 0 ? a.c0 : i == 1 ? a.c1 : i == 2 ? (a.res_w ? a.rc0 : 0) : (a.res_w ? a.rc1 : 0);
+        MPDB_REQUIRE(Ci == 0 || (a.tm_nch[i] >= 1 && a.tm_nch[i] <= (a.prec == 1 ? 4 : 2)), "tc conv: missing / oversized activation tensor map");
+    }
     // persistent: one CTA per SM (TMEM holds two accumulator stages) walking the (row tile, channel chunk) items
     static int sm_count[64] = {0};
     int dev = 0;
