@@ -494,8 +494,11 @@ static int ensure_workspace(mpdb_engine* e, int B) {
         const int Lp = b.L + 2 * HALO, SPT = TC_RT / Lp;
         const long long tiles = (B + SPT - 1) / SPT;
         const int chunks = b.C / TC_KCH;
-        e->tm_nch3[k] = chunks < 2 ? chunks : 2;
-        e->tm_nch1[k] = chunks < 4 ? chunks : 4;
+        // K-chunks per box: ~37 KB stages either way (22-bit split: 1 chunk x 2 planes + 20 KB of weights; precision 1: 2 chunks x hi
+        // plane + 2 x 10 KB), so the 211 KB ring is 5 stages deep — the L2 -> shared latency (~2 us) needs the depth more than the
+        // copy engine needs fewer, larger copies (profiles/r02_tc_timeline_cfg5.txt)
+        e->tm_nch3[k] = 1;
+        e->tm_nch1[k] = chunks < 2 ? chunks : 2;
         if (make_act_tensor_map(&e->tmap3[k], e->work_tc + e->tc_off[k], e->tc_plane[k], b.C, tiles, e->tm_nch3[k], 2)) return 1;
         if (make_act_tensor_map(&e->tmap1[k], e->work_tc + e->tc_off[k], e->tc_plane[k], b.C, tiles, e->tm_nch1[k], 1)) return 1;
     }
@@ -1626,7 +1629,7 @@ extern "C" int mpdb_debug_tc_conv5(const float* x_cm, const float* w, float* raw
         a.raw_out = raw;
         a.CO = CO; a.L = L; a.B = B; a.gs = 32; a.mode = TCM_CONV5;
         a.prec = 3;
-        a.tm_nch[0] = CI / TC_KCH < 2 ? CI / TC_KCH : 2;
+        a.tm_nch[0] = 1;
         rc = make_act_tensor_map(&a.tm[0], xh, (long long)plane, CI, tiles, a.tm_nch[0], 2);
         float* dummy = wp;  // gamma/beta/bias are not read in raw mode but must be non-null for the launch checks
         a.gamma = dummy; a.beta = dummy; a.bias = dummy;

@@ -88,11 +88,10 @@ struct TcConvArgs {
     // both planes with the 22-bit split, the hi plane alone in precision 1 — in ONE cp.async.bulk.tensor (UTMALDG)
     CUtensorMap tm[4];
     int tm_nch[4];
+    int ps_stages, ps_stage_bytes, ps_act_bytes;  // operand-ring geometry (set by launch_conv5_tc)
 };
-constexpr int TC_PS_STAGES = 2;                                       // ring depth of the persistent kernel
-constexpr int TC_PS_ACT_BYTES = 2 * 2 * (TC_KCH / 8) * TC_RT * 16;   // activation area of a stage: 2 chunks x 2 planes (or 4 chunks x hi plane)
-constexpr int TC_PS_W_BYTES = 2 * 5 * 2 * (TC_KCH / 8) * TC_NT * 16; // weight area: 2 chunks x 5 taps x (hi|lo) (or 4 chunks x hi)
-constexpr int TC_PS_STAGE_BYTES = TC_PS_ACT_BYTES + TC_PS_W_BYTES;   // 74,752
+constexpr int TC_PS_MAX_STAGES = 8;
+constexpr int TC_PS_RING_BYTES = 216064;  // operand ring of the persistent kernel, cut into stages of (activation box + weight group) bytes by launch_conv5_tc
 int make_act_tensor_map(CUtensorMap* out, const unsigned short* hi_plane, long long plane_elems, int C, long long tiles, int nch, int planes);
 int launch_conv5_tc(const TcConvArgs& a, cudaStream_t stream);
 

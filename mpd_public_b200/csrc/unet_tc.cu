@@ -69,9 +69,13 @@ __global__ void __launch_bounds__(TCL_THREADS, 1) conv5_tc_kernel(const __grid_c
     constexpr int NTAPS = MODE == TCM_CONV5 ? 5 : MODE == TCM_DOWN ? 3 : 4;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     // carve-up: stages | barriers | tmem slot | epilogue scratch
+    // ring geometry chosen by the launcher for this layer: NS stages of a.ps_stage_bytes = [activation box | weight group]
+    // (narrow layers: many small stages = deep prefetch over the ~2 us L2 -> shared latency; wide layers: few large ones)
+    const int NS = a.ps_stages;
+    const uint32_t STAGE_BYTES = (uint32_t)a.ps_stage_bytes, ACT_BYTES = (uint32_t)a.ps_act_bytes;
     unsigned char* stages = smem_raw;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + TC_PS_STAGES * TC_PS_STAGE_BYTES);  // full[S], empty[S], acc_full[2], acc_empty[2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_PS_STAGES + 4);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + TC_PS_RING_BYTES);  // full[8], empty[8], acc_full[2], acc_empty[2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_PS_MAX_STAGES + 4);
     float* part = reinterpret_cast<float*>(tmem_slot + 4);  // GroupNorm scratch
     // per-item epilogue parameters of the item's 32 output channels {bias, gamma, beta, residual bias, time-conditioning row at
     // uniform t}, double-buffered like the accumulators and filled by the producer warp one item ahead: in the item loop the
@@ -101,16 +105,16 @@ __global__ void __launch_bounds__(TCL_THREADS, 1) conv5_tc_kernel(const __grid_c
     const int n_main_ch = (a.c0 + a.c1) / TC_KCH, n_res_ch = a.res_w ? (a.rc0 + a.rc1) / TC_KCH : 0;
 
     const uint32_t stages_u32 = smem_u32(stages);
-    const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + TC_PS_STAGES);
-    const uint32_t acc_full0 = smem_u32(bars + 2 * TC_PS_STAGES), acc_empty0 = acc_full0 + 16;
+    const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + TC_PS_MAX_STAGES);
+    const uint32_t acc_full0 = smem_u32(bars + 2 * TC_PS_MAX_STAGES), acc_empty0 = acc_full0 + 16;
 
     if (tid == 0) {
-        for (int s = 0; s < TC_PS_STAGES; ++s) {
+        for (int s = 0; s < NS; ++s) {
             mbar_init(full0 + 8 * s, 1);
             mbar_init(empty0 + 8 * s, 2);  // both issuers release a stage
         }
         for (int s = 0; s < 2; ++s) {
-            mbar_init(acc_full0 + 8 * s, 3);                  // both issuers' MMAs of the item have retired + the producer's parameter rows are in place
+            mbar_init(acc_full0 + 8 * s, 3);                  // both issuers' MMAs of the item have retired + issuer 1's parameter rows are in place
             mbar_init(acc_empty0 + 8 * s, TC_THREADS / 32);   // every epilogue warp has read its part of the stage
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -144,7 +148,7 @@ __global__ void __launch_bounds__(TCL_THREADS, 1) conv5_tc_kernel(const __grid_c
         // previous kernel's epilogue. Activations follow it. =====
         auto produce = [&](int i, int item, int gi, bool weights, bool acts) {
             const int tile = item / NC, ntile = item - tile * NC;
-            const int s = i % TC_PS_STAGES;
+            const int s = i % NS;
             int src, c_src, nch, c_conv;
             group_geom(gi, src, c_src, nch, c_conv);
             const bool is_res = src >= 2;
@@ -152,45 +156,31 @@ __global__ void __launch_bounds__(TCL_THREADS, 1) conv5_tc_kernel(const __grid_c
             const uint32_t wmul = p1 ? 1u : 2u;  // precision 1 streams the hi halves only
             const uint32_t bbytes = (uint32_t)nch * wmul * ntaps * TC_B_TAP_BYTES;
             const uint32_t abytes = (uint32_t)a.tm_nch[src] * wmul * TC_A_PLANE_BYTES;  // the whole box (rows past the tensor are zero-filled)
-            const uint32_t st = stages_u32 + (uint32_t)s * TC_PS_STAGE_BYTES;
+            const uint32_t st = stages_u32 + (uint32_t)s * STAGE_BYTES;
             if (weights) {
                 const size_t welems = is_res ? ((size_t)ntile * n_res_ch + c_conv) * (2 * 1 * TC_B_TAP_BYTES / 2)
                                              : ((size_t)ntile * n_main_ch + c_conv) * (2 * NTAPS * TC_B_TAP_BYTES / 2);
                 const unsigned short* wsrc = p1 ? (is_res ? a.res_w_hi : a.w_hi) + welems / 2 : (is_res ? a.res_w : a.w) + welems;
                 mbar_expect_tx_elect(full0 + 8 * s, abytes + bbytes);  // covers the activation copy too
-                bulk_g2s_elect(st + TC_PS_ACT_BYTES, wsrc, bbytes, full0 + 8 * s);
+                bulk_g2s_elect(st + ACT_BYTES, wsrc, bbytes, full0 + 8 * s);
             }
             if (acts) tma_load_5d(st, &a.tm[src], 0, 0, c_src * (TC_KCH / 8), tile, 0, full0 + 8 * s);
         };
         int i = 0, pre = 0;
-        for (int item = blockIdx.x; item < n_items && pre < TC_PS_STAGES; item += gridDim.x)
-            for (int gi = 0; gi < n_groups && pre < TC_PS_STAGES; ++gi, ++pre) produce(pre, item, gi, true, false);
+        for (int item = blockIdx.x; item < n_items && pre < NS; item += gridDim.x)
+            for (int gi = 0; gi < n_groups && pre < NS; ++gi, ++pre) produce(pre, item, gi, true, false);
         pdl_wait();
         pre = 0;
-        for (int item = blockIdx.x; item < n_items && pre < TC_PS_STAGES; item += gridDim.x)
-            for (int gi = 0; gi < n_groups && pre < TC_PS_STAGES; ++gi, ++pre) produce(pre, item, gi, false, true);
-        int kk = 0;
-        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++kk) {
-            {   // parameter rows of this item -> ptab[stage]; the stage's previous user has read its rows before it released the accumulators
-                const int stage = kk & 1, ntile = item % NC;
-                mbar_wait(acc_empty0 + 8 * stage, (((uint32_t)kk >> 1) & 1u) ^ 1u);
-                float* pt = ptab + stage * 160;
-                const int c = ntile * TC_NT + lane;
-                pt[lane] = a.bias ? a.bias[c] : 0.f;
-                pt[32 + lane] = (MODE == TCM_CONV5 && a.gamma) ? a.gamma[c] : 0.f;
-                pt[64 + lane] = (MODE == TCM_CONV5 && a.beta) ? a.beta[c] : 0.f;
-                pt[96 + lane] = a.res_w ? a.res_bias[c] : 0.f;
-                pt[128 + lane] = (a.cond && !a.t_dev) ? a.cond[(size_t)a.t_uniform * a.CO + c] : 0.f;
-                __syncwarp();
-                if (lane == 0) mbar_arrive_local(acc_full0 + 8 * stage);  // release: the rows are visible to whoever sees the phase complete
-            }
+        for (int item = blockIdx.x; item < n_items && pre < NS; item += gridDim.x)
+            for (int gi = 0; gi < n_groups && pre < NS; ++gi, ++pre) produce(pre, item, gi, false, true);
+        // the ring is bounded by its own empty barriers only: operands run as far ahead of the MMAs as the stages allow
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x)
             for (int gi = 0; gi < n_groups; ++gi, ++i) {
-                if (i < TC_PS_STAGES) continue;  // issued above
-                mbar_wait(empty0 + 8 * (i % TC_PS_STAGES), ((uint32_t)(i / TC_PS_STAGES) & 1u) ^ 1u);
+                if (i < NS) continue;  // issued above
+                mbar_wait(empty0 + 8 * (i % NS), ((uint32_t)(i / NS) & 1u) ^ 1u);
                 __syncwarp();
                 produce(i, item, gi, true, true);
             }
-        }
     } else if (warp > TC_THREADS / 32) {
         // ===== two MMA-issue warps =====
         const int which = __shfl_sync(0xffffffffu, warp, 0) - (TC_THREADS / 32 + 1);
@@ -202,6 +192,19 @@ __global__ void __launch_bounds__(TCL_THREADS, 1) conv5_tc_kernel(const __grid_c
         const uint32_t b_lo_fixed = (((p1 ? 1u : 2u) * TC_NT * 16u) >> 4) << 16;
         constexpr uint32_t kstep_a = (2 * TC_RT * 16) >> 4;
         const uint32_t kstep_b = ((p1 ? 1u : 2u) * (2 * TC_NT * 16)) >> 4, tap_b = ((p1 ? 1u : 2u) * TC_B_TAP_BYTES) >> 4;
+        // issuer 1 also keeps the epilogue's parameter table filled: the rows of the NEXT item are fetched into registers right
+        // after this item's MMAs were issued (the loads fly while the warp waits on barriers) and written to the table slot
+        // once the slot's previous reader has released it (the same acc_empty wait the MMAs need anyway)
+        float prm[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+        auto fetch_params = [&](int item) {
+            const int c = (item % NC) * TC_NT + lane;
+            prm[0] = a.bias ? a.bias[c] : 0.f;
+            prm[1] = (MODE == TCM_CONV5 && a.gamma) ? a.gamma[c] : 0.f;
+            prm[2] = (MODE == TCM_CONV5 && a.beta) ? a.beta[c] : 0.f;
+            prm[3] = a.res_w ? a.res_bias[c] : 0.f;
+            prm[4] = (a.cond && !a.t_dev) ? a.cond[(size_t)a.t_uniform * a.CO + c] : 0.f;
+        };
+        if (which == 1 && (int)blockIdx.x < n_items) fetch_params(blockIdx.x);
         int i = 0, k = 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++k) {
             const int stage = k & 1;
@@ -209,20 +212,27 @@ __global__ void __launch_bounds__(TCL_THREADS, 1) conv5_tc_kernel(const __grid_c
             // the epilogue of the item that used this stage two items ago has emptied it (the first use of a stage passes)
             mbar_wait(acc_empty0 + 8 * stage, (((uint32_t)k >> 1) & 1u) ^ 1u);
             tc_fence_after();
+            if (which == 1) {
+                float* pt = ptab + stage * 160;
+#pragma unroll
+                for (int j = 0; j < 5; ++j) pt[32 * j + lane] = prm[j];
+                __syncwarp();
+                if (lane == 0) mbar_arrive_local(acc_full0 + 8 * stage);  // release: the rows are visible to whoever sees the phase complete
+            }
             uint32_t acc0 = 0u, acc1 = 0u;
             for (int gi = 0; gi < n_groups; ++gi, ++i) {
-                const int s = i % TC_PS_STAGES;
-                const uint32_t st = stages_u32 + (uint32_t)s * TC_PS_STAGE_BYTES;
+                const int s = i % NS;
+                const uint32_t st = stages_u32 + (uint32_t)s * STAGE_BYTES;
                 int src, c_src, nch, c_conv;
                 group_geom(gi, src, c_src, nch, c_conv);
                 const bool is_res = src >= 2;
                 // the box lands as [plane][k-group][row][8]: the lo plane starts after the box's chunks of the hi plane
                 const uint32_t plane_off = (which == 1 && !p1) ? (uint32_t)a.tm_nch[src] * TC_A_PLANE_BYTES : 0u;
-                mbar_wait(full0 + 8 * s, (uint32_t)(i / TC_PS_STAGES) & 1u);
+                mbar_wait(full0 + 8 * s, (uint32_t)(i / NS) & 1u);
                 tc_fence_after();
                 for (int u = 0; u < nch; ++u) {
                     const uint32_t a_lo = (((st + plane_off + (uint32_t)u * TC_A_PLANE_BYTES) >> 4) & 0x3FFFu) | a_lo_fixed;
-                    const uint32_t wst = st + TC_PS_ACT_BYTES + (uint32_t)u * (uint32_t)(is_res ? 1 : NTAPS) * (p1 ? 1u : 2u) * TC_B_TAP_BYTES;
+                    const uint32_t wst = st + ACT_BYTES + (uint32_t)u * (uint32_t)(is_res ? 1 : NTAPS) * (p1 ? 1u : 2u) * TC_B_TAP_BYTES;
                     const uint32_t b_lo = ((wst >> 4) & 0x3FFFu) | b_lo_fixed;
                     if (is_res) {  // fused 1x1 residual conv: centre row (+2), second accumulator
 #pragma unroll
@@ -251,6 +261,7 @@ __global__ void __launch_bounds__(TCL_THREADS, 1) conv5_tc_kernel(const __grid_c
                 tc_commit_elect(empty0 + 8 * s);  // frees the stage when both issuers' MMAs that read it have retired
             }
             tc_commit_elect(acc_full0 + 8 * stage);  // accumulators of this item complete
+            if (which == 1 && item + (int)gridDim.x < n_items) fetch_params(item + (int)gridDim.x);
         }
         // main loop over: let the next kernel start its prologue (barriers, TMEM, weight prefetch) under our last epilogues
         if (which == 0 && lane == 0) pdl_launch_dependents();
@@ -662,7 +673,9 @@ int launch_rtb_tc(const TcRtbArgs& a, cudaStream_t stream) {
     return 0;
 }
 
-int launch_conv5_tc(const TcConvArgs& a, cudaStream_t stream) {
+int launch_conv5_tc(const TcConvArgs& a_in, cudaStream_t stream) {
+    const TcConvArgs& a0_ = a_in;
+#define a a0_
     MPDB_REQUIRE(a.CO % TC_NT == 0, "tc conv: C_out must be a multiple of 32");
     MPDB_REQUIRE(a.c0 % TC_KCH == 0 && a.c1 % TC_KCH == 0 && a.c0 > 0, "tc conv: input widths must be multiples of 32");
     MPDB_REQUIRE(!a.res_w || (a.rc0 % TC_KCH == 0 && a.rc1 % TC_KCH == 0 && a.rc0 > 0), "tc conv: residual widths");
@@ -675,7 +688,23 @@ int launch_conv5_tc(const TcConvArgs& a, cudaStream_t stream) {
         MPDB_REQUIRE(!a.res_w && !a.res_cm && !a.cond && !a.raw_out, "tc down/up: no residual / conditioning");
     const int SPT = TC_RT / (a.L + 4);
     MPDB_REQUIRE(SPT <= 12, "tc conv: too many samples per tile");
-    const size_t smem = (size_t)TC_PS_STAGES * TC_PS_STAGE_BYTES + (2 * TC_PS_STAGES + 4) * 8 + 16 + TC_GN_SCRATCH_BYTES + 2 * 160 * sizeof(float) + 64;
+#undef a
+    const size_t smem = (size_t)TC_PS_RING_BYTES + (2 * TC_PS_MAX_STAGES + 4) * 8 + 16 + TC_GN_SCRATCH_BYTES + 2 * 160 * sizeof(float) + 64;
+    TcConvArgs a = a_in;
+    {   // ring geometry: a stage = the largest activation box + the largest weight group of this layer
+        const int wmul = a.prec == 1 ? 1 : 2, ntaps = a.mode == TCM_DOWN ? 3 : a.mode == TCM_UP ? 4 : 5;
+        int max_nch = 1;
+        for (int i = 0; i < 4; ++i) {
+            const int Ci = i == 0 ? a.c0 : i == 1 ? a.c1 : i == 2 ? (a.res_w ? a.rc0 : 0) : (a.res_w ? a.rc1 : 0);
+            if (Ci > 0 && a.tm_nch[i] > max_nch) max_nch = a.tm_nch[i];
+        }
+        a.ps_act_bytes = max_nch * wmul * TC_A_PLANE_BYTES;
+        a.ps_stage_bytes = a.ps_act_bytes + max_nch * wmul * ntaps * TC_B_TAP_BYTES;
+        a.ps_stage_bytes = (a.ps_stage_bytes + 127) / 128 * 128;
+        a.ps_stages = TC_PS_RING_BYTES / a.ps_stage_bytes;
+        if (a.ps_stages > TC_PS_MAX_STAGES) a.ps_stages = TC_PS_MAX_STAGES;
+        MPDB_REQUIRE(a.ps_stages >= 2, "tc conv: operand ring too small for this layer");
+    }
     for (int i = 0; i < 4; ++i) {
         const int Ci = i == 0 ? a.c0 : i == 1 ? a.c1 : i == 2 ? (a.res_w ? a.rc0 : 0) : (a.res_w ? a.rc1 : 0);
         MPDB_REQUIRE(Ci == 0 || (a.tm_nch[i] >= 1 && a.tm_nch[i] <= (a.prec == 1 ? 4 : 2)), "tc conv: missing / oversized activation tensor map");
@@ -693,7 +722,7 @@ int launch_conv5_tc(const TcConvArgs& a, cudaStream_t stream) {
         static unsigned long long configured = 0ull;                                                                            \
         if (mpdb::first_use_on_device(configured)) {                                                                                         \
             MPDB_CHECK_CUDA(cudaFuncSetAttribute(conv5_tc_kernel<M, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                                 220 * 1024));                                                     \
+                                                 227 * 1024));                                                     \
         }                                                                                                          \
         MPDB_CHECK_CUDA(launch_kernel(conv5_tc_kernel<M, G>, grid, dim3(TCL_THREADS), smem, stream, a));            \
     }
