@@ -143,7 +143,7 @@ int mpdb_engine_set_schedule(mpdb_engine* e, const float* sqrt_recip_alphas_cump
  * any batch; "fuse_final" = 1 (default: final_conv.1 + DDPM update in the cluster kernel's last epilogue inside the loop);
  * "fuse_guide" = 1 (default: the n_guide_steps evaluations of a loop step in one launch when the batch is co-resident — the
  * trajectory stays in shared memory, the batch-global clip flag is resolved per CTA, bit-identical to one launch per
- * evaluation; 0: one launch per evaluation); "prec1_amp_limit" (default 0.11; 0 disables): loop steps whose eps-to-mean
+ * evaluation; 0: one launch per evaluation); "prec1_amp_limit" (default 0.21; 0 disables): loop steps whose eps-to-mean
  * amplification posterior_mean_coef1[t] * sqrt(1/abar_t - 1) is at most this issue one fp16 product per MMA step instead of
  * the three of the 22-bit split ("tc_mode" = 2 always uses the split);
  * "fuse_rtb" = 1 (default: the per-layer path runs a residual block with C_out <= 128 as one cluster-fused launch while its

@@ -209,8 +209,10 @@ __device__ __forceinline__ void tc_load_acc(uint32_t t, bool p1, float (&v)[8]) 
 }
 
 // Stores 8 consecutive output channels [c8, c8+8) of sample b at output position lo in the fp32 CM layout and (split
-// into fp16 hi / scaled lo) in the TC layout of an activation with CO channels and L_out positions.
-__device__ __forceinline__ void tc_store_row(const TcConvArgs& a, const float (&v)[8], int b, int lo, int c8, int L_out) {
+// into fp16 hi / scaled lo) in the TC layout of an activation with CO channels and L_out positions. (to, so) = the output's
+// (row tile, sample slot within the tile) = (b / SPTo, b % SPTo) with SPTo = TC_RT / (L_out + 4): given by the caller, which
+// knows them without a division when the layer keeps the length (the epilogue is instruction-issue bound).
+__device__ __forceinline__ void tc_store_row_at(const TcConvArgs& a, const float (&v)[8], int b, int to, int so, int lo, int c8, int L_out) {
     const int Lpo = L_out + 4;
     if (a.out_cm != nullptr) {
         float* op = a.out_cm + ((size_t)b * a.CO + c8) * Lpo + 2 + lo;
@@ -218,20 +220,21 @@ __device__ __forceinline__ void tc_store_row(const TcConvArgs& a, const float (&
         for (int j = 0; j < 8; ++j) op[(size_t)j * Lpo] = v[j];
     }
     if (a.out_hi != nullptr) {
-        const int SPTo = TC_RT / Lpo;
-        const int to = b / SPTo, so = b - to * SPTo;
         const size_t o = (((size_t)to * (a.CO / 8) + c8 / 8) * TC_RT + (so * Lpo + lo + 2)) * 8;
-        unsigned short h[8], lo8[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) split_hl(v[e], h[e], lo8[e]);
-        uint4 ph, pl;
-        ph.x = h[0] | ((uint32_t)h[1] << 16); ph.y = h[2] | ((uint32_t)h[3] << 16);
-        ph.z = h[4] | ((uint32_t)h[5] << 16); ph.w = h[6] | ((uint32_t)h[7] << 16);
-        pl.x = lo8[0] | ((uint32_t)lo8[1] << 16); pl.y = lo8[2] | ((uint32_t)lo8[3] << 16);
-        pl.z = lo8[4] | ((uint32_t)lo8[5] << 16); pl.w = lo8[6] | ((uint32_t)lo8[7] << 16);
-        *reinterpret_cast<uint4*>(a.out_hi + o) = ph;
-        if (a.prec != 1) *reinterpret_cast<uint4*>(a.out_lo + o) = pl;  // precision 1 reads the hi plane only
+        if (a.prec == 1) {  // precision 1 reads the hi plane only
+            *reinterpret_cast<uint4*>(a.out_hi + o) = pack_hi8(v);
+        } else {
+            uint4 ph, pl;
+            pack_split8(v, ph, pl);  // same values as split_hl, two conversions per instruction
+            *reinterpret_cast<uint4*>(a.out_hi + o) = ph;
+            *reinterpret_cast<uint4*>(a.out_lo + o) = pl;
+        }
     }
+}
+__device__ __forceinline__ void tc_store_row(const TcConvArgs& a, const float (&v)[8], int b, int lo, int c8, int L_out) {
+    const int SPTo = TC_RT / (L_out + 4);
+    const int to = b / SPTo;
+    tc_store_row_at(a, v, b, to, b - to * SPTo, lo, c8, L_out);
 }
 
 // One-pass GroupNorm statistics + Mish on the 8 channels a thread owns (both tensor-core epilogues).
@@ -287,8 +290,16 @@ __device__ __forceinline__ void gn_mish8(float (&v)[8], bool valid, int r, int s
         const bool on = ss < SPT;
         double a0 = 0.0;
         if (on) {
+            // eight independent loads per round, then a fixed pairwise tree in double: a dependent load -> convert -> add chain
+            // per row group was ~50 cycles per term on the path between the two barriers
             const float* p = (m ? part2 : part) + (size_t)ss * (Lp >> 2) * 8 + blk;
-            for (int g = j; g < (L >> 2); g += JS) a0 += (double)p[g * 8];
+            const int n = L >> 2;
+            for (int g0 = j; g0 < n; g0 += 8 * JS) {
+                float f[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) f[u] = (g0 + u * JS < n) ? p[(g0 + u * JS) * 8] : 0.f;
+                a0 += (((double)f[0] + (double)f[1]) + ((double)f[2] + (double)f[3])) + (((double)f[4] + (double)f[5]) + ((double)f[6] + (double)f[7]));
+            }
         }
 #pragma unroll
         for (int o = 1; o < JS; o <<= 1) a0 += __shfl_xor_sync(0xffffffffu, a0, o);

@@ -76,11 +76,11 @@ __global__ void __launch_bounds__(TCL_THREADS, 1) conv5_tc_kernel(const __grid_c
     unsigned char* stages = smem_raw;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + TC_PS_RING_BYTES);  // full[8], empty[8], acc_full[2], acc_empty[2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_PS_MAX_STAGES + 4);
-    float* part = reinterpret_cast<float*>(tmem_slot + 4);  // GroupNorm scratch
+    float* part = reinterpret_cast<float*>(tmem_slot + 4);  // GroupNorm scratch, one copy per item parity (see the epilogue loop)
     // per-item epilogue parameters of the item's 32 output channels {bias, gamma, beta, residual bias, time-conditioning row at
     // uniform t}, double-buffered like the accumulators and filled by the producer warp one item ahead: in the item loop the
     // epilogue warps would otherwise pay a global-memory round trip per item with nothing to hide it behind
-    float* ptab = part + (TC_GN_SCRATCH_BYTES / (int)sizeof(float));  // [2][5][32]
+    float* ptab = part + 2 * (TC_GN_SCRATCH_BYTES / (int)sizeof(float));  // [2][5][32]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const bool dbg = a.dbg != nullptr && blockIdx.x == 0;
@@ -278,8 +278,13 @@ __global__ void __launch_bounds__(TCL_THREADS, 1) conv5_tc_kernel(const __grid_c
         const bool full = a.raw_out == nullptr;
         const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
         float rid_next[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        if (full && MODE == TCM_CONV5 && a.res_w == nullptr && a.res_cm != nullptr && (int)blockIdx.x < n_items) {
-            const int tile0 = blockIdx.x / NC, ntile0 = blockIdx.x - tile0 * NC, b0 = tile0 * SPT + s;
+        // (row tile, channel chunk) of the CTA's items without a division per item: item += gridDim.x moves them by (gq, gr)
+        const int gq = (int)gridDim.x / NC, gr = (int)gridDim.x - gq * NC;
+        int tile = (int)blockIdx.x / NC, ntile = (int)blockIdx.x - tile * NC;
+        const bool row_ok = (s < SPT) && (l < a.L);
+        const bool has_rid = full && MODE == TCM_CONV5 && a.res_w == nullptr && a.res_cm != nullptr;
+        if (has_rid && (int)blockIdx.x < n_items) {
+            const int tile0 = tile, ntile0 = ntile, b0 = tile0 * SPT + s;
             if ((s < SPT) && (l < a.L) && (b0 < a.B)) {
                 const float* rp = a.res_cm + ((size_t)b0 * a.CO + ntile0 * TC_NT + cg * 8) * Lp + 2 + l;
 #pragma unroll
@@ -288,10 +293,9 @@ __global__ void __launch_bounds__(TCL_THREADS, 1) conv5_tc_kernel(const __grid_c
         }
         int k = 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++k) {
-            const int tile = item / NC, ntile = item - tile * NC;
             const int stage = k & 1;
             const int b = tile * SPT + s;
-            const bool valid = (s < SPT) && (l < a.L) && (b < a.B);
+            const bool valid = row_ok && (b < a.B);
             const int c8 = ntile * TC_NT + cg * 8;  // first of this thread's 8 output channels
             float4 pc0 = z4, pc1 = z4;
             if (full && a.cond != nullptr && a.t_dev != nullptr && valid) {  // per-sample t (per-call entry points): the row depends on the sample
@@ -323,14 +327,15 @@ __global__ void __launch_bounds__(TCL_THREADS, 1) conv5_tc_kernel(const __grid_c
             __syncwarp();
             if (lane == 0) mbar_arrive_local(acc_empty0 + 8 * stage);
             // identity residual of the NEXT item of this CTA
-            if (full && MODE == TCM_CONV5 && a.res_w == nullptr && a.res_cm != nullptr) {
+            int tile_n = tile + gq, ntile_n = ntile + gr;
+            if (ntile_n >= NC) { ntile_n -= NC; ++tile_n; }
+            if (has_rid) {
                 const int item_n = item + (int)gridDim.x;
 #pragma unroll
                 for (int j = 0; j < 8; ++j) rid_next[j] = 0.f;
                 if (item_n < n_items) {
-                    const int tile_n = item_n / NC, ntile_n = item_n - tile_n * NC;
                     const int b_n = tile_n * SPT + s;
-                    if ((s < SPT) && (l < a.L) && (b_n < a.B)) {
+                    if (row_ok && (b_n < a.B)) {
                         const float* rp = a.res_cm + ((size_t)b_n * a.CO + ntile_n * TC_NT + cg * 8) * Lp + 2 + l;
 #pragma unroll
                         for (int j = 0; j < 8; ++j) rid_next[j] = rp[(size_t)j * Lp];
@@ -361,7 +366,10 @@ __global__ void __launch_bounds__(TCL_THREADS, 1) conv5_tc_kernel(const __grid_c
             } else {
                 v[0] += pb0.x; v[1] += pb0.y; v[2] += pb0.z; v[3] += pb0.w;
                 v[4] += pb1.x; v[5] += pb1.y; v[6] += pb1.z; v[7] += pb1.w;
-                gn_mish8<GS, true>(v, valid, r, s, cg, tid, SPT, Lp, a.L, part, pg0, pg1, pe0, pe1, (dbg && tid == 64 && k == 0) ? a.dbg : nullptr);
+                // scratch of parity k & 1: the partial sums of item k + 2 are written after every thread has passed the two
+                // barriers of item k + 1, i.e. after its last read of item k's statistics (no barrier at the end of an item)
+                gn_mish8<GS, true>(v, valid, r, s, cg, tid, SPT, Lp, a.L, part + stage * (TC_GN_SCRATCH_BYTES / (int)sizeof(float)), pg0, pg1, pe0, pe1,
+                                   (dbg && tid == 64 && k == 0) ? a.dbg : nullptr);
                 if (dbg && tid == 64 && k == 0) a.dbg[6] = clock64();  // GroupNorm + Mish done
                 // time conditioning (zero when absent), then the residual: fused 1x1 conv accumulator or identity values
                 v[0] += pc0.x; v[1] += pc0.y; v[2] += pc0.z; v[3] += pc0.w;
@@ -373,11 +381,9 @@ __global__ void __launch_bounds__(TCL_THREADS, 1) conv5_tc_kernel(const __grid_c
 #pragma unroll
                     for (int j = 0; j < 8; ++j) v[j] += rid[j];
                 }
-                if (valid) tc_store_row(a, v, b, l, c8, a.L);
-                // gn_mish8's scratch is reused by the next item: everyone is past its last read (the statistics) before anyone
-                // writes the next item's partial sums
-                epi_sync();
+                if (valid) tc_store_row_at(a, v, b, tile, s, l, c8, a.L);  // same length: same (row tile, slot) as the input
             }
+            tile = tile_n; ntile = ntile_n;
         }
         tc_fence_before();
     }
@@ -689,7 +695,8 @@ int launch_conv5_tc(const TcConvArgs& a_in, cudaStream_t stream) {
     const int SPT = TC_RT / (a.L + 4);
     MPDB_REQUIRE(SPT <= 12, "tc conv: too many samples per tile");
 #undef a
-    const size_t smem = (size_t)TC_PS_RING_BYTES + (2 * TC_PS_MAX_STAGES + 4) * 8 + 16 + TC_GN_SCRATCH_BYTES + 2 * 160 * sizeof(float) + 64;
+    const size_t smem = (size_t)TC_PS_RING_BYTES + (2 * TC_PS_MAX_STAGES + 4) * 8 + 16 + 2 * TC_GN_SCRATCH_BYTES + 2 * 160 * sizeof(float) + 64;
+    static_assert((size_t)TC_PS_RING_BYTES + (2 * TC_PS_MAX_STAGES + 4) * 8 + 16 + 2 * TC_GN_SCRATCH_BYTES + 2 * 160 * sizeof(float) + 64 <= 227 * 1024, "conv5_tc_kernel: shared memory");
     TcConvArgs a = a_in;
     {   // ring geometry: a stage = the largest activation box + the largest weight group of this layer
         const int wmul = a.prec == 1 ? 1 : 2, ntaps = a.mode == TCM_DOWN ? 3 : a.mode == TCM_UP ? 4 : 5;

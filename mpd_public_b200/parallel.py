@@ -42,7 +42,13 @@ def sample_sharded(sample_local, n_total: int, noise=None, gather=True, group=No
     """Runs `sample_local(n_local, noise_local)` on this rank's slice and gathers the plans.
 
     `noise` (optional, parity mode): the GLOBAL injected noise [S, n_total, H, D]; each rank takes its batch
-    slice, so the gathered result equals the single-process run shard by shard.
+    slice, so the gathered result equals the single-process run shard by shard — with ONE caveat: the guide
+    reproduces `LimitsNormalizer.unnormalize`'s batch-global clip (normalization.py:156-167: if ANY element of
+    the batch leaves [-1, 1] the whole batch is clamped) through one device flag per launch, and each rank's
+    flag sees only its own shard. A shard with no out-of-range value therefore does not clamp where the
+    single-process batch would have (and vice versa the result of the reference itself depends on which
+    trajectories share a batch). Unguided sampling has no such coupling and is shard-invariant bit for bit;
+    tests/test_gpu_parity.py (shard invariance, guided) counts the batch-dependent clamps of the run it compares.
     """
     if dist.is_available() and dist.is_initialized():
         world, rank = dist.get_world_size(group), dist.get_rank(group)

@@ -8,7 +8,8 @@ import sys
 
 rep = sys.argv[1]
 top_n = int(sys.argv[2]) if len(sys.argv) > 2 else 40
-raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"], capture_output=True, text=True).stdout
+sel = ["--launch-skip", sys.argv[3], "--launch-count", "1"] if len(sys.argv) > 3 else []  # one launch of the report (0-based)
+raw = subprocess.run(["ncu", "-i", rep, *sel, "--page", "source", "--csv", "--print-source", "cuda,sass"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
 cur, hdr, res, nk, kname = None, None, {}, 0, None
 stalls = {}
@@ -43,7 +44,7 @@ for r in rows:
         except (ValueError, IndexError):
             pass
 tot = sum(v[0] for v in res.values())
-print(f"kernel: {kname} (all captured launches of the report together)\ntotal warp-stall samples: {tot}")
+print(f"kernel: {kname} ({"launch " + sys.argv[3] if sel else "all captured launches"} of the report)\ntotal warp-stall samples: {tot}")
 print("stall reasons:", ", ".join(f"{k[6:]} {100 * v / max(tot, 1):.1f}%" for k, v in sorted(stalls.items(), key=lambda x: -x[1]) if v))
 print(f"{'samples':>8} {'share':>6}  {'warp-instrs':>11}  location")
 for (f, l), (s, src, n) in sorted(res.items(), key=lambda x: -x[1][0])[:top_n]:
