@@ -249,107 +249,108 @@ __device__ __forceinline__ void tc_store_row(const TcConvArgs& a, const float (&
 // rounding of the 16-term row-group partials (~6e-8 * (1 + mean^2/var)), far below the fp16-split MMA error. Three short
 // barriers, no redundant fp64 work. Deterministic and independent of how samples are tiled. BAR1: named barrier of the 512 epilogue
 // threads (fused kernel, where a producer warp is not part of the epilogue) instead of __syncthreads.
-template <int GS, bool BAR1>
-__device__ __forceinline__ void gn_mish8(float (&v)[8], bool valid, int r, int s, int cg, int tid, int SPT, int Lp, int L,
-                                         float* part, const float4& g0, const float4& g1, const float4& e0, const float4& e1,
-                                         long long* dbg = nullptr) {
+// The pieces (the persistent per-layer kernel software-pipelines them across work items, unet_tc.cu):
+// level 0: per-thread partials of the two 4-channel blocks, then the 4 rows of an aligned row group are added by two
+// xor-shuffles (rows = lanes; samples start at multiples of 4 rows, so groups never straddle samples and the tree is the
+// same wherever the sample sits in the tile)
+__device__ __forceinline__ void gn_level0(const float (&v)[8], bool valid, int r, int cg, float* part) {
+    float* part2 = part + TC_GN_PART;
+    float sA = (v[0] + v[1]) + (v[2] + v[3]), sB = (v[4] + v[5]) + (v[6] + v[7]);
+    float qA = fmaf(v[0], v[0], fmaf(v[1], v[1], fmaf(v[2], v[2], v[3] * v[3])));
+    float qB = fmaf(v[4], v[4], fmaf(v[5], v[5], fmaf(v[6], v[6], v[7] * v[7])));
+    if (!valid) { sA = 0.f; sB = 0.f; qA = 0.f; qB = 0.f; }
+#pragma unroll
+    for (int o = 1; o <= 2; o <<= 1) {
+        sA += __shfl_xor_sync(0xffffffffu, sA, o); sB += __shfl_xor_sync(0xffffffffu, sB, o);
+        qA += __shfl_xor_sync(0xffffffffu, qA, o); qB += __shfl_xor_sync(0xffffffffu, qB, o);
+    }
+    if ((r & 3) == 0) {
+        part[(r >> 2) * 8 + cg * 2 + 0] = sA;
+        part[(r >> 2) * 8 + cg * 2 + 1] = sB;
+        part2[(r >> 2) * 8 + cg * 2 + 0] = qA;
+        part2[(r >> 2) * 8 + cg * 2 + 1] = qB;
+    }
+}
+// levels 1 + 2 with at most 8 samples per tile, in one pass with no shared-memory round trip in between: JS threads per
+// (sample, block, moment) column add the sample's L/4 row-group sums in double (thread j takes groups j, j+JS, ...); fixed
+// xor-shuffle trees then combine the JS partial sums, bring the two moments together and add the BPG blocks of a GroupNorm
+// group (lane bits, low to high: j | moment | block), and one lane per (sample, group) publishes {mean, rstd}. Every thread
+// of the 16 warps calls it (whole warps take part in the shuffles).
+template <int GS>
+__device__ __forceinline__ void gn_stats_small(int tid, int SPT, int Lp, int L, float* part) {
     constexpr int BPG = GS / 4;
     float* part2 = part + TC_GN_PART;
     double* cs = reinterpret_cast<double*>(part + 2 * TC_GN_PART);  // [2][12][8]
-    {
-        // level 0: per-thread partials of the two 4-channel blocks, then the 4 rows of an aligned row group are added by
-        // two xor-shuffles (rows = lanes; samples start at multiples of 4 rows, so groups never straddle samples and the
-        // tree is the same wherever the sample sits in the tile)
-        float sA = (v[0] + v[1]) + (v[2] + v[3]), sB = (v[4] + v[5]) + (v[6] + v[7]);
-        float qA = fmaf(v[0], v[0], fmaf(v[1], v[1], fmaf(v[2], v[2], v[3] * v[3])));
-        float qB = fmaf(v[4], v[4], fmaf(v[5], v[5], fmaf(v[6], v[6], v[7] * v[7])));
-        if (!valid) { sA = 0.f; sB = 0.f; qA = 0.f; qB = 0.f; }
-#pragma unroll
-        for (int o = 1; o <= 2; o <<= 1) {
-            sA += __shfl_xor_sync(0xffffffffu, sA, o); sB += __shfl_xor_sync(0xffffffffu, sB, o);
-            qA += __shfl_xor_sync(0xffffffffu, qA, o); qB += __shfl_xor_sync(0xffffffffu, qB, o);
-        }
-        if ((r & 3) == 0) {
-            part[(r >> 2) * 8 + cg * 2 + 0] = sA;
-            part[(r >> 2) * 8 + cg * 2 + 1] = sB;
-            part2[(r >> 2) * 8 + cg * 2 + 0] = qA;
-            part2[(r >> 2) * 8 + cg * 2 + 1] = qB;
-        }
+    float* stat = reinterpret_cast<float*>(cs + 2 * 12 * 8);         // [12][8][2]
+    constexpr int JS = BPG == 8 ? 2 : 4;
+    const int j = tid % JS, m = (tid / JS) & 1, blk = (tid / (2 * JS)) & 7, ss = tid / (16 * JS);
+    const bool on = ss < SPT;
+    double a0 = 0.0;
+    if (on) {
+        // (eight independent loads + a pairwise tree per round was tried: slower — the fp32 -> fp64 conversions and double adds of
+        // the padding terms cost more than the dependent chain, 178 -> 180 us per forward of the cluster kernel)
+        const float* p = (m ? part2 : part) + (size_t)ss * (Lp >> 2) * 8 + blk;
+        for (int g = j; g < (L >> 2); g += JS) a0 += (double)p[g * 8];
     }
-    if (BAR1) asm volatile("bar.sync 1, %0;" ::"n"(TC_THREADS) : "memory"); else __syncthreads();
-    if (dbg) dbg[8] = clock64();
-    constexpr int NG = TC_NT / GS;
-    float* stat = reinterpret_cast<float*>(cs + 2 * 12 * 8);  // [12][8][2]
-    if (SPT <= 8) {
-        // levels 1 + 2 in one pass, no shared-memory round trip in between: JS threads per (sample, block, moment) column
-        // add the sample's L/4 row-group sums in double (thread j takes groups j, j+JS, ...); fixed xor-shuffle trees then
-        // combine the JS partial sums, bring the two moments together and add the BPG blocks of a GroupNorm group
-        // (lane bits, low to high: j | moment | block), and one lane per (sample, group) publishes {mean, rstd}.
-        constexpr int JS = BPG == 8 ? 2 : 4;
-        const int j = tid % JS, m = (tid / JS) & 1, blk = (tid / (2 * JS)) & 7, ss = tid / (16 * JS);
-        const bool on = ss < SPT;
-        double a0 = 0.0;
-        if (on) {
-            // eight independent loads per round, then a fixed pairwise tree in double: a dependent load -> convert -> add chain
-            // per row group was ~50 cycles per term on the path between the two barriers
-            const float* p = (m ? part2 : part) + (size_t)ss * (Lp >> 2) * 8 + blk;
-            const int n = L >> 2;
-            for (int g0 = j; g0 < n; g0 += 8 * JS) {
-                float f[8];
 #pragma unroll
-                for (int u = 0; u < 8; ++u) f[u] = (g0 + u * JS < n) ? p[(g0 + u * JS) * 8] : 0.f;
-                a0 += (((double)f[0] + (double)f[1]) + ((double)f[2] + (double)f[3])) + (((double)f[4] + (double)f[5]) + ((double)f[6] + (double)f[7]));
-            }
-        }
+    for (int o = 1; o < JS; o <<= 1) a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+    const double other = __shfl_xor_sync(0xffffffffu, a0, JS);  // the other moment of the same (sample, block)
+    double S = m ? other : a0, Q = m ? a0 : other;
 #pragma unroll
-        for (int o = 1; o < JS; o <<= 1) a0 += __shfl_xor_sync(0xffffffffu, a0, o);
-        const double other = __shfl_xor_sync(0xffffffffu, a0, JS);  // the other moment of the same (sample, block)
-        double S = m ? other : a0, Q = m ? a0 : other;
-#pragma unroll
-        for (int o = 1; o < BPG; o <<= 1) {
-            S += __shfl_xor_sync(0xffffffffu, S, o * 2 * JS);
-            Q += __shfl_xor_sync(0xffffffffu, Q, o * 2 * JS);
-        }
-        if (on && j == 0 && m == 0 && (blk % BPG) == 0) {
-            const int g = blk / BPG;
-            const double inv_n = (double)(1.0f / (float)(GS * L));  // L = 8 * 2^k, GS = 2^j: exact, and no fp64 division
-            const double mean = S * inv_n;
-            const double var = fmax(Q * inv_n - mean * mean, 0.0);
-            stat[(ss * 8 + g) * 2 + 0] = (float)mean;
-            stat[(ss * 8 + g) * 2 + 1] = 1.0f / sqrtf((float)var + 1e-5f);  // the cancellation-prone part is done; fp32 from here
-        }
-        if (dbg) dbg[9] = clock64();
-    } else {
-        if (tid < 2 * SPT * 8) {
-            // level 1 (more than 8 samples per tile): one thread per (moment, sample, block) column
-            const int m = tid >= SPT * 8 ? 1 : 0;
-            const int t2 = tid - m * SPT * 8;
-            const int ss = t2 >> 3, blk = t2 & 7;
-            const float* p = (m ? part2 : part) + (size_t)ss * (Lp >> 2) * 8 + blk;
-            double a0 = 0.0, a1 = 0.0;
+    for (int o = 1; o < BPG; o <<= 1) {
+        S += __shfl_xor_sync(0xffffffffu, S, o * 2 * JS);
+        Q += __shfl_xor_sync(0xffffffffu, Q, o * 2 * JS);
+    }
+    if (on && j == 0 && m == 0 && (blk % BPG) == 0) {
+        const int g = blk / BPG;
+        const double inv_n = (double)(1.0f / (float)(GS * L));  // L = 8 * 2^k, GS = 2^j: exact, and no fp64 division
+        const double mean = S * inv_n;
+        const double var = fmax(Q * inv_n - mean * mean, 0.0);
+        stat[(ss * 8 + g) * 2 + 0] = (float)mean;
+        stat[(ss * 8 + g) * 2 + 1] = 1.0f / sqrtf((float)var + 1e-5f);  // the cancellation-prone part is done; fp32 from here
+    }
+}
+// more than 8 samples per tile: level 1 = one thread per (moment, sample, block) column; a barrier; level 2 = one thread per
+// (sample, group) finishes the statistics in double and publishes {mean, rstd} as floats
+__device__ __forceinline__ void gn_stats_big1(int tid, int SPT, int Lp, int L, float* part) {
+    float* part2 = part + TC_GN_PART;
+    double* cs = reinterpret_cast<double*>(part + 2 * TC_GN_PART);
+    if (tid < 2 * SPT * 8) {
+        const int m = tid >= SPT * 8 ? 1 : 0;
+        const int t2 = tid - m * SPT * 8;
+        const int ss = t2 >> 3, blk = t2 & 7;
+        const float* p = (m ? part2 : part) + (size_t)ss * (Lp >> 2) * 8 + blk;
+        double a0 = 0.0, a1 = 0.0;
 #pragma unroll 4
-            for (int g = 0; g < (L >> 2); g += 2) {
-                a0 += (double)p[(g + 0) * 8];
-                a1 += (double)p[(g + 1) * 8];
-            }
-            cs[(m * 12 + ss) * 8 + blk] = a0 + a1;
+        for (int g = 0; g < (L >> 2); g += 2) {
+            a0 += (double)p[(g + 0) * 8];
+            a1 += (double)p[(g + 1) * 8];
         }
-        if (BAR1) asm volatile("bar.sync 1, %0;" ::"n"(TC_THREADS) : "memory"); else __syncthreads();
-        if (dbg) dbg[9] = clock64();
-        // level 2: one thread per (sample, group) finishes the statistics in double and publishes {mean, rstd} as floats
-        if (tid < SPT * NG) {
-            const int ss = tid / NG, g = tid - ss * NG;
-            double S = 0.0, Q = 0.0;
-#pragma unroll
-            for (int k = 0; k < BPG; ++k) { S += cs[(0 * 12 + ss) * 8 + g * BPG + k]; Q += cs[(1 * 12 + ss) * 8 + g * BPG + k]; }
-            const double inv_n = (double)(1.0f / (float)(GS * L));
-            const double m = S * inv_n;
-            const double var = fmax(Q * inv_n - m * m, 0.0);
-            stat[(ss * 8 + g) * 2 + 0] = (float)m;
-            stat[(ss * 8 + g) * 2 + 1] = 1.0f / sqrtf((float)var + 1e-5f);
-        }
+        cs[(m * 12 + ss) * 8 + blk] = a0 + a1;
     }
-    if (BAR1) asm volatile("bar.sync 1, %0;" ::"n"(TC_THREADS) : "memory"); else __syncthreads();
+}
+template <int GS>
+__device__ __forceinline__ void gn_stats_big2(int tid, int SPT, int L, float* part) {
+    constexpr int BPG = GS / 4, NG = TC_NT / GS;
+    double* cs = reinterpret_cast<double*>(part + 2 * TC_GN_PART);
+    float* stat = reinterpret_cast<float*>(cs + 2 * 12 * 8);
+    if (tid < SPT * NG) {
+        const int ss = tid / NG, g = tid - ss * NG;
+        double S = 0.0, Q = 0.0;
+#pragma unroll
+        for (int k = 0; k < BPG; ++k) { S += cs[(0 * 12 + ss) * 8 + g * BPG + k]; Q += cs[(1 * 12 + ss) * 8 + g * BPG + k]; }
+        const double inv_n = (double)(1.0f / (float)(GS * L));
+        const double m = S * inv_n;
+        const double var = fmax(Q * inv_n - m * m, 0.0);
+        stat[(ss * 8 + g) * 2 + 0] = (float)m;
+        stat[(ss * 8 + g) * 2 + 1] = 1.0f / sqrtf((float)var + 1e-5f);
+    }
+}
+// normalise + affine + Mish with the published statistics
+template <int GS>
+__device__ __forceinline__ void gn_apply(float (&v)[8], bool valid, int s, int cg, int SPT, const float* part, const float4& g0,
+                                         const float4& g1, const float4& e0, const float4& e1) {
+    const float* stat = reinterpret_cast<const float*>(reinterpret_cast<const double*>(part + 2 * TC_GN_PART) + 2 * 12 * 8);
     const int sc = s < SPT ? s : 0;
     const int gA = (cg * 8) / GS, gB = (cg * 8 + 4) / GS;
     const float mA = stat[(sc * 8 + gA) * 2], rA = stat[(sc * 8 + gA) * 2 + 1];
@@ -360,6 +361,26 @@ __device__ __forceinline__ void gn_mish8(float (&v)[8], bool valid, int r, int s
     v[2] = mishf_fast((v[2] - mA) * (rA * g0.z) + e0.z); v[3] = mishf_fast((v[3] - mA) * (rA * g0.w) + e0.w);
     v[4] = mishf_fast((v[4] - mB) * (rB * g1.x) + e1.x); v[5] = mishf_fast((v[5] - mB) * (rB * g1.y) + e1.y);
     v[6] = mishf_fast((v[6] - mB) * (rB * g1.z) + e1.z); v[7] = mishf_fast((v[7] - mB) * (rB * g1.w) + e1.w);
+}
+
+template <int GS, bool BAR1>
+__device__ __forceinline__ void gn_mish8(float (&v)[8], bool valid, int r, int s, int cg, int tid, int SPT, int Lp, int L,
+                                         float* part, const float4& g0, const float4& g1, const float4& e0, const float4& e1,
+                                         long long* dbg = nullptr) {
+    gn_level0(v, valid, r, cg, part);
+    if (BAR1) asm volatile("bar.sync 1, %0;" ::"n"(TC_THREADS) : "memory"); else __syncthreads();
+    if (dbg) dbg[8] = clock64();
+    if (SPT <= 8) {
+        gn_stats_small<GS>(tid, SPT, Lp, L, part);
+        if (dbg) dbg[9] = clock64();
+    } else {
+        gn_stats_big1(tid, SPT, Lp, L, part);
+        if (BAR1) asm volatile("bar.sync 1, %0;" ::"n"(TC_THREADS) : "memory"); else __syncthreads();
+        if (dbg) dbg[9] = clock64();
+        gn_stats_big2<GS>(tid, SPT, L, part);
+    }
+    if (BAR1) asm volatile("bar.sync 1, %0;" ::"n"(TC_THREADS) : "memory"); else __syncthreads();
+    gn_apply<GS>(v, valid, s, cg, SPT, part, g0, g1, e0, e1);
 }
 
 

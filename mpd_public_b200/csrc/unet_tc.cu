@@ -78,9 +78,11 @@ __global__ void __launch_bounds__(TCL_THREADS, 1) conv5_tc_kernel(const __grid_c
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_PS_MAX_STAGES + 4);
     float* part = reinterpret_cast<float*>(tmem_slot + 4);  // GroupNorm scratch, one copy per item parity (see the epilogue loop)
     // per-item epilogue parameters of the item's 32 output channels {bias, gamma, beta, residual bias, time-conditioning row at
-    // uniform t}, double-buffered like the accumulators and filled by the producer warp one item ahead: in the item loop the
-    // epilogue warps would otherwise pay a global-memory round trip per item with nothing to hide it behind
-    float* ptab = part + 2 * (TC_GN_SCRATCH_BYTES / (int)sizeof(float));  // [2][5][32]
+    // uniform t}, filled by issuer warp 1 one item ahead: in the item loop the epilogue warps would otherwise pay a
+    // global-memory round trip per item with nothing to hide it behind. Four slots: the software-pipelined epilogue reads the
+    // rows of item k (gamma, beta, ...) after it has released the accumulator stage of item k + 1; slot k & 3 is rewritten
+    // for item k + 4, after every epilogue warp has released the stage of item k + 2, which it does after finishing item k
+    float* ptab = part + 2 * (TC_GN_SCRATCH_BYTES / (int)sizeof(float));  // [4][5][32]: slot k & 3 for the CTA's k-th item
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const bool dbg = a.dbg != nullptr && blockIdx.x == 0;
@@ -213,7 +215,7 @@ __global__ void __launch_bounds__(TCL_THREADS, 1) conv5_tc_kernel(const __grid_c
             mbar_wait(acc_empty0 + 8 * stage, (((uint32_t)k >> 1) & 1u) ^ 1u);
             tc_fence_after();
             if (which == 1) {
-                float* pt = ptab + stage * 160;
+                float* pt = ptab + (k & 3) * 160;
 #pragma unroll
                 for (int j = 0; j < 5; ++j) pt[32 * j + lane] = prm[j];
                 __syncwarp();
@@ -277,113 +279,155 @@ __global__ void __launch_bounds__(TCL_THREADS, 1) conv5_tc_kernel(const __grid_c
         const int s = r / Lp, l = r - s * Lp;
         const bool full = a.raw_out == nullptr;
         const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        float rid_next[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         // (row tile, channel chunk) of the CTA's items without a division per item: item += gridDim.x moves them by (gq, gr)
         const int gq = (int)gridDim.x / NC, gr = (int)gridDim.x - gq * NC;
         int tile = (int)blockIdx.x / NC, ntile = (int)blockIdx.x - tile * NC;
         const bool row_ok = (s < SPT) && (l < a.L);
-        const bool has_rid = full && MODE == TCM_CONV5 && a.res_w == nullptr && a.res_cm != nullptr;
-        if (has_rid && (int)blockIdx.x < n_items) {
-            const int tile0 = tile, ntile0 = ntile, b0 = tile0 * SPT + s;
-            if ((s < SPT) && (l < a.L) && (b0 < a.B)) {
-                const float* rp = a.res_cm + ((size_t)b0 * a.CO + ntile0 * TC_NT + cg * 8) * Lp + 2 + l;
+        const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + cg * 8;
+        if (MODE == TCM_CONV5 && full) {
+            // ---- Conv1d k5 + GroupNorm + Mish [+ cond] [+ residual], SOFTWARE-PIPELINED over the CTA's items ----
+            // GroupNorm needs two block-wide hand-offs per item (row-group partial sums -> statistics -> everyone). Run item by
+            // item that is three barriers with little work between them and 16 warps that mostly wait (ncu: 30 % of the
+            // stall samples on the barriers, issue slots 35 % busy). Here iteration k does
+            //     X:  statistics of item k (from the partial sums written one iteration earlier)
+            //         + accumulators of item k+1 out of TMEM, bias, partial sums of item k+1          -> ONE barrier
+            //     Y:  normalise + Mish + cond + residual + stores of item k
+            // so a thread always has two independent instruction streams between barriers and an item costs one barrier
+            // (two when a tile holds more than 8 samples). Scratch (partial sums, statistics) alternates with the item parity:
+            // item k+2 writes partial sums after the barrier of iteration k+1, i.e. after the statistics of item k were read
+            // (iteration k, X) — and statistics after the barrier of iteration k+1, i.e. after every thread finished Y of item k.
+            constexpr int SCR = TC_GN_SCRATCH_BYTES / (int)sizeof(float);
+            const bool has_resw = a.res_w != nullptr, has_rid = a.res_w == nullptr && a.res_cm != nullptr;
+            auto load_item = [&](int kk, int tile_, int ntile_, float (&v)[8], float (&z)[8]) {
+                const int st = kk & 1;
+                const int b_ = tile_ * SPT + s;
+                const bool valid_ = row_ok && (b_ < a.B);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) rid_next[j] = rp[(size_t)j * Lp];
+                for (int j = 0; j < 8; ++j) z[j] = 0.f;
+                if (has_rid && valid_) {  // identity residual: requested before the accumulator wait, consumed one barrier later
+                    const float* rp = a.res_cm + ((size_t)b_ * a.CO + ntile_ * TC_NT + cg * 8) * Lp + 2 + l;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) z[j] = rp[(size_t)j * Lp];
+                }
+                mbar_wait(acc_full0 + 8 * st, ((uint32_t)kk >> 1) & 1u);
+                __syncwarp();
+                tc_fence_after();
+                if (dbg && tid == 64 && kk == 0) a.dbg[4] = clock64();  // accumulators ready
+                const uint32_t taddr = taddr0 + (uint32_t)st * TCL_ACC_COLS;
+                tc_load_acc(taddr, p1, v);
+                if (has_resw) tc_load_acc(taddr + 128, p1, z);  // the block's 1x1 residual conv
+                const float* pt = ptab + (kk & 3) * 160 + cg * 8;
+                const float4 pb0 = *reinterpret_cast<const float4*>(pt), pb1 = *reinterpret_cast<const float4*>(pt + 4);
+                // the accumulators are in registers: hand the stage back (the MMAs of the item after next may start)
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_local(acc_empty0 + 8 * st);
+                if (dbg && tid == 64 && kk == 0) a.dbg[5] = clock64();  // TMEM read
+                v[0] += pb0.x; v[1] += pb0.y; v[2] += pb0.z; v[3] += pb0.w;
+                v[4] += pb1.x; v[5] += pb1.y; v[6] += pb1.z; v[7] += pb1.w;
+                if (has_resw) {
+                    const float4 pr0 = *reinterpret_cast<const float4*>(pt + 96), pr1 = *reinterpret_cast<const float4*>(pt + 100);
+                    z[0] += pr0.x; z[1] += pr0.y; z[2] += pr0.z; z[3] += pr0.w;
+                    z[4] += pr1.x; z[5] += pr1.y; z[6] += pr1.z; z[7] += pr1.w;
+                }
+                gn_level0(v, valid_, r, cg, part + st * SCR);
+            };
+            float v0[8], z0[8];  // item k: conv accumulator + bias; residual values (1x1 conv + its bias | identity | zero)
+            if ((int)blockIdx.x < n_items) load_item(0, tile, ntile, v0, z0);
+            epi_sync();
+            int k = 0;
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++k) {
+                float* scr = part + (k & 1) * SCR;
+                const int b = tile * SPT + s;
+                const bool valid = row_ok && (b < a.B);
+                const int c8 = ntile * TC_NT + cg * 8;  // first of this thread's 8 output channels
+                int tile_n = tile + gq, ntile_n = ntile + gr;
+                if (ntile_n >= NC) { ntile_n -= NC; ++tile_n; }
+                const bool has_next = item + (int)gridDim.x < n_items;
+                float v1[8], z1[8];
+                // ---- X ----
+                if (SPT <= 8) {
+                    gn_stats_small<GS>(tid, SPT, Lp, a.L, scr);
+                    if (has_next) load_item(k + 1, tile_n, ntile_n, v1, z1);
+                    epi_sync();
+                } else {
+                    gn_stats_big1(tid, SPT, Lp, a.L, scr);
+                    if (has_next) load_item(k + 1, tile_n, ntile_n, v1, z1);
+                    epi_sync();
+                    gn_stats_big2<GS>(tid, SPT, a.L, scr);
+                    epi_sync();
+                }
+                if (dbg && tid == 64 && k == 0) a.dbg[9] = clock64();  // statistics of item 0 published
+                // ---- Y ----
+                const float* pt = ptab + (k & 3) * 160 + cg * 8;
+                const float4 pg0 = *reinterpret_cast<const float4*>(pt + 32), pg1 = *reinterpret_cast<const float4*>(pt + 36);
+                const float4 pe0 = *reinterpret_cast<const float4*>(pt + 64), pe1 = *reinterpret_cast<const float4*>(pt + 68);
+                float4 pc0 = z4, pc1 = z4;
+                if (a.t_dev == nullptr) { pc0 = *reinterpret_cast<const float4*>(pt + 128); pc1 = *reinterpret_cast<const float4*>(pt + 132); }
+                else if (a.cond != nullptr && valid) {  // per-sample t (per-call entry points): the row depends on the sample
+                    const float* cp = a.cond + (size_t)a.t_dev[b] * a.CO + c8;
+                    pc0 = *reinterpret_cast<const float4*>(cp); pc1 = *reinterpret_cast<const float4*>(cp + 4);
+                }
+                gn_apply<GS>(v0, valid, s, cg, SPT, scr, pg0, pg1, pe0, pe1);
+                if (dbg && tid == 64 && k == 0) a.dbg[6] = clock64();  // GroupNorm + Mish done
+                // time conditioning (zero when absent), then the residual: fused 1x1 conv accumulator + bias or identity values
+                v0[0] += pc0.x; v0[1] += pc0.y; v0[2] += pc0.z; v0[3] += pc0.w;
+                v0[4] += pc1.x; v0[5] += pc1.y; v0[6] += pc1.z; v0[7] += pc1.w;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v0[j] += z0[j];
+                if (valid) tc_store_row_at(a, v0, b, tile, s, l, c8, a.L);  // same length: same (row tile, slot) as the input
+                if (has_next) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) { v0[j] = v1[j]; z0[j] = z1[j]; }
+                }
+                tile = tile_n; ntile = ntile_n;
             }
-        }
-        int k = 0;
-        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++k) {
-            const int stage = k & 1;
-            const int b = tile * SPT + s;
-            const bool valid = row_ok && (b < a.B);
-            const int c8 = ntile * TC_NT + cg * 8;  // first of this thread's 8 output channels
-            float4 pc0 = z4, pc1 = z4;
-            if (full && a.cond != nullptr && a.t_dev != nullptr && valid) {  // per-sample t (per-call entry points): the row depends on the sample
-                const float* cp = a.cond + (size_t)a.t_dev[b] * a.CO + c8;
-                pc0 = *reinterpret_cast<const float4*>(cp); pc1 = *reinterpret_cast<const float4*>(cp + 4);
-            }
-            // identity residual of THIS item: requested one item ahead (below), so its latency hid behind the previous epilogue
-            float rid[8];
+        } else {
+            int k = 0;
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++k) {
+                const int stage = k & 1;
+                const int b = tile * SPT + s;
+                const bool valid = row_ok && (b < a.B);
+                const int c8 = ntile * TC_NT + cg * 8;  // first of this thread's 8 output channels
+                mbar_wait(acc_full0 + 8 * stage, ((uint32_t)k >> 1) & 1u);
+                __syncwarp();
+                tc_fence_after();
+                const uint32_t taddr = taddr0 + (uint32_t)stage * TCL_ACC_COLS;
+                if (dbg && tid == 64 && k == 0) a.dbg[4] = clock64();  // accumulators ready
+                float v[8], w[8];  // main accumulator; second accumulator (odd outputs of UP)
+                tc_load_acc(taddr, p1, v);
+                if (MODE == TCM_UP) tc_load_acc(taddr + 128, p1, w);
+                const float* pt = ptab + (k & 3) * 160 + cg * 8;  // parameter rows of the item's channels (issuer-filled table)
+                const float4 pb0 = *reinterpret_cast<const float4*>(pt), pb1 = *reinterpret_cast<const float4*>(pt + 4);
+                // the stage (accumulators and parameter rows) is in registers: hand it back (the MMAs of the item after next may start)
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_local(acc_empty0 + 8 * stage);
+                if (dbg && tid == 64 && k == 0) a.dbg[5] = clock64();  // TMEM read
+                if (!full) {
+                    float* dst = a.raw_out + (((size_t)tile * NC + ntile) * 128 + r) * 32 + cg * 8;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) rid[j] = rid_next[j];
-
-            mbar_wait(acc_full0 + 8 * stage, ((uint32_t)k >> 1) & 1u);
-            __syncwarp();
-            tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)stage * TCL_ACC_COLS + cg * 8;
-            if (dbg && tid == 64 && k == 0) a.dbg[4] = clock64();  // accumulators ready
-            float v[8], w[8];  // main accumulator; second accumulator (odd outputs of UP, the block's 1x1 residual conv)
-            tc_load_acc(taddr, p1, v);
-            if (MODE == TCM_UP || (MODE == TCM_CONV5 && a.res_w != nullptr)) tc_load_acc(taddr + 128, p1, w);
-            // parameter rows of the item's channels (producer-filled table)
-            const float* pt = ptab + stage * 160 + cg * 8;
-            const float4 pb0 = *reinterpret_cast<const float4*>(pt), pb1 = *reinterpret_cast<const float4*>(pt + 4);
-            const float4 pg0 = *reinterpret_cast<const float4*>(pt + 32), pg1 = *reinterpret_cast<const float4*>(pt + 36);
-            const float4 pe0 = *reinterpret_cast<const float4*>(pt + 64), pe1 = *reinterpret_cast<const float4*>(pt + 68);
-            const float4 pr0 = *reinterpret_cast<const float4*>(pt + 96), pr1 = *reinterpret_cast<const float4*>(pt + 100);
-            if (a.t_dev == nullptr) { pc0 = *reinterpret_cast<const float4*>(pt + 128); pc1 = *reinterpret_cast<const float4*>(pt + 132); }
-            // the stage (accumulators and parameter rows) is in registers: hand it back (the MMAs of the item after next may start)
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive_local(acc_empty0 + 8 * stage);
-            // identity residual of the NEXT item of this CTA
-            int tile_n = tile + gq, ntile_n = ntile + gr;
-            if (ntile_n >= NC) { ntile_n -= NC; ++tile_n; }
-            if (has_rid) {
-                const int item_n = item + (int)gridDim.x;
-#pragma unroll
-                for (int j = 0; j < 8; ++j) rid_next[j] = 0.f;
-                if (item_n < n_items) {
-                    const int b_n = tile_n * SPT + s;
-                    if (row_ok && (b_n < a.B)) {
-                        const float* rp = a.res_cm + ((size_t)b_n * a.CO + ntile_n * TC_NT + cg * 8) * Lp + 2 + l;
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) rid_next[j] = rp[(size_t)j * Lp];
+                    for (int j = 0; j < 8; ++j) dst[j] = v[j];
+                } else if (MODE == TCM_DOWN) {
+                    // stride-2 conv: the MMA evaluated every input position; keep the even ones (out[m] = conv at l = 2m)
+                    v[0] += pb0.x; v[1] += pb0.y; v[2] += pb0.z; v[3] += pb0.w;
+                    v[4] += pb1.x; v[5] += pb1.y; v[6] += pb1.z; v[7] += pb1.w;
+                    if (valid && (l & 1) == 0) tc_store_row(a, v, b, l >> 1, c8, a.L >> 1);
+                } else if (MODE == TCM_UP) {
+                    // transposed conv: accumulator 0 = even outputs (2l), accumulator 1 = odd outputs (2l + 1)
+                    v[0] += pb0.x; v[1] += pb0.y; v[2] += pb0.z; v[3] += pb0.w;
+                    v[4] += pb1.x; v[5] += pb1.y; v[6] += pb1.z; v[7] += pb1.w;
+                    w[0] += pb0.x; w[1] += pb0.y; w[2] += pb0.z; w[3] += pb0.w;
+                    w[4] += pb1.x; w[5] += pb1.y; w[6] += pb1.z; w[7] += pb1.w;
+                    if (valid) {
+                        tc_store_row(a, v, b, 2 * l, c8, 2 * a.L);
+                        tc_store_row(a, w, b, 2 * l + 1, c8, 2 * a.L);
                     }
                 }
+                int tile_n = tile + gq, ntile_n = ntile + gr;
+                if (ntile_n >= NC) { ntile_n -= NC; ++tile_n; }
+                tile = tile_n; ntile = ntile_n;
             }
-            if (dbg && tid == 64 && k == 0) a.dbg[5] = clock64();  // TMEM read
-
-            if (!full) {
-                float* dst = a.raw_out + (((size_t)tile * NC + ntile) * 128 + r) * 32 + cg * 8;
-#pragma unroll
-                for (int j = 0; j < 8; ++j) dst[j] = v[j];
-            } else if (MODE == TCM_DOWN) {
-                // stride-2 conv: the MMA evaluated every input position; keep the even ones (out[m] = conv at l = 2m)
-                v[0] += pb0.x; v[1] += pb0.y; v[2] += pb0.z; v[3] += pb0.w;
-                v[4] += pb1.x; v[5] += pb1.y; v[6] += pb1.z; v[7] += pb1.w;
-                if (valid && (l & 1) == 0) tc_store_row(a, v, b, l >> 1, c8, a.L >> 1);
-            } else if (MODE == TCM_UP) {
-                // transposed conv: accumulator 0 = even outputs (2l), accumulator 1 = odd outputs (2l + 1)
-                v[0] += pb0.x; v[1] += pb0.y; v[2] += pb0.z; v[3] += pb0.w;
-                v[4] += pb1.x; v[5] += pb1.y; v[6] += pb1.z; v[7] += pb1.w;
-                w[0] += pb0.x; w[1] += pb0.y; w[2] += pb0.z; w[3] += pb0.w;
-                w[4] += pb1.x; w[5] += pb1.y; w[6] += pb1.z; w[7] += pb1.w;
-                if (valid) {
-                    tc_store_row(a, v, b, 2 * l, c8, 2 * a.L);
-                    tc_store_row(a, w, b, 2 * l + 1, c8, 2 * a.L);
-                }
-            } else {
-                v[0] += pb0.x; v[1] += pb0.y; v[2] += pb0.z; v[3] += pb0.w;
-                v[4] += pb1.x; v[5] += pb1.y; v[6] += pb1.z; v[7] += pb1.w;
-                // scratch of parity k & 1: the partial sums of item k + 2 are written after every thread has passed the two
-                // barriers of item k + 1, i.e. after its last read of item k's statistics (no barrier at the end of an item)
-                gn_mish8<GS, true>(v, valid, r, s, cg, tid, SPT, Lp, a.L, part + stage * (TC_GN_SCRATCH_BYTES / (int)sizeof(float)), pg0, pg1, pe0, pe1,
-                                   (dbg && tid == 64 && k == 0) ? a.dbg : nullptr);
-                if (dbg && tid == 64 && k == 0) a.dbg[6] = clock64();  // GroupNorm + Mish done
-                // time conditioning (zero when absent), then the residual: fused 1x1 conv accumulator or identity values
-                v[0] += pc0.x; v[1] += pc0.y; v[2] += pc0.z; v[3] += pc0.w;
-                v[4] += pc1.x; v[5] += pc1.y; v[6] += pc1.z; v[7] += pc1.w;
-                if (a.res_w != nullptr) {
-                    v[0] += w[0] + pr0.x; v[1] += w[1] + pr0.y; v[2] += w[2] + pr0.z; v[3] += w[3] + pr0.w;
-                    v[4] += w[4] + pr1.x; v[5] += w[5] + pr1.y; v[6] += w[6] + pr1.z; v[7] += w[7] + pr1.w;
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) v[j] += rid[j];
-                }
-                if (valid) tc_store_row_at(a, v, b, tile, s, l, c8, a.L);  // same length: same (row tile, slot) as the input
-            }
-            tile = tile_n; ntile = ntile_n;
         }
         tc_fence_before();
     }
@@ -695,8 +739,8 @@ int launch_conv5_tc(const TcConvArgs& a_in, cudaStream_t stream) {
     const int SPT = TC_RT / (a.L + 4);
     MPDB_REQUIRE(SPT <= 12, "tc conv: too many samples per tile");
 #undef a
-    const size_t smem = (size_t)TC_PS_RING_BYTES + (2 * TC_PS_MAX_STAGES + 4) * 8 + 16 + 2 * TC_GN_SCRATCH_BYTES + 2 * 160 * sizeof(float) + 64;
-    static_assert((size_t)TC_PS_RING_BYTES + (2 * TC_PS_MAX_STAGES + 4) * 8 + 16 + 2 * TC_GN_SCRATCH_BYTES + 2 * 160 * sizeof(float) + 64 <= 227 * 1024, "conv5_tc_kernel: shared memory");
+    const size_t smem = (size_t)TC_PS_RING_BYTES + (2 * TC_PS_MAX_STAGES + 4) * 8 + 16 + 2 * TC_GN_SCRATCH_BYTES + 4 * 160 * sizeof(float) + 64;
+    static_assert((size_t)TC_PS_RING_BYTES + (2 * TC_PS_MAX_STAGES + 4) * 8 + 16 + 2 * TC_GN_SCRATCH_BYTES + 4 * 160 * sizeof(float) + 64 <= 227 * 1024, "conv5_tc_kernel: shared memory");
     TcConvArgs a = a_in;
     {   // ring geometry: a stage = the largest activation box + the largest weight group of this layer
         const int wmul = a.prec == 1 ? 1 : 2, ntaps = a.mode == TCM_DOWN ? 3 : a.mode == TCM_UP ? 4 : 5;
