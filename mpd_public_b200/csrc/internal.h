@@ -89,6 +89,7 @@ struct TcConvArgs {
     CUtensorMap tm[4];
     int tm_nch[4];
     int ps_stages, ps_stage_bytes, ps_act_bytes;  // operand-ring geometry (set by launch_conv5_tc)
+    int pdl;                      // launched with programmatic dependent launch (set by launch_conv5_tc): weights before the dependency wait
 };
 constexpr int TC_PS_MAX_STAGES = 8;
 constexpr int TC_PS_RING_BYTES = 216064;  // operand ring of the persistent kernel, cut into stages of (activation box + weight group) bytes by launch_conv5_tc

@@ -169,12 +169,20 @@ __global__ void __launch_bounds__(TCL_THREADS, 1) conv5_tc_kernel(const __grid_c
             if (acts) tma_load_5d(st, &a.tm[src], 0, 0, c_src * (TC_KCH / 8), tile, 0, full0 + 8 * s);
         };
         int i = 0, pre = 0;
-        for (int item = blockIdx.x; item < n_items && pre < NS; item += gridDim.x)
-            for (int gi = 0; gi < n_groups && pre < NS; ++gi, ++pre) produce(pre, item, gi, true, false);
-        pdl_wait();
-        pre = 0;
-        for (int item = blockIdx.x; item < n_items && pre < NS; item += gridDim.x)
-            for (int gi = 0; gi < n_groups && pre < NS; ++gi, ++pre) produce(pre, item, gi, false, true);
+        if (a.pdl) {
+            for (int item = blockIdx.x; item < n_items && pre < NS; item += gridDim.x)
+                for (int gi = 0; gi < n_groups && pre < NS; ++gi, ++pre) produce(pre, item, gi, true, false);
+            pdl_wait();
+            pre = 0;
+            for (int item = blockIdx.x; item < n_items && pre < NS; item += gridDim.x)
+                for (int gi = 0; gi < n_groups && pre < NS; ++gi, ++pre) produce(pre, item, gi, false, true);
+        } else {
+            // plain stream / graph order (the default): nothing to overlap with, so every stage gets its weights AND its
+            // activations at once, in ring order. One produce() costs the warp ~0.3 us; filling 8 stages weights-first meant the
+            // activations of the FIRST group left ~2.5 us after the CTA started and every launch saw its first accumulator at ~4 us
+            for (int item = blockIdx.x; item < n_items && pre < NS; item += gridDim.x)
+                for (int gi = 0; gi < n_groups && pre < NS; ++gi, ++pre) produce(pre, item, gi, true, true);
+        }
         // the ring is bounded by its own empty barriers only: operands run as far ahead of the MMAs as the stages allow
         for (int item = blockIdx.x; item < n_items; item += gridDim.x)
             for (int gi = 0; gi < n_groups; ++gi, ++i) {
@@ -742,6 +750,7 @@ int launch_conv5_tc(const TcConvArgs& a_in, cudaStream_t stream) {
     const size_t smem = (size_t)TC_PS_RING_BYTES + (2 * TC_PS_MAX_STAGES + 4) * 8 + 16 + 2 * TC_GN_SCRATCH_BYTES + 4 * 160 * sizeof(float) + 64;
     static_assert((size_t)TC_PS_RING_BYTES + (2 * TC_PS_MAX_STAGES + 4) * 8 + 16 + 2 * TC_GN_SCRATCH_BYTES + 4 * 160 * sizeof(float) + 64 <= 227 * 1024, "conv5_tc_kernel: shared memory");
     TcConvArgs a = a_in;
+    a.pdl = g_use_pdl ? 1 : 0;
     {   // ring geometry: a stage = the largest activation box + the largest weight group of this layer
         const int wmul = a.prec == 1 ? 1 : 2, ntaps = a.mode == TCM_DOWN ? 3 : a.mode == TCM_UP ? 4 : 5;
         int max_nch = 1;
