@@ -110,11 +110,59 @@ __global__ void __launch_bounds__(TCL_THREADS, 1) conv5_tc_kernel(const __grid_c
     const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + TC_PS_MAX_STAGES);
     const uint32_t acc_full0 = smem_u32(bars + 2 * TC_PS_MAX_STAGES), acc_empty0 = acc_full0 + 16;
 
-    if (tid == 0) {
-        for (int s = 0; s < NS; ++s) {
-            mbar_init(full0 + 8 * s, 1);
-            mbar_init(empty0 + 8 * s, 2);  // both issuers release a stage
+    // group gi of an item -> (source, first chunk within the source, chunks in the group, first chunk within main / residual conv)
+    auto group_geom = [&](int gi, int& src, int& c_src, int& nch, int& c_conv) {
+        src = 0;
+        int g = gi;
+        while (g >= ng[src]) { g -= ng[src]; ++src; }
+        c_src = g * a.tm_nch[src];
+        const int ch = Cs[src] / TC_KCH;
+        nch = ch - c_src < a.tm_nch[src] ? ch - c_src : a.tm_nch[src];
+        c_conv = c_src + ((src == 1) ? a.c0 / TC_KCH : (src == 3) ? a.rc0 / TC_KCH : 0);
+    };
+
+    // one K-chunk group of an item -> ring stage i % NS (producer warp only: the whole warp calls it, one elected lane issues)
+    auto produce = [&](int i, int item, int gi, bool weights, bool acts) {
+        const int tile = item / NC, ntile = item - tile * NC;
+        const int s = i % NS;
+        int src, c_src, nch, c_conv;
+        group_geom(gi, src, c_src, nch, c_conv);
+        const bool is_res = src >= 2;
+        const int ntaps = is_res ? 1 : NTAPS;
+        const uint32_t wmul = p1 ? 1u : 2u;  // precision 1 streams the hi halves only
+        const uint32_t bbytes = (uint32_t)nch * wmul * ntaps * TC_B_TAP_BYTES;
+        const uint32_t abytes = (uint32_t)a.tm_nch[src] * wmul * TC_A_PLANE_BYTES;  // the whole box (rows past the tensor are zero-filled)
+        const uint32_t st = stages_u32 + (uint32_t)s * STAGE_BYTES;
+        if (weights) {
+            const size_t welems = is_res ? ((size_t)ntile * n_res_ch + c_conv) * (2 * 1 * TC_B_TAP_BYTES / 2)
+                                         : ((size_t)ntile * n_main_ch + c_conv) * (2 * NTAPS * TC_B_TAP_BYTES / 2);
+            const unsigned short* wsrc = p1 ? (is_res ? a.res_w_hi : a.w_hi) + welems / 2 : (is_res ? a.res_w : a.w) + welems;
+            mbar_expect_tx_elect(full0 + 8 * s, abytes + bbytes);  // covers the activation copy too
+            bulk_g2s_elect(st + ACT_BYTES, wsrc, bbytes, full0 + 8 * s);
         }
+        if (acts) tma_load_5d(st, &a.tm[src], 0, 0, c_src * (TC_KCH / 8), tile, 0, full0 + 8 * s);
+    };
+    // The producer warp owns the operand ring: it initialises the ring's barriers itself and, outside programmatic dependent
+    // launch, issues the FIRST item's first groups before the block-wide setup barrier, so they travel while TMEM is being
+    // allocated (one produce() costs the warp ~0.3 us: two of them fit under the ~0.9 us of setup; issuing the whole ring
+    // here held the barrier for 2.4 us and was slower).
+    int n_early = 0;
+    if (warp == TC_THREADS / 32) {
+        if (lane == 0) {
+            for (int s = 0; s < NS; ++s) {
+                mbar_init(full0 + 8 * s, 1);
+                mbar_init(empty0 + 8 * s, 2);  // both issuers release a stage
+            }
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the copy engine completes transactions on these barriers
+        }
+        __syncwarp();
+        if (!a.pdl) {
+            const int e = n_groups < 2 ? n_groups : 2;
+            for (; n_early < e && n_early < NS; ++n_early) produce(n_early, (int)blockIdx.x, n_early, true, true);
+        }
+    }
+    if (tid == 0) {
         for (int s = 0; s < 2; ++s) {
             mbar_init(acc_full0 + 8 * s, 3);                  // both issuers' MMAs of the item have retired + issuer 1's parameter rows are in place
             mbar_init(acc_empty0 + 8 * s, TC_THREADS / 32);   // every epilogue warp has read its part of the stage
@@ -133,41 +181,10 @@ __global__ void __launch_bounds__(TCL_THREADS, 1) conv5_tc_kernel(const __grid_c
     const uint32_t tmem_base = *tmem_slot;
     if (dbg && tid == 64) a.dbg[1] = clock64();  // setup done (barriers, TMEM)
 
-    // group gi of an item -> (source, first chunk within the source, chunks in the group, first chunk within main / residual conv)
-    auto group_geom = [&](int gi, int& src, int& c_src, int& nch, int& c_conv) {
-        src = 0;
-        int g = gi;
-        while (g >= ng[src]) { g -= ng[src]; ++src; }
-        c_src = g * a.tm_nch[src];
-        const int ch = Cs[src] / TC_KCH;
-        nch = ch - c_src < a.tm_nch[src] ? ch - c_src : a.tm_nch[src];
-        c_conv = c_src + ((src == 1) ? a.c0 / TC_KCH : (src == 3) ? a.rc0 / TC_KCH : 0);
-    };
-
     if (warp == TC_THREADS / 32) {
         // ===== producer warp: group i of the CTA's item sequence -> stage i % STAGES. Weights are constants: the first groups'
         // weight copies are issued before the dependency wait, so under programmatic dependent launch they overlap the
         // previous kernel's epilogue. Activations follow it. =====
-        auto produce = [&](int i, int item, int gi, bool weights, bool acts) {
-            const int tile = item / NC, ntile = item - tile * NC;
-            const int s = i % NS;
-            int src, c_src, nch, c_conv;
-            group_geom(gi, src, c_src, nch, c_conv);
-            const bool is_res = src >= 2;
-            const int ntaps = is_res ? 1 : NTAPS;
-            const uint32_t wmul = p1 ? 1u : 2u;  // precision 1 streams the hi halves only
-            const uint32_t bbytes = (uint32_t)nch * wmul * ntaps * TC_B_TAP_BYTES;
-            const uint32_t abytes = (uint32_t)a.tm_nch[src] * wmul * TC_A_PLANE_BYTES;  // the whole box (rows past the tensor are zero-filled)
-            const uint32_t st = stages_u32 + (uint32_t)s * STAGE_BYTES;
-            if (weights) {
-                const size_t welems = is_res ? ((size_t)ntile * n_res_ch + c_conv) * (2 * 1 * TC_B_TAP_BYTES / 2)
-                                             : ((size_t)ntile * n_main_ch + c_conv) * (2 * NTAPS * TC_B_TAP_BYTES / 2);
-                const unsigned short* wsrc = p1 ? (is_res ? a.res_w_hi : a.w_hi) + welems / 2 : (is_res ? a.res_w : a.w) + welems;
-                mbar_expect_tx_elect(full0 + 8 * s, abytes + bbytes);  // covers the activation copy too
-                bulk_g2s_elect(st + ACT_BYTES, wsrc, bbytes, full0 + 8 * s);
-            }
-            if (acts) tma_load_5d(st, &a.tm[src], 0, 0, c_src * (TC_KCH / 8), tile, 0, full0 + 8 * s);
-        };
         int i = 0, pre = 0;
         if (a.pdl) {
             for (int item = blockIdx.x; item < n_items && pre < NS; item += gridDim.x)
@@ -181,7 +198,8 @@ __global__ void __launch_bounds__(TCL_THREADS, 1) conv5_tc_kernel(const __grid_c
             // activations at once, in ring order. One produce() costs the warp ~0.3 us; filling 8 stages weights-first meant the
             // activations of the FIRST group left ~2.5 us after the CTA started and every launch saw its first accumulator at ~4 us
             for (int item = blockIdx.x; item < n_items && pre < NS; item += gridDim.x)
-                for (int gi = 0; gi < n_groups && pre < NS; ++gi, ++pre) produce(pre, item, gi, true, true);
+                for (int gi = 0; gi < n_groups && pre < NS; ++gi, ++pre)
+                    if (pre >= n_early) produce(pre, item, gi, true, true);  // the first one or two left before the setup barrier
         }
         // the ring is bounded by its own empty barriers only: operands run as far ahead of the MMAs as the stages allow
         for (int item = blockIdx.x; item < n_items; item += gridDim.x)
