@@ -258,8 +258,10 @@ __global__ void __launch_bounds__(GUIDE_THREADS, OCC) guide_step_kernel(const __
     float* xn = smem;                      // [H][D] normalised trajectory (updated in place between evaluations)
     float* xu = xn + H * D;                // [H][D] unnormalised
     float* gq = xu + H * D;                // [n_coll][NI][8] d cost_c / d q_interp
-    float* fgrad = gq + n_coll * NI * 8;   // [n_coll + 1][H][8] clipped, weighted per-cost gradients (+ one scratch plane)
-    float* w1s = fgrad + (n_coll + 1) * H * 8;          // [NI] interpolation weight of the upper tap
+    float* tapw = gq + n_coll * NI * 8;    // [H][8] taps of the interpolation adjoint: weight ...
+    int* tapi = reinterpret_cast<int*>(tapw + H * 8);   // [H][8] ... and interpolated row (built once per launch)
+    float* gvs = tapw + 2 * H * 8;         // [H][8] scratch plane (finite-difference velocity mode)
+    float* w1s = gvs + H * 8;                           // [NI] interpolation weight of the upper tap
     int* i0s = reinterpret_cast<int*>(w1s + NI);        // [NI] lower tap
     float* fk = reinterpret_cast<float*>(i0s + NI);     // [42 + 3 S][FK_ROWS] FK scratch of one pass
     __shared__ int s_flag;
@@ -274,6 +276,36 @@ __global__ void __launch_bounds__(GUIDE_THREADS, OCC) guide_step_kernel(const __
     int flag = a.flag_in ? *a.flag_in : 0;
     const float ratio = NI > 1 ? (float)(H - 1) / (float)(NI - 1) : 0.f;  // align_corners=True
     const float inv_ratio = ratio > 0.f ? 1.f / ratio : 0.f;
+    // Adjoint of the linear interpolation as a gather: support row h receives from the interpolated rows i whose lower / upper
+    // tap is h. Which rows, and with which weight, depends only on (H, n_interp): the (row, weight) pairs are tabulated once per
+    // launch, in ascending i (the summation order of the on-the-fly form, so the sums are bit-identical), instead of being
+    // re-derived by every thread in every evaluation (22 % of the kernel's instructions, profiles/r02e_ncu_guide_hotspots.txt).
+    // Up to 8 taps per row (5 at n_interp = 2 H); a denser interpolation falls back to the on-the-fly loop.
+    __shared__ int s_tap_overflow;
+    if (tid == 0) s_tap_overflow = 0;
+    __syncthreads();
+    for (int h = tid; h < H; h += NTH) {
+        int lo_i = (int)floorf((float)(h - 1) * inv_ratio), hi_i = (int)ceilf((float)(h + 1) * inv_ratio);
+        if (lo_i < 0) lo_i = 0;
+        if (hi_i > NI - 1) hi_i = NI - 1;
+        int cnt = 0;
+        for (int i = lo_i; i <= hi_i; ++i) {
+            const float r = ratio * (float)i;  // the same expressions as in the row pass below
+            int i0 = (int)r;
+            if (i0 > H - 1) i0 = H - 1;
+            const float l1 = fminf(fmaxf(r - (float)i0, 0.f), 1.f);
+            const int i1 = i0 + (i0 < H - 1 ? 1 : 0);
+            const float cw = (i0 == h ? 1.f - l1 : 0.f) + (i1 == h ? l1 : 0.f);
+            if (cw != 0.f) {
+                if (cnt < 8) { tapw[h * 8 + cnt] = cw; tapi[h * 8 + cnt] = i; }
+                ++cnt;
+            }
+        }
+        if (cnt > 8) s_tap_overflow = 1;
+        for (int c = cnt; c < 8; ++c) { tapw[h * 8 + c] = 0.f; tapi[h * 8 + c] = 0; }
+    }
+    __syncthreads();
+    const bool use_taps = s_tap_overflow == 0;
 
     for (int it = 0; it < n_it; ++it) {
         const bool last_it = it == n_it - 1;
@@ -460,48 +492,8 @@ __global__ void __launch_bounds__(GUIDE_THREADS, OCC) guide_step_kernel(const __
         __syncthreads();
         if (dbg) dbg[3] = clock64();  // interpolation + kinematic chain + lookups + J^T
 
-        // ---------------- (E) adjoint of the interpolation (gather form), 1/sigma^2, per-cost clip / endpoint zero / weight ----------------
-        // 8 lanes per (support row, cost): lane k < q owns coordinate k; the clip norm is an xor-shuffle tree over the 8 lanes
-        for (int item0 = 0; item0 < H * n_coll; item0 += NTH / 8) {
-            const int item = item0 + (tid >> 3), k = tid & 7;
-            const bool on = item < H * n_coll;
-            // H is a multiple of 64 for every horizon the UNet accepts with 4 levels: a round of 64 items stays inside one cost
-            const int f0 = item0 / H;
-            const int f = !on ? 0 : (H & 63) == 0 ? f0 : item / H;
-            const int h = on ? item - f * H : 0;
-            float gsk = 0.f;
-            if (on && k < q) {
-                // rows i with ratio * i in (h - 1, h + 1) touch h; floor / ceil leave one row of slack on each side for the
-                // rounding of the products (rows that do not touch h contribute with weight 0)
-                int lo_i = (int)floorf((float)(h - 1) * inv_ratio);
-                int hi_i = (int)ceilf((float)(h + 1) * inv_ratio);
-                if (lo_i < 0) lo_i = 0;
-                if (hi_i > NI - 1) hi_i = NI - 1;
-                const float* gqf = gq + (long long)f * NI * 8 + k;
-                for (int i = lo_i; i <= hi_i; ++i) {
-                    const int i0 = i0s[i];
-                    const int i1 = i0 + (i0 < H - 1 ? 1 : 0);
-                    const float l1 = w1s[i];
-                    const float cw = (i0 == h ? 1.f - l1 : 0.f) + (i1 == h ? l1 : 0.f);
-                    gsk = cw != 0.f ? fmaf(cw, gqf[i * 8], gsk) : gsk;
-                }
-                gsk *= g.isig2[f];
-            }
-            float scale = 1.f;
-            if (g.clip) {
-                const float t = (on && k < q) ? gsk + 1e-6f : 0.f;
-                float n2 = t * t;
-                n2 += __shfl_xor_sync(0xffffffffu, n2, 1);
-                n2 += __shfl_xor_sync(0xffffffffu, n2, 2);
-                n2 += __shfl_xor_sync(0xffffffffu, n2, 4);
-                if (!pos_only) n2 += (float)(D - q) * (1e-6f * 1e-6f);  // the zero velocity half of the gradient, + 1e-6 each
-                scale = clip_scale(sqrtf(n2), g.max_norm);
-            }
-            if (on && k < q) fgrad[(f * H + h) * 8 + k] = (h != 0 && h != H - 1) ? g.weight[f] * (scale * gsk) : 0.f;
-        }
-        // finite-difference velocity (guides.py:77-79): the GP cost reaches the positions through v_h = (p_{h+1} - p_{h-1}) / 2dt
-        // as well; its raw velocity gradient is parked in the scratch plane for the position pass below
-        float* gvs = fgrad + (long long)n_coll * H * 8;
+        // ---------------- (E) finite-difference velocity mode only: raw velocity gradient of the GP cost, needed from the neighbours ----------------
+        // (guides.py:77-79: the GP cost reaches the positions through v_h = (p_{h+1} - p_{h-1}) / 2dt as well)
         if (g.vel_fd && g.use_gp) {
             for (int h0 = 0; h0 < H; h0 += NTH / 8) {
                 const int h = h0 + (tid >> 3), k = tid & 7;
@@ -518,11 +510,13 @@ __global__ void __launch_bounds__(GUIDE_THREADS, OCC) guide_step_kernel(const __
                     gvs[h * 8 + k] = gvk;
                 }
             }
+            __syncthreads();
         }
-        __syncthreads();
-        if (dbg) dbg[4] = clock64();  // interpolation adjoint + clip
+        if (dbg) dbg[4] = clock64();
 
-        // ---------------- (F) GP prior (constant velocity) + sum of the costs + update, 8 lanes per support row ----------------
+        // ---------------- (F) per support row, 8 lanes (lane k < q owns coordinate k): for every collision cost the adjoint of the
+        // interpolation (gather over the row's taps), 1/sigma^2, clip-by-norm (xor-shuffle tree over the 8 lanes), endpoint zeroing,
+        // weight; then the GP prior (constant velocity) 3-tap stencil, the sum in cost order, and the update ----------------
         bool v_hi = false, v_mid = false;
         float var = 1.f;
         const bool use_var = a.model_var != nullptr || a.use_var_uniform;
@@ -533,6 +527,52 @@ __global__ void __launch_bounds__(GUIDE_THREADS, OCC) guide_step_kernel(const __
             const int h = h0 + (tid >> 3), k = tid & 7;
             const bool rowk = h < H && k < q;
             const bool inner = rowk && h > 0 && h < H - 1;  // gradient rows 0 and H-1 are zeroed by the guide manager
+            float totp = 0.f, totv = 0.f;
+            for (int f = 0; f < n_coll; ++f) {  // cost order, as the reference's `grad += w * g`
+                float gsk = 0.f;
+                if (rowk) {
+                    const float* gqf = gq + (long long)f * NI * 8 + k;
+                    if (use_taps) {
+                        const float4 w0 = *reinterpret_cast<const float4*>(tapw + h * 8), w1 = *reinterpret_cast<const float4*>(tapw + h * 8 + 4);
+                        const int4 t0 = *reinterpret_cast<const int4*>(tapi + h * 8), t1 = *reinterpret_cast<const int4*>(tapi + h * 8 + 4);
+                        // a zero weight is a padding entry: skipped exactly as the on-the-fly form skips rows that do not touch h
+                        gsk = w0.x != 0.f ? fmaf(w0.x, gqf[t0.x * 8], gsk) : gsk;
+                        gsk = w0.y != 0.f ? fmaf(w0.y, gqf[t0.y * 8], gsk) : gsk;
+                        gsk = w0.z != 0.f ? fmaf(w0.z, gqf[t0.z * 8], gsk) : gsk;
+                        gsk = w0.w != 0.f ? fmaf(w0.w, gqf[t0.w * 8], gsk) : gsk;
+                        gsk = w1.x != 0.f ? fmaf(w1.x, gqf[t1.x * 8], gsk) : gsk;
+                        gsk = w1.y != 0.f ? fmaf(w1.y, gqf[t1.y * 8], gsk) : gsk;
+                        gsk = w1.z != 0.f ? fmaf(w1.z, gqf[t1.z * 8], gsk) : gsk;
+                        gsk = w1.w != 0.f ? fmaf(w1.w, gqf[t1.w * 8], gsk) : gsk;
+                    } else {
+                        // rows i with ratio * i in (h - 1, h + 1) touch h; floor / ceil leave one row of slack on each side for the
+                        // rounding of the products (rows that do not touch h contribute with weight 0)
+                        int lo_i = (int)floorf((float)(h - 1) * inv_ratio);
+                        int hi_i = (int)ceilf((float)(h + 1) * inv_ratio);
+                        if (lo_i < 0) lo_i = 0;
+                        if (hi_i > NI - 1) hi_i = NI - 1;
+                        for (int i = lo_i; i <= hi_i; ++i) {
+                            const int i0 = i0s[i];
+                            const int i1 = i0 + (i0 < H - 1 ? 1 : 0);
+                            const float l1 = w1s[i];
+                            const float cw = (i0 == h ? 1.f - l1 : 0.f) + (i1 == h ? l1 : 0.f);
+                            gsk = cw != 0.f ? fmaf(cw, gqf[i * 8], gsk) : gsk;
+                        }
+                    }
+                    gsk *= g.isig2[f];
+                }
+                float scale = 1.f;
+                if (g.clip) {
+                    const float t = rowk ? gsk + 1e-6f : 0.f;
+                    float n2c = t * t;
+                    n2c += __shfl_xor_sync(0xffffffffu, n2c, 1);
+                    n2c += __shfl_xor_sync(0xffffffffu, n2c, 2);
+                    n2c += __shfl_xor_sync(0xffffffffu, n2c, 4);
+                    if (!pos_only) n2c += (float)(D - q) * (1e-6f * 1e-6f);  // the zero velocity half of the gradient, + 1e-6 each
+                    scale = clip_scale(sqrtf(n2c), g.max_norm);
+                }
+                if (inner) totp += g.weight[f] * (scale * gsk);  // rows 0 and H-1: the guide manager zeroes them (adds +0)
+            }
             float gpk = 0.f, gvk = 0.f, n2 = 0.f, n2v = 0.f;
             if (g.use_gp && inner) {
                 const float pm = xu[(h - 1) * D + k], pc = xu[h * D + k], pn = xu[(h + 1) * D + k];
@@ -560,8 +600,6 @@ __global__ void __launch_bounds__(GUIDE_THREADS, OCC) guide_step_kernel(const __
             n2v += __shfl_xor_sync(0xffffffffu, n2v, 2);
             n2v += __shfl_xor_sync(0xffffffffu, n2v, 4);
             if (!rowk) continue;
-            float totp = 0.f, totv = 0.f;
-            for (int f = 0; f < n_coll; ++f) totp += fgrad[(f * H + h) * 8 + k];  // cost order, as the reference's `grad += w * g`
             if (g.use_gp && inner) {
                 const float scale = g.clip ? clip_scale(sqrtf(n2), g.max_norm) : 1.f;
                 const float scale_v = pos_only ? (g.clip ? clip_scale(sqrtf(n2v), g.max_norm) : 1.f) : scale;
@@ -728,7 +766,7 @@ __global__ void __launch_bounds__(FK_ROWS) fk_debug_kernel(const __grid_constant
 }
 
 static size_t guide_smem_bytes(const GuideDev& g, int H) {
-    size_t f = (size_t)2 * H * g.D + (size_t)g.n_coll * g.n_interp * 8 + (size_t)(g.n_coll + 1) * H * 8 + 2 * (size_t)g.n_interp +
+    size_t f = (size_t)2 * H * g.D + (size_t)g.n_coll * g.n_interp * 8 + (size_t)3 * H * 8 + 2 * (size_t)g.n_interp +
                (size_t)(42 + 3 * g.n_spheres) * FK_ROWS;
     return f * sizeof(float);
 }
