@@ -72,6 +72,9 @@ class ClockSampler(threading.Thread):
         self.index, self.period = index, period
         self.samples, self.reasons, self.max_mhz, self.power = [], set(), None, []
         self._halt = threading.Event()
+        # started before the timed region and armed at its first event: thread start-up and the first NVML round trips (a few ms
+        # on some hosts, under a driver lock that also holds back kernel launches) stay outside; only armed samples are kept
+        self._armed, self.primed = threading.Event(), threading.Event()
         self.ok = False
         try:
             import pynvml
@@ -96,18 +99,29 @@ class ClockSampler(threading.Thread):
         }
         while not self._halt.is_set():
             try:
-                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                armed = self._armed.is_set()
+                mhz = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
                 try:
                     mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
                 except Exception:
                     mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
-                for bit, name in names.items():
-                    if mask & bit:
-                        self.reasons.add(name)
-                self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+                watts = nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+                if armed:
+                    self.samples.append(mhz)
+                    for bit, name in names.items():
+                        if mask & bit:
+                            self.reasons.add(name)
+                    self.power.append(watts)
             except Exception:
                 pass
-            self._halt.wait(self.period)
+            self.primed.set()
+            if not self._armed.is_set():
+                self._armed.wait(self.period)  # wakes as soon as the timed region starts
+            else:
+                self._halt.wait(self.period)
+
+    def arm(self):
+        self._armed.set()
 
     def stop(self):
         self._halt.set()
@@ -394,11 +408,14 @@ def main():
         torch.cuda.synchronize()
 
     def timed(fn, k_steps, sampler=None):
-        barrier()
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         if sampler:
             sampler.start()
+            sampler.primed.wait(2.0)
+        barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
+        if sampler:
+            sampler.arm()
         for _ in range(k_steps):
             flush.zero_()
             fn()
@@ -416,6 +433,7 @@ def main():
             print(f"[bench rank {rank}] {msg}", file=sys.stderr, flush=True)
 
     log("setup done")
+    flush.zero_()  # the fill kernel's first launch loads its module (CUDA lazy loading, ~4 ms): not part of a step
     for _ in range(W):
         step_resident()
     log("warmup done")

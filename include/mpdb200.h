@@ -184,6 +184,12 @@ int mpdb_ddim_loop(mpdb_engine* e, mpdb_guide* g, const mpdb_ddim_params* p, con
  * the torch generator by n_draws * mpdb_normal_offset_increment(numel, device). */
 int mpdb_normal_fill(float* out, int64_t numel, int32_t n_draws, const int64_t* state_dev, int device, void* stream);
 int64_t mpdb_normal_offset_increment(int64_t numel, int device);
+/* LimitsNormalizer.normalize (mpd/datasets/normalization.py:150-155) in one launch: rows x[n_rows][d_in] (device, fp32,
+ * contiguous), zero-extended to d_out >= d_in columns — `get_hard_conditions` normalises cat(position, zeros),
+ * mpd/datasets/trajectories.py:214-237 —, out[n_rows][d_out] = 2 * ((v - mins[d]) / range[d]) - 1 with range = maxs - mins; the
+ * reference's operation order, every operation rounded on its own as in the eager torch ops (bit-identical, tested). */
+int mpdb_limits_normalize(const float* x, int64_t n_rows, int32_t d_in, const float* mins, const float* range, float* out,
+                          int32_t d_out, int device, void* stream);
 /* counter bumped whenever the engine reallocates device buffers, reloads parameters or changes an option: a caller that
  * captured mpdb_sample_loop (use_cuda_graph = 0) into its own CUDA graph must re-capture when it changes */
 int64_t mpdb_engine_generation(mpdb_engine* e);

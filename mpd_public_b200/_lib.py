@@ -87,6 +87,7 @@ SYMBOLS = {
     "mpdb_guide_steps_chain": (C.c_int, [_P, _P, C.c_int32, _P, C.c_int32, C.POINTER(C.c_int32), _P, _P, C.c_int64, C.c_int32,
                                          C.c_int32, _P]),
     "mpdb_normal_fill": (C.c_int, [_P, C.c_int64, C.c_int32, _P, C.c_int, _P]),
+    "mpdb_limits_normalize": (C.c_int, [_P, C.c_int64, C.c_int32, _P, _P, _P, C.c_int32, C.c_int, _P]),
     "mpdb_normal_offset_increment": (C.c_int64, [C.c_int64, C.c_int]),
     "mpdb_launch_count": (C.c_int64, []),
     "mpdb_engine_num_ops": (C.c_int, [_P]),

@@ -963,6 +963,13 @@ extern "C" int mpdb_engine_step_precision(mpdb_engine* e, int32_t t) {
     return e->tc_mode == 0 ? 0 : mpdb::step_prec(e, t);
 }
 
+extern "C" int mpdb_limits_normalize(const float* x, int64_t n_rows, int32_t d_in, const float* mins, const float* range, float* out,
+                                     int32_t d_out, int device, void* stream) {
+    MPDB_REQUIRE(x && mins && range && out && n_rows > 0 && d_in > 0 && d_out >= d_in, "mpdb_limits_normalize: bad argument");
+    MPDB_ENTER_DEVICE(device);
+    return mpdb::launch_limits_normalize(x, (long long)n_rows, d_in, mins, range, out, d_out, (cudaStream_t)stream);
+}
+
 extern "C" int64_t mpdb_engine_generation(mpdb_engine* e) { return e ? (int64_t)e->generation : -1; }
 
 extern "C" int mpdb_engine_set_option(mpdb_engine* e, const char* name, double value) {

@@ -105,6 +105,8 @@ struct TcRtbArgs {
 int launch_rtb_tc(const TcRtbArgs& a, cudaStream_t stream);
 int launch_pack_tc_weights(const float* src, unsigned short* dst, unsigned short* dst_hi, int CI, int CI_src, int CO, int ntaps,
                            unsigned perm, cudaStream_t stream);
+int launch_limits_normalize(const float* x, long long n_rows, int d_in, const float* mins, const float* range, float* out,
+                            int d_out, cudaStream_t stream);
 int launch_blc_to_tc(const float* x, unsigned short* hi, unsigned short* lo, int B, int L, int D, int C, cudaStream_t stream);
 int launch_cm_to_tc(const float* cm, unsigned short* hi, unsigned short* lo, int B, int C, int L, cudaStream_t stream);
 

@@ -721,4 +721,29 @@ int launch_copy_hc(float* x, float* out2, long long out2_bstride, int n_hc, cons
     return 0;
 }
 
+// LimitsNormalizer.normalize (normalization.py:150-155) of rows [n_rows][d_in], zero-extended to d_out columns (the hard
+// conditions are `cat(position, zeros)` before they are normalised, trajectories.py:214-237): out = 2 * ((v - min) / range) - 1
+// with the reference's operation order, each operation rounded separately (torch runs them as separate kernels).
+__global__ void limits_normalize_kernel(const float* __restrict__ x, long long n_rows, int d_in, const float* __restrict__ mins,
+                                        const float* __restrict__ range, float* __restrict__ out, int d_out) {
+    const long long n = n_rows * d_out;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int d = (int)(i % d_out);
+        const long long r = i / d_out;
+        const float v = d < d_in ? x[r * d_in + d] : 0.f;
+        const float u = __fdiv_rn(__fsub_rn(v, mins[d]), range[d]);
+        out[i] = __fsub_rn(__fmul_rn(2.f, u), 1.f);
+    }
+}
+
+int launch_limits_normalize(const float* x, long long n_rows, int d_in, const float* mins, const float* range, float* out,
+                            int d_out, cudaStream_t stream) {
+    const long long n = n_rows * d_out;
+    int blocks = (int)((n + 255) / 256);
+    if (blocks > 2048) blocks = 2048;
+    limits_normalize_kernel<<<blocks, 256, 0, stream>>>(x, n_rows, d_in, mins, range, out, d_out);
+    MPDB_LAUNCH_CHECK();
+    return 0;
+}
+
 }  // namespace mpdb

@@ -28,10 +28,29 @@ class Normalizer:
 class LimitsNormalizer(Normalizer):
     """maps [xmin, xmax] to [-1, 1] (reference :144-167)"""
 
-    def normalize(self, x):
+    def _range_tensor(self):
         rng = self.__dict__.get("_range")  # maxs - mins, the same fp32 subtraction as the reference's, done once
         if rng is None or rng.device != self.mins.device:
             rng = self.__dict__["_range"] = self.maxs - self.mins
+        return rng
+
+    def normalize(self, x, pad_to=None):
+        """`pad_to`: normalise `cat(x, zeros)` with `pad_to` columns in all (what `get_hard_conditions` needs) without
+        materialising the concatenation. fp32 CUDA tensors take ONE launch of `mpdb_limits_normalize` (same operations, same
+        roundings as the four eager kernels below: torch.equal, tests/test_gpu_parity.py); anything else runs the torch ops."""
+        rng = self._range_tensor()
+        d_out = x.shape[-1] if pad_to is None else int(pad_to)
+        if (x.is_cuda and x.dtype == torch.float32 and self.mins.is_cuda and self.mins.device == x.device
+                and self.mins.dtype == torch.float32 and self.mins.numel() == d_out and x.numel() > 0):
+            from . import _lib
+            xc = x.contiguous()
+            out = torch.empty((*x.shape[:-1], d_out), dtype=torch.float32, device=x.device)
+            _lib.check(_lib.lib().mpdb_limits_normalize(_lib.fptr(xc), xc.numel() // x.shape[-1], x.shape[-1],
+                                                        _lib.fptr(self.mins.contiguous()), _lib.fptr(rng.contiguous()),
+                                                        _lib.fptr(out), d_out, x.device.index, _lib.stream_ptr(x.device)))
+            return out
+        if pad_to is not None and d_out > x.shape[-1]:
+            x = torch.cat((x, torch.zeros((*x.shape[:-1], d_out - x.shape[-1]), dtype=x.dtype, device=x.device)), dim=-1)
         x = (x - self.mins) / rng
         x = 2 * x - 1
         return x
@@ -54,8 +73,8 @@ class DatasetNormalizer:
     def __call__(self, *args, **kwargs):
         return self.normalize(*args, **kwargs)
 
-    def normalize(self, x, key):
-        return self.normalizers[key].normalize(x)
+    def normalize(self, x, key, **kwargs):
+        return self.normalizers[key].normalize(x, **kwargs)
 
     def unnormalize(self, x, key):
         return self.normalizers[key].unnormalize(x)

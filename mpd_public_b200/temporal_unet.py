@@ -53,7 +53,11 @@ class TemporalUnet(nn.Module):
         in_out = list(zip(dims[:-1], dims[1:]))
         print(f'[ models/temporal ] Channel dimensions: {in_out}')
         # default-initialised like nn.Conv1d/nn.Linear/nn.GroupNorm would be (uniform +-1/sqrt(fan_in); GN = 1, 0)
-        for name, shape in unet_param_shapes(self.state_dim, self.unet_input_dim, self.dim_mults).items():
+        # registration order = the reference's state_dict() order: its __init__ creates the (still empty) `downs` and `ups`
+        # ModuleLists before the mid blocks (temporal_unet.py:60-116), so `ups.*` precedes `mid_block*` in a saved checkpoint
+        shapes_all = unet_param_shapes(self.state_dim, self.unet_input_dim, self.dim_mults)
+        rank = {"time_mlp": 0, "downs": 1, "ups": 2, "mid_block1": 3, "mid_block2": 4, "final_conv": 5}
+        for name, shape in sorted(shapes_all.items(), key=lambda kv: rank[kv[0].split(".")[0]]):
             if ".block.2." in name:
                 t = torch.ones(shape) if name.endswith("weight") else torch.zeros(shape)
             else:

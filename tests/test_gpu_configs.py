@@ -291,3 +291,48 @@ def test_position_only_model_runs_the_reverse_loop_with_its_guide():
     for k, v in hard.items():
         assert torch.equal(chain[:, :, k, :], v.expand(chain.shape[0], batch, q))
     assert not torch.equal(guide.velocity, vel0)
+
+
+
+def test_ingested_checkpoint_runs_the_guided_loop_on_the_gpu(tmp_path):
+    """SURVEY §8f.3 on the GPU: a model directory with the reference's on-disk layout (args.yaml + checkpoints/
+    ema_model_current_state_dict.pth holding the full GaussianDiffusionModel state dict — schedule buffers + `model.*` keys with
+    the reference's names, order and shapes, tests/golden/state_dict_keys.json) and a dataset directory (trajs-free.pt) are
+    ingested the way inference.py:103-149 does it; the guided loop of the ingested model equals, bit for bit, the loop of a
+    model built directly from the same tensors, and the normaliser limits come out of the trajectory file."""
+    import json
+    import os
+    import yaml
+    from mpd_public_b200 import ingest
+    d = str(tmp_path)
+    os.makedirs(os.path.join(d, "model", "checkpoints"))
+    os.makedirs(os.path.join(d, "data", "3"))
+    yaml.dump(dict(variance_schedule="exponential", n_diffusion_steps=C.T_DIFF, predict_epsilon=True, unet_input_dim=32,
+                   unet_dim_mults_option=0, diffusion_model_class="GaussianDiffusionModel", use_ema=True),
+              open(os.path.join(d, "model", "args.yaml"), "w"))
+    direct = cuda_model(UCASE)
+    sd = {k: v.detach().cpu() for k, v in direct.state_dict().items()}
+    ref_layout = json.load(open(os.path.join(C.GOLDEN_DIR, "state_dict_keys.json")))[UCASE]
+    assert list(ref_layout.keys()) == list(sd.keys())  # the file written below is what the reference's torch.save would hold
+    assert all(list(sd[k].shape) == list(shape) for k, shape in ref_layout.items())
+    torch.save(sd, os.path.join(d, "model", "checkpoints", "ema_model_current_state_dict.pth"))
+    model, args = ingest.load_diffusion_model(os.path.join(d, "model"), state_dim=4, n_support_points=H, device="cuda")
+    assert args["n_diffusion_steps"] == C.T_DIFF and not model.training and next(model.parameters()).is_cuda
+
+    trajs = torch.rand((40, H, 4), generator=torch.Generator().manual_seed(5)) * 2 - 1
+    torch.save(trajs, os.path.join(d, "data", "3", "trajs-free.pt"))
+    nz, h, dim = ingest.load_trajectory_limits(os.path.join(d, "data"), q_dim=2)
+    assert (h, dim) == (H, 4)
+    lim = nz.normalizers["traj"]
+    assert torch.equal(lim.mins, trajs.reshape(-1, 4).min(0).values) and torch.equal(lim.maxs, trajs.reshape(-1, 4).max(0).values)
+
+    wc, ws = CONFIGS["cfg2_dense2d"][2][0]
+    guide, ds, prob, _spec = build("cfg2_dense2d", wc, ws)
+    hard = ds.get_hard_conditions(torch.vstack((torch.as_tensor(prob.start), torch.as_tensor(prob.goal))).cuda(), normalize=True)
+    B = 16
+    noise = torch.randn((C.T_DIFF + 5 + 1, B, H, 4), generator=torch.Generator().manual_seed(9)).cuda()
+    kw = dict(guide=guide, n_guide_steps=5, t_start_guide=7, noise_std_extra_schedule_fn=lambda _t: 0.5,
+              n_diffusion_steps_without_noise=5)
+    a = model.run_inference(None, hard, n_samples=B, horizon=H, return_chain=False, noise=noise, **kw)
+    b = direct.run_inference(None, hard, n_samples=B, horizon=H, return_chain=False, noise=noise, **kw)
+    assert torch.isfinite(a).all() and torch.equal(a, b)

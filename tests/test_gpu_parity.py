@@ -523,3 +523,31 @@ def test_ddim_sample_vs_reference_golden_and_oracle(case):
     for _ in range(C.T_DIFF // 5):
         torch.randn(shape, device="cuda")
     assert torch.equal(after, torch.randn(3, device="cuda"))
+
+
+def test_limits_normalize_kernel_equals_the_eager_torch_ops():
+    """`LimitsNormalizer.normalize` on CUDA runs as one launch (mpdb_limits_normalize); the reference runs
+    `(x - mins) / (maxs - mins)`, `2 * x - 1` as four eager kernels (normalization.py:150-155). Same roundings: torch.equal,
+    also for the zero-extended form `get_hard_conditions` uses (trajectories.py:214-237) and for values far outside the limits."""
+    from mpd_public_b200.normalization import LimitsNormalizer
+    g = torch.Generator().manual_seed(11)
+    for d, q in ((14, 7), (4, 2), (7, 7)):
+        lim = torch.stack((-(torch.rand(d, generator=g) * 3 + 0.1), torch.rand(d, generator=g) * 3 + 0.1)).cuda()
+        nz = LimitsNormalizer(lim)
+        x = ((torch.rand((5, 64, d), generator=g) - 0.5) * 9).cuda()
+        want = 2 * ((x - nz.mins) / (nz.maxs - nz.mins)) - 1
+        assert torch.equal(nz.normalize(x), want)
+        if d == 2 * q:
+            pos = x[0, :2, :q]
+            want_hc = 2 * ((torch.cat((pos, torch.zeros_like(pos)), -1) - nz.mins) / (nz.maxs - nz.mins)) - 1
+            assert torch.equal(nz.normalize(pos, pad_to=d), want_hc)
+    # the dataset entry point: start / goal -> hard conditions, against the same expressions on the CPU
+    import mpd_public_b200 as M
+    from mpd_public_b200 import synthetic as S
+    prob = S.make_problem_by_id("EnvSpheres3D-RobotPanda", 64, cell=0.04)
+    ds = M.TrajectoryDataset(prob, "cuda")
+    sg = torch.vstack((torch.as_tensor(prob.start), torch.as_tensor(prob.goal)))
+    hc = ds.get_hard_conditions(sg.cuda(), normalize=True)
+    mins, maxs = torch.as_tensor(prob.mins), torch.as_tensor(prob.maxs)
+    want = 2 * ((torch.cat((sg, torch.zeros_like(sg)), -1) - mins) / (maxs - mins)) - 1
+    assert sorted(hc.keys()) == [0, 63] and torch.equal(hc[0].cpu(), want[0]) and torch.equal(hc[63].cpu(), want[1])
