@@ -33,6 +33,15 @@ if what in ("all", "layers"):
     model.tensor_cores = "auto"
     model._engine(H)
     eng.set_option("mega", 1)
+if what in ("all", "layers_big"):
+    # several work items per CTA: the software-pipelined epilogue of the persistent per-layer kernel (scratch alternating with
+    # the item parity, no end-of-item barrier), the four-slot parameter table, and final_kernel at one thread per row
+    xb = torch.randn((300, H, D), device=dev)
+    eng.set_option("mega", 0)
+    for t in (5, 20):
+        eng.unet_forward_uniform(xb, t)
+    model.p_mean_variance(xb, {}, None, torch.full((300,), 5, device=dev, dtype=torch.long))
+    eng.set_option("mega", 1)
 if what in ("all", "guide"):
     xg = x.clamp(-1, 1) * 0.7
     guide(xg)
