@@ -336,3 +336,33 @@ def test_ingested_checkpoint_runs_the_guided_loop_on_the_gpu(tmp_path):
     a = model.run_inference(None, hard, n_samples=B, horizon=H, return_chain=False, noise=noise, **kw)
     b = direct.run_inference(None, hard, n_samples=B, horizon=H, return_chain=False, noise=noise, **kw)
     assert torch.isfinite(a).all() and torch.equal(a, b)
+
+
+@pytest.mark.parametrize("n_interp", [64, 100, 200, 512])
+def test_guide_gradient_for_other_interpolation_densities(n_interp):
+    """`num_interpolated_points_for_collision` other than the default 128 (guides.py:160-167): equal to the horizon (ratio 1, one
+    tap per support row), a non-integer ratio, more rows than one pass of the row kernel holds (200 > 128), and a density whose
+    interpolation adjoint has more than 8 taps per support row (512 / 64: the kernel's on-the-fly fallback instead of its tap
+    table). Guide gradient and five gradient steps against the oracle on the config-2 problem."""
+    import mpd_public_b200 as M
+    name = "cfg2_dense2d"
+    model_id, batch, sweep = CONFIGS[name]
+    wc, ws = sweep[0]
+    guide, ds, prob, spec0 = build(name, wc, ws)
+    texels = [f.texels.cpu() for f in ds.task.get_collision_fields() if hasattr(f, "texels")]
+    spec = O.make_guide_spec(prob, wc, ws, texels_list=texels, n_interp=n_interp)
+    old = guide.num_interpolated_points_for_collision
+    try:
+        guide.num_interpolated_points_for_collision = n_interp  # re-read on every call, as the reference does
+        x = near_line_input(prob, 32, seed=90 + n_interp, out_of_range=True)
+        ref = O.guide_manager_grad(spec, x)
+        got = guide(x.cuda())
+        assert float(ref.abs().max()) > 0
+        assert rel(got, ref) < TOL_KERNEL, (n_interp, rel(got, ref))
+        hard = O.hard_conditions(prob)
+        ohc = {k: v[None].repeat(32, 1) for k, v in hard.items()}
+        ref5 = O.OracleDiffusion.guide_gradient_steps(None, x.clone(), ohc, lambda z: O.guide_manager_grad(spec, z), 5)
+        got5 = M.guide_gradient_steps(x.cuda(), hard_conds={k: v.cuda() for k, v in ohc.items()}, guide=guide, n_guide_steps=5)
+        assert rel(got5, ref5) < TOL_KERNEL, (n_interp, rel(got5, ref5))
+    finally:
+        guide.num_interpolated_points_for_collision = old
