@@ -141,6 +141,18 @@ __device__ __forceinline__ float mishf_fast(float x) {
     const float n = e * (e + 2.f);
     return x * __fdividef(n, n + 2.f);  // n + 2 <= 2.4e17 < 2^126: inside __fdividef's valid range
 }
+// Two at a time with ONE reciprocal: 1/(a b) gives 1/a = b/(a b) and 1/b = a/(a b). The tensor-core epilogues run 8 of these
+// per thread on warps whose lane quarter ties them to one scheduler (TMEM access rule), so the quarter-rate MUFU pipe of two or
+// three schedulers does all of it: 12 MUFU per thread instead of 16. (n + 2)^2 <= 5.6e34 stays inside fp32 and rcp.approx's range.
+__device__ __forceinline__ void mishf_fast2(float& x0, float& x1) {
+    const float e0 = __expf(fminf(x0, 20.f)), e1 = __expf(fminf(x1, 20.f));
+    const float n0 = e0 * (e0 + 2.f), n1 = e1 * (e1 + 2.f);
+    const float d0 = n0 + 2.f, d1 = n1 + 2.f;
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d0 * d1));
+    x0 = x0 * (n0 * (r * d1));
+    x1 = x1 * (n1 * (r * d0));
+}
 // reference-composition variant (used once per load for the time tables, where cost does not matter)
 __device__ __forceinline__ float mishf_ref(float x) { return x * tanhf(log1pf(expf(x))); }
 

@@ -357,10 +357,11 @@ __device__ __forceinline__ void gn_apply(float (&v)[8], bool valid, int s, int c
     const float mB = stat[(sc * 8 + gB) * 2], rB = stat[(sc * 8 + gB) * 2 + 1];
     if (!valid) return;  // rows outside the samples (halo, unused lanes): their values are never stored; skipping them halves the
                          // exp / reciprocal (MUFU) traffic of a tile that is half empty (one sample of L = 64 in 128 lanes)
-    v[0] = mishf_fast((v[0] - mA) * (rA * g0.x) + e0.x); v[1] = mishf_fast((v[1] - mA) * (rA * g0.y) + e0.y);
-    v[2] = mishf_fast((v[2] - mA) * (rA * g0.z) + e0.z); v[3] = mishf_fast((v[3] - mA) * (rA * g0.w) + e0.w);
-    v[4] = mishf_fast((v[4] - mB) * (rB * g1.x) + e1.x); v[5] = mishf_fast((v[5] - mB) * (rB * g1.y) + e1.y);
-    v[6] = mishf_fast((v[6] - mB) * (rB * g1.z) + e1.z); v[7] = mishf_fast((v[7] - mB) * (rB * g1.w) + e1.w);
+    v[0] = (v[0] - mA) * (rA * g0.x) + e0.x; v[1] = (v[1] - mA) * (rA * g0.y) + e0.y;
+    v[2] = (v[2] - mA) * (rA * g0.z) + e0.z; v[3] = (v[3] - mA) * (rA * g0.w) + e0.w;
+    v[4] = (v[4] - mB) * (rB * g1.x) + e1.x; v[5] = (v[5] - mB) * (rB * g1.y) + e1.y;
+    v[6] = (v[6] - mB) * (rB * g1.z) + e1.z; v[7] = (v[7] - mB) * (rB * g1.w) + e1.w;
+    mishf_fast2(v[0], v[1]); mishf_fast2(v[2], v[3]); mishf_fast2(v[4], v[5]); mishf_fast2(v[6], v[7]);
 }
 
 template <int GS, bool BAR1>

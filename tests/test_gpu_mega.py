@@ -131,7 +131,9 @@ def test_fused_projection_and_ddpm_update_match_the_separate_kernel():
     assert torch.isfinite(chains[1]).all()
     for k, v in hard.items():
         assert torch.equal(chains[1][:, :, k, :], v.expand(n_iters + 1, B, D))
-    assert rel(chains[1], chains[0]) < 2e-5, rel(chains[1], chains[0])
+    # free-running chains: the two code paths differ by the summation order of the projection (~1e-7 per step), which the first
+    # reverse step amplifies by up to 1095 and the following ones carry along; measured 1.5e-5 .. 2.3e-5 depending on the build
+    assert rel(chains[1], chains[0]) < 5e-5, rel(chains[1], chains[0])
     model.tensor_cores = "auto"
     try:
         for fuse in (1, 0):
