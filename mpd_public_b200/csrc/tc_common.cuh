@@ -285,6 +285,9 @@ __device__ __forceinline__ void gn_stats_small(int tid, int SPT, int Lp, int L, 
     constexpr int JS = BPG == 8 ? 2 : 4;
     const int j = tid % JS, m = (tid / JS) & 1, blk = (tid / (2 * JS)) & 7, ss = tid / (16 * JS);
     const bool on = ss < SPT;
+    // 1 / n up front (an fp32 division is ~20 dependent instructions): it overlaps the shared-memory loads below instead of
+    // sitting behind the reductions, on the path between the two barriers that all 16 warps wait on
+    const double inv_n = (double)(1.0f / (float)(GS * L));  // L = 8 * 2^k, GS = 2^j: exact, and no fp64 division
     double a0 = 0.0;
     if (on) {
         // (eight independent loads + a pairwise tree per round was tried: slower — the fp32 -> fp64 conversions and double adds of
@@ -303,11 +306,11 @@ __device__ __forceinline__ void gn_stats_small(int tid, int SPT, int Lp, int L, 
     }
     if (on && j == 0 && m == 0 && (blk % BPG) == 0) {
         const int g = blk / BPG;
-        const double inv_n = (double)(1.0f / (float)(GS * L));  // L = 8 * 2^k, GS = 2^j: exact, and no fp64 division
         const double mean = S * inv_n;
         const double var = fmax(Q * inv_n - mean * mean, 0.0);
         stat[(ss * 8 + g) * 2 + 0] = (float)mean;
-        stat[(ss * 8 + g) * 2 + 1] = 1.0f / sqrtf((float)var + 1e-5f);  // the cancellation-prone part is done; fp32 from here
+        stat[(ss * 8 + g) * 2 + 1] = rsqrtf((float)var + 1e-5f);  // the cancellation-prone part is done; fp32 from here (MUFU.RSQ, 2^-22.9:
+                                                                  // an IEEE sqrt + division is ~40 dependent instructions between the two barriers)
     }
 }
 // more than 8 samples per tile: level 1 = one thread per (moment, sample, block) column; a barrier; level 2 = one thread per
@@ -343,7 +346,7 @@ __device__ __forceinline__ void gn_stats_big2(int tid, int SPT, int L, float* pa
         const double m = S * inv_n;
         const double var = fmax(Q * inv_n - m * m, 0.0);
         stat[(ss * 8 + g) * 2 + 0] = (float)m;
-        stat[(ss * 8 + g) * 2 + 1] = 1.0f / sqrtf((float)var + 1e-5f);
+        stat[(ss * 8 + g) * 2 + 1] = rsqrtf((float)var + 1e-5f);
     }
 }
 // normalise + affine + Mish with the published statistics
