@@ -78,12 +78,13 @@ __device__ __forceinline__ void cp_async_wait() {
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
-extern bool g_use_pdl;  // MPDB_PDL=1 enables programmatic dependent launch (off by default, see engine.cu)
+extern bool g_use_pdl;     // MPDB_PDL=1: programmatic dependent launch for EVERY kernel (off by default, see engine.cu)
+extern bool g_pdl_layers;  // MPDB_PDL_LAYERS (default 1): for the persistent per-layer tensor-core kernels only (engine.cu)
 
-// Launch with the PDL attribute (falls back to a plain launch when disabled).
+// Launch with (pdl = true) or without the PDL attribute.
 template <typename... KArgs, typename... Args>
-inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
-                                 Args... args) {
+inline cudaError_t launch_kernel_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                     bool pdl, Args... args) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid;
     cfg.blockDim = block;
@@ -93,8 +94,14 @@ inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at;
-    cfg.numAttrs = g_use_pdl ? 1 : 0;
+    cfg.numAttrs = pdl ? 1 : 0;
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+// Launch with the PDL attribute when it is enabled globally (falls back to a plain launch otherwise).
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                 Args... args) {
+    return launch_kernel_pdl(kernel, grid, block, smem, stream, g_use_pdl, args...);
 }
 
 // Same, with a thread-block-cluster shape (cluster_y CTAs along grid y).

@@ -23,6 +23,12 @@ std::atomic<long long> g_launch_count{0};
 // stream-ordered launches (0.45 -> 0.37 ms per UNet forward) yet is ~2 % slower than plain kernel nodes under CUDA-graph
 // replay, which is the production path (profiles/README.md). MPDB_PDL=1 enables it.
 bool g_use_pdl = []() { const char* v = getenv("MPDB_PDL"); return v && v[0] == '1'; }();
+// Programmatic dependent launch between the persistent per-layer tensor-core kernels only (one CTA per SM, one wave): the next
+// layer's CTA starts on an SM as soon as this layer's CTA there has exited — no grid-wide completion + launch latency — and
+// runs its prologue (barriers, TMEM, first weight copies) up to griddepcontrol.wait. Kernels with more CTAs than fit at once
+// (the guide at 512 trajectories) must NOT trigger their dependents early: the waiting CTAs take the slots their own later
+// waves need (measured: PDL everywhere leaves cfg 5 unchanged and costs cfg 4 1 %; per-layer only: see profiles/README.md).
+bool g_pdl_layers = []() { const char* v = getenv("MPDB_PDL_LAYERS"); return !(v && v[0] == '0'); }();
 void set_error(const std::string& msg) { g_error = msg; }
 
 // TMA tensor map of one activation in the TC layout (plane[tile][C/8][132][8] fp16, hi plane followed by the lo plane at

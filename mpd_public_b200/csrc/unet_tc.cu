@@ -768,7 +768,7 @@ int launch_conv5_tc(const TcConvArgs& a_in, cudaStream_t stream) {
     const size_t smem = (size_t)TC_PS_RING_BYTES + (2 * TC_PS_MAX_STAGES + 4) * 8 + 16 + 2 * TC_GN_SCRATCH_BYTES + 4 * 160 * sizeof(float) + 64;
     static_assert((size_t)TC_PS_RING_BYTES + (2 * TC_PS_MAX_STAGES + 4) * 8 + 16 + 2 * TC_GN_SCRATCH_BYTES + 4 * 160 * sizeof(float) + 64 <= 227 * 1024, "conv5_tc_kernel: shared memory");
     TcConvArgs a = a_in;
-    a.pdl = g_use_pdl ? 1 : 0;
+    a.pdl = (g_use_pdl || g_pdl_layers) ? 1 : 0;
     {   // ring geometry: a stage = the largest activation box + the largest weight group of this layer
         const int wmul = a.prec == 1 ? 1 : 2, ntaps = a.mode == TCM_DOWN ? 3 : a.mode == TCM_UP ? 4 : 5;
         int max_nch = 1;
@@ -802,7 +802,7 @@ int launch_conv5_tc(const TcConvArgs& a_in, cudaStream_t stream) {
             MPDB_CHECK_CUDA(cudaFuncSetAttribute(conv5_tc_kernel<M, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                                  227 * 1024));                                                     \
         }                                                                                                          \
-        MPDB_CHECK_CUDA(launch_kernel(conv5_tc_kernel<M, G>, grid, dim3(TCL_THREADS), smem, stream, a));            \
+        MPDB_CHECK_CUDA(launch_kernel_pdl(conv5_tc_kernel<M, G>, grid, dim3(TCL_THREADS), smem, stream, a.pdl != 0, a)); \
     }
     if (a.mode == TCM_DOWN) MPDB_TC_LAUNCH(TCM_DOWN, 4)
     else if (a.mode == TCM_UP) MPDB_TC_LAUNCH(TCM_UP, 4)
