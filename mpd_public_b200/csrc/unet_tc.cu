@@ -49,12 +49,16 @@ constexpr int TCL_TMEM_COLS = 512;  // two stages: the MMAs of work item k+1 run
 // stage; the epilogue releases a stage as soon as its values are in registers), so per item the CTA pays
 // max(MMA + operand streaming, epilogue) instead of setup + first-copy latency + MMA + epilogue + teardown: at 512
 // trajectories per GPU a layer is 500-1000 items on 148 SMs and one-CTA-per-item launches spent ~10 us per item on ~2 us of work.
-// Operand ring: TC_PS_STAGES stages of 74,752 B = [activations | weights]. A stage holds a GROUP of K-chunks of one source
+// Operand ring: 2-8 stages of [activations | weights], the geometry chosen per layer by launch_conv5_tc (TC_PS_RING_BYTES cut into
+// stages of the layer's largest activation box + weight group). A stage holds a GROUP of K-chunks of one source
 // tensor — 2 with the 22-bit split (both planes), 4 in precision 1 (hi plane only; fewer when the tensor is narrower) —
 // brought by TWO asynchronous copies: one cp.async.bulk.tensor (TMA tensor map, 5-D box {8, 132 rows, 4 * chunks k-groups, 1
 // tile, planes}: lands as [plane][k-group][row][8], the tcgen05 operand layout) and one cp.async.bulk for the group's weights
 // (contiguous in the packed layout). A bulk copy costs ~800 cycles of the copy engine whatever its size
 // (tools/probes/bulk_probe.cu), so the wide layers were bound by the NUMBER of copies: 3 per K-chunk before, 2 per group now.
+// The epilogue is software-pipelined over the items (see the epilogue branch), and consecutive layer launches are chained by
+// programmatic dependent launch (TcConvArgs::pdl): the next layer's CTA starts on an SM when this layer's CTA there has exited,
+// prefetches weights and blocks in griddepcontrol.wait before it touches activations or writes anything.
 __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, int c2, int c3, int c4, uint32_t bar) {
     asm volatile(
         "{\n\t.reg .pred q;\n\t"
