@@ -80,6 +80,7 @@ __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepc
 
 extern bool g_use_pdl;     // MPDB_PDL=1: programmatic dependent launch for EVERY kernel (off by default, see engine.cu)
 extern bool g_pdl_layers;  // MPDB_PDL_LAYERS (default 1): for the persistent per-layer tensor-core kernels only (engine.cu)
+extern bool g_pdl_loop;    // MPDB_PDL_LOOP (default 1): cluster-kernel forwards and the single-wave guide launches between them
 
 // Launch with (pdl = true) or without the PDL attribute.
 template <typename... KArgs, typename... Args>

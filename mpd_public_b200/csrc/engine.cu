@@ -29,6 +29,10 @@ bool g_use_pdl = []() { const char* v = getenv("MPDB_PDL"); return v && v[0] == 
 // (the guide at 512 trajectories) must NOT trigger their dependents early: the waiting CTAs take the slots their own later
 // waves need (measured: PDL everywhere leaves cfg 5 unchanged and costs cfg 4 1 %; per-layer only: see profiles/README.md).
 bool g_pdl_layers = []() { const char* v = getenv("MPDB_PDL_LAYERS"); return !(v && v[0] == '0'); }();
+// The small-batch loop: cluster-kernel forwards (104 CTAs) and fused guide launches (one CTA per trajectory, one wave) trigger
+// their dependents late — in the last layer's epilogue / the last evaluation's update pass — so the next kernel starts on the
+// SMs that are idle or free up, runs its prologue and blocks in griddepcontrol.wait.
+bool g_pdl_loop = []() { const char* v = getenv("MPDB_PDL_LOOP"); return !(v && v[0] == '0'); }();
 void set_error(const std::string& msg) { g_error = msg; }
 
 // TMA tensor map of one activation in the TC layout (plane[tile][C/8][132][8] fp16, hi plane followed by the lo plane at
@@ -1270,6 +1274,7 @@ static int enqueue_loop(mpdb_engine* e, mpdb_guide* g, const mpdb_loop_params* p
             a.out2_bstride = chain_batch_stride;
             a.B = B;
             a.H = H;
+            a.pdl = (g_pdl_loop && fused) ? 1 : 0;  // next to cluster-kernel forwards the launch is a single wave
             if (guide_launch_step(g, a, st)) return 1;
         } else if (guided) {
             for (int k = 0; k < p->n_guide_steps; ++k) {

@@ -268,12 +268,10 @@ __global__ void __launch_bounds__(GUIDE_THREADS, OCC) guide_step_kernel(const __
 
     long long* dbg = (a.dbg != nullptr && blockIdx.x == 0 && threadIdx.x == 0) ? a.dbg : nullptr;
     if (dbg) dbg[0] = clock64();
-    pdl_launch_dependents();
-    pdl_wait();  // x and the clip flag come from the previous kernel
     const int n_it = a.n_iters > 1 ? a.n_iters : 1;
     const bool pos_only = a.vel_io != nullptr || g.vel_fd;  // x holds positions only (GuideManagerTrajectories)
     const int Dio = pos_only ? q : D;                       // columns of x_in / x_out
-    int flag = a.flag_in ? *a.flag_in : 0;
+    int flag = 0;  // read after the dependency wait below
     const float ratio = NI > 1 ? (float)(H - 1) / (float)(NI - 1) : 0.f;  // align_corners=True
     const float inv_ratio = ratio > 0.f ? 1.f / ratio : 0.f;
     // Adjoint of the linear interpolation as a gather: support row h receives from the interpolated rows i whose lower / upper
@@ -306,6 +304,8 @@ __global__ void __launch_bounds__(GUIDE_THREADS, OCC) guide_step_kernel(const __
     }
     __syncthreads();
     const bool use_taps = s_tap_overflow == 0;
+    pdl_wait();  // x and the clip flag come from the previous kernel; everything above depends on the launch parameters only
+    flag = a.flag_in ? *a.flag_in : 0;
 
     for (int it = 0; it < n_it; ++it) {
         const bool last_it = it == n_it - 1;
@@ -514,6 +514,7 @@ __global__ void __launch_bounds__(GUIDE_THREADS, OCC) guide_step_kernel(const __
         }
         if (dbg) dbg[4] = clock64();
 
+        if (last_it && tid == 0) pdl_launch_dependents();  // a programmatic dependent may start its prologue where SMs are free
         // ---------------- (F) per support row, 8 lanes (lane k < q owns coordinate k): for every collision cost the adjoint of the
         // interpolation (gather over the row's taps), 1/sigma^2, clip-by-norm (xor-shuffle tree over the 8 lanes), endpoint zeroing,
         // weight; then the GP prior (constant velocity) 3-tap stencil, the sum in cost order, and the update ----------------
@@ -823,7 +824,8 @@ int guide_launch_step(mpdb_guide* gd, const GuideStepArgs& a_in, cudaStream_t st
         if (mpdb::first_use_on_device(configured)) {                                                                         \
             MPDB_CHECK_CUDA(cudaFuncSetAttribute(guide_step_kernel<K, O>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)); \
         }                                                                                                                    \
-        MPDB_CHECK_CUDA(launch_kernel(guide_step_kernel<K, O>, dim3(a.B), dim3(GUIDE_THREADS), smem, stream, g, a));         \
+        MPDB_CHECK_CUDA(launch_kernel_pdl(guide_step_kernel<K, O>, dim3(a.B), dim3(GUIDE_THREADS), smem, stream,             \
+                                          g_use_pdl || a.pdl != 0, g, a));                                                    \
     }
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, gd->device);

@@ -265,6 +265,7 @@ struct GuideStepArgs {
     long long* dbg;      // optional clock64 stamps of thread 0 of CTA 0 (MPDB_GUIDE_TIMELINE=1 in mpdb_profile_guide)
     unsigned int* dep_count;  // counts (trajectory, evaluation) pairs whose clamp was decided by OTHER trajectories (set by the launcher)
     int32_t* dec;        // parity instrumentation (mpdb_guide_record_decisions): [n_iters][B][n_costs][n_interp][n_spheres], else null
+    int pdl;             // launch with the programmatic-serialization attribute (the loop sets it next to cluster-kernel forwards)
 };
 int guide_launch_step(mpdb_guide* g, const GuideStepArgs& a, cudaStream_t stream);
 int guide_max_coresident(mpdb_guide* g, int H);  // CTAs of the guide kernel that can be resident at once (grid-barrier bound)

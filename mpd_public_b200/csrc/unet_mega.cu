@@ -310,6 +310,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) unet_mega_kernel(const __grid_c
         const MegaLayer& Ld = P.layers[l];
         // outputs of the previous layer have landed everywhere (also keeps idle CTAs in lock step)
         if (l > 0) mbar_wait(a_full, (uint32_t)(l - 1) & 1u);  // these warps read nothing the peers wrote: CTA-scope wait
+        if (l == P.n_layers - 1 && tid == 0) pdl_launch_dependents();  // last layer: a programmatic dependent may start where SMs are free
         long long* dbg = (P.dbg != nullptr && cluster == P.dbg_cluster && tid == 0) ? P.dbg + ((size_t)l * MEGA_CLUSTER + rank) * MEGA_DBG : nullptr;
         if (dbg) dbg[0] = clock64();  // inputs landed
         const bool active = rank < Ld.MT * Ld.NC;
@@ -604,7 +605,7 @@ int launch_unet_mega(const MegaProgram& P, cudaStream_t stream) {
     at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at;
-    cfg.numAttrs = g_use_pdl ? 2 : 1;
+    cfg.numAttrs = (g_use_pdl || g_pdl_loop) ? 2 : 1;
     MPDB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, unet_mega_kernel, P));
     MPDB_LAUNCH_CHECK();
     return 0;
