@@ -11,6 +11,11 @@
  * Every function returns 0 on success or a non-zero status; `mpdb_last_error()` returns the message
  * of the last failure on the calling thread (the Python binding raises RuntimeError with it —
  * the reference signals errors with Python exceptions, diffusion_model_base.py:72,275).
+ *
+ * Concurrency: an engine or guide handle owns device scratch (activation workspace, clip flags, captured graphs) and serves ONE
+ * stream at a time, like the reference's single Python thread on the current stream. Calls on different handles
+ * may run concurrently; calls on the same handle must be ordered by the caller (same stream, or events between streams).
+ * Every entry point saves and restores the calling thread's current device.
  */
 #ifndef MPDB200_H
 #define MPDB200_H
